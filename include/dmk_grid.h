@@ -1,0 +1,198 @@
+/* dmk_grid.h -- C ABI of libdamask_grid_b200.so: the B200-native hot path of the DAMASK grid solver.
+ *
+ * Drop-in boundary for the C++ driver of dmentock/solver_cpp.  Two groups of entry points:
+ *
+ *  (1) the Fortran-named symbols the reference's `Spectral` class binds today
+ *      (/root/reference/src/grid/spectral.h:16-23, damask_grid.h:15-18), with identical signatures and meaning;
+ *      they act on the context made current with dmk_bind_global() and exchange data through HOST mirrors,
+ *      exactly like the Fortran module arrays they replace;
+ *
+ *  (2) dmk_* functions: the same operations with explicit context and DEVICE-resident fields, plus the spectral
+ *      half (`spectral_utilities` / `mechanical_spectral_basic` surface: FFT, Gamma convolution, divergence RMS,
+ *      masked compliance, forward/rate, residual, convergence test, NGMRES-driven solve).
+ *
+ * Conventions: all field pointers use the reference's Fortran memory order -- F(3,3,nx,ny,nz_local), first index
+ * fastest, i.e. one 72-byte record per cell with component c = i + 3*j.  3x3 / 3x3x3x3 host arguments are also
+ * Fortran order (T(i,j) at [i + 3*j], C(i,j,k,l) at [i + 3*j + 9*k + 27*l]).  Every function returns 0 on
+ * success; dmk_last_error() describes the last failure.  Nothing here falls back to a CPU implementation.
+ */
+#ifndef DMK_GRID_H
+#define DMK_GRID_H
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct dmk_ctx dmk_ctx;
+
+/* ---- limits of the device constitutive kernels */
+#define DMK_MAX_SL 24
+#define DMK_MAX_TW 12
+#define DMK_MAX_STATE (3 * DMK_MAX_SL + DMK_MAX_TW)
+#define DMK_MAX_PHASES 8
+
+enum { DMK_LAW_NONE = 0, DMK_LAW_ISOTROPIC = 1, DMK_LAW_PHENOPOWERLAW = 2, DMK_LAW_DISLOTWIN = 3 };
+enum { DMK_DERIVATIVE_CONTINUOUS = 0, DMK_DERIVATIVE_CENTRAL_DIFF = 1, DMK_DERIVATIVE_FWBW_DIFF = 2 };
+enum { DMK_DIVCORR_NONE = 0, DMK_DIVCORR_SIZE = 1, DMK_DIVCORR_SIZE_GRID = 2 };
+
+/* grid + decomposition (reference: DiscretizationGrid, /root/reference/src/grid/discretization_grid.h:24-60;
+ * Config::NumFFT, config.h:60-72) */
+typedef struct {
+  int cells[3];               /* nx, ny, nz (global)                                   */
+  double size[3];             /* geom_size / m                                         */
+  int world_size, rank;       /* z-slab decomposition: nz % world_size == 0, ny % world_size == 0 */
+  int derivative;             /* DMK_DERIVATIVE_*                                      */
+  int divergence_correction;  /* DMK_DIVCORR_*                                         */
+  int kt_y, kt_z;             /* kx records per tile in the y / z pass (0 = automatic) */
+} dmk_grid_desc;
+
+/* numerics of the per-point integrator (phase_mechanical.f90:277-294) and of the grid solver (config.h:50-58) */
+typedef struct {
+  double r_cutback_min, r_cutback, r_increase, eps_rel_state;
+  int N_iter_state_max, N_iter_Lp_max;
+  double r_linesearch_Lp, eps_rel_Lp, eps_abs_Lp;
+  int f_update_jacobi_Lp;
+  int itmin, itmax, update_gamma;
+  double eps_abs_div, eps_rel_div, eps_abs_P, eps_rel_P;
+} dmk_numerics;
+
+/* one phase: Hooke elasticity + plastic law, expanded per system (reference tParameters of each law).
+ * Matrices are row-major: P_sl[a][3*i+j]; h_x_y[reacting][acting]. */
+typedef struct {
+  int law, n_sl, n_tw, n_state;
+  double C66[36];                          /* lattice-symmetrised Voigt stiffness at T */
+  double atol[DMK_MAX_STATE];
+  double state_init[DMK_MAX_STATE];
+  double P_sl[DMK_MAX_SL][9], P_nS_pos[DMK_MAX_SL][9], P_nS_neg[DMK_MAX_SL][9], P_tw[DMK_MAX_TW][9];
+  double h_sl_sl[DMK_MAX_SL][DMK_MAX_SL], h_sl_tw[DMK_MAX_SL][DMK_MAX_TW];
+  double h_tw_sl[DMK_MAX_TW][DMK_MAX_SL], h_tw_tw[DMK_MAX_TW][DMK_MAX_TW];
+  /* isotropic (phase_mechanical_plastic_isotropic.f90:11-40); dilatation must be 0 on the device path */
+  double iso_xi_inf, iso_dot_gamma_0, iso_n, iso_h_0, iso_h, iso_M, iso_h_ln, iso_c_1, iso_c_2, iso_c_3, iso_c_4, iso_a;
+  int iso_dilatation;
+  /* phenopowerlaw (phase_mechanical_plastic_phenopowerlaw.f90:11-58) */
+  double dot_gamma_0_sl[DMK_MAX_SL], n_sl_exp[DMK_MAX_SL], a_sl[DMK_MAX_SL], h_0_sl_sl[DMK_MAX_SL], c_1[DMK_MAX_SL],
+      c_2[DMK_MAX_SL], xi_inf_sl[DMK_MAX_SL], f_sat_sl_tw[DMK_MAX_SL];
+  double dot_gamma_0_tw[DMK_MAX_TW], n_tw_exp[DMK_MAX_TW], c_3[DMK_MAX_TW], c_4[DMK_MAX_TW], h_0_tw_sl[DMK_MAX_TW],
+      h_0_tw_tw[DMK_MAX_TW], gamma_char_tw[DMK_MAX_TW];
+  /* dislotwin (phase_mechanical_plastic_dislotwin.f90:12-92), twinning only (no transformation systems) */
+  double dt_mu, dt_nu, dt_kB_T, dt_Gamma_sf, dt_Q_cl, dt_omega, dt_D, dt_p_sb, dt_q_sb, dt_i_tw, dt_L_tw, dt_x_c,
+      dt_V_cs, dt_tau_sb, dt_gamma_0_sb, dt_E_sb;
+  int dt_extended, dt_omit_dipoles;
+  double dt_b_sl[DMK_MAX_SL], dt_Q_sl[DMK_MAX_SL], dt_v_0[DMK_MAX_SL], dt_i_sl[DMK_MAX_SL], dt_p[DMK_MAX_SL],
+      dt_q[DMK_MAX_SL], dt_tau_0[DMK_MAX_SL], dt_B[DMK_MAX_SL], dt_d_caron[DMK_MAX_SL];
+  double dt_n0_sl[DMK_MAX_SL][3], dt_forest[DMK_MAX_SL][DMK_MAX_SL];
+  double dt_b_tw[DMK_MAX_TW], dt_t_tw[DMK_MAX_TW], dt_r[DMK_MAX_TW];
+  int dt_pair[DMK_MAX_TW][2];              /* 0-based slip pair nucleating twin i (crystal.f90:82-95) */
+  double dt_C66_tw[DMK_MAX_TW][36];
+} dmk_phase;
+
+/* collective callbacks for world_size > 1 (all stream-ordered on the context's stream; device pointers).
+ * The Python host implements them with torch.distributed / NCCL, a C++ host with ncclSend/ncclRecv. */
+typedef struct {
+  void* user;
+  int (*alltoall)(void* user, const void* d_send, void* d_recv, size_t bytes_per_peer);
+  int (*allreduce_sum)(void* user, double* d_buf, int n);
+  int (*allreduce_max)(void* user, double* d_buf, int n);
+} dmk_comm;
+
+/* solution status, mirrors Config::SolutionState (config.h:35-40) */
+typedef struct {
+  int required_iterations, converged, stag_converged, terminally_ill;
+} dmk_solution_state;
+
+/* ------------------------------------------------------------------ lifecycle */
+const char* dmk_last_error(void);
+int dmk_create(dmk_ctx** ctx, const dmk_grid_desc* grid);
+void dmk_destroy(dmk_ctx* ctx);
+int dmk_set_stream(dmk_ctx* ctx, void* cuda_stream);
+int dmk_set_comm(dmk_ctx* ctx, const dmk_comm* comm);
+int dmk_synchronize(dmk_ctx* ctx);
+int dmk_local_cells(const dmk_ctx* ctx, int* nz_local, int* z_offset, int* ny_local, int* y_offset);
+int dmk_kernel_launches(const dmk_ctx* ctx, long long* n);        /* kernels launched so far by this context */
+
+/* ------------------------------------------------------------------ crystal tables (host, pure; crystal.f90)
+ * fill the geometry-derived members of a dmk_phase for lattice "cF" or "cI" */
+int dmk_crystal_schmid_slip(const char* lattice, const int* N_sl, int n_fam, double* P /* [sum][9] */);
+int dmk_crystal_schmid_twin(const char* lattice, const int* N_tw, int n_fam, double* P);
+int dmk_crystal_slip_normal(const char* lattice, const int* N_sl, int n_fam, double* n /* [sum][3] */);
+int dmk_crystal_interaction(const char* kind /* "sl-sl","tw-tw","sl-tw","tw-sl" */, const char* lattice,
+                            const int* N_react, int nf_react, const int* N_act, int nf_act, const double* values,
+                            int n_values, double* h /* [sum_react][sum_act] */);
+int dmk_crystal_forest_projection(const char* lattice, const int* N_sl, int n_fam, const double* f_edge, double* proj);
+int dmk_crystal_C66_twin(const char* lattice, const int* N_tw, int n_fam, const double* C66, double* C66_tw);
+int dmk_crystal_twin_nucleation_pairs(const int* N_tw, int n_fam, int* pairs /* [sum][2], 0-based */);
+void dmk_qu2om(const double q[4], double om[9] /* row-major */);
+
+/* ------------------------------------------------------------------ constitutive half (device-resident)
+ * replaces f_materialpoint_initDamask + f_discretization_init for the hot path:
+ * phase_of_cell / O_of_cell describe the LOCAL z-slab, cell order x fastest (VTI order). */
+int dmk_material_init(dmk_ctx* ctx, const dmk_phase* phases, int n_phases, const int* phase_of_cell,
+                      const double* O_of_cell /* [n_local][9] row-major rotation matrices (Fp0) */,
+                      const dmk_numerics* num);
+/* f_homogenization_mechanical_response + _response2 (P only): integrate every local cell from its *0 state to the
+ * deformation gradient field d_F; writes d_P, the ill flag, and the slab's sum of P. */
+int dmk_constitutive_response(dmk_ctx* ctx, const double* d_F, double* d_P, double dt);
+/* phase_mechanical_dPdF reduced on the fly (spectral.cpp:189-218): C_volAvg, C_minMaxAvg from the state left by the
+ * last dmk_constitutive_response; host outputs, Fortran order; d_dPdF (81 doubles/cell) is optional. */
+int dmk_tangent_response(dmk_ctx* ctx, double dt, double* C_volAvg, double* C_minMaxAvg, double* d_dPdF,
+                         long long minmax_cells[2]);
+int dmk_materialpoint_forward(dmk_ctx* ctx);                       /* f_materialpoint_forward */
+int dmk_get_state(dmk_ctx* ctx, const char* name, double* host_out, size_t n_doubles); /* "Fp","S","state",... */
+int dmk_get_counters(dmk_ctx* ctx, long long counters[6]);         /* Lp iters, stress calls, state iters, substeps, cutbacks, ill */
+int dmk_terminally_ill(dmk_ctx* ctx, int* flag, int reset);
+
+/* ------------------------------------------------------------------ spectral half (device-resident fields)
+ * FFT<5>::forward / backward (fft.h:37-60): half spectrum layout [kz][ky_local][kx][9] complex, unnormalised */
+int dmk_fft_forward(dmk_ctx* ctx, const double* d_real, double* d_fourier);
+int dmk_fft_backward(dmk_ctx* ctx, const double* d_fourier, double* d_real, double wgt);
+size_t dmk_fourier_doubles(const dmk_ctx* ctx);                    /* size of a half-spectrum buffer in doubles */
+int dmk_update_gamma(dmk_ctx* ctx, const double* C /* host, 81 */);/* MechBase::update_gamma (mech_base.cpp:156) */
+/* calculate_divergence_rms + gamma_convolution fused (mech_base.cpp:302-477): d_field in: stress, out: Gamma*field;
+ * field_aim host 3x3 (already rotated to lab); err_div returned on the host */
+int dmk_divergence_and_gamma(dmk_ctx* ctx, double* d_field, const double* field_aim, double* err_div);
+int dmk_masked_compliance(const double* C /*81*/, const double* R /*9 row-major*/, const int* stress_mask /*9, 1='x'*/,
+                          double* S /*81*/);                        /* MechBase::calculate_masked_compliance */
+int dmk_forward_field(dmk_ctx* ctx, double dt, const double* d_field_last, const double* d_rate, const double* aim,
+                      double* d_out);                               /* MechBase::forward_field  (aim may be NULL) */
+int dmk_calculate_rate(dmk_ctx* ctx, int heterogeneous, const double* d_field0, const double* d_field, double dt,
+                       const double* av_rate, double* d_rate);      /* MechBase::calculate_rate */
+
+/* ------------------------------------------------------------------ mechanical_spectral_basic surface
+ * MechSolverBasic::{init, forward, calculate_solution, form_residual, converged} (mech_solver_basic.cpp) with the
+ * solution vector, its history (NGMRES, m = 30) and all work fields resident in HBM. */
+int dmk_mech_init(dmk_ctx* ctx, const long long* gamma_pair_cells /* NULL or 2 global cell indices */);
+int dmk_mech_forward(dmk_ctx* ctx, int cut_back, int guess, double dt, double dt_old, double t_remaining,
+                     const char* deformation_type, const double* deformation_values, const int* deformation_mask,
+                     const char* stress_type, const double* stress_values, const int* stress_mask,
+                     const double* R /* 9 row-major */);
+int dmk_mech_calculate_solution(dmk_ctx* ctx, dmk_solution_state* out);
+int dmk_mech_form_residual(dmk_ctx* ctx, const double* d_F, double* d_r);  /* one evaluation, device pointers */
+int dmk_mech_form_residual_host(dmk_ctx* ctx, const double* F, double* r); /* same with host buffers (H2D + D2H) */
+int dmk_mech_get(dmk_ctx* ctx, const char* what, double* out, size_t n);   /* "P_av","F_aim","err_div","err_BC","C_volAvg",... */
+int dmk_mech_get_field(dmk_ctx* ctx, const char* what, double* host_out);  /* "F","P","F_lastInc": local slab, 9*n doubles */
+int dmk_mech_set_field(dmk_ctx* ctx, const char* what, const double* host_in);
+int dmk_mech_eval_log(dmk_ctx* ctx, double* out, size_t max_rows, size_t* n_rows); /* per evaluation: 9 P_av, err_div, err_BC, total_iter */
+
+/* ------------------------------------------------------------------ (1) Fortran-named drop-in symbols */
+int dmk_bind_global(dmk_ctx* ctx);
+void f_homogenization_fetch_tensor_pointers(double** homogenization_F0, double** homogenization_F,
+                                            double** homogenization_P, double** homogenization_dPdF,
+                                            void** terminally_ill);
+void f_homogenization_mechanical_response(double* delta_t, int* cell_start, int* cell_end);
+void f_homogenization_thermal_response(double* delta_t, int* cell_start, int* cell_end);
+void f_homogenization_mechanical_response2(double* delta_t, int* FEsolving_execIP, int* FEsolving_execElem);
+void f_materialpoint_forward(void);
+void f_materialpoint_result(int* inc, double* t);
+/* helpers of utilities_fortran.h:8-15 */
+void f_math_invert(double* InvA, int* err, double* A, int* n);
+void f_math_3333to99(double* m3333, double* m99);
+void f_math_99to3333(double* m99, double* m3333);
+void f_math_mul3333xx33(double* A, double* B, double* res);
+void f_rotate_tensor2(double* qu, double* T, double* rotated, int* active);
+void f_rotate_tensor4(double* qu, double* T, double* rotated, int* active);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DMK_GRID_H */

@@ -75,7 +75,7 @@ def freq_derivative(kind, cells, size, k):
         out = np.empty(k.shape, complex)
         for i in range(3):
             j, l = (i + 1) % 3, (i + 2) % 3
-            own = (np.cos(ang[..., i]) - (1.0 if i == 0 else -1.0)) + 1j * np.sin(ang[..., i])
+            own = (np.cos(ang[..., i]) - 1.0) + 1j * np.sin(ang[..., i])      # upstream; the rewrite has +1 for i>0 (D11)
             a = (np.cos(ang[..., j]) + 1.0) + 1j * np.sin(ang[..., j])
             b = (np.cos(ang[..., l]) + 1.0) + 1j * np.sin(ang[..., l])
             out[..., i] = own * a * b / (4.0 * size[i] / cells[i])

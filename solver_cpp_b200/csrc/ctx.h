@@ -1,0 +1,67 @@
+// Internal definition of the solver context shared by the translation units of libdamask_grid_b200.so.
+#pragma once
+#include <vector>
+#include <string>
+#include "../../include/dmk_grid.h"
+#include "fft_host.h"
+
+struct DmkPointArrays;   // constitutive.cuh
+struct DmkMech;          // mech_solver.cu
+
+struct dmk_ctx {
+  dmk_grid_desc g;
+  int nx, ny, nz, nxr;
+  int P, rank;                    // world size / rank
+  int nz_loc, z_off, ny_loc, y_off;
+  long long n_local;              // cells in the local z-slab
+  long long n_global;
+  double wgt;                     // 1 / n_global
+  cudaStream_t stream; bool own_stream;
+  dmk_comm comm; bool has_comm;
+  long long launches;
+
+  // ---- spectral
+  DmkFftPlan plx, ply, plz;
+  double2* xi_own[3]; double2* xi_oth[3]; unsigned char* nyq[3];
+  bool xi_imag;
+  double scaled_size[3], rescale[3];
+  int kt_y, kt_z;
+  double2* bufA;                  // [nz_loc][ny][nxr][9] after x/y passes; [nz][ny_loc][nxr][9] in the z pass
+  double2* bufB;                  // exchange buffer [peer][nz_loc][ny_loc][nxr][9] (world_size > 1 only)
+  size_t hat_records;             // records in bufA
+  double* d_Cref;                 // 81, row-major C_ref(l,n,m,o)
+  double* d_dc;                   // 9, record order
+  double* d_div;                  // 1
+  double* d_scratch;              // small device scratch (>= 4096 doubles)
+  double* h_pinned;               // small pinned host scratch (>= 4096 doubles)
+  bool gamma_set;
+
+  // ---- constitutive
+  DmkPointArrays* pts;
+  dmk_numerics num;
+  // ---- mechanical solver
+  DmkMech* mech;
+  // ---- Fortran-named drop-in mirrors (pinned host)
+  double *m_F0, *m_F, *m_P, *m_dPdF; int* m_ill;
+};
+
+int dmk_spectral_setup(dmk_ctx* c);
+void dmk_spectral_teardown(dmk_ctx* c);
+void dmk_points_teardown(dmk_ctx* c);
+void dmk_mech_teardown(dmk_ctx* c);
+// full transforms between a real slab field (device) and the z-pass layout in c->bufA
+int dmk_fft_forward_internal(dmk_ctx* c, const double* d_real);
+int dmk_fft_backward_internal(dmk_ctx* c, double* d_real, double scale);
+int dmk_gamma_internal(dmk_ctx* c);     // fused z pass on c->bufA using c->d_dc, accumulating into c->d_div
+
+// Fortran-order <-> row-major helpers for small host tensors
+static inline void f2c33(const double* f, double* c) { for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) c[3 * i + j] = f[i + 3 * j]; }
+static inline void c2f33(const double* c, double* f) { for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) f[i + 3 * j] = c[3 * i + j]; }
+static inline void f2c3333(const double* f, double* c) {
+  for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) for (int k = 0; k < 3; k++) for (int l = 0; l < 3; l++)
+    c[((i * 3 + j) * 3 + k) * 3 + l] = f[i + 3 * j + 9 * k + 27 * l];
+}
+static inline void c2f3333(const double* c, double* f) {
+  for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) for (int k = 0; k < 3; k++) for (int l = 0; l < 3; l++)
+    f[i + 3 * j + 9 * k + 27 * l] = c[((i * 3 + j) * 3 + k) * 3 + l];
+}

@@ -1,0 +1,45 @@
+// Host-visible declarations of the FFT pass launchers (fft_kernels.cu) and the fused Gamma pass (gamma_kernels.cu).
+#pragma once
+#include "fft.cuh"
+
+// Address map of one strided pass over a [..][..][n0] record array:
+//   record(o, line, i0) = (line / split) * hi_stride + o * o_stride + (line % split) * e_stride + i0
+// single GPU  y pass on [z][ky][kx]             : split = ny,     o = z,  o_stride = ny*nxr,     e_stride = nxr
+// multi  GPU  y pass on [peer][z_loc][ky_loc][kx]: split = ky_loc, hi_stride = nz_loc*ky_loc*nxr, o_stride = ky_loc*nxr
+//             z pass on [z][ky_loc][kx]         : split = nz,     o = ky, o_stride = nxr,        e_stride = ky_loc*nxr
+struct DmkLineMap {
+  long long hi_stride, o_stride, e_stride;
+  int split;
+};
+__host__ __device__ __forceinline__ long long dmk_line_rec(const DmkLineMap& m, int o, int line, int i0) {
+  int hi = line / m.split, lo = line - hi * m.split;
+  return hi * m.hi_stride + o * m.o_stride + lo * m.e_stride + i0;
+}
+
+int dmk_fft_plan_create(DmkFftPlan* pl, int n);
+void dmk_fft_plan_destroy(DmkFftPlan* pl);
+int dmk_launch_xpass_r2c(const double* in, double2* out, const DmkFftPlan& pl, int nrows, cudaStream_t st);
+int dmk_launch_xpass_c2r(const double2* in, double* out, const DmkFftPlan& pl, int nrows, double scale, cudaStream_t st);
+int dmk_launch_line_pass(bool inverse, const double2* src, double2* dst, const DmkFftPlan& pl, DmkLineMap ms,
+                         DmkLineMap md, int n0, int n_outer, int KT, cudaStream_t st);
+
+// ---- fused z pass: forward FFT along z, divergence-RMS accumulation, Gamma-operator contraction, inverse FFT
+struct DmkGammaParams {
+  const double* C_ref;         // device, 81 doubles, index ((l*3+n)*3+m)*3+o  (== C_ref(l,n,m,o), row-major 3333)
+  const double2* xi_x;         // device per-axis derivative factor tables (see context.cu: build_xi_tables)
+  const double2* xi_y;
+  const double2* xi_z;
+  const double2* xo_x;         // "other axis" factors (FWBW stencil), 1 otherwise
+  const double2* xo_y;
+  const double2* xo_z;
+  const unsigned char* nyq_x;  // per-axis flag: xi1st component zeroed at this index (even-grid Nyquist, continuous)
+  const unsigned char* nyq_y;
+  const unsigned char* nyq_z;
+  double rescale[3];           // geom_size / scaled_geom_size  (divergence correction)
+  int nx;                      // real-space cells along x (for the kx weighting)
+  int ky_offset;               // global ky index of local ky 0 (slab decomposition)
+  const double* dc_value;      // device, 9 doubles in record order c = i + 3 j: value written to the k = 0 coefficient
+  double* div_accum;           // device, 1 double: += sum_k w_k |P_hat(k) . conj(-xi1st) rescale|^2
+};
+int dmk_launch_gamma_zpass(double2* data, const DmkFftPlan& plz, DmkLineMap map, int n0, int n_outer, int KT,
+                           const DmkGammaParams& gp, cudaStream_t st, bool imag_xi);

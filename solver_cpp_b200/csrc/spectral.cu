@@ -1,0 +1,340 @@
+// Context life cycle and the spectral-utilities half of the C ABI (device-resident fields).
+//
+// Mirrors (does not copy) the reference's Spectral::init / MechBase::base_init / update_gamma / gamma_convolution /
+// calculate_divergence_rms / forward_field / calculate_rate:
+//   /root/reference/src/grid/spectral.cpp:12-130, mech_base.cpp:11-43,156-247,302-497
+#include <cstdarg>
+#include <cstring>
+#include <cmath>
+#include <algorithm>
+#include "ctx.h"
+#include "reduce.cuh"
+
+static thread_local char g_err[1024] = "";
+void dmk_set_error(const char* fmt, ...) {
+  va_list ap; va_start(ap, fmt); vsnprintf(g_err, sizeof g_err, fmt, ap); va_end(ap);
+}
+extern "C" const char* dmk_last_error(void) { return g_err; }
+
+// ------------------------------------------------------------------------------------------------ set-up
+static int upload(const void* h, size_t bytes, void** d) {
+  DMK_CUDA_CHECK(cudaMalloc(d, bytes));
+  DMK_CUDA_CHECK(cudaMemcpy(*d, h, bytes, cudaMemcpyHostToDevice));
+  return DMK_OK;
+}
+
+static int build_xi_axis(dmk_ctx* c, int axis, int n, int count, double L) {
+  const double TAU = 6.283185307179586476925286766559;
+  std::vector<double2> own(count), oth(count);
+  std::vector<unsigned char> nyq(count);
+  for (int idx = 0; idx < count; idx++) {
+    int ks = (idx > n / 2) ? idx - n : idx;
+    double a = TAU * (double)ks / (double)n;
+    switch (c->g.derivative) {
+      case DMK_DERIVATIVE_CONTINUOUS:
+        own[idx] = make_double2(0.0, TAU * (double)ks / L); oth[idx] = make_double2(1.0, 0.0); break;
+      case DMK_DERIVATIVE_CENTRAL_DIFF:
+        own[idx] = make_double2(0.0, sin(a) / (2.0 * L / n)); oth[idx] = make_double2(1.0, 0.0); break;
+      case DMK_DERIVATIVE_FWBW_DIFF: {
+        double d = 4.0 * L / n;
+        own[idx] = make_double2((cos(a) - 1.0) / d, sin(a) / d); oth[idx] = make_double2(cos(a) + 1.0, sin(a)); break; }
+      default: dmk_set_error("invalid spectral derivative id %d", c->g.derivative); return DMK_ERR_ARG;
+    }
+    nyq[idx] = (c->g.derivative == DMK_DERIVATIVE_CONTINUOUS && (n % 2 == 0) && idx == n / 2) ? 1 : 0;
+  }
+  int rc;
+  if ((rc = upload(own.data(), count * sizeof(double2), (void**)&c->xi_own[axis]))) return rc;
+  if ((rc = upload(oth.data(), count * sizeof(double2), (void**)&c->xi_oth[axis]))) return rc;
+  if ((rc = upload(nyq.data(), count, (void**)&c->nyq[axis]))) return rc;
+  return DMK_OK;
+}
+
+int dmk_spectral_setup(dmk_ctx* c) {
+  int rc;
+  if ((rc = dmk_fft_plan_create(&c->plx, c->nx))) return rc;
+  if ((rc = dmk_fft_plan_create(&c->ply, c->ny))) return rc;
+  if ((rc = dmk_fft_plan_create(&c->plz, c->nz))) return rc;
+  if ((rc = build_xi_axis(c, 0, c->nx, c->nxr, c->g.size[0]))) return rc;
+  if ((rc = build_xi_axis(c, 1, c->ny, c->ny, c->g.size[1]))) return rc;
+  if ((rc = build_xi_axis(c, 2, c->nz, c->nz, c->g.size[2]))) return rc;
+  c->xi_imag = (c->g.derivative != DMK_DERIVATIVE_FWBW_DIFF);
+  // divergence correction (mech_base.cpp:11-33)
+  const double* sz = c->g.size; const int cells[3] = {c->nx, c->ny, c->nz};
+  int idx[3] = {0, 1, 2};
+  if (c->g.divergence_correction == DMK_DIVCORR_SIZE) {
+    std::stable_sort(idx, idx + 3, [&](int a, int b) { return sz[a] < sz[b]; });
+    for (int j = 0; j < 3; j++) c->scaled_size[j] = sz[j] / sz[idx[1]];
+  } else if (c->g.divergence_correction == DMK_DIVCORR_SIZE_GRID) {
+    double nrm[3] = {sz[0] / cells[0], sz[1] / cells[1], sz[2] / cells[2]};
+    std::stable_sort(idx, idx + 3, [&](int a, int b) { return nrm[a] < nrm[b]; });
+    for (int j = 0; j < 3; j++) c->scaled_size[j] = sz[j] / sz[idx[1]] * cells[idx[1]];
+  } else {
+    for (int j = 0; j < 3; j++) c->scaled_size[j] = sz[j];
+  }
+  for (int j = 0; j < 3; j++) c->rescale[j] = sz[j] / c->scaled_size[j];
+  // half-spectrum buffers: both views of bufA must fit
+  size_t recA = (size_t)c->nz_loc * c->ny * c->nxr, recZ = (size_t)c->nz * c->ny_loc * c->nxr;
+  c->hat_records = std::max(recA, recZ);
+  DMK_CUDA_CHECK(cudaMalloc((void**)&c->bufA, c->hat_records * DMK_NC * sizeof(double2)));
+  c->bufB = nullptr;
+  if (c->P > 1) DMK_CUDA_CHECK(cudaMalloc((void**)&c->bufB, c->hat_records * DMK_NC * sizeof(double2)));
+  DMK_CUDA_CHECK(cudaMalloc((void**)&c->d_Cref, 81 * sizeof(double)));
+  DMK_CUDA_CHECK(cudaMalloc((void**)&c->d_dc, 9 * sizeof(double)));
+  DMK_CUDA_CHECK(cudaMalloc((void**)&c->d_div, sizeof(double)));
+  DMK_CUDA_CHECK(cudaMalloc((void**)&c->d_scratch, DMK_SCRATCH_DOUBLES * sizeof(double)));
+  DMK_CUDA_CHECK(cudaMallocHost((void**)&c->h_pinned, DMK_SCRATCH_DOUBLES * sizeof(double)));
+  // tile widths: keep a tile near 36 KB so several CTAs share an SM and loads overlap butterflies
+  auto auto_kt = [&](int n) { int kt = (int)(36864 / ((size_t)n * DMK_NC * sizeof(double2))); return std::max(1, std::min(kt, 16)); };
+  c->kt_y = c->g.kt_y > 0 ? c->g.kt_y : auto_kt(c->ny);
+  c->kt_z = c->g.kt_z > 0 ? c->g.kt_z : auto_kt(c->nz);
+  c->gamma_set = false;
+  return DMK_OK;
+}
+
+void dmk_spectral_teardown(dmk_ctx* c) {
+  dmk_fft_plan_destroy(&c->plx); dmk_fft_plan_destroy(&c->ply); dmk_fft_plan_destroy(&c->plz);
+  for (int a = 0; a < 3; a++) { cudaFree(c->xi_own[a]); cudaFree(c->xi_oth[a]); cudaFree(c->nyq[a]); }
+  cudaFree(c->bufA); if (c->bufB) cudaFree(c->bufB);
+  cudaFree(c->d_Cref); cudaFree(c->d_dc); cudaFree(c->d_div); cudaFree(c->d_scratch);
+  if (c->h_pinned) cudaFreeHost(c->h_pinned);
+}
+
+extern "C" int dmk_create(dmk_ctx** out, const dmk_grid_desc* g) {
+  if (!out || !g) { dmk_set_error("null argument"); return DMK_ERR_ARG; }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) {
+    dmk_set_error("no CUDA device: libdamask_grid_b200 has no CPU fallback"); return DMK_ERR_CUDA;
+  }
+  dmk_ctx* c = new dmk_ctx();
+  memset(c, 0, sizeof(dmk_ctx));
+  c->g = *g;
+  c->nx = g->cells[0]; c->ny = g->cells[1]; c->nz = g->cells[2]; c->nxr = c->nx / 2 + 1;
+  c->P = g->world_size < 1 ? 1 : g->world_size; c->rank = g->rank;
+  if (c->nx < 1 || c->ny < 1 || c->nz < 1 || c->rank < 0 || c->rank >= c->P) { dmk_set_error("bad grid descriptor"); delete c; return DMK_ERR_ARG; }
+  if (c->P > 1 && (c->nz % c->P || c->ny % c->P)) {
+    dmk_set_error("slab decomposition needs nz %% P == 0 and ny %% P == 0 (nz=%d ny=%d P=%d)", c->nz, c->ny, c->P);
+    delete c; return DMK_ERR_UNSUPPORTED;
+  }
+  c->nz_loc = c->nz / c->P; c->z_off = c->rank * c->nz_loc;
+  c->ny_loc = c->ny / c->P; c->y_off = c->rank * c->ny_loc;
+  c->n_local = (long long)c->nx * c->ny * c->nz_loc;
+  c->n_global = (long long)c->nx * c->ny * c->nz;
+  c->wgt = 1.0 / (double)c->n_global;
+  if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { dmk_set_error("stream creation failed"); delete c; return DMK_ERR_CUDA; }
+  c->own_stream = true;
+  int rc = dmk_spectral_setup(c);
+  if (rc) { delete c; return rc; }
+  *out = c;
+  return DMK_OK;
+}
+
+extern "C" void dmk_destroy(dmk_ctx* c) {
+  if (!c) return;
+  cudaStreamSynchronize(c->stream);
+  dmk_mech_teardown(c);
+  dmk_points_teardown(c);
+  dmk_spectral_teardown(c);
+  if (c->m_F0) cudaFreeHost(c->m_F0); if (c->m_F) cudaFreeHost(c->m_F); if (c->m_P) cudaFreeHost(c->m_P);
+  if (c->m_dPdF) cudaFreeHost(c->m_dPdF); if (c->m_ill) cudaFreeHost(c->m_ill);
+  if (c->own_stream) cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+extern "C" int dmk_set_stream(dmk_ctx* c, void* s) {
+  if (c->own_stream) { cudaStreamSynchronize(c->stream); cudaStreamDestroy(c->stream); c->own_stream = false; }
+  c->stream = (cudaStream_t)s;
+  return DMK_OK;
+}
+extern "C" int dmk_set_comm(dmk_ctx* c, const dmk_comm* comm) {
+  if (comm) { c->comm = *comm; c->has_comm = true; } else c->has_comm = false;
+  return DMK_OK;
+}
+extern "C" int dmk_synchronize(dmk_ctx* c) { DMK_CUDA_CHECK(cudaStreamSynchronize(c->stream)); return DMK_OK; }
+extern "C" int dmk_local_cells(const dmk_ctx* c, int* nz_local, int* z_offset, int* ny_local, int* y_offset) {
+  if (nz_local) *nz_local = c->nz_loc; if (z_offset) *z_offset = c->z_off;
+  if (ny_local) *ny_local = c->ny_loc; if (y_offset) *y_offset = c->y_off;
+  return DMK_OK;
+}
+extern "C" int dmk_kernel_launches(const dmk_ctx* c, long long* n) { *n = c->launches; return DMK_OK; }
+extern "C" size_t dmk_fourier_doubles(const dmk_ctx* c) { return c->hat_records * DMK_NC * 2; }
+
+// ------------------------------------------------------------------------------------------------ transforms
+static DmkLineMap map_y(const dmk_ctx* c, bool exchange_layout) {
+  DmkLineMap m;
+  if (!exchange_layout) { m.split = c->ny; m.hi_stride = 0; m.o_stride = (long long)c->ny * c->nxr; m.e_stride = c->nxr; }
+  else { m.split = c->ny_loc; m.hi_stride = (long long)c->nz_loc * c->ny_loc * c->nxr; m.o_stride = (long long)c->ny_loc * c->nxr; m.e_stride = c->nxr; }
+  return m;
+}
+static DmkLineMap map_z(const dmk_ctx* c) {
+  DmkLineMap m; m.split = c->nz; m.hi_stride = 0; m.o_stride = c->nxr; m.e_stride = (long long)c->ny_loc * c->nxr;
+  return m;
+}
+
+static int exchange(dmk_ctx* c, const double2* send, double2* recv) {
+  if (!c->has_comm || !c->comm.alltoall) { dmk_set_error("world_size > 1 but no alltoall callback set (dmk_set_comm)"); return DMK_ERR_STATE; }
+  size_t bytes = (size_t)c->nz_loc * c->ny_loc * c->nxr * DMK_NC * sizeof(double2);
+  if (c->comm.alltoall(c->comm.user, send, recv, bytes)) { dmk_set_error("alltoall callback failed"); return DMK_ERR_STATE; }
+  return DMK_OK;
+}
+
+int dmk_fft_forward_internal(dmk_ctx* c, const double* d_real) {
+  int rc;
+  if ((rc = dmk_launch_xpass_r2c(d_real, c->bufA, c->plx, c->ny * c->nz_loc, c->stream))) return rc;
+  c->launches++;
+  if (c->P == 1) {
+    if (c->ny > 1) { if ((rc = dmk_launch_line_pass(false, c->bufA, c->bufA, c->ply, map_y(c, false), map_y(c, false), c->nxr, c->nz_loc, c->kt_y, c->stream))) return rc; c->launches++; }
+  } else {
+    if ((rc = dmk_launch_line_pass(false, c->bufA, c->bufB, c->ply, map_y(c, false), map_y(c, true), c->nxr, c->nz_loc, c->kt_y, c->stream))) return rc;
+    c->launches++;
+    if ((rc = exchange(c, c->bufB, c->bufA))) return rc;
+  }
+  return DMK_OK;
+}
+
+int dmk_fft_backward_internal(dmk_ctx* c, double* d_real, double scale) {
+  int rc;
+  if (c->P == 1) {
+    if (c->ny > 1) { if ((rc = dmk_launch_line_pass(true, c->bufA, c->bufA, c->ply, map_y(c, false), map_y(c, false), c->nxr, c->nz_loc, c->kt_y, c->stream))) return rc; c->launches++; }
+  } else {
+    if ((rc = exchange(c, c->bufA, c->bufB))) return rc;
+    if ((rc = dmk_launch_line_pass(true, c->bufB, c->bufA, c->ply, map_y(c, true), map_y(c, false), c->nxr, c->nz_loc, c->kt_y, c->stream))) return rc;
+    c->launches++;
+  }
+  if ((rc = dmk_launch_xpass_c2r(c->bufA, d_real, c->plx, c->ny * c->nz_loc, scale, c->stream))) return rc;
+  c->launches++;
+  return DMK_OK;
+}
+
+static void fill_gamma_params(dmk_ctx* c, DmkGammaParams* gp) {
+  gp->C_ref = c->d_Cref;
+  gp->xi_x = c->xi_own[0]; gp->xi_y = c->xi_own[1]; gp->xi_z = c->xi_own[2];
+  gp->xo_x = c->xi_oth[0]; gp->xo_y = c->xi_oth[1]; gp->xo_z = c->xi_oth[2];
+  gp->nyq_x = c->nyq[0]; gp->nyq_y = c->nyq[1]; gp->nyq_z = c->nyq[2];
+  for (int j = 0; j < 3; j++) gp->rescale[j] = c->rescale[j];
+  gp->nx = c->nx; gp->ky_offset = c->y_off; gp->dc_value = c->d_dc; gp->div_accum = c->d_div;
+}
+
+int dmk_gamma_internal(dmk_ctx* c) {
+  if (!c->gamma_set) { dmk_set_error("reference stiffness not set (dmk_update_gamma)"); return DMK_ERR_STATE; }
+  DmkGammaParams gp; fill_gamma_params(c, &gp);
+  int rc = dmk_launch_gamma_zpass(c->bufA, c->plz, map_z(c), c->nxr, c->ny_loc, c->kt_z, gp, c->stream, c->xi_imag);
+  if (!rc) c->launches++;
+  return rc;
+}
+
+// plain z passes (test API dmk_fft_forward / dmk_fft_backward only)
+static int zpass_plain(dmk_ctx* c, bool inverse) {
+  if (c->nz == 1) return DMK_OK;
+  int rc = dmk_launch_line_pass(inverse, c->bufA, c->bufA, c->plz, map_z(c), map_z(c), c->nxr, c->ny_loc, c->kt_z, c->stream);
+  if (!rc) c->launches++;
+  return rc;
+}
+
+extern "C" int dmk_fft_forward(dmk_ctx* c, const double* d_real, double* d_fourier) {
+  int rc;
+  if ((rc = dmk_fft_forward_internal(c, d_real))) return rc;
+  if ((rc = zpass_plain(c, false))) return rc;
+  size_t bytes = (size_t)c->nz * c->ny_loc * c->nxr * DMK_NC * sizeof(double2);
+  DMK_CUDA_CHECK(cudaMemcpyAsync(d_fourier, c->bufA, bytes, cudaMemcpyDeviceToDevice, c->stream));
+  return DMK_OK;
+}
+
+extern "C" int dmk_fft_backward(dmk_ctx* c, const double* d_fourier, double* d_real, double wgt) {
+  int rc;
+  size_t bytes = (size_t)c->nz * c->ny_loc * c->nxr * DMK_NC * sizeof(double2);
+  DMK_CUDA_CHECK(cudaMemcpyAsync(c->bufA, d_fourier, bytes, cudaMemcpyDeviceToDevice, c->stream));
+  if ((rc = zpass_plain(c, true))) return rc;
+  return dmk_fft_backward_internal(c, d_real, wgt);
+}
+
+extern "C" int dmk_update_gamma(dmk_ctx* c, const double* C) {
+  double Cr[81], Cf[81];
+  f2c3333(C, Cr);
+  for (int i = 0; i < 81; i++) Cf[i] = Cr[i] / c->wgt;                  // C_ref = C / wgt (mech_base.cpp:157)
+  DMK_CUDA_CHECK(cudaMemcpyAsync(c->d_Cref, Cf, sizeof Cf, cudaMemcpyHostToDevice, c->stream));
+  DMK_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+  c->gamma_set = true;
+  return DMK_OK;
+}
+
+double dmk_finish_div(dmk_ctx* c, double raw_sum) {
+  double rms = sqrt(raw_sum) * c->wgt;
+  if (c->nx == 1) rms *= 0.5;
+  return rms;
+}
+
+extern "C" int dmk_divergence_and_gamma(dmk_ctx* c, double* d_field, const double* field_aim, double* err_div) {
+  int rc;
+  DMK_CUDA_CHECK(cudaMemcpyAsync(c->d_dc, field_aim, 9 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  DMK_CUDA_CHECK(cudaMemsetAsync(c->d_div, 0, sizeof(double), c->stream));
+  if ((rc = dmk_fft_forward_internal(c, d_field))) return rc;
+  if ((rc = dmk_gamma_internal(c))) return rc;
+  if (c->P > 1) {
+    if (!c->has_comm || !c->comm.allreduce_sum) { dmk_set_error("no allreduce callback"); return DMK_ERR_STATE; }
+    if (c->comm.allreduce_sum(c->comm.user, c->d_div, 1)) { dmk_set_error("allreduce failed"); return DMK_ERR_STATE; }
+  }
+  if ((rc = dmk_fft_backward_internal(c, d_field, 1.0))) return rc;
+  DMK_CUDA_CHECK(cudaMemcpyAsync(c->h_pinned, c->d_div, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  DMK_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+  if (err_div) *err_div = dmk_finish_div(c, c->h_pinned[0]);
+  return DMK_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ field ops
+__global__ void dmk_axpy_shift_kernel(const double* __restrict__ a, const double* __restrict__ b, double s,
+                                      const double* __restrict__ shift9, double* __restrict__ out, long long n9) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < n9; i += stride) {
+    double v = a[i] + s * b[i];
+    if (shift9) v -= shift9[i % 9];
+    out[i] = v;
+  }
+}
+__global__ void dmk_shift_inplace_kernel(double* f, const double* __restrict__ shift9, long long n9) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < n9; i += stride) f[i] -= shift9[i % 9];
+}
+__global__ void dmk_rate_kernel(const double* __restrict__ f0, const double* __restrict__ f, double dt,
+                                const double* __restrict__ av9, int heterogeneous, double* __restrict__ out, long long n9) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < n9; i += stride) out[i] = heterogeneous ? (f[i] - f0[i]) / dt : av9[i % 9];
+}
+__global__ void dmk_mean_minus_aim_kernel(const double* __restrict__ sum9, const double* __restrict__ aim9, double wgt,
+                                          double* __restrict__ out9) {
+  int c = threadIdx.x;
+  if (c < 9) out9[c] = sum9[c] * wgt - aim9[c];
+}
+
+extern "C" int dmk_forward_field(dmk_ctx* c, double dt, const double* d_last, const double* d_rate, const double* aim, double* d_out) {
+  const long long n9 = c->n_local * 9;
+  int grid = 148 * 8;
+  dmk_axpy_shift_kernel<<<grid, 256, 0, c->stream>>>(d_last, d_rate, dt, nullptr, d_out, n9);
+  c->launches++;
+  if (aim) {
+    // field_diff = mean(field) - aim, subtracted everywhere (mech_base.cpp:222-244)
+    double* d_sum = c->d_scratch + DMK_SCRATCH_SUM9;        // 9 doubles
+    double* d_aim = c->d_scratch + DMK_SCRATCH_TMP;         // 9 doubles
+    double* d_diff = c->d_scratch + DMK_SCRATCH_TMP + 16;   // 9 doubles
+    int rc = dmk_sum_records(c, d_out, c->n_local, d_sum); if (rc) return rc;
+    if (c->P > 1) { if (c->comm.allreduce_sum(c->comm.user, d_sum, 9)) { dmk_set_error("allreduce failed"); return DMK_ERR_STATE; } }
+    DMK_CUDA_CHECK(cudaMemcpyAsync(d_aim, aim, 9 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    dmk_mean_minus_aim_kernel<<<1, 32, 0, c->stream>>>(d_sum, d_aim, c->wgt, d_diff);
+    dmk_shift_inplace_kernel<<<grid, 256, 0, c->stream>>>(d_out, d_diff, n9);
+    c->launches += 2;
+  }
+  DMK_CUDA_CHECK(cudaGetLastError());
+  return DMK_OK;
+}
+
+extern "C" int dmk_calculate_rate(dmk_ctx* c, int heterogeneous, const double* d_f0, const double* d_f, double dt,
+                                  const double* av_rate, double* d_rate) {
+  double* d_av = c->d_scratch + DMK_SCRATCH_TMP;
+  DMK_CUDA_CHECK(cudaMemcpyAsync(d_av, av_rate, 9 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  dmk_rate_kernel<<<148 * 8, 256, 0, c->stream>>>(d_f0, d_f, dt, d_av, heterogeneous, d_rate, c->n_local * 9);
+  c->launches++;
+  DMK_CUDA_CHECK(cudaGetLastError());
+  return DMK_OK;
+}

@@ -1,0 +1,137 @@
+"""Host-side mirror of the reference's `Spectral` / `MechBase` call surface for the device path.
+
+Names follow /root/reference/src/grid/spectral.h:27-41 and mech_base.h:43-73; every method forwards to the C ABI
+(include/dmk_grid.h).  Fields are torch CUDA tensors of float64 holding the reference's Fortran memory order:
+shape (nz_local, ny, nx, 9) with component c = i + 3*j, i.e. natural[..., i, j] == tensor[..., i + 3*j]."""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import lib as L
+
+
+def natural_to_records(a):
+    """numpy [..., 3, 3] (natural i,j) -> [..., 9] Fortran component order c = i + 3 j"""
+    a = np.asarray(a, float)
+    return np.ascontiguousarray(np.swapaxes(a, -1, -2)).reshape(a.shape[:-2] + (9,))
+
+
+def records_to_natural(r):
+    r = np.asarray(r)
+    return np.swapaxes(r.reshape(r.shape[:-1] + (3, 3)), -1, -2)
+
+
+def c3333_to_fortran(Cn):
+    """natural C[i,j,k,l] -> flat Fortran order (i fastest)"""
+    return np.ascontiguousarray(np.transpose(np.asarray(Cn, float), (3, 2, 1, 0))).reshape(-1)
+
+
+def fortran_to_c3333(f):
+    return np.transpose(np.asarray(f, float).reshape(3, 3, 3, 3), (3, 2, 1, 0))
+
+
+def _p(t):
+    return C.c_void_p(t.data_ptr())
+
+
+def _hp(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class GridContext:
+    """Owns a dmk_ctx for one z-slab on the current CUDA device."""
+
+    def __init__(self, cells, size, derivative=0, divergence_correction=2, world_size=1, rank=0, kt_y=0, kt_z=0,
+                 device=None):
+        if not torch.cuda.is_available():
+            raise L.DmkError('no CUDA device: solver_cpp_b200 has no CPU fallback')
+        self.lib = L.load()
+        self.device = torch.device('cuda', torch.cuda.current_device()) if device is None else torch.device(device)
+        g = L.GridDesc()
+        g.cells[:] = [int(c) for c in cells]
+        g.size[:] = [float(s) for s in size]
+        g.world_size, g.rank = int(world_size), int(rank)
+        g.derivative, g.divergence_correction, g.kt_y, g.kt_z = derivative, divergence_correction, kt_y, kt_z
+        self.ctx = C.c_void_p()
+        L.check(self.lib.dmk_create(C.byref(self.ctx), C.byref(g)))
+        L.check(self.lib.dmk_set_stream(self.ctx, C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        self.cells = tuple(int(c) for c in cells)
+        self.size = tuple(float(s) for s in size)
+        nzl, zo, nyl, yo = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+        L.check(self.lib.dmk_local_cells(self.ctx, C.byref(nzl), C.byref(zo), C.byref(nyl), C.byref(yo)))
+        self.nz_local, self.z_offset, self.ny_local, self.y_offset = nzl.value, zo.value, nyl.value, yo.value
+        nx, ny, nz = self.cells
+        self.nxr = nx // 2 + 1
+        self.n_local = nx * ny * self.nz_local
+        self.field_shape = (self.nz_local, ny, nx, 9)
+        self.fourier_shape = (nz, self.ny_local, self.nxr, 9, 2)
+        self.world_size, self.rank = world_size, rank
+        self._comm_keepalive = None
+
+    def close(self):
+        if self.ctx:
+            self.lib.dmk_destroy(self.ctx)
+            self.ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- helpers
+    def new_field(self):
+        return torch.empty(self.field_shape, dtype=torch.float64, device=self.device)
+
+    def to_device(self, natural):
+        return torch.from_numpy(natural_to_records(natural)).to(self.device).reshape(self.field_shape).contiguous()
+
+    def to_natural(self, t):
+        return records_to_natural(t.detach().cpu().numpy())
+
+    def synchronize(self):
+        L.check(self.lib.dmk_synchronize(self.ctx))
+
+    def kernel_launches(self):
+        n = C.c_longlong()
+        L.check(self.lib.dmk_kernel_launches(self.ctx, C.byref(n)))
+        return n.value
+
+    # ---- FFT<5>::forward / backward (fft.h:37-60)
+    def fft_forward(self, field):
+        out = torch.empty(self.fourier_shape, dtype=torch.float64, device=self.device)
+        L.check(self.lib.dmk_fft_forward(self.ctx, _p(field), _p(out)))
+        return out
+
+    def fft_backward(self, hat, wgt=1.0):
+        out = self.new_field()
+        L.check(self.lib.dmk_fft_backward(self.ctx, _p(hat), _p(out), C.c_double(wgt)))
+        return out
+
+    # ---- MechBase::update_gamma (mech_base.cpp:156)
+    def update_gamma(self, C_natural):
+        f = c3333_to_fortran(C_natural)
+        L.check(self.lib.dmk_update_gamma(self.ctx, _hp(f)))
+
+    # ---- calculate_divergence_rms + gamma_convolution (mech_base.cpp:302-477), in place on `field`
+    def divergence_and_gamma(self, field, field_aim_natural):
+        aim = natural_to_records(np.asarray(field_aim_natural, float))
+        err = C.c_double()
+        L.check(self.lib.dmk_divergence_and_gamma(self.ctx, _p(field), _hp(aim), C.byref(err)))
+        return err.value
+
+    # ---- MechBase::forward_field / calculate_rate (mech_base.cpp:213-247, 479-497)
+    def forward_field(self, dt, field_last, rate, aim_natural=None):
+        out = self.new_field()
+        aim = None if aim_natural is None else natural_to_records(np.asarray(aim_natural, float))
+        L.check(self.lib.dmk_forward_field(self.ctx, C.c_double(dt), _p(field_last), _p(rate),
+                                           None if aim is None else _hp(aim), _p(out)))
+        return out
+
+    def calculate_rate(self, heterogeneous, field0, field, dt, av_rate_natural):
+        out = self.new_field()
+        av = natural_to_records(np.asarray(av_rate_natural, float))
+        L.check(self.lib.dmk_calculate_rate(self.ctx, C.c_int(int(heterogeneous)), _p(field0), _p(field),
+                                            C.c_double(dt), _hp(av), _p(out)))
+        return out
