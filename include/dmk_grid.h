@@ -110,10 +110,15 @@ int dmk_set_comm(dmk_ctx* ctx, const dmk_comm* comm);
 int dmk_synchronize(dmk_ctx* ctx);
 int dmk_local_cells(const dmk_ctx* ctx, int* nz_local, int* z_offset, int* ny_local, int* y_offset);
 int dmk_kernel_launches(const dmk_ctx* ctx, long long* n);        /* kernels launched so far by this context */
+int dmk_sizeof_phase(void);                                       /* sizeof(dmk_phase), for binding checks */
+int dmk_sizeof_numerics(void);
 
 /* ------------------------------------------------------------------ crystal tables (host, pure; crystal.f90)
  * fill the geometry-derived members of a dmk_phase for lattice "cF" or "cI" */
 int dmk_crystal_schmid_slip(const char* lattice, const int* N_sl, int n_fam, double* P /* [sum][9] */);
+/* with the cI non-Schmid coefficients of family 1 and the sense (+1 / -1) of the slip direction (crystal.f90:1353-1431) */
+int dmk_crystal_schmid_slip_ns(const char* lattice, const int* N_sl, int n_fam, const double* non_schmid, int n_coeff,
+                               int sense, double* P);
 int dmk_crystal_schmid_twin(const char* lattice, const int* N_tw, int n_fam, double* P);
 int dmk_crystal_slip_normal(const char* lattice, const int* N_sl, int n_fam, double* n /* [sum][3] */);
 int dmk_crystal_interaction(const char* kind /* "sl-sl","tw-tw","sl-tw","tw-sl" */, const char* lattice,

@@ -762,6 +762,10 @@ static void dPdF_point(pt_t *p, double Dt, double *dPdF) {
 
 /* ================================================================== exported entry points */
 /* F_in: [n][9] row-major per point (the ctypes wrapper converts from the Fortran [3][3][N] boundary layout) */
+/* optional per-cell log of sub-step cut-backs (test diagnostics: cells whose Newton path is rounding-chaotic) */
+static int *g_point_cutbacks = NULL;
+void orc_set_point_log(int *buf) { g_point_cutbacks = buf; }
+
 int orc_mechanical_response(const orc_phase_t *phases, const orc_num_t *num, orc_points_t *st, const double *F_in,
                             double Dt, int cell_start, int cell_end, long *counters) {
   int ill = 0;
@@ -776,6 +780,7 @@ int orc_mechanical_response(const orc_phase_t *phases, const orc_num_t *num, orc
     memcpy(p.state, p.state0, sizeof(double)*ns);
     memcpy(p.F, F_in + 9*(size_t)ce, 9*sizeof(double));             /* phase_set_F */
     if (!constitutive(&p, Dt, &cnt)) ill |= 1;
+    if (g_point_cutbacks) g_point_cutbacks[ce] = (int)cnt.n_cutbacks;
     c0 += cnt.n_Lp_iter; c1 += cnt.n_Li_iter; c2 += cnt.n_stress_calls; c3 += cnt.n_state_iter; c4 += cnt.n_substeps; c5 += cnt.n_cutbacks;
   }
   if (counters) { counters[0] = c0; counters[1] = c1; counters[2] = c2; counters[3] = c3; counters[4] = c4; counters[5] = c5; }

@@ -1,0 +1,507 @@
+// Constitutive half of the C ABI: per-point state in HBM, the integration kernel (one thread per material point),
+// the consistent-tangent kernel with on-the-fly homogenisation, and f_materialpoint_forward.
+//
+// Replaces f_homogenization_mechanical_response / _response2 / f_materialpoint_forward
+// (/root/reference/src/homogenization.f90:219-324, materialpoint.f90:208-218) and the reductions of
+// Spectral::constitutive_response (/root/reference/src/grid/spectral.cpp:160-218).
+#include <cstring>
+#include <cmath>
+#include <vector>
+#include <algorithm>
+#include "constitutive_dev.cuh"
+#include "tangent_dev.cuh"
+#include "reduce.cuh"
+
+#define DMK_PT_THREADS 128
+
+// ------------------------------------------------------------------------------------------------ kernels
+template <int LAW, int NS, int ND>
+__global__ void __launch_bounds__(DMK_PT_THREADS) dmk_constitutive_kernel(DmkPointArrays pa, int phase, DmkNumDev num,
+                                                                          const double* __restrict__ Fin, double* __restrict__ Pout,
+                                                                          double Dt) {
+  const long long n = pa.n;
+  DmkCnt cnt = {0, 0, 0, 0, 0, 0};
+  unsigned ill = 0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    if (pa.phase[i] != phase) continue;
+    DmkPt<LAW, NS, ND> p;
+    p.ph = pa.d_phases + phase;
+    p.C66 = p.ph->p.C66;
+    const int ns = p.ph->p.n_state;
+    double F0[9], Ft[9], Fp0[9], Lp0[9], S0[6];
+    double state0[NS > 0 ? NS : 1];
+#pragma unroll
+    for (int a = 0; a < 3; a++)
+#pragma unroll
+      for (int b = 0; b < 3; b++) Ft[3 * a + b] = Fin[i * 9 + a + 3 * b];            // boundary record: c = i + 3 j
+#pragma unroll
+    for (int a = 0; a < 9; a++) {
+      F0[a] = pa.F0[a * n + i]; Fp0[a] = pa.Fp0[a * n + i]; Lp0[a] = pa.Lp0[a * n + i];
+      p.Lp[a] = pa.Lp[a * n + i];                  // phase_restore(includeL = .false.): Lp keeps the last guess
+      p.Fp[a] = Fp0[a]; p.Fe[a] = pa.Fe[a * n + i]; p.P[a] = 0.0;
+    }
+#pragma unroll
+    for (int a = 0; a < 6; a++) { S0[a] = pa.S0[a * n + i]; p.S[a] = S0[a]; }
+    for (int k = 0; k < ns; k++) { state0[k] = pa.state0[k * n + i]; p.st[k] = state0[k]; }
+    if constexpr (ND > 0) { const int nd = p.ph->n_dep; for (int k = 0; k < nd; k++) p.dep[k] = pa.dep[k * n + i]; }
+    const bool ok = constitutive_point(p, num, F0, Ft, Fp0, Lp0, S0, state0, Dt, cnt);
+    if (!ok) ill = 1;
+#pragma unroll
+    for (int a = 0; a < 9; a++) {
+      pa.F[a * n + i] = Ft[a]; pa.Fp[a * n + i] = p.Fp[a]; pa.Lp[a * n + i] = p.Lp[a]; pa.Fe[a * n + i] = p.Fe[a];
+    }
+#pragma unroll
+    for (int a = 0; a < 3; a++)
+#pragma unroll
+      for (int b = 0; b < 3; b++) Pout[i * 9 + a + 3 * b] = p.P[3 * a + b];
+#pragma unroll
+    for (int a = 0; a < 6; a++) pa.S[a * n + i] = p.S[a];
+    for (int k = 0; k < ns; k++) pa.state[k * n + i] = p.st[k];
+    if constexpr (ND > 0) { const int nd = p.ph->n_dep; for (int k = 0; k < nd; k++) pa.dep[k * n + i] = p.dep[k]; }
+  }
+  // counters: warp reduce, one atomic per warp and counter
+  unsigned v[7] = {cnt.Lp_iter, cnt.Li_iter, cnt.stress_calls, cnt.state_iter, cnt.substeps, cnt.cutbacks, ill};
+#pragma unroll
+  for (int k = 0; k < 7; k++) {
+    unsigned s = v[k];
+    for (int off = 16; off > 0; off >>= 1) s += __shfl_down_sync(0xffffffffu, s, off);
+    if ((threadIdx.x & 31) == 0 && s) atomicAdd(&pa.d_counters[k], (unsigned long long)s);
+  }
+  if (ill) atomicOr(pa.d_ill, 1);
+}
+
+// tangent: dPdF per point (row-major 3333), summed per block into partials; optional materialisation; ||.||^2 per point
+template <int LAW, int NS, int ND>
+__global__ void __launch_bounds__(DMK_PT_THREADS) dmk_tangent_kernel(DmkPointArrays pa, int phase, double Dt, long long first,
+                                                                     long long count, double* __restrict__ partial,
+                                                                     double* __restrict__ dPdF_out, double* __restrict__ single_out) {
+  __shared__ double sh[DMK_PT_THREADS / 32];
+  const long long n = pa.n;
+  double acc[81];
+  for (int k = 0; k < 81; k++) acc[k] = 0.0;
+  for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < count; j += (long long)gridDim.x * blockDim.x) {
+    const long long i = first + j;
+    if (pa.phase[i] != phase) continue;
+    DmkPt<LAW, NS, ND> p;
+    p.ph = pa.d_phases + phase;
+    p.C66 = p.ph->p.C66;
+    const int ns = p.ph->p.n_state;
+    double F[9], Fp0[9];
+#pragma unroll
+    for (int a = 0; a < 9; a++) {
+      F[a] = pa.F[a * n + i]; Fp0[a] = pa.Fp0[a * n + i];
+      p.Fp[a] = pa.Fp[a * n + i]; p.Fe[a] = pa.Fe[a * n + i]; p.Lp[a] = 0.0; p.P[a] = 0.0;
+    }
+#pragma unroll
+    for (int a = 0; a < 6; a++) p.S[a] = pa.S[a * n + i];
+    for (int k = 0; k < ns; k++) p.st[k] = pa.state[k * n + i];
+    if constexpr (ND > 0) { const int nd = p.ph->n_dep; for (int k = 0; k < nd; k++) p.dep[k] = pa.dep[k * n + i]; }
+    double dPdF[81];
+    tangent_point(p, F, Fp0, Dt, dPdF);
+    double nrm = 0.0;
+    for (int k = 0; k < 81; k++) { acc[k] += dPdF[k]; nrm += dPdF[k] * dPdF[k]; }
+    if (pa.nrm && !single_out) pa.nrm[i] = nrm;
+    if (single_out) for (int k = 0; k < 81; k++) single_out[k] = dPdF[k];
+    if (dPdF_out) {
+      // Fortran order of dPdF(3,3,3,3,cell): i fastest
+      for (int a = 0; a < 3; a++) for (int b = 0; b < 3; b++) for (int cidx = 0; cidx < 3; cidx++) for (int d = 0; d < 3; d++)
+        dPdF_out[i * 81 + a + 3 * b + 9 * cidx + 27 * d] = dPdF[((a * 3 + b) * 3 + cidx) * 3 + d];
+    }
+  }
+  if (!partial) return;
+  for (int k = 0; k < 81; k++) {
+    double s = acc[k];
+    for (int off = 16; off > 0; off >>= 1) s += __shfl_down_sync(0xffffffffu, s, off);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double t = 0.0;
+      for (int w = 0; w < DMK_PT_THREADS / 32; w++) t += sh[w];
+      partial[(size_t)blockIdx.x * 81 + k] += t;          // partials accumulate over the per-phase launches
+    }
+    __syncthreads();
+  }
+}
+
+__global__ void dmk_forward_copy_kernel(DmkPointArrays pa) {
+  const long long n = pa.n;
+  const long long tot9 = 9 * n, tot6 = 6 * n, tots = (long long)pa.max_state * n;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < tots || i < tot9; i += (long long)gridDim.x * blockDim.x) {
+    if (i < tot9) { pa.F0[i] = pa.F[i]; pa.Fp0[i] = pa.Fp[i]; pa.Lp0[i] = pa.Lp[i]; }
+    if (i < tot6) pa.S0[i] = pa.S[i];
+    if (i < tots) pa.state0[i] = pa.state[i];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ launch dispatch
+static DmkNumDev num_dev(const dmk_numerics& n) {
+  DmkNumDev d;
+  d.r_cutback_min = n.r_cutback_min; d.r_cutback = n.r_cutback; d.r_increase = n.r_increase; d.eps_rel_state = n.eps_rel_state;
+  d.N_iter_state_max = n.N_iter_state_max; d.N_iter_Lp_max = n.N_iter_Lp_max; d.r_linesearch_Lp = n.r_linesearch_Lp;
+  d.eps_rel_Lp = n.eps_rel_Lp; d.eps_abs_Lp = n.eps_abs_Lp; d.f_update_jacobi_Lp = n.f_update_jacobi_Lp > 0 ? n.f_update_jacobi_Lp : 1;
+  return d;
+}
+
+static int point_grid(long long n) {
+  long long b = (n + DMK_PT_THREADS - 1) / DMK_PT_THREADS;
+  const long long cap = 148LL * 64;
+  return (int)std::max(1LL, std::min(b, cap));
+}
+
+#define DMK_DISPATCH(KERNEL, law, nstate, ...)                                                                  \
+  do {                                                                                                          \
+    if (law == DMK_LAW_NONE) KERNEL<DMK_LAW_NONE, 0, 0> __VA_ARGS__;                                            \
+    else if (law == DMK_LAW_ISOTROPIC) KERNEL<DMK_LAW_ISOTROPIC, 1, 0> __VA_ARGS__;                             \
+    else if (law == DMK_LAW_PHENOPOWERLAW && nstate <= 24) KERNEL<DMK_LAW_PHENOPOWERLAW, 24, 0> __VA_ARGS__;    \
+    else if (law == DMK_LAW_PHENOPOWERLAW && nstate <= 48) KERNEL<DMK_LAW_PHENOPOWERLAW, 48, 0> __VA_ARGS__;    \
+    else if (law == DMK_LAW_PHENOPOWERLAW) KERNEL<DMK_LAW_PHENOPOWERLAW, 2 * DMK_MAX_SYS, 0> __VA_ARGS__;       \
+    else if (law == DMK_LAW_DISLOTWIN && nstate <= 48) KERNEL<DMK_LAW_DISLOTWIN, 48, 36> __VA_ARGS__;           \
+    else KERNEL<DMK_LAW_DISLOTWIN, DMK_MAX_STATE, DMK_MAX_DEP> __VA_ARGS__;                                     \
+  } while (0)
+
+int dmk_points_constitutive(dmk_ctx* c, const double* d_F, double* d_P, double dt) {
+  DmkPointArrays& pa = *c->pts;
+  const DmkNumDev nd = num_dev(c->num);
+  const int grid = point_grid(pa.n);
+  for (int ph = 0; ph < pa.n_phases; ph++) {
+    if (pa.n_cells_of_phase[ph] == 0) continue;
+    const int law = pa.law_of_phase[ph], nst = pa.nstate_of_phase[ph];
+    DMK_DISPATCH(dmk_constitutive_kernel, law, nst, <<<grid, DMK_PT_THREADS, 0, c->stream>>>(pa, ph, nd, d_F, d_P, dt));
+    c->launches++;
+  }
+  DMK_CUDA_CHECK(cudaGetLastError());
+  return DMK_OK;
+}
+
+#define DMK_TANGENT_BLOCKS (148 * 8)
+
+int dmk_points_tangent(dmk_ctx* c, double dt, double* d_Csum81, double* d_dPdF) {
+  DmkPointArrays& pa = *c->pts;
+  double* partial = c->d_scratch + DMK_SCRATCH_PARTIAL;            // DMK_TANGENT_BLOCKS * 81 doubles
+  const int grid = (int)std::max(1LL, std::min((pa.n + DMK_PT_THREADS - 1) / DMK_PT_THREADS, (long long)DMK_TANGENT_BLOCKS));
+  DMK_CUDA_CHECK(cudaMemsetAsync(partial, 0, (size_t)grid * 81 * sizeof(double), c->stream));
+  for (int ph = 0; ph < pa.n_phases; ph++) {
+    if (pa.n_cells_of_phase[ph] == 0) continue;
+    const int law = pa.law_of_phase[ph], nst = pa.nstate_of_phase[ph];
+    DMK_DISPATCH(dmk_tangent_kernel, law, nst, <<<grid, DMK_PT_THREADS, 0, c->stream>>>(pa, ph, dt, 0LL, pa.n, partial, d_dPdF, nullptr));
+    c->launches++;
+  }
+  dmk_sum_partials_kernel<<<1, 96, 0, c->stream>>>(partial, grid, 81, d_Csum81);
+  c->launches++;
+  DMK_CUDA_CHECK(cudaGetLastError());
+  return DMK_OK;
+}
+
+int dmk_points_tangent_cell(dmk_ctx* c, double dt, long long cell, double* d_out81) {
+  DmkPointArrays& pa = *c->pts;
+  int ph = 0;
+  DMK_CUDA_CHECK(cudaMemcpyAsync(&ph, pa.phase + cell, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  DMK_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+  const int law = pa.law_of_phase[ph], nst = pa.nstate_of_phase[ph];
+  DMK_DISPATCH(dmk_tangent_kernel, law, nst, <<<1, DMK_PT_THREADS, 0, c->stream>>>(pa, ph, dt, cell, 1LL, nullptr, nullptr, d_out81));
+  c->launches++;
+  DMK_CUDA_CHECK(cudaGetLastError());
+  return DMK_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ set-up
+static void voigt_strain_of(const double* P, double* pv) {
+  pv[0] = P[0]; pv[1] = P[4]; pv[2] = P[8]; pv[3] = P[5] + P[7]; pv[4] = P[2] + P[6]; pv[5] = P[1] + P[3];
+}
+static void q_host(const double* C66, const double* pv, double* Q) {
+  for (int b = 0; b < 6; b++) { double s = 0.0; for (int a = 0; a < 6; a++) s += pv[a] * C66[6 * a + b]; Q[b] = s; }
+}
+
+static int check_phase(const dmk_phase& p, int idx) {
+  if (p.law < DMK_LAW_NONE || p.law > DMK_LAW_DISLOTWIN) { dmk_set_error("phase %d: unknown plastic law %d", idx, p.law); return DMK_ERR_ARG; }
+  if (p.n_sl < 0 || p.n_sl > DMK_MAX_SL || p.n_tw < 0 || p.n_tw > DMK_MAX_TW) { dmk_set_error("phase %d: too many slip/twin systems", idx); return DMK_ERR_UNSUPPORTED; }
+  if (p.law == DMK_LAW_ISOTROPIC && p.iso_dilatation) { dmk_set_error("phase %d: isotropic plasticity with dilatation (Li != 0) is not offered on the device path", idx); return DMK_ERR_UNSUPPORTED; }
+  if (p.law == DMK_LAW_DISLOTWIN && p.dt_gamma_0_sb != 0.0) { dmk_set_error("phase %d: dislotwin shear banding is not offered on the device path", idx); return DMK_ERR_UNSUPPORTED; }
+  int expect = 0;
+  if (p.law == DMK_LAW_ISOTROPIC) expect = 1;
+  else if (p.law == DMK_LAW_PHENOPOWERLAW) expect = 2 * (p.n_sl + p.n_tw);
+  else if (p.law == DMK_LAW_DISLOTWIN) expect = 3 * p.n_sl + p.n_tw;
+  if (p.n_state != expect) { dmk_set_error("phase %d: n_state %d, expected %d", idx, p.n_state, expect); return DMK_ERR_ARG; }
+  return DMK_OK;
+}
+
+void dmk_points_teardown(dmk_ctx* c) {
+  if (!c->pts) return;
+  DmkPointArrays* pa = c->pts;
+  cudaFree(pa->phase); cudaFree(pa->F0); cudaFree(pa->F); cudaFree(pa->Fp0); cudaFree(pa->Fp); cudaFree(pa->Fe);
+  cudaFree(pa->Lp0); cudaFree(pa->Lp); cudaFree(pa->S0); cudaFree(pa->S); cudaFree(pa->state0); cudaFree(pa->state);
+  if (pa->dep) cudaFree(pa->dep);
+  cudaFree(pa->nrm); cudaFree(pa->d_phases); cudaFree(pa->d_counters); cudaFree(pa->d_ill);
+  delete[] pa->h_phases;
+  delete pa;
+  c->pts = nullptr;
+}
+
+template <int LAW, int NS, int ND>
+__global__ void dmk_init_dependent_kernel(DmkPointArrays pa, int phase) {
+  const long long n = pa.n;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    if (pa.phase[i] != phase) continue;
+    if constexpr (LAW == DMK_LAW_DISLOTWIN) {
+      DmkPt<LAW, NS, ND> p;
+      p.ph = pa.d_phases + phase;
+      const int ns = p.ph->p.n_state, nd = p.ph->n_dep;
+      for (int k = 0; k < ns; k++) p.st[k] = pa.state[k * n + i];
+      dt_dependentState(p);
+      for (int k = 0; k < nd; k++) pa.dep[k * n + i] = p.dep[k];
+    }
+  }
+}
+
+extern "C" int dmk_material_init(dmk_ctx* c, const dmk_phase* phases, int n_phases, const int* phase_of_cell,
+                                 const double* O_of_cell, const dmk_numerics* num) {
+  if (!c || !phases || !phase_of_cell || !O_of_cell || !num) { dmk_set_error("null argument"); return DMK_ERR_ARG; }
+  if (n_phases < 1 || n_phases > DMK_MAX_PHASES) { dmk_set_error("1..%d phases supported", DMK_MAX_PHASES); return DMK_ERR_UNSUPPORTED; }
+  for (int i = 0; i < n_phases; i++) { int rc = check_phase(phases[i], i); if (rc) return rc; }
+  dmk_points_teardown(c);
+  c->num = *num;
+  DmkPointArrays* pa = new DmkPointArrays();
+  memset(pa, 0, sizeof *pa);
+  c->pts = pa;
+  const long long n = c->n_local;
+  pa->n = n; pa->n_phases = n_phases;
+  pa->h_phases = new dmk_phase[n_phases];
+  memcpy(pa->h_phases, phases, sizeof(dmk_phase) * n_phases);
+  std::vector<DmkDevPhase> dev(n_phases);
+  int max_state = 1, max_dep = 0;
+  for (int i = 0; i < n_phases; i++) {
+    DmkDevPhase& d = dev[i];
+    memset(&d, 0, sizeof d);
+    d.p = phases[i];
+    const dmk_phase& p = phases[i];
+    bool nons = false;
+    for (int a = 0; a < p.n_sl; a++) {
+      const double* pos = (p.law == DMK_LAW_DISLOTWIN) ? p.P_sl[a] : p.P_nS_pos[a];
+      voigt_strain_of(pos, d.pv_pos[a]); q_host(p.C66, d.pv_pos[a], d.Q_pos[a]);
+      voigt_strain_of(p.P_nS_neg[a], d.pv_neg[a]); q_host(p.C66, d.pv_neg[a], d.Q_neg[a]);
+      for (int k = 0; k < 9; k++) if (p.P_nS_neg[a][k] != -p.P_nS_pos[a][k]) nons = true;
+    }
+    for (int a = 0; a < p.n_tw; a++) { voigt_strain_of(p.P_tw[a], d.pv_tw[a]); q_host(p.C66, d.pv_tw[a], d.Q_tw[a]); }
+    d.nonschmid = nons ? 1 : 0;
+    d.n_dep = (p.law == DMK_LAW_DISLOTWIN) ? 2 * p.n_sl + p.n_tw : 0;
+    pa->law_of_phase[i] = p.law; pa->nstate_of_phase[i] = p.n_state; pa->nsys_of_phase[i] = p.n_sl + p.n_tw;
+    max_state = std::max(max_state, p.n_state); max_dep = std::max(max_dep, d.n_dep);
+  }
+  pa->max_state = max_state; pa->max_dep = max_dep;
+  // host staging of the initial state (mechanical_init: F = Fe.Fp with Fp0 = O, Fe = O^T; phase_mechanical.f90:248-259)
+  std::vector<int> ph(n);
+  for (long long i = 0; i < n; i++) {
+    ph[i] = phase_of_cell[i];
+    if (ph[i] < 0 || ph[i] >= n_phases) { dmk_set_error("cell %lld: phase index %d out of range", i, ph[i]); return DMK_ERR_ARG; }
+    pa->n_cells_of_phase[ph[i]]++;
+  }
+  auto dalloc = [&](double** p, size_t count) -> int { DMK_CUDA_CHECK(cudaMalloc((void**)p, count * sizeof(double))); return DMK_OK; };
+  int rc;
+  if ((rc = dalloc(&pa->F0, 9 * n)) || (rc = dalloc(&pa->F, 9 * n)) || (rc = dalloc(&pa->Fp0, 9 * n)) || (rc = dalloc(&pa->Fp, 9 * n)) ||
+      (rc = dalloc(&pa->Fe, 9 * n)) || (rc = dalloc(&pa->Lp0, 9 * n)) || (rc = dalloc(&pa->Lp, 9 * n)) || (rc = dalloc(&pa->S0, 6 * n)) ||
+      (rc = dalloc(&pa->S, 6 * n)) || (rc = dalloc(&pa->state0, (size_t)max_state * n)) || (rc = dalloc(&pa->state, (size_t)max_state * n)) ||
+      (rc = dalloc(&pa->nrm, n))) return rc;
+  if (max_dep > 0) { if ((rc = dalloc(&pa->dep, (size_t)max_dep * n))) return rc; DMK_CUDA_CHECK(cudaMemset(pa->dep, 0, (size_t)max_dep * n * sizeof(double))); }
+  DMK_CUDA_CHECK(cudaMalloc((void**)&pa->phase, n * sizeof(int)));
+  DMK_CUDA_CHECK(cudaMalloc((void**)&pa->d_phases, n_phases * sizeof(DmkDevPhase)));
+  DMK_CUDA_CHECK(cudaMalloc((void**)&pa->d_counters, 8 * sizeof(unsigned long long)));
+  DMK_CUDA_CHECK(cudaMalloc((void**)&pa->d_ill, sizeof(int)));
+  DMK_CUDA_CHECK(cudaMemset(pa->d_counters, 0, 8 * sizeof(unsigned long long)));
+  DMK_CUDA_CHECK(cudaMemset(pa->d_ill, 0, sizeof(int)));
+  DMK_CUDA_CHECK(cudaMemcpy(pa->phase, ph.data(), n * sizeof(int), cudaMemcpyHostToDevice));
+  DMK_CUDA_CHECK(cudaMemcpy(pa->d_phases, dev.data(), n_phases * sizeof(DmkDevPhase), cudaMemcpyHostToDevice));
+  {
+    std::vector<double> buf((size_t)9 * n);
+    auto up = [&](double* d, size_t count) -> int { DMK_CUDA_CHECK(cudaMemcpy(d, buf.data(), count * sizeof(double), cudaMemcpyHostToDevice)); return DMK_OK; };
+    for (int a = 0; a < 9; a++) for (long long i = 0; i < n; i++) buf[(size_t)a * n + i] = (a % 4 == 0) ? 1.0 : 0.0;      // F = I
+    if ((rc = up(pa->F0, 9 * n)) || (rc = up(pa->F, 9 * n))) return rc;
+    for (int a = 0; a < 9; a++) for (long long i = 0; i < n; i++) buf[(size_t)a * n + i] = O_of_cell[i * 9 + a];           // Fp = O
+    if ((rc = up(pa->Fp0, 9 * n)) || (rc = up(pa->Fp, 9 * n))) return rc;
+    for (int a = 0; a < 3; a++) for (int b = 0; b < 3; b++) for (long long i = 0; i < n; i++) buf[(size_t)(3 * a + b) * n + i] = O_of_cell[i * 9 + 3 * b + a];
+    if ((rc = up(pa->Fe, 9 * n))) return rc;                                                                              // Fe = O^T
+    DMK_CUDA_CHECK(cudaMemset(pa->Lp0, 0, 9 * n * sizeof(double))); DMK_CUDA_CHECK(cudaMemset(pa->Lp, 0, 9 * n * sizeof(double)));
+    DMK_CUDA_CHECK(cudaMemset(pa->S0, 0, 6 * n * sizeof(double))); DMK_CUDA_CHECK(cudaMemset(pa->S, 0, 6 * n * sizeof(double)));
+    std::vector<double> st((size_t)max_state * n, 0.0);
+    for (long long i = 0; i < n; i++) { const dmk_phase& p = phases[ph[i]]; for (int k = 0; k < p.n_state; k++) st[(size_t)k * n + i] = p.state_init[k]; }
+    DMK_CUDA_CHECK(cudaMemcpy(pa->state0, st.data(), st.size() * sizeof(double), cudaMemcpyHostToDevice));
+    DMK_CUDA_CHECK(cudaMemcpy(pa->state, st.data(), st.size() * sizeof(double), cudaMemcpyHostToDevice));
+  }
+  // crystallite_init: dependent state from the initial state (phase.f90:564)
+  for (int i = 0; i < n_phases; i++) {
+    if (pa->law_of_phase[i] != DMK_LAW_DISLOTWIN || pa->n_cells_of_phase[i] == 0) continue;
+    const int grid = point_grid(n);
+    if (pa->nstate_of_phase[i] <= 48) dmk_init_dependent_kernel<DMK_LAW_DISLOTWIN, 48, 36><<<grid, DMK_PT_THREADS, 0, c->stream>>>(*pa, i);
+    else dmk_init_dependent_kernel<DMK_LAW_DISLOTWIN, DMK_MAX_STATE, DMK_MAX_DEP><<<grid, DMK_PT_THREADS, 0, c->stream>>>(*pa, i);
+    c->launches++;
+  }
+  DMK_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+  DMK_CUDA_CHECK(cudaGetLastError());
+  return DMK_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ C ABI
+static int need_points(dmk_ctx* c) {
+  if (!c || !c->pts) { dmk_set_error("material not initialised (dmk_material_init)"); return DMK_ERR_STATE; }
+  return DMK_OK;
+}
+
+extern "C" int dmk_constitutive_response(dmk_ctx* c, const double* d_F, double* d_P, double dt) {
+  int rc = need_points(c); if (rc) return rc;
+  return dmk_points_constitutive(c, d_F, d_P, dt);
+}
+
+extern "C" int dmk_materialpoint_forward(dmk_ctx* c) {
+  int rc = need_points(c); if (rc) return rc;
+  dmk_forward_copy_kernel<<<148 * 8, 256, 0, c->stream>>>(*c->pts);
+  c->launches++;
+  DMK_CUDA_CHECK(cudaGetLastError());
+  return DMK_OK;
+}
+
+extern "C" int dmk_terminally_ill(dmk_ctx* c, int* flag, int reset) {
+  int rc = need_points(c); if (rc) return rc;
+  int h = 0;
+  DMK_CUDA_CHECK(cudaMemcpyAsync(&h, c->pts->d_ill, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  if (reset) DMK_CUDA_CHECK(cudaMemsetAsync(c->pts->d_ill, 0, sizeof(int), c->stream));
+  DMK_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+  if (c->P > 1 && c->has_comm && c->comm.allreduce_max) {
+    double* d = c->d_scratch + DMK_SCRATCH_TMP;
+    double v = (double)h;
+    DMK_CUDA_CHECK(cudaMemcpyAsync(d, &v, sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    if (c->comm.allreduce_max(c->comm.user, d, 1)) { dmk_set_error("allreduce failed"); return DMK_ERR_STATE; }
+    DMK_CUDA_CHECK(cudaMemcpyAsync(&v, d, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    DMK_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    h = v != 0.0;
+  }
+  if (flag) *flag = h;
+  return DMK_OK;
+}
+
+extern "C" int dmk_get_counters(dmk_ctx* c, long long counters[6]) {
+  int rc = need_points(c); if (rc) return rc;
+  unsigned long long h[8];
+  DMK_CUDA_CHECK(cudaMemcpyAsync(h, c->pts->d_counters, sizeof h, cudaMemcpyDeviceToHost, c->stream));
+  DMK_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+  counters[0] = (long long)h[0]; counters[1] = (long long)h[2]; counters[2] = (long long)h[3];
+  counters[3] = (long long)h[4]; counters[4] = (long long)h[5]; counters[5] = (long long)h[6];
+  return DMK_OK;
+}
+
+// host copy of a per-point array, cell-major: out[cell][component] (row-major tensors; S as full 3x3)
+extern "C" int dmk_get_state(dmk_ctx* c, const char* name, double* out, size_t n_doubles) {
+  int rc = need_points(c); if (rc) return rc;
+  DmkPointArrays& pa = *c->pts;
+  const long long n = pa.n;
+  const double* src = nullptr; int comps = 9; bool voigt = false;
+  std::string s(name ? name : "");
+  if (s == "F") src = pa.F; else if (s == "F0") src = pa.F0; else if (s == "Fp") src = pa.Fp; else if (s == "Fp0") src = pa.Fp0;
+  else if (s == "Fe") src = pa.Fe; else if (s == "Lp") src = pa.Lp; else if (s == "Lp0") src = pa.Lp0;
+  else if (s == "S") { src = pa.S; comps = 6; voigt = true; } else if (s == "S0") { src = pa.S0; comps = 6; voigt = true; }
+  else if (s == "state") { src = pa.state; comps = pa.max_state; } else if (s == "state0") { src = pa.state0; comps = pa.max_state; }
+  else if (s == "dep") { src = pa.dep; comps = pa.max_dep; }
+  if (!src) { dmk_set_error("dmk_get_state: unknown or empty array '%s'", s.c_str()); return DMK_ERR_ARG; }
+  const int out_comps = voigt ? 9 : comps;
+  if (n_doubles < (size_t)out_comps * n) { dmk_set_error("dmk_get_state: buffer too small (%zu < %lld)", n_doubles, (long long)out_comps * n); return DMK_ERR_ARG; }
+  std::vector<double> buf((size_t)comps * n);
+  DMK_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+  DMK_CUDA_CHECK(cudaMemcpy(buf.data(), src, buf.size() * sizeof(double), cudaMemcpyDeviceToHost));
+  static const int V[9] = {0, 5, 4, 5, 1, 3, 4, 3, 2};
+  for (long long i = 0; i < n; i++)
+    for (int k = 0; k < out_comps; k++) out[i * out_comps + k] = buf[(size_t)(voigt ? V[k] : k) * n + i];
+  return DMK_OK;
+}
+
+// ---- min/max selection of ||dPdF||^2 with the shared tie rule (oracle/spectral.py select_minmax)
+__global__ void dmk_minmax_value_kernel(const double* __restrict__ nrm, long long n, double* __restrict__ out2) {
+  __shared__ double smx[8], smn[8];
+  double mx = -INFINITY, mn = INFINITY;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const double v = nrm[i]; mx = fmax(mx, v); mn = fmin(mn, v);
+  }
+  for (int off = 16; off > 0; off >>= 1) { mx = fmax(mx, __shfl_down_sync(0xffffffffu, mx, off)); mn = fmin(mn, __shfl_down_sync(0xffffffffu, mn, off)); }
+  if ((threadIdx.x & 31) == 0) { smx[threadIdx.x >> 5] = mx; smn[threadIdx.x >> 5] = mn; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < (blockDim.x >> 5); w++) { mx = fmax(mx, smx[w]); mn = fmin(mn, smn[w]); }
+    // doubles >= 0: the IEEE bit pattern is monotone, so integer atomics give an exact max / min
+    atomicMax((unsigned long long*)&out2[0], (unsigned long long)__double_as_longlong(mx));
+    atomicMin((unsigned long long*)&out2[1], (unsigned long long)__double_as_longlong(mn));
+  }
+}
+__global__ void dmk_minmax_index_kernel(const double* __restrict__ nrm, long long n, long long offset, double vmax, double vmin,
+                                        double tol, unsigned long long* __restrict__ idx2) {
+  unsigned long long imx = ~0ULL, imn = ~0ULL;
+  const double tmax = vmax * (1.0 - tol), tmin = vmin * (1.0 + tol);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const double v = nrm[i];
+    if (v >= tmax && (unsigned long long)(i + offset) < imx) imx = (unsigned long long)(i + offset);
+    if (v <= tmin && (unsigned long long)(i + offset) < imn) imn = (unsigned long long)(i + offset);
+  }
+  if (imx != ~0ULL) atomicMin(&idx2[0], imx);
+  if (imn != ~0ULL) atomicMin(&idx2[1], imn);
+}
+
+extern "C" int dmk_tangent_response(dmk_ctx* c, double dt, double* C_volAvg, double* C_minMaxAvg, double* d_dPdF,
+                                    long long minmax_cells[2]) {
+  int rc = need_points(c); if (rc) return rc;
+  DmkPointArrays& pa = *c->pts;
+  double* d_sum = c->d_scratch + DMK_SCRATCH_TMP;               // 81
+  double* d_mm = c->d_scratch + DMK_SCRATCH_TMP + 96;           // 2 values + 2 indices
+  if ((rc = dmk_points_tangent(c, dt, d_sum, d_dPdF))) return rc;
+  if (c->P > 1) { if (c->comm.allreduce_sum(c->comm.user, d_sum, 81)) { dmk_set_error("allreduce failed"); return DMK_ERR_STATE; } }
+  // extremes of the norm
+  double init[2] = {0.0, INFINITY};
+  DMK_CUDA_CHECK(cudaMemcpyAsync(d_mm, init, sizeof init, cudaMemcpyHostToDevice, c->stream));
+  dmk_minmax_value_kernel<<<148 * 4, 256, 0, c->stream>>>(pa.nrm, pa.n, d_mm);
+  c->launches++;
+  if (c->P > 1) {
+    // max over ranks of (vmax, -vmin)
+    double h[2];
+    DMK_CUDA_CHECK(cudaMemcpyAsync(h, d_mm, sizeof h, cudaMemcpyDeviceToHost, c->stream));
+    DMK_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    h[1] = -h[1];
+    DMK_CUDA_CHECK(cudaMemcpyAsync(d_mm, h, sizeof h, cudaMemcpyHostToDevice, c->stream));
+    if (c->comm.allreduce_max(c->comm.user, d_mm, 2)) { dmk_set_error("allreduce failed"); return DMK_ERR_STATE; }
+    DMK_CUDA_CHECK(cudaMemcpyAsync(h, d_mm, sizeof h, cudaMemcpyDeviceToHost, c->stream));
+    DMK_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    h[1] = -h[1];
+    DMK_CUDA_CHECK(cudaMemcpyAsync(d_mm, h, sizeof h, cudaMemcpyHostToDevice, c->stream));
+  }
+  double hv[2];
+  DMK_CUDA_CHECK(cudaMemcpyAsync(hv, d_mm, sizeof hv, cudaMemcpyDeviceToHost, c->stream));
+  DMK_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+  unsigned long long hidx[2] = {~0ULL, ~0ULL};
+  unsigned long long* d_idx = (unsigned long long*)(d_mm + 2);
+  DMK_CUDA_CHECK(cudaMemcpyAsync(d_idx, hidx, sizeof hidx, cudaMemcpyHostToDevice, c->stream));
+  const long long offset = (long long)c->z_off * c->nx * c->ny;
+  dmk_minmax_index_kernel<<<148 * 4, 256, 0, c->stream>>>(pa.nrm, pa.n, offset, hv[0], hv[1], 1.0e-12, d_idx);
+  c->launches++;
+  DMK_CUDA_CHECK(cudaMemcpyAsync(hidx, d_idx, sizeof hidx, cudaMemcpyDeviceToHost, c->stream));
+  DMK_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+  long long gidx[2] = {hidx[0] == ~0ULL ? -1 : (long long)hidx[0], hidx[1] == ~0ULL ? -1 : (long long)hidx[1]};
+  if (c->P > 1) {
+    // lowest global index over ranks: max of the negated index (exact in a double below 2^53)
+    double h[2] = {gidx[0] < 0 ? -9.0e15 : -(double)gidx[0], gidx[1] < 0 ? -9.0e15 : -(double)gidx[1]};
+    DMK_CUDA_CHECK(cudaMemcpyAsync(d_mm, h, sizeof h, cudaMemcpyHostToDevice, c->stream));
+    if (c->comm.allreduce_max(c->comm.user, d_mm, 2)) { dmk_set_error("allreduce failed"); return DMK_ERR_STATE; }
+    DMK_CUDA_CHECK(cudaMemcpyAsync(h, d_mm, sizeof h, cudaMemcpyDeviceToHost, c->stream));
+    DMK_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    gidx[0] = (long long)(-h[0]); gidx[1] = (long long)(-h[1]);
+  }
+  if (minmax_cells) { minmax_cells[0] = gidx[0]; minmax_cells[1] = gidx[1]; }
+  // dPdF of the two selected cells (owner computes, everyone receives through a sum)
+  double* d_two = c->d_scratch + DMK_SCRATCH_TMP + 112;          // 2 x 81 -> up to TMP+274: keep inside the MECH gap
+  DMK_CUDA_CHECK(cudaMemsetAsync(d_two, 0, 162 * sizeof(double), c->stream));
+  for (int k = 0; k < 2; k++) {
+    const long long loc = gidx[k] - offset;
+    if (loc >= 0 && loc < pa.n) { if ((rc = dmk_points_tangent_cell(c, dt, loc, d_two + 81 * k))) return rc; }
+  }
+  if (c->P > 1) { if (c->comm.allreduce_sum(c->comm.user, d_two, 162)) { dmk_set_error("allreduce failed"); return DMK_ERR_STATE; } }
+  double hs[81], ht[162], r[81];
+  DMK_CUDA_CHECK(cudaMemcpyAsync(hs, d_sum, sizeof hs, cudaMemcpyDeviceToHost, c->stream));
+  DMK_CUDA_CHECK(cudaMemcpyAsync(ht, d_two, sizeof ht, cudaMemcpyDeviceToHost, c->stream));
+  DMK_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+  if (C_volAvg) { for (int k = 0; k < 81; k++) r[k] = hs[k] * c->wgt; c2f3333(r, C_volAvg); }
+  if (C_minMaxAvg) { for (int k = 0; k < 81; k++) r[k] = 0.5 * (ht[k] + ht[81 + k]); c2f3333(r, C_minMaxAvg); }
+  return DMK_OK;
+}

@@ -1,0 +1,55 @@
+// Per-material-point constitutive state held in HBM and the device-side phase parameter tables.
+//
+// Replaces the Fortran module arrays of the reference's constitutive library (phase_mechanical_F/Fp/Fe/Lp/S and
+// their *0 twins, plasticState(ph)%state/state0: /root/reference/src/phase_mechanical.f90:183-260, phase.f90:26-46).
+// Layout: structure of arrays, component-major -- X[c * n + cell] -- so that the 32 lanes of a warp (32 neighbouring
+// cells along x) read and write 256 contiguous bytes per component.  Tensors are row-major (c = 3 i + j) internally;
+// the AoS record fields that cross the boundary (F in, P out) keep the reference's Fortran order (c = i + 3 j).
+// The intermediate configuration is fixed to Fi = I, Li = 0 on the device (no dilatational law is offered), which
+// removes Fi, Fi0, Li, Li0 from the per-point state without changing any result bit.
+#pragma once
+#include "ctx.h"
+#include "dmk_common.cuh"
+
+#define DMK_MAX_DEP (2 * DMK_MAX_SL + DMK_MAX_TW)      // dislotwin dependent state: Lambda_sl | Lambda_tw | tau_pass
+#define DMK_MAX_SYS (DMK_MAX_SL + DMK_MAX_TW)
+
+struct DmkDevPhase {
+  dmk_phase p;
+  // Q = C : P_nonSchmid as symmetric Voigt-6 (11,22,33,23,13,12), for the analytic Newton Jacobian of the Lp loop
+  double Q_pos[DMK_MAX_SL][6], Q_neg[DMK_MAX_SL][6], Q_tw[DMK_MAX_TW][6];
+  // strain-like Voigt projections of the (non-)Schmid tensors: pv[alpha] = P(ij) + P(ji) (shear), P(ii) (normal)
+  double pv_pos[DMK_MAX_SL][6], pv_neg[DMK_MAX_SL][6], pv_tw[DMK_MAX_TW][6];
+  int nonschmid;      // P_nS_neg != -P_nS_pos (cI with non-Schmid coefficients)
+  int n_dep;
+};
+
+struct DmkPointArrays {
+  long long n;                         // local cells
+  int n_phases;
+  int max_state, max_dep;
+  int* phase;                          // [n] phase index of each cell
+  double *F0, *F, *Fp0, *Fp, *Fe, *Lp0, *Lp;   // [9][n]
+  double *S0, *S;                      // [6][n] Voigt (11,22,33,23,13,12)
+  double *state0, *state;              // [max_state][n]
+  double* dep;                         // [max_dep][n]  (dislotwin only, else nullptr)
+  double* nrm;                         // [n] ||dPdF||^2 scratch of the tangent pass
+  DmkDevPhase* d_phases;               // device array
+  dmk_phase* h_phases;                 // host copy
+  int law_of_phase[DMK_MAX_PHASES], nstate_of_phase[DMK_MAX_PHASES], nsys_of_phase[DMK_MAX_PHASES];
+  unsigned long long* d_counters;      // 8: Lp iters, Li iters, stress calls, state iters, substeps, cutbacks, ill cells, -
+  int* d_ill;                          // device flag (OR of broken cells since the last reset)
+  long long n_cells_of_phase[DMK_MAX_PHASES];
+};
+
+struct DmkNumDev {
+  double r_cutback_min, r_cutback, r_increase, eps_rel_state;
+  int N_iter_state_max, N_iter_Lp_max;
+  double r_linesearch_Lp, eps_rel_Lp, eps_abs_Lp;
+  int f_update_jacobi_Lp;
+};
+
+int dmk_points_constitutive(dmk_ctx* c, const double* d_F, double* d_P, double dt);
+int dmk_points_tangent(dmk_ctx* c, double dt, double* d_Csum81 /*device, row-major sum over local cells*/,
+                       double* d_dPdF /*optional [n][81] Fortran order*/);
+int dmk_points_tangent_cell(dmk_ctx* c, double dt, long long cell, double* d_out81 /*row-major*/);

@@ -156,6 +156,8 @@ extern "C" int dmk_local_cells(const dmk_ctx* c, int* nz_local, int* z_offset, i
   return DMK_OK;
 }
 extern "C" int dmk_kernel_launches(const dmk_ctx* c, long long* n) { *n = c->launches; return DMK_OK; }
+extern "C" int dmk_sizeof_phase(void) { return (int)sizeof(dmk_phase); }
+extern "C" int dmk_sizeof_numerics(void) { return (int)sizeof(dmk_numerics); }
 extern "C" size_t dmk_fourier_doubles(const dmk_ctx* c) { return c->hat_records * DMK_NC * 2; }
 
 // ------------------------------------------------------------------------------------------------ transforms

@@ -135,3 +135,49 @@ class GridContext:
         L.check(self.lib.dmk_calculate_rate(self.ctx, C.c_int(int(heterogeneous)), _p(field0), _p(field),
                                             C.c_double(dt), _hp(av), _p(out)))
         return out
+
+    # ---- f_materialpoint_initDamask + f_discretization_init for the hot path
+    def material_init(self, material, numerics=None):
+        """material: solver_cpp_b200.material.Material for THIS slab (cell order x fastest)"""
+        from . import material as M
+        if self.lib.dmk_sizeof_phase() != C.sizeof(L.Phase) or self.lib.dmk_sizeof_numerics() != C.sizeof(L.Numerics):
+            raise L.DmkError('ctypes layout of dmk_phase / dmk_numerics does not match the library')
+        if material.phase_of_cell.size != self.n_local:
+            raise L.DmkError('material has %d cells, slab has %d' % (material.phase_of_cell.size, self.n_local))
+        self.numerics = numerics if numerics is not None else M.make_numerics()
+        self._material = material
+        L.check(self.lib.dmk_material_init(self.ctx, material.phases, C.c_int(len(material.phases)),
+                                           _hp(material.phase_of_cell), _hp(material.O_of_cell), C.byref(self.numerics)))
+
+    # ---- f_homogenization_mechanical_response (+ P of _response2)
+    def constitutive_response(self, F, dt, P=None):
+        P = self.new_field() if P is None else P
+        L.check(self.lib.dmk_constitutive_response(self.ctx, _p(F), _p(P), C.c_double(dt)))
+        return P
+
+    # ---- dPdF reductions of Spectral::constitutive_response (spectral.cpp:189-218)
+    def tangent_response(self, dt, materialise=False):
+        Cv, Cm = np.zeros(81), np.zeros(81)
+        cells = (C.c_longlong * 2)()
+        d = torch.empty((self.n_local, 81), dtype=torch.float64, device=self.device) if materialise else None
+        L.check(self.lib.dmk_tangent_response(self.ctx, C.c_double(dt), _hp(Cv), _hp(Cm), None if d is None else _p(d), cells))
+        out = (fortran_to_c3333(Cv), fortran_to_c3333(Cm), (cells[0], cells[1]))
+        return out + (d,) if materialise else out
+
+    def materialpoint_forward(self):
+        L.check(self.lib.dmk_materialpoint_forward(self.ctx))
+
+    def terminally_ill(self, reset=False):
+        f = C.c_int()
+        L.check(self.lib.dmk_terminally_ill(self.ctx, C.byref(f), C.c_int(int(reset))))
+        return bool(f.value)
+
+    def counters(self):
+        a = (C.c_longlong * 6)()
+        L.check(self.lib.dmk_get_counters(self.ctx, a))
+        return dict(zip(('Lp_iter', 'stress_calls', 'state_iter', 'substeps', 'cutbacks', 'ill_cells'), list(a)))
+
+    def get_state(self, name, comps):
+        out = np.zeros((self.n_local, comps))
+        L.check(self.lib.dmk_get_state(self.ctx, name.encode(), _hp(out), C.c_size_t(out.size)))
+        return out

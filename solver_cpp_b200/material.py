@@ -1,0 +1,346 @@
+"""material.yaml -> device phase tables (dmk_phase) and per-cell phase / orientation arrays.
+
+Host-side set-up the reference performs once in f_materialpoint_initDamask:
+  elastic Hooke C66(T)                /root/reference/src/phase_mechanical_elastic.f90:24-104
+  phenopowerlaw parameters            /root/reference/src/phase_mechanical_plastic_phenopowerlaw.f90:72-290
+  isotropic parameters                /root/reference/src/phase_mechanical_plastic_isotropic.f90:48-148
+  dislotwin parameters                /root/reference/src/phase_mechanical_plastic_dislotwin.f90:129-452
+  Fp0 = O, numerics                   /root/reference/src/phase_mechanical.f90:183-339
+  polynomials in (T - T_ref)          /root/reference/src/polynomials.f90:65-110
+Crystallography comes from the library's own C functions (csrc/crystal.cpp); nothing here touches oracle/."""
+import ctypes as C
+
+import numpy as np
+
+from . import lib as L
+
+T_ROOM = 293.15                # constants.f90:12
+K_B = 1.380649e-23             # constants.f90:13
+LAW_NONE, LAW_ISOTROPIC, LAW_PHENOPOWERLAW, LAW_DISLOTWIN = 0, 1, 2, 3
+
+
+def _ia(v):
+    a = np.ascontiguousarray(v, dtype=np.int32)
+    return a, a.ctypes.data_as(C.POINTER(C.c_int))
+
+
+def _da(v):
+    a = np.ascontiguousarray(v, dtype=np.float64)
+    return a, a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def _check(rc):
+    if rc != 0:
+        raise L.DmkError(L.load().dmk_last_error().decode())
+
+
+def schmid_slip(lattice, N_sl, non_schmid=None, sense=1):
+    n = int(np.sum(N_sl))
+    out = np.zeros((n, 9))
+    Ni, Np = _ia(N_sl)
+    ns, nsp = _da(non_schmid if non_schmid is not None and len(non_schmid) else [0.0])
+    ncoef = 0 if non_schmid is None else len(non_schmid)
+    _check(L.load().dmk_crystal_schmid_slip_ns(lattice.encode(), Np, len(Ni), nsp, ncoef, int(sense),
+                                                out.ctypes.data_as(C.POINTER(C.c_double))))
+    return out
+
+
+def schmid_twin(lattice, N_tw):
+    out = np.zeros((int(np.sum(N_tw)), 9))
+    Ni, Np = _ia(N_tw)
+    _check(L.load().dmk_crystal_schmid_twin(lattice.encode(), Np, len(Ni), out.ctypes.data_as(C.POINTER(C.c_double))))
+    return out
+
+
+def slip_normal(lattice, N_sl):
+    out = np.zeros((int(np.sum(N_sl)), 3))
+    Ni, Np = _ia(N_sl)
+    _check(L.load().dmk_crystal_slip_normal(lattice.encode(), Np, len(Ni), out.ctypes.data_as(C.POINTER(C.c_double))))
+    return out
+
+
+def interaction(kind, lattice, N_react, N_act, values):
+    out = np.zeros((int(np.sum(N_react)), int(np.sum(N_act))))
+    Nr, Nrp = _ia(N_react)
+    Na, Nap = _ia(N_act)
+    v, vp = _da(values)
+    _check(L.load().dmk_crystal_interaction(kind.encode(), lattice.encode(), Nrp, len(Nr), Nap, len(Na), vp, len(v),
+                                            out.ctypes.data_as(C.POINTER(C.c_double))))
+    return out
+
+
+def forest_projection(lattice, N_sl, f_edge):
+    n = int(np.sum(N_sl))
+    out = np.zeros((n, n))
+    Ni, Np = _ia(N_sl)
+    f, fp = _da(f_edge)
+    _check(L.load().dmk_crystal_forest_projection(lattice.encode(), Np, len(Ni), fp, out.ctypes.data_as(C.POINTER(C.c_double))))
+    return out
+
+
+def C66_twin(lattice, N_tw, C66):
+    out = np.zeros((int(np.sum(N_tw)), 36))
+    Ni, Np = _ia(N_tw)
+    c, cp = _da(np.asarray(C66).reshape(36))
+    _check(L.load().dmk_crystal_C66_twin(lattice.encode(), Np, len(Ni), cp, out.ctypes.data_as(C.POINTER(C.c_double))))
+    return out
+
+
+def twin_nucleation_pairs(N_tw):
+    out = np.zeros((int(np.sum(N_tw)), 2), dtype=np.int32)
+    Ni, Np = _ia(N_tw)
+    _check(L.load().dmk_crystal_twin_nucleation_pairs(Np, len(Ni), out.ctypes.data_as(C.POINTER(C.c_int))))
+    return out
+
+
+def qu2om(q):
+    qa, qp = _da(q)
+    out = np.zeros(9)
+    L.load().dmk_qu2om(qp, out.ctypes.data_as(C.POINTER(C.c_double)))
+    return out.reshape(3, 3)
+
+
+# ------------------------------------------------------------------------------------------------
+def poly_at(dct, key, T, var='T'):
+    """value of a (possibly temperature dependent) parameter: key, key,T, key,T^2 ... around T_ref"""
+    coef = [float(dct[key])]
+    if f'{key},{var}' in dct:
+        coef.append(float(dct[f'{key},{var}']))
+    for o in (2, 3, 4):
+        k = f'{key},{var}^{o}'
+        if k in dct:
+            coef += [0.0] * (o - len(coef)) + [float(dct[k])]
+    if len(coef) == 1:
+        return coef[0]
+    x = T - float(dct[f'{var}_ref'])
+    y = coef[-1]
+    for c in coef[-2::-1]:
+        y = y * x + c
+    return y
+
+
+def cubic_C66(C11, C12, C44):
+    """crystal_symmetrize_C66 for cubic lattices (crystal.f90:1680-1720)"""
+    Cm = np.zeros((6, 6))
+    Cm[:3, :3] = C12
+    Cm[np.arange(3), np.arange(3)] = C11
+    Cm[np.arange(3, 6), np.arange(3, 6)] = C44
+    return Cm
+
+
+def isotropic_mu(C66, bound='isostrain'):
+    b = bound.lower()
+    if b == 'isostrain':
+        return (C66[0, 0] - C66[0, 1] + C66[3, 3] * 3.0) / 5.0
+    if b == 'isostress':
+        return 5.0 / (4.0 / (C66[0, 0] - C66[0, 1]) + 3.0 / C66[3, 3])
+    raise ValueError(bound)
+
+
+def isotropic_nu(C66, bound='isostrain'):
+    b = bound.lower()
+    if b == 'isostrain':
+        K = np.sum(C66[:3, :3]) / 9.0
+    elif b == 'isostress':
+        K = 1.0 / np.sum(np.linalg.inv(C66)[:3, :3])
+    else:
+        raise ValueError(bound)
+    mu = isotropic_mu(C66, bound)
+    return (1.5 * K - mu) / (3.0 * K + mu)
+
+
+def _expand(vals, N):
+    return np.repeat(np.asarray(vals, float), N)
+
+
+def _set(field, values):
+    a = np.ctypeslib.as_array(field)
+    v = np.asarray(values)
+    if any(s > t for s, t in zip(v.shape, a.shape)):
+        raise L.DmkError('phase table overflow: %s into %s' % (v.shape, a.shape))
+    a[tuple(slice(0, s) for s in v.shape)] = v
+
+
+def make_phase(cfg, T=T_ROOM):
+    """one `phase:` entry of material.yaml -> lib.Phase"""
+    ph = L.Phase()
+    lattice = cfg['lattice']
+    if lattice not in ('cF', 'cI'):
+        raise L.DmkError('lattice %s is not offered on the device path (cF, cI)' % lattice)
+    mech = cfg['mechanical']
+    el = mech['elastic']
+    if el.get('type', 'Hooke') != 'Hooke':
+        raise L.DmkError('elastic type %s' % el.get('type'))
+    C66 = cubic_C66(poly_at(el, 'C_11', T), poly_at(el, 'C_12', T), poly_at(el, 'C_44', T))
+    _set(ph.C66, C66.reshape(36))
+    pl = mech.get('plastic')
+    kind = 'none' if pl is None else pl['type']
+    state_init, atol = np.zeros(0), np.zeros(0)
+    if kind == 'none':
+        ph.law = LAW_NONE
+    elif kind == 'isotropic':
+        ph.law = LAW_ISOTROPIC
+        ph.iso_xi_inf, ph.iso_dot_gamma_0, ph.iso_n = pl['xi_inf'], pl['dot_gamma_0'], pl['n']
+        ph.iso_h_0, ph.iso_h, ph.iso_M, ph.iso_h_ln = pl['h_0'], pl.get('h', 3.0), pl['M'], pl.get('h_ln', 0.0)
+        ph.iso_c_1, ph.iso_c_2, ph.iso_c_3, ph.iso_c_4 = (pl.get('c_1', 0.0), pl.get('c_2', 0.0), pl.get('c_3', 0.0),
+                                                          pl.get('c_4', 0.0))
+        ph.iso_a = pl['a']
+        ph.iso_dilatation = int(bool(pl.get('dilatation', False)))
+        state_init = np.array([float(pl['xi_0'])])
+        atol = np.array([float(pl.get('atol_xi', 1.0))])
+    elif kind == 'phenopowerlaw':
+        ph.law = LAW_PHENOPOWERLAW
+        N_sl, N_tw = list(pl.get('N_sl', [])), list(pl.get('N_tw', []))
+        ns, nt = int(np.sum(N_sl)), int(np.sum(N_tw))
+        ph.n_sl, ph.n_tw = ns, nt
+        xi0_sl, xi0_tw = np.zeros(0), np.zeros(0)
+        if ns:
+            one = np.ones(len(N_sl))
+            _set(ph.dot_gamma_0_sl, _expand(pl.get('dot_gamma_0_sl', one), N_sl))
+            _set(ph.n_sl_exp, _expand(pl.get('n_sl', one), N_sl))
+            _set(ph.a_sl, _expand(pl.get('a_sl', one), N_sl))
+            _set(ph.h_0_sl_sl, _expand(pl.get('h_0_sl-sl', 0 * one), N_sl))
+            _set(ph.c_1, _expand(pl.get('c_1', 0 * one), N_sl))
+            _set(ph.c_2, _expand(pl.get('c_2', one), N_sl))
+            xi0_sl = _expand(pl['xi_0_sl'], N_sl)
+            _set(ph.xi_inf_sl, _expand(pl['xi_inf_sl'], N_sl))
+            _set(ph.f_sat_sl_tw, _expand(pl.get('f_sat_sl-tw', 0 * one), N_sl))
+            _set(ph.h_sl_sl, interaction('sl-sl', lattice, N_sl, N_sl, pl['h_sl-sl']))
+            P = schmid_slip(lattice, N_sl)
+            _set(ph.P_sl, P)
+            if lattice == 'cI':
+                a_nS = pl.get('a_nonSchmid_110', [])
+                _set(ph.P_nS_pos, schmid_slip(lattice, N_sl, a_nS, +1))
+                _set(ph.P_nS_neg, schmid_slip(lattice, N_sl, a_nS, -1))
+            else:
+                _set(ph.P_nS_pos, P)
+                _set(ph.P_nS_neg, -P)
+        if nt:
+            one = np.ones(len(N_tw))
+            _set(ph.dot_gamma_0_tw, _expand(pl.get('dot_gamma_0_tw', one), N_tw))
+            _set(ph.n_tw_exp, _expand(pl.get('n_tw', one), N_tw))
+            _set(ph.c_3, _expand(pl.get('c_3', 0 * one), N_tw))
+            _set(ph.c_4, _expand(pl.get('c_4', 0 * one), N_tw))
+            _set(ph.h_0_tw_tw, _expand(pl.get('h_0_tw-tw', 0 * one), N_tw))
+            xi0_tw = _expand(pl['xi_0_tw'], N_tw)
+            _set(ph.gamma_char_tw, np.full(nt, 0.5 * np.sqrt(2.0)))          # crystal.f90:466-473 (cF, cI)
+            _set(ph.h_tw_tw, interaction('tw-tw', lattice, N_tw, N_tw, pl['h_tw-tw']))
+            _set(ph.P_tw, schmid_twin(lattice, N_tw))
+        if ns and nt:
+            _set(ph.h_0_tw_sl, _expand(pl.get('h_0_tw-sl', np.zeros(len(N_tw))), N_tw))
+            _set(ph.h_sl_tw, interaction('sl-tw', lattice, N_sl, N_tw, pl['h_sl-tw']))
+            _set(ph.h_tw_sl, interaction('tw-sl', lattice, N_tw, N_sl, pl['h_tw-sl']))
+        state_init = np.concatenate([xi0_sl, xi0_tw, np.zeros(ns), np.zeros(nt)])
+        atol = np.concatenate([np.full(ns + nt, float(pl.get('atol_xi', 1.0))),
+                               np.full(ns + nt, float(pl.get('atol_gamma', 1.0e-6)))])
+    elif kind == 'dislotwin':
+        ph.law = LAW_DISLOTWIN
+        N_sl, N_tw, N_tr = list(pl.get('N_sl', [])), list(pl.get('N_tw', [])), list(pl.get('N_tr', []))
+        ns, nt = int(np.sum(N_sl)), int(np.sum(N_tw))
+        if int(np.sum(N_tr)) > 0:
+            raise L.DmkError('dislotwin transformation systems (N_tr) are not offered on the device path')
+        if ns == 0:
+            raise L.DmkError('dislotwin without slip systems')
+        ph.n_sl, ph.n_tw = ns, nt
+        bound = pl.get('isotropic_bound', 'isostrain')
+        ph.dt_mu, ph.dt_nu = isotropic_mu(C66, bound), isotropic_nu(C66, bound)
+        ph.dt_kB_T = K_B * T
+        _set(ph.P_sl, schmid_slip(lattice, N_sl))
+        _set(ph.dt_n0_sl, slip_normal(lattice, N_sl))
+        ph.dt_extended = int(bool(pl.get('extend_dislocations', False)))
+        ph.dt_omit_dipoles = int(bool(pl.get('omit_dipoles', False)))
+        ph.dt_Q_cl = pl['Q_cl']
+        nf = len(N_sl)
+        f_edge = _expand(pl.get('f_edge', [0.5] * nf), N_sl)
+        rho_mob_0, rho_dip_0 = _expand(pl['rho_mob_0'], N_sl), _expand(pl['rho_dip_0'], N_sl)
+        b_sl = _expand(pl['b_sl'], N_sl)
+        _set(ph.dt_v_0, _expand(pl['v_0'], N_sl)); _set(ph.dt_b_sl, b_sl); _set(ph.dt_Q_sl, _expand(pl['Q_sl'], N_sl))
+        _set(ph.dt_i_sl, _expand(pl['i_sl'], N_sl)); _set(ph.dt_p, _expand(pl['p_sl'], N_sl))
+        _set(ph.dt_q, _expand(pl['q_sl'], N_sl)); _set(ph.dt_tau_0, _expand(pl['tau_0'], N_sl))
+        _set(ph.dt_B, _expand(pl.get('B', [0.0] * nf), N_sl)); _set(ph.dt_d_caron, b_sl * float(pl['D_a']))
+        _set(ph.h_sl_sl, interaction('sl-sl', lattice, N_sl, N_sl, pl['h_sl-sl']))
+        _set(ph.dt_forest, forest_projection(lattice, N_sl, f_edge))
+        fcc_nucleation = lattice == 'cF' and N_sl[0] == 12
+        ph.dt_omega = float(pl.get('omega', 1000.0)) * (12.0 if lattice in ('cF', 'hP') else 8.0)
+        if nt:
+            if not fcc_nucleation or len(N_tw) != 1:
+                raise L.DmkError('twinning in dislotwin needs cF with the 12 {111} slip systems')
+            _set(ph.P_tw, schmid_twin(lattice, N_tw))
+            _set(ph.gamma_char_tw, np.full(nt, 0.5 * np.sqrt(2.0)))
+            ph.dt_L_tw, ph.dt_i_tw = pl['L_tw'], pl['i_tw']
+            _set(ph.dt_b_tw, _expand(pl['b_tw'], N_tw)); _set(ph.dt_t_tw, _expand(pl['t_tw'], N_tw))
+            _set(ph.dt_r, _expand(pl['p_tw'], N_tw))
+            _set(ph.h_tw_tw, interaction('tw-tw', lattice, N_tw, N_tw, pl['h_tw-tw']))
+            _set(ph.h_sl_tw, interaction('sl-tw', lattice, N_sl, N_tw, pl['h_sl-tw']))
+            _set(ph.dt_pair, twin_nucleation_pairs(N_tw))
+            _set(ph.dt_C66_tw, C66_twin(lattice, N_tw, C66))
+            ph.dt_x_c, ph.dt_V_cs = pl['x_c'], pl['V_cs']
+        if nt or ph.dt_extended:
+            ph.dt_Gamma_sf = poly_at(pl, 'Gamma_sf', T)
+        ph.dt_gamma_0_sb = float(pl.get('gamma_0_sb', 0.0))
+        ph.dt_tau_sb = ph.dt_E_sb = ph.dt_p_sb = ph.dt_q_sb = 1.0
+        if ph.dt_gamma_0_sb > 0.0:
+            ph.dt_tau_sb, ph.dt_E_sb, ph.dt_p_sb, ph.dt_q_sb = pl['tau_sb'], pl['Q_sb'], pl['p_sb'], pl['q_sb']
+        ph.dt_D = pl['D']
+        state_init = np.concatenate([rho_mob_0, rho_dip_0, np.zeros(ns), np.zeros(nt)])
+        atol = np.concatenate([np.full(2 * ns, float(pl.get('atol_rho', 1.0))), np.full(ns, float(pl.get('atol_gamma', 1.0e-6))),
+                               np.full(nt, float(pl.get('atol_f_tw', 1.0e-6)))])
+    else:
+        raise L.DmkError('plastic law %s is not offered on the device path' % kind)
+    ph.n_state = len(state_init)
+    _set(ph.state_init, state_init)
+    _set(ph.atol, atol)
+    return ph
+
+
+NUMERICS_DEFAULTS = dict(r_cutback_min=1.0e-3, r_cutback=0.25, r_increase=1.5, eps_rel_state=1.0e-6, N_iter_state_max=20,
+                         N_iter_Lp_max=40, r_linesearch_Lp=0.5, eps_rel_Lp=1.0e-6, eps_abs_Lp=1.0e-8, f_update_jacobi_Lp=1,
+                         itmin=1, itmax=100, update_gamma=0, eps_abs_div=1.0e-4, eps_rel_div=5.0e-4, eps_abs_P=1.0e3,
+                         eps_rel_P=1.0e-3)
+
+
+def make_numerics(phase_mech=None, grid_mech=None):
+    """numerics.yaml `phase: mechanical:` and `solver: grid: mechanical:` dicts -> lib.Numerics (defaults:
+    phase_mechanical.f90:277-294, /root/reference/src/grid/config.h:50-58)"""
+    d = dict(NUMERICS_DEFAULTS)
+    src = dict(phase_mech or {})
+    pl = src.pop('plastic', {}) or {}
+    for k in ('r_cutback_min', 'r_cutback', 'r_increase', 'eps_rel_state', 'N_iter_state_max'):
+        if k in src:
+            d[k] = src[k]
+    for k in ('N_iter_Lp_max', 'r_linesearch_Lp', 'eps_rel_Lp', 'eps_abs_Lp', 'f_update_jacobi_Lp'):
+        if k in pl:
+            d[k] = pl[k]
+    if pl.get('integrator_state', 'FPI') != 'FPI':
+        raise L.DmkError('only the FPI state integrator is offered on the device path')
+    g = dict(grid_mech or {})
+    ren = dict(N_iter_min='itmin', N_iter_max='itmax')
+    for k, v in g.items():
+        k = ren.get(k, k)
+        if k in d:
+            d[k] = int(v) if k in ('itmin', 'itmax', 'update_gamma') else v
+    n = L.Numerics()
+    for k, v in d.items():
+        setattr(n, k, v)
+    return n
+
+
+class Material:
+    """phases + per-cell assignment for one z-slab"""
+
+    def __init__(self, material, material_at, T=T_ROOM):
+        names = list(material['phase'].keys())
+        self.phase_names = names
+        self.phases = (L.Phase * len(names))(*[make_phase(material['phase'][k], T) for k in names])
+        mats = material['material']
+        ph_of_mat = np.empty(len(mats), dtype=np.int32)
+        O_of_mat = np.empty((len(mats), 9))
+        for m, entry in enumerate(mats):
+            cons = entry['constituents']
+            if len(cons) != 1:
+                raise L.DmkError('only single-constituent (pass) homogenisation is offered')
+            ph_of_mat[m] = names.index(cons[0]['phase'])
+            O_of_mat[m] = qu2om(cons[0]['O']).reshape(9)
+        material_at = np.asarray(material_at).reshape(-1)
+        self.phase_of_cell = np.ascontiguousarray(ph_of_mat[material_at], dtype=np.int32)
+        self.O_of_cell = np.ascontiguousarray(O_of_mat[material_at])

@@ -1,0 +1,64 @@
+"""CPU tests: the product's per-point device functions (csrc/constitutive_dev.cuh, tangent_dev.cuh) compiled for the
+host by tests/host_twin (test infrastructure) and compared with the oracle.  This is the same source the CUDA kernels
+instantiate, so law / tangent logic errors show up here, on the GPU-less build box, before the -m gpu parity run."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), 'host_twin'))
+
+from oracle.constitutive import ConstitutiveOracle   # noqa: E402
+
+V6 = [0, 4, 8, 5, 2, 1]
+
+
+def _path(cells, n_inc, rng, rate):
+    nx, ny, nz = cells
+    fluct = rng.standard_normal((nz * ny * nx, 3, 3))
+    out = []
+    for inc in range(n_inc):
+        Fbar = np.eye(3) + np.diag([rate * 0.5 * (inc + 1), -0.3 * rate * 0.5 * (inc + 1), -0.3 * rate * 0.5 * (inc + 1)])
+        out.append(Fbar + 2.0e-4 * (inc + 1) * fluct)
+    return out
+
+
+@pytest.mark.parametrize('phase,rate', [('Al_pheno', 3.0e-3), ('Al_iso', 2.0e-3), ('TWIP', 7.0e-3), ('Al_elastic', 2.0e-3)])
+def test_twin_matches_oracle(phase, rate):
+    import twin
+    from solver_cpp_b200 import workloads as W, material as M
+    lib = twin.build()
+    cells = (4, 4, 3)
+    material, material_at, size = W.polycrystal(cells, 7, phase, 0)
+    o = ConstitutiveOracle(material, material_at)
+    m = M.Material(material, material_at)
+    num = M.make_numerics()
+    n = int(np.prod(cells))
+    ns = o.phases[0].n_state
+    nd = max(1, 2 * o.phases[0].n_sl + o.phases[0].n_tw)
+    dep = o.a['dep'][:, :nd].copy()
+    Lp = np.zeros((n, 9))
+    rng = np.random.default_rng(2)
+    worst = 0.0
+    for F in _path(cells, 4, rng, rate):
+        snap = o.snapshot()
+        o.mechanical_response(F.reshape(n, 9), 0.5)
+        P_o, dPdF_o = o.mechanical_response2(0.5, tangent=True)
+        for i in range(n):
+            r = twin.run_point(lib, m.phases[0], num, snap['F0'][i], F[i].reshape(9), snap['Fp0'][i], snap['Lp0'][i], Lp[i],
+                               snap['S0'][i][V6], snap['state0'][i][:max(ns, 1)], dep[i], 0.5, tangent=True)
+            Lp[i] = r['Lp']; dep[i] = r['dep']
+            if o.point_cutbacks[i]:
+                continue                                   # rounding-chaotic path, see test_oracle_golden.py
+            e = np.abs(r['P'] - o.a['P'][i]).max() / np.abs(o.a['P'][i]).max()
+            e = max(e, np.abs(r['Fp'] - o.a['Fp'][i]).max())
+            if ns:
+                atol = np.ctypeslib.as_array(o.phases[0].atol)[:ns]            # the integrator's own absolute state tolerance
+                e = max(e, (np.abs(r['state'][:ns] - o.a['state'][i, :ns]) / np.maximum(np.abs(o.a['state'][i, :ns]), atol)).max())
+            et = np.abs(r['dPdF'] - dPdF_o[i].reshape(81)).max() / np.abs(dPdF_o[i]).max()
+            assert e < 1e-9 and et < 1e-8, (phase, i, e, et)
+            worst = max(worst, e)
+        o.forward()
+    if phase != 'Al_elastic':
+        assert np.abs(o.a['Lp']).max() > 1e-6

@@ -70,3 +70,34 @@ def test_tie_rule_is_order_independent():
     assert sp.select_minmax(nrm) == (0, 0)
     nrm[17] *= 1.001; nrm[30] *= 0.999
     assert sp.select_minmax(nrm) == (17, 30)
+
+
+def test_cutback_path_is_rounding_sensitive(tmp_path):
+    """Documents a property of the reference ALGORITHM, not of any implementation: for a soft virgin material the first
+    trial sub-step overshoots (Lp ~ 1e27), and whether the following cut-back sub-step converges is decided by
+    rounding.  The oracle and the same source compiled with FMA contraction disagree on O(1%) of the cells by O(1e-3);
+    cells that never cut back agree to 1e-9.  GPU parity tests therefore exempt exactly those cells."""
+    import ctypes as C
+    import subprocess
+    from solver_cpp_b200 import workloads as W
+    import oracle.constitutive as oc
+    src = os.path.join(os.path.dirname(oc.__file__), 'constitutive.c')
+    lib = str(tmp_path / 'liboracle_fma.so')
+    subprocess.check_call(['gcc', '-O2', '-fopenmp', '-ffp-contract=fast', '-mfma', '-std=c11', '-shared', '-fPIC', '-o', lib, src, '-lm'],
+                          cwd=os.path.dirname(src))
+    cells = (16, 16, 8)
+    material, material_at, size = W.polycrystal(cells, 20, 'Cu_pheno', 0)
+    n = int(np.prod(cells))
+    rng = np.random.default_rng(11)
+    F = np.eye(3) + np.diag([5e-4, -1.5e-4, -1.5e-4]) + 1e-4 * rng.standard_normal((n, 3, 3))
+    a = oc.ConstitutiveOracle(material, material_at)
+    b = oc.ConstitutiveOracle(material, material_at)
+    b.lib = C.CDLL(lib)
+    b.lib.orc_mechanical_response.restype = C.c_int
+    a.mechanical_response(F.reshape(n, 9), 0.5)
+    b.mechanical_response(F.reshape(n, 9), 0.5)
+    err = np.abs(a.a['P'] - b.a['P']).max(1) / np.abs(a.a['P']).max(1)
+    quiet = (a.point_cutbacks == 0) & (b.point_cutbacks == 0)
+    assert err[quiet].max(initial=0.0) < 1e-9
+    assert (a.point_cutbacks > 0).any()
+    assert (err >= 1e-9).mean() < 0.1
