@@ -143,7 +143,9 @@ int dmk_constitutive_response(dmk_ctx* ctx, const double* d_F, double* d_P, doub
 int dmk_tangent_response(dmk_ctx* ctx, double dt, double* C_volAvg, double* C_minMaxAvg, double* d_dPdF,
                          long long minmax_cells[2]);
 int dmk_materialpoint_forward(dmk_ctx* ctx);                       /* f_materialpoint_forward */
-int dmk_get_state(dmk_ctx* ctx, const char* name, double* host_out, size_t n_doubles); /* "Fp","S","state",... */
+/* host copy, cell-major [cell][component]: "F","F0","Fp","Fp0","Fe","Lp","Lp0","S","S0" (row-major 3x3), "state","state0",
+ * "dep", and "cutbacks" (sub-step cut-backs of each cell in the last response call) */
+int dmk_get_state(dmk_ctx* ctx, const char* name, double* host_out, size_t n_doubles);
 int dmk_get_counters(dmk_ctx* ctx, long long counters[6]);         /* Lp iters, stress calls, state iters, substeps, cutbacks, ill */
 int dmk_terminally_ill(dmk_ctx* ctx, int* flag, int reset);
 
@@ -167,6 +169,7 @@ int dmk_calculate_rate(dmk_ctx* ctx, int heterogeneous, const double* d_field0, 
  * MechSolverBasic::{init, forward, calculate_solution, form_residual, converged} (mech_solver_basic.cpp) with the
  * solution vector, its history (NGMRES, m = 30) and all work fields resident in HBM. */
 int dmk_mech_init(dmk_ctx* ctx, const long long* gamma_pair_cells /* NULL or 2 global cell indices */);
+/* BC values / masks / R: row-major 3x3 (index 3*i+j); mask 1 = 'x' (component not controlled) */
 int dmk_mech_forward(dmk_ctx* ctx, int cut_back, int guess, double dt, double dt_old, double t_remaining,
                      const char* deformation_type, const double* deformation_values, const int* deformation_mask,
                      const char* stress_type, const double* stress_values, const int* stress_mask,
@@ -177,7 +180,13 @@ int dmk_mech_form_residual_host(dmk_ctx* ctx, const double* F, double* r); /* sa
 int dmk_mech_get(dmk_ctx* ctx, const char* what, double* out, size_t n);   /* "P_av","F_aim","err_div","err_BC","C_volAvg",... */
 int dmk_mech_get_field(dmk_ctx* ctx, const char* what, double* host_out);  /* "F","P","F_lastInc": local slab, 9*n doubles */
 int dmk_mech_set_field(dmk_ctx* ctx, const char* what, const double* host_in);
-int dmk_mech_eval_log(dmk_ctx* ctx, double* out, size_t max_rows, size_t* n_rows); /* per evaluation: 9 P_av, err_div, err_BC, total_iter */
+int dmk_mech_device_field(dmk_ctx* ctx, const char* what, double** d_ptr);  /* device pointer of "F","F_lastInc","F_dot","r" */
+int dmk_mech_copy_field(dmk_ctx* ctx, const char* what, double* d_dst);      /* device-to-device copy of a solver field */
+/* test aid: keep host copies of the F handed to and the r returned by every residual evaluation of the solver */
+int dmk_mech_capture(dmk_ctx* ctx, int enable);
+int dmk_mech_get_capture(dmk_ctx* ctx, double* F_out, double* r_out, size_t max_evals, size_t* n_evals);
+int dmk_mech_eval_log(dmk_ctx* ctx, double* out, size_t max_rows, size_t* n_rows); /* per evaluation: 9 P_av (row-major), err_div, err_BC, total_iter */
+int dmk_mech_reports(dmk_ctx* ctx, double* out, size_t max_rows, size_t* n_rows);  /* per convergence check: total_iter, err_div, divTol, err_BC, BCTol, reason */
 
 /* ------------------------------------------------------------------ (1) Fortran-named drop-in symbols */
 int dmk_bind_global(dmk_ctx* ctx);

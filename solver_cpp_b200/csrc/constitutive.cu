@@ -44,8 +44,10 @@ __global__ void __launch_bounds__(DMK_PT_THREADS) dmk_constitutive_kernel(DmkPoi
     for (int a = 0; a < 6; a++) { S0[a] = pa.S0[a * n + i]; p.S[a] = S0[a]; }
     for (int k = 0; k < ns; k++) { state0[k] = pa.state0[k * n + i]; p.st[k] = state0[k]; }
     if constexpr (ND > 0) { const int nd = p.ph->n_dep; for (int k = 0; k < nd; k++) p.dep[k] = pa.dep[k * n + i]; }
+    const unsigned cb0 = cnt.cutbacks;
     const bool ok = constitutive_point(p, num, F0, Ft, Fp0, Lp0, S0, state0, Dt, cnt);
     if (!ok) ill = 1;
+    pa.cutbacks[i] = (int)(cnt.cutbacks - cb0);
 #pragma unroll
     for (int a = 0; a < 9; a++) {
       pa.F[a * n + i] = Ft[a]; pa.Fp[a * n + i] = p.Fp[a]; pa.Lp[a * n + i] = p.Lp[a]; pa.Fe[a * n + i] = p.Fe[a];
@@ -231,7 +233,7 @@ void dmk_points_teardown(dmk_ctx* c) {
   cudaFree(pa->phase); cudaFree(pa->F0); cudaFree(pa->F); cudaFree(pa->Fp0); cudaFree(pa->Fp); cudaFree(pa->Fe);
   cudaFree(pa->Lp0); cudaFree(pa->Lp); cudaFree(pa->S0); cudaFree(pa->S); cudaFree(pa->state0); cudaFree(pa->state);
   if (pa->dep) cudaFree(pa->dep);
-  cudaFree(pa->nrm); cudaFree(pa->d_phases); cudaFree(pa->d_counters); cudaFree(pa->d_ill);
+  cudaFree(pa->nrm); cudaFree(pa->cutbacks); cudaFree(pa->d_phases); cudaFree(pa->d_counters); cudaFree(pa->d_ill);
   delete[] pa->h_phases;
   delete pa;
   c->pts = nullptr;
@@ -303,6 +305,8 @@ extern "C" int dmk_material_init(dmk_ctx* c, const dmk_phase* phases, int n_phas
       (rc = dalloc(&pa->nrm, n))) return rc;
   if (max_dep > 0) { if ((rc = dalloc(&pa->dep, (size_t)max_dep * n))) return rc; DMK_CUDA_CHECK(cudaMemset(pa->dep, 0, (size_t)max_dep * n * sizeof(double))); }
   DMK_CUDA_CHECK(cudaMalloc((void**)&pa->phase, n * sizeof(int)));
+  DMK_CUDA_CHECK(cudaMalloc((void**)&pa->cutbacks, n * sizeof(int)));
+  DMK_CUDA_CHECK(cudaMemset(pa->cutbacks, 0, n * sizeof(int)));
   DMK_CUDA_CHECK(cudaMalloc((void**)&pa->d_phases, n_phases * sizeof(DmkDevPhase)));
   DMK_CUDA_CHECK(cudaMalloc((void**)&pa->d_counters, 8 * sizeof(unsigned long long)));
   DMK_CUDA_CHECK(cudaMalloc((void**)&pa->d_ill, sizeof(int)));
@@ -352,6 +356,7 @@ extern "C" int dmk_constitutive_response(dmk_ctx* c, const double* d_F, double* 
 
 extern "C" int dmk_materialpoint_forward(dmk_ctx* c) {
   int rc = need_points(c); if (rc) return rc;
+  if (c->mech && (rc = dmk_mech_before_point_forward(c))) return rc;     // dPdF must see the pre-forward *0 state
   dmk_forward_copy_kernel<<<148 * 8, 256, 0, c->stream>>>(*c->pts);
   c->launches++;
   DMK_CUDA_CHECK(cudaGetLastError());
@@ -399,6 +404,14 @@ extern "C" int dmk_get_state(dmk_ctx* c, const char* name, double* out, size_t n
   else if (s == "S") { src = pa.S; comps = 6; voigt = true; } else if (s == "S0") { src = pa.S0; comps = 6; voigt = true; }
   else if (s == "state") { src = pa.state; comps = pa.max_state; } else if (s == "state0") { src = pa.state0; comps = pa.max_state; }
   else if (s == "dep") { src = pa.dep; comps = pa.max_dep; }
+  if (s == "cutbacks") {
+    if (n_doubles < (size_t)n) { dmk_set_error("dmk_get_state: buffer too small"); return DMK_ERR_ARG; }
+    std::vector<int> ib(n);
+    DMK_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    DMK_CUDA_CHECK(cudaMemcpy(ib.data(), pa.cutbacks, n * sizeof(int), cudaMemcpyDeviceToHost));
+    for (long long i = 0; i < n; i++) out[i] = (double)ib[i];
+    return DMK_OK;
+  }
   if (!src) { dmk_set_error("dmk_get_state: unknown or empty array '%s'", s.c_str()); return DMK_ERR_ARG; }
   const int out_comps = voigt ? 9 : comps;
   if (n_doubles < (size_t)out_comps * n) { dmk_set_error("dmk_get_state: buffer too small (%zu < %lld)", n_doubles, (long long)out_comps * n); return DMK_ERR_ARG; }
@@ -414,7 +427,7 @@ extern "C" int dmk_get_state(dmk_ctx* c, const char* name, double* out, size_t n
 // ---- min/max selection of ||dPdF||^2 with the shared tie rule (oracle/spectral.py select_minmax)
 __global__ void dmk_minmax_value_kernel(const double* __restrict__ nrm, long long n, double* __restrict__ out2) {
   __shared__ double smx[8], smn[8];
-  double mx = -INFINITY, mn = INFINITY;
+  double mx = 0.0, mn = INFINITY;            // norms are >= 0; an idle block must not contribute -inf (bit pattern order)
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const double v = nrm[i]; mx = fmax(mx, v); mn = fmin(mn, v);
   }

@@ -34,6 +34,7 @@ struct DmkPointArrays {
   double *state0, *state;              // [max_state][n]
   double* dep;                         // [max_dep][n]  (dislotwin only, else nullptr)
   double* nrm;                         // [n] ||dPdF||^2 scratch of the tangent pass
+  int* cutbacks;                       // [n] sub-step cut-backs of each cell in the last response call (diagnostic)
   DmkDevPhase* d_phases;               // device array
   dmk_phase* h_phases;                 // host copy
   int law_of_phase[DMK_MAX_PHASES], nstate_of_phase[DMK_MAX_PHASES], nsys_of_phase[DMK_MAX_PHASES];

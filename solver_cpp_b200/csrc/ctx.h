@@ -53,6 +53,8 @@ void dmk_mech_teardown(dmk_ctx* c);
 int dmk_fft_forward_internal(dmk_ctx* c, const double* d_real);
 int dmk_fft_backward_internal(dmk_ctx* c, double* d_real, double scale);
 int dmk_gamma_internal(dmk_ctx* c);     // fused z pass on c->bufA using c->d_dc, accumulating into c->d_div
+double dmk_finish_div(dmk_ctx* c, double raw_sum);
+int dmk_mech_before_point_forward(dmk_ctx* c);   // computes the pending tangent reductions before state0 <- state
 
 // Fortran-order <-> row-major helpers for small host tensors
 static inline void f2c33(const double* f, double* c) { for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) c[3 * i + j] = f[i + 3 * j]; }
