@@ -110,6 +110,12 @@ int dmk_set_comm(dmk_ctx* ctx, const dmk_comm* comm);
 int dmk_synchronize(dmk_ctx* ctx);
 int dmk_local_cells(const dmk_ctx* ctx, int* nz_local, int* z_offset, int* ny_local, int* y_offset);
 int dmk_kernel_launches(const dmk_ctx* ctx, long long* n);        /* kernels launched so far by this context */
+/* CUDA-event section timing of residual evaluations: out[0..4] = accumulated ms of {constitutive kernel, P sum + aim,
+ * forward FFT x+y, fused z / Gamma / divergence pass, inverse FFT y+x}, out[5] = evaluations accumulated */
+int dmk_set_profiling(dmk_ctx* ctx, int enable);
+int dmk_get_profile(dmk_ctx* ctx, double out[6], int reset);
+/* measured FP64 FMA throughput of the device (register-resident DFMA chains), TFLOP/s: the constitutive roofline */
+int dmk_fp64_peak(double* tflops);
 int dmk_sizeof_phase(void);                                       /* sizeof(dmk_phase), for binding checks */
 int dmk_sizeof_numerics(void);
 
@@ -175,6 +181,9 @@ int dmk_mech_forward(dmk_ctx* ctx, int cut_back, int guess, double dt, double dt
                      const char* stress_type, const double* stress_values, const int* stress_mask,
                      const double* R /* 9 row-major */);
 int dmk_mech_calculate_solution(dmk_ctx* ctx, dmk_solution_state* out);
+int dmk_mech_prepare(dmk_ctx* ctx);   /* the pre-SNES part of calculate_solution: tangent reductions, masked compliance */
+int dmk_mech_set(dmk_ctx* ctx, const char* what, const double* values9);   /* "F_aim","F_aim_lastInc","P_aim" (Fortran order) */
+int dmk_mech_set_field_device(dmk_ctx* ctx, const char* what, const double* d_src); /* "F","F_lastInc","F_dot" */
 int dmk_mech_form_residual(dmk_ctx* ctx, const double* d_F, double* d_r);  /* one evaluation, device pointers */
 int dmk_mech_form_residual_host(dmk_ctx* ctx, const double* F, double* r); /* same with host buffers (H2D + D2H) */
 int dmk_mech_get(dmk_ctx* ctx, const char* what, double* out, size_t n);   /* "P_av","F_aim","err_div","err_BC","C_volAvg",... */

@@ -19,6 +19,8 @@ struct dmk_ctx {
   cudaStream_t stream; bool own_stream;
   dmk_comm comm; bool has_comm;
   long long launches;
+  // optional section timing of one residual evaluation (dmk_set_profiling): events on the context's stream
+  bool profiling; cudaEvent_t ev[8]; double prof_ms[8]; long long prof_n;
 
   // ---- spectral
   DmkFftPlan plx, ply, plz;

@@ -260,25 +260,36 @@ static int upload_block(dmk_ctx* c) {
 }
 
 // evaluates r = Gamma * P(F) with all side effects of form_residual except the iteration bookkeeping
+#define PROF(i) do { if (c->profiling) cudaEventRecord(c->ev[i], c->stream); } while (0)
 static int evaluate(dmk_ctx* c, const double* d_F, double* d_r) {
   DmkMech* m = c->mech;
   int rc;
+  PROF(0);
   if ((rc = dmk_points_constitutive(c, d_F, d_r, m->dt))) return rc;
+  PROF(1);
   m->tangent_stale = true; m->tangent_dt = m->dt;
   if ((rc = dmk_sum_records(c, d_r, c->n_local, m->d_blk + B_SUM))) return rc;
   if (c->P > 1) { if (c->comm.allreduce_sum(c->comm.user, m->d_blk + B_SUM, 9)) { dmk_set_error("allreduce failed"); return DMK_ERR_STATE; } }
   dmk_mech_aim_kernel<<<1, 32, 0, c->stream>>>(m->d_blk, c->wgt, c->d_dc, c->d_div);
   c->launches++;
+  PROF(2);
   if ((rc = dmk_fft_forward_internal(c, d_r))) return rc;
+  PROF(3);
   if ((rc = dmk_gamma_internal(c))) return rc;
+  PROF(4);
   if (c->P > 1) { if (c->comm.allreduce_sum(c->comm.user, c->d_div, 1)) { dmk_set_error("allreduce failed"); return DMK_ERR_STATE; } }
   if ((rc = dmk_fft_backward_internal(c, d_r, 1.0))) return rc;
+  PROF(5);
   dmk_mech_collect_kernel<<<1, 32, 0, c->stream>>>(m->d_blk, c->d_div);
   c->launches++;
   DMK_CUDA_CHECK(cudaMemcpyAsync(c->h_pinned, m->d_blk + B_OUT, 20 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
   DMK_CUDA_CHECK(cudaStreamSynchronize(c->stream));
   for (int a = 0; a < 9; a++) { m->P_av[a] = c->h_pinned[a]; m->F_aim[a] = c->h_pinned[9 + a]; }
   m->err_BC = c->h_pinned[18]; m->div_raw = c->h_pinned[19];
+  if (c->profiling) {      // sections: constitutive | P sum + aim | forward FFT (x, y) | fused z + Gamma + div | inverse FFT (y, x)
+    for (int i = 0; i < 5; i++) { float ms = 0.f; cudaEventElapsedTime(&ms, c->ev[i], c->ev[i + 1]); c->prof_ms[i] += ms; }
+    c->prof_n++;
+  }
   m->err_div = dmk_finish_div(c, m->div_raw);
   return DMK_OK;
 }
@@ -554,6 +565,36 @@ extern "C" int dmk_mech_calculate_solution(dmk_ctx* c, dmk_solution_state* out) 
   if ((rc = dmk_terminally_ill(c, &ill, 1))) return rc;
   if (out) { out->converged = m->snes_reason > 0; out->required_iterations = m->total_iter; out->terminally_ill = ill; out->stag_converged = 1; }
   for (int a = 0; a < 9; a++) if (m->stress_mask[a]) m->P_aim[a] = m->P_av[a];
+  return DMK_OK;
+}
+
+// what calculate_solution does before SNESSolve: tangent reductions, masked compliance, optional Gamma update
+extern "C" int dmk_mech_prepare(dmk_ctx* c) {
+  int rc = need_mech(c); if (rc) return rc;
+  DmkMech* m = c->mech;
+  if ((rc = ensure_tangent(c))) return rc;
+  if ((rc = masked_compliance_rm(m->C_volAvg, m->R, m->stress_mask, m->S))) return rc;
+  if (c->num.update_gamma) { double Cf[81]; c2f3333(m->C_minMaxAvg, Cf); if ((rc = dmk_update_gamma(c, Cf))) return rc; }
+  return DMK_OK;
+}
+// 3x3 host values in Fortran order: "F_aim", "F_aim_lastInc", "P_aim"
+extern "C" int dmk_mech_set(dmk_ctx* c, const char* what, const double* values) {
+  int rc = need_mech(c); if (rc) return rc;
+  DmkMech* m = c->mech;
+  const std::string w(what ? what : "");
+  double* dst = w == "F_aim" ? m->F_aim : w == "F_aim_lastInc" ? m->F_aim_lastInc : w == "P_aim" ? m->P_aim : nullptr;
+  if (!dst) { dmk_set_error("dmk_mech_set: unknown quantity '%s'", w.c_str()); return DMK_ERR_ARG; }
+  f2c33(values, dst);
+  return DMK_OK;
+}
+extern "C" int dmk_mech_set_field_device(dmk_ctx* c, const char* what, const double* d_src) {
+  int rc = need_mech(c); if (rc) return rc;
+  double* f = nullptr;
+  const std::string w(what ? what : "");
+  if (w == "F") f = c->mech->F; else if (w == "F_lastInc") f = c->mech->F_lastInc; else if (w == "F_dot") f = c->mech->F_dot;
+  if (!f) { dmk_set_error("dmk_mech_set_field_device: unknown field '%s'", w.c_str()); return DMK_ERR_ARG; }
+  DMK_CUDA_CHECK(cudaMemcpyAsync(f, d_src, c->mech->n9 * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+  DMK_CUDA_CHECK(cudaStreamSynchronize(c->stream));
   return DMK_OK;
 }
 

@@ -136,6 +136,7 @@ extern "C" void dmk_destroy(dmk_ctx* c) {
   dmk_spectral_teardown(c);
   if (c->m_F0) cudaFreeHost(c->m_F0); if (c->m_F) cudaFreeHost(c->m_F); if (c->m_P) cudaFreeHost(c->m_P);
   if (c->m_dPdF) cudaFreeHost(c->m_dPdF); if (c->m_ill) cudaFreeHost(c->m_ill);
+  if (c->ev[0]) for (int i = 0; i < 8; i++) cudaEventDestroy(c->ev[i]);
   if (c->own_stream) cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -156,6 +157,19 @@ extern "C" int dmk_local_cells(const dmk_ctx* c, int* nz_local, int* z_offset, i
   return DMK_OK;
 }
 extern "C" int dmk_kernel_launches(const dmk_ctx* c, long long* n) { *n = c->launches; return DMK_OK; }
+// section timing of residual evaluations: out[0..4] = accumulated ms of {constitutive, P sum + aim, forward FFT x+y,
+// fused z/Gamma/div pass, inverse FFT y+x}, out[5] = evaluations accumulated; reset != 0 clears the accumulators
+extern "C" int dmk_set_profiling(dmk_ctx* c, int enable) {
+  if (enable && !c->ev[0]) { for (int i = 0; i < 8; i++) DMK_CUDA_CHECK(cudaEventCreate(&c->ev[i])); }
+  c->profiling = enable != 0;
+  return DMK_OK;
+}
+extern "C" int dmk_get_profile(dmk_ctx* c, double out[6], int reset) {
+  for (int i = 0; i < 5; i++) out[i] = c->prof_ms[i];
+  out[5] = (double)c->prof_n;
+  if (reset) { for (int i = 0; i < 8; i++) c->prof_ms[i] = 0.0; c->prof_n = 0; }
+  return DMK_OK;
+}
 extern "C" int dmk_sizeof_phase(void) { return (int)sizeof(dmk_phase); }
 extern "C" int dmk_sizeof_numerics(void) { return (int)sizeof(dmk_numerics); }
 extern "C" size_t dmk_fourier_doubles(const dmk_ctx* c) { return c->hat_records * DMK_NC * 2; }

@@ -181,3 +181,23 @@ class GridContext:
         out = np.zeros((self.n_local, comps))
         L.check(self.lib.dmk_get_state(self.ctx, name.encode(), _hp(out), C.c_size_t(out.size)))
         return out
+
+    # ---- measurement aids
+    def set_profiling(self, enable=True):
+        L.check(self.lib.dmk_set_profiling(self.ctx, C.c_int(int(enable))))
+
+    def get_profile(self, reset=True):
+        out = (C.c_double * 6)()
+        L.check(self.lib.dmk_get_profile(self.ctx, out, C.c_int(int(reset))))
+        keys = ('constitutive_ms', 'reduce_aim_ms', 'fft_forward_ms', 'gamma_zpass_ms', 'fft_inverse_ms', 'evaluations')
+        return dict(zip(keys, list(out)))
+
+    def fp64_peak_tflops(self):
+        v = C.c_double()
+        L.check(self.lib.dmk_fp64_peak(C.byref(v)))
+        return v.value
+
+    # ---- multi-GPU: collective callbacks (solver_cpp_b200.parallel.TorchComm)
+    def set_comm(self, comm):
+        self._comm_keepalive = comm
+        L.check(self.lib.dmk_set_comm(self.ctx, C.byref(comm.struct)))

@@ -107,6 +107,20 @@ class MechSolverBasic:
         L.check(self.lib.dmk_mech_form_residual_host(self.ctx, _hp(F_host), _hp(r_host)))
         return r_host
 
+    def prepare_evaluation(self):
+        """the pre-SNES part of calculate_solution (tangent reductions, masked compliance)"""
+        L.check(self.lib.dmk_mech_prepare(self.ctx))
+
+    def set_history(self, F=None, F_lastInc=None, F_aim=None, F_aim_lastInc=None, P_aim=None):
+        """restart-style injection of solver state (device tensors for fields, natural 3x3 for aims)"""
+        for name, t in (('F', F), ('F_lastInc', F_lastInc)):
+            if t is not None:
+                L.check(self.lib.dmk_mech_set_field_device(self.ctx, name.encode(), _p(t)))
+        for name, a in (('F_aim', F_aim), ('F_aim_lastInc', F_aim_lastInc), ('P_aim', P_aim)):
+            if a is not None:
+                v = np.ascontiguousarray(np.asarray(a, float).T.reshape(9))
+                L.check(self.lib.dmk_mech_set(self.ctx, name.encode(), _hp(v)))
+
     # ---- state access
     def get(self, what, n=1):
         out = np.zeros(n)

@@ -1,0 +1,93 @@
+"""z-slab decomposition and the collective callbacks of the multi-GPU path (one process per GPU).
+
+Decomposition as the reference's DiscretizationGrid (/root/reference/src/grid/discretization_grid.cpp:40-56, FFTW-MPI
+default blocks): real space is split along z, Fourier space along y (FFTW_MPI_TRANSPOSED_OUT).  The library asks for
+three collectives through the dmk_comm callback table (include/dmk_grid.h): the all-to-all of the distributed-FFT
+transpose and sum / max all-reduces of a few doubles.  Here they are bound to torch.distributed (NCCL over
+NVLink/NVSwitch on GPUs; gloo on CPU tensors for the host-logic tests)."""
+import ctypes as C
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import lib as L
+
+
+def slab_range(nz, world_size, rank):
+    """contiguous z-range [z0, z1) of `rank`; requires nz % world_size == 0 like the library"""
+    if nz % world_size:
+        raise L.DmkError('nz = %d is not divisible by the number of ranks (%d)' % (nz, world_size))
+    n = nz // world_size
+    return rank * n, (rank + 1) * n
+
+
+def exchange_layout(nxr, ny, nz, world_size):
+    """shapes of the transpose buffers: send [peer][z_loc][ky_loc][kx][9] complex, received [z][ky_loc][kx][9]"""
+    return (world_size, nz // world_size, ny // world_size, nxr, 9), (nz, ny // world_size, nxr, 9)
+
+
+class _DevPtr:
+    """zero-copy view of raw device memory for torch.as_tensor (CUDA array interface v2)"""
+
+    def __init__(self, ptr, n_doubles):
+        self.__cuda_array_interface__ = {'shape': (n_doubles,), 'typestr': '<f8', 'data': (int(ptr), False), 'version': 2}
+
+
+def _view(ptr, n_doubles, device):
+    return torch.as_tensor(_DevPtr(ptr, n_doubles), device=device)
+
+
+class TorchComm:
+    """dmk_comm callbacks on torch.distributed; keeps the ctypes thunks alive"""
+
+    def __init__(self, world_size, rank, group=None):
+        self.world_size, self.rank, self.group = world_size, rank, group
+        self.device = torch.device('cuda', torch.cuda.current_device())
+
+        def alltoall(user, d_send, d_recv, bytes_per_peer):
+            try:
+                n = bytes_per_peer // 8 * self.world_size
+                send, recv = _view(d_send, n, self.device), _view(d_recv, n, self.device)
+                dist.all_to_all_single(recv, send, group=self.group)
+                return 0
+            except Exception as e:                                   # surfaced as rc != 0 in the library
+                print('alltoall callback failed:', e)
+                return 1
+
+        def allreduce(op):
+            def f(user, d_buf, n):
+                try:
+                    dist.all_reduce(_view(d_buf, n, self.device), op=op, group=self.group)
+                    return 0
+                except Exception as e:
+                    print('allreduce callback failed:', e)
+                    return 1
+            return f
+        self._a2a = L.ALLTOALL_FN(alltoall)
+        self._sum = L.ALLREDUCE_FN(allreduce(dist.ReduceOp.SUM))
+        self._max = L.ALLREDUCE_FN(allreduce(dist.ReduceOp.MAX))
+        self.struct = L.Comm(None, self._a2a, self._sum, self._max)
+
+
+def make_comm(world_size, rank, group=None):
+    return TorchComm(world_size, rank, group)
+
+
+def alltoall_transpose_host(send, group=None):
+    """the transpose exchange on a CPU tensor (gloo): send [peer][...] -> recv [peer][...]; host-logic twin of the
+    device path used by the world_size-2 tests"""
+    recv = torch.empty_like(send)
+    dist.all_to_all_single(recv.view(-1), send.contiguous().view(-1), group=group) if dist.get_backend(group) != 'gloo' else \
+        _gloo_alltoall(recv, send, group)
+    return recv
+
+
+def _gloo_alltoall(recv, send, group):
+    # gloo has no all_to_all_single for CPU tensors in every build: emulate with P scatters (test sizes only)
+    P = dist.get_world_size(group)
+    me = dist.get_rank(group)
+    for src in range(P):
+        out = recv[src]
+        dist.scatter(out, [send[p].contiguous() for p in range(P)] if me == src else None, src=src, group=group)
+    return recv

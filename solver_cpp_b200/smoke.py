@@ -31,3 +31,33 @@ def run(verbose=True):
     assert err <= 1e-11, err
     if verbose:
         print('smoke: spectral residual tail 16^3 ok, rel err %.2e, launches %d' % (err, g.kernel_launches()))
+    run_residual(verbose)
+
+
+def run_residual(verbose=True):
+    """one residual evaluation (constitutive update + homogenisation + FFT + Gamma/div + inverse FFT) of the 16^3
+    phenopowerlaw configuration through the C ABI, against the oracle's form_residual"""
+    from . import mech, workloads as W
+    from oracle.solver import MechSolverBasicOracle, parse_load as oparse      # checker
+    from oracle import spectral as osp
+    cells = (16, 16, 16)
+    material, material_at, size = W.polycrystal(cells, 20, 'Al_pheno', 0)
+    s = mech.make_solver(cells, size, material, material_at)
+    s.init()
+    o = MechSolverBasicOracle(cells, size, material, material_at)
+    o.init()
+    st, sto = mech.parse_load(W.TENSION_X)[0], oparse(W.TENSION_X)[0]
+    s.forward(False, False, 0.5, 1.0, 5.0, st['deformation'], st['stress'], st['R'])
+    s.g.materialpoint_forward()
+    o.forward(False, False, 0.5, 1.0, 5.0, sto['deformation'], sto['stress'], sto['R'])
+    o.con.forward()
+    s.prepare_evaluation()
+    o.S = osp.masked_compliance(o.C_volAvg, o.params['R'], o.params['stress_mask'])
+    r = s.g.to_natural(s.form_residual(s.field('F')))
+    r_o = o.form_residual(o.F.reshape(-1), 1, 1).reshape(o.shape)
+    err = np.abs(r - r_o).max() / np.abs(r_o).max()
+    errP = np.abs(s.get33('P_av') - o.P_av).max() / np.abs(o.P_av).max()
+    assert err < 1e-9 and errP < 1e-9, (err, errP)
+    if verbose:
+        print('smoke: residual evaluation 16^3 phenopowerlaw ok, rel err r %.2e, P_av %.2e, launches %d'
+              % (err, errP, s.g.kernel_launches()))
