@@ -5,18 +5,99 @@
 // (/root/reference/src/homogenization.f90:219-324, materialpoint.f90:208-218) and the reductions of
 // Spectral::constitutive_response (/root/reference/src/grid/spectral.cpp:160-218).
 #include <cstring>
+#include <cstdlib>
+#include <string>
 #include <cmath>
 #include <vector>
 #include <algorithm>
 #include "constitutive_dev.cuh"
+#include "machine_dev.cuh"
 #include "tangent_dev.cuh"
 #include "reduce.cuh"
 
 #define DMK_PT_THREADS 128
 
 // ------------------------------------------------------------------------------------------------ kernels
+// Lane-persistent integration kernel: every lane owns one material point at a time and walks it through the state
+// machine of machine_dev.cuh; one trip of the outer loop = one Lp Newton iteration for all lanes inside an Lp loop.
 template <int LAW, int NS, int ND>
 __global__ void __launch_bounds__(DMK_PT_THREADS) dmk_constitutive_kernel(DmkPointArrays pa, int phase, DmkNumDev num,
+                                                                          const double* __restrict__ Fin, double* __restrict__ Pout,
+                                                                          double Dt) {
+  const long long n = pa.n;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  DmkCnt cnt = {0, 0, 0, 0, 0, 0};
+  unsigned ill = 0, cb0 = 0;
+  DmkMachine<LAW, NS, ND> m;
+  DmkMachineStore<LAW, NS, ND> store;
+  machine_bind(m, store);
+  m.state = M_FETCH;
+  m.p.ph = pa.d_phases + phase;
+  m.p.C66 = m.p.ph->p.C66;
+  const int ns = m.p.ph->p.n_state;
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x - stride;
+  bool have = false;
+  for (;;) {
+    while (m.state != M_LP && m.state != M_EXIT) {
+      if (m.state == M_FETCH) {
+        if (have) {                                                      // store the finished point
+          if (!m.converged) ill = 1;
+          pa.cutbacks[i] = (int)(cnt.cutbacks - cb0);
+#pragma unroll
+          for (int a = 0; a < 9; a++) {
+            pa.F[a * n + i] = m.Ft[a]; pa.Fp[a * n + i] = m.p.Fp[a]; pa.Lp[a * n + i] = m.p.Lp[a]; pa.Fe[a * n + i] = m.p.Fe[a];
+          }
+#pragma unroll
+          for (int a = 0; a < 3; a++)
+#pragma unroll
+            for (int b = 0; b < 3; b++) Pout[i * 9 + a + 3 * b] = m.p.P[3 * a + b];
+#pragma unroll
+          for (int a = 0; a < 6; a++) pa.S[a * n + i] = m.p.S[a];
+          for (int k = 0; k < ns; k++) pa.state[k * n + i] = m.p.st[k];
+          if constexpr (ND > 0) { const int nd = m.p.ph->n_dep; for (int k = 0; k < nd; k++) pa.dep[k * n + i] = m.p.dep[k]; }
+          have = false;
+        }
+        do { i += stride; } while (i < n && pa.phase[i] != phase);
+        if (i >= n) { m.state = M_EXIT; break; }
+#pragma unroll
+        for (int a = 0; a < 3; a++)
+#pragma unroll
+          for (int b = 0; b < 3; b++) m.Ft[3 * a + b] = Fin[i * 9 + a + 3 * b];     // boundary record: c = i + 3 j
+#pragma unroll
+        for (int a = 0; a < 9; a++) {
+          m.F0in[a] = pa.F0[a * n + i]; m.Fp0[a] = pa.Fp0[a * n + i]; m.Lp0[a] = pa.Lp0[a * n + i];
+          m.p.Lp[a] = pa.Lp[a * n + i];            // phase_restore(includeL = .false.): Lp keeps the last guess
+          m.p.Fe[a] = pa.Fe[a * n + i];
+        }
+#pragma unroll
+        for (int a = 0; a < 6; a++) m.S0in[a] = pa.S0[a * n + i];
+        for (int k = 0; k < ns; k++) m.state0[k] = pa.state0[k * n + i];
+        if constexpr (ND > 0) { const int nd = m.p.ph->n_dep; for (int k = 0; k < nd; k++) m.p.dep[k] = pa.dep[k * n + i]; }
+        if constexpr (LAW == DMK_LAW_DISLOTWIN) m.p.C66 = m.p.ph->p.C66;
+        cb0 = cnt.cutbacks;
+        have = true;
+        machine_begin(m, num);
+      } else if (m.state == M_SUBSTEP) machine_substep(m, num, Dt, cnt);
+      else if (m.state == M_STRESS_PRO) machine_stress_prologue(m, num, cnt);
+      else machine_stress_epilogue(m, num);
+    }
+    if (!__any_sync(0xffffffffu, m.state != M_EXIT)) break;
+    if (m.state == M_LP) machine_lp_iteration(m, num, cnt);
+  }
+  // counters: warp reduce, one atomic per warp and counter
+  unsigned v[7] = {cnt.Lp_iter, cnt.Li_iter, cnt.stress_calls, cnt.state_iter, cnt.substeps, cnt.cutbacks, ill};
+#pragma unroll
+  for (int k = 0; k < 7; k++) {
+    unsigned s = v[k];
+    for (int off = 16; off > 0; off >>= 1) s += __shfl_down_sync(0xffffffffu, s, off);
+    if ((threadIdx.x & 31) == 0 && s) atomicAdd(&pa.d_counters[k], (unsigned long long)s);
+  }
+  if (ill) atomicOr(pa.d_ill, 1);
+}
+
+// Straight formulation: one thread per point, nested sub-step / state / Lp loops (lanes idle while their neighbours iterate).
+template <int LAW, int NS, int ND>
+__global__ void __launch_bounds__(DMK_PT_THREADS) dmk_constitutive_nested_kernel(DmkPointArrays pa, int phase, DmkNumDev num,
                                                                           const double* __restrict__ Fin, double* __restrict__ Pout,
                                                                           double Dt) {
   const long long n = pa.n;
@@ -25,6 +106,8 @@ __global__ void __launch_bounds__(DMK_PT_THREADS) dmk_constitutive_kernel(DmkPoi
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     if (pa.phase[i] != phase) continue;
     DmkPt<LAW, NS, ND> p;
+    DmkPtStore<LAW, NS, ND> pstore;
+    dmk_pt_bind(p, pstore);
     p.ph = pa.d_phases + phase;
     p.C66 = p.ph->p.C66;
     const int ns = p.ph->p.n_state;
@@ -85,6 +168,8 @@ __global__ void __launch_bounds__(DMK_PT_THREADS) dmk_tangent_kernel(DmkPointArr
     const long long i = first + j;
     if (pa.phase[i] != phase) continue;
     DmkPt<LAW, NS, ND> p;
+    DmkPtStore<LAW, NS, ND> pstore;
+    dmk_pt_bind(p, pstore);
     p.ph = pa.d_phases + phase;
     p.C66 = p.ph->p.C66;
     const int ns = p.ph->p.n_state;
@@ -149,6 +234,26 @@ static int point_grid(long long n) {
   const long long cap = 148LL * 64;
   return (int)std::max(1LL, std::min(b, cap));
 }
+// persistent launch: one resident wave (SM count x blocks per SM), fewer if there are fewer points
+template <typename K>
+static int persistent_grid(K kernel, long long n) {
+  int dev = 0, sms = 148, occ = 1;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, DMK_PT_THREADS, 0) != cudaSuccess || occ < 1) occ = 1;
+  const long long b = (n + DMK_PT_THREADS - 1) / DMK_PT_THREADS;
+  return (int)std::max(1LL, std::min(b, (long long)sms * occ));
+}
+#define DMK_LAUNCH_PERSISTENT(KERNEL, law, nstate, n, st, ...)                                                                      \
+  do {                                                                                                                             \
+    if (law == DMK_LAW_NONE) KERNEL<DMK_LAW_NONE, 0, 0><<<persistent_grid(KERNEL<DMK_LAW_NONE, 0, 0>, n), DMK_PT_THREADS, 0, st>>> __VA_ARGS__; \
+    else if (law == DMK_LAW_ISOTROPIC) KERNEL<DMK_LAW_ISOTROPIC, 1, 0><<<persistent_grid(KERNEL<DMK_LAW_ISOTROPIC, 1, 0>, n), DMK_PT_THREADS, 0, st>>> __VA_ARGS__; \
+    else if (law == DMK_LAW_PHENOPOWERLAW && nstate <= 24) KERNEL<DMK_LAW_PHENOPOWERLAW, 24, 0><<<persistent_grid(KERNEL<DMK_LAW_PHENOPOWERLAW, 24, 0>, n), DMK_PT_THREADS, 0, st>>> __VA_ARGS__; \
+    else if (law == DMK_LAW_PHENOPOWERLAW && nstate <= 48) KERNEL<DMK_LAW_PHENOPOWERLAW, 48, 0><<<persistent_grid(KERNEL<DMK_LAW_PHENOPOWERLAW, 48, 0>, n), DMK_PT_THREADS, 0, st>>> __VA_ARGS__; \
+    else if (law == DMK_LAW_PHENOPOWERLAW) KERNEL<DMK_LAW_PHENOPOWERLAW, 2 * DMK_MAX_SYS, 0><<<persistent_grid(KERNEL<DMK_LAW_PHENOPOWERLAW, 2 * DMK_MAX_SYS, 0>, n), DMK_PT_THREADS, 0, st>>> __VA_ARGS__; \
+    else if (law == DMK_LAW_DISLOTWIN && nstate <= 48) KERNEL<DMK_LAW_DISLOTWIN, 48, 36><<<persistent_grid(KERNEL<DMK_LAW_DISLOTWIN, 48, 36>, n), DMK_PT_THREADS, 0, st>>> __VA_ARGS__; \
+    else KERNEL<DMK_LAW_DISLOTWIN, DMK_MAX_STATE, DMK_MAX_DEP><<<persistent_grid(KERNEL<DMK_LAW_DISLOTWIN, DMK_MAX_STATE, DMK_MAX_DEP>, n), DMK_PT_THREADS, 0, st>>> __VA_ARGS__; \
+  } while (0)
 
 #define DMK_DISPATCH(KERNEL, law, nstate, ...)                                                                  \
   do {                                                                                                          \
@@ -164,11 +269,13 @@ static int point_grid(long long n) {
 int dmk_points_constitutive(dmk_ctx* c, const double* d_F, double* d_P, double dt) {
   DmkPointArrays& pa = *c->pts;
   const DmkNumDev nd = num_dev(c->num);
-  const int grid = point_grid(pa.n);
+  // two formulations of the same arithmetic (bit-identical, tests/host_twin): lane-persistent state machine | nested loops
+  static const bool use_machine = [] { const char* e = getenv("DMK_CONSTITUTIVE"); return e && std::string(e) == "machine"; }();
   for (int ph = 0; ph < pa.n_phases; ph++) {
     if (pa.n_cells_of_phase[ph] == 0) continue;
     const int law = pa.law_of_phase[ph], nst = pa.nstate_of_phase[ph];
-    DMK_DISPATCH(dmk_constitutive_kernel, law, nst, <<<grid, DMK_PT_THREADS, 0, c->stream>>>(pa, ph, nd, d_F, d_P, dt));
+    if (use_machine) DMK_LAUNCH_PERSISTENT(dmk_constitutive_kernel, law, nst, pa.n, c->stream, (pa, ph, nd, d_F, d_P, dt));
+    else DMK_DISPATCH(dmk_constitutive_nested_kernel, law, nst, <<<point_grid(pa.n), DMK_PT_THREADS, 0, c->stream>>>(pa, ph, nd, d_F, d_P, dt));
     c->launches++;
   }
   DMK_CUDA_CHECK(cudaGetLastError());
@@ -246,6 +353,8 @@ __global__ void dmk_init_dependent_kernel(DmkPointArrays pa, int phase) {
     if (pa.phase[i] != phase) continue;
     if constexpr (LAW == DMK_LAW_DISLOTWIN) {
       DmkPt<LAW, NS, ND> p;
+      DmkPtStore<LAW, NS, ND> pstore;
+      dmk_pt_bind(p, pstore);
       p.ph = pa.d_phases + phase;
       const int ns = p.ph->p.n_state, nd = p.ph->n_dep;
       for (int k = 0; k < ns; k++) p.st[k] = pa.state[k * n + i];
@@ -285,6 +394,10 @@ extern "C" int dmk_material_init(dmk_ctx* c, const dmk_phase* phases, int n_phas
     }
     for (int a = 0; a < p.n_tw; a++) { voigt_strain_of(p.P_tw[a], d.pv_tw[a]); q_host(p.C66, d.pv_tw[a], d.Q_tw[a]); }
     d.nonschmid = nons ? 1 : 0;
+    auto small_int = [](double v) { return (v >= 1.0 && v <= 64.0 && v == std::floor(v)) ? (int)v : 0; };
+    for (int a = 0; a < p.n_sl; a++) d.n_sl_int[a] = small_int(p.n_sl_exp[a]);
+    for (int a = 0; a < p.n_tw; a++) d.n_tw_int[a] = small_int(p.n_tw_exp[a]);
+    d.iso_n_int = small_int(p.iso_n);
     d.n_dep = (p.law == DMK_LAW_DISLOTWIN) ? 2 * p.n_sl + p.n_tw : 0;
     pa->law_of_phase[i] = p.law; pa->nstate_of_phase[i] = p.n_state; pa->nsys_of_phase[i] = p.n_sl + p.n_tw;
     max_state = std::max(max_state, p.n_state); max_dep = std::max(max_dep, d.n_dep);

@@ -21,6 +21,9 @@ struct DmkDevPhase {
   // strain-like Voigt projections of the (non-)Schmid tensors: pv[alpha] = P(ij) + P(ji) (shear), P(ii) (normal)
   double pv_pos[DMK_MAX_SL][6], pv_neg[DMK_MAX_SL][6], pv_tw[DMK_MAX_TW][6];
   int nonschmid;      // P_nS_neg != -P_nS_pos (cI with non-Schmid coefficients)
+  // stress exponents that are small positive integers (n = 20 in every shipped parameter set) are evaluated by repeated
+  // squaring instead of pow(): 0 = use pow
+  int n_sl_int[DMK_MAX_SL], n_tw_int[DMK_MAX_TW], iso_n_int;
   int n_dep;
 };
 

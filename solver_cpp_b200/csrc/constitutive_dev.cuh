@@ -31,6 +31,13 @@ DMK_HD __forceinline__ bool deq0(double a) { return fabs(a) <= 10.0 * DBL_MIN; }
 DMK_HD __forceinline__ bool deq(double a, double b) { return fabs(a - b) <= DBL_EPSILON * fmax(fabs(a), fabs(b)); }
 DMK_HD __forceinline__ double fsign(double a, double b) { return copysign(fabs(a), b); }
 
+// x^n for a small positive integer n by repeated squaring (a few ulp, like pow)
+DMK_HD __forceinline__ double powi(double x, int n) {
+  double r = 1.0, b = x;
+  while (n) { if (n & 1) r *= b; b *= b; n >>= 1; }
+  return r;
+}
+
 struct DmkCnt { unsigned Lp_iter, Li_iter, stress_calls, state_iter, substeps, cutbacks; };
 
 // ------------------------------------------------------------------------------------------------ 3x3 helpers
@@ -126,10 +133,11 @@ DMK_HD __forceinline__ bool solve9(double (&J)[81], double (&b)[9]) {
         double t = b[k]; b[k] = b[i]; b[i] = t;
       }
     }
-    const double piv = J[9 * k + k];
+    const double rpiv = 1.0 / J[9 * k + k];        // one reciprocal per pivot instead of 8 - k quotients (<= 1 ulp apart)
+    J[9 * k + k] = rpiv;
 #pragma unroll
     for (int i = k + 1; i < 9; i++) {
-      const double l = J[9 * i + k] / piv;
+      const double l = J[9 * i + k] * rpiv;
 #pragma unroll
       for (int j = k + 1; j < 9; j++) J[9 * i + j] -= l * J[9 * k + j];
       b[i] -= l * b[k];
@@ -140,7 +148,7 @@ DMK_HD __forceinline__ bool solve9(double (&J)[81], double (&b)[9]) {
     double s = b[i];
 #pragma unroll
     for (int j = i + 1; j < 9; j++) s -= J[9 * i + j] * b[j];
-    b[i] = s / J[9 * i + i];
+    b[i] = s * J[9 * i + i];                        // diagonal holds the reciprocal pivot
   }
   return sing;
 }
@@ -180,10 +188,20 @@ struct DmkPt {
   const double* C66;          // 36 doubles: phase table (global) or the per-call homogenised copy (dislotwin, local)
   double Fp[9], Lp[9], Fe[9], P[9];
   double S[6];
+  // dynamically indexed arrays live OUTSIDE this struct (DmkPtStore): one variable-index access would otherwise keep the
+  // whole aggregate -- and with it every tensor above -- in local memory instead of registers
+  double* st;
+  double* dep;
+  double* C66h;
+};
+template <int LAW, int NS, int ND>
+struct DmkPtStore {
   double st[NS > 0 ? NS : 1];
   double dep[ND > 0 ? ND : 1];
   double C66h[LAW == DMK_LAW_DISLOTWIN ? 36 : 1];
 };
+template <int LAW, int NS, int ND>
+DMK_HD __forceinline__ void dmk_pt_bind(DmkPt<LAW, NS, ND>& p, DmkPtStore<LAW, NS, ND>& s) { p.st = s.st; p.dep = s.dep; p.C66h = s.C66h; }
 
 // Hooke with Fi = I: S = C66 . Voigt_strain(1/2 (Fe^T Fe - I))      (phase_mechanical_elastic.f90:157-195)
 DMK_HD __forceinline__ void hooke_S(const double* __restrict__ C66, const double (&Fe)[9], double (&S)[6]) {
@@ -222,7 +240,9 @@ DMK_HD __forceinline__ void pheno_slip_rate(const DmkPt<LAW, NS, ND>& p, const d
   const double tn = d.nonschmid ? sdot(S, d.p.P_nS_neg[i]) : -tp;
   const double tmax = fmax(tp, tn);
   const double n = d.p.n_sl_exp[i];
-  dg = ((tp > tn) ? 1.0 : -1.0) * d.p.dot_gamma_0_sl[i] * pow(tmax / p.st[i], n);
+  const int ni = d.n_sl_int[i];
+  const double ratio = tmax / p.st[i];
+  dg = ((tp > tn) ? 1.0 : -1.0) * d.p.dot_gamma_0_sl[i] * (ni ? powi(ratio, ni) : pow(ratio, n));
   ddg = deq0(dg) ? 0.0 : dg * n / tmax;
 }
 template <int LAW, int NS, int ND>
@@ -231,7 +251,9 @@ DMK_HD __forceinline__ void pheno_twin_rate(const DmkPt<LAW, NS, ND>& p, const d
   const dmk_phase& q = p.ph->p;
   const double tau = sdot(S, q.P_tw[i]);
   const double n = q.n_tw_exp[i];
-  dg = (tau > 0.0) ? (1.0 - sumF) * q.dot_gamma_0_tw[i] * pow(tau / p.st[q.n_sl + i], n) : 0.0;
+  const int ni = p.ph->n_tw_int[i];
+  const double ratio = tau / p.st[q.n_sl + i];
+  dg = (tau > 0.0) ? (1.0 - sumF) * q.dot_gamma_0_tw[i] * (ni ? powi(ratio, ni) : pow(ratio, n)) : 0.0;
   ddg = deq0(dg) ? 0.0 : dg * n / tau;
 }
 template <int LAW, int NS, int ND>
@@ -327,7 +349,8 @@ DMK_HD __forceinline__ void iso_Lp(const DmkPt<LAW, NS, ND>& p, const double (&S
   deviator(S, dev, sq);
   const double nrm = sqrt(sq);
   if (nrm > 0.0) {
-    const double dgam = q.iso_dot_gamma_0 * pow(sqrt(1.5) * nrm / (q.iso_M * p.st[0]), q.iso_n);
+    const double ratio = sqrt(1.5) * nrm / (q.iso_M * p.st[0]);
+    const double dgam = q.iso_dot_gamma_0 * (p.ph->iso_n_int ? powi(ratio, p.ph->iso_n_int) : pow(ratio, q.iso_n));
 #pragma unroll
     for (int a = 0; a < 9; a++) Lp[a] = dgam * dev[a] / nrm;
     dgam_over_nrm = dgam / nrm;
@@ -375,7 +398,8 @@ DMK_HD __forceinline__ void iso_dotState(const DmkPt<LAW, NS, ND>& p, const doub
   double dev[9], sq;
   deviator(S, dev, sq);
   const double nrm = sqrt(sq);
-  const double dgam = q.iso_dot_gamma_0 * pow(sqrt(1.5) * nrm / (q.iso_M * xi), q.iso_n);
+  const double ratio = sqrt(1.5) * nrm / (q.iso_M * xi);
+  const double dgam = q.iso_dot_gamma_0 * (p.ph->iso_n_int ? powi(ratio, p.ph->iso_n_int) : pow(ratio, q.iso_n));
   if (dgam > 1e-12) {
     double xi_inf_star;
     if (deq0(q.iso_c_1)) xi_inf_star = q.iso_xi_inf;

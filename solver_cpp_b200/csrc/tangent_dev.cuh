@@ -54,7 +54,8 @@ DMK_HD __noinline__ void full_dLp_dMp(DmkPt<LAW, NS, ND>& p, double* __restrict_
     deviator(p.S, dev, sq);
     const double nrm = sqrt(sq);
     if (nrm > 0.0) {
-      const double dgam = d.p.iso_dot_gamma_0 * pow(sqrt(1.5) * nrm / (d.p.iso_M * p.st[0]), d.p.iso_n);
+      const double ratio = sqrt(1.5) * nrm / (d.p.iso_M * p.st[0]);
+      const double dgam = d.p.iso_dot_gamma_0 * (d.iso_n_int ? powi(ratio, d.iso_n_int) : pow(ratio, d.p.iso_n));
       for (int k = 0; k < 9; k++) for (int m = 0; m < 9; m++) dM[9 * k + m] = (d.p.iso_n - 1.0) * dev[k] * dev[m] / sq;
       for (int k = 0; k < 9; k++) dM[10 * k] += 1.0;
       for (int k = 0; k < 3; k++) for (int m = 0; m < 3; m++) T4(dM, k, k, m, m) -= 1.0 / 3.0;

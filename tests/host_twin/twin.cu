@@ -4,15 +4,21 @@
 #include <cstring>
 #include <vector>
 #include "../../solver_cpp_b200/csrc/constitutive_dev.cuh"
+#include "../../solver_cpp_b200/csrc/machine_dev.cuh"
 #include "../../solver_cpp_b200/csrc/tangent_dev.cuh"
 
 void dmk_set_error(const char*, ...) {}
+static int g_use_nested = 0;     // 1: the straight nested-loop formulation (cross-check of the state machine)
+extern "C" void twin_use_nested(int v) { g_use_nested = v; }
 
 template <int LAW, int NS, int ND>
 static int run_point(const DmkDevPhase* ph, const DmkNumDev& num, const double* F0, const double* Ft, const double* Fp0,
                      const double* Lp0, double* Lp, const double* S0, const double* state0, double* dep, double Dt,
                      double* P, double* Fp, double* Fe, double* S, double* state, unsigned* cnt_out, double* dPdF) {
-  DmkPt<LAW, NS, ND> p;
+  static DmkMachine<LAW, NS, ND> mach;                // the product path: the resumable state machine
+  static DmkMachineStore<LAW, NS, ND> mstore;
+  machine_bind(mach, mstore);
+  DmkPt<LAW, NS, ND>& p = mach.p;
   p.ph = ph; p.C66 = ph->p.C66;
   double f0[9], ft[9], fp0[9], lp0[9], s0[6];
   for (int a = 0; a < 9; a++) { f0[a] = F0[a]; ft[a] = Ft[a]; fp0[a] = Fp0[a]; lp0[a] = Lp0[a]; p.Lp[a] = Lp[a]; p.Fp[a] = Fp0[a]; p.Fe[a] = Fe[a]; p.P[a] = 0; }
@@ -20,7 +26,14 @@ static int run_point(const DmkDevPhase* ph, const DmkNumDev& num, const double* 
   for (int k = 0; k < ph->p.n_state; k++) p.st[k] = state0[k];
   for (int k = 0; k < ph->n_dep; k++) p.dep[k] = dep[k];
   DmkCnt cnt = {0, 0, 0, 0, 0, 0};
-  bool ok = constitutive_point(p, num, f0, ft, fp0, lp0, s0, state0, Dt, cnt);
+  bool ok;
+  if (g_use_nested) ok = constitutive_point(p, num, f0, ft, fp0, lp0, s0, state0, Dt, cnt);
+  else {
+    for (int a = 0; a < 9; a++) { mach.Ft[a] = Ft[a]; mach.F0in[a] = F0[a]; mach.Fp0[a] = Fp0[a]; mach.Lp0[a] = Lp0[a]; }
+    for (int a = 0; a < 6; a++) mach.S0in[a] = S0[a];
+    for (int k = 0; k < ph->p.n_state; k++) mach.state0[k] = state0[k];
+    ok = machine_run_point(mach, num, Dt, cnt);
+  }
   for (int a = 0; a < 9; a++) { P[a] = p.P[a]; Fp[a] = p.Fp[a]; Fe[a] = p.Fe[a]; Lp[a] = p.Lp[a]; }
   for (int a = 0; a < 6; a++) S[a] = p.S[a];
   for (int k = 0; k < ph->p.n_state; k++) state[k] = p.st[k];
@@ -48,6 +61,10 @@ extern "C" int twin_point(const dmk_phase* phase, const dmk_numerics* n, const d
     for (int k = 0; k < 9; k++) if (p.P_nS_neg[a][k] != -p.P_nS_pos[a][k]) nons = true;
   }
   for (int a = 0; a < p.n_tw; a++) { voigt_strain_of(p.P_tw[a], d.pv_tw[a]); q_host(p.C66, d.pv_tw[a], d.Q_tw[a]); }
+  auto small_int = [](double v) { return (v >= 1.0 && v <= 64.0 && v == floor(v)) ? (int)v : 0; };
+  for (int a = 0; a < p.n_sl; a++) d.n_sl_int[a] = small_int(p.n_sl_exp[a]);
+  for (int a = 0; a < p.n_tw; a++) d.n_tw_int[a] = small_int(p.n_tw_exp[a]);
+  d.iso_n_int = small_int(p.iso_n);
   d.nonschmid = nons; d.n_dep = (p.law == DMK_LAW_DISLOTWIN) ? 2 * p.n_sl + p.n_tw : 0;
   DmkNumDev nd;
   nd.r_cutback_min = n->r_cutback_min; nd.r_cutback = n->r_cutback; nd.r_increase = n->r_increase; nd.eps_rel_state = n->eps_rel_state;

@@ -62,3 +62,36 @@ def test_twin_matches_oracle(phase, rate):
         o.forward()
     if phase != 'Al_elastic':
         assert np.abs(o.a['Lp']).max() > 1e-6
+
+
+def test_state_machine_is_bit_identical_to_nested_loops():
+    """machine_dev.cuh (what the kernel runs) against the straight nested-loop formulation of constitutive_dev.cuh:
+    same arithmetic in the same order -> identical bits, including cells that cut back."""
+    import twin
+    from solver_cpp_b200 import workloads as W, material as M
+    lib = twin.build()
+    for phase, rate in (('Cu_pheno', 2.0e-3), ('Al_iso', 2.0e-3), ('TWIP', 7.0e-3)):
+        cells = (4, 4, 2)
+        material, material_at, size = W.polycrystal(cells, 5, phase, 0)
+        o = ConstitutiveOracle(material, material_at)
+        m = M.Material(material, material_at)
+        num = M.make_numerics()
+        n = int(np.prod(cells))
+        ns = max(1, o.phases[0].n_state)
+        nd = max(1, 2 * o.phases[0].n_sl + o.phases[0].n_tw)
+        rng = np.random.default_rng(4)
+        F = _path(cells, 1, rng, rate)[0]
+        cut = 0
+        for i in range(n):
+            args = (lib, m.phases[0], num, o.a['F0'][i], F[i].reshape(9), o.a['Fp0'][i], o.a['Lp0'][i], o.a['Lp'][i],
+                    o.a['S0'][i][V6], o.a['state0'][i][:ns], o.a['dep'][i][:nd], 0.5)
+            lib.twin_use_nested(1)
+            a = twin.run_point(*args)
+            lib.twin_use_nested(0)
+            b = twin.run_point(*args)
+            for k in ('P', 'Fp', 'Fe', 'S', 'state', 'Lp', 'dep', 'cnt'):
+                assert np.array_equal(a[k], b[k]), (phase, i, k)
+            assert a['ok'] == b['ok']
+            cut += int(a['cnt'][5])
+        if phase != 'TWIP':
+            assert cut > 0
