@@ -1,0 +1,80 @@
+"""Multi-GPU parity script (run under torchrun, one rank per GPU): the z-slab decomposed solver against the single-GPU
+solver on the same problem.  Used by tests/test_gpu_multi.py and by hand:
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tests/mgpu_parity.py"""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    world, rank, local = int(os.environ['WORLD_SIZE']), int(os.environ['RANK']), int(os.environ['LOCAL_RANK'])
+    torch.cuda.set_device(local)
+    dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    from solver_cpp_b200 import mech, workloads as W, parallel
+    from solver_cpp_b200.grid import GridContext
+    ok = True
+    # ---- spectral half: forward FFT + Gamma + inverse on a random field, slab vs whole
+    cells, size = (16, 8 * world, 4 * world), (2e-5, 1e-5, 1.5e-5)
+    nx, ny, nz = cells
+    rng = np.random.default_rng(1)
+    P = 1e8 * rng.standard_normal((nz, ny, nx, 3, 3))
+    aim = 1e-4 * rng.standard_normal((3, 3))
+    C = rng.standard_normal((3, 3, 3, 3)) * 1e8
+    for i in range(3):
+        for j in range(3):
+            C[i, j, i, j] += 1e11
+            C[i, j, j, i] += 2e10
+    z0, z1 = parallel.slab_range(nz, world, rank)
+    for deriv in (0, 2):
+        g = GridContext(cells, size, derivative=deriv, world_size=world, rank=rank)
+        g.set_comm(parallel.make_comm(world, rank))
+        g.update_gamma(C)
+        d = g.to_device(P[z0:z1])
+        rms = g.divergence_and_gamma(d, aim)
+        out = g.to_natural(d)
+        g1 = GridContext(cells, size, derivative=deriv)
+        g1.update_gamma(C)
+        d1 = g1.to_device(P)
+        rms1 = g1.divergence_and_gamma(d1, aim)
+        ref = g1.to_natural(d1)[z0:z1]
+        e = np.abs(out - ref).max() / np.abs(ref).max()
+        ok &= e < 1e-12 and abs(rms - rms1) <= 1e-12 * rms1
+        if rank == 0:
+            print('spectral deriv %d: rel err %.2e, rms %.15e vs %.15e' % (deriv, e, rms, rms1))
+    # ---- full solver: 2 increments of tensionX on a polycrystal
+    cells = (16, 16, 8 * world)
+    nz = cells[2]
+    z0, z1 = parallel.slab_range(nz, world, rank)
+    material, mat_slab, size = W.polycrystal(cells, 12, 'Al_pheno', 0, z_range=(z0, z1))
+    _, mat_all, _ = W.polycrystal(cells, 12, 'Al_pheno', 0)
+    s = mech.make_solver(cells, size, material, mat_slab, world_size=world, rank=rank, comm=parallel.make_comm(world, rank))
+    s.init()
+    recs = mech.loop_over_loadcase(s, mech.parse_load(W.TENSION_X), max_increments=2)
+    s1 = mech.make_solver(cells, size, material, mat_all)
+    s1.init()
+    recs1 = mech.loop_over_loadcase(s1, mech.parse_load(W.TENSION_X), max_increments=2)
+    it, it1 = [r['iterations'] for r in recs], [r['iterations'] for r in recs1]
+    eP = max(np.abs(a['P_av'] - b['P_av']).max() / np.abs(b['P_av']).max() for a, b in zip(recs, recs1))
+    F = s.g.to_natural(s.field('F'))
+    F1 = s1.g.to_natural(s1.field('F'))[z0:z1]
+    eF = np.abs(F - F1).max()
+    sel = tuple(int(v) for v in s.get('minmax_cells', 2)), tuple(int(v) for v in s1.get('minmax_cells', 2))
+    ok &= it == it1 and eP < 1e-9 and eF < 1e-10 and sel[0] == sel[1]
+    if rank == 0:
+        print('solver: iterations %s vs %s, P_av rel %.2e, F abs %.2e, minmax cells %s vs %s' % (it, it1, eP, eF, sel[0], sel[1]))
+    t = torch.tensor([1.0 if ok else 0.0], device='cuda')
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        print('MGPU_PARITY_OK' if t.item() == 1.0 else 'MGPU_PARITY_FAILED')
+    dist.destroy_process_group()
+    sys.exit(0 if t.item() == 1.0 else 1)
+
+
+if __name__ == '__main__':
+    main()
