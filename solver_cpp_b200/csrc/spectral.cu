@@ -128,8 +128,10 @@ extern "C" int dmk_create(dmk_ctx** out, const dmk_grid_desc* g) {
   return DMK_OK;
 }
 
+void dmk_unbind_if_current(dmk_ctx* c);
 extern "C" void dmk_destroy(dmk_ctx* c) {
   if (!c) return;
+  dmk_unbind_if_current(c);
   cudaStreamSynchronize(c->stream);
   dmk_mech_teardown(c);
   dmk_points_teardown(c);

@@ -146,3 +146,38 @@ def test_form_residual_host_roundtrip():
     rh = np.zeros_like(Fh)
     s2.form_residual_host(Fh, rh)
     assert np.abs(rh - r_dev).max() == 0.0
+
+
+def test_fortran_named_dropin_symbols():
+    """f_homogenization_fetch_tensor_pointers / _mechanical_response / _response2 / f_materialpoint_forward through
+    host mirrors (spectral.h:16-23 of the reference) against the device-pointer API"""
+    import ctypes as C
+    from solver_cpp_b200 import workloads as W, material as M, lib as L
+    from solver_cpp_b200.grid import GridContext
+    cells = (6, 5, 4)
+    n = int(np.prod(cells))
+    material, material_at, size = W.polycrystal(cells, 5, 'Al_pheno', 0)
+    ga, gb = GridContext(cells, size), GridContext(cells, size)
+    ga.material_init(M.Material(material, material_at)); gb.material_init(M.Material(material, material_at))
+    lib = L.load()
+    L.check(lib.dmk_bind_global(ga.ctx))
+    pF0, pF, pP, pT, pill = (C.POINTER(C.c_double)(), C.POINTER(C.c_double)(), C.POINTER(C.c_double)(), C.POINTER(C.c_double)(), C.c_void_p())
+    lib.f_homogenization_fetch_tensor_pointers(C.byref(pF0), C.byref(pF), C.byref(pP), C.byref(pT), C.byref(pill))
+    F = np.ctypeslib.as_array(pF, shape=(n * 9,)); Pm = np.ctypeslib.as_array(pP, shape=(n * 9,)); T = np.ctypeslib.as_array(pT, shape=(n * 81,))
+    rng = np.random.default_rng(0)
+    Fnat = np.eye(3) + np.diag([1.5e-3, -5e-4, -5e-4]) + 2e-4 * rng.standard_normal((cells[2], cells[1], cells[0], 3, 3))
+    from solver_cpp_b200.grid import natural_to_records
+    F[:] = natural_to_records(Fnat).reshape(-1)
+    dt, one, nn = C.c_double(0.5), C.c_int(1), C.c_int(n)
+    lib.f_homogenization_mechanical_response(C.byref(dt), C.byref(one), C.byref(nn))
+    ip = (C.c_int * 2)(1, 1); el = (C.c_int * 2)(1, n)
+    lib.f_homogenization_mechanical_response2(C.byref(dt), ip, el)
+    P_b = gb.constitutive_response(gb.to_device(Fnat), 0.5).cpu().numpy().reshape(-1)
+    _, _, _, d = gb.tangent_response(0.5, materialise=True)
+    assert np.array_equal(Pm, P_b)
+    assert np.array_equal(T, d.cpu().numpy().reshape(-1))
+    assert C.cast(pill, C.POINTER(C.c_int))[0] == 0
+    lib.f_materialpoint_forward()
+    gb.materialpoint_forward()
+    assert np.array_equal(ga.get_state('Fp0', 9), gb.get_state('Fp0', 9))
+    L.check(lib.dmk_bind_global(None))
