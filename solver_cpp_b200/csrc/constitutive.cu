@@ -271,9 +271,13 @@ int dmk_points_constitutive(dmk_ctx* c, const double* d_F, double* d_P, double d
   const DmkNumDev nd = num_dev(c->num);
   // two formulations of the same arithmetic (bit-identical, tests/host_twin): lane-persistent state machine | nested loops
   static const bool use_machine = [] { const char* e = getenv("DMK_CONSTITUTIVE"); return e && std::string(e) == "machine"; }();
+  static const bool use_generic = [] { const char* e = getenv("DMK_CONSTITUTIVE"); return e && (std::string(e) == "generic" || std::string(e) == "machine"); }();
   for (int ph = 0; ph < pa.n_phases; ph++) {
     if (pa.n_cells_of_phase[ph] == 0) continue;
     const int law = pa.law_of_phase[ph], nst = pa.nstate_of_phase[ph];
+    bool handled = false;
+    if (!use_generic) { int rc = dmk_points_pheno_fast(c, ph, nd, d_F, d_P, dt, &handled); if (rc) return rc; }
+    if (handled) { c->launches++; continue; }
     if (use_machine) DMK_LAUNCH_PERSISTENT(dmk_constitutive_kernel, law, nst, pa.n, c->stream, (pa, ph, nd, d_F, d_P, dt));
     else DMK_DISPATCH(dmk_constitutive_nested_kernel, law, nst, <<<point_grid(pa.n), DMK_PT_THREADS, 0, c->stream>>>(pa, ph, nd, d_F, d_P, dt));
     c->launches++;
@@ -342,6 +346,7 @@ void dmk_points_teardown(dmk_ctx* c) {
   if (pa->dep) cudaFree(pa->dep);
   cudaFree(pa->nrm); cudaFree(pa->cutbacks); cudaFree(pa->d_phases); cudaFree(pa->d_counters); cudaFree(pa->d_ill);
   delete[] pa->h_phases;
+  delete[] pa->h_dev_phases;
   delete pa;
   c->pts = nullptr;
 }
@@ -427,6 +432,8 @@ extern "C" int dmk_material_init(dmk_ctx* c, const dmk_phase* phases, int n_phas
   DMK_CUDA_CHECK(cudaMemset(pa->d_ill, 0, sizeof(int)));
   DMK_CUDA_CHECK(cudaMemcpy(pa->phase, ph.data(), n * sizeof(int), cudaMemcpyHostToDevice));
   DMK_CUDA_CHECK(cudaMemcpy(pa->d_phases, dev.data(), n_phases * sizeof(DmkDevPhase), cudaMemcpyHostToDevice));
+  pa->h_dev_phases = new DmkDevPhase[n_phases];
+  memcpy(pa->h_dev_phases, dev.data(), n_phases * sizeof(DmkDevPhase));
   {
     std::vector<double> buf((size_t)9 * n);
     auto up = [&](double* d, size_t count) -> int { DMK_CUDA_CHECK(cudaMemcpy(d, buf.data(), count * sizeof(double), cudaMemcpyHostToDevice)); return DMK_OK; };

@@ -40,6 +40,7 @@ struct DmkPointArrays {
   int* cutbacks;                       // [n] sub-step cut-backs of each cell in the last response call (diagnostic)
   DmkDevPhase* d_phases;               // device array
   dmk_phase* h_phases;                 // host copy
+  DmkDevPhase* h_dev_phases;           // host copy of the device tables
   int law_of_phase[DMK_MAX_PHASES], nstate_of_phase[DMK_MAX_PHASES], nsys_of_phase[DMK_MAX_PHASES];
   unsigned long long* d_counters;      // 8: Lp iters, Li iters, stress calls, state iters, substeps, cutbacks, ill cells, -
   int* d_ill;                          // device flag (OR of broken cells since the last reset)
@@ -54,6 +55,7 @@ struct DmkNumDev {
 };
 
 int dmk_points_constitutive(dmk_ctx* c, const double* d_F, double* d_P, double dt);
+int dmk_points_pheno_fast(dmk_ctx* c, int ph, const DmkNumDev& nd, const double* d_F, double* d_P, double dt, bool* handled);
 int dmk_points_tangent(dmk_ctx* c, double dt, double* d_Csum81 /*device, row-major sum over local cells*/,
                        double* d_dPdF /*optional [n][81] Fortran order*/);
 int dmk_points_tangent_cell(dmk_ctx* c, double dt, long long cell, double* d_out81 /*row-major*/);

@@ -6,6 +6,7 @@
 #include "../../solver_cpp_b200/csrc/constitutive_dev.cuh"
 #include "../../solver_cpp_b200/csrc/machine_dev.cuh"
 #include "../../solver_cpp_b200/csrc/tangent_dev.cuh"
+#include "../../solver_cpp_b200/csrc/pheno_fast_dev.cuh"
 
 void dmk_set_error(const char*, ...) {}
 static int g_use_nested = 0;     // 1: the straight nested-loop formulation (cross-check of the state machine)
@@ -43,6 +44,35 @@ static int run_point(const DmkDevPhase* ph, const DmkNumDev& num, const double* 
   return ok ? 1 : 0;
 }
 
+// the register-resident slip-only phenopowerlaw formulation (pheno_fast_dev.cuh) on a one-point DmkPointArrays
+template <int NSL, int NEXP>
+static int run_point_fast(const DmkDevPhase* ph, const DmkNumDev& num, const double* F0, const double* Ft, const double* Fp0,
+                          const double* Lp0, double* Lp, const double* S0, const double* state0, double Dt,
+                          double* P, double* Fp, double* Fe, double* S, double* state, unsigned* cnt_out) {
+  static DmkPhenoK<NSL> K;
+  dmk_pheno_fast_tables<NSL>(*ph, K);
+  DmkPointArrays pa;
+  memset(&pa, 0, sizeof pa);
+  pa.n = 1;
+  double F[9], f0[9], fp0[9], lp0[9], s0[6], st0[2 * NSL], Frec[9], Prec[9];
+  int cut = 0;
+  for (int a = 0; a < 9; a++) { f0[a] = F0[a]; fp0[a] = Fp0[a]; lp0[a] = Lp0[a]; F[a] = 0; }
+  for (int a = 0; a < 3; a++) for (int b = 0; b < 3; b++) Frec[a + 3 * b] = Ft[3 * a + b];
+  for (int a = 0; a < 6; a++) s0[a] = S0[a];
+  for (int k = 0; k < 2 * NSL; k++) st0[k] = state0[k];
+  pa.F0 = f0; pa.F = F; pa.Fp0 = fp0; pa.Fp = Fp; pa.Fe = Fe; pa.Lp0 = lp0; pa.Lp = Lp; pa.S0 = s0; pa.S = S; pa.state0 = st0; pa.state = state;
+  pa.cutbacks = &cut;
+  double scratch[PF_NARR * 2 * NSL];
+  DmkScr scr = {scratch, 1};
+  DmkCnt cnt = {0, 0, 0, 0, 0, 0};
+  const bool ok = pf_point<NSL, NEXP>(K, num, pa, 0, Frec, Prec, Dt, scr, cnt);
+  for (int a = 0; a < 3; a++) for (int b = 0; b < 3; b++) P[3 * a + b] = Prec[a + 3 * b];
+  cnt_out[0] = cnt.Lp_iter; cnt_out[1] = cnt.Li_iter; cnt_out[2] = cnt.stress_calls; cnt_out[3] = cnt.state_iter; cnt_out[4] = cnt.substeps; cnt_out[5] = cnt.cutbacks;
+  return ok ? 1 : 0;
+}
+static int g_use_fast = 0;       // 1: route eligible phases through pheno_fast_dev.cuh
+extern "C" void twin_use_fast(int v) { g_use_fast = v; }
+
 static void voigt_strain_of(const double* P, double* pv) { pv[0] = P[0]; pv[1] = P[4]; pv[2] = P[8]; pv[3] = P[5] + P[7]; pv[4] = P[2] + P[6]; pv[5] = P[1] + P[3]; }
 static void q_host(const double* C66, const double* pv, double* Q) { for (int b = 0; b < 6; b++) { double s = 0; for (int a = 0; a < 6; a++) s += pv[a] * C66[6 * a + b]; Q[b] = s; } }
 
@@ -70,6 +100,23 @@ extern "C" int twin_point(const dmk_phase* phase, const dmk_numerics* n, const d
   nd.r_cutback_min = n->r_cutback_min; nd.r_cutback = n->r_cutback; nd.r_increase = n->r_increase; nd.eps_rel_state = n->eps_rel_state;
   nd.N_iter_state_max = n->N_iter_state_max; nd.N_iter_Lp_max = n->N_iter_Lp_max; nd.r_linesearch_Lp = n->r_linesearch_Lp;
   nd.eps_rel_Lp = n->eps_rel_Lp; nd.eps_abs_Lp = n->eps_abs_Lp; nd.f_update_jacobi_Lp = n->f_update_jacobi_Lp > 0 ? n->f_update_jacobi_Lp : 1;
+  int nexp = 0;
+  if (g_use_fast && dmk_pheno_fast_eligible(d, 12, &nexp)) {
+    int ok = (nexp == 20) ? run_point_fast<12, 20>(&d, nd, F0, Ft, Fp0, Lp0, Lp, S0, state0, Dt, P, Fp, Fe, S, state, cnt)
+                          : run_point_fast<12, 0>(&d, nd, F0, Ft, Fp0, Lp0, Lp, S0, state0, Dt, P, Fp, Fe, S, state, cnt);
+    if (dPdF) {
+      static DmkPt<DMK_LAW_PHENOPOWERLAW, 2 * DMK_MAX_SYS, 0> p;
+      static DmkPtStore<DMK_LAW_PHENOPOWERLAW, 2 * DMK_MAX_SYS, 0> ps;
+      dmk_pt_bind(p, ps);
+      p.ph = &d; p.C66 = d.p.C66;
+      double ft[9], fp0[9];
+      for (int a = 0; a < 9; a++) { ft[a] = Ft[a]; fp0[a] = Fp0[a]; p.Fp[a] = Fp[a]; p.Fe[a] = Fe[a]; p.Lp[a] = Lp[a]; p.P[a] = P[a]; }
+      for (int a = 0; a < 6; a++) p.S[a] = S[a];
+      for (int k = 0; k < d.p.n_state; k++) p.st[k] = state[k];
+      tangent_point(p, ft, fp0, Dt, dPdF);
+    }
+    return ok;
+  }
 #define ARGS &d, nd, F0, Ft, Fp0, Lp0, Lp, S0, state0, dep, Dt, P, Fp, Fe, S, state, cnt, dPdF
   switch (p.law) {
     case DMK_LAW_NONE: return run_point<DMK_LAW_NONE, 0, 0>(ARGS);

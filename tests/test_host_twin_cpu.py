@@ -95,3 +95,52 @@ def test_state_machine_is_bit_identical_to_nested_loops():
             cut += int(a['cnt'][5])
         if phase != 'TWIP':
             assert cut > 0
+
+
+@pytest.mark.parametrize('phase,rate', [('Al_pheno', 3.0e-3), ('Cu_pheno', 2.0e-3)])
+def test_register_resident_pheno_matches_oracle(phase, rate):
+    """pheno_fast_dev.cuh (6x6 Woodbury Newton system, constant-bank tables; what the GPU runs for slip-only
+    phenopowerlaw phases) against the oracle over a multi-increment path: P, Fp, state to 1e-9, identical inner
+    iteration counters on cells that do not cut back."""
+    import twin
+    from solver_cpp_b200 import workloads as W, material as M
+    lib = twin.build()
+    cells = (4, 4, 3)
+    material, material_at, size = W.polycrystal(cells, 7, phase, 0)
+    o = ConstitutiveOracle(material, material_at)
+    m = M.Material(material, material_at)
+    num = M.make_numerics()
+    n = int(np.prod(cells))
+    ns = o.phases[0].n_state
+    Lp = np.zeros((n, 9))
+    rng = np.random.default_rng(2)
+    lib.twin_use_fast(1)
+    try:
+        n_clean = 0
+        for F in _path(cells, 4, rng, rate):
+            snap = o.snapshot()
+            o.mechanical_response(F.reshape(n, 9), 0.5)
+            _, dPdF_o = o.mechanical_response2(0.5, tangent=True)
+            cnt = np.zeros(6, dtype=np.int64)
+            for i in range(n):
+                r = twin.run_point(lib, m.phases[0], num, snap['F0'][i], F[i].reshape(9), snap['Fp0'][i], snap['Lp0'][i], Lp[i],
+                                   snap['S0'][i][V6], snap['state0'][i][:ns], np.zeros(1), 0.5, tangent=True)
+                Lp[i] = r['Lp']
+                cnt += r['cnt']
+                assert r['ok']
+                if o.point_cutbacks[i] or r['cnt'][5]:
+                    continue
+                n_clean += 1
+                e = np.abs(r['P'] - o.a['P'][i]).max() / np.abs(o.a['P'][i]).max()
+                e = max(e, np.abs(r['Fp'] - o.a['Fp'][i]).max(), np.abs(r['Fe'] - o.a['Fe'][i]).max())
+                atol = np.ctypeslib.as_array(o.phases[0].atol)[:ns]
+                e = max(e, (np.abs(r['state'][:ns] - o.a['state'][i, :ns]) / np.maximum(np.abs(o.a['state'][i, :ns]), atol)).max())
+                et = np.abs(r['dPdF'] - dPdF_o[i].reshape(81)).max() / np.abs(dPdF_o[i]).max()
+                assert e < 1e-9 and et < 1e-8, (phase, i, e, et)
+            if not o.point_cutbacks.any():
+                assert tuple(cnt[[0, 2, 3, 4, 5]]) == tuple(o.counters[[0, 2, 3, 4, 5]])
+            o.forward()
+        assert n_clean > 2 * n
+        assert np.abs(o.a['Lp']).max() > 1e-6
+    finally:
+        lib.twin_use_fast(0)
