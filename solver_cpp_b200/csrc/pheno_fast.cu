@@ -39,7 +39,7 @@ static int launch_pheno_fast(dmk_ctx* c, DmkPointArrays& pa, int ph, const DmkDe
                              double* d_P, double dt) {
   DmkPhenoK<NSL> K;
   dmk_pheno_fast_tables<NSL>(d, K);
-  const size_t smem = (size_t)PF_NARR * 2 * NSL * DMK_PF_THREADS * sizeof(double);
+  const size_t smem = (size_t)PfOff<NSL>::TOTAL * DMK_PF_THREADS * sizeof(double);
   static bool attr_set = false;
   if (!attr_set) {
     DMK_CUDA_CHECK(cudaFuncSetAttribute(dmk_pheno_fast_kernel<NSL, NEXP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

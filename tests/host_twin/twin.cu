@@ -62,7 +62,7 @@ static int run_point_fast(const DmkDevPhase* ph, const DmkNumDev& num, const dou
   for (int k = 0; k < 2 * NSL; k++) st0[k] = state0[k];
   pa.F0 = f0; pa.F = F; pa.Fp0 = fp0; pa.Fp = Fp; pa.Fe = Fe; pa.Lp0 = lp0; pa.Lp = Lp; pa.S0 = s0; pa.S = S; pa.state0 = st0; pa.state = state;
   pa.cutbacks = &cut;
-  double scratch[PF_NARR * 2 * NSL];
+  double scratch[PfOff<NSL>::TOTAL];
   DmkScr scr = {scratch, 1};
   DmkCnt cnt = {0, 0, 0, 0, 0, 0};
   const bool ok = pf_point<NSL, NEXP>(K, num, pa, 0, Frec, Prec, Dt, scr, cnt);
