@@ -152,7 +152,8 @@ int dmk_materialpoint_forward(dmk_ctx* ctx);                       /* f_material
 /* host copy, cell-major [cell][component]: "F","F0","Fp","Fp0","Fe","Lp","Lp0","S","S0" (row-major 3x3), "state","state0",
  * "dep", and "cutbacks" (sub-step cut-backs of each cell in the last response call) */
 int dmk_get_state(dmk_ctx* ctx, const char* name, double* host_out, size_t n_doubles);
-int dmk_get_counters(dmk_ctx* ctx, long long counters[6]);         /* Lp iters, stress calls, state iters, substeps, cutbacks, ill */
+int dmk_get_counters(dmk_ctx* ctx, long long counters[7]);         /* Lp iters, stress calls, state iters, substeps, cutbacks, ill,
+                                                                     * cells deferred to the reference-order kernel */
 int dmk_terminally_ill(dmk_ctx* ctx, int* flag, int reset);
 
 /* ------------------------------------------------------------------ spectral half (device-resident fields)

@@ -99,11 +99,15 @@ __global__ void __launch_bounds__(DMK_PT_THREADS) dmk_constitutive_kernel(DmkPoi
 template <int LAW, int NS, int ND>
 __global__ void __launch_bounds__(DMK_PT_THREADS) dmk_constitutive_nested_kernel(DmkPointArrays pa, int phase, DmkNumDev num,
                                                                           const double* __restrict__ Fin, double* __restrict__ Pout,
-                                                                          double Dt) {
+                                                                          double Dt, const int* __restrict__ list,
+                                                                          const unsigned* __restrict__ list_n) {
+  // list == nullptr: every cell of `phase`; else the *list_n cells of list[] (deferred by the register-resident kernel)
   const long long n = pa.n;
+  const long long total = list ? (long long)*list_n : n;
   DmkCnt cnt = {0, 0, 0, 0, 0, 0};
   unsigned ill = 0;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+  for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < total; j += (long long)gridDim.x * blockDim.x) {
+    const long long i = list ? (long long)list[j] : j;
     if (pa.phase[i] != phase) continue;
     DmkPt<LAW, NS, ND> p;
     DmkPtStore<LAW, NS, ND> pstore;
@@ -275,11 +279,18 @@ int dmk_points_constitutive(dmk_ctx* c, const double* d_F, double* d_P, double d
   for (int ph = 0; ph < pa.n_phases; ph++) {
     if (pa.n_cells_of_phase[ph] == 0) continue;
     const int law = pa.law_of_phase[ph], nst = pa.nstate_of_phase[ph];
-    bool handled = false;
-    if (!use_generic) { int rc = dmk_points_pheno_fast(c, ph, nd, d_F, d_P, dt, &handled); if (rc) return rc; }
-    if (handled) { c->launches++; continue; }
+    bool handled = false, deferred = false;
+    if (!use_generic) { int rc = dmk_points_pheno_fast(c, ph, nd, d_F, d_P, dt, &handled, &deferred); if (rc) return rc; }
+    if (handled) {
+      c->launches++;
+      if (deferred) {          // second pass over the deferred cells only (count read on the device: no host round trip)
+        DMK_DISPATCH(dmk_constitutive_nested_kernel, law, nst, <<<148 * 4, DMK_PT_THREADS, 0, c->stream>>>(pa, ph, nd, d_F, d_P, dt, pa.defer_list, pa.d_defer_count));
+        c->launches++;
+      }
+      continue;
+    }
     if (use_machine) DMK_LAUNCH_PERSISTENT(dmk_constitutive_kernel, law, nst, pa.n, c->stream, (pa, ph, nd, d_F, d_P, dt));
-    else DMK_DISPATCH(dmk_constitutive_nested_kernel, law, nst, <<<point_grid(pa.n), DMK_PT_THREADS, 0, c->stream>>>(pa, ph, nd, d_F, d_P, dt));
+    else DMK_DISPATCH(dmk_constitutive_nested_kernel, law, nst, <<<point_grid(pa.n), DMK_PT_THREADS, 0, c->stream>>>(pa, ph, nd, d_F, d_P, dt, nullptr, nullptr));
     c->launches++;
   }
   DMK_CUDA_CHECK(cudaGetLastError());
@@ -344,7 +355,7 @@ void dmk_points_teardown(dmk_ctx* c) {
   cudaFree(pa->phase); cudaFree(pa->F0); cudaFree(pa->F); cudaFree(pa->Fp0); cudaFree(pa->Fp); cudaFree(pa->Fe);
   cudaFree(pa->Lp0); cudaFree(pa->Lp); cudaFree(pa->S0); cudaFree(pa->S); cudaFree(pa->state0); cudaFree(pa->state);
   if (pa->dep) cudaFree(pa->dep);
-  cudaFree(pa->nrm); cudaFree(pa->cutbacks); cudaFree(pa->d_phases); cudaFree(pa->d_counters); cudaFree(pa->d_ill);
+  cudaFree(pa->nrm); cudaFree(pa->cutbacks); cudaFree(pa->defer_list); cudaFree(pa->d_defer_count); cudaFree(pa->d_phases); cudaFree(pa->d_counters); cudaFree(pa->d_ill);
   delete[] pa->h_phases;
   delete[] pa->h_dev_phases;
   delete pa;
@@ -425,6 +436,9 @@ extern "C" int dmk_material_init(dmk_ctx* c, const dmk_phase* phases, int n_phas
   DMK_CUDA_CHECK(cudaMalloc((void**)&pa->phase, n * sizeof(int)));
   DMK_CUDA_CHECK(cudaMalloc((void**)&pa->cutbacks, n * sizeof(int)));
   DMK_CUDA_CHECK(cudaMemset(pa->cutbacks, 0, n * sizeof(int)));
+  DMK_CUDA_CHECK(cudaMalloc((void**)&pa->defer_list, n * sizeof(int)));
+  DMK_CUDA_CHECK(cudaMalloc((void**)&pa->d_defer_count, sizeof(unsigned)));
+  DMK_CUDA_CHECK(cudaMemset(pa->d_defer_count, 0, sizeof(unsigned)));
   DMK_CUDA_CHECK(cudaMalloc((void**)&pa->d_phases, n_phases * sizeof(DmkDevPhase)));
   DMK_CUDA_CHECK(cudaMalloc((void**)&pa->d_counters, 8 * sizeof(unsigned long long)));
   DMK_CUDA_CHECK(cudaMalloc((void**)&pa->d_ill, sizeof(int)));
@@ -502,13 +516,13 @@ extern "C" int dmk_terminally_ill(dmk_ctx* c, int* flag, int reset) {
   return DMK_OK;
 }
 
-extern "C" int dmk_get_counters(dmk_ctx* c, long long counters[6]) {
+extern "C" int dmk_get_counters(dmk_ctx* c, long long counters[7]) {
   int rc = need_points(c); if (rc) return rc;
   unsigned long long h[8];
   DMK_CUDA_CHECK(cudaMemcpyAsync(h, c->pts->d_counters, sizeof h, cudaMemcpyDeviceToHost, c->stream));
   DMK_CUDA_CHECK(cudaStreamSynchronize(c->stream));
   counters[0] = (long long)h[0]; counters[1] = (long long)h[2]; counters[2] = (long long)h[3];
-  counters[3] = (long long)h[4]; counters[4] = (long long)h[5]; counters[5] = (long long)h[6];
+  counters[3] = (long long)h[4]; counters[4] = (long long)h[5]; counters[5] = (long long)h[6]; counters[6] = (long long)h[7];
   return DMK_OK;
 }
 

@@ -38,11 +38,13 @@ struct DmkPointArrays {
   double* dep;                         // [max_dep][n]  (dislotwin only, else nullptr)
   double* nrm;                         // [n] ||dPdF||^2 scratch of the tangent pass
   int* cutbacks;                       // [n] sub-step cut-backs of each cell in the last response call (diagnostic)
+  int* defer_list;                     // [n] cells the register-resident kernel handed to the reference-order kernel
+  unsigned* d_defer_count;             // entries of defer_list written by the last register-resident launch
   DmkDevPhase* d_phases;               // device array
   dmk_phase* h_phases;                 // host copy
   DmkDevPhase* h_dev_phases;           // host copy of the device tables
   int law_of_phase[DMK_MAX_PHASES], nstate_of_phase[DMK_MAX_PHASES], nsys_of_phase[DMK_MAX_PHASES];
-  unsigned long long* d_counters;      // 8: Lp iters, Li iters, stress calls, state iters, substeps, cutbacks, ill cells, -
+  unsigned long long* d_counters;      // 8: Lp iters, Li iters, stress calls, state iters, substeps, cutbacks, ill cells, deferred cells
   int* d_ill;                          // device flag (OR of broken cells since the last reset)
   long long n_cells_of_phase[DMK_MAX_PHASES];
 };
@@ -55,7 +57,8 @@ struct DmkNumDev {
 };
 
 int dmk_points_constitutive(dmk_ctx* c, const double* d_F, double* d_P, double dt);
-int dmk_points_pheno_fast(dmk_ctx* c, int ph, const DmkNumDev& nd, const double* d_F, double* d_P, double dt, bool* handled);
+int dmk_points_pheno_fast(dmk_ctx* c, int ph, const DmkNumDev& nd, const double* d_F, double* d_P, double dt, bool* handled,
+                          bool* deferred /*out: cells may be waiting in pa.defer_list*/);
 int dmk_points_tangent(dmk_ctx* c, double dt, double* d_Csum81 /*device, row-major sum over local cells*/,
                        double* d_dPdF /*optional [n][81] Fortran order*/);
 int dmk_points_tangent_cell(dmk_ctx* c, double dt, long long cell, double* d_out81 /*row-major*/);

@@ -1,0 +1,212 @@
+// Register-resident batched FFT passes for power-of-two line lengths (see fft_fast.cuh for the scheme).
+// Replaces FFT<5>::forward / backward of the reference (/root/reference/src/grid/fft.h:37-60, plans fft.cpp:48-58).
+//
+//   x r2c : rows of nx reals x 9 components; two rows packed as re/im of one complex line; HBM -> registers (first
+//           stage) -> shared -> Hermitian separation -> HBM.  Loads and stores are whole contiguous rows.
+//   y / z : tile = all N positions of a line x KT neighbouring kx records (KT*9 columns of double2); HBM -> registers
+//           -> shared -> registers -> HBM; every global access is a run of KT*144 bytes.
+//   x c2r : the reverse of r2c.
+// One tile (or NP row pairs) per CTA, 2-3 CTAs per SM, so that one CTA's loads overlap another's butterflies/stores.
+#include <cstdlib>
+#include <cstring>
+#include "fft_fast.cuh"
+
+bool dmk_fast_disabled() {
+  static const bool v = [] { const char* e = getenv("DMK_FFT"); return e && !strcmp(e, "generic"); }();
+  return v;
+}
+
+// ------------------------------------------------------------------------------------------------ strided pass (y, z)
+template <class PL, int KT, bool INV, int NT>
+__global__ void __launch_bounds__(NT) dmk_fast_line_kernel(const double2* __restrict__ src, double2* __restrict__ dst,
+                                                           const double2* __restrict__ tw, DmkLineMap ms, DmkLineMap md,
+                                                           int n0, int tiles0) {
+  constexpr int N = PL::N, R1 = PL::R1, R2 = PL::R2, R3 = PL::R3, B = KT * DMK_NC;
+  extern __shared__ double2 s[];
+  const int o = blockIdx.x / tiles0, i0 = (blockIdx.x - o * tiles0) * KT;
+  const int bact = min(KT, n0 - i0) * DMK_NC;
+  const bool ns_s = ms.split >= N, ns_d = md.split >= N;
+  auto ldg = [&](int, int p, int col) { return __ldg(src + dmk_line_rec_fast(ms, ns_s, o, p, i0) * DMK_NC + col); };
+  auto lds = [&](int, int p, int col) { return s[p * B + col]; };
+  auto sts = [&](int, int p, int col, double2 v) { s[p * B + col] = v; };
+  auto stg = [&](int, int p, int col, double2 v) { dst[dmk_line_rec_fast(md, ns_d, o, PL::freq(p), i0) * DMK_NC + col] = v; };
+  fstage<N, R1, R2 * R3, B, INV, false>(1, bact, tw, ldg, sts);
+  __syncthreads();
+  if constexpr (R3 > 1) {
+    fstage<N, R2, R3, B, INV, false>(1, bact, tw, lds, sts);
+    __syncthreads();
+    fstage<N, R3, 1, B, INV, false>(1, bact, tw, lds, stg);
+  } else {
+    fstage<N, R2, 1, B, INV, false>(1, bact, tw, lds, stg);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ x pass, r2c
+template <class PL, int NP, int NT>
+__global__ void __launch_bounds__(NT) dmk_fast_xr2c_kernel(const double* __restrict__ in, double2* __restrict__ out,
+                                                           const double2* __restrict__ tw, int nrows) {
+  constexpr int N = PL::N, R1 = PL::R1, R2 = PL::R2, R3 = PL::R3, B = DMK_NC, NXR = N / 2 + 1, NE = N * DMK_NC;
+  extern __shared__ double2 s[];
+  const int pair0 = blockIdx.x * NP;
+  const int npairs = (nrows + 1) / 2;
+  const int np = min(NP, npairs - pair0);
+  auto ldg = [&](int sub, int p, int col) {
+    const int ra = 2 * (pair0 + sub);
+    const double* a = in + (size_t)ra * NE + p * DMK_NC + col;
+    return make_double2(__ldg(a), (ra + 1 < nrows) ? __ldg(a + NE) : 0.0);
+  };
+  auto lds = [&](int sub, int p, int col) { return s[(sub * N + p) * B + col]; };
+  auto sts = [&](int sub, int p, int col, double2 v) { s[(sub * N + p) * B + col] = v; };
+  fstage<N, R1, R2 * R3, B, false, false>(np, B, tw, ldg, sts);
+  __syncthreads();
+  if constexpr (R3 > 1) {
+    fstage<N, R2, R3, B, false, false>(np, B, tw, lds, sts);
+    __syncthreads();
+    fstage<N, R3, 1, B, false, false>(np, B, tw, lds, sts);
+  } else {
+    fstage<N, R2, 1, B, false, false>(np, B, tw, lds, sts);
+  }
+  __syncthreads();
+  // Hermitian separation of the two packed rows: A_k = (Z_k + conj Z_{N-k}) / 2, B_k = (Z_k - conj Z_{N-k}) / (2i)
+  constexpr int PER = NXR * DMK_NC;
+  for (int t = threadIdx.x; t < np * PER; t += blockDim.x) {
+    const int sub = t / PER, r = t - sub * PER;
+    const int k = r / DMK_NC, c = r - k * DMK_NC;
+    const int kn = (N - k) & (N - 1);
+    const double2 zk = s[(sub * N + PL::slot(k)) * B + c], zn = s[(sub * N + PL::slot(kn)) * B + c];
+    const int ra = 2 * (pair0 + sub);
+    double2* oa = out + (size_t)ra * PER;
+    oa[r] = make_double2(0.5 * (zk.x + zn.x), 0.5 * (zk.y - zn.y));
+    if (ra + 1 < nrows) oa[PER + r] = make_double2(0.5 * (zk.y + zn.y), -0.5 * (zk.x - zn.x));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ x pass, c2r
+template <class PL, int NP, int NT>
+__global__ void __launch_bounds__(NT) dmk_fast_xc2r_kernel(const double2* __restrict__ in, double* __restrict__ out,
+                                                           const double2* __restrict__ tw, int nrows, double scale) {
+  constexpr int N = PL::N, R1 = PL::R1, R2 = PL::R2, R3 = PL::R3, B = DMK_NC, NXR = N / 2 + 1, NE = N * DMK_NC;
+  extern __shared__ double2 s[];
+  const int pair0 = blockIdx.x * NP;
+  const int npairs = (nrows + 1) / 2;
+  const int np = min(NP, npairs - pair0);
+  constexpr int PER = NXR * DMK_NC;
+  // Z_k = A_k + i B_k, Z_{N-k} = conj(A_k) + i conj(B_k), natural order
+  for (int t = threadIdx.x; t < np * PER; t += blockDim.x) {
+    const int sub = t / PER, r = t - sub * PER;
+    const int k = r / DMK_NC, c = r - k * DMK_NC;
+    const int ra = 2 * (pair0 + sub);
+    const double2* ia = in + (size_t)ra * PER;
+    double2 A = __ldg(ia + r);
+    double2 Bv = (ra + 1 < nrows) ? __ldg(ia + PER + r) : make_double2(0.0, 0.0);
+    const bool selfconj = (k == 0) || (2 * k == N);
+    if (selfconj) { A.y = 0.0; Bv.y = 0.0; }             // FFTW c2r ignores these imaginary parts
+    s[(sub * N + k) * B + c] = make_double2(A.x - Bv.y, A.y + Bv.x);
+    if (!selfconj) s[(sub * N + N - k) * B + c] = make_double2(A.x + Bv.y, Bv.x - A.y);
+  }
+  __syncthreads();
+  auto lds = [&](int sub, int p, int col) { return s[(sub * N + p) * B + col]; };
+  auto sts = [&](int sub, int p, int col, double2 v) { s[(sub * N + p) * B + col] = v; };
+  auto stg = [&](int sub, int p, int col, double2 v) {
+    const int ra = 2 * (pair0 + sub);
+    double* a = out + (size_t)ra * NE + PL::freq(p) * DMK_NC + col;
+    a[0] = v.x * scale;
+    if (ra + 1 < nrows) a[NE] = v.y * scale;
+  };
+  fstage<N, R1, R2 * R3, B, true, false>(np, B, tw, lds, sts);
+  __syncthreads();
+  if constexpr (R3 > 1) {
+    fstage<N, R2, R3, B, true, false>(np, B, tw, lds, sts);
+    __syncthreads();
+    fstage<N, R3, 1, B, true, false>(np, B, tw, lds, stg);
+  } else {
+    fstage<N, R2, 1, B, true, false>(np, B, tw, lds, stg);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+template <typename K>
+static int set_smem(K kernel, size_t smem) {
+  if (smem > 48 * 1024) DMK_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  return DMK_OK;
+}
+
+template <class PL, int KT, int NT>
+static int launch_line(bool inverse, const double2* src, double2* dst, const DmkFftPlan& pl, DmkLineMap ms, DmkLineMap md, int n0,
+                       int n_outer, cudaStream_t st) {
+  const size_t smem = (size_t)PL::N * KT * DMK_NC * sizeof(double2);
+  const int tiles0 = (n0 + KT - 1) / KT;
+  const long long grid = (long long)tiles0 * n_outer;
+  if (grid > 0x7fffffffLL) { dmk_set_error("line pass grid too large"); return DMK_ERR_UNSUPPORTED; }
+  int rc;
+  if (inverse) {
+    if ((rc = set_smem(dmk_fast_line_kernel<PL, KT, true, NT>, smem))) return rc;
+    dmk_fast_line_kernel<PL, KT, true, NT><<<(int)grid, NT, smem, st>>>(src, dst, pl.tw, ms, md, n0, tiles0);
+  } else {
+    if ((rc = set_smem(dmk_fast_line_kernel<PL, KT, false, NT>, smem))) return rc;
+    dmk_fast_line_kernel<PL, KT, false, NT><<<(int)grid, NT, smem, st>>>(src, dst, pl.tw, ms, md, n0, tiles0);
+  }
+  DMK_CUDA_CHECK(cudaGetLastError());
+  return DMK_OK;
+}
+
+int dmk_fast_line_pass(bool inverse, const double2* src, double2* dst, const DmkFftPlan& pl, DmkLineMap ms, DmkLineMap md,
+                       int n0, int n_outer, cudaStream_t st, bool* done) {
+  *done = true;
+  if (dmk_fast_disabled()) { *done = false; return DMK_OK; }
+  switch (pl.n) {
+    case 16: return launch_line<DmkFastPlan<4, 4, 1>, 8, 288>(inverse, src, dst, pl, ms, md, n0, n_outer, st);
+    case 32: return launch_line<DmkFastPlan<8, 4, 1>, 8, 288>(inverse, src, dst, pl, ms, md, n0, n_outer, st);
+    case 64: return launch_line<DmkFastPlan<8, 8, 1>, 4, 288>(inverse, src, dst, pl, ms, md, n0, n_outer, st);
+    case 128: return launch_line<DmkFastPlan<16, 8, 1>, 4, 288>(inverse, src, dst, pl, ms, md, n0, n_outer, st);
+    case 256: return launch_line<DmkFastPlan<16, 16, 1>, 2, 288>(inverse, src, dst, pl, ms, md, n0, n_outer, st);
+    case 512: return launch_line<DmkFastPlan<8, 8, 8>, 1, 288>(inverse, src, dst, pl, ms, md, n0, n_outer, st);
+    default: *done = false; return DMK_OK;
+  }
+}
+
+template <class PL, int NP, int NT>
+static int launch_xr2c(const double* in, double2* out, const DmkFftPlan& pl, int nrows, cudaStream_t st) {
+  const size_t smem = (size_t)PL::N * NP * DMK_NC * sizeof(double2);
+  const int npairs = (nrows + 1) / 2, grid = (npairs + NP - 1) / NP;
+  int rc = set_smem(dmk_fast_xr2c_kernel<PL, NP, NT>, smem); if (rc) return rc;
+  dmk_fast_xr2c_kernel<PL, NP, NT><<<grid, NT, smem, st>>>(in, out, pl.tw, nrows);
+  DMK_CUDA_CHECK(cudaGetLastError());
+  return DMK_OK;
+}
+template <class PL, int NP, int NT>
+static int launch_xc2r(const double2* in, double* out, const DmkFftPlan& pl, int nrows, double scale, cudaStream_t st) {
+  const size_t smem = (size_t)PL::N * NP * DMK_NC * sizeof(double2);
+  const int npairs = (nrows + 1) / 2, grid = (npairs + NP - 1) / NP;
+  int rc = set_smem(dmk_fast_xc2r_kernel<PL, NP, NT>, smem); if (rc) return rc;
+  dmk_fast_xc2r_kernel<PL, NP, NT><<<grid, NT, smem, st>>>(in, out, pl.tw, nrows, scale);
+  DMK_CUDA_CHECK(cudaGetLastError());
+  return DMK_OK;
+}
+
+int dmk_fast_xpass_r2c(const double* in, double2* out, const DmkFftPlan& pl, int nrows, cudaStream_t st, bool* done) {
+  *done = true;
+  if (dmk_fast_disabled()) { *done = false; return DMK_OK; }
+  switch (pl.n) {
+    case 16: return launch_xr2c<DmkFastPlan<4, 4, 1>, 8, 288>(in, out, pl, nrows, st);
+    case 32: return launch_xr2c<DmkFastPlan<8, 4, 1>, 8, 288>(in, out, pl, nrows, st);
+    case 64: return launch_xr2c<DmkFastPlan<8, 8, 1>, 4, 288>(in, out, pl, nrows, st);
+    case 128: return launch_xr2c<DmkFastPlan<16, 8, 1>, 4, 288>(in, out, pl, nrows, st);
+    case 256: return launch_xr2c<DmkFastPlan<16, 16, 1>, 2, 288>(in, out, pl, nrows, st);
+    case 512: return launch_xr2c<DmkFastPlan<8, 8, 8>, 1, 288>(in, out, pl, nrows, st);
+    default: *done = false; return DMK_OK;
+  }
+}
+int dmk_fast_xpass_c2r(const double2* in, double* out, const DmkFftPlan& pl, int nrows, double scale, cudaStream_t st, bool* done) {
+  *done = true;
+  if (dmk_fast_disabled()) { *done = false; return DMK_OK; }
+  switch (pl.n) {
+    case 16: return launch_xc2r<DmkFastPlan<4, 4, 1>, 8, 288>(in, out, pl, nrows, scale, st);
+    case 32: return launch_xc2r<DmkFastPlan<8, 4, 1>, 8, 288>(in, out, pl, nrows, scale, st);
+    case 64: return launch_xc2r<DmkFastPlan<8, 8, 1>, 4, 288>(in, out, pl, nrows, scale, st);
+    case 128: return launch_xc2r<DmkFastPlan<16, 8, 1>, 4, 288>(in, out, pl, nrows, scale, st);
+    case 256: return launch_xc2r<DmkFastPlan<16, 16, 1>, 2, 288>(in, out, pl, nrows, scale, st);
+    case 512: return launch_xc2r<DmkFastPlan<8, 8, 8>, 1, 288>(in, out, pl, nrows, scale, st);
+    default: *done = false; return DMK_OK;
+  }
+}

@@ -13,6 +13,7 @@
 #include <cmath>
 #include "fft.cuh"
 #include "fft_host.h"
+#include "fft_fast.cuh"
 
 // ------------------------------------------------------------------------------------------------ x pass, r2c
 __global__ void __launch_bounds__(256, 2) dmk_xpass_r2c_kernel(const double* __restrict__ in, double2* __restrict__ out,
@@ -194,6 +195,7 @@ static int grid_for(K kernel, int threads, size_t smem, long long work, int* gri
 }
 
 int dmk_launch_xpass_r2c(const double* in, double2* out, const DmkFftPlan& pl, int nrows, cudaStream_t st) {
+  { bool done = false; int rc = dmk_fast_xpass_r2c(in, out, pl, nrows, st, &done); if (rc || done) return rc; }
   size_t smem = (size_t)pl.n * DMK_NC * sizeof(double2);
   int grid; int rc = grid_for(dmk_xpass_r2c_kernel, 256, smem, (nrows + 1) / 2, &grid); if (rc) return rc;
   dmk_xpass_r2c_kernel<<<grid, 256, smem, st>>>(in, out, pl, nrows);
@@ -202,6 +204,7 @@ int dmk_launch_xpass_r2c(const double* in, double2* out, const DmkFftPlan& pl, i
 }
 
 int dmk_launch_xpass_c2r(const double2* in, double* out, const DmkFftPlan& pl, int nrows, double scale, cudaStream_t st) {
+  { bool done = false; int rc = dmk_fast_xpass_c2r(in, out, pl, nrows, scale, st, &done); if (rc || done) return rc; }
   size_t smem = (size_t)pl.n * DMK_NC * sizeof(double2);
   int grid; int rc = grid_for(dmk_xpass_c2r_kernel, 256, smem, (nrows + 1) / 2, &grid); if (rc) return rc;
   dmk_xpass_c2r_kernel<<<grid, 256, smem, st>>>(in, out, pl, nrows, scale);
@@ -211,6 +214,7 @@ int dmk_launch_xpass_c2r(const double2* in, double* out, const DmkFftPlan& pl, i
 
 int dmk_launch_line_pass(bool inverse, const double2* src, double2* dst, const DmkFftPlan& pl, DmkLineMap ms,
                          DmkLineMap md, int n0, int n_outer, int KT, cudaStream_t st) {
+  { bool done = false; int rc = dmk_fast_line_pass(inverse, src, dst, pl, ms, md, n0, n_outer, st, &done); if (rc || done) return rc; }
   if (KT < 1) KT = 1;
   if (KT > n0) KT = n0;
   size_t smem = (size_t)pl.n * KT * DMK_NC * sizeof(double2);

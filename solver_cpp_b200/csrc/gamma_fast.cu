@@ -1,0 +1,121 @@
+// Fused z pass for power-of-two nz on the register-resident FFT stages (fft_fast.cuh):
+//   HBM -> [first forward stage in registers] -> shared -> [last forward stage] -> divergence RMS + Gamma contraction on
+//   the digit-reversed line in shared memory -> [adjoint of the last stage] -> [adjoint of the first stage] -> HBM.
+// Replaces MechBase::calculate_divergence_rms (/root/reference/src/grid/mech_base.cpp:302-398) and
+// MechBase::gamma_convolution (mech_base.cpp:400-477); operator definition and per-k-point arithmetic: gamma_kernels.cu,
+// gamma_point.cuh (shared with the shared-memory-only kernel, so both produce the same bits per k-point).
+// One tile (N kz positions x KT kx records) per CTA; the half spectrum is read once and written once (144 B/point).
+#include "fft_fast.cuh"
+#include "gamma_point.cuh"
+
+template <class PL, int KT, bool IMAG_XI, int NT>
+__global__ void __launch_bounds__(NT) dmk_fast_gamma_kernel(double2* __restrict__ data, const double2* __restrict__ tw,
+                                                            DmkLineMap map, int n0, int tiles0, DmkGammaParams gp) {
+  constexpr int N = PL::N, R1 = PL::R1, R2 = PL::R2, R3 = PL::R3, B = KT * DMK_NC;
+  extern __shared__ double2 s[];
+  __shared__ double sC[81];
+  __shared__ double sred[NT / 32];
+  const int o = blockIdx.x / tiles0, i0 = (blockIdx.x - o * tiles0) * KT;
+  const int kt = min(KT, n0 - i0);
+  const int bact = kt * DMK_NC;
+  const bool nosplit = map.split >= N;
+  for (int i = threadIdx.x; i < 81; i += NT) sC[i] = gp.C_ref[i];
+  auto ldg = [&](int, int p, int col) { return data[dmk_line_rec_fast(map, nosplit, o, p, i0) * DMK_NC + col]; };
+  auto lds = [&](int, int p, int col) { return s[p * B + col]; };
+  auto sts = [&](int, int p, int col, double2 v) { s[p * B + col] = v; };
+  auto stg = [&](int, int p, int col, double2 v) { data[dmk_line_rec_fast(map, nosplit, o, p, i0) * DMK_NC + col] = v; };
+  // ---- forward along z: natural order in HBM -> digit-reversed slots in shared memory
+  fstage<N, R1, R2 * R3, B, false, false>(1, bact, tw, ldg, sts);
+  __syncthreads();
+  if constexpr (R3 > 1) {
+    fstage<N, R2, R3, B, false, false>(1, bact, tw, lds, sts);
+    __syncthreads();
+    fstage<N, R3, 1, B, false, false>(1, bact, tw, lds, sts);
+  } else {
+    fstage<N, R2, 1, B, false, false>(1, bact, tw, lds, sts);
+  }
+  __syncthreads();
+  // ---- per k-point: divergence contribution and Gamma contraction (slot -> kz = PL::freq(slot))
+  const double resc[3] = {gp.rescale[0], gp.rescale[1], gp.rescale[2]};
+  const int ky = o + gp.ky_offset;
+  const int nxr = n0;
+  double div_local = 0.0;
+  for (int pnt = threadIdx.x; pnt < N * KT; pnt += NT) {
+    const int slot = pnt / KT, j = pnt - slot * KT;
+    if (j >= kt) continue;
+    const int kz = PL::freq(slot);
+    const int kx = i0 + j;
+    double2 t[9];
+    double2* ps = s + slot * B + j * DMK_NC;
+#pragma unroll
+    for (int c = 0; c < 9; c++) t[c] = ps[c];
+    double2 xi[3];
+    load_xi(gp, kx, ky, kz, xi);
+    const bool is_dc = (kx == 0) && (ky == 0) && (kz == 0);
+    const double wgt = ((kx == 0) ? 1.0 : 0.0) + ((kx == nxr - 1) ? 1.0 : 0.0) + ((kx > 0 && kx < nxr - 1) ? 2.0 : 0.0);
+    double d;
+    if (IMAG_XI) {
+      const double q[3] = {xi[0].y, xi[1].y, xi[2].y};
+      d = gamma_point_imag(t, sC, q, resc, is_dc, gp.dc_value);
+    } else {
+      d = gamma_point_cplx(t, sC, xi, resc, is_dc, gp.dc_value);
+    }
+    div_local += wgt * d;
+#pragma unroll
+    for (int c = 0; c < 9; c++) ps[c] = t[c];
+  }
+  __syncthreads();
+  // ---- inverse along z: the adjoint network, digit-reversed slots -> natural order in HBM (unnormalised)
+  if constexpr (R3 > 1) {
+    fstage<N, R3, 1, B, true, true>(1, bact, tw, lds, sts);
+    __syncthreads();
+    fstage<N, R2, R3, B, true, true>(1, bact, tw, lds, sts);
+  } else {
+    fstage<N, R2, 1, B, true, true>(1, bact, tw, lds, sts);
+  }
+  __syncthreads();
+  fstage<N, R1, R2 * R3, B, true, true>(1, bact, tw, lds, stg);
+  // ---- block reduction of the divergence sum, one atomic per CTA
+  for (int off = 16; off > 0; off >>= 1) div_local += __shfl_down_sync(0xffffffffu, div_local, off);
+  if ((threadIdx.x & 31) == 0) sred[threadIdx.x >> 5] = div_local;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double tot = 0.0;
+#pragma unroll
+    for (int w = 0; w < NT / 32; w++) tot += sred[w];
+    atomicAdd(gp.div_accum, tot);
+  }
+}
+
+template <class PL, int KT, int NT>
+static int launch_gamma(double2* data, const DmkFftPlan& pl, DmkLineMap map, int n0, int n_outer, const DmkGammaParams& gp,
+                        cudaStream_t st, bool imag_xi) {
+  const size_t smem = (size_t)PL::N * KT * DMK_NC * sizeof(double2);
+  const int tiles0 = (n0 + KT - 1) / KT;
+  const long long grid = (long long)tiles0 * n_outer;
+  if (grid > 0x7fffffffLL) { dmk_set_error("gamma pass grid too large"); return DMK_ERR_UNSUPPORTED; }
+  if (imag_xi) {
+    if (smem > 48 * 1024) DMK_CUDA_CHECK(cudaFuncSetAttribute(dmk_fast_gamma_kernel<PL, KT, true, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dmk_fast_gamma_kernel<PL, KT, true, NT><<<(int)grid, NT, smem, st>>>(data, pl.tw, map, n0, tiles0, gp);
+  } else {
+    if (smem > 48 * 1024) DMK_CUDA_CHECK(cudaFuncSetAttribute(dmk_fast_gamma_kernel<PL, KT, false, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dmk_fast_gamma_kernel<PL, KT, false, NT><<<(int)grid, NT, smem, st>>>(data, pl.tw, map, n0, tiles0, gp);
+  }
+  DMK_CUDA_CHECK(cudaGetLastError());
+  return DMK_OK;
+}
+
+int dmk_fast_gamma_zpass(double2* data, const DmkFftPlan& plz, DmkLineMap map, int n0, int n_outer, const DmkGammaParams& gp,
+                         cudaStream_t st, bool imag_xi, bool* done) {
+  *done = true;
+  if (dmk_fast_disabled()) { *done = false; return DMK_OK; }
+  switch (plz.n) {
+    case 16: return launch_gamma<DmkFastPlan<4, 4, 1>, 8, 288>(data, plz, map, n0, n_outer, gp, st, imag_xi);
+    case 32: return launch_gamma<DmkFastPlan<8, 4, 1>, 8, 288>(data, plz, map, n0, n_outer, gp, st, imag_xi);
+    case 64: return launch_gamma<DmkFastPlan<8, 8, 1>, 4, 288>(data, plz, map, n0, n_outer, gp, st, imag_xi);
+    case 128: return launch_gamma<DmkFastPlan<16, 8, 1>, 4, 288>(data, plz, map, n0, n_outer, gp, st, imag_xi);
+    case 256: return launch_gamma<DmkFastPlan<16, 16, 1>, 2, 288>(data, plz, map, n0, n_outer, gp, st, imag_xi);
+    case 512: return launch_gamma<DmkFastPlan<8, 8, 8>, 1, 288>(data, plz, map, n0, n_outer, gp, st, imag_xi);
+    default: *done = false; return DMK_OK;
+  }
+}

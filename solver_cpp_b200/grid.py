@@ -173,9 +173,9 @@ class GridContext:
         return bool(f.value)
 
     def counters(self):
-        a = (C.c_longlong * 6)()
+        a = (C.c_longlong * 7)()
         L.check(self.lib.dmk_get_counters(self.ctx, a))
-        return dict(zip(('Lp_iter', 'stress_calls', 'state_iter', 'substeps', 'cutbacks', 'ill_cells'), list(a)))
+        return dict(zip(('Lp_iter', 'stress_calls', 'state_iter', 'substeps', 'cutbacks', 'ill_cells', 'deferred'), list(a)))
 
     def get_state(self, name, comps):
         out = np.zeros((self.n_local, comps))

@@ -44,6 +44,10 @@ static int run_point(const DmkDevPhase* ph, const DmkNumDev& num, const double* 
   return ok ? 1 : 0;
 }
 
+static int g_defer = 0;          // pf_stress deferral threshold (0: never defer), as DMK_PHENO_DEFER in the product
+static int g_last_deferred = 0;
+extern "C" void twin_set_defer(int v) { g_defer = v; }
+extern "C" int twin_last_deferred() { return g_last_deferred; }
 // the register-resident slip-only phenopowerlaw formulation (pheno_fast_dev.cuh) on a one-point DmkPointArrays
 template <int NSL, int NEXP>
 static int run_point_fast(const DmkDevPhase* ph, const DmkNumDev& num, const double* F0, const double* Ft, const double* Fp0,
@@ -65,10 +69,11 @@ static int run_point_fast(const DmkDevPhase* ph, const DmkNumDev& num, const dou
   double scratch[PfOff<NSL>::TOTAL];
   DmkScr scr = {scratch, 1};
   DmkCnt cnt = {0, 0, 0, 0, 0, 0};
-  const bool ok = pf_point<NSL, NEXP>(K, num, pa, 0, Frec, Prec, Dt, scr, cnt);
+  const int rc = pf_point<NSL, NEXP, 1>(K, num, g_defer, pa, 0, Frec, Prec, Dt, scr, cnt);
+  if (rc == PF_DEFER) return 2;                       // nothing written: the caller replays the point on the reference-order path
   for (int a = 0; a < 3; a++) for (int b = 0; b < 3; b++) P[3 * a + b] = Prec[a + 3 * b];
   cnt_out[0] = cnt.Lp_iter; cnt_out[1] = cnt.Li_iter; cnt_out[2] = cnt.stress_calls; cnt_out[3] = cnt.state_iter; cnt_out[4] = cnt.substeps; cnt_out[5] = cnt.cutbacks;
-  return ok ? 1 : 0;
+  return rc == PF_OK ? 1 : 0;
 }
 static int g_use_fast = 0;       // 1: route eligible phases through pheno_fast_dev.cuh
 extern "C" void twin_use_fast(int v) { g_use_fast = v; }
@@ -101,9 +106,11 @@ extern "C" int twin_point(const dmk_phase* phase, const dmk_numerics* n, const d
   nd.N_iter_state_max = n->N_iter_state_max; nd.N_iter_Lp_max = n->N_iter_Lp_max; nd.r_linesearch_Lp = n->r_linesearch_Lp;
   nd.eps_rel_Lp = n->eps_rel_Lp; nd.eps_abs_Lp = n->eps_abs_Lp; nd.f_update_jacobi_Lp = n->f_update_jacobi_Lp > 0 ? n->f_update_jacobi_Lp : 1;
   int nexp = 0;
+  g_last_deferred = 0;
   if (g_use_fast && dmk_pheno_fast_eligible(d, 12, &nexp)) {
     int ok = (nexp == 20) ? run_point_fast<12, 20>(&d, nd, F0, Ft, Fp0, Lp0, Lp, S0, state0, Dt, P, Fp, Fe, S, state, cnt)
                           : run_point_fast<12, 0>(&d, nd, F0, Ft, Fp0, Lp0, Lp, S0, state0, Dt, P, Fp, Fe, S, state, cnt);
+    if (ok == 2) { g_last_deferred = 1; goto generic; }
     if (dPdF) {
       static DmkPt<DMK_LAW_PHENOPOWERLAW, 2 * DMK_MAX_SYS, 0> p;
       static DmkPtStore<DMK_LAW_PHENOPOWERLAW, 2 * DMK_MAX_SYS, 0> ps;
@@ -117,6 +124,7 @@ extern "C" int twin_point(const dmk_phase* phase, const dmk_numerics* n, const d
     }
     return ok;
   }
+generic:
 #define ARGS &d, nd, F0, Ft, Fp0, Lp0, Lp, S0, state0, dep, Dt, P, Fp, Fe, S, state, cnt, dPdF
   switch (p.law) {
     case DMK_LAW_NONE: return run_point<DMK_LAW_NONE, 0, 0>(ARGS);

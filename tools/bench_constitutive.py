@@ -37,6 +37,7 @@ for inc in range(1, reps + 1):
     ms_t = e0.elapsed_time(e1)
     g.materialpoint_forward()
     res.append(dict(inc=inc, ms=ms, Mpts_per_s=n ** 3 / ms / 1e3, Lp_iter_per_pt=(c1['Lp_iter'] - c0['Lp_iter']) / n ** 3,
-                    stress_calls_per_pt=(c1['stress_calls'] - c0['stress_calls']) / n ** 3, ms_tangent=ms_t,
+                    stress_calls_per_pt=(c1['stress_calls'] - c0['stress_calls']) / n ** 3,
+                    deferred_frac=(c1['deferred'] - c0['deferred']) / n ** 3, ms_tangent=ms_t,
                     ill=g.terminally_ill(), P11=float(P[..., 0].mean()) / 1e6))
 print(json.dumps(dict(n=n, phase=phase, setup_s=t_setup, evals=res)))
