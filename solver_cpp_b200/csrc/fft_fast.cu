@@ -17,8 +17,8 @@ bool dmk_fast_disabled() {
 }
 
 // ------------------------------------------------------------------------------------------------ strided pass (y, z)
-template <class PL, int KT, bool INV, int NT>
-__global__ void __launch_bounds__(NT) dmk_fast_line_kernel(const double2* __restrict__ src, double2* __restrict__ dst,
+template <class PL, int KT, bool INV, int NT, int MINB>
+__global__ void __launch_bounds__(NT, MINB) dmk_fast_line_kernel(const double2* __restrict__ src, double2* __restrict__ dst,
                                                            const double2* __restrict__ tw, DmkLineMap ms, DmkLineMap md,
                                                            int n0, int tiles0) {
   constexpr int N = PL::N, R1 = PL::R1, R2 = PL::R2, R3 = PL::R3, B = KT * DMK_NC;
@@ -42,8 +42,8 @@ __global__ void __launch_bounds__(NT) dmk_fast_line_kernel(const double2* __rest
 }
 
 // ------------------------------------------------------------------------------------------------ x pass, r2c
-template <class PL, int NP, int NT>
-__global__ void __launch_bounds__(NT) dmk_fast_xr2c_kernel(const double* __restrict__ in, double2* __restrict__ out,
+template <class PL, int NP, int NT, int MINB>
+__global__ void __launch_bounds__(NT, MINB) dmk_fast_xr2c_kernel(const double* __restrict__ in, double2* __restrict__ out,
                                                            const double2* __restrict__ tw, int nrows) {
   constexpr int N = PL::N, R1 = PL::R1, R2 = PL::R2, R3 = PL::R3, B = DMK_NC, NXR = N / 2 + 1, NE = N * DMK_NC;
   extern __shared__ double2 s[];
@@ -82,8 +82,8 @@ __global__ void __launch_bounds__(NT) dmk_fast_xr2c_kernel(const double* __restr
 }
 
 // ------------------------------------------------------------------------------------------------ x pass, c2r
-template <class PL, int NP, int NT>
-__global__ void __launch_bounds__(NT) dmk_fast_xc2r_kernel(const double2* __restrict__ in, double* __restrict__ out,
+template <class PL, int NP, int NT, int MINB>
+__global__ void __launch_bounds__(NT, MINB) dmk_fast_xc2r_kernel(const double2* __restrict__ in, double* __restrict__ out,
                                                            const double2* __restrict__ tw, int nrows, double scale) {
   constexpr int N = PL::N, R1 = PL::R1, R2 = PL::R2, R3 = PL::R3, B = DMK_NC, NXR = N / 2 + 1, NE = N * DMK_NC;
   extern __shared__ double2 s[];
@@ -131,7 +131,7 @@ static int set_smem(K kernel, size_t smem) {
   return DMK_OK;
 }
 
-template <class PL, int KT, int NT>
+template <class PL, int KT, int NT, int MINB = 1>
 static int launch_line(bool inverse, const double2* src, double2* dst, const DmkFftPlan& pl, DmkLineMap ms, DmkLineMap md, int n0,
                        int n_outer, cudaStream_t st) {
   const size_t smem = (size_t)PL::N * KT * DMK_NC * sizeof(double2);
@@ -140,11 +140,11 @@ static int launch_line(bool inverse, const double2* src, double2* dst, const Dmk
   if (grid > 0x7fffffffLL) { dmk_set_error("line pass grid too large"); return DMK_ERR_UNSUPPORTED; }
   int rc;
   if (inverse) {
-    if ((rc = set_smem(dmk_fast_line_kernel<PL, KT, true, NT>, smem))) return rc;
-    dmk_fast_line_kernel<PL, KT, true, NT><<<(int)grid, NT, smem, st>>>(src, dst, pl.tw, ms, md, n0, tiles0);
+    if ((rc = set_smem(dmk_fast_line_kernel<PL, KT, true, NT, MINB>, smem))) return rc;
+    dmk_fast_line_kernel<PL, KT, true, NT, MINB><<<(int)grid, NT, smem, st>>>(src, dst, pl.tw, ms, md, n0, tiles0);
   } else {
-    if ((rc = set_smem(dmk_fast_line_kernel<PL, KT, false, NT>, smem))) return rc;
-    dmk_fast_line_kernel<PL, KT, false, NT><<<(int)grid, NT, smem, st>>>(src, dst, pl.tw, ms, md, n0, tiles0);
+    if ((rc = set_smem(dmk_fast_line_kernel<PL, KT, false, NT, MINB>, smem))) return rc;
+    dmk_fast_line_kernel<PL, KT, false, NT, MINB><<<(int)grid, NT, smem, st>>>(src, dst, pl.tw, ms, md, n0, tiles0);
   }
   DMK_CUDA_CHECK(cudaGetLastError());
   return DMK_OK;
@@ -154,32 +154,33 @@ int dmk_fast_line_pass(bool inverse, const double2* src, double2* dst, const Dmk
                        int n0, int n_outer, cudaStream_t st, bool* done) {
   *done = true;
   if (dmk_fast_disabled()) { *done = false; return DMK_OK; }
+  // tile width, threads and CTAs/SM per length: tools/fft_tune.cu sweeps on B200 (profiles/r01_fft_tuning.md)
   switch (pl.n) {
-    case 16: return launch_line<DmkFastPlan<4, 4, 1>, 8, 288>(inverse, src, dst, pl, ms, md, n0, n_outer, st);
-    case 32: return launch_line<DmkFastPlan<8, 4, 1>, 8, 288>(inverse, src, dst, pl, ms, md, n0, n_outer, st);
-    case 64: return launch_line<DmkFastPlan<8, 8, 1>, 4, 288>(inverse, src, dst, pl, ms, md, n0, n_outer, st);
-    case 128: return launch_line<DmkFastPlan<16, 8, 1>, 4, 288>(inverse, src, dst, pl, ms, md, n0, n_outer, st);
-    case 256: return launch_line<DmkFastPlan<16, 16, 1>, 2, 288>(inverse, src, dst, pl, ms, md, n0, n_outer, st);
-    case 512: return launch_line<DmkFastPlan<8, 8, 8>, 1, 288>(inverse, src, dst, pl, ms, md, n0, n_outer, st);
+    case 16: return launch_line<DmkFastPlan<4, 4, 1>, 4, 144, 4>(inverse, src, dst, pl, ms, md, n0, n_outer, st);
+    case 32: return launch_line<DmkFastPlan<8, 4, 1>, 4, 144, 4>(inverse, src, dst, pl, ms, md, n0, n_outer, st);
+    case 64: return launch_line<DmkFastPlan<8, 8, 1>, 2, 144, 4>(inverse, src, dst, pl, ms, md, n0, n_outer, st);
+    case 128: return launch_line<DmkFastPlan<16, 8, 1>, 2, 144, 3>(inverse, src, dst, pl, ms, md, n0, n_outer, st);
+    case 256: return launch_line<DmkFastPlan<16, 16, 1>, 1, 144, 3>(inverse, src, dst, pl, ms, md, n0, n_outer, st);
+    case 512: return launch_line<DmkFastPlan<8, 8, 8>, 1, 288, 2>(inverse, src, dst, pl, ms, md, n0, n_outer, st);
     default: *done = false; return DMK_OK;
   }
 }
 
-template <class PL, int NP, int NT>
+template <class PL, int NP, int NT, int MINB = 1>
 static int launch_xr2c(const double* in, double2* out, const DmkFftPlan& pl, int nrows, cudaStream_t st) {
   const size_t smem = (size_t)PL::N * NP * DMK_NC * sizeof(double2);
   const int npairs = (nrows + 1) / 2, grid = (npairs + NP - 1) / NP;
-  int rc = set_smem(dmk_fast_xr2c_kernel<PL, NP, NT>, smem); if (rc) return rc;
-  dmk_fast_xr2c_kernel<PL, NP, NT><<<grid, NT, smem, st>>>(in, out, pl.tw, nrows);
+  int rc = set_smem(dmk_fast_xr2c_kernel<PL, NP, NT, MINB>, smem); if (rc) return rc;
+  dmk_fast_xr2c_kernel<PL, NP, NT, MINB><<<grid, NT, smem, st>>>(in, out, pl.tw, nrows);
   DMK_CUDA_CHECK(cudaGetLastError());
   return DMK_OK;
 }
-template <class PL, int NP, int NT>
+template <class PL, int NP, int NT, int MINB = 1>
 static int launch_xc2r(const double2* in, double* out, const DmkFftPlan& pl, int nrows, double scale, cudaStream_t st) {
   const size_t smem = (size_t)PL::N * NP * DMK_NC * sizeof(double2);
   const int npairs = (nrows + 1) / 2, grid = (npairs + NP - 1) / NP;
-  int rc = set_smem(dmk_fast_xc2r_kernel<PL, NP, NT>, smem); if (rc) return rc;
-  dmk_fast_xc2r_kernel<PL, NP, NT><<<grid, NT, smem, st>>>(in, out, pl.tw, nrows, scale);
+  int rc = set_smem(dmk_fast_xc2r_kernel<PL, NP, NT, MINB>, smem); if (rc) return rc;
+  dmk_fast_xc2r_kernel<PL, NP, NT, MINB><<<grid, NT, smem, st>>>(in, out, pl.tw, nrows, scale);
   DMK_CUDA_CHECK(cudaGetLastError());
   return DMK_OK;
 }
@@ -188,12 +189,12 @@ int dmk_fast_xpass_r2c(const double* in, double2* out, const DmkFftPlan& pl, int
   *done = true;
   if (dmk_fast_disabled()) { *done = false; return DMK_OK; }
   switch (pl.n) {
-    case 16: return launch_xr2c<DmkFastPlan<4, 4, 1>, 8, 288>(in, out, pl, nrows, st);
-    case 32: return launch_xr2c<DmkFastPlan<8, 4, 1>, 8, 288>(in, out, pl, nrows, st);
-    case 64: return launch_xr2c<DmkFastPlan<8, 8, 1>, 4, 288>(in, out, pl, nrows, st);
-    case 128: return launch_xr2c<DmkFastPlan<16, 8, 1>, 4, 288>(in, out, pl, nrows, st);
-    case 256: return launch_xr2c<DmkFastPlan<16, 16, 1>, 2, 288>(in, out, pl, nrows, st);
-    case 512: return launch_xr2c<DmkFastPlan<8, 8, 8>, 1, 288>(in, out, pl, nrows, st);
+    case 16: return launch_xr2c<DmkFastPlan<4, 4, 1>, 4, 144, 4>(in, out, pl, nrows, st);
+    case 32: return launch_xr2c<DmkFastPlan<8, 4, 1>, 4, 144, 4>(in, out, pl, nrows, st);
+    case 64: return launch_xr2c<DmkFastPlan<8, 8, 1>, 2, 144, 4>(in, out, pl, nrows, st);
+    case 128: return launch_xr2c<DmkFastPlan<16, 8, 1>, 2, 144, 3>(in, out, pl, nrows, st);
+    case 256: return launch_xr2c<DmkFastPlan<16, 16, 1>, 1, 144, 4>(in, out, pl, nrows, st);
+    case 512: return launch_xr2c<DmkFastPlan<8, 8, 8>, 1, 288, 2>(in, out, pl, nrows, st);
     default: *done = false; return DMK_OK;
   }
 }
@@ -201,12 +202,12 @@ int dmk_fast_xpass_c2r(const double2* in, double* out, const DmkFftPlan& pl, int
   *done = true;
   if (dmk_fast_disabled()) { *done = false; return DMK_OK; }
   switch (pl.n) {
-    case 16: return launch_xc2r<DmkFastPlan<4, 4, 1>, 8, 288>(in, out, pl, nrows, scale, st);
-    case 32: return launch_xc2r<DmkFastPlan<8, 4, 1>, 8, 288>(in, out, pl, nrows, scale, st);
-    case 64: return launch_xc2r<DmkFastPlan<8, 8, 1>, 4, 288>(in, out, pl, nrows, scale, st);
-    case 128: return launch_xc2r<DmkFastPlan<16, 8, 1>, 4, 288>(in, out, pl, nrows, scale, st);
-    case 256: return launch_xc2r<DmkFastPlan<16, 16, 1>, 2, 288>(in, out, pl, nrows, scale, st);
-    case 512: return launch_xc2r<DmkFastPlan<8, 8, 8>, 1, 288>(in, out, pl, nrows, scale, st);
+    case 16: return launch_xc2r<DmkFastPlan<4, 4, 1>, 4, 144, 4>(in, out, pl, nrows, scale, st);
+    case 32: return launch_xc2r<DmkFastPlan<8, 4, 1>, 4, 144, 4>(in, out, pl, nrows, scale, st);
+    case 64: return launch_xc2r<DmkFastPlan<8, 8, 1>, 2, 144, 4>(in, out, pl, nrows, scale, st);
+    case 128: return launch_xc2r<DmkFastPlan<16, 8, 1>, 2, 144, 4>(in, out, pl, nrows, scale, st);
+    case 256: return launch_xc2r<DmkFastPlan<8, 8, 4>, 1, 144, 6>(in, out, pl, nrows, scale, st);
+    case 512: return launch_xc2r<DmkFastPlan<8, 8, 8>, 1, 288, 2>(in, out, pl, nrows, scale, st);
     default: *done = false; return DMK_OK;
   }
 }

@@ -66,6 +66,21 @@ struct DmkFastPlan {
 // multiply-high.  `bact` <= B columns are live (ragged last tile).  ld(sub, pos, col) / st(sub, pos, col, value).
 //   DIT = false: butterfly, then multiply output q by w_L^(q j)          (decimation in frequency, forward network)
 //   DIT = true : multiply input q by conj-or-not w_L^(q j), then butterfly (its adjoint; used with INV = true)
+// Twiddles w_L^(q j), q = 1..R-1, of one butterfly.  Only the powers of two (w^1, w^2, w^4, w^8) are loaded from the
+// length-N table; the others are products of two of them (one rounding each, ~1e-16).  Loading all R-1 made the L1/LSU
+// data pipe, which also carries every shared-memory access of these kernels, the limiter (ncu: 73-86 % of its peak
+// with DRAM at 35-50 %, profiles/r01_summary.md).
+template <int R> __device__ __forceinline__ void load_twiddles(const double2* __restrict__ tw, int base, double2 (&w)[R]) {
+  w[1] = __ldg(&tw[base]);
+  if constexpr (R > 2) { w[2] = __ldg(&tw[2 * base]); w[3] = cmul(w[1], w[2]); }
+  if constexpr (R > 4) { w[4] = __ldg(&tw[4 * base]); w[5] = cmul(w[1], w[4]); w[6] = cmul(w[2], w[4]); w[7] = cmul(w[3], w[4]); }
+  if constexpr (R > 8) {
+    w[8] = __ldg(&tw[8 * base]);
+#pragma unroll
+    for (int q = 9; q < 16; q++) w[q] = cmul(w[q - 8], w[8]);
+  }
+}
+
 template <int N, int R, int ST, int B, bool INV, bool DIT, class LD, class SR>
 __device__ __forceinline__ void fstage(int nsub, int bact, const double2* __restrict__ tw, LD ld, SR sr) {
   constexpr int L = R * ST, TSTEP = N / L, PER = (N / R) * B;
@@ -80,13 +95,17 @@ __device__ __forceinline__ void fstage(int nsub, int bact, const double2* __rest
 #pragma unroll
     for (int m = 0; m < R; m++) v[m] = ld(sub, p0 + m * ST, col);
     if constexpr (DIT && ST > 1) {
+      double2 w[R];
+      load_twiddles<R>(tw, j * TSTEP, w);
 #pragma unroll
-      for (int q = 1; q < R; q++) { const double2 w = __ldg(&tw[q * j * TSTEP]); v[q] = INV ? cmulc(v[q], w) : cmul(v[q], w); }
+      for (int q = 1; q < R; q++) v[q] = INV ? cmulc(v[q], w[q]) : cmul(v[q], w[q]);
     }
     bfly_p2<R, INV>(v);
     if constexpr (!DIT && ST > 1) {
+      double2 w[R];
+      load_twiddles<R>(tw, j * TSTEP, w);
 #pragma unroll
-      for (int q = 1; q < R; q++) { const double2 w = __ldg(&tw[q * j * TSTEP]); v[q] = INV ? cmulc(v[q], w) : cmul(v[q], w); }
+      for (int q = 1; q < R; q++) v[q] = INV ? cmulc(v[q], w[q]) : cmul(v[q], w[q]);
     }
 #pragma unroll
     for (int q = 0; q < R; q++) sr(sub, p0 + q * ST, col, v[q]);

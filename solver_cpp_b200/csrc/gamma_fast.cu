@@ -8,10 +8,11 @@
 #include "fft_fast.cuh"
 #include "gamma_point.cuh"
 
-template <class PL, int KT, bool IMAG_XI, int NT>
-__global__ void __launch_bounds__(NT) dmk_fast_gamma_kernel(double2* __restrict__ data, const double2* __restrict__ tw,
+template <class PL, int KT, bool IMAG_XI, int NT, int MINB>
+__global__ void __launch_bounds__(NT, MINB) dmk_fast_gamma_kernel(double2* __restrict__ data, const double2* __restrict__ tw,
                                                             DmkLineMap map, int n0, int tiles0, DmkGammaParams gp) {
   constexpr int N = PL::N, R1 = PL::R1, R2 = PL::R2, R3 = PL::R3, B = KT * DMK_NC;
+  static_assert(NT % 32 == 0, "whole warps: the divergence sum is reduced with full-warp shuffles");
   extern __shared__ double2 s[];
   __shared__ double sC[81];
   __shared__ double sred[NT / 32];
@@ -19,7 +20,8 @@ __global__ void __launch_bounds__(NT) dmk_fast_gamma_kernel(double2* __restrict_
   const int kt = min(KT, n0 - i0);
   const int bact = kt * DMK_NC;
   const bool nosplit = map.split >= N;
-  for (int i = threadIdx.x; i < 81; i += NT) sC[i] = gp.C_ref[i];
+  // imaginary xi: the 54-entry symmetrised table behind the 81 stiffness entries (dmk_update_gamma)
+  for (int i = threadIdx.x; i < (IMAG_XI ? 54 : 81); i += NT) sC[i] = gp.C_ref[IMAG_XI ? 81 + i : i];
   auto ldg = [&](int, int p, int col) { return data[dmk_line_rec_fast(map, nosplit, o, p, i0) * DMK_NC + col]; };
   auto lds = [&](int, int p, int col) { return s[p * B + col]; };
   auto sts = [&](int, int p, int col, double2 v) { s[p * B + col] = v; };
@@ -87,7 +89,7 @@ __global__ void __launch_bounds__(NT) dmk_fast_gamma_kernel(double2* __restrict_
   }
 }
 
-template <class PL, int KT, int NT>
+template <class PL, int KT, int NT, int MINB = 1>
 static int launch_gamma(double2* data, const DmkFftPlan& pl, DmkLineMap map, int n0, int n_outer, const DmkGammaParams& gp,
                         cudaStream_t st, bool imag_xi) {
   const size_t smem = (size_t)PL::N * KT * DMK_NC * sizeof(double2);
@@ -95,11 +97,11 @@ static int launch_gamma(double2* data, const DmkFftPlan& pl, DmkLineMap map, int
   const long long grid = (long long)tiles0 * n_outer;
   if (grid > 0x7fffffffLL) { dmk_set_error("gamma pass grid too large"); return DMK_ERR_UNSUPPORTED; }
   if (imag_xi) {
-    if (smem > 48 * 1024) DMK_CUDA_CHECK(cudaFuncSetAttribute(dmk_fast_gamma_kernel<PL, KT, true, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    dmk_fast_gamma_kernel<PL, KT, true, NT><<<(int)grid, NT, smem, st>>>(data, pl.tw, map, n0, tiles0, gp);
+    if (smem > 48 * 1024) DMK_CUDA_CHECK(cudaFuncSetAttribute(dmk_fast_gamma_kernel<PL, KT, true, NT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dmk_fast_gamma_kernel<PL, KT, true, NT, MINB><<<(int)grid, NT, smem, st>>>(data, pl.tw, map, n0, tiles0, gp);
   } else {
-    if (smem > 48 * 1024) DMK_CUDA_CHECK(cudaFuncSetAttribute(dmk_fast_gamma_kernel<PL, KT, false, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    dmk_fast_gamma_kernel<PL, KT, false, NT><<<(int)grid, NT, smem, st>>>(data, pl.tw, map, n0, tiles0, gp);
+    if (smem > 48 * 1024) DMK_CUDA_CHECK(cudaFuncSetAttribute(dmk_fast_gamma_kernel<PL, KT, false, NT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dmk_fast_gamma_kernel<PL, KT, false, NT, MINB><<<(int)grid, NT, smem, st>>>(data, pl.tw, map, n0, tiles0, gp);
   }
   DMK_CUDA_CHECK(cudaGetLastError());
   return DMK_OK;
@@ -109,13 +111,14 @@ int dmk_fast_gamma_zpass(double2* data, const DmkFftPlan& plz, DmkLineMap map, i
                          cudaStream_t st, bool imag_xi, bool* done) {
   *done = true;
   if (dmk_fast_disabled()) { *done = false; return DMK_OK; }
+  // the Gamma section needs ~168 registers, so CTAs are small (<= 192 threads, 2 per SM): tools/fft_tune.cu sweeps
   switch (plz.n) {
-    case 16: return launch_gamma<DmkFastPlan<4, 4, 1>, 8, 288>(data, plz, map, n0, n_outer, gp, st, imag_xi);
-    case 32: return launch_gamma<DmkFastPlan<8, 4, 1>, 8, 288>(data, plz, map, n0, n_outer, gp, st, imag_xi);
-    case 64: return launch_gamma<DmkFastPlan<8, 8, 1>, 4, 288>(data, plz, map, n0, n_outer, gp, st, imag_xi);
-    case 128: return launch_gamma<DmkFastPlan<16, 8, 1>, 4, 288>(data, plz, map, n0, n_outer, gp, st, imag_xi);
-    case 256: return launch_gamma<DmkFastPlan<16, 16, 1>, 2, 288>(data, plz, map, n0, n_outer, gp, st, imag_xi);
-    case 512: return launch_gamma<DmkFastPlan<8, 8, 8>, 1, 288>(data, plz, map, n0, n_outer, gp, st, imag_xi);
+    case 16: return launch_gamma<DmkFastPlan<4, 4, 1>, 4, 160, 2>(data, plz, map, n0, n_outer, gp, st, imag_xi);
+    case 32: return launch_gamma<DmkFastPlan<8, 4, 1>, 4, 160, 2>(data, plz, map, n0, n_outer, gp, st, imag_xi);
+    case 64: return launch_gamma<DmkFastPlan<8, 8, 1>, 4, 160, 2>(data, plz, map, n0, n_outer, gp, st, imag_xi);
+    case 128: return launch_gamma<DmkFastPlan<16, 8, 1>, 4, 192, 2>(data, plz, map, n0, n_outer, gp, st, imag_xi);
+    case 256: return launch_gamma<DmkFastPlan<16, 16, 1>, 2, 192, 2>(data, plz, map, n0, n_outer, gp, st, imag_xi);
+    case 512: return launch_gamma<DmkFastPlan<8, 8, 8>, 1, 192, 2>(data, plz, map, n0, n_outer, gp, st, imag_xi);
     default: *done = false; return DMK_OK;
   }
 }

@@ -27,7 +27,8 @@ __global__ void __launch_bounds__(256, 2) dmk_gamma_zpass_kernel(double2* __rest
   const int tiles0 = (n0 + KT - 1) / KT;
   const long long ntiles = (long long)tiles0 * n_outer;
   const int nxr = n0;
-  for (int i = threadIdx.x; i < 81; i += blockDim.x) sC[i] = gp.C_ref[i];
+  // imaginary xi: the 54-entry symmetrised table behind the 81 stiffness entries (dmk_update_gamma)
+  for (int i = threadIdx.x; i < (IMAG_XI ? 54 : 81); i += blockDim.x) sC[i] = gp.C_ref[IMAG_XI ? 81 + i : i];
   const double resc[3] = {gp.rescale[0], gp.rescale[1], gp.rescale[2]};
   double div_local = 0.0;
   for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {

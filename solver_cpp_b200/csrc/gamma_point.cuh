@@ -16,9 +16,15 @@ __device__ __forceinline__ void load_xi(const DmkGammaParams& gp, int kx, int ky
   if (__ldg(&gp.nyq_z[kz])) xi[2] = make_double2(0.0, 0.0);
 }
 
-// One k-point, xi purely imaginary (continuous / central-difference stencils): D, A real.
-// t = 9 complex in record order (component c = i + 3 j).  Returns the divergence contribution.
-__device__ __forceinline__ double gamma_point_imag(double2* __restrict__ t, const double* __restrict__ C,
+// One k-point, xi purely imaginary (continuous / central-difference stencils): xi = i q, so D(l,m) = conj(-xi_l) xi_m =
+// -q_l q_m is real, symmetric and of rank one.  That structure is used twice:
+//   A(l,m) = sum_{n,o} C_ref(l,n,m,o) D(n,o) = sum_v Csym(l,m,v) D_v over the 6 distinct (n,o) pairs, with
+//            Csym(l,m,v) = C_ref(l,n,m,o) + C_ref(l,o,m,n) (n != o) precomputed on the host (dmk_update_gamma): 54 FMA, not 81;
+//   A^-1 . tau . D = -(A^-1 (tau q)) q^T : two 3x3 matrix-vector products and an outer product per real/imaginary part
+//            (54 flop) instead of two 3x3 matrix-matrix products (108).
+// t = 9 complex in record order (component c = i + 3 j).  Csym: 54 doubles, index (l*3+m)*6 + v, v = (00,11,22,12,02,01).
+// Returns the divergence contribution.
+__device__ __forceinline__ double gamma_point_imag(double2* __restrict__ t, const double* __restrict__ Csym,
                                                    const double q[3], const double resc[3], bool is_dc,
                                                    const double* __restrict__ dc_value) {
   // divergence: prod_l = sum_m tau(l,m) * conj(-xi_m) * resc_m = i * sum_m tau(l,m) q_m resc_m
@@ -35,12 +41,7 @@ __device__ __forceinline__ double gamma_point_imag(double2* __restrict__ t, cons
     for (int c = 0; c < 9; c++) t[c] = make_double2(dc_value[c], 0.0);
     return div;
   }
-  // D(l,m) = conj(-i q_l) (i q_m) = -q_l q_m
-  double D[3][3];
-#pragma unroll
-  for (int l = 0; l < 3; l++)
-#pragma unroll
-    for (int m = 0; m < 3; m++) D[l][m] = -q[l] * q[m];
+  const double Dv[6] = {-q[0] * q[0], -q[1] * q[1], -q[2] * q[2], -q[1] * q[2], -q[0] * q[2], -q[0] * q[1]};
   double A[3][3];
 #pragma unroll
   for (int l = 0; l < 3; l++)
@@ -48,9 +49,7 @@ __device__ __forceinline__ double gamma_point_imag(double2* __restrict__ t, cons
     for (int m = 0; m < 3; m++) {
       double acc = 0.0;
 #pragma unroll
-      for (int n = 0; n < 3; n++)
-#pragma unroll
-        for (int o = 0; o < 3; o++) acc += C[((l * 3 + n) * 3 + m) * 3 + o] * D[n][o];
+      for (int v = 0; v < 6; v++) acc += Csym[(l * 3 + m) * 6 + v] * Dv[v];
       A[l][m] = acc;
     }
   double c00 = A[1][1] * A[2][2] - A[1][2] * A[2][1];
@@ -71,27 +70,25 @@ __device__ __forceinline__ double gamma_point_imag(double2* __restrict__ t, cons
   Ai[0][2] = (A[0][1] * A[1][2] - A[0][2] * A[1][1]) * id;
   Ai[1][2] = (A[0][2] * A[1][0] - A[0][0] * A[1][2]) * id;
   Ai[2][2] = (A[0][0] * A[1][1] - A[0][1] * A[1][0]) * id;
-  // out = Ai . tau . D, real and imaginary parts separately (Ai, D real)
+  // out(l,m) = -u_l q_m,  u = Ai w,  w_n = sum_o tau(n,o) q_o   (real and imaginary parts separately: Ai, q real)
+  double2 u[3];
+  {
+    double2 w[3];
 #pragma unroll
-  for (int part = 0; part < 2; part++) {
-    double M[3][3];
+    for (int n = 0; n < 3; n++) {
+      w[n].x = t[n].x * q[0] + t[n + 3].x * q[1] + t[n + 6].x * q[2];
+      w[n].y = t[n].y * q[0] + t[n + 3].y * q[1] + t[n + 6].y * q[2];
+    }
 #pragma unroll
-    for (int n = 0; n < 3; n++)
-#pragma unroll
-      for (int m = 0; m < 3; m++) {
-        double acc = 0.0;
-#pragma unroll
-        for (int o = 0; o < 3; o++) acc += (part ? t[n + 3 * o].y : t[n + 3 * o].x) * D[o][m];
-        M[n][m] = acc;
-      }
-#pragma unroll
-    for (int l = 0; l < 3; l++)
-#pragma unroll
-      for (int m = 0; m < 3; m++) {
-        double acc = Ai[l][0] * M[0][m] + Ai[l][1] * M[1][m] + Ai[l][2] * M[2][m];
-        if (part) t[l + 3 * m].y = acc; else t[l + 3 * m].x = acc;
-      }
+    for (int l = 0; l < 3; l++) {
+      u[l].x = -(Ai[l][0] * w[0].x + Ai[l][1] * w[1].x + Ai[l][2] * w[2].x);
+      u[l].y = -(Ai[l][0] * w[0].y + Ai[l][1] * w[1].y + Ai[l][2] * w[2].y);
+    }
   }
+#pragma unroll
+  for (int l = 0; l < 3; l++)
+#pragma unroll
+    for (int m = 0; m < 3; m++) t[l + 3 * m] = make_double2(u[l].x * q[m], u[l].y * q[m]);
   return div;
 }
 

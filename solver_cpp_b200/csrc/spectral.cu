@@ -78,7 +78,7 @@ int dmk_spectral_setup(dmk_ctx* c) {
   DMK_CUDA_CHECK(cudaMalloc((void**)&c->bufA, c->hat_records * DMK_NC * sizeof(double2)));
   c->bufB = nullptr;
   if (c->P > 1) DMK_CUDA_CHECK(cudaMalloc((void**)&c->bufB, c->hat_records * DMK_NC * sizeof(double2)));
-  DMK_CUDA_CHECK(cudaMalloc((void**)&c->d_Cref, 81 * sizeof(double)));
+  DMK_CUDA_CHECK(cudaMalloc((void**)&c->d_Cref, (81 + 54) * sizeof(double)));   // C_ref | symmetrised pairs (gamma_point.cuh)
   DMK_CUDA_CHECK(cudaMalloc((void**)&c->d_dc, 9 * sizeof(double)));
   DMK_CUDA_CHECK(cudaMalloc((void**)&c->d_div, sizeof(double)));
   DMK_CUDA_CHECK(cudaMalloc((void**)&c->d_scratch, DMK_SCRATCH_DOUBLES * sizeof(double)));
@@ -266,9 +266,17 @@ extern "C" int dmk_fft_backward(dmk_ctx* c, const double* d_fourier, double* d_r
 }
 
 extern "C" int dmk_update_gamma(dmk_ctx* c, const double* C) {
-  double Cr[81], Cf[81];
+  double Cr[81], Cf[81 + 54];
   f2c3333(C, Cr);
   for (int i = 0; i < 81; i++) Cf[i] = Cr[i] / c->wgt;                  // C_ref = C / wgt (mech_base.cpp:157)
+  // Csym(l,m,v) = C_ref(l,n,m,o) + C_ref(l,o,m,n) over the 6 distinct (n,o) pairs v = (00,11,22,12,02,01): gamma_point.cuh
+  static const int vn[6] = {0, 1, 2, 1, 0, 0}, vo[6] = {0, 1, 2, 2, 2, 1};
+  for (int l = 0; l < 3; l++) for (int m = 0; m < 3; m++) for (int v = 0; v < 6; v++) {
+    const int n = vn[v], o = vo[v];
+    double s = Cf[((l * 3 + n) * 3 + m) * 3 + o];
+    if (n != o) s += Cf[((l * 3 + o) * 3 + m) * 3 + n];
+    Cf[81 + (l * 3 + m) * 6 + v] = s;
+  }
   DMK_CUDA_CHECK(cudaMemcpyAsync(c->d_Cref, Cf, sizeof Cf, cudaMemcpyHostToDevice, c->stream));
   DMK_CUDA_CHECK(cudaStreamSynchronize(c->stream));
   c->gamma_set = true;
