@@ -146,21 +146,12 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm
-def run_ours(args):
+def setup_state(cells, world=1, rank=0):
+    """the bench state on this rank's z-slab: solver `s` on a polycrystal after two homogeneous (Taylor) increments and
+    N_RELAX fixed-point iterations of the third; returns (s, X, R) with X the iterate to evaluate, R a residual buffer"""
     import torch
-    import torch.distributed as dist
-    world = int(os.environ.get('WORLD_SIZE', '1'))
-    rank = int(os.environ.get('RANK', '0'))
-    local = int(os.environ.get('LOCAL_RANK', '0'))
-    if not torch.cuda.is_available():
-        raise RuntimeError('bench.py needs a CUDA device: the product path has no CPU fallback')
-    torch.cuda.set_device(local)
-    if world > 1:
-        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
-    from solver_cpp_b200 import workloads as W, mech, material as M
+    from solver_cpp_b200 import workloads as W, mech
     from solver_cpp_b200 import parallel
-
-    cells = tuple(args.cells) if args.cells else (256, 256, 256 * world)
     nx, ny, nz = cells
     grains = max(8, int(round(500 * np.prod(cells) / 256.0 ** 3)))
     z0, z1 = parallel.slab_range(nz, world, rank)
@@ -169,7 +160,6 @@ def run_ours(args):
     s = mech.make_solver(cells, size, material, material_at, world_size=world, rank=rank, comm=comm)
     g = s.g
     s.init()
-    n_local, n_global = g.n_local, nx * ny * nz
     # ---- state: two homogeneous increments
     F = g.new_field()
     P = g.new_field()
@@ -193,6 +183,25 @@ def run_ours(args):
         s.form_residual(X, R)
         X.sub_(R)
     g.synchronize()
+    return s, X, R, grains
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if not torch.cuda.is_available():
+        raise RuntimeError('bench.py needs a CUDA device: the product path has no CPU fallback')
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    cells = tuple(args.cells) if args.cells else (256, 256, 256 * world)
+    nx, ny, nz = cells
+    s, X, R, grains = setup_state(cells, world, rank)
+    g = s.g
+    n_local, n_global = g.n_local, nx * ny * nz
 
     def barrier():
         if world > 1:
@@ -274,6 +283,7 @@ def run_ours(args):
         'newton_iters_per_s': 0.5 * 1e3 / per_step,
         'inner_Lp_iterations_per_cell': lp_iters / n_local,
         'deferred_cell_fraction': (c1['deferred'] - c0['deferred']) / K / n_local,
+        'per_cell': {k: (c1[k] - c0[k]) / K / n_local for k in ('stress_calls', 'state_iter', 'substeps', 'cutbacks')},
         'gpu_launches': int(launches),
         'kernel_ms': {'constitutive': con_ms, 'reduce_aim': prof['reduce_aim_ms'] / max(prof['evaluations'], 1),
                       'fft_forward_xy': prof['fft_forward_ms'] / max(prof['evaluations'], 1),

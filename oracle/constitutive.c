@@ -765,6 +765,9 @@ static void dPdF_point(pt_t *p, double Dt, double *dPdF) {
 /* optional per-cell log of sub-step cut-backs (test diagnostics: cells whose Newton path is rounding-chaotic) */
 static int *g_point_cutbacks = NULL;
 void orc_set_point_log(int *buf) { g_point_cutbacks = buf; }
+/* optional per-cell log of Lp Newton iterations (test diagnostics: cells where a stopping / line-search decision flipped) */
+static int *g_point_lp_iter = NULL;
+void orc_set_point_lp_log(int *buf) { g_point_lp_iter = buf; }
 
 int orc_mechanical_response(const orc_phase_t *phases, const orc_num_t *num, orc_points_t *st, const double *F_in,
                             double Dt, int cell_start, int cell_end, long *counters) {
@@ -781,6 +784,7 @@ int orc_mechanical_response(const orc_phase_t *phases, const orc_num_t *num, orc
     memcpy(p.F, F_in + 9*(size_t)ce, 9*sizeof(double));             /* phase_set_F */
     if (!constitutive(&p, Dt, &cnt)) ill |= 1;
     if (g_point_cutbacks) g_point_cutbacks[ce] = (int)cnt.n_cutbacks;
+    if (g_point_lp_iter) g_point_lp_iter[ce] = (int)cnt.n_Lp_iter;
     c0 += cnt.n_Lp_iter; c1 += cnt.n_Li_iter; c2 += cnt.n_stress_calls; c3 += cnt.n_state_iter; c4 += cnt.n_substeps; c5 += cnt.n_cutbacks;
   }
   if (counters) { counters[0] = c0; counters[1] = c1; counters[2] = c2; counters[3] = c3; counters[4] = c4; counters[5] = c5; }

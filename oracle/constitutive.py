@@ -267,6 +267,7 @@ class ConstitutiveOracle:
         self.lib.orc_mechanical_response.restype = C.c_int
         self.counters = np.zeros(6, dtype=np.int64)
         self.point_cutbacks = np.zeros(n, dtype=np.int32)       # per-cell cut-backs of the last response call
+        self.point_lp_iter = np.zeros(n, dtype=np.int32)        # per-cell Lp Newton iterations of the last response call
         self.terminally_ill = False
         self.threads = threads
 
@@ -277,6 +278,8 @@ class ConstitutiveOracle:
         cnt = np.zeros(6, dtype=np.int64)
         self.point_cutbacks[:] = 0
         self.lib.orc_set_point_log(self.point_cutbacks.ctypes.data_as(C.POINTER(C.c_int)))
+        self.point_lp_iter[:] = 0
+        self.lib.orc_set_point_lp_log(self.point_lp_iter.ctypes.data_as(C.POINTER(C.c_int)))
         ill = self.lib.orc_mechanical_response(self.phases, C.byref(self.num), C.byref(self.st),
                                                F.ctypes.data_as(C.POINTER(C.c_double)), C.c_double(dt),
                                                C.c_int(cell_start), C.c_int(cell_end),

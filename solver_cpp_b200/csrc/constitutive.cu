@@ -27,7 +27,7 @@ __global__ void __launch_bounds__(DMK_PT_THREADS) dmk_constitutive_kernel(DmkPoi
   const long long n = pa.n;
   const long long stride = (long long)gridDim.x * blockDim.x;
   DmkCnt cnt = {0, 0, 0, 0, 0, 0};
-  unsigned ill = 0, cb0 = 0;
+  unsigned ill = 0, cb0 = 0, lp0 = 0;
   DmkMachine<LAW, NS, ND> m;
   DmkMachineStore<LAW, NS, ND> store;
   machine_bind(m, store);
@@ -43,6 +43,7 @@ __global__ void __launch_bounds__(DMK_PT_THREADS) dmk_constitutive_kernel(DmkPoi
         if (have) {                                                      // store the finished point
           if (!m.converged) ill = 1;
           pa.cutbacks[i] = (int)(cnt.cutbacks - cb0);
+          pa.lp_iter[i] = (int)(cnt.Lp_iter - lp0);
 #pragma unroll
           for (int a = 0; a < 9; a++) {
             pa.F[a * n + i] = m.Ft[a]; pa.Fp[a * n + i] = m.p.Fp[a]; pa.Lp[a * n + i] = m.p.Lp[a]; pa.Fe[a * n + i] = m.p.Fe[a];
@@ -74,7 +75,7 @@ __global__ void __launch_bounds__(DMK_PT_THREADS) dmk_constitutive_kernel(DmkPoi
         for (int k = 0; k < ns; k++) m.state0[k] = pa.state0[k * n + i];
         if constexpr (ND > 0) { const int nd = m.p.ph->n_dep; for (int k = 0; k < nd; k++) m.p.dep[k] = pa.dep[k * n + i]; }
         if constexpr (LAW == DMK_LAW_DISLOTWIN) m.p.C66 = m.p.ph->p.C66;
-        cb0 = cnt.cutbacks;
+        cb0 = cnt.cutbacks; lp0 = cnt.Lp_iter;
         have = true;
         machine_begin(m, num);
       } else if (m.state == M_SUBSTEP) machine_substep(m, num, Dt, cnt);
@@ -131,10 +132,11 @@ __global__ void __launch_bounds__(DMK_PT_THREADS) dmk_constitutive_nested_kernel
     for (int a = 0; a < 6; a++) { S0[a] = pa.S0[a * n + i]; p.S[a] = S0[a]; }
     for (int k = 0; k < ns; k++) { state0[k] = pa.state0[k * n + i]; p.st[k] = state0[k]; }
     if constexpr (ND > 0) { const int nd = p.ph->n_dep; for (int k = 0; k < nd; k++) p.dep[k] = pa.dep[k * n + i]; }
-    const unsigned cb0 = cnt.cutbacks;
+    const unsigned cb0 = cnt.cutbacks, lp0 = cnt.Lp_iter;
     const bool ok = constitutive_point(p, num, F0, Ft, Fp0, Lp0, S0, state0, Dt, cnt);
     if (!ok) ill = 1;
     pa.cutbacks[i] = (int)(cnt.cutbacks - cb0);
+    pa.lp_iter[i] = (int)(cnt.Lp_iter - lp0);
 #pragma unroll
     for (int a = 0; a < 9; a++) {
       pa.F[a * n + i] = Ft[a]; pa.Fp[a * n + i] = p.Fp[a]; pa.Lp[a * n + i] = p.Lp[a]; pa.Fe[a * n + i] = p.Fe[a];
@@ -355,7 +357,7 @@ void dmk_points_teardown(dmk_ctx* c) {
   cudaFree(pa->phase); cudaFree(pa->F0); cudaFree(pa->F); cudaFree(pa->Fp0); cudaFree(pa->Fp); cudaFree(pa->Fe);
   cudaFree(pa->Lp0); cudaFree(pa->Lp); cudaFree(pa->S0); cudaFree(pa->S); cudaFree(pa->state0); cudaFree(pa->state);
   if (pa->dep) cudaFree(pa->dep);
-  cudaFree(pa->nrm); cudaFree(pa->cutbacks); cudaFree(pa->defer_list); cudaFree(pa->d_defer_count); cudaFree(pa->d_phases); cudaFree(pa->d_counters); cudaFree(pa->d_ill);
+  cudaFree(pa->nrm); cudaFree(pa->cutbacks); cudaFree(pa->lp_iter); cudaFree(pa->defer_list); cudaFree(pa->d_defer_count); cudaFree(pa->d_work); cudaFree(pa->d_phases); cudaFree(pa->d_counters); cudaFree(pa->d_ill);
   delete[] pa->h_phases;
   delete[] pa->h_dev_phases;
   delete pa;
@@ -436,9 +438,12 @@ extern "C" int dmk_material_init(dmk_ctx* c, const dmk_phase* phases, int n_phas
   DMK_CUDA_CHECK(cudaMalloc((void**)&pa->phase, n * sizeof(int)));
   DMK_CUDA_CHECK(cudaMalloc((void**)&pa->cutbacks, n * sizeof(int)));
   DMK_CUDA_CHECK(cudaMemset(pa->cutbacks, 0, n * sizeof(int)));
+  DMK_CUDA_CHECK(cudaMalloc((void**)&pa->lp_iter, n * sizeof(int)));
+  DMK_CUDA_CHECK(cudaMemset(pa->lp_iter, 0, n * sizeof(int)));
   DMK_CUDA_CHECK(cudaMalloc((void**)&pa->defer_list, n * sizeof(int)));
   DMK_CUDA_CHECK(cudaMalloc((void**)&pa->d_defer_count, sizeof(unsigned)));
   DMK_CUDA_CHECK(cudaMemset(pa->d_defer_count, 0, sizeof(unsigned)));
+  DMK_CUDA_CHECK(cudaMalloc((void**)&pa->d_work, sizeof(unsigned long long)));
   DMK_CUDA_CHECK(cudaMalloc((void**)&pa->d_phases, n_phases * sizeof(DmkDevPhase)));
   DMK_CUDA_CHECK(cudaMalloc((void**)&pa->d_counters, 8 * sizeof(unsigned long long)));
   DMK_CUDA_CHECK(cudaMalloc((void**)&pa->d_ill, sizeof(int)));
@@ -538,11 +543,11 @@ extern "C" int dmk_get_state(dmk_ctx* c, const char* name, double* out, size_t n
   else if (s == "S") { src = pa.S; comps = 6; voigt = true; } else if (s == "S0") { src = pa.S0; comps = 6; voigt = true; }
   else if (s == "state") { src = pa.state; comps = pa.max_state; } else if (s == "state0") { src = pa.state0; comps = pa.max_state; }
   else if (s == "dep") { src = pa.dep; comps = pa.max_dep; }
-  if (s == "cutbacks") {
+  if (s == "cutbacks" || s == "lp_iter") {
     if (n_doubles < (size_t)n) { dmk_set_error("dmk_get_state: buffer too small"); return DMK_ERR_ARG; }
     std::vector<int> ib(n);
     DMK_CUDA_CHECK(cudaStreamSynchronize(c->stream));
-    DMK_CUDA_CHECK(cudaMemcpy(ib.data(), pa.cutbacks, n * sizeof(int), cudaMemcpyDeviceToHost));
+    DMK_CUDA_CHECK(cudaMemcpy(ib.data(), s == "cutbacks" ? pa.cutbacks : pa.lp_iter, n * sizeof(int), cudaMemcpyDeviceToHost));
     for (long long i = 0; i < n; i++) out[i] = (double)ib[i];
     return DMK_OK;
   }

@@ -38,8 +38,10 @@ struct DmkPointArrays {
   double* dep;                         // [max_dep][n]  (dislotwin only, else nullptr)
   double* nrm;                         // [n] ||dPdF||^2 scratch of the tangent pass
   int* cutbacks;                       // [n] sub-step cut-backs of each cell in the last response call (diagnostic)
+  int* lp_iter;                        // [n] Lp Newton iterations of each cell in the last response call (diagnostic)
   int* defer_list;                     // [n] cells the register-resident kernel handed to the reference-order kernel
   unsigned* d_defer_count;             // entries of defer_list written by the last register-resident launch
+  unsigned long long* d_work;          // next unclaimed cell of the lane-persistent kernel's chunk queue (pheno_fast.cu)
   DmkDevPhase* d_phases;               // device array
   dmk_phase* h_phases;                 // host copy
   DmkDevPhase* h_dev_phases;           // host copy of the device tables

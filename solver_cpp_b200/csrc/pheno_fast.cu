@@ -3,7 +3,9 @@
 #include <algorithm>
 #include <cstdint>
 #include <cstdlib>
+#include <string>
 #include "pheno_fast_dev.cuh"
+#include "pheno_lanes_dev.cuh"
 
 // One thread per point, one warp-sized pair of warps per block (DMK_PF_THREADS points), phase tables as a
 // __grid_constant__ parameter, state-integrator arrays in shared memory ([k][thread]).  Blocks are small and end
@@ -46,9 +48,11 @@ static int defer_setting() {
   return v < 0 ? 0 : v;
 }
 
-// DMK_PHENO_UNROLL=<1|4|12>: unroll factor of the slip-system loops inside the Newton iteration
+// DMK_PHENO_UNROLL=<1|4|12>: unroll factor of the slip-system loops inside the Newton iteration.  Default 1: the kernels
+// are instruction-fetch bound (ncu: no_instruction is the top stall, 57 % instruction-cache hit rate with the loops
+// unrolled 12-fold; 128^3 solver iterate: 28.1 / 29.7 / 31.3 ms for 1 / 4 / 12, profiles/r01_summary.md)
 static int unroll_setting() {
-  static const int v = [] { const char* e = getenv("DMK_PHENO_UNROLL"); return e ? atoi(e) : 12; }();
+  static const int v = [] { const char* e = getenv("DMK_PHENO_UNROLL"); return e ? atoi(e) : 1; }();
   return v;
 }
 
@@ -70,6 +74,119 @@ static int launch_pheno_fast(dmk_ctx* c, DmkPointArrays& pa, int ph, const DmkDe
   return DMK_OK;
 }
 
+
+// ------------------------------------------------------------------------------------------------ lane-persistent kernel
+// pheno_lanes_dev.cuh.  One resident wave of 64-thread blocks; a warp claims chunks of DMK_PL_CHUNK consecutive cells from a
+// global queue (one atomic per chunk) and deals them to its lanes as they become free, so neighbouring lanes keep working
+// on neighbouring cells (coalesced structure-of-arrays accesses) and no warp is left with a long tail.  No barrier anywhere.
+#define DMK_PL_THREADS 64
+#ifndef DMK_PL_MINBLOCKS
+#define DMK_PL_MINBLOCKS 4
+#endif
+#define DMK_PL_CHUNK 256
+template <int NSL, int NEXP, int UNR>
+__global__ void __launch_bounds__(DMK_PL_THREADS, DMK_PL_MINBLOCKS)
+dmk_pheno_lanes_kernel(const __grid_constant__ DmkPhenoK<NSL> K, DmkPointArrays pa, int phase, DmkNumDev num,
+                       const double* __restrict__ Fin, double* __restrict__ Pout, double step, double dt) {
+  extern __shared__ double pf_sm[];
+  const DmkScr scr = {pf_sm + threadIdx.x, DMK_PL_THREADS};
+  const unsigned FULL = 0xffffffffu, lane = threadIdx.x & 31u, lt = (1u << lane) - 1u;
+  PlLane<NSL> L;
+  L.mode = PL_NEED;
+  long long c_next = 0, c_end = 0;                      // the warp's current chunk (warp-uniform)
+  bool drained = false;
+  unsigned n_Lp = 0, n_calls = 0, n_pts = 0, n_defer = 0;
+  double S[6];
+  for (;;) {
+    // ---- vote: a trip runs EITHER one Newton iteration OR refill + state block, whichever has more lanes waiting for it.
+    // Running both every trip left 12.8 of 32 lanes active per instruction (ncu, profiles/r01_summary.md): the state
+    // block and the refill were executed for the few lanes that needed them at that moment.  Waiting lanes accumulate
+    // until they are the majority, go through their block together and then iterate in step.
+    const unsigned bL = __ballot_sync(FULL, L.mode == PL_LP);
+    const unsigned bS = __ballot_sync(FULL, L.mode == PL_INIT || L.mode == PL_CONV);
+    unsigned need = drained ? 0u : __ballot_sync(FULL, L.mode == PL_NEED);
+    if (!(bL | bS | need)) break;
+    if (__popc(bL) >= __popc(bS) + __popc(need)) {
+      // ---- one Newton iteration
+      if (L.mode == PL_LP) {
+        const int rc = pl_lp_iteration<NSL, NEXP, UNR>(K, num, dt, scr, L);
+        if (rc == PL_DONE) L.mode = PL_CONV;
+        else if (rc == PL_DEFER) { pa.defer_list[atomicAdd(pa.d_defer_count, 1u)] = (int)L.i; n_defer++; L.mode = PL_NEED; }
+      }
+      continue;
+    }
+    // ---- refill
+    while (need) {
+      if (c_next >= c_end) {
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(pa.d_work, (unsigned long long)DMK_PL_CHUNK);
+        base = __shfl_sync(FULL, base, 0);
+        if ((long long)base >= pa.n) { drained = true; break; }
+        c_next = (long long)base;
+        c_end = min(c_next + DMK_PL_CHUNK, pa.n);
+      }
+      const int avail = (int)min(32LL, c_end - c_next);
+      const int rank = __popc(need & lt);
+      if (L.mode == PL_NEED && rank < avail) {
+        const long long i = c_next + rank;
+        if (pa.phase[i] == phase) {
+          if (pl_begin<NSL>(pa, i, Fin, step, scr, L, S)) L.mode = PL_INIT;
+          else { pa.defer_list[atomicAdd(pa.d_defer_count, 1u)] = (int)i; n_defer++; }
+        }
+      }
+      c_next += min(__popc(need), avail);
+      need = __ballot_sync(FULL, L.mode == PL_NEED);
+    }
+    // ---- state block
+    if (L.mode == PL_INIT || L.mode == PL_CONV) {
+      const int rc = pl_state_block<NSL, NEXP>(K, num, pa, Fin, Pout, dt, scr, L, S, L.mode == PL_INIT);
+      if (rc == PL_CONTINUE) L.mode = PL_LP;
+      else {
+        if (rc == PL_DONE) { n_Lp += L.nLp_pt; n_calls += (unsigned)L.it; n_pts++; }
+        else { pa.defer_list[atomicAdd(pa.d_defer_count, 1u)] = (int)L.i; n_defer++; }
+        L.mode = PL_NEED;
+      }
+    }
+  }
+  // counters (d_counters: Lp, Li, stress calls, state iterations, sub-steps, cut-backs, ill, deferred)
+  unsigned v[8] = {n_Lp, n_calls, n_calls, n_calls, n_pts, 0u, 0u, n_defer};
+#pragma unroll
+  for (int k = 0; k < 8; k++) {
+    unsigned s = v[k];
+    for (int off = 16; off > 0; off >>= 1) s += __shfl_down_sync(FULL, s, off);
+    if (lane == 0 && s) atomicAdd(&pa.d_counters[k], (unsigned long long)s);
+  }
+}
+
+// DMK_PHENO_SCHEDULE=nested: one thread walks one point through the nested loops (dmk_pheno_fast_kernel); default: lanes
+static bool lanes_setting() {
+  static const bool v = [] { const char* e = getenv("DMK_PHENO_SCHEDULE"); return !(e && std::string(e) == "nested"); }();
+  return v;
+}
+
+template <int NSL, int NEXP, int UNR>
+static int launch_pheno_lanes(dmk_ctx* c, DmkPointArrays& pa, int ph, const DmkDevPhase& d, const DmkNumDev& nd, const double* d_F,
+                              double* d_P, double step, double dt) {
+  DmkPhenoK<NSL> K;
+  dmk_pheno_fast_tables<NSL>(d, K);
+  const size_t smem = (size_t)PfOff<NSL>::TOTAL * DMK_PL_THREADS * sizeof(double);
+  static int grid = 0;
+  if (!grid) {
+    DMK_CUDA_CHECK(cudaFuncSetAttribute(dmk_pheno_lanes_kernel<NSL, NEXP, UNR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int dev = 0, sms = 148, occ = 1;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, dmk_pheno_lanes_kernel<NSL, NEXP, UNR>, DMK_PL_THREADS, smem) != cudaSuccess || occ < 1) occ = 1;
+    grid = sms * occ;                                  // one resident wave
+  }
+  const long long warps_needed = (pa.n + 31) / 32;
+  const int g = (int)std::max(1LL, std::min((long long)grid, (warps_needed + 1) / 2));
+  DMK_CUDA_CHECK(cudaMemsetAsync(pa.d_defer_count, 0, sizeof(unsigned), c->stream));
+  DMK_CUDA_CHECK(cudaMemsetAsync(pa.d_work, 0, sizeof(unsigned long long), c->stream));
+  dmk_pheno_lanes_kernel<NSL, NEXP, UNR><<<g, DMK_PL_THREADS, smem, c->stream>>>(K, pa, ph, nd, d_F, d_P, step, step * dt);
+  return DMK_OK;
+}
+
 // Runs phase `ph` through the register-resident kernel if it qualifies (*handled), else leaves it to the generic kernel.
 int dmk_points_pheno_fast(dmk_ctx* c, int ph, const DmkNumDev& nd, const double* d_F, double* d_P, double dt, bool* handled,
                           bool* deferred) {
@@ -81,6 +198,19 @@ int dmk_points_pheno_fast(dmk_ctx* c, int ph, const DmkNumDev& nd, const double*
   const DmkDevPhase& d = pa.h_dev_phases[ph];
   const int u = unroll_setting();
   int rc;
+  double step = 1.0;
+  if (lanes_setting() && dmk_pheno_lanes_eligible(nd, &step)) {
+    *deferred = true;
+    if (nexp == 20) rc = (u == 1) ? launch_pheno_lanes<12, 20, 1>(c, pa, ph, d, nd, d_F, d_P, step, dt)
+                       : (u == 4) ? launch_pheno_lanes<12, 20, 4>(c, pa, ph, d, nd, d_F, d_P, step, dt)
+                                  : launch_pheno_lanes<12, 20, 12>(c, pa, ph, d, nd, d_F, d_P, step, dt);
+    else rc = (u == 1) ? launch_pheno_lanes<12, 0, 1>(c, pa, ph, d, nd, d_F, d_P, step, dt)
+            : (u == 4) ? launch_pheno_lanes<12, 0, 4>(c, pa, ph, d, nd, d_F, d_P, step, dt)
+                       : launch_pheno_lanes<12, 0, 12>(c, pa, ph, d, nd, d_F, d_P, step, dt);
+    if (rc) return rc;
+    DMK_CUDA_CHECK(cudaGetLastError());
+    return DMK_OK;
+  }
   if (nexp == 20) rc = (u == 1) ? launch_pheno_fast<12, 20, 1>(c, pa, ph, d, nd, d_F, d_P, dt)
                  : (u == 4) ? launch_pheno_fast<12, 20, 4>(c, pa, ph, d, nd, d_F, d_P, dt)
                             : launch_pheno_fast<12, 20, 12>(c, pa, ph, d, nd, d_F, d_P, dt);

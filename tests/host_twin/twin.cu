@@ -7,6 +7,7 @@
 #include "../../solver_cpp_b200/csrc/machine_dev.cuh"
 #include "../../solver_cpp_b200/csrc/tangent_dev.cuh"
 #include "../../solver_cpp_b200/csrc/pheno_fast_dev.cuh"
+#include "../../solver_cpp_b200/csrc/pheno_lanes_dev.cuh"
 
 void dmk_set_error(const char*, ...) {}
 static int g_use_nested = 0;     // 1: the straight nested-loop formulation (cross-check of the state machine)
@@ -44,6 +45,8 @@ static int run_point(const DmkDevPhase* ph, const DmkNumDev& num, const double* 
   return ok ? 1 : 0;
 }
 
+static int g_use_fast = 0;       // 1: route eligible phases through pheno_fast_dev.cuh; 2: through its lane schedule (pheno_lanes_dev.cuh)
+extern "C" void twin_use_fast(int v) { g_use_fast = v; }
 static int g_defer = 0;          // pf_stress deferral threshold (0: never defer), as DMK_PHENO_DEFER in the product
 static int g_last_deferred = 0;
 extern "C" void twin_set_defer(int v) { g_defer = v; }
@@ -66,17 +69,20 @@ static int run_point_fast(const DmkDevPhase* ph, const DmkNumDev& num, const dou
   for (int k = 0; k < 2 * NSL; k++) st0[k] = state0[k];
   pa.F0 = f0; pa.F = F; pa.Fp0 = fp0; pa.Fp = Fp; pa.Fe = Fe; pa.Lp0 = lp0; pa.Lp = Lp; pa.S0 = s0; pa.S = S; pa.state0 = st0; pa.state = state;
   pa.cutbacks = &cut;
+  int lpi = 0;
+  pa.lp_iter = &lpi;
   double scratch[PfOff<NSL>::TOTAL];
   DmkScr scr = {scratch, 1};
   DmkCnt cnt = {0, 0, 0, 0, 0, 0};
-  const int rc = pf_point<NSL, NEXP, 1>(K, num, g_defer, pa, 0, Frec, Prec, Dt, scr, cnt);
+  int rc;
+  double step = 1.0;
+  if (g_use_fast == 2 && dmk_pheno_lanes_eligible(num, &step)) rc = pl_run_point<NSL, NEXP>(K, num, pa, 0, Frec, Prec, step, Dt, scr, cnt);
+  else rc = pf_point<NSL, NEXP, 1>(K, num, g_defer, pa, 0, Frec, Prec, Dt, scr, cnt);
   if (rc == PF_DEFER) return 2;                       // nothing written: the caller replays the point on the reference-order path
   for (int a = 0; a < 3; a++) for (int b = 0; b < 3; b++) P[3 * a + b] = Prec[a + 3 * b];
   cnt_out[0] = cnt.Lp_iter; cnt_out[1] = cnt.Li_iter; cnt_out[2] = cnt.stress_calls; cnt_out[3] = cnt.state_iter; cnt_out[4] = cnt.substeps; cnt_out[5] = cnt.cutbacks;
   return rc == PF_OK ? 1 : 0;
 }
-static int g_use_fast = 0;       // 1: route eligible phases through pheno_fast_dev.cuh
-extern "C" void twin_use_fast(int v) { g_use_fast = v; }
 
 static void voigt_strain_of(const double* P, double* pv) { pv[0] = P[0]; pv[1] = P[4]; pv[2] = P[8]; pv[3] = P[5] + P[7]; pv[4] = P[2] + P[6]; pv[5] = P[1] + P[3]; }
 static void q_host(const double* C66, const double* pv, double* Q) { for (int b = 0; b < 6; b++) { double s = 0; for (int a = 0; a < 6; a++) s += pv[a] * C66[6 * a + b]; Q[b] = s; } }

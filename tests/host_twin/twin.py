@@ -7,7 +7,7 @@ def build():
     lib = os.path.join(HERE, '_build', 'libtwin.so')
     src = os.path.join(HERE, 'twin.cu')
     os.makedirs(os.path.dirname(lib), exist_ok=True)
-    deps = [src] + [os.path.join(HERE, '..', '..', 'solver_cpp_b200', 'csrc', f) for f in ('constitutive_dev.cuh', 'tangent_dev.cuh', 'constitutive.cuh', 'machine_dev.cuh', 'pheno_fast_dev.cuh')]
+    deps = [src] + [os.path.join(HERE, '..', '..', 'solver_cpp_b200', 'csrc', f) for f in ('constitutive_dev.cuh', 'tangent_dev.cuh', 'constitutive.cuh', 'machine_dev.cuh', 'pheno_fast_dev.cuh', 'pheno_lanes_dev.cuh')]
     if not os.path.exists(lib) or any(os.path.getmtime(d) > os.path.getmtime(lib) for d in deps):
         subprocess.check_call(['nvcc', '-O2', '-std=c++17', '-Xcompiler', '-fPIC', '-shared', '-I', os.path.join(HERE, '..', '..', 'include'),
                                '-o', lib, src], stderr=subprocess.DEVNULL)

@@ -65,7 +65,13 @@ def test_constitutive_matches_oracle_over_increments(phase, cells, grains, n_inc
     when the first trial step overshoots by tens of orders of magnitude (soft virgin Cu), whether the next, smaller
     sub-step converges is decided by the last bit, and ANY two IEEE-valid builds of the reference algorithm differ
     there (tests/test_oracle_golden.py::test_cutback_path_is_rounding_sensitive shows it for the oracle and its own
-    FMA-contracted build).  Such cells must have cut back (in the oracle or on the device), stay rare, and stay close."""
+    FMA-contracted build).  Such cells must have cut back (in the oracle or on the device), stay rare, and stay close.
+    Second, milder case: a stopping / line-search decision of the Lp Newton loop whose two sides agree to rounding may
+    flip; the cell then ends an iteration apart from the oracle (per-cell Lp iteration counts differ), both answers
+    inside the integrator's own tolerance (1e-6).  Such cells must agree to 1e-6 (observed: 1e-11).  On this deliberately
+    rough path (white-noise F, most Cu cells cut back, the others need 50-90 Newton iterations with long line searches)
+    they are a sizeable part of the few quiet cells; test_newton_decisions_rarely_flip_on_a_solver_iterate bounds their
+    share on the kind of iterate a running solve produces."""
     g, o = _setup(cells, grains, phase)
     rng = np.random.default_rng(11)
     dt = 0.5
@@ -86,6 +92,9 @@ def test_constitutive_matches_oracle_over_increments(phase, cells, grains, n_inc
                 aux = np.maximum(aux, _pointwise_rel(g.get_state('state', o.max_state)[:, :nst], o.a['state'][:, :nst]))
             bad = ((err >= RTOL) | (aux >= 10 * RTOL)) & clean
             quiet = (o.point_cutbacks == 0) & (g.get_state('cutbacks', 1)[:, 0] == 0)      # no cut-back on either side
+            flipped = quiet & clean & (g.get_state('lp_iter', 1)[:, 0] != o.point_lp_iter)   # a Newton stopping decision flipped
+            assert (err[flipped] < 1e-6).all(), (inc, flipped.mean(), err[flipped].max())
+            quiet &= ~flipped
             assert not (bad & quiet).any(), (inc, err[bad & quiet].max(), aux[bad & quiet].max())
             assert err[clean].max() < 0.2
             assert _rel(g.get_state('Lp', 9)[clean & ~bad], o.a['Lp'][clean & ~bad]) < 1e-7
@@ -98,6 +107,43 @@ def test_constitutive_matches_oracle_over_increments(phase, cells, grains, n_inc
     # plasticity was active (otherwise the test pins only Hooke)
     if phase not in ('Al_elastic',):
         assert np.abs(o.a['Lp']).max() > 1e-6
+
+
+def test_newton_decisions_rarely_flip_on_a_solver_iterate():
+    """Cu polycrystal, homogeneous pre-strain, then a smooth in-grain fluctuation of the size a running solve produces
+    (no cut-backs; every third cell needs the line search): per-cell Lp iteration counts equal the oracle's on all but
+    <= 0.5 % of the cells, P to 1e-9 on the rest and 1e-6 on those."""
+    cells = (16, 16, 8)
+    g, o = _setup(cells, 12, 'Cu_pheno')
+    n = int(np.prod(cells))
+    nx, ny, nz = cells
+    dt = 0.5
+    rng = np.random.default_rng(21)
+    z, y, x = np.meshgrid(np.arange(nz) / nz, np.arange(ny) / ny, np.arange(nx) / nx, indexing='ij')
+    smooth = sum(rng.standard_normal((3, 3)) * np.cos(2 * np.pi * (k[0] * x + k[1] * y + k[2] * z + rng.random()))[..., None, None]
+                 for k in ((1, 0, 0), (0, 1, 0), (0, 0, 1), (1, 1, 0), (2, 1, 1), (1, 2, 3)))
+    clean = np.ones(n, bool)                    # no cut-back anywhere in the cell's history, on either side
+    e = 0.0
+    for de in (1e-5, 1e-5, 2e-5, 4e-5, 8e-5) + (1.6e-4,) * 8:       # gentle ramp: virgin Cu cuts back on anything faster
+        e += de
+        F = np.broadcast_to(np.diag([1 + e, 1 - 0.5 * e, 1 - 0.5 * e]), (nz, ny, nx, 3, 3)).copy()
+        o.mechanical_response(F.reshape(n, 9), dt)
+        g.constitutive_response(g.to_device(F), dt)
+        clean &= (o.point_cutbacks == 0) & (g.get_state('cutbacks', 1)[:, 0] == 0)
+        g.materialpoint_forward(); o.forward()
+    n_quiet = n_flipped = 0
+    for amp in (1.5e-5, 3.0e-5, 4.5e-5):
+        F = np.diag([1 + e + 1.6e-4, 1 - 0.5 * (e + 1.6e-4), 1 - 0.5 * (e + 1.6e-4)]) + amp * smooth
+        o.mechanical_response(F.reshape(n, 9), dt)
+        P_o, _ = o.mechanical_response2(dt, tangent=False)
+        P = g.to_natural(g.constitutive_response(g.to_device(F), dt)).reshape(n, 3, 3)
+        quiet = clean & (o.point_cutbacks == 0) & (g.get_state('cutbacks', 1)[:, 0] == 0)
+        flipped = quiet & (g.get_state('lp_iter', 1)[:, 0] != o.point_lp_iter)
+        err = _pointwise_rel(P, P_o)
+        assert (err[quiet & ~flipped] < RTOL).all() and (err[flipped] < 1e-6).all()
+        n_quiet += quiet.sum(); n_flipped += flipped.sum()
+    assert n_quiet > 2.5 * n and n_flipped <= 0.005 * n_quiet, (n_quiet, n_flipped)
+    assert o.point_lp_iter.mean() > 8 and g.counters()['deferred'] == 0
 
 
 def test_iteration_counters_match_oracle():

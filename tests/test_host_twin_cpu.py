@@ -116,7 +116,7 @@ def test_register_resident_pheno_matches_oracle(phase, rate):
     rng = np.random.default_rng(2)
     lib.twin_use_fast(1)
     try:
-        n_clean = 0
+        n_clean = n_flipped = 0
         for F in _path(cells, 4, rng, rate):
             snap = o.snapshot()
             o.mechanical_response(F.reshape(n, 9), 0.5)
@@ -130,17 +130,64 @@ def test_register_resident_pheno_matches_oracle(phase, rate):
                 assert r['ok']
                 if o.point_cutbacks[i] or r['cnt'][5]:
                     continue
+                # a stopping decision of the Newton loop (residual within rounding of its tolerance) may flip: such a
+                # cell ends one iteration apart, both answers inside the integrator's tolerance (1e-6); it must be rare
+                flipped = int(r['cnt'][0]) != int(o.point_lp_iter[i])
+                n_flipped += flipped
                 n_clean += 1
                 e = np.abs(r['P'] - o.a['P'][i]).max() / np.abs(o.a['P'][i]).max()
                 e = max(e, np.abs(r['Fp'] - o.a['Fp'][i]).max(), np.abs(r['Fe'] - o.a['Fe'][i]).max())
                 atol = np.ctypeslib.as_array(o.phases[0].atol)[:ns]
                 e = max(e, (np.abs(r['state'][:ns] - o.a['state'][i, :ns]) / np.maximum(np.abs(o.a['state'][i, :ns]), atol)).max())
                 et = np.abs(r['dPdF'] - dPdF_o[i].reshape(81)).max() / np.abs(dPdF_o[i]).max()
-                assert e < 1e-9 and et < 1e-8, (phase, i, e, et)
+                assert e < (1e-6 if flipped else 1e-9) and et < (1e-5 if flipped else 1e-8), (phase, i, e, et, flipped)
             if not o.point_cutbacks.any():
-                assert tuple(cnt[[0, 2, 3, 4, 5]]) == tuple(o.counters[[0, 2, 3, 4, 5]])
+                assert tuple(cnt[[2, 3, 4, 5]]) == tuple(o.counters[[2, 3, 4, 5]])
+                assert abs(int(cnt[0]) - int(o.counters[0])) <= n_flipped
             o.forward()
-        assert n_clean > 2 * n
+        assert n_clean > 2 * n and n_flipped <= 0.01 * n_clean
         assert np.abs(o.a['Lp']).max() > 1e-6
     finally:
         lib.twin_use_fast(0)
+
+
+def test_lane_schedule_is_bit_identical_to_nested_fast_formulation():
+    """pheno_lanes_dev.cuh (the three resumable pieces the lane-persistent kernel runs, line search included) against
+    pf_point without deferral: the points pf_point cuts back are exactly the ones the lane schedule gives up (they go to
+    the reference-order kernel), identical bits and counters on all others, over a multi-increment path."""
+    import twin
+    from solver_cpp_b200 import workloads as W, material as M
+    lib = twin.build()
+    cells = (4, 4, 3)
+    material, material_at, size = W.polycrystal(cells, 7, 'Cu_pheno', 0)
+    o = ConstitutiveOracle(material, material_at)
+    m = M.Material(material, material_at)
+    num = M.make_numerics()
+    n = int(np.prod(cells))
+    ns = o.phases[0].n_state
+    rng = np.random.default_rng(5)
+    lib.twin_set_defer(0)
+    n_fast = n_deferred = n_linesearch = 0
+    try:
+        for F in _path(cells, 4, rng, 2.0e-3):
+            snap = o.snapshot()
+            for i in range(n):
+                args = (lib, m.phases[0], num, snap['F0'][i], F[i].reshape(9), snap['Fp0'][i], snap['Lp0'][i], snap['Lp'][i],
+                        snap['S0'][i][V6], snap['state0'][i][:ns], np.zeros(1), 0.5)
+                lib.twin_use_fast(1)
+                a = twin.run_point(*args)
+                lib.twin_use_fast(2)
+                b = twin.run_point(*args)
+                gave_up = bool(lib.twin_last_deferred())
+                assert gave_up == (a['cnt'][5] > 0), i
+                n_deferred += gave_up
+                if gave_up:
+                    continue
+                n_fast += 1
+                for k in ('P', 'Fp', 'Fe', 'S', 'state', 'Lp', 'cnt'):
+                    assert np.array_equal(a[k], b[k]), (i, k)
+            o.mechanical_response(F.reshape(n, 9), 0.5)
+            o.forward()
+    finally:
+        lib.twin_use_fast(0)
+    assert n_fast > n and n_deferred > 0
