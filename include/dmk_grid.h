@@ -154,6 +154,9 @@ int dmk_materialpoint_forward(dmk_ctx* ctx);                       /* f_material
 int dmk_get_state(dmk_ctx* ctx, const char* name, double* host_out, size_t n_doubles);
 int dmk_get_counters(dmk_ctx* ctx, long long counters[7]);         /* Lp iters, stress calls, state iters, substeps, cutbacks, ill,
                                                                      * cells deferred to the reference-order kernel */
+/* cumulative lane-schedule statistics of the lane-persistent constitutive kernel: {Newton-block warp trips, lanes served,
+ * state-block trips, lanes, refill trips, lanes, Newton steps solved, 0} */
+int dmk_get_schedule_stats(dmk_ctx* ctx, long long stats[8]);
 int dmk_terminally_ill(dmk_ctx* ctx, int* flag, int reset);
 
 /* ------------------------------------------------------------------ spectral half (device-resident fields)

@@ -445,9 +445,9 @@ extern "C" int dmk_material_init(dmk_ctx* c, const dmk_phase* phases, int n_phas
   DMK_CUDA_CHECK(cudaMemset(pa->d_defer_count, 0, sizeof(unsigned)));
   DMK_CUDA_CHECK(cudaMalloc((void**)&pa->d_work, sizeof(unsigned long long)));
   DMK_CUDA_CHECK(cudaMalloc((void**)&pa->d_phases, n_phases * sizeof(DmkDevPhase)));
-  DMK_CUDA_CHECK(cudaMalloc((void**)&pa->d_counters, 8 * sizeof(unsigned long long)));
+  DMK_CUDA_CHECK(cudaMalloc((void**)&pa->d_counters, 16 * sizeof(unsigned long long)));
   DMK_CUDA_CHECK(cudaMalloc((void**)&pa->d_ill, sizeof(int)));
-  DMK_CUDA_CHECK(cudaMemset(pa->d_counters, 0, 8 * sizeof(unsigned long long)));
+  DMK_CUDA_CHECK(cudaMemset(pa->d_counters, 0, 16 * sizeof(unsigned long long)));
   DMK_CUDA_CHECK(cudaMemset(pa->d_ill, 0, sizeof(int)));
   DMK_CUDA_CHECK(cudaMemcpy(pa->phase, ph.data(), n * sizeof(int), cudaMemcpyHostToDevice));
   DMK_CUDA_CHECK(cudaMemcpy(pa->d_phases, dev.data(), n_phases * sizeof(DmkDevPhase), cudaMemcpyHostToDevice));
@@ -528,6 +528,17 @@ extern "C" int dmk_get_counters(dmk_ctx* c, long long counters[7]) {
   DMK_CUDA_CHECK(cudaStreamSynchronize(c->stream));
   counters[0] = (long long)h[0]; counters[1] = (long long)h[2]; counters[2] = (long long)h[3];
   counters[3] = (long long)h[4]; counters[4] = (long long)h[5]; counters[5] = (long long)h[6]; counters[6] = (long long)h[7];
+  return DMK_OK;
+}
+
+// lane-schedule statistics of the lane-persistent kernel (pheno_fast.cu), cumulative: warp trips and lanes served of the
+// Newton block, the state block and the refill; Newton steps solved (lanes that went past the residual)
+extern "C" int dmk_get_schedule_stats(dmk_ctx* c, long long stats[8]) {
+  int rc = need_points(c); if (rc) return rc;
+  unsigned long long h[16];
+  DMK_CUDA_CHECK(cudaMemcpyAsync(h, c->pts->d_counters, sizeof h, cudaMemcpyDeviceToHost, c->stream));
+  DMK_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+  for (int k = 0; k < 8; k++) stats[k] = (long long)h[8 + k];
   return DMK_OK;
 }
 

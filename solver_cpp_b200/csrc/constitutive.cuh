@@ -46,7 +46,7 @@ struct DmkPointArrays {
   dmk_phase* h_phases;                 // host copy
   DmkDevPhase* h_dev_phases;           // host copy of the device tables
   int law_of_phase[DMK_MAX_PHASES], nstate_of_phase[DMK_MAX_PHASES], nsys_of_phase[DMK_MAX_PHASES];
-  unsigned long long* d_counters;      // 8: Lp iters, Li iters, stress calls, state iters, substeps, cutbacks, ill cells, deferred cells
+  unsigned long long* d_counters;      // 16: Lp iters, Li iters, stress calls, state iters, substeps, cutbacks, ill cells, deferred cells | 8 lane-schedule statistics
   int* d_ill;                          // device flag (OR of broken cells since the last reset)
   long long n_cells_of_phase[DMK_MAX_PHASES];
 };

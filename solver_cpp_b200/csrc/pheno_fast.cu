@@ -48,11 +48,12 @@ static int defer_setting() {
   return v < 0 ? 0 : v;
 }
 
-// DMK_PHENO_UNROLL=<1|4|12>: unroll factor of the slip-system loops inside the Newton iteration.  Default 1: the kernels
-// are instruction-fetch bound (ncu: no_instruction is the top stall, 57 % instruction-cache hit rate with the loops
-// unrolled 12-fold; 128^3 solver iterate: 28.1 / 29.7 / 31.3 ms for 1 / 4 / 12, profiles/r01_summary.md)
+// DMK_PHENO_UNROLL=<1|2|3|4|12>: unroll factor of the slip-system loops inside the Newton iteration.  Default 2: unrolled
+// 12-fold the kernels are instruction-fetch bound (ncu: no_instruction the top stall, 57 % instruction-cache hit rate;
+// 128^3 solver iterate 31.3 ms against 28.1 ms rolled); 2 adds a little instruction-level parallelism to the rolled
+// loops (25.0 against 25.9 ms), profiles/r01_summary.md
 static int unroll_setting() {
-  static const int v = [] { const char* e = getenv("DMK_PHENO_UNROLL"); return e ? atoi(e) : 1; }();
+  static const int v = [] { const char* e = getenv("DMK_PHENO_UNROLL"); return e ? atoi(e) : 2; }();
   return v;
 }
 
@@ -96,6 +97,7 @@ dmk_pheno_lanes_kernel(const __grid_constant__ DmkPhenoK<NSL> K, DmkPointArrays 
   long long c_next = 0, c_end = 0;                      // the warp's current chunk (warp-uniform)
   bool drained = false;
   unsigned n_Lp = 0, n_calls = 0, n_pts = 0, n_defer = 0;
+  unsigned t_lp = 0, l_lp = 0, t_sb = 0, l_sb = 0, t_rf = 0, l_rf = 0;     // schedule statistics (lane 0: warp totals)
   double S[6];
   for (;;) {
     // ---- vote: a trip runs EITHER one Newton iteration OR refill + state block, whichever has more lanes waiting for it.
@@ -108,6 +110,7 @@ dmk_pheno_lanes_kernel(const __grid_constant__ DmkPhenoK<NSL> K, DmkPointArrays 
     if (!(bL | bS | need)) break;
     if (__popc(bL) >= __popc(bS) + __popc(need)) {
       // ---- one Newton iteration
+      t_lp++; l_lp += __popc(bL);
       if (L.mode == PL_LP) {
         const int rc = pl_lp_iteration<NSL, NEXP, UNR>(K, num, dt, scr, L);
         if (rc == PL_DONE) L.mode = PL_CONV;
@@ -116,6 +119,7 @@ dmk_pheno_lanes_kernel(const __grid_constant__ DmkPhenoK<NSL> K, DmkPointArrays 
       continue;
     }
     // ---- refill
+    if (need) { t_rf++; l_rf += __popc(need); }
     while (need) {
       if (c_next >= c_end) {
         unsigned long long base = 0;
@@ -138,8 +142,10 @@ dmk_pheno_lanes_kernel(const __grid_constant__ DmkPhenoK<NSL> K, DmkPointArrays 
       need = __ballot_sync(FULL, L.mode == PL_NEED);
     }
     // ---- state block
+    const unsigned group = __ballot_sync(FULL, L.mode == PL_INIT || L.mode == PL_CONV);
+    t_sb++; l_sb += __popc(group);
     if (L.mode == PL_INIT || L.mode == PL_CONV) {
-      const int rc = pl_state_block<NSL, NEXP>(K, num, pa, Fin, Pout, dt, scr, L, S, L.mode == PL_INIT);
+      const int rc = pl_state_block<NSL, NEXP>(K, num, pa, Fin, Pout, dt, scr, L, S, L.mode == PL_INIT, group);
       if (rc == PL_CONTINUE) L.mode = PL_LP;
       else {
         if (rc == PL_DONE) { n_Lp += L.nLp_pt; n_calls += (unsigned)L.it; n_pts++; }
@@ -155,6 +161,11 @@ dmk_pheno_lanes_kernel(const __grid_constant__ DmkPhenoK<NSL> K, DmkPointArrays 
     unsigned s = v[k];
     for (int off = 16; off > 0; off >>= 1) s += __shfl_down_sync(FULL, s, off);
     if (lane == 0 && s) atomicAdd(&pa.d_counters[k], (unsigned long long)s);
+  }
+  if (lane == 0) {
+    const unsigned w[6] = {t_lp, l_lp, t_sb, l_sb, t_rf, l_rf};
+#pragma unroll
+    for (int k = 0; k < 6; k++) atomicAdd(&pa.d_counters[8 + k], (unsigned long long)w[k]);
   }
 }
 
@@ -201,12 +212,14 @@ int dmk_points_pheno_fast(dmk_ctx* c, int ph, const DmkNumDev& nd, const double*
   double step = 1.0;
   if (lanes_setting() && dmk_pheno_lanes_eligible(nd, &step)) {
     *deferred = true;
-    if (nexp == 20) rc = (u == 1) ? launch_pheno_lanes<12, 20, 1>(c, pa, ph, d, nd, d_F, d_P, step, dt)
-                       : (u == 4) ? launch_pheno_lanes<12, 20, 4>(c, pa, ph, d, nd, d_F, d_P, step, dt)
-                                  : launch_pheno_lanes<12, 20, 12>(c, pa, ph, d, nd, d_F, d_P, step, dt);
-    else rc = (u == 1) ? launch_pheno_lanes<12, 0, 1>(c, pa, ph, d, nd, d_F, d_P, step, dt)
-            : (u == 4) ? launch_pheno_lanes<12, 0, 4>(c, pa, ph, d, nd, d_F, d_P, step, dt)
-                       : launch_pheno_lanes<12, 0, 12>(c, pa, ph, d, nd, d_F, d_P, step, dt);
+#define DMK_PL_LAUNCH(NEXP_)                                                                                   \
+  (u == 2)    ? launch_pheno_lanes<12, NEXP_, 2>(c, pa, ph, d, nd, d_F, d_P, step, dt)                         \
+  : (u == 3)  ? launch_pheno_lanes<12, NEXP_, 3>(c, pa, ph, d, nd, d_F, d_P, step, dt)                         \
+  : (u == 4)  ? launch_pheno_lanes<12, NEXP_, 4>(c, pa, ph, d, nd, d_F, d_P, step, dt)                         \
+  : (u == 12) ? launch_pheno_lanes<12, NEXP_, 12>(c, pa, ph, d, nd, d_F, d_P, step, dt)                        \
+              : launch_pheno_lanes<12, NEXP_, 1>(c, pa, ph, d, nd, d_F, d_P, step, dt)
+    rc = (nexp == 20) ? (DMK_PL_LAUNCH(20)) : (DMK_PL_LAUNCH(0));
+#undef DMK_PL_LAUNCH
     if (rc) return rc;
     DMK_CUDA_CHECK(cudaGetLastError());
     return DMK_OK;

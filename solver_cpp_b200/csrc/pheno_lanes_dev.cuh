@@ -36,6 +36,15 @@
 #define PL_DONE 1
 #define PL_DEFER 2
 
+// re-convergence point of the lanes of `group` (device); nothing on the host twin, which runs one point at a time
+DMK_HD __forceinline__ void pl_converge(unsigned group) {
+#ifdef __CUDA_ARCH__
+  __syncwarp(group);
+#else
+  (void)group;
+#endif
+}
+
 template <int NSL>
 struct PlLane {
   double A[9], Lp[9];
@@ -72,6 +81,7 @@ DMK_HD __forceinline__ bool pl_begin(const DmkPointArrays& pa, long long i, cons
   for (int a = 0; a < 6; a++) S[a] = pa.S0[a * n + i];
 #pragma unroll 1
   for (int k = 0; k < 2 * NSL; k++) scr(O::ST + k) = pa.state0[k * n + i];
+  pf_rxi<NSL>(scr);                                   // 1 / xi of state0, for the predictor's dotState
   L.i = i; L.it = 0; L.nLp = 0; L.nLp_pt = 0; L.res_old = 0.0; L.step = 1.0;
   return true;
 }
@@ -123,17 +133,22 @@ DMK_HD __forceinline__ int pl_lp_iteration(const DmkPhenoK<NSL>& K, const DmkNum
   return PL_CONTINUE;
 }
 
-// State block of integrateStateFPI.  init: predictor (state = state0 + dotState(S0) dt).  Else: Fp and P of the stress
+// State block of integrateStateFPI.  init: predictor (state = state0 + dotState(S0) dt).  Else: S of the stress
 // integration that just converged, dotState, damper, corrector, convergence.  PL_CONTINUE: a Newton loop follows (1/xi
 // refreshed); PL_DONE: the point is finished and stored; PL_DEFER: nothing stored.
+// Predictor and corrector lanes run ONE copy of every loop (the predictor is the corrector with last(1) = last(2) = 0,
+// zeta = 1 and state == state0, bit for bit); `group` = the warp's lanes inside this call, re-converged before each
+// shared stretch -- with separate branches the compiler duplicated dotState and the loops and ran them once per branch,
+// at 3.8 and 17 of 32 lanes (ncu source view, profiles/r01_summary.md).
 template <int NSL, int NEXP>
 DMK_HD __forceinline__ int pl_state_block(const DmkPhenoK<NSL>& K, const DmkNumDev& num, const DmkPointArrays& pa,
                                           const double* __restrict__ Fin, double* __restrict__ Pout, double dt, const DmkScr& scr,
-                                          PlLane<NSL>& L, double (&S)[6], bool init) {
+                                          PlLane<NSL>& L, double (&S)[6], bool init, unsigned group) {
   typedef PfOff<NSL> O;
   constexpr int NST = 2 * NSL;
   const long long n = pa.n, i = L.i;
   double B[9], Fe[9];
+  bool defer = false;
   if (!init) {
     L.nLp_pt += (unsigned)L.nLp;
 #pragma unroll
@@ -141,25 +156,18 @@ DMK_HD __forceinline__ int pl_state_block(const DmkPhenoK<NSL>& K, const DmkNumD
     // The reference forms Fp and P after every stress integration (phase_mechanical.f90:586-604) and fails the sub-step if
     // Fp_new^-1 = Fp0^-1 B is singular; only the last Fp and P survive, so they are formed once, when the point is stored.
     // Fp0^-1 is regular (pl_begin), so the singularity test is made on B here.
-    if (deq0(det3(B))) return PL_DEFER;
+    defer = deq0(det3(B));
     mm3(L.A, B, Fe);
     hooke_S(K.C66, Fe, S);
   }
-  bool finished = false;
-  if (init) pf_rxi<NSL>(scr);                         // 1/xi of state0 (Newton lanes keep the one of their current iterate)
+  pl_converge(group);
   const bool nan = pf_dot_state<NSL, NEXP>(K, S, scr);
-  if (init) {
-    if (nan) return PL_DEFER;                         // reference: the sub-step fails and is cut back
-#pragma unroll 1
-    for (int k = 0; k < NST; k++) {                   // state = state0 + dot dt; last(1) = dot, last(2) = 0
-      const double d = pf_dot<NSL>(scr, k);
-      scr(O::ST + k) += d * dt;
-      scr(O::L1 + k) = d;
-      scr(O::D + k) = d;
-    }
-  } else if (nan) {
-    finished = true;                                  // NaN rate: leaves with broken = .false. (reference :660)
-  } else {
+  // reference: a NaN rate fails the predictor's sub-step (cut back: defer), but ENDS the corrector loop with
+  // broken = .false. (:660): the point is stored with the state of the previous iterate
+  defer = defer || (init && nan);
+  bool finished = !init && nan;
+  double zeta = 1.0;
+  if (!init && !nan) {
     double d12 = 0.0, d22 = 0.0, d01 = 0.0;           // damper (:677-690); D = last(1) - last(2)
 #pragma unroll 1
     for (int k = 0; k < NST; k++) {
@@ -168,28 +176,32 @@ DMK_HD __forceinline__ int pl_state_block(const DmkPhenoK<NSL>& K, const DmkNumD
       d22 += dd * dd;
       d01 += dk * l1;
     }
-    double zeta = 1.0;
     if (fmin(d01, d12) < 0.0 && d22 > 0.0) zeta = 0.75 + 0.25 * tanh(2.0 + 4.0 * d12 / d22);
+  }
+  pl_converge(group);
+  if (!nan) {
     bool conv = true;
 #pragma unroll 1
     for (int k = 0; k < NST; k++) {
-      const double l1 = scr(O::L1 + k);
+      const double l1 = init ? 0.0 : scr(O::L1 + k);
       const double d = pf_dot<NSL>(scr, k) * zeta + l1 * (1.0 - zeta);
       scr(O::D + k) = d - l1;
       scr(O::L1 + k) = d;
       double s = scr(O::ST + k);
-      const double r = s - pa.state0[k * n + i] - d * dt;
+      const double r = s - pa.state0[k * n + i] - d * dt;       // predictor: s == state0, r = -d dt
       s -= r;
       scr(O::ST + k) = s;
       if (!(fabs(r) <= fmax(K.atol[k], num.eps_rel_state * fabs(s)))) conv = false;
     }
-    finished = conv || L.it >= num.N_iter_state_max;  // a loop that runs out leaves broken = .false., as in the reference
+    finished = !init && (conv || L.it >= num.N_iter_state_max);   // a loop that runs out leaves broken = .false. (reference)
   }
-  if (!finished) {
+  pl_converge(group);
+  if (!finished && !defer) {
     L.it++; L.nLp = 0; L.step = 1.0;
     pf_rxi<NSL>(scr);
-    return PL_CONTINUE;
   }
+  if (defer) return PL_DEFER;
+  if (!finished) return PL_CONTINUE;
   // ---- Fp, P (phase_mechanical.f90:586-604; F invFp_new == A B == Fe) and store the point
   double P[9], Fp[9];
   {
@@ -238,11 +250,11 @@ DMK_HD inline int pl_run_point(const DmkPhenoK<NSL>& K, const DmkNumDev& num, co
   double S[6];
   const double dt = step * Dt;
   if (!pl_begin<NSL>(pa, i, Fin, step, scr, L, S)) return PF_DEFER;
-  int rc = pl_state_block<NSL, NEXP>(K, num, pa, Fin, Pout, dt, scr, L, S, true);
+  int rc = pl_state_block<NSL, NEXP>(K, num, pa, Fin, Pout, dt, scr, L, S, true, 0xffffffffu);
   while (rc == PL_CONTINUE) {
     do { rc = pl_lp_iteration<NSL, NEXP, 1>(K, num, dt, scr, L); } while (rc == PL_CONTINUE);
     if (rc == PL_DEFER) return PF_DEFER;
-    rc = pl_state_block<NSL, NEXP>(K, num, pa, Fin, Pout, dt, scr, L, S, false);
+    rc = pl_state_block<NSL, NEXP>(K, num, pa, Fin, Pout, dt, scr, L, S, false, 0xffffffffu);
   }
   if (rc == PL_DEFER) return PF_DEFER;
   cnt.Lp_iter += L.nLp_pt; cnt.Li_iter += L.it; cnt.stress_calls += L.it; cnt.state_iter += L.it; cnt.substeps += 1;

@@ -177,6 +177,11 @@ class GridContext:
         L.check(self.lib.dmk_get_counters(self.ctx, a))
         return dict(zip(('Lp_iter', 'stress_calls', 'state_iter', 'substeps', 'cutbacks', 'ill_cells', 'deferred'), list(a)))
 
+    def schedule_stats(self):
+        a = (C.c_longlong * 8)()
+        L.check(self.lib.dmk_get_schedule_stats(self.ctx, a))
+        return dict(zip(('lp_trips', 'lp_lanes', 'sb_trips', 'sb_lanes', 'refill_trips', 'refill_lanes'), list(a)[:6]))
+
     def get_state(self, name, comps):
         out = np.zeros((self.n_local, comps))
         L.check(self.lib.dmk_get_state(self.ctx, name.encode(), _hp(out), C.c_size_t(out.size)))
