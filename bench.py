@@ -45,6 +45,22 @@ def peaks():
     return 6650.0, 'fallback (B200_PROFILING.md)'
 
 
+def section_traffic(cells, world):
+    """dram__bytes_read + dram__bytes_write of the five FFT/Gamma kernels of one evaluation from the round's `ncu --set full`
+    capture (profiles/r01_step_ncu_metrics.csv), bytes per evaluation; None for configurations that were not captured"""
+    p = os.path.join(ROOT, 'profiles', 'r01_step_ncu_metrics.csv')
+    if world != 1 or tuple(cells) != (256, 256, 256) or not os.path.exists(p):
+        return None
+    import csv
+    rows = list(csv.reader(open(p)))
+    h = rows[0]
+    tot = 0.0
+    for r in rows[2:]:
+        if 'dmk_fast_' in r[h.index('Kernel Name')]:
+            tot += (float(r[h.index('dram__bytes_read.sum')]) + float(r[h.index('dram__bytes_write.sum')])) * 1e9
+    return tot or None
+
+
 def taylor_F(inc, shape_prefix=None):
     """homogeneous tensionX deformation gradient after `inc` increments (lateral contraction ~ incompressible flow)"""
     e = RATE * DT * inc
@@ -298,8 +314,8 @@ def run_ours(args):
                       'gamma_div_zpass': prof['gamma_zpass_ms'] / max(prof['evaluations'], 1),
                       'fft_inverse_yx': prof['fft_inverse_ms'] / max(prof['evaluations'], 1)},
         'roofline': {'bound': 'hbm', 'kernel': 'FFT + Gamma/div section (x r2c, y, fused z, y^-1, x c2r): 5 passes x 144 B/cell',
-                     'achieved': achieved, 'peak': hbm_peak, 'unit': 'GB/s', 'frac': achieved / hbm_peak, 'traffic': None,
-                     'peak_source': peak_src},
+                     'achieved': achieved, 'peak': hbm_peak, 'unit': 'GB/s', 'frac': achieved / hbm_peak,
+                     'traffic': section_traffic(cells, world), 'peak_source': peak_src},
         'roofline_fp64': {'bound': 'fp64', 'kernel': 'dmk_constitutive_kernel (dominant by time)', 'achieved': fp64_achieved,
                           'peak': fp64_peak, 'unit': 'TFLOP/s', 'frac': fp64_achieved / fp64_peak if fp64_peak else None,
                           'peak_source': 'measured in this run (DFMA chains, dmk_fp64_peak)',

@@ -105,7 +105,7 @@ DMK_HD __forceinline__ int pl_lp_iteration(const DmkPhenoK<NSL>& K, const DmkNum
   double res[9];
 #pragma unroll
   for (int a = 0; a < 9; a++) res[a] = 0.0;
-#pragma unroll UNR
+#pragma unroll (unr_rate(UNR))
   for (int s = 0; s < NSL; s++) {
     double dg, c;
     pf_rate<NSL, NEXP>(K, s, S, scr(O::RXI + s), dg, c);
