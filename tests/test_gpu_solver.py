@@ -126,6 +126,22 @@ def test_masked_compliance_known_answer():
         assert _rel(fortran_to_c3333(out), S_o) < 1e-12
 
 
+def test_g3_masked_compliance_unit_test_literal(golden_dir):
+    """the reference's own unit-test vector (test_mech_base.cpp:239-321): literal stiffness and mask -> literal compliance"""
+    import ctypes as C
+    from solver_cpp_b200 import lib as L
+    from solver_cpp_b200.grid import c3333_to_fortran, fortran_to_c3333
+    g3 = np.load(os.path.join(golden_dir, 'g3_unit_test_literals.npz'))
+    out = np.zeros(81)
+    Cf = c3333_to_fortran(g3['mc_C'])
+    Rm = np.ascontiguousarray(np.eye(3).reshape(9))
+    mi = np.ascontiguousarray(g3['mc_mask_stress'].reshape(9), dtype=np.int32)
+    L.check(L.load().dmk_masked_compliance(Cf.ctypes.data_as(C.c_void_p), Rm.ctypes.data_as(C.c_void_p),
+                                           mi.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p)))
+    exp = g3['mc_expected']
+    assert np.abs(fortran_to_c3333(out) - exp).max() <= 1e-12 * np.abs(exp).max()
+
+
 def test_form_residual_host_roundtrip():
     """the reference-facing call with HOST buffers in the reference's memory order equals the device-pointer call"""
     from solver_cpp_b200 import mech, workloads as W

@@ -104,3 +104,15 @@ def test_forward_field_and_rate():
     out = g.forward_field(0.5, g.to_device(f0), rate, aim)
     ref = osp.forward_field(0.5, f0, ref_rate, grid, aim)
     assert np.abs(g.to_natural(out) - ref).max() < 1e-13
+
+
+def test_g3_divergence_rms_unit_test_literal(golden_dir):
+    """the reference's own unit-test vector (test_mech_base.cpp:324-385): literal 4x1x1 field -> 1481.2323577332318"""
+    import os
+    g3 = np.load(os.path.join(golden_dir, 'g3_unit_test_literals.npz'))
+    cells = tuple(int(c) for c in g3['div_cells'])
+    g = _ctx(cells, tuple(1e-5 * c for c in cells), derivative=0)
+    g.update_gamma(_stiffness(np.random.default_rng(0)))
+    field = np.ascontiguousarray(np.transpose(g3['div_field'], (4, 3, 2, 0, 1)))
+    rms = g.divergence_and_gamma(g.to_device(field), np.zeros((3, 3)))
+    assert abs(rms - float(g3['div_rms'])) <= 1e-12 * float(g3['div_rms'])

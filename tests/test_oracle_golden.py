@@ -101,3 +101,40 @@ def test_cutback_path_is_rounding_sensitive(tmp_path):
     assert err[quiet].max(initial=0.0) < 1e-9
     assert (a.point_cutbacks > 0).any()
     assert (err >= 1e-9).mean() < 0.1
+
+
+@pytest.fixture(scope='module')
+def g3(golden_dir):
+    return np.load(os.path.join(golden_dir, 'g3_unit_test_literals.npz'))
+
+
+def test_g3_divergence_rms_unit_test_literal(g3):
+    """test_mech_base.cpp:324-385 (MechBaseTestDivergenceRMS): the reference's own literal field on a 4x1x1 grid and its
+    expected value 1481.2323577332318; the xi table the oracle builds must be the literal one of the test."""
+    cells = tuple(int(c) for c in g3['div_cells'])
+    grid = sp.Grid(cells, tuple(1e-5 * c for c in cells))             # conftest.h:39-40: geom_size = cells * 1e-5
+    xi1, _ = sp.xi_tables(grid, 0)
+    lit = np.transpose(g3['div_xi1st'], (2, 3, 1, 0))                  # (3, kx, kz, ky) -> [kz, ky, kx, 3]
+    assert np.abs(xi1 - lit).max() <= 1e-9 * np.abs(lit).max()
+    field = np.transpose(g3['div_field'], (4, 3, 2, 0, 1))             # (i, j, x, y, z) -> [z, y, x, i, j]
+    rms, _ = sp.divergence_rms(sp.fft_forward(field), xi1, grid, sp.scaled_geom_size(grid))
+    assert abs(rms - float(g3['div_rms'])) <= 1e-12 * float(g3['div_rms'])
+
+
+def test_g3_masked_compliance_unit_test_literal(g3):
+    """test_mech_base.cpp:239-321 (MechBaseTestMaskedCompliance): literal stiffness, tensionX-like mask, literal result."""
+    S = sp.masked_compliance(g3['mc_C'], np.eye(3), g3['mc_mask_stress'])
+    exp = g3['mc_expected']
+    assert np.abs(S - exp).max() <= 1e-12 * np.abs(exp).max()
+    assert (S[exp == 0] == 0).all()
+
+
+def test_g3_homogenisation_unit_test_literal(g3):
+    """test_spectral.cpp:58-216 (SpectralTestConstitutiveResponse): literal P and dPdF of two cells ('10th iteration of
+    tensionX') -> literal P_av, C_volAvg, C_minMaxAvg."""
+    grid = sp.Grid((2, 1, 1), (2e-5, 1e-5, 1e-5))
+    P = np.transpose(g3['hom_P'], (2, 0, 1))                           # (i, j, cell) -> [cell, i, j]
+    dPdF = np.transpose(g3['hom_dPdF'], (4, 0, 1, 2, 3))
+    P_av, C_vol, C_mm, _ = sp.homogenise(P, dPdF, grid)
+    for got, key in ((P_av, 'hom_P_av'), (C_vol, 'hom_C_vol_avg'), (C_mm, 'hom_C_minmax_avg')):
+        assert np.abs(got - g3[key]).max() <= 1e-12 * np.abs(g3[key]).max(), key
