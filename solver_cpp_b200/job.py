@@ -1,0 +1,44 @@
+"""A DAMASK grid job from the reference's own input files: geometry (.vti), material.yaml, load.yaml, numerics.yaml --
+what `DAMASK_grid -g .. -m .. -l .. -n ..` parses in main.cpp:31-101, config.cpp:247-430 and discretization_grid.cpp:8-76
+of the reference -- handed to the device-resident solver.  Host-side input plumbing; no result files."""
+import numpy as np
+import yaml
+
+from . import material as M
+from . import mech, parallel
+from .vti import read_vti
+
+_DERIVATIVE = {'continuous': 0, 'central_difference': 1, 'FWBW_difference': 2}
+_DIVCORR = {'none': 0, 'size': 1, 'size+grid': 2, 'grid+size': 2}
+
+
+def read_numerics(path=None):
+    """numerics.yaml -> (lib.Numerics, derivative id, divergence-correction id); defaults: config.h:50-78 of the reference"""
+    d = yaml.safe_load(open(path)) if path else {}
+    d = d or {}
+    grid = ((d.get('solver') or {}).get('grid') or {})
+    fft = grid.get('FFT') or {}
+    num = M.make_numerics(((d.get('phase') or {}).get('mechanical')), grid.get('mechanical'))
+    return num, _DERIVATIVE[fft.get('derivative', 'continuous')], _DIVCORR[str(fft.get('divergence_correction', 'size+grid'))]
+
+
+def load_job(geometry, material, load, numerics=None, world_size=1, rank=0, comm=None):
+    """-> (MechSolverBasic on this rank's z-slab, parsed load steps).  `material` / `load` may be paths or parsed dicts."""
+    geo = read_vti(geometry)
+    mat = yaml.safe_load(open(material)) if isinstance(material, str) else material
+    ld = yaml.safe_load(open(load)) if isinstance(load, str) else load
+    num, derivative, divcorr = read_numerics(numerics)
+    cells = tuple(int(c) for c in geo['cells'])
+    if int(geo['material'].max()) >= len(mat['material']) or int(geo['material'].min()) < 0:
+        raise ValueError('geometry refers to material %d, material.yaml has %d entries' % (int(geo['material'].max()), len(mat['material'])))
+    z0, z1 = parallel.slab_range(cells[2], world_size, rank)
+    solver = mech.make_solver(cells, tuple(float(s) for s in geo['size']), mat, np.ascontiguousarray(geo['material'][z0:z1]), numerics=num,
+                              derivative=derivative, divergence_correction=divcorr, world_size=world_size, rank=rank, comm=comm)
+    return solver, mech.parse_load(ld)
+
+
+def run_job(geometry, material, load, numerics=None, **kw):
+    """the whole load case; one record per converged increment (mech.loop_over_loadcase)"""
+    solver, steps = load_job(geometry, material, load, numerics, **kw)
+    solver.init()
+    return mech.loop_over_loadcase(solver, steps)

@@ -1,0 +1,33 @@
+"""Golden set G4: per-point F and P of a REAL DAMASK run (DAMASK_grid 3.0.0-alpha7-366, 6x7x8 cells, 6 grains, fcc
+phenopowerlaw, tensionY, 40 increments) shipped with the reference as a DADF5 result file, extracted with the repo's
+own minimal HDF5 reader into tests/golden/g4_damask_run.npz.  The run's inputs are the three fixtures next to it
+(6grains6x7x8_single_phase.vti / .material.yaml, 6grains6x7x8_tensionY.load.yaml: copies of the reference's files).
+Run in the build container:  python tests/golden/make_golden_g4.py"""
+import importlib.util
+import os
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SRC = '/root/reference/python/tests/resources/Result/6grains6x7x8_single_phase_tensionY.hdf5'
+spec = importlib.util.spec_from_file_location('hdf5_min', os.path.join(HERE, '..', '..', 'solver_cpp_b200', 'hdf5_min.py'))
+h5 = importlib.util.module_from_spec(spec)
+spec.loader.exec_module(h5)
+
+
+def main():
+    f = h5.H5File(SRC)
+    raw = f.read('/cell_to/phase').tobytes()
+    rec = len(raw) // 336
+    entry = np.array([int.from_bytes(raw[rec * i + rec - 8:rec * i + rec], 'little') for i in range(336)])
+    assert (entry == np.arange(336)).all()                    # phase entries are stored in cell order (x fastest)
+    incs = [4, 8, 20, 40]
+    out = {'increments': np.array(incs)}
+    for name in ('F', 'P'):
+        out[name] = np.stack([f.read('/increment_%d/phase/pheno_fcc/mechanical/%s' % (i, name)) for i in incs])
+    out['xi_sl_final'] = f.read('/increment_40/phase/pheno_fcc/mechanical/xi_sl')
+    np.savez_compressed(os.path.join(HERE, 'g4_damask_run.npz'), **out)
+    print({k: v.shape for k, v in out.items()})
+
+
+if __name__ == '__main__':
+    main()

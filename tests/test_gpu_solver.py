@@ -142,6 +142,39 @@ def test_g3_masked_compliance_unit_test_literal(golden_dir):
     assert np.abs(fortran_to_c3333(out) - exp).max() <= 1e-12 * np.abs(exp).max()
 
 
+def test_g4_job_from_the_reference_input_files(golden_dir):
+    """The reference's own input deck (geometry .vti, material.yaml, load.yaml) read by solver_cpp_b200.job and solved on
+    the GPU: identical iteration counts and 1e-9 agreement with the free-running oracle, and agreement with the REAL
+    DAMASK result file of that deck (golden set G4) within the solver's tolerances, at increments 4 and 8."""
+    from solver_cpp_b200 import job, mech
+    from solver_cpp_b200.vti import read_vti
+    g4 = np.load(os.path.join(golden_dir, 'g4_damask_run.npz'))
+    files = [os.path.join(golden_dir, f) for f in ('6grains6x7x8_single_phase.vti', '6grains6x7x8_single_phase.material.yaml',
+                                                   '6grains6x7x8_tensionY.load.yaml')]
+    s, steps = job.load_job(*files)
+    s.init()
+    snap = {}
+
+    def cb(rec, solver):
+        if rec['inc'] in (4, 8):
+            snap[rec['inc']] = solver.g.to_natural(solver.field('F')).reshape(-1, 3, 3).copy()
+    recs = mech.loop_over_loadcase(s, steps, callback=cb, max_increments=8)
+    geo = read_vti(files[0])
+    o = MechSolverBasicOracle(tuple(int(c) for c in geo['cells']), tuple(geo['size']), yaml.safe_load(open(files[1])),
+                              geo['material'].reshape(-1))
+    o.init()
+    st = oparse(yaml.safe_load(open(files[2])))
+    st[0]['N'], st[0]['t'] = 8, st[0]['t'] * 8 / st[0]['N']
+    recs_o = run_loadcase(o, st)
+    assert [r['iterations'] for r in recs] == [r['iterations'] for r in recs_o]
+    for a, b in zip(recs, recs_o):
+        assert _rel(a['P_av'], b['P_av']) < 1e-9
+    for k, inc in enumerate(g4['increments'][:2]):
+        Pd = g4['P'][k]
+        assert np.abs(snap[int(inc)] - g4['F'][k]).max() < 1e-5
+        assert np.abs(recs[int(inc) - 1]['P_av'] - Pd.mean(0)).max() < 3e-4 * np.abs(Pd.mean(0)).max()
+
+
 def test_form_residual_host_roundtrip():
     """the reference-facing call with HOST buffers in the reference's memory order equals the device-pointer call"""
     from solver_cpp_b200 import mech, workloads as W

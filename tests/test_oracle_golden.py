@@ -138,3 +138,39 @@ def test_g3_homogenisation_unit_test_literal(g3):
     P_av, C_vol, C_mm, _ = sp.homogenise(P, dPdF, grid)
     for got, key in ((P_av, 'hom_P_av'), (C_vol, 'hom_C_vol_avg'), (C_mm, 'hom_C_minmax_avg')):
         assert np.abs(got - g3[key]).max() <= 1e-12 * np.abs(g3[key]).max(), key
+
+
+def test_g4_real_damask_run_reproduced_within_solver_tolerance(golden_dir):
+    """Golden set G4: a real DAMASK_grid (3.0.0-alpha7) result file shipped with the reference
+    (python/tests/resources/Result/6grains6x7x8_single_phase_tensionY.hdf5; non-cubic 6x7x8 grid, mixed boundary
+    conditions, 40 increments), read with the repo's HDF5 reader (tests/golden/make_golden_g4.py).  Two converged
+    equilibrium solves agree to the solver's own tolerances (eps_rel_div = 5e-4, eps_rel_P = 1e-3), not to rounding:
+    per-point F to 1e-5 absolute, per-point P to 5e-4 of max|P|, homogenised P to 3e-4, final slip resistances to 1e-4."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location('dmk_vti', os.path.join(golden_dir, '..', '..', 'solver_cpp_b200', 'vti.py'))
+    vti = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(vti)
+    g4 = np.load(os.path.join(golden_dir, 'g4_damask_run.npz'))
+    geo = vti.read_vti(os.path.join(golden_dir, '6grains6x7x8_single_phase.vti'))
+    mat = yaml.safe_load(open(os.path.join(golden_dir, '6grains6x7x8_single_phase.material.yaml')))
+    load = yaml.safe_load(open(os.path.join(golden_dir, '6grains6x7x8_tensionY.load.yaml')))
+    o = MechSolverBasicOracle(tuple(int(c) for c in geo['cells']), tuple(geo['size']), mat, geo['material'].reshape(-1))
+    o.init()
+    snap = {}
+
+    def cb(rec, s):
+        if rec['inc'] in g4['increments']:
+            snap[rec['inc']] = (s.F.reshape(-1, 3, 3).copy(), s.con.a['P'].reshape(-1, 3, 3).copy(), s.con.a['state'].copy())
+    recs = run_loadcase(o, parse_load(load), callback=cb)
+    assert len(recs) == 40 and all(r['converged'] for r in recs)
+    for k, inc in enumerate(g4['increments']):
+        F, P, _ = snap[int(inc)]
+        Pd = g4['P'][k]
+        assert np.abs(F - g4['F'][k]).max() < 1e-5
+        assert np.abs(P - Pd).max() < 5e-4 * np.abs(Pd).max()
+        assert np.abs(P.mean(0) - Pd.mean(0)).max() < 3e-4 * np.abs(Pd.mean(0)).max()
+        dFav = np.abs(F.mean(0) - g4['F'][k].mean(0))
+        free = np.zeros((3, 3), bool)
+        free[0, 0] = free[2, 2] = True                                  # stress-controlled components of the average
+        assert dFav[~free].max() < 1e-12 and dFav[free].max() < 1e-6
+    assert np.abs(snap[40][2][:, :12] - g4['xi_sl_final']).max() < 1e-4 * g4['xi_sl_final'].max()

@@ -1,0 +1,41 @@
+"""CPU tests of the geometry reader / writer (solver_cpp_b200/vti.py) against a file written by upstream DAMASK's own
+tooling (fixture copied from the reference tree: python/tests/resources/Result/6grains6x7x8_single_phase.vti)."""
+import importlib.util
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+_spec = importlib.util.spec_from_file_location('dmk_vti', os.path.join(HERE, '..', 'solver_cpp_b200', 'vti.py'))
+vti = importlib.util.module_from_spec(_spec)
+_spec.loader.exec_module(vti)          # by path: importing the package would load the CUDA library
+
+
+def test_reads_a_damask_written_file(golden_dir):
+    d = vti.read_vti(os.path.join(golden_dir, '6grains6x7x8_single_phase.vti'))
+    assert tuple(d['cells']) == (6, 7, 8)
+    assert np.allclose(d['size'], (0.75, 0.875, 1.0)) and np.allclose(d['origin'], 0.0)
+    m = d['material']
+    assert m.shape == (8, 7, 6) and m.min() == 0 and m.max() == 5          # RangeMin / RangeMax of the file
+    assert np.bincount(m.ravel()).tolist() == [49, 58, 51, 56, 60, 62]
+
+
+def test_round_trip_compressed_and_plain(tmp_path):
+    rng = np.random.default_rng(0)
+    m = rng.integers(0, 500, size=(9, 17, 33))
+    for compress in (True, False):
+        p = str(tmp_path / ('g%d.vti' % compress))
+        vti.write_vti(p, m, (3.3e-5, 1.7e-5, 0.9e-5), origin=(1e-6, 0, 0), compress=compress, block=4096)
+        d = vti.read_vti(p)
+        assert (d['material'] == m).all() and tuple(d['cells']) == (33, 17, 9)
+        assert np.allclose(d['size'], (3.3e-5, 1.7e-5, 0.9e-5), rtol=1e-14) and np.allclose(d['origin'], (1e-6, 0, 0))
+
+
+def test_rejects_wrong_cell_count(tmp_path):
+    import pytest
+    p = str(tmp_path / 'bad.vti')
+    vti.write_vti(p, np.zeros((2, 2, 2), int), (1, 1, 1))
+    txt = open(p).read().replace('WholeExtent="0 2 0 2 0 2"', 'WholeExtent="0 3 0 2 0 2"')
+    open(p, 'w').write(txt)
+    with pytest.raises(ValueError):
+        vti.read_vti(p)
