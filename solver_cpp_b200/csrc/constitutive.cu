@@ -272,6 +272,11 @@ static int persistent_grid(K kernel, long long n) {
     else KERNEL<DMK_LAW_DISLOTWIN, DMK_MAX_STATE, DMK_MAX_DEP> __VA_ARGS__;                                     \
   } while (0)
 
+int dmk_wait_staged_input(dmk_ctx* c, const double* d_F) {
+  if (c->stage_chunks > 1 && d_F == c->stage_dst) DMK_CUDA_CHECK(cudaStreamWaitEvent(c->stream, c->stage_ev[c->stage_chunks - 1], 0));
+  return DMK_OK;
+}
+
 int dmk_points_constitutive(dmk_ctx* c, const double* d_F, double* d_P, double dt) {
   DmkPointArrays& pa = *c->pts;
   const DmkNumDev nd = num_dev(c->num);
@@ -291,6 +296,7 @@ int dmk_points_constitutive(dmk_ctx* c, const double* d_F, double* d_P, double d
       }
       continue;
     }
+    { int rc = dmk_wait_staged_input(c, d_F); if (rc) return rc; }
     if (use_machine) DMK_LAUNCH_PERSISTENT(dmk_constitutive_kernel, law, nst, pa.n, c->stream, (pa, ph, nd, d_F, d_P, dt));
     else DMK_DISPATCH(dmk_constitutive_nested_kernel, law, nst, <<<point_grid(pa.n), DMK_PT_THREADS, 0, c->stream>>>(pa, ph, nd, d_F, d_P, dt, nullptr, nullptr));
     c->launches++;

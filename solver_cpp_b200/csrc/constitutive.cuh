@@ -59,6 +59,7 @@ struct DmkNumDev {
 };
 
 int dmk_points_constitutive(dmk_ctx* c, const double* d_F, double* d_P, double dt);
+int dmk_wait_staged_input(dmk_ctx* c, const double* d_F);   // kernels without chunked launches: wait for the whole staged field
 int dmk_points_pheno_fast(dmk_ctx* c, int ph, const DmkNumDev& nd, const double* d_F, double* d_P, double dt, bool* handled,
                           bool* deferred /*out: cells may be waiting in pa.defer_list*/);
 int dmk_points_tangent(dmk_ctx* c, double dt, double* d_Csum81 /*device, row-major sum over local cells*/,

@@ -40,6 +40,10 @@ struct dmk_ctx {
 
   // ---- constitutive
   DmkPointArrays* pts;
+  // input staging of dmk_mech_form_residual_host: F arrives in `stage_chunks` z-chunks on `copy_stream`, chunk k is complete
+  // when stage_ev[k] fires; the lane-persistent kernel is launched per chunk behind its event (0: F is resident)
+  cudaStream_t copy_stream; cudaEvent_t stage_ev[8]; cudaEvent_t stage_begin; int stage_chunks; bool stage_ready;
+  const double* stage_dst;        // device field the staged copy fills (the chunked launches apply to this input only)
   dmk_numerics num;
   // ---- mechanical solver
   DmkMech* mech;

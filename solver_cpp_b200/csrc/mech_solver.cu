@@ -613,8 +613,35 @@ extern "C" int dmk_mech_form_residual(dmk_ctx* c, const double* d_F, double* d_r
 extern "C" int dmk_mech_form_residual_host(dmk_ctx* c, const double* F, double* r) {
   int rc = need_mech(c); if (rc) return rc;
   DmkMech* m = c->mech;
-  DMK_CUDA_CHECK(cudaMemcpyAsync(m->XM, F, m->n9 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
-  if ((rc = dmk_mech_form_residual(c, m->XM, m->FM))) return rc;
+  // F goes up in z-chunks on a second stream; the per-point kernel of chunk k starts when chunk k has arrived, so the
+  // host-to-device copy (72 B/cell over PCIe) hides behind the constitutive update of the chunks before it
+  static const int chunks_setting = [] { const char* e = getenv("DMK_STAGE_CHUNKS"); int v = e ? atoi(e) : 8; return v < 1 ? 1 : (v > 8 ? 8 : v); }();
+  const int chunks = (c->nz_loc >= chunks_setting) ? chunks_setting : 1;
+  if (chunks > 1) {
+    if (!c->stage_ready) {
+      DMK_CUDA_CHECK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+      for (int k = 0; k < 8; k++) DMK_CUDA_CHECK(cudaEventCreateWithFlags(&c->stage_ev[k], cudaEventDisableTiming));
+      DMK_CUDA_CHECK(cudaEventCreateWithFlags(&c->stage_begin, cudaEventDisableTiming));
+      c->stage_ready = true;
+    }
+    DMK_CUDA_CHECK(cudaEventRecord(c->stage_begin, c->stream));             // XM may still be read by earlier work
+    DMK_CUDA_CHECK(cudaStreamWaitEvent(c->copy_stream, c->stage_begin, 0));
+    const long long plane9 = 9LL * c->nx * c->ny;
+    for (int k = 0; k < chunks; k++) {
+      const long long z0 = (long long)c->nz_loc * k / chunks, z1 = (long long)c->nz_loc * (k + 1) / chunks;
+      DMK_CUDA_CHECK(cudaMemcpyAsync(m->XM + z0 * plane9, F + z0 * plane9, (size_t)((z1 - z0) * plane9) * sizeof(double),
+                                     cudaMemcpyHostToDevice, c->copy_stream));
+      DMK_CUDA_CHECK(cudaEventRecord(c->stage_ev[k], c->copy_stream));
+    }
+    c->stage_chunks = chunks; c->stage_dst = m->XM;
+  } else {
+    DMK_CUDA_CHECK(cudaMemcpyAsync(m->XM, F, m->n9 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  }
+  rc = dmk_mech_form_residual(c, m->XM, m->FM);
+  if (chunks > 1) {
+    c->stage_chunks = 0; c->stage_dst = nullptr;
+  }
+  if (rc) return rc;
   DMK_CUDA_CHECK(cudaMemcpyAsync(r, m->FM, m->n9 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
   DMK_CUDA_CHECK(cudaStreamSynchronize(c->stream));
   return DMK_OK;

@@ -68,6 +68,7 @@ static int launch_pheno_fast(dmk_ctx* c, DmkPointArrays& pa, int ph, const DmkDe
     DMK_CUDA_CHECK(cudaFuncSetAttribute(dmk_pheno_fast_kernel<NSL, NEXP, UNR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set = true;
   }
+  { int rc = dmk_wait_staged_input(c, d_F); if (rc) return rc; }
   const long long blocks = (pa.n + DMK_PF_THREADS - 1) / DMK_PF_THREADS;
   const int grid = (int)std::max(1LL, std::min(blocks, (long long)INT32_MAX));
   DMK_CUDA_CHECK(cudaMemsetAsync(pa.d_defer_count, 0, sizeof(unsigned), c->stream));
@@ -88,7 +89,9 @@ static int launch_pheno_fast(dmk_ctx* c, DmkPointArrays& pa, int ph, const DmkDe
 template <int NSL, int NEXP, int UNR>
 __global__ void __launch_bounds__(DMK_PL_THREADS, DMK_PL_MINBLOCKS)
 dmk_pheno_lanes_kernel(const __grid_constant__ DmkPhenoK<NSL> K, DmkPointArrays pa, int phase, DmkNumDev num,
-                       const double* __restrict__ Fin, double* __restrict__ Pout, double step, double dt) {
+                       const double* __restrict__ Fin, double* __restrict__ Pout, double step, double dt, long long cell_begin,
+                       long long cell_end) {
+  // cells [cell_begin, cell_end) are this launch's share (whole slab, or one staged z-chunk); *pa.d_work counts from 0
   extern __shared__ double pf_sm[];
   const DmkScr scr = {pf_sm + threadIdx.x, DMK_PL_THREADS};
   const unsigned FULL = 0xffffffffu, lane = threadIdx.x & 31u, lt = (1u << lane) - 1u;
@@ -124,10 +127,10 @@ dmk_pheno_lanes_kernel(const __grid_constant__ DmkPhenoK<NSL> K, DmkPointArrays 
       if (c_next >= c_end) {
         unsigned long long base = 0;
         if (lane == 0) base = atomicAdd(pa.d_work, (unsigned long long)DMK_PL_CHUNK);
-        base = __shfl_sync(FULL, base, 0);
-        if ((long long)base >= pa.n) { drained = true; break; }
+        base = __shfl_sync(FULL, base, 0) + (unsigned long long)cell_begin;
+        if ((long long)base >= cell_end) { drained = true; break; }
         c_next = (long long)base;
-        c_end = min(c_next + DMK_PL_CHUNK, pa.n);
+        c_end = min(c_next + DMK_PL_CHUNK, cell_end);
       }
       const int avail = (int)min(32LL, c_end - c_next);
       const int rank = __popc(need & lt);
@@ -190,11 +193,21 @@ static int launch_pheno_lanes(dmk_ctx* c, DmkPointArrays& pa, int ph, const DmkD
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, dmk_pheno_lanes_kernel<NSL, NEXP, UNR>, DMK_PL_THREADS, smem) != cudaSuccess || occ < 1) occ = 1;
     grid = sms * occ;                                  // one resident wave
   }
-  const long long warps_needed = (pa.n + 31) / 32;
-  const int g = (int)std::max(1LL, std::min((long long)grid, (warps_needed + 1) / 2));
   DMK_CUDA_CHECK(cudaMemsetAsync(pa.d_defer_count, 0, sizeof(unsigned), c->stream));
-  DMK_CUDA_CHECK(cudaMemsetAsync(pa.d_work, 0, sizeof(unsigned long long), c->stream));
-  dmk_pheno_lanes_kernel<NSL, NEXP, UNR><<<g, DMK_PL_THREADS, smem, c->stream>>>(K, pa, ph, nd, d_F, d_P, step, step * dt);
+  // one launch over the slab, or one per staged z-chunk of F, each behind the event of its host-to-device copy
+  const int chunks = (c->stage_chunks > 1 && d_F == c->stage_dst) ? c->stage_chunks : 1;
+  const long long plane = (long long)c->nx * c->ny;
+  for (int k = 0; k < chunks; k++) {
+    const long long z0 = (long long)c->nz_loc * k / chunks, z1 = (long long)c->nz_loc * (k + 1) / chunks;
+    const long long first = z0 * plane, end = z1 * plane;
+    if (end <= first) continue;
+    if (chunks > 1) DMK_CUDA_CHECK(cudaStreamWaitEvent(c->stream, c->stage_ev[k], 0));
+    DMK_CUDA_CHECK(cudaMemsetAsync(pa.d_work, 0, sizeof(unsigned long long), c->stream));
+    const long long warps_needed = (end - first + 31) / 32;
+    const int g = (int)std::max(1LL, std::min((long long)grid, (warps_needed + 1) / 2));
+    dmk_pheno_lanes_kernel<NSL, NEXP, UNR><<<g, DMK_PL_THREADS, smem, c->stream>>>(K, pa, ph, nd, d_F, d_P, step, step * dt, first, end);
+    if (k > 0) c->launches++;
+  }
   return DMK_OK;
 }
 

@@ -139,6 +139,7 @@ extern "C" void dmk_destroy(dmk_ctx* c) {
   if (c->m_F0) cudaFreeHost(c->m_F0); if (c->m_F) cudaFreeHost(c->m_F); if (c->m_P) cudaFreeHost(c->m_P);
   if (c->m_dPdF) cudaFreeHost(c->m_dPdF); if (c->m_ill) cudaFreeHost(c->m_ill);
   if (c->ev[0]) for (int i = 0; i < 8; i++) cudaEventDestroy(c->ev[i]);
+  if (c->stage_ready) { for (int k = 0; k < 8; k++) cudaEventDestroy(c->stage_ev[k]); cudaEventDestroy(c->stage_begin); cudaStreamDestroy(c->copy_stream); }
   if (c->own_stream) cudaStreamDestroy(c->stream);
   delete c;
 }
