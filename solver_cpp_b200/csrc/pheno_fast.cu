@@ -3,6 +3,7 @@
 #include <algorithm>
 #include <cstdint>
 #include <cstdlib>
+#include <cstdio>
 #include <string>
 #include "pheno_fast_dev.cuh"
 #include "pheno_lanes_dev.cuh"
@@ -86,11 +87,11 @@ static int launch_pheno_fast(dmk_ctx* c, DmkPointArrays& pa, int ph, const DmkDe
 #define DMK_PL_MINBLOCKS 4
 #endif
 #define DMK_PL_CHUNK 256
-template <int NSL, int NEXP, int UNR>
+template <int NSL, int NEXP, int UNR, bool VOTE3>
 __global__ void __launch_bounds__(DMK_PL_THREADS, DMK_PL_MINBLOCKS)
 dmk_pheno_lanes_kernel(const __grid_constant__ DmkPhenoK<NSL> K, DmkPointArrays pa, int phase, DmkNumDev num,
                        const double* __restrict__ Fin, double* __restrict__ Pout, double step, double dt, long long cell_begin,
-                       long long cell_end) {
+                       long long cell_end, int3 vw) {
   // cells [cell_begin, cell_end) are this launch's share (whole slab, or one staged z-chunk); *pa.d_work counts from 0
   extern __shared__ double pf_sm[];
   const DmkScr scr = {pf_sm + threadIdx.x, DMK_PL_THREADS};
@@ -108,10 +109,34 @@ dmk_pheno_lanes_kernel(const __grid_constant__ DmkPhenoK<NSL> K, DmkPointArrays 
     // block and the refill were executed for the few lanes that needed them at that moment.  Waiting lanes accumulate
     // until they are the majority, go through their block together and then iterate in step.
     const unsigned bL = __ballot_sync(FULL, L.mode == PL_LP);
+    const unsigned bN = VOTE3 ? __ballot_sync(FULL, L.mode == PL_NEWTON) : 0u;
     const unsigned bS = __ballot_sync(FULL, L.mode == PL_INIT || L.mode == PL_CONV);
     unsigned need = drained ? 0u : __ballot_sync(FULL, L.mode == PL_NEED);
-    if (!(bL | bS | need)) break;
-    if (__popc(bL) >= __popc(bS) + __popc(need)) {
+    if (!(bL | bN | bS | need)) break;
+    if constexpr (VOTE3) {
+      // three-way vote: the Newton step runs only for the lanes whose residual test failed (2/3 of the Newton lanes), so
+      // it is a block of its own in which such lanes accumulate
+      const int cL = vw.x * __popc(bL), cN = vw.y * __popc(bN), cS = vw.z * (__popc(bS) + __popc(need));
+      if (cN >= cL && cN >= cS) {
+        t_lp++; l_lp += __popc(bN);
+        if (L.mode == PL_NEWTON) {
+          const int rc = pl_newton<NSL, UNR>(K, dt, scr, L);
+          if (rc == PL_DEFER) { pa.defer_list[atomicAdd(pa.d_defer_count, 1u)] = (int)L.i; n_defer++; L.mode = PL_NEED; }
+          else L.mode = PL_LP;
+        }
+        continue;
+      }
+      if (cL >= cS) {
+        t_lp++; l_lp += __popc(bL);
+        if (L.mode == PL_LP) {
+          const int rc = pl_residual<NSL, NEXP, UNR>(K, num, dt, scr, L);
+          if (rc == PL_DONE) L.mode = PL_CONV;
+          else if (rc == PL_STEP) L.mode = PL_NEWTON;
+          else if (rc == PL_DEFER) { pa.defer_list[atomicAdd(pa.d_defer_count, 1u)] = (int)L.i; n_defer++; L.mode = PL_NEED; }
+        }
+        continue;
+      }
+    } else if (__popc(bL) >= __popc(bS) + __popc(need)) {
       // ---- one Newton iteration
       t_lp++; l_lp += __popc(bL);
       if (L.mode == PL_LP) {
@@ -172,13 +197,27 @@ dmk_pheno_lanes_kernel(const __grid_constant__ DmkPhenoK<NSL> K, DmkPointArrays 
   }
 }
 
+// DMK_PHENO_VOTE=2: two-way vote (whole Newton iteration / state block) instead of the default three-way vote (residual /
+// Newton step / state block) in the lane-persistent kernel (128^3 solver iterate: 23.0 ms against 21.6 ms)
+static bool vote3_setting() {
+  static const bool v = [] { const char* e = getenv("DMK_PHENO_VOTE"); return !(e && atoi(e) == 2); }();
+  return v;
+}
+
+// DMK_PHENO_VOTE_WEIGHTS=l,n,s: integer weights of the lane counts in the three-way vote.  Default 4,4,3: the state block is
+// the longest of the three, letting it wait for a few more lanes pays (sweep in profiles/r01_summary.md)
+static int3 vote_weights() {
+  static const int3 v = [] { int3 w = make_int3(4, 4, 3); const char* e = getenv("DMK_PHENO_VOTE_WEIGHTS"); if (e) sscanf(e, "%d,%d,%d", &w.x, &w.y, &w.z); return w; }();
+  return v;
+}
+
 // DMK_PHENO_SCHEDULE=nested: one thread walks one point through the nested loops (dmk_pheno_fast_kernel); default: lanes
 static bool lanes_setting() {
   static const bool v = [] { const char* e = getenv("DMK_PHENO_SCHEDULE"); return !(e && std::string(e) == "nested"); }();
   return v;
 }
 
-template <int NSL, int NEXP, int UNR>
+template <int NSL, int NEXP, int UNR, bool VOTE3 = false>
 static int launch_pheno_lanes(dmk_ctx* c, DmkPointArrays& pa, int ph, const DmkDevPhase& d, const DmkNumDev& nd, const double* d_F,
                               double* d_P, double step, double dt) {
   DmkPhenoK<NSL> K;
@@ -186,11 +225,11 @@ static int launch_pheno_lanes(dmk_ctx* c, DmkPointArrays& pa, int ph, const DmkD
   const size_t smem = (size_t)PfOff<NSL>::TOTAL * DMK_PL_THREADS * sizeof(double);
   static int grid = 0;
   if (!grid) {
-    DMK_CUDA_CHECK(cudaFuncSetAttribute(dmk_pheno_lanes_kernel<NSL, NEXP, UNR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    DMK_CUDA_CHECK(cudaFuncSetAttribute(dmk_pheno_lanes_kernel<NSL, NEXP, UNR, VOTE3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int dev = 0, sms = 148, occ = 1;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, dmk_pheno_lanes_kernel<NSL, NEXP, UNR>, DMK_PL_THREADS, smem) != cudaSuccess || occ < 1) occ = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, dmk_pheno_lanes_kernel<NSL, NEXP, UNR, VOTE3>, DMK_PL_THREADS, smem) != cudaSuccess || occ < 1) occ = 1;
     grid = sms * occ;                                  // one resident wave
   }
   DMK_CUDA_CHECK(cudaMemsetAsync(pa.d_defer_count, 0, sizeof(unsigned), c->stream));
@@ -205,7 +244,7 @@ static int launch_pheno_lanes(dmk_ctx* c, DmkPointArrays& pa, int ph, const DmkD
     DMK_CUDA_CHECK(cudaMemsetAsync(pa.d_work, 0, sizeof(unsigned long long), c->stream));
     const long long warps_needed = (end - first + 31) / 32;
     const int g = (int)std::max(1LL, std::min((long long)grid, (warps_needed + 1) / 2));
-    dmk_pheno_lanes_kernel<NSL, NEXP, UNR><<<g, DMK_PL_THREADS, smem, c->stream>>>(K, pa, ph, nd, d_F, d_P, step, step * dt, first, end);
+    dmk_pheno_lanes_kernel<NSL, NEXP, UNR, VOTE3><<<g, DMK_PL_THREADS, smem, c->stream>>>(K, pa, ph, nd, d_F, d_P, step, step * dt, first, end, vote_weights());
     if (k > 0) c->launches++;
   }
   return DMK_OK;
@@ -226,6 +265,8 @@ int dmk_points_pheno_fast(dmk_ctx* c, int ph, const DmkNumDev& nd, const double*
   if (lanes_setting() && dmk_pheno_lanes_eligible(nd, &step)) {
     *deferred = true;
 #define DMK_PL_LAUNCH(NEXP_)                                                                                   \
+  (vote3_setting() && u == 2) ? launch_pheno_lanes<12, NEXP_, 2, true>(c, pa, ph, d, nd, d_F, d_P, step, dt)  \
+  :                                                                                                            \
   (u == 2)    ? launch_pheno_lanes<12, NEXP_, 2>(c, pa, ph, d, nd, d_F, d_P, step, dt)                         \
   : (u == 3)  ? launch_pheno_lanes<12, NEXP_, 3>(c, pa, ph, d, nd, d_F, d_P, step, dt)                         \
   : (u == 4)  ? launch_pheno_lanes<12, NEXP_, 4>(c, pa, ph, d, nd, d_F, d_P, step, dt)                         \

@@ -30,6 +30,7 @@
 #define PL_INIT 1        // point loaded: state predictor pending
 #define PL_LP 2          // inside an Lp Newton loop
 #define PL_CONV 3        // Newton loop converged: Fp, P, state corrector pending
+#define PL_NEWTON 5      // residual accepted: Newton step pending (three-way vote only)
 #define PL_EXIT 4        // no work left
 
 #define PL_CONTINUE 0
@@ -89,11 +90,13 @@ DMK_HD __forceinline__ bool pl_begin(const DmkPointArrays& pa, long long i, cons
   return true;
 }
 
-// One trip of integrateStress' Lp loop (pf_stress): residual at L.Lp, then accept + Newton step, or shorten the last
-// step (line search).  PL_DONE: converged at the current L.Lp.  The state block sets nLp = 0, step = 1 before a loop.
+// integrateStress' Lp loop (pf_stress), one trip = pl_residual [+ pl_newton].
+// pl_residual: residual at L.Lp and the loop's decisions.  PL_DONE: converged at the current L.Lp; PL_CONTINUE: the last
+// step was shortened (line search), evaluate the residual again; PL_STEP: iterate accepted, L.delta holds the residual
+// and a Newton step is due (pl_newton).  The state block sets nLp = 0, step = 1 before a loop.
+#define PL_STEP 3
 template <int NSL, int NEXP, int UNR>
-DMK_HD __forceinline__ int pl_lp_iteration(const DmkPhenoK<NSL>& K, const DmkNumDev& num, double dt, const DmkScr& scr,
-                                           PlLane<NSL>& L) {
+DMK_HD __forceinline__ int pl_residual(const DmkPhenoK<NSL>& K, const DmkNumDev& num, double dt, const DmkScr& scr, PlLane<NSL>& L) {
   typedef PfOff<NSL> O;
   L.nLp++;
   if (L.nLp > num.N_iter_Lp_max) return PL_DEFER;
@@ -122,18 +125,34 @@ DMK_HD __forceinline__ int pl_lp_iteration(const DmkPhenoK<NSL>& K, const DmkNum
   if (L.nLp == 1 || rn < L.res_old) {
     L.res_old = rn;
 #pragma unroll
-    for (int a = 0; a < 9; a++) scr(O::LOLD + a) = L.Lp[a];
+    for (int a = 0; a < 9; a++) { scr(O::LOLD + a) = L.Lp[a]; L.delta[a] = res[a]; }   // the old step is dead: delta carries the residual
     L.step = 1.0;
-  } else {
-    L.step = num.r_linesearch_Lp * L.step;
-#pragma unroll
-    for (int a = 0; a < 9; a++) L.Lp[a] = scr(O::LOLD + a) + L.delta[a] * L.step;
-    return PL_CONTINUE;
+    return PL_STEP;
   }
+  L.step = num.r_linesearch_Lp * L.step;
+#pragma unroll
+  for (int a = 0; a < 9; a++) L.Lp[a] = scr(O::LOLD + a) + L.delta[a] * L.step;
+  return PL_CONTINUE;
+}
+
+// Newton step from the accepted iterate L.Lp with residual L.delta: delta <- -(dR/dLp)^-1 R, Lp += delta.
+template <int NSL, int UNR>
+DMK_HD __forceinline__ int pl_newton(const DmkPhenoK<NSL>& K, double dt, const DmkScr& scr, PlLane<NSL>& L) {
+  double B[9], Fe[9], res[9];
+#pragma unroll
+  for (int a = 0; a < 9; a++) { B[a] = ((a % 4 == 0) ? 1.0 : 0.0) - dt * L.Lp[a]; res[a] = L.delta[a]; }
+  mm3(L.A, B, Fe);
   if (pf_newton_step<NSL, UNR>(K, L.A, Fe, scr, res)) return PL_DEFER;
 #pragma unroll
   for (int a = 0; a < 9; a++) { L.delta[a] = -res[a]; L.Lp[a] += L.delta[a] * L.step; }
   return PL_CONTINUE;
+}
+
+template <int NSL, int NEXP, int UNR>
+DMK_HD __forceinline__ int pl_lp_iteration(const DmkPhenoK<NSL>& K, const DmkNumDev& num, double dt, const DmkScr& scr,
+                                           PlLane<NSL>& L) {
+  const int rc = pl_residual<NSL, NEXP, UNR>(K, num, dt, scr, L);
+  return rc == PL_STEP ? pl_newton<NSL, UNR>(K, dt, scr, L) : rc;
 }
 
 // State block of integrateStateFPI.  init: predictor (state = state0 + dotState(S0) dt).  Else: S of the stress
