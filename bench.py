@@ -337,8 +337,7 @@ def run_ours(args):
 
 
 def main():
-    if os.environ.get('NCCL_DEBUG', '').upper() == 'VERSION':       # NCCL prints its version banner to STDOUT, where the one JSON line goes
-        os.environ['NCCL_DEBUG'] = 'WARN'
+    os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')        # NCCL's banner / warnings go to STDOUT by default, where the one JSON line goes
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=5)

@@ -168,6 +168,10 @@ int dmk_update_gamma(dmk_ctx* ctx, const double* C /* host, 81 */);/* MechBase::
 /* calculate_divergence_rms + gamma_convolution fused (mech_base.cpp:302-477): d_field in: stress, out: Gamma*field;
  * field_aim host 3x3 (already rotated to lab); err_div returned on the host */
 int dmk_divergence_and_gamma(dmk_ctx* ctx, double* d_field, const double* field_aim, double* err_div);
+/* MechBase::base_update_coords (mech_base.cpp:45-154): deformed node and cell-centre coordinates of the local slab from F
+ * (device field).  Host outputs x_n[nz_loc+1][ny+1][nx+1][3] and x_p[nz_loc][ny][nx][3] (= the reference's x_n(3,i,j,k),
+ * x_p(3,i,j,k), first index fastest). */
+int dmk_update_coords(dmk_ctx* ctx, const double* d_F, double* h_x_n, double* h_x_p);
 int dmk_masked_compliance(const double* C /*81*/, const double* R /*9 row-major*/, const int* stress_mask /*9, 1='x'*/,
                           double* S /*81*/);                        /* MechBase::calculate_masked_compliance */
 int dmk_forward_field(dmk_ctx* ctx, double dt, const double* d_field_last, const double* d_rate, const double* aim,

@@ -365,3 +365,130 @@ extern "C" int dmk_calculate_rate(dmk_ctx* c, int heterogeneous, const double* d
   DMK_CUDA_CHECK(cudaGetLastError());
   return DMK_OK;
 }
+
+// ------------------------------------------------------------------------------------------------ update_coords
+// MechBase::base_update_coords (/root/reference/src/grid/mech_base.cpp:45-154) with upstream DAMASK's arithmetic
+// (utilities_updateCoords), which the real DAMASK result file of golden set G4 confirms to rounding (oracle/spectral.py
+// update_coords): the C++ port negates the Fourier-space denominator and applies wgt twice; neither is followed.
+//   u_hat(k) = F_hat(k) . xi2nd(k) / sum_l conj(-xi2nd_l) xi2nd_l  (k != 0),  xi2nd = i 2 pi k_s / size (continuous, no Nyquist zeroing)
+// The 3-vector rides in components 0..2 of the 9-component record (the vector FFT<4> of the reference), once per increment.
+__global__ void dmk_coords_integrate_kernel(double2* __restrict__ hat, int nxr, int ny_loc, int nz, int ny, int y_off,
+                                            double fx, double fy, double fz) {
+  const long long n = (long long)nz * ny_loc * nxr;
+  for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += (long long)gridDim.x * blockDim.x) {
+    const int kx = (int)(r % nxr);
+    const int kyl = (int)((r / nxr) % ny_loc);
+    const int kz = (int)(r / ((long long)nxr * ny_loc));
+    const int ky = kyl + y_off;
+    const double q[3] = {fx * kx, fy * (ky > ny / 2 ? ky - ny : ky), fz * (kz > nz / 2 ? kz - nz : kz)};   // xi2nd = i q
+    double2* t = hat + r * DMK_NC;
+    double2 u[3];
+    const double den = -(q[0] * q[0] + q[1] * q[1] + q[2] * q[2]);        // sum conj(-i q)(i q) = -|q|^2
+    if (kx == 0 && ky == 0 && kz == 0) { u[0] = u[1] = u[2] = make_double2(0.0, 0.0); }
+    else {
+      const double rd = 1.0 / den;
+#pragma unroll
+      for (int l = 0; l < 3; l++) {
+        // (F_hat . i q)_l = i sum_m F_hat(l,m) q_m ; record component of F(l,m) is l + 3 m
+        const double re = t[l].x * q[0] + t[l + 3].x * q[1] + t[l + 6].x * q[2];
+        const double im = t[l].y * q[0] + t[l + 3].y * q[1] + t[l + 6].y * q[2];
+        u[l] = make_double2(-im * rd, re * rd);
+      }
+    }
+#pragma unroll
+    for (int cidx = 0; cidx < DMK_NC; cidx++) t[cidx] = (cidx < 3) ? u[cidx] : make_double2(0.0, 0.0);
+  }
+}
+
+// layers [ny][nx][3] of the cell-centre fluctuation: k = 0 -> lo_out, k = nz_loc - 1 -> hi_out
+__global__ void dmk_coords_layers_kernel(const double* __restrict__ field, int nx, int ny, int nz_loc, double* __restrict__ lo_out,
+                                         double* __restrict__ hi_out) {
+  const long long n = (long long)nx * ny;
+  for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += (long long)gridDim.x * blockDim.x)
+    for (int p = 0; p < 3; p++) {
+      lo_out[r * 3 + p] = field[r * DMK_NC + p];
+      hi_out[r * 3 + p] = field[((long long)(nz_loc - 1) * n + r) * DMK_NC + p];
+    }
+}
+
+// x_n [nz_loc+1][ny+1][nx+1][3], x_p [nz_loc][ny][nx][3]; below / above: the neighbouring slabs' top / bottom layer
+__global__ void dmk_coords_assemble_kernel(const double* __restrict__ field, const double* __restrict__ below,
+                                           const double* __restrict__ above, const double* __restrict__ Fsum9, double wgt, int nx,
+                                           int ny, int nz_loc, int z_off, double sx, double sy, double sz, double* __restrict__ x_n,
+                                           double* __restrict__ x_p) {
+  double Fav[9];                                   // row-major (l, m); record component l + 3 m
+  for (int l = 0; l < 3; l++) for (int m = 0; m < 3; m++) Fav[3 * l + m] = Fsum9[l + 3 * m] * wgt;
+  const long long nn = (long long)(nx + 1) * (ny + 1) * (nz_loc + 1);
+  const long long plane = (long long)nx * ny;
+  for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < nn; r += (long long)gridDim.x * blockDim.x) {
+    const int i = (int)(r % (nx + 1)), j = (int)((r / (nx + 1)) % (ny + 1)), k = (int)(r / ((long long)(nx + 1) * (ny + 1)));
+    const double X[3] = {i * sx, j * sy, (k + z_off) * sz};
+    double acc[3] = {0.0, 0.0, 0.0};
+    for (int dz = -1; dz <= 0; dz++) for (int dy = -1; dy <= 0; dy++) for (int dx = -1; dx <= 0; dx++) {
+      const int ci = (i + dx + nx) % nx, cj = (j + dy + ny) % ny, ck = k + dz;
+      const double* src;
+      if (ck < 0) src = below + ((long long)cj * nx + ci) * 3;
+      else if (ck >= nz_loc) src = above + ((long long)cj * nx + ci) * 3;
+      else src = nullptr;
+      for (int p = 0; p < 3; p++) acc[p] += src ? src[p] : field[(ck * plane + (long long)cj * nx + ci) * DMK_NC + p];
+    }
+    for (int p = 0; p < 3; p++) x_n[r * 3 + p] = Fav[3 * p] * X[0] + Fav[3 * p + 1] * X[1] + Fav[3 * p + 2] * X[2] + 0.125 * acc[p];
+    if (i < nx && j < ny && k < nz_loc) {
+      const double Xc[3] = {(i + 0.5) * sx, (j + 0.5) * sy, (k + 0.5 + z_off) * sz};
+      const long long cell = k * plane + (long long)j * nx + i;
+      for (int p = 0; p < 3; p++)
+        x_p[cell * 3 + p] = Fav[3 * p] * Xc[0] + Fav[3 * p + 1] * Xc[1] + Fav[3 * p + 2] * Xc[2] + field[cell * DMK_NC + p];
+    }
+  }
+}
+
+extern "C" int dmk_update_coords(dmk_ctx* c, const double* d_F, double* h_x_n, double* h_x_p) {
+  if (!c || !d_F || !h_x_n || !h_x_p) { dmk_set_error("null argument"); return DMK_ERR_ARG; }
+  const double PI2 = 6.283185307179586476925286766559;
+  int rc;
+  // average F (all ranks)
+  double* d_sum = c->d_scratch + DMK_SCRATCH_SUM9;
+  if ((rc = dmk_sum_records(c, d_F, c->n_local, d_sum))) return rc;
+  if (c->P > 1) { if (c->comm.allreduce_sum(c->comm.user, d_sum, 9)) { dmk_set_error("allreduce failed"); return DMK_ERR_STATE; } }
+  // F_hat -> u_hat -> u_tilde (components 0..2 of a scratch field)
+  if ((rc = dmk_fft_forward_internal(c, d_F))) return rc;
+  if ((rc = zpass_plain(c, false))) return rc;
+  dmk_coords_integrate_kernel<<<148 * 8, 256, 0, c->stream>>>(c->bufA, c->nxr, c->ny_loc, c->nz, c->ny, c->y_off, PI2 / c->g.size[0],
+                                                               PI2 / c->g.size[1], PI2 / c->g.size[2]);
+  c->launches++;
+  if ((rc = zpass_plain(c, true))) return rc;
+  double* d_u = nullptr;
+  const size_t plane3 = (size_t)c->nx * c->ny * 3;
+  const size_t n_nodes = (size_t)(c->nx + 1) * (c->ny + 1) * (c->nz_loc + 1);
+  DMK_CUDA_CHECK(cudaMalloc((void**)&d_u, ((size_t)c->n_local * DMK_NC + (2 + 2 * (size_t)c->P) * 2 * plane3 + n_nodes * 3 + (size_t)c->n_local * 3) * sizeof(double)));
+  double* d_send = d_u + (size_t)c->n_local * DMK_NC;          // [peer][2][plane3]
+  double* d_recv = d_send + (size_t)c->P * 2 * plane3;
+  double* d_lo = d_recv + (size_t)c->P * 2 * plane3;           // my bottom / top layer
+  double* d_hi = d_lo + plane3;
+  double* d_xn = d_hi + plane3 + 2 * plane3;
+  double* d_xp = d_xn + n_nodes * 3;
+  auto fail = [&](int code) { cudaFree(d_u); return code; };
+  if ((rc = dmk_fft_backward_internal(c, d_u, c->wgt))) return fail(rc);
+  dmk_coords_layers_kernel<<<148, 256, 0, c->stream>>>(d_u, c->nx, c->ny, c->nz_loc, d_lo, d_hi);
+  c->launches++;
+  const double *below = d_hi, *above = d_lo;                   // one rank: periodic in z
+  if (c->P > 1) {
+    // halo exchange through the all-to-all callback: slot of the rank below gets my bottom layer (first half), slot of the
+    // rank above my top layer (second half); everything else is zero
+    const int rb = (c->rank - 1 + c->P) % c->P, rt = (c->rank + 1) % c->P;
+    if (cudaMemsetAsync(d_send, 0, (size_t)c->P * 2 * plane3 * sizeof(double), c->stream) != cudaSuccess) return fail(DMK_ERR_CUDA);
+    cudaMemcpyAsync(d_send + ((size_t)rb * 2 + 0) * plane3, d_lo, plane3 * sizeof(double), cudaMemcpyDeviceToDevice, c->stream);
+    cudaMemcpyAsync(d_send + ((size_t)rt * 2 + 1) * plane3, d_hi, plane3 * sizeof(double), cudaMemcpyDeviceToDevice, c->stream);
+    if (!c->has_comm || c->comm.alltoall(c->comm.user, d_send, d_recv, 2 * plane3 * sizeof(double))) { dmk_set_error("alltoall callback failed"); return fail(DMK_ERR_STATE); }
+    above = d_recv + ((size_t)rt * 2 + 0) * plane3;            // bottom layer of the rank above
+    below = d_recv + ((size_t)rb * 2 + 1) * plane3;            // top layer of the rank below
+  }
+  dmk_coords_assemble_kernel<<<148 * 8, 256, 0, c->stream>>>(d_u, below, above, d_sum, c->wgt, c->nx, c->ny, c->nz_loc, c->z_off,
+                                                              c->g.size[0] / c->nx, c->g.size[1] / c->ny, c->g.size[2] / c->nz, d_xn, d_xp);
+  c->launches++;
+  if (cudaMemcpyAsync(h_x_n, d_xn, n_nodes * 3 * sizeof(double), cudaMemcpyDeviceToHost, c->stream) != cudaSuccess ||
+      cudaMemcpyAsync(h_x_p, d_xp, (size_t)c->n_local * 3 * sizeof(double), cudaMemcpyDeviceToHost, c->stream) != cudaSuccess ||
+      cudaStreamSynchronize(c->stream) != cudaSuccess || cudaGetLastError() != cudaSuccess) { dmk_set_error("update_coords: CUDA error"); return fail(DMK_ERR_CUDA); }
+  cudaFree(d_u);
+  return DMK_OK;
+}

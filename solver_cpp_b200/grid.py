@@ -121,6 +121,14 @@ class GridContext:
         L.check(self.lib.dmk_divergence_and_gamma(self.ctx, _p(field), _hp(aim), C.byref(err)))
         return err.value
 
+    # ---- MechBase::base_update_coords (mech_base.cpp:45-154): deformed node / cell-centre coordinates of the local slab
+    def update_coords(self, F):
+        nx, ny, _ = self.cells
+        x_n = np.zeros((self.nz_local + 1, ny + 1, nx + 1, 3))
+        x_p = np.zeros((self.nz_local, ny, nx, 3))
+        L.check(self.lib.dmk_update_coords(self.ctx, _p(F), _hp(x_n), _hp(x_p)))
+        return x_n, x_p
+
     # ---- MechBase::forward_field / calculate_rate (mech_base.cpp:213-247, 479-497)
     def forward_field(self, dt, field_last, rate, aim_natural=None):
         out = self.new_field()

@@ -107,6 +107,10 @@ class MechSolverBasic:
         L.check(self.lib.dmk_mech_form_residual_host(self.ctx, _hp(F_host), _hp(r_host)))
         return r_host
 
+    def update_coords(self):
+        """MechSolverBasic::update_coords (mech_solver_basic.cpp:222-240): node and cell-centre coordinates of the current F"""
+        return self.g.update_coords(self.field('F'))
+
     def prepare_evaluation(self):
         """the pre-SNES part of calculate_solution (tangent reductions, masked compliance)"""
         L.check(self.lib.dmk_mech_prepare(self.ctx))

@@ -24,6 +24,8 @@ def main():
     out = {'increments': np.array(incs)}
     for name in ('F', 'P'):
         out[name] = np.stack([f.read('/increment_%d/phase/pheno_fcc/mechanical/%s' % (i, name)) for i in incs])
+    for name in ('u_p', 'u_n'):                               # cell-centre / nodal displacements (update_coords)
+        out[name] = np.stack([f.read('/increment_%d/geometry/%s' % (i, name)) for i in incs])
     out['xi_sl_final'] = f.read('/increment_40/phase/pheno_fcc/mechanical/xi_sl')
     np.savez_compressed(os.path.join(HERE, 'g4_damask_run.npz'), **out)
     print({k: v.shape for k, v in out.items()})

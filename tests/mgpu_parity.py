@@ -66,8 +66,14 @@ def main():
     eF = np.abs(F - F1).max()
     sel = tuple(int(v) for v in s.get('minmax_cells', 2)), tuple(int(v) for v in s1.get('minmax_cells', 2))
     ok &= it == it1 and eP < 1e-9 and eF < 1e-10 and sel[0] == sel[1]
+    # ---- update_coords: slab (halo layers through the all-to-all callback) vs whole grid
+    x_n, x_p = s.update_coords()
+    x_n1, x_p1 = s1.update_coords()
+    eX = max(np.abs(x_p - x_p1[z0:z1]).max(), np.abs(x_n - x_n1[z0:z1 + 1]).max()) / max(size)
+    ok &= eX < 1e-12
     if rank == 0:
         print('solver: iterations %s vs %s, P_av rel %.2e, F abs %.2e, minmax cells %s vs %s' % (it, it1, eP, eF, sel[0], sel[1]))
+        print('update_coords: rel err %.2e' % eX)
     t = torch.tensor([1.0 if ok else 0.0], device='cuda')
     dist.all_reduce(t, op=dist.ReduceOp.MIN)
     if rank == 0:

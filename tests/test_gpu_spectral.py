@@ -116,3 +116,33 @@ def test_g3_divergence_rms_unit_test_literal(golden_dir):
     field = np.ascontiguousarray(np.transpose(g3['div_field'], (4, 3, 2, 0, 1)))
     rms = g.divergence_and_gamma(g.to_device(field), np.zeros((3, 3)))
     assert abs(rms - float(g3['div_rms'])) <= 1e-12 * float(g3['div_rms'])
+
+
+@pytest.mark.parametrize('cells,size', [((6, 7, 8), (0.75, 0.875, 1.0)), ((16, 16, 16), (1e-5,) * 3), ((5, 1, 1), (5e-5, 1e-5, 1e-5)),
+                                        ((32, 16, 48), (2e-5, 1e-5, 3e-5))])
+def test_update_coords_matches_oracle(cells, size):
+    """MechBase::base_update_coords: Fourier-space integration of F, nodal averaging (oracle pinned by the displacements of
+    a real DAMASK result file, tests/test_oracle_golden.py)."""
+    rng = np.random.default_rng(4)
+    nx, ny, nz = cells
+    F = np.eye(3) + 1e-2 * rng.standard_normal((nz, ny, nx, 3, 3))
+    grid = osp.Grid(cells, size)
+    x_n_o, x_p_o = osp.update_coords(F, grid)
+    g = _ctx(cells, size)
+    x_n, x_p = g.update_coords(g.to_device(F))
+    scale = max(size)
+    assert np.abs(x_p - x_p_o).max() < 1e-13 * scale
+    assert np.abs(x_n - x_n_o).max() < 1e-13 * scale
+
+
+def test_g4_displacements_of_the_real_damask_run(golden_dir):
+    """cell-centre and nodal displacements u_p, u_n stored by DAMASK itself (golden set G4) from the stored F"""
+    import os
+    g4 = np.load(os.path.join(golden_dir, 'g4_damask_run.npz'))
+    cells, size = (6, 7, 8), (0.75, 0.875, 1.0)
+    g = _ctx(cells, size)
+    x_n0, x_p0 = g.update_coords(g.to_device(np.broadcast_to(np.eye(3), (8, 7, 6, 3, 3)).copy()))
+    for k in range(len(g4['increments'])):
+        x_n, x_p = g.update_coords(g.to_device(g4['F'][k].reshape(8, 7, 6, 3, 3)))
+        assert np.abs((x_p - x_p0).reshape(-1, 3) - g4['u_p'][k]).max() < 1e-14
+        assert np.abs((x_n - x_n0).reshape(-1, 3) - g4['u_n'][k]).max() < 1e-14
