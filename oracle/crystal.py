@@ -116,11 +116,29 @@ CF_SLIP_TWIN = np.vstack([_tab("""
 CF_SLIP_TRANS = CF_SLIP_TWIN.copy()
 CF_TWIN_SLIP = np.ones((12, 18), dtype=int)
 
+# cI slip-slip interaction types (Madec & Kubin 2017 labelling, crystal.f90:648-701), <111>{110} family only (the first 12 of
+# the 48 systems); 0 = not offered here (the {112} and {123} families)
+CI_SLIP_SLIP = np.zeros((48, 48), dtype=int)
+CI_SLIP_SLIP[:12, :12] = _tab("""
+ 1  3  6  6  7  5  4  2  4  2  7  5
+ 3  1  6  6  4  2  7  5  7  5  4  2
+ 6  6  1  3  5  7  2  4  5  7  2  4
+ 6  6  3  1  2  4  5  7  2  4  5  7
+ 7  5  4  2  1  3  6  6  2  4  7  5
+ 4  2  7  5  3  1  6  6  5  7  4  2
+ 5  7  2  4  6  6  1  3  7  5  2  4
+ 2  4  5  7  6  6  3  1  4  2  5  7
+ 5  7  4  2  2  4  7  5  1  3  6  6
+ 2  4  7  5  5  7  4  2  3  1  6  6
+ 7  5  2  4  7  5  2  4  6  6  1  3
+ 4  2  5  7  4  2  5  7  6  6  3  1
+""", 12)
+
 _LATT = {
     'cF': dict(nslip=CF_NSLIP, slip=CF_SLIP, ntwin=CF_NTWIN, twin=CF_TWIN, ntrans=[12],
                slip_slip=CF_SLIP_SLIP, twin_twin=CF_TWIN_TWIN, slip_twin=CF_SLIP_TWIN,
                twin_slip=CF_TWIN_SLIP, trans_trans=CF_TRANS_TRANS, slip_trans=CF_SLIP_TRANS),
-    'cI': dict(nslip=CI_NSLIP, slip=CI_SLIP, ntwin=CI_NTWIN, twin=CI_TWIN),
+    'cI': dict(nslip=CI_NSLIP, slip=CI_SLIP, ntwin=CI_NTWIN, twin=CI_TWIN, slip_slip=CI_SLIP_SLIP),
 }
 
 
@@ -197,6 +215,8 @@ def _interaction(react_used, act_used, react_max, act_max, values, table):
     r = _active_rows(react_used, react_max)
     a = _active_rows(act_used, act_max)
     types = table[np.ix_(r, a)]
+    if types.size and types.min() < 1:
+        raise NotImplementedError('interaction types of these system families are not offered')
     if types.size and types.max() > len(values):
         raise ValueError('not enough interaction values')
     return values[types - 1]

@@ -93,6 +93,21 @@ const Lattice& lattice_cI() {
       -1, 1, 1, 3, 1, 2,   1, 1, 1, -3, 1, 2,      1, 1, -1, 3, -1, 2,   1, -1, 1, 3, 1, -2,
       -1, 1, 1, 3, 2, 1,   1, 1, 1, -3, 2, 1,      1, 1, -1, 3, -2, 1,   1, -1, 1, 3, 2, -1});
   for (int i = 12; i < 24; i++) L.twin.push_back(L.slip[i]);
+  // slip-slip interaction types, <111>{110} family only (first 12 of the 48 systems; crystal.f90:648-701); 0 = not offered
+  static const int ss[12][12] = {
+      {1, 3, 6, 6, 7, 5, 4, 2, 4, 2, 7, 5},
+      {3, 1, 6, 6, 4, 2, 7, 5, 7, 5, 4, 2},
+      {6, 6, 1, 3, 5, 7, 2, 4, 5, 7, 2, 4},
+      {6, 6, 3, 1, 2, 4, 5, 7, 2, 4, 5, 7},
+      {7, 5, 4, 2, 1, 3, 6, 6, 2, 4, 7, 5},
+      {4, 2, 7, 5, 3, 1, 6, 6, 5, 7, 4, 2},
+      {5, 7, 2, 4, 6, 6, 1, 3, 7, 5, 2, 4},
+      {2, 4, 5, 7, 6, 6, 3, 1, 4, 2, 5, 7},
+      {5, 7, 4, 2, 2, 4, 7, 5, 1, 3, 6, 6},
+      {2, 4, 7, 5, 5, 7, 4, 2, 3, 1, 6, 6},
+      {7, 5, 2, 4, 7, 5, 2, 4, 6, 6, 1, 3},
+      {4, 2, 5, 7, 4, 2, 5, 7, 6, 6, 3, 1}};
+  for (int i = 0; i < 48; i++) { std::vector<int> r(48, 0); if (i < 12) for (int j = 0; j < 12; j++) r[j] = ss[i][j]; L.slip_slip.push_back(r); }
   static const int tt[12][12] = {
       {1, 3, 3, 3, 3, 3, 3, 2, 3, 3, 2, 3}, {3, 1, 3, 3, 3, 3, 2, 3, 3, 3, 3, 2}, {3, 3, 1, 3, 3, 2, 3, 3, 2, 3, 3, 3},
       {3, 3, 3, 1, 2, 3, 3, 3, 3, 2, 3, 3}, {3, 3, 3, 2, 1, 3, 3, 3, 3, 2, 3, 3}, {3, 3, 2, 3, 3, 1, 3, 3, 2, 3, 3, 3},
@@ -217,6 +232,7 @@ int dmk_crystal_interaction(const char* kind, const char* lattice, const int* N_
   for (size_t r = 0; r < ir.size(); r++)
     for (size_t a = 0; a < ia.size(); a++) {
       const int type = (*tab)[ir[r]][ia[a]];
+      if (type < 1) { dmk_set_error("%s interaction types of these system families of lattice %s are not offered", k.c_str(), lattice); return 3; }
       if (type > n_values) { dmk_set_error("%s interaction needs at least %d values, %d given", k.c_str(), type, n_values); return 2; }
       h[r * ia.size() + a] = values[type - 1];
     }

@@ -31,5 +31,29 @@ def main():
     print({k: v.shape for k, v in out.items()})
 
 
+def main_two_phase():
+    """12grains6x7x8_tensionY.hdf5: the same load case on a 12-grain microstructure with an fcc and a bcc phase"""
+    f = h5.H5File('/root/reference/python/tests/resources/Result/12grains6x7x8_tensionY.hdf5')
+    raw = f.read('/cell_to/phase').tobytes()
+    rec = len(raw) // 336
+    label = [raw[rec * i:rec * i + rec - 8].split(b'\0')[0].decode() for i in range(336)]
+    entry = np.array([int.from_bytes(raw[rec * i + rec - 8:rec * i + rec], 'little') for i in range(336)])
+    incs = [4, 20, 40]
+    out = {'increments': np.array(incs)}
+    for name in ('F', 'P'):
+        per_inc = []
+        for i in incs:
+            a = np.zeros((336, 3, 3))
+            for ph in sorted(set(label)):
+                d = f.read('/increment_%d/phase/%s/mechanical/%s' % (i, ph, name))
+                sel = np.array([l == ph for l in label])
+                a[sel] = d[entry[sel]]
+            per_inc.append(a)
+        out[name] = np.stack(per_inc)
+    np.savez_compressed(os.path.join(HERE, 'g4b_damask_run_two_phase.npz'), **out)
+    print({k: v.shape for k, v in out.items()}, sorted(set(label)))
+
+
 if __name__ == '__main__':
     main()
+    main_two_phase()

@@ -175,6 +175,33 @@ def test_g4_job_from_the_reference_input_files(golden_dir):
         assert np.abs(recs[int(inc) - 1]['P_av'] - Pd.mean(0)).max() < 3e-4 * np.abs(Pd.mean(0)).max()
 
 
+def test_g4b_two_phase_job_from_the_reference_input_files(golden_dir):
+    """fcc + bcc deck of the reference (12grains6x7x8): two phases, each through the lane-persistent kernel; the first
+    four increments against the free-running oracle (iterations identical, 1e-9) and the real DAMASK result at increment 4"""
+    from solver_cpp_b200 import job, mech
+    from solver_cpp_b200.vti import read_vti
+    g4 = np.load(os.path.join(golden_dir, 'g4b_damask_run_two_phase.npz'))
+    files = [os.path.join(golden_dir, f) for f in ('12grains6x7x8.vti', '12grains6x7x8.material.yaml', '6grains6x7x8_tensionY.load.yaml')]
+    s, steps = job.load_job(*files)
+    s.init()
+    recs = mech.loop_over_loadcase(s, steps, max_increments=4)
+    F = s.g.to_natural(s.field('F')).reshape(-1, 3, 3)
+    geo = read_vti(files[0])
+    o = MechSolverBasicOracle(tuple(int(c) for c in geo['cells']), tuple(geo['size']), yaml.safe_load(open(files[1])),
+                              geo['material'].reshape(-1))
+    o.init()
+    st = oparse(yaml.safe_load(open(files[2])))
+    st[0]['N'], st[0]['t'] = 4, st[0]['t'] * 4 / st[0]['N']
+    recs_o = run_loadcase(o, st)
+    assert [r['iterations'] for r in recs] == [r['iterations'] for r in recs_o]
+    for a, b in zip(recs, recs_o):
+        assert _rel(a['P_av'], b['P_av']) < 1e-9
+    assert int(g4['increments'][0]) == 4
+    Pd = g4['P'][0]
+    assert np.abs(F - g4['F'][0]).max() < 1e-5
+    assert np.abs(recs[3]['P_av'] - Pd.mean(0)).max() < 3e-4 * np.abs(Pd.mean(0)).max()
+
+
 def test_form_residual_host_roundtrip():
     """the reference-facing call with HOST buffers in the reference's memory order equals the device-pointer call"""
     from solver_cpp_b200 import mech, workloads as W

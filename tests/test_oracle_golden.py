@@ -186,3 +186,31 @@ def test_g4_update_coords_reproduces_damask_displacements(golden_dir):
         x_n, x_p = sp.update_coords(g4['F'][k].reshape(8, 7, 6, 3, 3), grid)
         assert np.abs((x_p - x_p0).reshape(-1, 3) - g4['u_p'][k]).max() < 1e-15
         assert np.abs((x_n - x_n0).reshape(-1, 3) - g4['u_n'][k]).max() < 1e-15
+
+
+def test_g4b_two_phase_real_damask_run_within_solver_tolerance(golden_dir):
+    """12grains6x7x8_tensionY.hdf5 of the reference: the same load case on a 12-grain microstructure with an fcc and a bcc
+    (cI, <111>{110}) phenopowerlaw phase -- pins the multi-phase path and the cI tables against a real DAMASK run."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location('dmk_vti', os.path.join(golden_dir, '..', '..', 'solver_cpp_b200', 'vti.py'))
+    vti = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(vti)
+    g4 = np.load(os.path.join(golden_dir, 'g4b_damask_run_two_phase.npz'))
+    geo = vti.read_vti(os.path.join(golden_dir, '12grains6x7x8.vti'))
+    mat = yaml.safe_load(open(os.path.join(golden_dir, '12grains6x7x8.material.yaml')))
+    load = yaml.safe_load(open(os.path.join(golden_dir, '6grains6x7x8_tensionY.load.yaml')))
+    o = MechSolverBasicOracle(tuple(int(c) for c in geo['cells']), tuple(geo['size']), mat, geo['material'].reshape(-1))
+    o.init()
+    snap = {}
+
+    def cb(rec, s):
+        if rec['inc'] in g4['increments']:
+            snap[rec['inc']] = (s.F.reshape(-1, 3, 3).copy(), s.con.a['P'].reshape(-1, 3, 3).copy())
+    recs = run_loadcase(o, parse_load(load), callback=cb)
+    assert len(recs) == 40 and all(r['converged'] for r in recs)
+    for k, inc in enumerate(g4['increments']):
+        F, P = snap[int(inc)]
+        Pd = g4['P'][k]
+        assert np.abs(F - g4['F'][k]).max() < 1e-5
+        assert np.abs(P - Pd).max() < 6e-4 * np.abs(Pd).max()
+        assert np.abs(P.mean(0) - Pd.mean(0)).max() < 3e-4 * np.abs(Pd.mean(0)).max()
