@@ -168,6 +168,13 @@ int dmk_update_gamma(dmk_ctx* ctx, const double* C /* host, 81 */);/* MechBase::
 /* calculate_divergence_rms + gamma_convolution fused (mech_base.cpp:302-477): d_field in: stress, out: Gamma*field;
  * field_aim host 3x3 (already rotated to lab); err_div returned on the host */
 int dmk_divergence_and_gamma(dmk_ctx* ctx, double* d_field, const double* field_aim, double* err_div);
+/* Fused exchange of the distributed FFT over peer memory (NVLink / NVSwitch): each rank exports the CUDA IPC handles of its
+ * two spectral buffers (128 bytes), the host side all-gathers them, dmk_p2p_import opens the peers' buffers.  From then on
+ * the y pass stores its tiles straight into the owning peer's z-pass buffer and the (Gamma-fused) inverse z pass stores
+ * straight into the owning peer's y-pass buffer; the all-to-all callback is no longer used, two 1-double all-reduces order
+ * the stores.  *enabled = 0: the grid does not qualify (line lengths), the all-to-all path stays. */
+int dmk_p2p_export(dmk_ctx* ctx, unsigned char* handles128);
+int dmk_p2p_import(dmk_ctx* ctx, const unsigned char* all_handles, int* enabled);
 /* MechBase::base_update_coords (mech_base.cpp:45-154): deformed node and cell-centre coordinates of the local slab from F
  * (device field).  Host outputs x_n[nz_loc+1][ny+1][nx+1][3] and x_p[nz_loc][ny][nx][3] (= the reference's x_n(3,i,j,k),
  * x_p(3,i,j,k), first index fastest). */

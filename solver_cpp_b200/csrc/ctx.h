@@ -31,6 +31,9 @@ struct dmk_ctx {
   double2* bufA;                  // [nz_loc][ny][nxr][9] after x/y passes; [nz][ny_loc][nxr][9] in the z pass
   double2* bufB;                  // exchange buffer [peer][nz_loc][ny_loc][nxr][9] (world_size > 1 only)
   size_t hat_records;             // records in bufA
+  // fused exchange over peer memory (dmk_p2p_import): peers' bufA / bufB, opened through CUDA IPC.  When on, the forward y
+  // pass stores into the peers' bufB (the z-pass layout lives in bufB), the inverse z pass stores into the peers' bufA.
+  bool p2p; double2* peerA[DMK_MAX_PEERS]; double2* peerB[DMK_MAX_PEERS];
   double* d_Cref;                 // 81, row-major C_ref(l,n,m,o)
   double* d_dc;                   // 9, record order
   double* d_div;                  // 1

@@ -20,7 +20,7 @@ bool dmk_fast_disabled() {
 template <class PL, int KT, bool INV, int NT, int MINB>
 __global__ void __launch_bounds__(NT, MINB) dmk_fast_line_kernel(const double2* __restrict__ src, double2* __restrict__ dst,
                                                            const double2* __restrict__ tw, DmkLineMap ms, DmkLineMap md,
-                                                           int n0, int tiles0) {
+                                                           int n0, int tiles0, const __grid_constant__ DmkPeerStore ps) {
   constexpr int N = PL::N, R1 = PL::R1, R2 = PL::R2, R3 = PL::R3, B = KT * DMK_NC;
   extern __shared__ double2 s[];
   const int o = blockIdx.x / tiles0, i0 = (blockIdx.x - o * tiles0) * KT;
@@ -29,7 +29,7 @@ __global__ void __launch_bounds__(NT, MINB) dmk_fast_line_kernel(const double2* 
   auto ldg = [&](int, int p, int col) { return __ldg(src + dmk_line_rec_fast(ms, ns_s, o, p, i0) * DMK_NC + col); };
   auto lds = [&](int, int p, int col) { return s[p * B + col]; };
   auto sts = [&](int, int p, int col, double2 v) { s[p * B + col] = v; };
-  auto stg = [&](int, int p, int col, double2 v) { dst[dmk_line_rec_fast(md, ns_d, o, PL::freq(p), i0) * DMK_NC + col] = v; };
+  auto stg = [&](int, int p, int col, double2 v) { dmk_line_store_ptr(md, ps, dst, ns_d, o, PL::freq(p), i0)[col] = v; };
   fstage<N, R1, R2 * R3, B, INV, false>(1, bact, tw, ldg, sts);
   __syncthreads();
   if constexpr (R3 > 1) {
@@ -133,7 +133,7 @@ static int set_smem(K kernel, size_t smem) {
 
 template <class PL, int KT, int NT, int MINB = 1>
 static int launch_line(bool inverse, const double2* src, double2* dst, const DmkFftPlan& pl, DmkLineMap ms, DmkLineMap md, int n0,
-                       int n_outer, cudaStream_t st) {
+                       int n_outer, cudaStream_t st, const DmkPeerStore& ps) {
   const size_t smem = (size_t)PL::N * KT * DMK_NC * sizeof(double2);
   const int tiles0 = (n0 + KT - 1) / KT;
   const long long grid = (long long)tiles0 * n_outer;
@@ -141,27 +141,29 @@ static int launch_line(bool inverse, const double2* src, double2* dst, const Dmk
   int rc;
   if (inverse) {
     if ((rc = set_smem(dmk_fast_line_kernel<PL, KT, true, NT, MINB>, smem))) return rc;
-    dmk_fast_line_kernel<PL, KT, true, NT, MINB><<<(int)grid, NT, smem, st>>>(src, dst, pl.tw, ms, md, n0, tiles0);
+    dmk_fast_line_kernel<PL, KT, true, NT, MINB><<<(int)grid, NT, smem, st>>>(src, dst, pl.tw, ms, md, n0, tiles0, ps);
   } else {
     if ((rc = set_smem(dmk_fast_line_kernel<PL, KT, false, NT, MINB>, smem))) return rc;
-    dmk_fast_line_kernel<PL, KT, false, NT, MINB><<<(int)grid, NT, smem, st>>>(src, dst, pl.tw, ms, md, n0, tiles0);
+    dmk_fast_line_kernel<PL, KT, false, NT, MINB><<<(int)grid, NT, smem, st>>>(src, dst, pl.tw, ms, md, n0, tiles0, ps);
   }
   DMK_CUDA_CHECK(cudaGetLastError());
   return DMK_OK;
 }
 
 int dmk_fast_line_pass(bool inverse, const double2* src, double2* dst, const DmkFftPlan& pl, DmkLineMap ms, DmkLineMap md,
-                       int n0, int n_outer, cudaStream_t st, bool* done) {
+                       int n0, int n_outer, cudaStream_t st, bool* done, const DmkPeerStore* psp) {
   *done = true;
   if (dmk_fast_disabled()) { *done = false; return DMK_OK; }
+  DmkPeerStore ps;
+  if (psp) ps = *psp; else memset(&ps, 0, sizeof ps);
   // tile width, threads and CTAs/SM per length: tools/fft_tune.cu sweeps on B200 (profiles/r01_fft_tuning.md)
   switch (pl.n) {
-    case 16: return launch_line<DmkFastPlan<4, 4, 1>, 4, 144, 4>(inverse, src, dst, pl, ms, md, n0, n_outer, st);
-    case 32: return launch_line<DmkFastPlan<8, 4, 1>, 4, 144, 4>(inverse, src, dst, pl, ms, md, n0, n_outer, st);
-    case 64: return launch_line<DmkFastPlan<8, 8, 1>, 2, 144, 4>(inverse, src, dst, pl, ms, md, n0, n_outer, st);
-    case 128: return launch_line<DmkFastPlan<16, 8, 1>, 2, 144, 3>(inverse, src, dst, pl, ms, md, n0, n_outer, st);
-    case 256: return launch_line<DmkFastPlan<16, 16, 1>, 1, 144, 3>(inverse, src, dst, pl, ms, md, n0, n_outer, st);
-    case 512: return launch_line<DmkFastPlan<8, 8, 8>, 1, 288, 2>(inverse, src, dst, pl, ms, md, n0, n_outer, st);
+    case 16: return launch_line<DmkFastPlan<4, 4, 1>, 4, 144, 4>(inverse, src, dst, pl, ms, md, n0, n_outer, st, ps);
+    case 32: return launch_line<DmkFastPlan<8, 4, 1>, 4, 144, 4>(inverse, src, dst, pl, ms, md, n0, n_outer, st, ps);
+    case 64: return launch_line<DmkFastPlan<8, 8, 1>, 2, 144, 4>(inverse, src, dst, pl, ms, md, n0, n_outer, st, ps);
+    case 128: return launch_line<DmkFastPlan<16, 8, 1>, 2, 144, 3>(inverse, src, dst, pl, ms, md, n0, n_outer, st, ps);
+    case 256: return launch_line<DmkFastPlan<16, 16, 1>, 1, 144, 3>(inverse, src, dst, pl, ms, md, n0, n_outer, st, ps);
+    case 512: return launch_line<DmkFastPlan<8, 8, 8>, 1, 288, 2>(inverse, src, dst, pl, ms, md, n0, n_outer, st, ps);
     default: *done = false; return DMK_OK;
   }
 }

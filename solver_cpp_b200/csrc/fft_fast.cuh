@@ -118,11 +118,21 @@ __device__ __forceinline__ long long dmk_line_rec_fast(const DmkLineMap& m, bool
   return dmk_line_rec(m, o, line, i0);
 }
 
+// where the last stage of a strided pass stores line position `line`: own buffer, or a peer's (DmkPeerStore)
+__device__ __forceinline__ double2* dmk_line_store_ptr(const DmkLineMap& m, const DmkPeerStore& ps, double2* local, bool nosplit, int o,
+                                                       int line, int i0) {
+  if (ps.remote) {
+    const int hi = line / ps.split, lo = line - hi * ps.split;
+    return ps.peer[hi] + ((long long)ps.me * ps.hi_stride + o * ps.o_stride + lo * ps.e_stride + i0) * DMK_NC;
+  }
+  return local + dmk_line_rec_fast(m, nosplit, o, line, i0) * DMK_NC;
+}
+
 // launchers (fft_fast.cu, gamma_fast.cu): return DMK_OK and set *done = true if the length is covered
 int dmk_fast_xpass_r2c(const double* in, double2* out, const DmkFftPlan& pl, int nrows, cudaStream_t st, bool* done);
 int dmk_fast_xpass_c2r(const double2* in, double* out, const DmkFftPlan& pl, int nrows, double scale, cudaStream_t st, bool* done);
 int dmk_fast_line_pass(bool inverse, const double2* src, double2* dst, const DmkFftPlan& pl, DmkLineMap ms, DmkLineMap md,
-                       int n0, int n_outer, cudaStream_t st, bool* done);
+                       int n0, int n_outer, cudaStream_t st, bool* done, const DmkPeerStore* ps = nullptr);
 int dmk_fast_gamma_zpass(double2* data, const DmkFftPlan& plz, DmkLineMap map, int n0, int n_outer, const DmkGammaParams& gp,
-                         cudaStream_t st, bool imag_xi, bool* done);
+                         cudaStream_t st, bool imag_xi, bool* done, const DmkPeerStore* ps = nullptr);
 bool dmk_fast_disabled();      // DMK_FFT=generic forces the shared-memory-only kernels of fft_kernels.cu (comparison runs)

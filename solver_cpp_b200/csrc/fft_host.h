@@ -16,12 +16,22 @@ __host__ __device__ __forceinline__ long long dmk_line_rec(const DmkLineMap& m, 
   return hi * m.hi_stride + o * m.o_stride + lo * m.e_stride + i0;
 }
 
+// Fused exchange over peer memory (NVLink): when `remote` is set, the LAST stage of a strided pass stores line position
+// `line` not into its own buffer but into block `me` of the buffer of peer line / split -- the transpose of the
+// distributed FFT happens inside the FFT pass, tile by tile, instead of in a separate all-to-all.
+#define DMK_MAX_PEERS 8
+struct DmkPeerStore {
+  int remote, me, split;
+  long long hi_stride, o_stride, e_stride;      // record = me * hi_stride + o * o_stride + (line % split) * e_stride + i0
+  double2* peer[DMK_MAX_PEERS];
+};
+
 int dmk_fft_plan_create(DmkFftPlan* pl, int n);
 void dmk_fft_plan_destroy(DmkFftPlan* pl);
 int dmk_launch_xpass_r2c(const double* in, double2* out, const DmkFftPlan& pl, int nrows, cudaStream_t st);
 int dmk_launch_xpass_c2r(const double2* in, double* out, const DmkFftPlan& pl, int nrows, double scale, cudaStream_t st);
 int dmk_launch_line_pass(bool inverse, const double2* src, double2* dst, const DmkFftPlan& pl, DmkLineMap ms,
-                         DmkLineMap md, int n0, int n_outer, int KT, cudaStream_t st);
+                         DmkLineMap md, int n0, int n_outer, int KT, cudaStream_t st, const DmkPeerStore* ps = nullptr);
 
 // ---- fused z pass: forward FFT along z, divergence-RMS accumulation, Gamma-operator contraction, inverse FFT
 struct DmkGammaParams {
@@ -42,4 +52,4 @@ struct DmkGammaParams {
   double* div_accum;           // device, 1 double: += sum_k w_k |P_hat(k) . conj(-xi1st) rescale|^2
 };
 int dmk_launch_gamma_zpass(double2* data, const DmkFftPlan& plz, DmkLineMap map, int n0, int n_outer, int KT,
-                           const DmkGammaParams& gp, cudaStream_t st, bool imag_xi);
+                           const DmkGammaParams& gp, cudaStream_t st, bool imag_xi, const DmkPeerStore* ps = nullptr);

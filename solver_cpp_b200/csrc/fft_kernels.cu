@@ -213,8 +213,9 @@ int dmk_launch_xpass_c2r(const double2* in, double* out, const DmkFftPlan& pl, i
 }
 
 int dmk_launch_line_pass(bool inverse, const double2* src, double2* dst, const DmkFftPlan& pl, DmkLineMap ms,
-                         DmkLineMap md, int n0, int n_outer, int KT, cudaStream_t st) {
-  { bool done = false; int rc = dmk_fast_line_pass(inverse, src, dst, pl, ms, md, n0, n_outer, st, &done); if (rc || done) return rc; }
+                         DmkLineMap md, int n0, int n_outer, int KT, cudaStream_t st, const DmkPeerStore* ps) {
+  { bool done = false; int rc = dmk_fast_line_pass(inverse, src, dst, pl, ms, md, n0, n_outer, st, &done, ps); if (rc || done) return rc; }
+  if (ps && ps->remote) { dmk_set_error("the fused exchange needs a power-of-two line length (16..512), got %d", pl.n); return DMK_ERR_UNSUPPORTED; }
   if (KT < 1) KT = 1;
   if (KT > n0) KT = n0;
   size_t smem = (size_t)pl.n * KT * DMK_NC * sizeof(double2);

@@ -5,12 +5,14 @@
 // MechBase::gamma_convolution (mech_base.cpp:400-477); operator definition and per-k-point arithmetic: gamma_kernels.cu,
 // gamma_point.cuh (shared with the shared-memory-only kernel, so both produce the same bits per k-point).
 // One tile (N kz positions x KT kx records) per CTA; the half spectrum is read once and written once (144 B/point).
+#include <cstring>
 #include "fft_fast.cuh"
 #include "gamma_point.cuh"
 
 template <class PL, int KT, bool IMAG_XI, int NT, int MINB>
 __global__ void __launch_bounds__(NT, MINB) dmk_fast_gamma_kernel(double2* __restrict__ data, const double2* __restrict__ tw,
-                                                            DmkLineMap map, int n0, int tiles0, DmkGammaParams gp) {
+                                                            DmkLineMap map, int n0, int tiles0, DmkGammaParams gp,
+                                                            const __grid_constant__ DmkPeerStore ps) {
   constexpr int N = PL::N, R1 = PL::R1, R2 = PL::R2, R3 = PL::R3, B = KT * DMK_NC;
   static_assert(NT % 32 == 0, "whole warps: the divergence sum is reduced with full-warp shuffles");
   extern __shared__ double2 s[];
@@ -25,7 +27,7 @@ __global__ void __launch_bounds__(NT, MINB) dmk_fast_gamma_kernel(double2* __res
   auto ldg = [&](int, int p, int col) { return data[dmk_line_rec_fast(map, nosplit, o, p, i0) * DMK_NC + col]; };
   auto lds = [&](int, int p, int col) { return s[p * B + col]; };
   auto sts = [&](int, int p, int col, double2 v) { s[p * B + col] = v; };
-  auto stg = [&](int, int p, int col, double2 v) { data[dmk_line_rec_fast(map, nosplit, o, p, i0) * DMK_NC + col] = v; };
+  auto stg = [&](int, int p, int col, double2 v) { dmk_line_store_ptr(map, ps, data, nosplit, o, p, i0)[col] = v; };
   // ---- forward along z: natural order in HBM -> digit-reversed slots in shared memory
   fstage<N, R1, R2 * R3, B, false, false>(1, bact, tw, ldg, sts);
   __syncthreads();
@@ -91,34 +93,36 @@ __global__ void __launch_bounds__(NT, MINB) dmk_fast_gamma_kernel(double2* __res
 
 template <class PL, int KT, int NT, int MINB = 1>
 static int launch_gamma(double2* data, const DmkFftPlan& pl, DmkLineMap map, int n0, int n_outer, const DmkGammaParams& gp,
-                        cudaStream_t st, bool imag_xi) {
+                        cudaStream_t st, bool imag_xi, const DmkPeerStore& ps) {
   const size_t smem = (size_t)PL::N * KT * DMK_NC * sizeof(double2);
   const int tiles0 = (n0 + KT - 1) / KT;
   const long long grid = (long long)tiles0 * n_outer;
   if (grid > 0x7fffffffLL) { dmk_set_error("gamma pass grid too large"); return DMK_ERR_UNSUPPORTED; }
   if (imag_xi) {
     if (smem > 48 * 1024) DMK_CUDA_CHECK(cudaFuncSetAttribute(dmk_fast_gamma_kernel<PL, KT, true, NT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    dmk_fast_gamma_kernel<PL, KT, true, NT, MINB><<<(int)grid, NT, smem, st>>>(data, pl.tw, map, n0, tiles0, gp);
+    dmk_fast_gamma_kernel<PL, KT, true, NT, MINB><<<(int)grid, NT, smem, st>>>(data, pl.tw, map, n0, tiles0, gp, ps);
   } else {
     if (smem > 48 * 1024) DMK_CUDA_CHECK(cudaFuncSetAttribute(dmk_fast_gamma_kernel<PL, KT, false, NT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    dmk_fast_gamma_kernel<PL, KT, false, NT, MINB><<<(int)grid, NT, smem, st>>>(data, pl.tw, map, n0, tiles0, gp);
+    dmk_fast_gamma_kernel<PL, KT, false, NT, MINB><<<(int)grid, NT, smem, st>>>(data, pl.tw, map, n0, tiles0, gp, ps);
   }
   DMK_CUDA_CHECK(cudaGetLastError());
   return DMK_OK;
 }
 
 int dmk_fast_gamma_zpass(double2* data, const DmkFftPlan& plz, DmkLineMap map, int n0, int n_outer, const DmkGammaParams& gp,
-                         cudaStream_t st, bool imag_xi, bool* done) {
+                         cudaStream_t st, bool imag_xi, bool* done, const DmkPeerStore* psp) {
   *done = true;
   if (dmk_fast_disabled()) { *done = false; return DMK_OK; }
+  DmkPeerStore ps;
+  if (psp) ps = *psp; else memset(&ps, 0, sizeof ps);
   // the Gamma section needs ~168 registers, so CTAs are small (<= 192 threads, 2 per SM): tools/fft_tune.cu sweeps
   switch (plz.n) {
-    case 16: return launch_gamma<DmkFastPlan<4, 4, 1>, 4, 160, 2>(data, plz, map, n0, n_outer, gp, st, imag_xi);
-    case 32: return launch_gamma<DmkFastPlan<8, 4, 1>, 4, 160, 2>(data, plz, map, n0, n_outer, gp, st, imag_xi);
-    case 64: return launch_gamma<DmkFastPlan<8, 8, 1>, 4, 160, 2>(data, plz, map, n0, n_outer, gp, st, imag_xi);
-    case 128: return launch_gamma<DmkFastPlan<16, 8, 1>, 4, 192, 2>(data, plz, map, n0, n_outer, gp, st, imag_xi);
-    case 256: return launch_gamma<DmkFastPlan<16, 16, 1>, 2, 192, 2>(data, plz, map, n0, n_outer, gp, st, imag_xi);
-    case 512: return launch_gamma<DmkFastPlan<8, 8, 8>, 1, 192, 2>(data, plz, map, n0, n_outer, gp, st, imag_xi);
+    case 16: return launch_gamma<DmkFastPlan<4, 4, 1>, 4, 160, 2>(data, plz, map, n0, n_outer, gp, st, imag_xi, ps);
+    case 32: return launch_gamma<DmkFastPlan<8, 4, 1>, 4, 160, 2>(data, plz, map, n0, n_outer, gp, st, imag_xi, ps);
+    case 64: return launch_gamma<DmkFastPlan<8, 8, 1>, 4, 160, 2>(data, plz, map, n0, n_outer, gp, st, imag_xi, ps);
+    case 128: return launch_gamma<DmkFastPlan<16, 8, 1>, 4, 192, 2>(data, plz, map, n0, n_outer, gp, st, imag_xi, ps);
+    case 256: return launch_gamma<DmkFastPlan<16, 16, 1>, 2, 192, 2>(data, plz, map, n0, n_outer, gp, st, imag_xi, ps);
+    case 512: return launch_gamma<DmkFastPlan<8, 8, 8>, 1, 192, 2>(data, plz, map, n0, n_outer, gp, st, imag_xi, ps);
     default: *done = false; return DMK_OK;
   }
 }

@@ -84,8 +84,6 @@ __global__ void __launch_bounds__(256, 2) dmk_gamma_zpass_kernel(double2* __rest
   }
 }
 
-int dmk_launch_gamma_zpass(double2* data, const DmkFftPlan& plz, DmkLineMap map, int n0, int n_outer, int KT,
-                           const DmkGammaParams& gp, cudaStream_t st, bool imag_xi);
 
 template <typename K>
 static int grid_for_g(K kernel, int threads, size_t smem, long long work, int* grid) {
@@ -102,12 +100,13 @@ static int grid_for_g(K kernel, int threads, size_t smem, long long work, int* g
 }
 
 int dmk_launch_gamma_zpass(double2* data, const DmkFftPlan& plz, DmkLineMap map, int n0, int n_outer, int KT,
-                           const DmkGammaParams& gp, cudaStream_t st, bool imag_xi) {
+                           const DmkGammaParams& gp, cudaStream_t st, bool imag_xi, const DmkPeerStore* ps) {
   {
     bool done = false;
-    int rc = dmk_fast_gamma_zpass(data, plz, map, n0, n_outer, gp, st, imag_xi, &done);
+    int rc = dmk_fast_gamma_zpass(data, plz, map, n0, n_outer, gp, st, imag_xi, &done, ps);
     if (rc || done) return rc;
   }
+  if (ps && ps->remote) { dmk_set_error("the fused exchange needs a power-of-two line length (16..512), got %d", plz.n); return DMK_ERR_UNSUPPORTED; }
   if (KT < 1) KT = 1;
   if (KT > n0) KT = n0;
   size_t smem = (size_t)plz.n * KT * DMK_NC * sizeof(double2);

@@ -95,6 +95,7 @@ void dmk_spectral_teardown(dmk_ctx* c) {
   dmk_fft_plan_destroy(&c->plx); dmk_fft_plan_destroy(&c->ply); dmk_fft_plan_destroy(&c->plz);
   for (int a = 0; a < 3; a++) { cudaFree(c->xi_own[a]); cudaFree(c->xi_oth[a]); cudaFree(c->nyq[a]); }
   cudaFree(c->bufA); if (c->bufB) cudaFree(c->bufB);
+  if (c->p2p) for (int p = 0; p < c->P; p++) if (p != c->rank) { cudaIpcCloseMemHandle(c->peerA[p]); cudaIpcCloseMemHandle(c->peerB[p]); }
   cudaFree(c->d_Cref); cudaFree(c->d_dc); cudaFree(c->d_div); cudaFree(c->d_scratch);
   if (c->h_pinned) cudaFreeHost(c->h_pinned);
 }
@@ -189,6 +190,33 @@ static DmkLineMap map_z(const dmk_ctx* c) {
   return m;
 }
 
+// the buffer holding the z-pass layout [kz][ky_loc][kx]
+static inline double2* zbuf(dmk_ctx* c) { return c->p2p ? c->bufB : c->bufA; }
+
+// stream-ordered barrier over all ranks (a 1-double all-reduce): orders the remote stores of the fused exchange
+static int p2p_barrier(dmk_ctx* c) {
+  double* d = c->d_scratch + DMK_SCRATCH_TMP + 300;
+  DMK_CUDA_CHECK(cudaMemsetAsync(d, 0, sizeof(double), c->stream));
+  if (!c->has_comm || c->comm.allreduce_sum(c->comm.user, d, 1)) { dmk_set_error("allreduce callback failed (fused exchange barrier)"); return DMK_ERR_STATE; }
+  return DMK_OK;
+}
+// forward: y position ky -> peer ky / ny_loc, block `me` of its bufB = rows kz = me * nz_loc + z_loc of the z-pass layout
+static DmkPeerStore peers_forward(const dmk_ctx* c) {
+  DmkPeerStore ps; memset(&ps, 0, sizeof ps);
+  ps.remote = 1; ps.me = c->rank; ps.split = c->ny_loc;
+  ps.hi_stride = (long long)c->nz_loc * c->ny_loc * c->nxr; ps.o_stride = (long long)c->ny_loc * c->nxr; ps.e_stride = c->nxr;
+  for (int p = 0; p < c->P; p++) ps.peer[p] = c->peerB[p];
+  return ps;
+}
+// inverse: z position kz -> peer kz / nz_loc, block `me` of its bufA in the exchange layout [src][z_loc][ky_loc][kx]
+static DmkPeerStore peers_inverse(const dmk_ctx* c) {
+  DmkPeerStore ps; memset(&ps, 0, sizeof ps);
+  ps.remote = 1; ps.me = c->rank; ps.split = c->nz_loc;
+  ps.hi_stride = (long long)c->nz_loc * c->ny_loc * c->nxr; ps.o_stride = c->nxr; ps.e_stride = (long long)c->ny_loc * c->nxr;
+  for (int p = 0; p < c->P; p++) ps.peer[p] = c->peerA[p];
+  return ps;
+}
+
 static int exchange(dmk_ctx* c, const double2* send, double2* recv) {
   if (!c->has_comm || !c->comm.alltoall) { dmk_set_error("world_size > 1 but no alltoall callback set (dmk_set_comm)"); return DMK_ERR_STATE; }
   size_t bytes = (size_t)c->nz_loc * c->ny_loc * c->nxr * DMK_NC * sizeof(double2);
@@ -202,6 +230,13 @@ int dmk_fft_forward_internal(dmk_ctx* c, const double* d_real) {
   c->launches++;
   if (c->P == 1) {
     if (c->ny > 1) { if ((rc = dmk_launch_line_pass(false, c->bufA, c->bufA, c->ply, map_y(c, false), map_y(c, false), c->nxr, c->nz_loc, c->kt_y, c->stream))) return rc; c->launches++; }
+  } else if (c->p2p) {
+    // fused y pass + transpose: the last stage stores each tile straight into the owner's bufB over NVLink
+    const DmkPeerStore ps = peers_forward(c);
+    if ((rc = p2p_barrier(c))) return rc;                      // the peers are done reading their bufB (previous inverse)
+    if ((rc = dmk_launch_line_pass(false, c->bufA, c->bufB, c->ply, map_y(c, false), map_y(c, true), c->nxr, c->nz_loc, c->kt_y, c->stream, &ps))) return rc;
+    c->launches++;
+    if ((rc = p2p_barrier(c))) return rc;                      // every rank's stores have landed
   } else {
     if ((rc = dmk_launch_line_pass(false, c->bufA, c->bufB, c->ply, map_y(c, false), map_y(c, true), c->nxr, c->nz_loc, c->kt_y, c->stream))) return rc;
     c->launches++;
@@ -214,6 +249,14 @@ int dmk_fft_backward_internal(dmk_ctx* c, double* d_real, double scale) {
   int rc;
   if (c->P == 1) {
     if (c->ny > 1) { if ((rc = dmk_launch_line_pass(true, c->bufA, c->bufA, c->ply, map_y(c, false), map_y(c, false), c->nxr, c->nz_loc, c->kt_y, c->stream))) return rc; c->launches++; }
+  } else if (c->p2p) {
+    // the inverse z pass (fused Gamma pass or plain) has stored into the peers' bufA in the exchange layout
+    if ((rc = p2p_barrier(c))) return rc;
+    if ((rc = dmk_launch_line_pass(true, c->bufA, c->bufB, c->ply, map_y(c, true), map_y(c, false), c->nxr, c->nz_loc, c->kt_y, c->stream))) return rc;
+    c->launches++;
+    if ((rc = dmk_launch_xpass_c2r(c->bufB, d_real, c->plx, c->ny * c->nz_loc, scale, c->stream))) return rc;
+    c->launches++;
+    return DMK_OK;
   } else {
     if ((rc = exchange(c, c->bufA, c->bufB))) return rc;
     if ((rc = dmk_launch_line_pass(true, c->bufB, c->bufA, c->ply, map_y(c, true), map_y(c, false), c->nxr, c->nz_loc, c->kt_y, c->stream))) return rc;
@@ -236,7 +279,8 @@ static void fill_gamma_params(dmk_ctx* c, DmkGammaParams* gp) {
 int dmk_gamma_internal(dmk_ctx* c) {
   if (!c->gamma_set) { dmk_set_error("reference stiffness not set (dmk_update_gamma)"); return DMK_ERR_STATE; }
   DmkGammaParams gp; fill_gamma_params(c, &gp);
-  int rc = dmk_launch_gamma_zpass(c->bufA, c->plz, map_z(c), c->nxr, c->ny_loc, c->kt_z, gp, c->stream, c->xi_imag);
+  DmkPeerStore ps; if (c->p2p) ps = peers_inverse(c);
+  int rc = dmk_launch_gamma_zpass(zbuf(c), c->plz, map_z(c), c->nxr, c->ny_loc, c->kt_z, gp, c->stream, c->xi_imag, c->p2p ? &ps : nullptr);
   if (!rc) c->launches++;
   return rc;
 }
@@ -244,7 +288,9 @@ int dmk_gamma_internal(dmk_ctx* c) {
 // plain z passes (test API dmk_fft_forward / dmk_fft_backward only)
 static int zpass_plain(dmk_ctx* c, bool inverse) {
   if (c->nz == 1) return DMK_OK;
-  int rc = dmk_launch_line_pass(inverse, c->bufA, c->bufA, c->plz, map_z(c), map_z(c), c->nxr, c->ny_loc, c->kt_z, c->stream);
+  DmkPeerStore ps; const bool remote = c->p2p && inverse;      // the inverse z pass feeds the exchange (see backward_internal)
+  if (remote) ps = peers_inverse(c);
+  int rc = dmk_launch_line_pass(inverse, zbuf(c), zbuf(c), c->plz, map_z(c), map_z(c), c->nxr, c->ny_loc, c->kt_z, c->stream, remote ? &ps : nullptr);
   if (!rc) c->launches++;
   return rc;
 }
@@ -254,14 +300,14 @@ extern "C" int dmk_fft_forward(dmk_ctx* c, const double* d_real, double* d_fouri
   if ((rc = dmk_fft_forward_internal(c, d_real))) return rc;
   if ((rc = zpass_plain(c, false))) return rc;
   size_t bytes = (size_t)c->nz * c->ny_loc * c->nxr * DMK_NC * sizeof(double2);
-  DMK_CUDA_CHECK(cudaMemcpyAsync(d_fourier, c->bufA, bytes, cudaMemcpyDeviceToDevice, c->stream));
+  DMK_CUDA_CHECK(cudaMemcpyAsync(d_fourier, zbuf(c), bytes, cudaMemcpyDeviceToDevice, c->stream));
   return DMK_OK;
 }
 
 extern "C" int dmk_fft_backward(dmk_ctx* c, const double* d_fourier, double* d_real, double wgt) {
   int rc;
   size_t bytes = (size_t)c->nz * c->ny_loc * c->nxr * DMK_NC * sizeof(double2);
-  DMK_CUDA_CHECK(cudaMemcpyAsync(c->bufA, d_fourier, bytes, cudaMemcpyDeviceToDevice, c->stream));
+  DMK_CUDA_CHECK(cudaMemcpyAsync(zbuf(c), d_fourier, bytes, cudaMemcpyDeviceToDevice, c->stream));
   if ((rc = zpass_plain(c, true))) return rc;
   return dmk_fft_backward_internal(c, d_real, wgt);
 }
@@ -453,7 +499,7 @@ extern "C" int dmk_update_coords(dmk_ctx* c, const double* d_F, double* h_x_n, d
   // F_hat -> u_hat -> u_tilde (components 0..2 of a scratch field)
   if ((rc = dmk_fft_forward_internal(c, d_F))) return rc;
   if ((rc = zpass_plain(c, false))) return rc;
-  dmk_coords_integrate_kernel<<<148 * 8, 256, 0, c->stream>>>(c->bufA, c->nxr, c->ny_loc, c->nz, c->ny, c->y_off, PI2 / c->g.size[0],
+  dmk_coords_integrate_kernel<<<148 * 8, 256, 0, c->stream>>>(zbuf(c), c->nxr, c->ny_loc, c->nz, c->ny, c->y_off, PI2 / c->g.size[0],
                                                                PI2 / c->g.size[1], PI2 / c->g.size[2]);
   c->launches++;
   if ((rc = zpass_plain(c, true))) return rc;
@@ -490,5 +536,42 @@ extern "C" int dmk_update_coords(dmk_ctx* c, const double* d_F, double* h_x_n, d
       cudaMemcpyAsync(h_x_p, d_xp, (size_t)c->n_local * 3 * sizeof(double), cudaMemcpyDeviceToHost, c->stream) != cudaSuccess ||
       cudaStreamSynchronize(c->stream) != cudaSuccess || cudaGetLastError() != cudaSuccess) { dmk_set_error("update_coords: CUDA error"); return fail(DMK_ERR_CUDA); }
   cudaFree(d_u);
+  return DMK_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ fused exchange set-up
+// CUDA IPC handles of this rank's two spectral buffers (2 x 64 bytes), to be all-gathered by the host side
+extern "C" int dmk_p2p_export(dmk_ctx* c, unsigned char* handles128) {
+  if (!c || !handles128) { dmk_set_error("null argument"); return DMK_ERR_ARG; }
+  if (c->P < 2 || !c->bufB) { dmk_set_error("fused exchange: single-rank context"); return DMK_ERR_STATE; }
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  cudaIpcMemHandle_t h;
+  DMK_CUDA_CHECK(cudaIpcGetMemHandle(&h, c->bufA)); memcpy(handles128, &h, 64);
+  DMK_CUDA_CHECK(cudaIpcGetMemHandle(&h, c->bufB)); memcpy(handles128 + 64, &h, 64);
+  return DMK_OK;
+}
+
+bool dmk_fast_disabled();      // fft_fast.cu
+static bool fast_len(int n) { return n == 16 || n == 32 || n == 64 || n == 128 || n == 256 || n == 512; }
+
+// all ranks' handles ([rank][A|B][64]); opens the peers' buffers and switches the transposes of the distributed FFT from
+// the all-to-all callback to stores over peer memory inside the y and z passes.  *enabled = 0 (and no error) when the
+// grid does not qualify (line lengths the register-resident passes do not cover).
+extern "C" int dmk_p2p_import(dmk_ctx* c, const unsigned char* all_handles, int* enabled) {
+  if (!c || !all_handles) { dmk_set_error("null argument"); return DMK_ERR_ARG; }
+  if (enabled) *enabled = 0;
+  if (c->P < 2 || c->P > DMK_MAX_PEERS || !c->has_comm) { dmk_set_error("fused exchange: needs 2..%d ranks and the collective callbacks", DMK_MAX_PEERS); return DMK_ERR_STATE; }
+  if (!fast_len(c->ny) || !fast_len(c->nz) || dmk_fast_disabled()) return DMK_OK;
+  for (int p = 0; p < c->P; p++) {
+    if (p == c->rank) { c->peerA[p] = c->bufA; c->peerB[p] = c->bufB; continue; }
+    cudaIpcMemHandle_t h;
+    void* ptr = nullptr;
+    memcpy(&h, all_handles + (size_t)p * 128, 64);
+    DMK_CUDA_CHECK(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess)); c->peerA[p] = (double2*)ptr;
+    memcpy(&h, all_handles + (size_t)p * 128 + 64, 64);
+    DMK_CUDA_CHECK(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess)); c->peerB[p] = (double2*)ptr;
+  }
+  c->p2p = true;
+  if (enabled) *enabled = 1;
   return DMK_OK;
 }

@@ -211,6 +211,21 @@ class GridContext:
         return v.value
 
     # ---- multi-GPU: collective callbacks (solver_cpp_b200.parallel.TorchComm)
+    def enable_fused_exchange(self, group=None):
+        """all-gathers the CUDA IPC handles of every rank's spectral buffers and switches the distributed FFT's transposes to
+        stores over peer memory inside the y / z passes (dmk_p2p_import).  Returns True if the fused path is on."""
+        import torch.distributed as dist
+        mine = (C.c_ubyte * 128)()
+        L.check(self.lib.dmk_p2p_export(self.ctx, mine))
+        t = torch.tensor(list(bytes(mine)), dtype=torch.uint8, device=self.device)
+        out = torch.empty(128 * self.world_size, dtype=torch.uint8, device=self.device)
+        dist.all_gather_into_tensor(out, t, group=group)
+        allh = (C.c_ubyte * (128 * self.world_size))(*out.cpu().tolist())
+        on = C.c_int(0)
+        L.check(self.lib.dmk_p2p_import(self.ctx, allh, C.byref(on)))
+        self.fused_exchange = bool(on.value)
+        return self.fused_exchange
+
     def set_comm(self, comm):
         self._comm_keepalive = comm
         L.check(self.lib.dmk_set_comm(self.ctx, C.byref(comm.struct)))

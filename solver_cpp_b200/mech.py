@@ -233,5 +233,8 @@ def make_solver(cells, size, material, material_at, numerics=None, derivative=0,
     g = GridContext(cells, size, derivative=derivative, divergence_correction=divergence_correction, world_size=world_size, rank=rank)
     if comm is not None:
         g.set_comm(comm)
+        from . import parallel
+        if world_size > 1 and parallel.fused_exchange_wanted():
+            g.enable_fused_exchange(getattr(comm, 'group', None))
     g.material_init(M.Material(material, material_at), numerics)
     return MechSolverBasic(g)

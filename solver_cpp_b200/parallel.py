@@ -74,6 +74,12 @@ def make_comm(world_size, rank, group=None):
     return TorchComm(world_size, rank, group)
 
 
+def fused_exchange_wanted():
+    """DMK_EXCHANGE=nccl keeps the transposes on the NCCL all-to-all (comparison runs); default: fused over peer memory"""
+    import os
+    return os.environ.get('DMK_EXCHANGE', 'p2p').lower() != 'nccl'
+
+
 def alltoall_transpose_host(send, group=None):
     """the transpose exchange on a CPU tensor (gloo): send [peer][...] -> recv [peer][...]; host-logic twin of the
     device path used by the world_size-2 tests"""
