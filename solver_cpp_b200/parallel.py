@@ -97,3 +97,26 @@ def _gloo_alltoall(recv, send, group):
         out = recv[src]
         dist.scatter(out, [send[p].contiguous() for p in range(P)] if me == src else None, src=src, group=group)
     return recv
+
+
+def peer_store_forward(nxr, ny, nz, world_size, me):
+    """host twin of the library's DmkPeerStore for the forward exchange (csrc/spectral.cu: peers_forward): where rank `me`
+    stores y-line position ky of its local plane z_loc, record kx -> (peer, record index in the peer's z-pass buffer
+    [kz][ky_loc][kx])"""
+    ny_loc, nz_loc = ny // world_size, nz // world_size
+    hi, o, e = nz_loc * ny_loc * nxr, ny_loc * nxr, nxr
+
+    def target(z_loc, ky, kx):
+        return ky // ny_loc, me * hi + z_loc * o + (ky % ny_loc) * e + kx
+    return target
+
+
+def peer_store_inverse(nxr, ny, nz, world_size, me):
+    """... and for the inverse exchange (peers_inverse): z-line position kz of local ky_loc -> (peer, record index in the
+    peer's y-pass buffer in the exchange layout [src][z_loc][ky_loc][kx])"""
+    ny_loc, nz_loc = ny // world_size, nz // world_size
+    hi, o, e = nz_loc * ny_loc * nxr, nxr, ny_loc * nxr
+
+    def target(ky_loc, kz, kx):
+        return kz // nz_loc, me * hi + ky_loc * o + (kz % nz_loc) * e + kx
+    return target

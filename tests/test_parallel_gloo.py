@@ -53,6 +53,42 @@ def test_slab_range_and_layout():
     assert parallel.exchange_layout(5, 8, 4, 2) == ((2, 2, 4, 5, 9), (4, 4, 5, 9))
 
 
+def test_fused_exchange_addressing_equals_the_all_to_all():
+    """the store addresses of the fused exchange over peer memory (DmkPeerStore, csrc/spectral.cu) reproduce, rank by rank,
+    exactly what the all-to-all transposes deliver: forward into the z-pass layout, inverse into the exchange layout"""
+    sys.path.insert(0, ROOT)
+    from solver_cpp_b200 import parallel
+    for world, (nx, ny, nz) in ((2, (6, 8, 4)), (4, (4, 8, 12)), (8, (2, 16, 8))):
+        nxr = nx // 2 + 1
+        ny_loc, nz_loc = ny // world, nz // world
+        rng = np.random.default_rng(world)
+        full = rng.standard_normal((nz, ny, nxr))                       # one value per record, global (z, ky, kx)
+        # forward: rank me holds [z_loc][ky][kx]; after the exchange rank p must hold [kz][ky_loc][kx] = full[:, p's ky range]
+        bufB = [np.full(nz * ny_loc * nxr, np.nan) for _ in range(world)]
+        for me in range(world):
+            tgt = parallel.peer_store_forward(nxr, ny, nz, world, me)
+            for z_loc in range(nz_loc):
+                for ky in range(ny):
+                    for kx in range(nxr):
+                        p, rec = tgt(z_loc, ky, kx)
+                        bufB[p][rec] = full[me * nz_loc + z_loc, ky, kx]
+        for p in range(world):
+            assert np.array_equal(bufB[p].reshape(nz, ny_loc, nxr), full[:, p * ny_loc:(p + 1) * ny_loc])
+        # inverse: rank me holds [kz][ky_loc][kx]; rank p must receive [src][z_loc][ky_loc][kx] (what the inverse y pass reads)
+        bufA = [np.full(world * nz_loc * ny_loc * nxr, np.nan) for _ in range(world)]
+        for me in range(world):
+            tgt = parallel.peer_store_inverse(nxr, ny, nz, world, me)
+            for ky_loc in range(ny_loc):
+                for kz in range(nz):
+                    for kx in range(nxr):
+                        p, rec = tgt(ky_loc, kz, kx)
+                        bufA[p][rec] = full[kz, me * ny_loc + ky_loc, kx]
+        for p in range(world):
+            got = bufA[p].reshape(world, nz_loc, ny_loc, nxr)
+            for src in range(world):
+                assert np.array_equal(got[src], full[p * nz_loc:(p + 1) * nz_loc, src * ny_loc:(src + 1) * ny_loc])
+
+
 def test_transpose_exchange_world_size_2():
     world, port = 2, 29533
     ctx = mp.get_context('spawn')
