@@ -17,7 +17,7 @@ bool dmk_fast_disabled() {
 }
 
 // ------------------------------------------------------------------------------------------------ strided pass (y, z)
-template <class PL, int KT, bool INV, int NT, int MINB>
+template <class PL, int KT, bool INV, int NT, int MINB, bool REMOTE>
 __global__ void __launch_bounds__(NT, MINB) dmk_fast_line_kernel(const double2* __restrict__ src, double2* __restrict__ dst,
                                                            const double2* __restrict__ tw, DmkLineMap ms, DmkLineMap md,
                                                            int n0, int tiles0, const __grid_constant__ DmkPeerStore ps) {
@@ -29,7 +29,7 @@ __global__ void __launch_bounds__(NT, MINB) dmk_fast_line_kernel(const double2* 
   auto ldg = [&](int, int p, int col) { return __ldg(src + dmk_line_rec_fast(ms, ns_s, o, p, i0) * DMK_NC + col); };
   auto lds = [&](int, int p, int col) { return s[p * B + col]; };
   auto sts = [&](int, int p, int col, double2 v) { s[p * B + col] = v; };
-  auto stg = [&](int, int p, int col, double2 v) { dmk_line_store_ptr(md, ps, dst, ns_d, o, PL::freq(p), i0)[col] = v; };
+  auto stg = [&](int, int p, int col, double2 v) { dmk_line_store_ptr<REMOTE>(md, ps, dst, ns_d, o, PL::freq(p), i0)[col] = v; };
   fstage<N, R1, R2 * R3, B, INV, false>(1, bact, tw, ldg, sts);
   __syncthreads();
   if constexpr (R3 > 1) {
@@ -139,13 +139,15 @@ static int launch_line(bool inverse, const double2* src, double2* dst, const Dmk
   const long long grid = (long long)tiles0 * n_outer;
   if (grid > 0x7fffffffLL) { dmk_set_error("line pass grid too large"); return DMK_ERR_UNSUPPORTED; }
   int rc;
-  if (inverse) {
-    if ((rc = set_smem(dmk_fast_line_kernel<PL, KT, true, NT, MINB>, smem))) return rc;
-    dmk_fast_line_kernel<PL, KT, true, NT, MINB><<<(int)grid, NT, smem, st>>>(src, dst, pl.tw, ms, md, n0, tiles0, ps);
-  } else {
-    if ((rc = set_smem(dmk_fast_line_kernel<PL, KT, false, NT, MINB>, smem))) return rc;
-    dmk_fast_line_kernel<PL, KT, false, NT, MINB><<<(int)grid, NT, smem, st>>>(src, dst, pl.tw, ms, md, n0, tiles0, ps);
-  }
+  // REMOTE (fused exchange over peer memory) is a compile-time variant: the single-GPU passes must not pay for the branch
+#define DMK_LINE_LAUNCH(INV_, REM_)                                                                                          \
+  do {                                                                                                                       \
+    if ((rc = set_smem(dmk_fast_line_kernel<PL, KT, INV_, NT, MINB, REM_>, smem))) return rc;                               \
+    dmk_fast_line_kernel<PL, KT, INV_, NT, MINB, REM_><<<(int)grid, NT, smem, st>>>(src, dst, pl.tw, ms, md, n0, tiles0, ps); \
+  } while (0)
+  if (inverse) { if (ps.remote) DMK_LINE_LAUNCH(true, true); else DMK_LINE_LAUNCH(true, false); }
+  else { if (ps.remote) DMK_LINE_LAUNCH(false, true); else DMK_LINE_LAUNCH(false, false); }
+#undef DMK_LINE_LAUNCH
   DMK_CUDA_CHECK(cudaGetLastError());
   return DMK_OK;
 }

@@ -119,9 +119,10 @@ __device__ __forceinline__ long long dmk_line_rec_fast(const DmkLineMap& m, bool
 }
 
 // where the last stage of a strided pass stores line position `line`: own buffer, or a peer's (DmkPeerStore)
+template <bool REMOTE>
 __device__ __forceinline__ double2* dmk_line_store_ptr(const DmkLineMap& m, const DmkPeerStore& ps, double2* local, bool nosplit, int o,
                                                        int line, int i0) {
-  if (ps.remote) {
+  if constexpr (REMOTE) {
     const int hi = line / ps.split, lo = line - hi * ps.split;
     return ps.peer[hi] + ((long long)ps.me * ps.hi_stride + o * ps.o_stride + lo * ps.e_stride + i0) * DMK_NC;
   }

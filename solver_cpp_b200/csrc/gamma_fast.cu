@@ -9,7 +9,7 @@
 #include "fft_fast.cuh"
 #include "gamma_point.cuh"
 
-template <class PL, int KT, bool IMAG_XI, int NT, int MINB>
+template <class PL, int KT, bool IMAG_XI, int NT, int MINB, bool REMOTE>
 __global__ void __launch_bounds__(NT, MINB) dmk_fast_gamma_kernel(double2* __restrict__ data, const double2* __restrict__ tw,
                                                             DmkLineMap map, int n0, int tiles0, DmkGammaParams gp,
                                                             const __grid_constant__ DmkPeerStore ps) {
@@ -27,7 +27,7 @@ __global__ void __launch_bounds__(NT, MINB) dmk_fast_gamma_kernel(double2* __res
   auto ldg = [&](int, int p, int col) { return data[dmk_line_rec_fast(map, nosplit, o, p, i0) * DMK_NC + col]; };
   auto lds = [&](int, int p, int col) { return s[p * B + col]; };
   auto sts = [&](int, int p, int col, double2 v) { s[p * B + col] = v; };
-  auto stg = [&](int, int p, int col, double2 v) { dmk_line_store_ptr(map, ps, data, nosplit, o, p, i0)[col] = v; };
+  auto stg = [&](int, int p, int col, double2 v) { dmk_line_store_ptr<REMOTE>(map, ps, data, nosplit, o, p, i0)[col] = v; };
   // ---- forward along z: natural order in HBM -> digit-reversed slots in shared memory
   fstage<N, R1, R2 * R3, B, false, false>(1, bact, tw, ldg, sts);
   __syncthreads();
@@ -98,13 +98,14 @@ static int launch_gamma(double2* data, const DmkFftPlan& pl, DmkLineMap map, int
   const int tiles0 = (n0 + KT - 1) / KT;
   const long long grid = (long long)tiles0 * n_outer;
   if (grid > 0x7fffffffLL) { dmk_set_error("gamma pass grid too large"); return DMK_ERR_UNSUPPORTED; }
-  if (imag_xi) {
-    if (smem > 48 * 1024) DMK_CUDA_CHECK(cudaFuncSetAttribute(dmk_fast_gamma_kernel<PL, KT, true, NT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    dmk_fast_gamma_kernel<PL, KT, true, NT, MINB><<<(int)grid, NT, smem, st>>>(data, pl.tw, map, n0, tiles0, gp, ps);
-  } else {
-    if (smem > 48 * 1024) DMK_CUDA_CHECK(cudaFuncSetAttribute(dmk_fast_gamma_kernel<PL, KT, false, NT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    dmk_fast_gamma_kernel<PL, KT, false, NT, MINB><<<(int)grid, NT, smem, st>>>(data, pl.tw, map, n0, tiles0, gp, ps);
-  }
+#define DMK_GAMMA_LAUNCH(IMAG_, REM_)                                                                                        \
+  do {                                                                                                                       \
+    if (smem > 48 * 1024) DMK_CUDA_CHECK(cudaFuncSetAttribute(dmk_fast_gamma_kernel<PL, KT, IMAG_, NT, MINB, REM_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    dmk_fast_gamma_kernel<PL, KT, IMAG_, NT, MINB, REM_><<<(int)grid, NT, smem, st>>>(data, pl.tw, map, n0, tiles0, gp, ps);  \
+  } while (0)
+  if (imag_xi) { if (ps.remote) DMK_GAMMA_LAUNCH(true, true); else DMK_GAMMA_LAUNCH(true, false); }
+  else { if (ps.remote) DMK_GAMMA_LAUNCH(false, true); else DMK_GAMMA_LAUNCH(false, false); }
+#undef DMK_GAMMA_LAUNCH
   DMK_CUDA_CHECK(cudaGetLastError());
   return DMK_OK;
 }
