@@ -17,6 +17,7 @@ static double* d_real; static double2* d_hat; static DmkFftPlan pl; static int n
 static DmkGammaParams gp;
 static cudaEvent_t e0, e1;
 static const char* g_filter = nullptr;
+static DmkPeerStore g_no_peers = {};        // local stores (no fused exchange)
 
 template <class F> static void timeit(const char* name, F f) {
   if (g_filter && !strstr(name, g_filter)) return;
@@ -38,12 +39,12 @@ template <class F> static void timeit(const char* name, F f) {
 template <class PL, int KT, int NT, int MINB> static void line_y(const char* tag) {
   DmkLineMap m; m.split = n; m.hi_stride = 0; m.o_stride = (long long)n * nxr; m.e_stride = nxr;
   char name[96]; snprintf(name, 96, "y  <%d,%d,%d> KT%d NT%d MINB%d %s", PL::R1, PL::R2, PL::R3, KT, NT, MINB, tag);
-  timeit(name, [&] { launch_line<PL, KT, NT, MINB>(false, d_hat, d_hat, pl, m, m, nxr, n, 0); });
+  timeit(name, [&] { launch_line<PL, KT, NT, MINB>(false, d_hat, d_hat, pl, m, m, nxr, n, 0, g_no_peers); });
 }
 template <class PL, int KT, int NT, int MINB> static void gamma_z(const char* tag) {
   DmkLineMap m; m.split = n; m.hi_stride = 0; m.o_stride = nxr; m.e_stride = (long long)n * nxr;
   char name[96]; snprintf(name, 96, "gz <%d,%d,%d> KT%d NT%d MINB%d %s", PL::R1, PL::R2, PL::R3, KT, NT, MINB, tag);
-  timeit(name, [&] { launch_gamma<PL, KT, NT, MINB>(d_hat, pl, m, nxr, n, gp, 0, true); });
+  timeit(name, [&] { launch_gamma<PL, KT, NT, MINB>(d_hat, pl, m, nxr, n, gp, 0, true, g_no_peers); });
 }
 template <class PL, int NP, int NT, int MINB> static void xr2c(const char* tag) {
   char name[96]; snprintf(name, 96, "xf <%d,%d,%d> NP%d NT%d MINB%d %s", PL::R1, PL::R2, PL::R3, NP, NT, MINB, tag);
