@@ -175,6 +175,7 @@ int dmk_divergence_and_gamma(dmk_ctx* ctx, double* d_field, const double* field_
  * the stores.  *enabled = 0: the grid does not qualify (line lengths), the all-to-all path stays. */
 int dmk_p2p_export(dmk_ctx* ctx, unsigned char* handles128);
 int dmk_p2p_import(dmk_ctx* ctx, const unsigned char* all_handles, int* enabled);
+int dmk_p2p_disable(dmk_ctx* ctx);                                 /* back to the all-to-all callback (collective decision) */
 /* MechBase::base_update_coords (mech_base.cpp:45-154): deformed node and cell-centre coordinates of the local slab from F
  * (device field).  Host outputs x_n[nz_loc+1][ny+1][nx+1][3] and x_p[nz_loc][ny][nx][3] (= the reference's x_n(3,i,j,k),
  * x_p(3,i,j,k), first index fastest). */

@@ -575,3 +575,11 @@ extern "C" int dmk_p2p_import(dmk_ctx* c, const unsigned char* all_handles, int*
   if (enabled) *enabled = 1;
   return DMK_OK;
 }
+
+// back to the all-to-all path (the host side calls this on every rank if any rank could not open its peers' buffers)
+extern "C" int dmk_p2p_disable(dmk_ctx* c) {
+  if (!c) { dmk_set_error("null argument"); return DMK_ERR_ARG; }
+  if (c->p2p) for (int p = 0; p < c->P; p++) if (p != c->rank) { cudaIpcCloseMemHandle(c->peerA[p]); cudaIpcCloseMemHandle(c->peerB[p]); }
+  c->p2p = false;
+  return DMK_OK;
+}

@@ -4,6 +4,7 @@ Names follow /root/reference/src/grid/spectral.h:27-41 and mech_base.h:43-73; ev
 (include/dmk_grid.h).  Fields are torch CUDA tensors of float64 holding the reference's Fortran memory order:
 shape (nz_local, ny, nx, 9) with component c = i + 3*j, i.e. natural[..., i, j] == tensor[..., i + 3*j]."""
 import ctypes as C
+import sys
 
 import numpy as np
 import torch
@@ -215,14 +216,28 @@ class GridContext:
         """all-gathers the CUDA IPC handles of every rank's spectral buffers and switches the distributed FFT's transposes to
         stores over peer memory inside the y / z passes (dmk_p2p_import).  Returns True if the fused path is on."""
         import torch.distributed as dist
+        ok, on = 1, C.c_int(0)
         mine = (C.c_ubyte * 128)()
-        L.check(self.lib.dmk_p2p_export(self.ctx, mine))
+        try:
+            L.check(self.lib.dmk_p2p_export(self.ctx, mine))
+        except L.DmkError:
+            ok = 0
         t = torch.tensor(list(bytes(mine)), dtype=torch.uint8, device=self.device)
         out = torch.empty(128 * self.world_size, dtype=torch.uint8, device=self.device)
         dist.all_gather_into_tensor(out, t, group=group)
-        allh = (C.c_ubyte * (128 * self.world_size))(*out.cpu().tolist())
-        on = C.c_int(0)
-        L.check(self.lib.dmk_p2p_import(self.ctx, allh, C.byref(on)))
+        if ok:
+            allh = (C.c_ubyte * (128 * self.world_size))(*out.cpu().tolist())
+            try:
+                L.check(self.lib.dmk_p2p_import(self.ctx, allh, C.byref(on)))
+            except L.DmkError as e:                    # e.g. CUDA IPC not permitted in this environment
+                sys.stderr.write('solver_cpp_b200: fused exchange unavailable (%s); using the all-to-all path\n' % e)
+                ok = 0
+        # the path is a collective property: every rank on the fused exchange, or none
+        flag = torch.tensor([1.0 if (ok and on.value) else 0.0], device=self.device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+        if flag.item() == 0.0:
+            L.check(self.lib.dmk_p2p_disable(self.ctx))
+            on = C.c_int(0)
         self.fused_exchange = bool(on.value)
         return self.fused_exchange
 
