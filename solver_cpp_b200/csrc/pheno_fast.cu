@@ -49,12 +49,12 @@ static int defer_setting() {
   return v < 0 ? 0 : v;
 }
 
-// DMK_PHENO_UNROLL=<1|2|3|4|12>: unroll factor of the slip-system loops inside the Newton iteration.  Default 2: unrolled
-// 12-fold the kernels are instruction-fetch bound (ncu: no_instruction the top stall, 57 % instruction-cache hit rate;
-// 128^3 solver iterate 31.3 ms against 28.1 ms rolled); 2 adds a little instruction-level parallelism to the rolled
-// loops (25.0 against 25.9 ms), profiles/r01_summary.md
+// DMK_PHENO_UNROLL=<1|2|3|4|12>: unroll factor of the slip-system loops inside the Newton iteration.  Default 1 (rolled):
+// the kernels are instruction-fetch sensitive -- unrolled 12-fold `no_instruction` was the top stall at a 57 %
+// instruction-cache hit rate (128^3 solver iterate 31.3 ms against 28.1 ms rolled); with the three-way vote 1 beats 2
+// (21.1 against 21.6 ms), profiles/r01_summary.md
 static int unroll_setting() {
-  static const int v = [] { const char* e = getenv("DMK_PHENO_UNROLL"); return e ? atoi(e) : 2; }();
+  static const int v = [] { const char* e = getenv("DMK_PHENO_UNROLL"); return e ? atoi(e) : 1; }();
   return v;
 }
 
@@ -266,6 +266,7 @@ int dmk_points_pheno_fast(dmk_ctx* c, int ph, const DmkNumDev& nd, const double*
     *deferred = true;
 #define DMK_PL_LAUNCH(NEXP_)                                                                                   \
   (vote3_setting() && u == 2) ? launch_pheno_lanes<12, NEXP_, 2, true>(c, pa, ph, d, nd, d_F, d_P, step, dt)  \
+  : (vote3_setting() && u == 1) ? launch_pheno_lanes<12, NEXP_, 1, true>(c, pa, ph, d, nd, d_F, d_P, step, dt) \
   :                                                                                                            \
   (u == 2)    ? launch_pheno_lanes<12, NEXP_, 2>(c, pa, ph, d, nd, d_F, d_P, step, dt)                         \
   : (u == 3)  ? launch_pheno_lanes<12, NEXP_, 3>(c, pa, ph, d, nd, d_F, d_P, step, dt)                         \
