@@ -53,6 +53,7 @@ typedef struct {
   int N_iter_state_max, N_iter_Lp_max;
   double r_linesearch_Lp, eps_rel_Lp, eps_abs_Lp;
   int f_update_jacobi_Lp;
+  int integrator_state;       /* 0 FPI (default), 1 Euler, 2 AdaptiveEuler, 3 RK4, 4 RKCK45 (phase_mechanical.f90:310-323) */
   int itmin, itmax, update_gamma;
   double eps_abs_div, eps_rel_div, eps_abs_P, eps_rel_P;
 } dmk_numerics;

@@ -648,6 +648,84 @@ static int integrateStateFPI(pt_t *p, const double *F, const double *Fp0, const 
   return broken;
 }
 
+/* ------------------------------------------------------------------ the other state integrators; return broken */
+static int state_converged(const pt_t *p, const double *r, int n) {                 /* phase.f90:626-638 */
+  for (int i = 0; i < n; i++) if (!(fabs(r[i]) <= fmax(p->ph->atol[i], p->num->eps_rel_state * fabs(p->state[i])))) return 0;
+  return 1;
+}
+/* integrateStateEuler, phase_mechanical.f90:699-735 (plastic_deltaState: .false. for the laws restated here) */
+static int integrateStateEuler(pt_t *p, const double *F, const double *Fp0, const double *Fi0, const double *state0, double dt, orc_counters_t *cnt) {
+  int n = p->ph->n_state; double dot[ORC_MAX_STATE]; memset(dot, 0, sizeof dot);
+  dotState(p, dot);
+  if (any_nan(dot, n)) return 1;
+  for (int i = 0; i < n; i++) p->state[i] = state0[i] + dot[i] * dt;
+  return integrateStress(p, F, Fp0, Fi0, dt, cnt);
+}
+/* integrateStateAdaptiveEuler, :738-787 */
+static int integrateStateAdaptiveEuler(pt_t *p, const double *F, const double *Fp0, const double *Fi0, const double *state0, double dt, orc_counters_t *cnt) {
+  int n = p->ph->n_state; double dot[ORC_MAX_STATE], r[ORC_MAX_STATE]; memset(dot, 0, sizeof dot);
+  dotState(p, dot);
+  if (any_nan(dot, n)) return 1;
+  for (int i = 0; i < n; i++) { r[i] = -dot[i] * 0.5 * dt; p->state[i] = state0[i] + dot[i] * dt; }
+  if (integrateStress(p, F, Fp0, Fi0, dt, cnt)) return 1;
+  dotState(p, dot);
+  if (any_nan(dot, n)) return 1;
+  for (int i = 0; i < n; i++) r[i] = r[i] + 0.5 * dot[i] * dt;
+  return !state_converged(p, r, n);
+}
+/* integrateStateRK, :862-932: explicit Runge-Kutta with Butcher tableau A (ns x ns, A[stage][n]), weights B (ns + 1),
+   nodes C (ns), optional embedded error weights DB (ns + 1).  NB the stage deformation gradient is F_0 + (F - F_0) dt C(stage)
+   -- times dt, as the reference has it (:902). */
+static int integrateStateRK(pt_t *p, const double *F_0, const double *F, const double *Fp0, const double *Fi0, const double *state0,
+                            double dt, orc_counters_t *cnt, int ns, const double *A, const double *B, const double *C, const double *DB) {
+  int n = p->ph->n_state; double dot[ORC_MAX_STATE], rk[6][ORC_MAX_STATE], Fs[9];
+  int broken = 1;
+  memset(dot, 0, sizeof dot);
+  dotState(p, dot);
+  if (any_nan(dot, n)) return 1;
+  for (int stage = 0; stage < ns; stage++) {
+    memcpy(rk[stage], dot, sizeof(double) * n);
+    for (int i = 0; i < n; i++) dot[i] = A[stage * ns + 0] * rk[0][i];
+    for (int m = 1; m <= stage; m++) for (int i = 0; i < n; i++) dot[i] += A[stage * ns + m] * rk[m][i];
+    for (int i = 0; i < n; i++) p->state[i] = state0[i] + dot[i] * dt;
+    for (int a = 0; a < 9; a++) Fs[a] = F_0[a] + (F[a] - F_0[a]) * dt * C[stage];
+    broken = integrateStress(p, Fs, Fp0, Fi0, dt * C[stage], cnt);
+    if (broken) break;
+    dotState(p, dot);
+    if (any_nan(dot, n)) break;
+  }
+  if (broken) return 1;
+  memcpy(rk[ns], dot, sizeof(double) * n);
+  for (int i = 0; i < n; i++) { double s = 0.0; for (int m = 0; m <= ns; m++) s += rk[m][i] * B[m]; dot[i] = s; }
+  for (int i = 0; i < n; i++) p->state[i] = state0[i] + dot[i] * dt;
+  if (DB) {
+    double r[ORC_MAX_STATE];
+    for (int i = 0; i < n; i++) { double s = 0.0; for (int m = 0; m <= ns; m++) s += rk[m][i] * DB[m]; r[i] = s * dt; }
+    if (!state_converged(p, r, n)) return 1;
+  }
+  return integrateStress(p, F, Fp0, Fi0, dt, cnt);
+}
+static const double RK4_A[9] = {0.5, 0, 0,  0, 0.5, 0,  0, 0, 1.0};
+static const double RK4_C[3] = {0.5, 0.5, 1.0};
+static const double RK4_B[4] = {1.0 / 6.0, 1.0 / 3.0, 1.0 / 3.0, 1.0 / 6.0};
+static const double CK_A[25] = {1. / 5., 0, 0, 0, 0,   3. / 40., 9. / 40., 0, 0, 0,   3. / 10., -9. / 10., 6. / 5., 0, 0,
+                                -11. / 54., 5. / 2., -70. / 27., 35. / 27., 0,
+                                1631. / 55296., 175. / 512., 575. / 13824., 44275. / 110592., 253. / 4096.};
+static const double CK_C[5] = {0.2, 0.3, 0.6, 1.0, 0.875};
+static const double CK_B[6] = {37. / 378., 0, 250. / 621., 125. / 594., 0, 512. / 1771.};
+static const double CK_DB[6] = {37. / 378. - 2825. / 27648., 0, 250. / 621. - 18575. / 48384., 125. / 594. - 13525. / 55296.,
+                                0 - 277. / 14336., 512. / 1771. - 1. / 4.};
+static int integrateState(pt_t *p, const double *F_0, const double *F, const double *Fp0, const double *Fi0, const double *state0,
+                          double dt, orc_counters_t *cnt) {
+  switch (p->num->integrator_state) {
+    case 1: return integrateStateEuler(p, F, Fp0, Fi0, state0, dt, cnt);
+    case 2: return integrateStateAdaptiveEuler(p, F, Fp0, Fi0, state0, dt, cnt);
+    case 3: return integrateStateRK(p, F_0, F, Fp0, Fi0, state0, dt, cnt, 3, RK4_A, RK4_B, RK4_C, NULL);
+    case 4: return integrateStateRK(p, F_0, F, Fp0, Fi0, state0, dt, cnt, 5, CK_A, CK_B, CK_C, CK_DB);
+    default: return integrateStateFPI(p, F, Fp0, Fi0, state0, dt, cnt);
+  }
+}
+
 /* ------------------------------------------------------------------ phase_mechanical_constitutive; returns converged */
 static int constitutive(pt_t *p, double Dt, orc_counters_t *cnt) {
   const orc_phase_t *ph = p->ph; const orc_num_t *num = p->num; int ns = ph->n_state;
@@ -676,7 +754,7 @@ static int constitutive(pt_t *p, double Dt, orc_counters_t *cnt) {
     if (todo) {
       cnt->n_substeps++;
       for (int a = 0; a < 9; a++) F[a] = F0[a] + step * (p->F[a] - p->F0[a]);
-      converged = !integrateStateFPI(p, F, Fp0, Fi0, state0, step * Dt, cnt);
+      converged = !integrateState(p, F0, F, Fp0, Fi0, state0, step * Dt, cnt);
     }
   }
   return converged;

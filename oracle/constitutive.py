@@ -28,6 +28,9 @@ NUMERICS_DEFAULTS = dict(r_cutback_min=1.0e-3, r_cutback=0.25, r_increase=1.5, e
                          eps_rel_Li=None, eps_abs_Li=None, f_update_jacobi_Li=None)
 
 
+INTEGRATORS = {'FPI': 0, 'Euler': 1, 'AdaptiveEuler': 2, 'RK4': 3, 'RKCK45': 4}
+
+
 def make_numerics(num_phase_mech=None):
     """num_phase_mech: the `phase: mechanical:` dict of numerics.yaml (may be None)."""
     d = dict(NUMERICS_DEFAULTS)
@@ -49,8 +52,7 @@ def make_numerics(num_phase_mech=None):
         d['eps_abs_Li'] = d['eps_abs_Lp']
     if d['f_update_jacobi_Li'] is None:
         d['f_update_jacobi_Li'] = d['f_update_jacobi_Lp']
-    if pl.get('integrator_state', 'FPI') != 'FPI':
-        raise NotImplementedError('only the FPI state integrator is restated')
+    d['integrator_state'] = INTEGRATORS[pl.get('integrator_state', 'FPI')]
     n = Numerics()
     for k, v in d.items():
         setattr(n, k, v)

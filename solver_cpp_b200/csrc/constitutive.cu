@@ -232,6 +232,7 @@ static DmkNumDev num_dev(const dmk_numerics& n) {
   d.r_cutback_min = n.r_cutback_min; d.r_cutback = n.r_cutback; d.r_increase = n.r_increase; d.eps_rel_state = n.eps_rel_state;
   d.N_iter_state_max = n.N_iter_state_max; d.N_iter_Lp_max = n.N_iter_Lp_max; d.r_linesearch_Lp = n.r_linesearch_Lp;
   d.eps_rel_Lp = n.eps_rel_Lp; d.eps_abs_Lp = n.eps_abs_Lp; d.f_update_jacobi_Lp = n.f_update_jacobi_Lp > 0 ? n.f_update_jacobi_Lp : 1;
+  d.integrator = n.integrator_state;
   return d;
 }
 
@@ -281,13 +282,14 @@ int dmk_points_constitutive(dmk_ctx* c, const double* d_F, double* d_P, double d
   DmkPointArrays& pa = *c->pts;
   const DmkNumDev nd = num_dev(c->num);
   // two formulations of the same arithmetic (bit-identical, tests/host_twin): lane-persistent state machine | nested loops
-  static const bool use_machine = [] { const char* e = getenv("DMK_CONSTITUTIVE"); return e && std::string(e) == "machine"; }();
+  static const bool want_machine = [] { const char* e = getenv("DMK_CONSTITUTIVE"); return e && std::string(e) == "machine"; }();
+  const bool use_machine = want_machine && nd.integrator == DMK_INTEG_FPI;     // the lane machine walks the FPI loop only
   static const bool use_generic = [] { const char* e = getenv("DMK_CONSTITUTIVE"); return e && (std::string(e) == "generic" || std::string(e) == "machine"); }();
   for (int ph = 0; ph < pa.n_phases; ph++) {
     if (pa.n_cells_of_phase[ph] == 0) continue;
     const int law = pa.law_of_phase[ph], nst = pa.nstate_of_phase[ph];
     bool handled = false, deferred = false;
-    if (!use_generic) { int rc = dmk_points_pheno_fast(c, ph, nd, d_F, d_P, dt, &handled, &deferred); if (rc) return rc; }
+    if (!use_generic && nd.integrator == DMK_INTEG_FPI) { int rc = dmk_points_pheno_fast(c, ph, nd, d_F, d_P, dt, &handled, &deferred); if (rc) return rc; }
     if (handled) {
       c->launches++;
       if (deferred) {          // second pass over the deferred cells only (count read on the device: no host round trip)

@@ -56,6 +56,7 @@ struct DmkNumDev {
   int N_iter_state_max, N_iter_Lp_max;
   double r_linesearch_Lp, eps_rel_Lp, eps_abs_Lp;
   int f_update_jacobi_Lp;
+  int integrator;                      // DMK_INTEG_* (constitutive_dev.cuh)
 };
 
 int dmk_points_constitutive(dmk_ctx* c, const double* d_F, double* d_P, double dt);

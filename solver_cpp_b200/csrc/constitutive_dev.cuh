@@ -716,6 +716,77 @@ DMK_HD __forceinline__ bool integrate_state_FPI(DmkPt<LAW, NS, ND>& p, const Dmk
   return broken;
 }
 
+// ------------------------------------------------------------------------------------------------ the other state integrators
+// integrateStateEuler / AdaptiveEuler / RK4 / RKCK45 (phase_mechanical.f90:699-932; numerics `integrator_state`).  Kept out
+// of line: FPI is the default and the only integrator of the benchmark configurations.  Returns broken.
+#define DMK_INTEG_FPI 0
+#define DMK_INTEG_EULER 1
+#define DMK_INTEG_ADAPTIVE_EULER 2
+#define DMK_INTEG_RK4 3
+#define DMK_INTEG_RKCK45 4
+template <int LAW, int NS, int ND>
+DMK_HD __noinline__ bool integrate_state_other(DmkPt<LAW, NS, ND>& p, const DmkNumDev& num, const double (&F_0)[9], const double (&F)[9],
+                                               const double (&Fp0)[9], const double* __restrict__ state0, double dt, DmkCnt& cnt) {
+  constexpr int NSX = NS > 0 ? NS : 1;
+  const int n = p.ph->p.n_state;
+  double dot[NSX];
+  for (int i = 0; i < n; i++) dot[i] = 0.0;
+  dot_state(p, dot);
+  for (int i = 0; i < n; i++) if (isnan(dot[i])) return true;
+  auto converged = [&](const double* r) {                                    // phase.f90:626-638
+    for (int i = 0; i < n; i++) if (!(fabs(r[i]) <= fmax(p.ph->p.atol[i], num.eps_rel_state * fabs(p.st[i])))) return false;
+    return true;
+  };
+  if (num.integrator == DMK_INTEG_EULER || num.integrator == DMK_INTEG_ADAPTIVE_EULER) {
+    double r[NSX];
+    for (int i = 0; i < n; i++) { r[i] = -dot[i] * 0.5 * dt; p.st[i] = state0[i] + dot[i] * dt; }
+    if (integrate_stress(p, num, F, Fp0, dt, cnt)) return true;
+    if (num.integrator == DMK_INTEG_EULER) return false;
+    dot_state(p, dot);
+    for (int i = 0; i < n; i++) if (isnan(dot[i])) return true;
+    for (int i = 0; i < n; i++) r[i] = r[i] + 0.5 * dot[i] * dt;
+    return !converged(r);
+  }
+  // explicit Runge-Kutta (integrateStateRK, :862-932); A[stage][m], nodes C, weights B, embedded error weights DB (RKCK45)
+  const double A4[9] = {0.5, 0, 0, 0, 0.5, 0, 0, 0, 1.0}, C4[3] = {0.5, 0.5, 1.0}, B4[4] = {1.0 / 6.0, 1.0 / 3.0, 1.0 / 3.0, 1.0 / 6.0};
+  const double A5[25] = {1. / 5., 0, 0, 0, 0, 3. / 40., 9. / 40., 0, 0, 0, 3. / 10., -9. / 10., 6. / 5., 0, 0,
+                         -11. / 54., 5. / 2., -70. / 27., 35. / 27., 0,
+                         1631. / 55296., 175. / 512., 575. / 13824., 44275. / 110592., 253. / 4096.};
+  const double C5[5] = {0.2, 0.3, 0.6, 1.0, 0.875};
+  const double B5[6] = {37. / 378., 0, 250. / 621., 125. / 594., 0, 512. / 1771.};
+  const double DB5[6] = {37. / 378. - 2825. / 27648., 0, 250. / 621. - 18575. / 48384., 125. / 594. - 13525. / 55296.,
+                         0 - 277. / 14336., 512. / 1771. - 1. / 4.};
+  const bool ck = num.integrator == DMK_INTEG_RKCK45;
+  const int ns = ck ? 5 : 3;
+  const double* A = ck ? A5 : A4; const double* C = ck ? C5 : C4; const double* B = ck ? B5 : B4;
+  double rk[6][NSX];
+  bool broken = true;
+  for (int stage = 0; stage < ns; stage++) {
+    for (int i = 0; i < n; i++) { rk[stage][i] = dot[i]; dot[i] = A[stage * ns] * rk[0][i]; }
+    for (int m = 1; m <= stage; m++) for (int i = 0; i < n; i++) dot[i] += A[stage * ns + m] * rk[m][i];
+    for (int i = 0; i < n; i++) p.st[i] = state0[i] + dot[i] * dt;
+    double Fs[9];
+#pragma unroll
+    for (int a = 0; a < 9; a++) Fs[a] = F_0[a] + (F[a] - F_0[a]) * dt * C[stage];      // times dt, as the reference has it (:902)
+    broken = integrate_stress(p, num, Fs, Fp0, dt * C[stage], cnt);
+    if (broken) break;
+    dot_state(p, dot);
+    bool nan = false;
+    for (int i = 0; i < n; i++) nan = nan || isnan(dot[i]);
+    if (nan) break;
+  }
+  if (broken) return true;
+  for (int i = 0; i < n; i++) rk[ns][i] = dot[i];
+  for (int i = 0; i < n; i++) { double s = 0.0; for (int m = 0; m <= ns; m++) s += rk[m][i] * B[m]; dot[i] = s; }
+  for (int i = 0; i < n; i++) p.st[i] = state0[i] + dot[i] * dt;
+  if (ck) {
+    double r[NSX];
+    for (int i = 0; i < n; i++) { double s = 0.0; for (int m = 0; m <= ns; m++) s += rk[m][i] * DB5[m]; r[i] = s * dt; }
+    if (!converged(r)) return true;
+  }
+  return integrate_stress(p, num, F, Fp0, dt, cnt);
+}
+
 // ------------------------------------------------------------------------------------------------ constitutive
 // Integrates one point from its increment-start state (arguments *0) to the target F.  Returns converged.
 template <int LAW, int NS, int ND>
@@ -757,7 +828,8 @@ DMK_HD __forceinline__ bool constitutive_point(DmkPt<LAW, NS, ND>& p, const DmkN
       cnt.substeps++;
 #pragma unroll
       for (int a = 0; a < 9; a++) F[a] = F0[a] + step * (Ftarget[a] - F0in[a]);
-      converged = !integrate_state_FPI(p, num, F, Fp0, state0, step * Dt, cnt);
+      converged = (num.integrator == DMK_INTEG_FPI) ? !integrate_state_FPI(p, num, F, Fp0, state0, step * Dt, cnt)
+                                                     : !integrate_state_other(p, num, F0, F, Fp0, state0, step * Dt, cnt);
     }
   }
   return converged;

@@ -21,7 +21,7 @@ class Numerics(C.Structure):
     _fields_ = [('r_cutback_min', C.c_double), ('r_cutback', C.c_double), ('r_increase', C.c_double),
                 ('eps_rel_state', C.c_double), ('N_iter_state_max', C.c_int), ('N_iter_Lp_max', C.c_int),
                 ('r_linesearch_Lp', C.c_double), ('eps_rel_Lp', C.c_double), ('eps_abs_Lp', C.c_double),
-                ('f_update_jacobi_Lp', C.c_int), ('itmin', C.c_int), ('itmax', C.c_int), ('update_gamma', C.c_int),
+                ('f_update_jacobi_Lp', C.c_int), ('integrator_state', C.c_int), ('itmin', C.c_int), ('itmax', C.c_int), ('update_gamma', C.c_int),
                 ('eps_abs_div', C.c_double), ('eps_rel_div', C.c_double), ('eps_abs_P', C.c_double),
                 ('eps_rel_P', C.c_double)]
 

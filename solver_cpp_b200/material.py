@@ -295,8 +295,12 @@ def make_phase(cfg, T=T_ROOM):
 
 NUMERICS_DEFAULTS = dict(r_cutback_min=1.0e-3, r_cutback=0.25, r_increase=1.5, eps_rel_state=1.0e-6, N_iter_state_max=20,
                          N_iter_Lp_max=40, r_linesearch_Lp=0.5, eps_rel_Lp=1.0e-6, eps_abs_Lp=1.0e-8, f_update_jacobi_Lp=1,
+                         integrator_state=0,
                          itmin=1, itmax=100, update_gamma=0, eps_abs_div=1.0e-4, eps_rel_div=5.0e-4, eps_abs_P=1.0e3,
                          eps_rel_P=1.0e-3)
+
+
+INTEGRATORS = {'FPI': 0, 'Euler': 1, 'AdaptiveEuler': 2, 'RK4': 3, 'RKCK45': 4}
 
 
 def make_numerics(phase_mech=None, grid_mech=None):
@@ -311,8 +315,10 @@ def make_numerics(phase_mech=None, grid_mech=None):
     for k in ('N_iter_Lp_max', 'r_linesearch_Lp', 'eps_rel_Lp', 'eps_abs_Lp', 'f_update_jacobi_Lp'):
         if k in pl:
             d[k] = pl[k]
-    if pl.get('integrator_state', 'FPI') != 'FPI':
-        raise L.DmkError('only the FPI state integrator is offered on the device path')
+    integ = pl.get('integrator_state', 'FPI')
+    if integ not in INTEGRATORS:
+        raise L.DmkError('unknown state integrator %s' % integ)
+    d['integrator_state'] = INTEGRATORS[integ]
     g = dict(grid_mech or {})
     ren = dict(N_iter_min='itmin', N_iter_max='itmax')
     for k, v in g.items():

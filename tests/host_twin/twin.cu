@@ -29,7 +29,7 @@ static int run_point(const DmkDevPhase* ph, const DmkNumDev& num, const double* 
   for (int k = 0; k < ph->n_dep; k++) p.dep[k] = dep[k];
   DmkCnt cnt = {0, 0, 0, 0, 0, 0};
   bool ok;
-  if (g_use_nested) ok = constitutive_point(p, num, f0, ft, fp0, lp0, s0, state0, Dt, cnt);
+  if (g_use_nested || num.integrator != DMK_INTEG_FPI) ok = constitutive_point(p, num, f0, ft, fp0, lp0, s0, state0, Dt, cnt);
   else {
     for (int a = 0; a < 9; a++) { mach.Ft[a] = Ft[a]; mach.F0in[a] = F0[a]; mach.Fp0[a] = Fp0[a]; mach.Lp0[a] = Lp0[a]; }
     for (int a = 0; a < 6; a++) mach.S0in[a] = S0[a];
@@ -111,9 +111,10 @@ extern "C" int twin_point(const dmk_phase* phase, const dmk_numerics* n, const d
   nd.r_cutback_min = n->r_cutback_min; nd.r_cutback = n->r_cutback; nd.r_increase = n->r_increase; nd.eps_rel_state = n->eps_rel_state;
   nd.N_iter_state_max = n->N_iter_state_max; nd.N_iter_Lp_max = n->N_iter_Lp_max; nd.r_linesearch_Lp = n->r_linesearch_Lp;
   nd.eps_rel_Lp = n->eps_rel_Lp; nd.eps_abs_Lp = n->eps_abs_Lp; nd.f_update_jacobi_Lp = n->f_update_jacobi_Lp > 0 ? n->f_update_jacobi_Lp : 1;
+  nd.integrator = n->integrator_state;
   int nexp = 0;
   g_last_deferred = 0;
-  if (g_use_fast && dmk_pheno_fast_eligible(d, 12, &nexp)) {
+  if (g_use_fast && nd.integrator == DMK_INTEG_FPI && dmk_pheno_fast_eligible(d, 12, &nexp)) {
     int ok = (nexp == 20) ? run_point_fast<12, 20>(&d, nd, F0, Ft, Fp0, Lp0, Lp, S0, state0, Dt, P, Fp, Fe, S, state, cnt)
                           : run_point_fast<12, 0>(&d, nd, F0, Ft, Fp0, Lp0, Lp, S0, state0, Dt, P, Fp, Fe, S, state, cnt);
     if (ok == 2) { g_last_deferred = 1; goto generic; }

