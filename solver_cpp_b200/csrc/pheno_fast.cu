@@ -87,10 +87,10 @@ static int launch_pheno_fast(dmk_ctx* c, DmkPointArrays& pa, int ph, const DmkDe
 #define DMK_PL_MINBLOCKS 4
 #endif
 #define DMK_PL_CHUNK 256
-template <int NSL, int NEXP, int UNR, bool VOTE3>
+template <int NSL, int NEXP, int UNR, bool VOTE3, bool CUTBACK>
 __global__ void __launch_bounds__(DMK_PL_THREADS, DMK_PL_MINBLOCKS)
 dmk_pheno_lanes_kernel(const __grid_constant__ DmkPhenoK<NSL> K, DmkPointArrays pa, int phase, DmkNumDev num,
-                       const double* __restrict__ Fin, double* __restrict__ Pout, double step, double dt, long long cell_begin,
+                       const double* __restrict__ Fin, double* __restrict__ Pout, double Dt, long long cell_begin,
                        long long cell_end, int3 vw) {
   // cells [cell_begin, cell_end) are this launch's share (whole slab, or one staged z-chunk); *pa.d_work counts from 0
   extern __shared__ double pf_sm[];
@@ -100,28 +100,32 @@ dmk_pheno_lanes_kernel(const __grid_constant__ DmkPhenoK<NSL> K, DmkPointArrays 
   L.mode = PL_NEED;
   long long c_next = 0, c_end = 0;                      // the warp's current chunk (warp-uniform)
   bool drained = false;
-  unsigned n_Lp = 0, n_calls = 0, n_pts = 0, n_defer = 0;
+  unsigned n_Lp = 0, n_calls = 0, n_sub = 0, n_cut = 0, n_ill = 0, n_defer = 0;
   unsigned t_lp = 0, l_lp = 0, t_sb = 0, l_sb = 0, t_rf = 0, l_rf = 0;     // schedule statistics (lane 0: warp totals)
   double S[6];
+  auto fail = [&]() { L.ok = false; L.mode = PL_RESTART; };               // the running sub-step is cut back
+  auto done = [&](bool ill) {
+    n_Lp += L.nLp_pt; n_calls += L.calls_pt; n_sub += L.nsub; n_cut += L.ncut; n_ill += ill ? 1u : 0u;
+    L.mode = PL_NEED;
+  };
   for (;;) {
-    // ---- vote: a trip runs EITHER one Newton iteration OR refill + state block, whichever has more lanes waiting for it.
-    // Running both every trip left 12.8 of 32 lanes active per instruction (ncu, profiles/r01_summary.md): the state
-    // block and the refill were executed for the few lanes that needed them at that moment.  Waiting lanes accumulate
-    // until they are the majority, go through their block together and then iterate in step.
+    // ---- vote: a trip runs ONE block -- the Newton residual, the Newton step, or refill + sub-step set-up + state block --
+    // whichever has most lanes waiting for it (weights vw).  Running everything every trip left 12.8 of 32 lanes active per
+    // instruction (ncu, profiles/r01_summary.md): the state block and the refill were executed for the few lanes that needed
+    // them at that moment.  Waiting lanes accumulate until their block wins, go through it together and then iterate in step.
     const unsigned bL = __ballot_sync(FULL, L.mode == PL_LP);
     const unsigned bN = VOTE3 ? __ballot_sync(FULL, L.mode == PL_NEWTON) : 0u;
-    const unsigned bS = __ballot_sync(FULL, L.mode == PL_INIT || L.mode == PL_CONV);
+    const unsigned bS = __ballot_sync(FULL, L.mode == PL_INIT || L.mode == PL_CONV || L.mode == PL_RESTART);
     unsigned need = drained ? 0u : __ballot_sync(FULL, L.mode == PL_NEED);
     if (!(bL | bN | bS | need)) break;
     if constexpr (VOTE3) {
-      // three-way vote: the Newton step runs only for the lanes whose residual test failed (2/3 of the Newton lanes), so
-      // it is a block of its own in which such lanes accumulate
+      // the Newton step runs only for the lanes whose residual test failed (2/3 of the Newton lanes), so it is a block of
+      // its own in which such lanes accumulate
       const int cL = vw.x * __popc(bL), cN = vw.y * __popc(bN), cS = vw.z * (__popc(bS) + __popc(need));
       if (cN >= cL && cN >= cS) {
         t_lp++; l_lp += __popc(bN);
         if (L.mode == PL_NEWTON) {
-          const int rc = pl_newton<NSL, UNR>(K, dt, scr, L);
-          if (rc == PL_DEFER) { pa.defer_list[atomicAdd(pa.d_defer_count, 1u)] = (int)L.i; n_defer++; L.mode = PL_NEED; }
+          if (pl_newton<NSL, UNR>(K, scr, L) == PL_FAIL) { L.nLp_pt += (unsigned)L.nLp; fail(); }
           else L.mode = PL_LP;
         }
         continue;
@@ -129,24 +133,23 @@ dmk_pheno_lanes_kernel(const __grid_constant__ DmkPhenoK<NSL> K, DmkPointArrays 
       if (cL >= cS) {
         t_lp++; l_lp += __popc(bL);
         if (L.mode == PL_LP) {
-          const int rc = pl_residual<NSL, NEXP, UNR>(K, num, dt, scr, L);
+          const int rc = pl_residual<NSL, NEXP, UNR>(K, num, scr, L);
           if (rc == PL_DONE) L.mode = PL_CONV;
           else if (rc == PL_STEP) L.mode = PL_NEWTON;
-          else if (rc == PL_DEFER) { pa.defer_list[atomicAdd(pa.d_defer_count, 1u)] = (int)L.i; n_defer++; L.mode = PL_NEED; }
+          else if (rc == PL_FAIL) { L.nLp_pt += (unsigned)L.nLp; fail(); }
         }
         continue;
       }
     } else if (__popc(bL) >= __popc(bS) + __popc(need)) {
-      // ---- one Newton iteration
       t_lp++; l_lp += __popc(bL);
       if (L.mode == PL_LP) {
-        const int rc = pl_lp_iteration<NSL, NEXP, UNR>(K, num, dt, scr, L);
+        const int rc = pl_lp_iteration<NSL, NEXP, UNR>(K, num, scr, L);
         if (rc == PL_DONE) L.mode = PL_CONV;
-        else if (rc == PL_DEFER) { pa.defer_list[atomicAdd(pa.d_defer_count, 1u)] = (int)L.i; n_defer++; L.mode = PL_NEED; }
+        else if (rc == PL_FAIL) { L.nLp_pt += (unsigned)L.nLp; fail(); }
       }
       continue;
     }
-    // ---- refill
+    // ---- refill: lanes without a point take the next cell of the warp's chunk
     if (need) { t_rf++; l_rf += __popc(need); }
     while (need) {
       if (c_next >= c_end) {
@@ -161,35 +164,39 @@ dmk_pheno_lanes_kernel(const __grid_constant__ DmkPhenoK<NSL> K, DmkPointArrays 
       const int rank = __popc(need & lt);
       if (L.mode == PL_NEED && rank < avail) {
         const long long i = c_next + rank;
-        if (pa.phase[i] == phase) {
-          if (pl_begin<NSL>(pa, i, Fin, step, scr, L, S)) L.mode = PL_INIT;
-          else { pa.defer_list[atomicAdd(pa.d_defer_count, 1u)] = (int)i; n_defer++; }
-        }
+        if (pa.phase[i] == phase) { pl_fetch<NSL>(pa, num, i, L); L.mode = PL_RESTART; }
       }
       c_next += min(__popc(need), avail);
       need = __ballot_sync(FULL, L.mode == PL_NEED);
+    }
+    // ---- sub-step set-up (first, next or cut-back sub-step of the lane's point)
+    if (L.mode == PL_RESTART) {
+      const int rc = pl_substep_begin<NSL, CUTBACK>(num, pa, Fin, Pout, Dt, scr, L, S);
+      if (rc == PL_CONTINUE) L.mode = PL_INIT;
+      else if (rc == PL_ILL) done(true);
+      else if (rc == PL_GIVEUP) { pa.defer_list[atomicAdd(pa.d_defer_count, 1u)] = (int)L.i; n_defer++; L.mode = PL_NEED; }
+      // PL_FAIL: stays in PL_RESTART with ok = false: cut back on the next visit
     }
     // ---- state block
     const unsigned group = __ballot_sync(FULL, L.mode == PL_INIT || L.mode == PL_CONV);
     t_sb++; l_sb += __popc(group);
     if (L.mode == PL_INIT || L.mode == PL_CONV) {
-      const int rc = pl_state_block<NSL, NEXP>(K, num, pa, Fin, Pout, dt, scr, L, S, L.mode == PL_INIT, group);
+      const int rc = pl_state_block<NSL, NEXP, CUTBACK>(K, num, pa, Fin, Pout, scr, L, S, L.mode == PL_INIT, group);
       if (rc == PL_CONTINUE) L.mode = PL_LP;
-      else {
-        if (rc == PL_DONE) { n_Lp += L.nLp_pt; n_calls += (unsigned)L.it; n_pts++; }
-        else { pa.defer_list[atomicAdd(pa.d_defer_count, 1u)] = (int)L.i; n_defer++; }
-        L.mode = PL_NEED;
-      }
+      else if (rc == PL_RESTART) L.mode = PL_RESTART;
+      else if (rc == PL_DONE) done(false);
+      else fail();
     }
   }
   // counters (d_counters: Lp, Li, stress calls, state iterations, sub-steps, cut-backs, ill, deferred)
-  unsigned v[8] = {n_Lp, n_calls, n_calls, n_calls, n_pts, 0u, 0u, n_defer};
+  unsigned v[8] = {n_Lp, n_calls, n_calls, n_calls, n_sub, n_cut, n_ill, n_defer};
 #pragma unroll
   for (int k = 0; k < 8; k++) {
     unsigned s = v[k];
     for (int off = 16; off > 0; off >>= 1) s += __shfl_down_sync(FULL, s, off);
     if (lane == 0 && s) atomicAdd(&pa.d_counters[k], (unsigned long long)s);
   }
+  if (n_ill) atomicOr(pa.d_ill, 1);
   if (lane == 0) {
     const unsigned w[6] = {t_lp, l_lp, t_sb, l_sb, t_rf, l_rf};
 #pragma unroll
@@ -211,25 +218,32 @@ static int3 vote_weights() {
   return v;
 }
 
+// DMK_PHENO_CUTBACK=lanes: failed sub-steps are cut back in-lane (pheno_lanes_dev.cuh) instead of being handed to the
+// reference-order kernel (default)
+static bool cutback_setting() {
+  static const bool v = [] { const char* e = getenv("DMK_PHENO_CUTBACK"); return e && std::string(e) == "lanes"; }();
+  return v;
+}
+
 // DMK_PHENO_SCHEDULE=nested: one thread walks one point through the nested loops (dmk_pheno_fast_kernel); default: lanes
 static bool lanes_setting() {
   static const bool v = [] { const char* e = getenv("DMK_PHENO_SCHEDULE"); return !(e && std::string(e) == "nested"); }();
   return v;
 }
 
-template <int NSL, int NEXP, int UNR, bool VOTE3 = false>
+template <int NSL, int NEXP, int UNR, bool VOTE3, bool CUTBACK>
 static int launch_pheno_lanes(dmk_ctx* c, DmkPointArrays& pa, int ph, const DmkDevPhase& d, const DmkNumDev& nd, const double* d_F,
-                              double* d_P, double step, double dt) {
+                              double* d_P, double dt) {
   DmkPhenoK<NSL> K;
   dmk_pheno_fast_tables<NSL>(d, K);
   const size_t smem = (size_t)PfOff<NSL>::TOTAL * DMK_PL_THREADS * sizeof(double);
   static int grid = 0;
   if (!grid) {
-    DMK_CUDA_CHECK(cudaFuncSetAttribute(dmk_pheno_lanes_kernel<NSL, NEXP, UNR, VOTE3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    DMK_CUDA_CHECK(cudaFuncSetAttribute(dmk_pheno_lanes_kernel<NSL, NEXP, UNR, VOTE3, CUTBACK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int dev = 0, sms = 148, occ = 1;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, dmk_pheno_lanes_kernel<NSL, NEXP, UNR, VOTE3>, DMK_PL_THREADS, smem) != cudaSuccess || occ < 1) occ = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, dmk_pheno_lanes_kernel<NSL, NEXP, UNR, VOTE3, CUTBACK>, DMK_PL_THREADS, smem) != cudaSuccess || occ < 1) occ = 1;
     grid = sms * occ;                                  // one resident wave
   }
   DMK_CUDA_CHECK(cudaMemsetAsync(pa.d_defer_count, 0, sizeof(unsigned), c->stream));
@@ -244,7 +258,7 @@ static int launch_pheno_lanes(dmk_ctx* c, DmkPointArrays& pa, int ph, const DmkD
     DMK_CUDA_CHECK(cudaMemsetAsync(pa.d_work, 0, sizeof(unsigned long long), c->stream));
     const long long warps_needed = (end - first + 31) / 32;
     const int g = (int)std::max(1LL, std::min((long long)grid, (warps_needed + 1) / 2));
-    dmk_pheno_lanes_kernel<NSL, NEXP, UNR, VOTE3><<<g, DMK_PL_THREADS, smem, c->stream>>>(K, pa, ph, nd, d_F, d_P, step, step * dt, first, end, vote_weights());
+    dmk_pheno_lanes_kernel<NSL, NEXP, UNR, VOTE3, CUTBACK><<<g, DMK_PL_THREADS, smem, c->stream>>>(K, pa, ph, nd, d_F, d_P, dt, first, end, vote_weights());
     if (k > 0) c->launches++;
   }
   return DMK_OK;
@@ -261,18 +275,17 @@ int dmk_points_pheno_fast(dmk_ctx* c, int ph, const DmkNumDev& nd, const double*
   const DmkDevPhase& d = pa.h_dev_phases[ph];
   const int u = unroll_setting();
   int rc;
-  double step = 1.0;
-  if (lanes_setting() && dmk_pheno_lanes_eligible(nd, &step)) {
-    *deferred = true;
+  const bool cb = cutback_setting();
+  if (lanes_setting() && dmk_pheno_lanes_eligible(nd, cb)) {
+    *deferred = !cb;                                    // in-lane cut-backs: nothing is handed to the reference-order kernel
 #define DMK_PL_LAUNCH(NEXP_)                                                                                   \
-  (vote3_setting() && u == 2) ? launch_pheno_lanes<12, NEXP_, 2, true>(c, pa, ph, d, nd, d_F, d_P, step, dt)  \
-  : (vote3_setting() && u == 1) ? launch_pheno_lanes<12, NEXP_, 1, true>(c, pa, ph, d, nd, d_F, d_P, step, dt) \
-  :                                                                                                            \
-  (u == 2)    ? launch_pheno_lanes<12, NEXP_, 2>(c, pa, ph, d, nd, d_F, d_P, step, dt)                         \
-  : (u == 3)  ? launch_pheno_lanes<12, NEXP_, 3>(c, pa, ph, d, nd, d_F, d_P, step, dt)                         \
-  : (u == 4)  ? launch_pheno_lanes<12, NEXP_, 4>(c, pa, ph, d, nd, d_F, d_P, step, dt)                         \
-  : (u == 12) ? launch_pheno_lanes<12, NEXP_, 12>(c, pa, ph, d, nd, d_F, d_P, step, dt)                        \
-              : launch_pheno_lanes<12, NEXP_, 1>(c, pa, ph, d, nd, d_F, d_P, step, dt)
+  (cb ? ((u == 2) ? launch_pheno_lanes<12, NEXP_, 2, true, true>(c, pa, ph, d, nd, d_F, d_P, dt)              \
+                  : launch_pheno_lanes<12, NEXP_, 1, true, true>(c, pa, ph, d, nd, d_F, d_P, dt))             \
+      : !vote3_setting() ? launch_pheno_lanes<12, NEXP_, 1, false, false>(c, pa, ph, d, nd, d_F, d_P, dt)     \
+      : (u == 2)  ? launch_pheno_lanes<12, NEXP_, 2, true, false>(c, pa, ph, d, nd, d_F, d_P, dt)             \
+      : (u == 4)  ? launch_pheno_lanes<12, NEXP_, 4, true, false>(c, pa, ph, d, nd, d_F, d_P, dt)             \
+      : (u == 12) ? launch_pheno_lanes<12, NEXP_, 12, true, false>(c, pa, ph, d, nd, d_F, d_P, dt)            \
+                  : launch_pheno_lanes<12, NEXP_, 1, true, false>(c, pa, ph, d, nd, d_F, d_P, dt))
     rc = (nexp == 20) ? (DMK_PL_LAUNCH(20)) : (DMK_PL_LAUNCH(0));
 #undef DMK_PL_LAUNCH
     if (rc) return rc;

@@ -75,8 +75,9 @@ static int run_point_fast(const DmkDevPhase* ph, const DmkNumDev& num, const dou
   DmkScr scr = {scratch, 1};
   DmkCnt cnt = {0, 0, 0, 0, 0, 0};
   int rc;
-  double step = 1.0;
-  if (g_use_fast == 2 && dmk_pheno_lanes_eligible(num, &step)) rc = pl_run_point<NSL, NEXP>(K, num, pa, 0, Frec, Prec, step, Dt, scr, cnt);
+  if (g_use_fast == 2 && dmk_pheno_lanes_eligible(num, g_defer == 0))
+    rc = (g_defer == 0) ? pl_run_point<NSL, NEXP, true>(K, num, pa, 0, Frec, Prec, Dt, scr, cnt)
+                        : pl_run_point<NSL, NEXP, false>(K, num, pa, 0, Frec, Prec, Dt, scr, cnt);
   else rc = pf_point<NSL, NEXP, 1>(K, num, g_defer, pa, 0, Frec, Prec, Dt, scr, cnt);
   if (rc == PF_DEFER) return 2;                       // nothing written: the caller replays the point on the reference-order path
   for (int a = 0; a < 3; a++) for (int b = 0; b < 3; b++) P[3 * a + b] = Prec[a + 3 * b];
