@@ -96,7 +96,7 @@ DMK_HD __forceinline__ int pl_substep_begin(const DmkNumDev& num, const DmkPoint
   const double* Fp0s = sub ? pa.Fp : pa.Fp0;
   if (!L.ok) {
     L.sstep = num.r_cutback * L.sstep;
-    if (L.sstep < 1.0) {
+    if (CUTBACK && L.sstep < 1.0) {                   // (CUTBACK = false: the only sub-step set up here is the full first one)
       L.ncut++;
       const double* Lp0s = sub ? pa.Lp : pa.Lp0;
 #pragma unroll
@@ -109,7 +109,7 @@ DMK_HD __forceinline__ int pl_substep_begin(const DmkNumDev& num, const DmkPoint
 #pragma unroll
       for (int k = 0; k < 2 * NSL; k++) { scr(O::ST + k) = *src; src += n; }
     }
-    if (!(L.sstep > num.r_cutback_min)) {             // terminally ill: what pf_point leaves behind (P of no converged sub-step: 0)
+    if (CUTBACK && !(L.sstep > num.r_cutback_min)) {  // terminally ill: what pf_point leaves behind (P of no converged sub-step: 0)
       pa.cutbacks[i] = (int)L.ncut;
       pa.lp_iter[i] = (int)L.nLp_pt;
 #pragma unroll
