@@ -166,7 +166,7 @@ def run_reference(args):
             'e2e': {'value': v, 'unit': 'cells*evaluations/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
             'note': 'oracle/ = CPU restatement of the reference algorithm (the reference itself cannot be built here: no gfortran/'
                     'MPI/FFTW/PETSc/HDF5); constitutive loop OpenMP over cells, FFT scipy pocketfft with all cores'}
-    print(json.dumps(line))
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm
@@ -331,13 +331,30 @@ def run_ours(args):
         line['cpu_baseline'] = {'value': v, 'unit': 'cells*evaluations/s', 'cores': threads, 'kind': 'port',
                                 'sample': '%dx%dx%d sub-problem of the same workload, same protocol, %.2f s per evaluation'
                                           % (CPU_SAMPLE_CELLS + (sec,))}
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def emit(line):
+    sys.stdout.flush()
+    data = (json.dumps(line) + '\n').encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
-    os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')        # NCCL's banner / warnings go to STDOUT by default, where the one JSON line goes
+    # Libraries (NCCL's version banner, torch) write to file descriptor 1; the contract is ONE JSON line on stdout.  Everything
+    # but that line is sent to stderr: fd 1 is pointed at fd 2 and the line is written to the saved descriptor (emit).
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=5)
