@@ -1,7 +1,7 @@
 """CPU experiment: the register-resident formulation WITH its own line search (host twin, defer off) against the oracle
 on bench.py's kind of state.  Which cells deviate by more than 1e-9, and do they coincide with differing iteration counts?"""
 import os, sys
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, 'tests', 'host_twin'))
 import numpy as np
 import bench, twin
