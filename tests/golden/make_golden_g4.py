@@ -54,6 +54,26 @@ def main_two_phase():
     print({k: v.shape for k, v in out.items()}, sorted(set(label)))
 
 
+def input_decks():
+    """the input files of the two runs, re-written from the reference's own (geometry through solver_cpp_b200/vti.py, YAML through
+    PyYAML): same content, this repo's writers"""
+    import yaml
+    spec2 = importlib.util.spec_from_file_location('dmk_vti', os.path.join(HERE, '..', '..', 'solver_cpp_b200', 'vti.py'))
+    vti = importlib.util.module_from_spec(spec2)
+    spec2.loader.exec_module(vti)
+    R = '/root/reference/python/tests/resources/Result/'
+    for src, dst in (('6grains6x7x8_single_phase.vti', '6grains6x7x8_single_phase.vti'), ('12grains6x7x8.vti', '12grains6x7x8.vti')):
+        g = vti.read_vti(R + src)
+        vti.write_vti(os.path.join(HERE, dst), g['material'], g['size'], g['origin'])
+    for src, dst in (('6grains6x7x8_single_phase.material.yaml', '6grains6x7x8_single_phase.material.yaml'),
+                     ('12grains6x7x8.material.yaml', '12grains6x7x8.material.yaml'), ('tensionY.yaml', '6grains6x7x8_tensionY.load.yaml')):
+        d = yaml.safe_load(open(R + src))
+        with open(os.path.join(HERE, dst), 'w') as f:
+            f.write('# written by tests/golden/make_golden_g4.py from the reference\'s python/tests/resources/Result/%s\n' % src)
+            yaml.safe_dump(d, f, default_flow_style=None, sort_keys=False)
+
+
 if __name__ == '__main__':
+    input_decks()
     main()
     main_two_phase()

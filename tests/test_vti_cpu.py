@@ -1,5 +1,7 @@
-"""CPU tests of the geometry reader / writer (solver_cpp_b200/vti.py) against a file written by upstream DAMASK's own
-tooling (fixture copied from the reference tree: python/tests/resources/Result/6grains6x7x8_single_phase.vti)."""
+"""CPU tests of the geometry reader / writer (solver_cpp_b200/vti.py): a file written by upstream DAMASK's own tooling
+(tests/golden/damask_written_4grains2x4x3.vti, a 741-byte data fixture taken verbatim from the reference tree,
+python/tests/resources/Result/4grains2x4x3.vti: VTK's base64 / zlib block conventions as DAMASK emits them) and the input
+decks of golden set G4, which tests/golden/make_golden_g4.py re-writes with this module's writer."""
 import importlib.util
 import os
 
@@ -12,6 +14,12 @@ _spec.loader.exec_module(vti)          # by path: importing the package would lo
 
 
 def test_reads_a_damask_written_file(golden_dir):
+    d = vti.read_vti(os.path.join(golden_dir, 'damask_written_4grains2x4x3.vti'))
+    assert tuple(d['cells']) == (2, 4, 3) and np.allclose(d['size'], 1.0) and np.allclose(d['origin'], 0.0)
+    assert d['material'].shape == (3, 4, 2) and np.bincount(d['material'].ravel()).tolist() == [6, 11, 2, 5]
+
+
+def test_reads_the_g4_geometry(golden_dir):
     d = vti.read_vti(os.path.join(golden_dir, '6grains6x7x8_single_phase.vti'))
     assert tuple(d['cells']) == (6, 7, 8)
     assert np.allclose(d['size'], (0.75, 0.875, 1.0)) and np.allclose(d['origin'], 0.0)
