@@ -123,11 +123,22 @@ def cpu_evaluations(cells, steps, warmup, threads):
     o.S = osp.masked_compliance(o.C_volAvg, o.params['R'], o.params['stress_mask'])
     X = o.F.reshape(-1).copy()
 
+    split = {'constitutive_s': 0.0, 'spectral_s': 0.0}
+
     def one():
         # residual evaluation without the per-evaluation tangent (the product computes it once per increment, too)
         F = X.reshape(o.shape)
+        tc = time.perf_counter()
         o.con.mechanical_response(F, o.params['dt'])
         P, _ = o.con.mechanical_response2(o.params['dt'], tangent=False)
+        split['constitutive_s'] += time.perf_counter() - tc
+        ts = time.perf_counter()
+        try:
+            return spectral_tail(P)
+        finally:
+            split['spectral_s'] += time.perf_counter() - ts
+
+    def spectral_tail(P):
         P = P.reshape(o.shape)
         P_av = P.sum(axis=(0, 1, 2)) * o.grid.wgt
         hat = osp.fft_forward(P)
@@ -140,10 +151,12 @@ def cpu_evaluations(cells, steps, warmup, threads):
         X -= one().reshape(-1)
     for _ in range(warmup):
         one()
+    split['constitutive_s'] = split['spectral_s'] = 0.0
     t0 = time.perf_counter()
     for _ in range(steps):
         one()
     dt = (time.perf_counter() - t0) / steps
+    cpu_evaluations.split = {k: v / steps for k, v in split.items()}
     return float(np.prod(cells)) / dt, dt
 
 
@@ -162,7 +175,8 @@ def run_reference(args):
             'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
             'config': {'workload': 'C3: 256^3-per-GPU 500-grain phenopowerlaw Cu polycrystal, tensionX; CPU arm on a bounded sample',
                        'cells': list(cells), 'sample_cells': list(CPU_SAMPLE_CELLS)},
-            'cpu_baseline': {'value': v, 'unit': 'cells*evaluations/s', 'cores': threads, 'kind': 'port', 'sample': sample},
+            'cpu_baseline': {'value': v, 'unit': 'cells*evaluations/s', 'cores': threads, 'kind': 'port', 'sample': sample,
+                             'seconds_per_evaluation': dict(cpu_evaluations.split)},
             'e2e': {'value': v, 'unit': 'cells*evaluations/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
             'note': 'oracle/ = CPU restatement of the reference algorithm (the reference itself cannot be built here: no gfortran/'
                     'MPI/FFTW/PETSc/HDF5); constitutive loop OpenMP over cells, FFT scipy pocketfft with all cores'}
@@ -330,7 +344,8 @@ def run_ours(args):
         v, sec = cpu_evaluations(CPU_SAMPLE_CELLS, 3, 1, threads)
         line['cpu_baseline'] = {'value': v, 'unit': 'cells*evaluations/s', 'cores': threads, 'kind': 'port',
                                 'sample': '%dx%dx%d sub-problem of the same workload, same protocol, %.2f s per evaluation'
-                                          % (CPU_SAMPLE_CELLS + (sec,))}
+                                          % (CPU_SAMPLE_CELLS + (sec,)),
+                                'seconds_per_evaluation': dict(cpu_evaluations.split)}
     emit(line)
     if world > 1:
         dist.destroy_process_group()
