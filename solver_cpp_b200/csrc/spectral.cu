@@ -540,6 +540,8 @@ extern "C" int dmk_update_coords(dmk_ctx* c, const double* d_F, double* h_x_n, d
 }
 
 // ------------------------------------------------------------------------------------------------ fused exchange set-up
+static double p2p_signature(int rank, int which) { return 7.0e8 + 1000.0 * rank + which + 0.125; }
+
 // CUDA IPC handles of this rank's two spectral buffers (2 x 64 bytes), to be all-gathered by the host side
 extern "C" int dmk_p2p_export(dmk_ctx* c, unsigned char* handles128) {
   if (!c || !handles128) { dmk_set_error("null argument"); return DMK_ERR_ARG; }
@@ -548,10 +550,17 @@ extern "C" int dmk_p2p_export(dmk_ctx* c, unsigned char* handles128) {
   cudaIpcMemHandle_t h;
   DMK_CUDA_CHECK(cudaIpcGetMemHandle(&h, c->bufA)); memcpy(handles128, &h, 64);
   DMK_CUDA_CHECK(cudaIpcGetMemHandle(&h, c->bufB)); memcpy(handles128 + 64, &h, 64);
+  // signature at the start of either buffer: dmk_p2p_import checks that an opened handle really maps the peer's buffer
+  // (an IPC handle names an allocation, not a pointer into it)
+  const double sigA[2] = {p2p_signature(c->rank, 0), 0.0}, sigB[2] = {p2p_signature(c->rank, 1), 0.0};
+  DMK_CUDA_CHECK(cudaMemcpyAsync(c->bufA, sigA, sizeof sigA, cudaMemcpyHostToDevice, c->stream));
+  DMK_CUDA_CHECK(cudaMemcpyAsync(c->bufB, sigB, sizeof sigB, cudaMemcpyHostToDevice, c->stream));
+  DMK_CUDA_CHECK(cudaStreamSynchronize(c->stream));
   return DMK_OK;
 }
 
 bool dmk_fast_disabled();      // fft_fast.cu
+extern "C" int dmk_p2p_disable(dmk_ctx* c);
 static bool fast_len(int n) { return n == 16 || n == 32 || n == 64 || n == 128 || n == 256 || n == 512; }
 
 // all ranks' handles ([rank][A|B][64]); opens the peers' buffers and switches the transposes of the distributed FFT from
@@ -571,7 +580,16 @@ extern "C" int dmk_p2p_import(dmk_ctx* c, const unsigned char* all_handles, int*
     memcpy(&h, all_handles + (size_t)p * 128 + 64, 64);
     DMK_CUDA_CHECK(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess)); c->peerB[p] = (double2*)ptr;
   }
-  c->p2p = true;
+  // every opened pointer must show its owner's signature (written by dmk_p2p_export before the all-gather)
+  bool good = true;
+  for (int p = 0; p < c->P && good; p++) {
+    double a = 0.0, b = 0.0;
+    DMK_CUDA_CHECK(cudaMemcpy(&a, c->peerA[p], sizeof(double), cudaMemcpyDeviceToHost));
+    DMK_CUDA_CHECK(cudaMemcpy(&b, c->peerB[p], sizeof(double), cudaMemcpyDeviceToHost));
+    good = (a == p2p_signature(p, 0)) && (b == p2p_signature(p, 1));
+  }
+  c->p2p = true;                                       // (so that dmk_p2p_disable closes the handles)
+  if (!good) return dmk_p2p_disable(c);
   if (enabled) *enabled = 1;
   return DMK_OK;
 }
