@@ -153,6 +153,11 @@ int dmk_materialpoint_forward(dmk_ctx* ctx);                       /* f_material
 /* host copy, cell-major [cell][component]: "F","F0","Fp","Fp0","Fe","Lp","Lp0","S","S0" (row-major 3x3), "state","state0",
  * "dep", and "cutbacks" (sub-step cut-backs of each cell in the last response call) */
 int dmk_get_state(dmk_ctx* ctx, const char* name, double* host_out, size_t n_doubles);
+/* inverse of dmk_get_state for "F","F0","Fp","Fp0","Fe","Lp","Lp0","S","S0","state","state0","dep": restart of the per-point state
+ * (what phase_mechanical.f90:1264-1298 writes to / reads from the restart file) */
+int dmk_set_state(dmk_ctx* ctx, const char* name, const double* host_in, size_t n_doubles);
+int dmk_max_state(dmk_ctx* ctx);                                   /* components of "state" / "state0" */
+int dmk_max_dep(dmk_ctx* ctx);                                     /* components of "dep" (0: none) */
 int dmk_get_counters(dmk_ctx* ctx, long long counters[7]);         /* Lp iters, stress calls, state iters, substeps, cutbacks, ill,
                                                                      * cells deferred to the reference-order kernel */
 /* cumulative lane-schedule statistics of the lane-persistent constitutive kernel: {Newton-block warp trips, lanes served,

@@ -550,6 +550,9 @@ extern "C" int dmk_get_schedule_stats(dmk_ctx* c, long long stats[8]) {
   return DMK_OK;
 }
 
+extern "C" int dmk_max_state(dmk_ctx* c) { return (c && c->pts) ? c->pts->max_state : 0; }
+extern "C" int dmk_max_dep(dmk_ctx* c) { return (c && c->pts) ? c->pts->max_dep : 0; }
+
 // host copy of a per-point array, cell-major: out[cell][component] (row-major tensors; S as full 3x3)
 extern "C" int dmk_get_state(dmk_ctx* c, const char* name, double* out, size_t n_doubles) {
   int rc = need_points(c); if (rc) return rc;
@@ -579,6 +582,31 @@ extern "C" int dmk_get_state(dmk_ctx* c, const char* name, double* out, size_t n
   static const int V[9] = {0, 5, 4, 5, 1, 3, 4, 3, 2};
   for (long long i = 0; i < n; i++)
     for (int k = 0; k < out_comps; k++) out[i * out_comps + k] = buf[(size_t)(voigt ? V[k] : k) * n + i];
+  return DMK_OK;
+}
+
+// inverse of dmk_get_state for the arrays a restart needs (phase_mechanical.f90:1264-1298 writes / reads the same set:
+// F, F0, Fp, Fp0, Lp, Lp0, S, S0, the plastic state and its increment-start copy; Fe is kept as well)
+extern "C" int dmk_set_state(dmk_ctx* c, const char* name, const double* in, size_t n_doubles) {
+  int rc = need_points(c); if (rc) return rc;
+  DmkPointArrays& pa = *c->pts;
+  const long long n = pa.n;
+  double* dst = nullptr; int comps = 9; bool voigt = false;
+  std::string s(name ? name : "");
+  if (s == "F") dst = pa.F; else if (s == "F0") dst = pa.F0; else if (s == "Fp") dst = pa.Fp; else if (s == "Fp0") dst = pa.Fp0;
+  else if (s == "Fe") dst = pa.Fe; else if (s == "Lp") dst = pa.Lp; else if (s == "Lp0") dst = pa.Lp0;
+  else if (s == "S") { dst = pa.S; comps = 6; voigt = true; } else if (s == "S0") { dst = pa.S0; comps = 6; voigt = true; }
+  else if (s == "state") { dst = pa.state; comps = pa.max_state; } else if (s == "state0") { dst = pa.state0; comps = pa.max_state; }
+  else if (s == "dep") { dst = pa.dep; comps = pa.max_dep; }
+  if (!dst) { dmk_set_error("dmk_set_state: unknown or empty array '%s'", s.c_str()); return DMK_ERR_ARG; }
+  const int in_comps = voigt ? 9 : comps;
+  if (n_doubles < (size_t)in_comps * n) { dmk_set_error("dmk_set_state: buffer too small (%zu < %lld)", n_doubles, (long long)in_comps * n); return DMK_ERR_ARG; }
+  std::vector<double> buf((size_t)comps * n);
+  static const int V6[6] = {0, 4, 8, 5, 2, 1};                       // Voigt (11,22,33,23,13,12) out of the full 3x3
+  for (long long i = 0; i < n; i++)
+    for (int k = 0; k < comps; k++) buf[(size_t)k * n + i] = in[i * in_comps + (voigt ? V6[k] : k)];
+  DMK_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+  DMK_CUDA_CHECK(cudaMemcpy(dst, buf.data(), buf.size() * sizeof(double), cudaMemcpyHostToDevice));
   return DMK_OK;
 }
 

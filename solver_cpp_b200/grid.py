@@ -196,6 +196,28 @@ class GridContext:
         L.check(self.lib.dmk_get_state(self.ctx, name.encode(), _hp(out), C.c_size_t(out.size)))
         return out
 
+    RESTART_ARRAYS = (('F', 9), ('F0', 9), ('Fp', 9), ('Fp0', 9), ('Fe', 9), ('Lp', 9), ('Lp0', 9), ('S', 9), ('S0', 9))
+
+    def set_state(self, name, array):
+        a = np.ascontiguousarray(array, dtype=float)
+        L.check(self.lib.dmk_set_state(self.ctx, name.encode(), _hp(a), C.c_size_t(a.size)))
+
+    def save_point_state(self, path):
+        """restart data of the per-point integrator (phase_mechanical.f90:1264-1298 writes the same set to the restart file)"""
+        d = {k: self.get_state(k, n) for k, n in self.RESTART_ARRAYS}
+        ms = int(self.lib.dmk_max_state(self.ctx))
+        if ms > 0:
+            d['state'], d['state0'] = self.get_state('state', ms), self.get_state('state0', ms)
+        md = int(self.lib.dmk_max_dep(self.ctx))
+        if md > 0:
+            d['dep'] = self.get_state('dep', md)
+        np.savez(path, **d)
+
+    def load_point_state(self, path):
+        d = np.load(path)
+        for k in d.files:
+            self.set_state(k, d[k])
+
     # ---- measurement aids
     def set_profiling(self, enable=True):
         L.check(self.lib.dmk_set_profiling(self.ctx, C.c_int(int(enable))))

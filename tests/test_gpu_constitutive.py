@@ -244,3 +244,27 @@ def test_homogenisation_known_answer_two_cells():
     out = g.forward_field(0.0, g.to_device(P), g.to_device(np.zeros_like(P)), np.zeros((3, 3)))
     ref = P - P.mean(axis=(0, 1, 2))
     assert np.abs(g.to_natural(out) - ref).max() < 1e-6
+
+
+def test_point_state_restart_round_trip(tmp_path):
+    """save_point_state / load_point_state (dmk_get_state / dmk_set_state): a fresh context loaded with the saved per-point
+    state continues bit-identically (restart of the constitutive half, phase_mechanical.f90:1264-1298)"""
+    from solver_cpp_b200 import workloads as W, material as M
+    cells = (8, 6, 5)
+    material, material_at, size = W.polycrystal(cells, 11, 'Al_pheno', 0)
+    rng = np.random.default_rng(5)
+    seq = _F_sequence(cells, 3, rng, rate=3.0e-3)
+    g = _ctx(cells, size)
+    g.material_init(M.Material(material, material_at))
+    for F in seq[:2]:
+        g.constitutive_response(g.to_device(F), 0.5)
+        g.materialpoint_forward()
+    path = str(tmp_path / 'restart.npz')
+    g.save_point_state(path)
+    P_a = g.constitutive_response(g.to_device(seq[2]), 0.5).cpu().numpy().copy()
+    g2 = _ctx(cells, size)
+    g2.material_init(M.Material(material, material_at))
+    g2.load_point_state(path)
+    P_b = g2.constitutive_response(g2.to_device(seq[2]), 0.5).cpu().numpy()
+    assert np.array_equal(P_a, P_b)
+    assert np.array_equal(g.get_state('state', 24), g2.get_state('state', 24))
