@@ -120,3 +120,13 @@ def peer_store_inverse(nxr, ny, nz, world_size, me):
     def target(ky_loc, kz, kx):
         return kz // nz_loc, me * hi + ky_loc * o + (kz % nz_loc) * e + kx
     return target
+
+
+def halo_slots(world_size, rank):
+    """host twin of the z-halo exchange of update_coords (csrc/spectral.cu: dmk_update_coords): the all-to-all carries two
+    layer slots per peer.  Returns (send, recv): send[(peer, half)] = 'bottom' | 'top' (which of my layers goes there),
+    recv['above'] / recv['below'] = (peer, half) where the neighbouring layers arrive."""
+    rb, rt = (rank - 1 + world_size) % world_size, (rank + 1) % world_size
+    send = {(rb, 0): 'bottom', (rt, 1): 'top'}
+    recv = {'above': (rt, 0), 'below': (rb, 1)}
+    return send, recv

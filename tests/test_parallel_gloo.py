@@ -89,6 +89,25 @@ def test_fused_exchange_addressing_equals_the_all_to_all():
                 assert np.array_equal(got[src], full[p * nz_loc:(p + 1) * nz_loc, src * ny_loc:(src + 1) * ny_loc])
 
 
+def test_update_coords_halo_slots():
+    """the two-slots-per-peer all-to-all of update_coords delivers, for every world size, the top layer of the rank below and
+    the bottom layer of the rank above (for 2 ranks both slots of the one peer are used)"""
+    sys.path.insert(0, ROOT)
+    from solver_cpp_b200 import parallel
+    for world in (2, 3, 4, 8):
+        # all-to-all: what rank r puts in slot (p, h) arrives at rank p in slot (r, h)
+        arrived = [dict() for _ in range(world)]
+        for r in range(world):
+            send, _ = parallel.halo_slots(world, r)
+            for (p, h), which in send.items():
+                assert (r, h) not in arrived[p]
+                arrived[p][(r, h)] = (r, which)
+        for r in range(world):
+            _, recv = parallel.halo_slots(world, r)
+            assert arrived[r][recv['above']] == ((r + 1) % world, 'bottom')
+            assert arrived[r][recv['below']] == ((r - 1) % world, 'top')
+
+
 def test_transpose_exchange_world_size_2():
     world, port = 2, 29533
     ctx = mp.get_context('spawn')
