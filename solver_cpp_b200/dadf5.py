@@ -1,0 +1,183 @@
+"""DADF5 result files (the reference's HDF5 output: /root/reference/src/result.f90:75-155 file frame and increments,
+src/discretization.f90:100-116 displacements, src/phase_mechanical.f90:917-965 per-phase tensors, src/material.f90 cell_to
+mappings; layout as read by /root/reference/python/damask/_result.py:100-125).  Host-side output plumbing
+on top of hdf5_min.H5Writer; nothing here is on the hot path.
+
+    w = ResultWriter(cells, size, material, material_at, setup={'material.yaml': text, ...})
+    mech.loop_over_loadcase(solver, steps, callback=w.callback(every=4))
+    w.save('job.hdf5')
+
+Layout written (everything damask.Result reads for a single-constituent grid job):
+    / attrs DADF5_version_major/minor, creator, created, call
+    /geometry attrs cells, size, origin
+    /cell_to/phase [N,1], /cell_to/homogenization [N]: compound (label, entry)
+    /setup/<file name>: the input decks as strings
+    /increment_<n> attr t/s
+        geometry/u_n [(nx+1)(ny+1)(nz+1),3], u_p [N,3]
+        phase/<label>/mechanical/F, F_e, F_p, L_p, P, S [n_ph,3,3], O [n_ph,4], xi_sl (phenopowerlaw) [n_ph,N_sl]
+        homogenization/<label>/mechanical/ (empty, like the reference for 'pass')
+Strings are fixed-length (the reference writes variable-length ones); h5py returns them as bytes."""
+import time
+
+import numpy as np
+
+from .hdf5_min import H5Writer
+
+VERSION = 'solver_cpp_b200'
+
+_DESCR = {                                                             # phase_mechanical.f90:933-958
+    'F': ('deformation gradient', '1'), 'F_e': ('elastic deformation gradient', '1'), 'F_p': ('plastic deformation gradient', '1'),
+    'L_p': ('plastic velocity gradient', '1/s'), 'P': ('first Piola-Kirchhoff stress', 'Pa'),
+    'S': ('second Piola-Kirchhoff stress', 'Pa'), 'O': ('crystal orientation as quaternion q_0 (q_1 q_2 q_3)', 'q_0 (q_1 q_2 q_3)'),
+    'xi_sl': ('resistance against plastic slip', 'Pa'), 'gamma_sl': ('plastic shear', '1'),
+    'u_n': ('displacements of the nodes', 'm'), 'u_p': ('displacements of the materialpoints (cell centers)', 'm'),
+}
+
+
+def rotational_part(F):
+    """R of F = R U for a stack of 3x3 matrices (math.f90:1117-1156 computes the same R in closed form)"""
+    U, _, Vt = np.linalg.svd(F)
+    return U @ Vt
+
+
+def om2qu(om):
+    """passive rotation matrices [n,3,3] -> unit quaternions [n,4], q_0 >= 0, P = -1 (rotations.f90 convention)"""
+    om = np.asarray(om, float)
+    t = np.trace(om, axis1=-2, axis2=-1)
+    q = np.empty(om.shape[:-2] + (4,))
+    q[..., 0] = 0.5 * np.sqrt(np.maximum(0.0, 1.0 + t))
+    d = [om[..., 0, 0], om[..., 1, 1], om[..., 2, 2]]
+    q[..., 1] = 0.5 * np.sqrt(np.maximum(0.0, 1.0 + d[0] - d[1] - d[2]))
+    q[..., 2] = 0.5 * np.sqrt(np.maximum(0.0, 1.0 - d[0] + d[1] - d[2]))
+    q[..., 3] = 0.5 * np.sqrt(np.maximum(0.0, 1.0 - d[0] - d[1] + d[2]))
+    q[..., 1] *= np.where(om[..., 2, 1] < om[..., 1, 2], -1.0, 1.0)
+    q[..., 2] *= np.where(om[..., 0, 2] < om[..., 2, 0], -1.0, 1.0)
+    q[..., 3] *= np.where(om[..., 1, 0] < om[..., 0, 1], -1.0, 1.0)
+    q[..., 1:] *= -1.0                                                  # P = -1
+    return q / np.linalg.norm(q, axis=-1, keepdims=True)
+
+
+def orientation_from_Fe(Fe):
+    """crystallite_orientations (phase.f90:577-590): O = fromMatrix(transpose(rotationalPart(F_e)))"""
+    return om2qu(np.swapaxes(rotational_part(Fe), -1, -2))
+
+
+class ResultWriter:
+    def __init__(self, cells, size, material, material_at, origin=(0.0, 0.0, 0.0), setup=None, call='solver_cpp_b200'):
+        """material: parsed material.yaml; material_at: material index of every cell of the WHOLE grid, x fastest"""
+        self.cells = tuple(int(c) for c in cells)
+        self.size = np.asarray(size, float)
+        n = int(np.prod(self.cells))
+        material_at = np.asarray(material_at).reshape(-1)
+        if material_at.size != n:
+            raise ValueError('material_at has %d entries for %d cells' % (material_at.size, n))
+        mats = material['material']
+        self.phase_label = np.array([m['constituents'][0]['phase'] for m in mats], dtype=object)[material_at]
+        homog_label = np.array([m['homogenization'] for m in mats], dtype=object)[material_at]
+        self.phases = list(material['phase'].keys())
+        self.lattice = {k: (v or {}).get('lattice') for k, v in material['phase'].items()}
+        self.n_sl = {}
+        for k, v in material['phase'].items():
+            pl = ((v or {}).get('mechanical') or {}).get('plastic') or {}
+            if pl.get('type') == 'phenopowerlaw':
+                self.n_sl[k] = int(np.sum(pl.get('N_sl', [0])))
+        self.homogs = sorted(set(homog_label))
+        self.w = w = H5Writer()
+        now = time.strftime('%Y-%m-%d %H:%M:%S%z')
+        self._stamp = dict(creator=VERSION, created=now)
+        w.group('/', DADF5_version_major=np.int32(1), DADF5_version_minor=np.int32(0), creator=call + ' ' + VERSION, created=now,
+                call=call)
+        w.group('/geometry', cells=np.asarray(self.cells, np.int32), size=self.size, origin=np.asarray(origin, float))
+        w.group('/cell_to', description='mappings to place data in space')
+        w.group('/setup', description='input data used to run the simulation')
+        self.cells_of_phase = {}
+        ph_map = self._mapping(self.phase_label, self.cells_of_phase)
+        w.dataset('/cell_to/phase', ph_map.reshape(n, 1), description='cell ID and constituent ID to phase results', **self._stamp)
+        w.dataset('/cell_to/homogenization', self._mapping(homog_label, {}), description='cell ID to homogenization results',
+                  **self._stamp)
+        for name, text in (setup or {}).items():
+            w.dataset('/setup/' + name, np.array([text.encode() if isinstance(text, str) else text]), **self._stamp)
+        self.increments = []
+
+    @staticmethod
+    def _mapping(labels, members):
+        """(label, entry) per cell: entry = running index of the cell among the cells with the same label (material.f90)"""
+        width = max(len(l.encode()) for l in labels)
+        out = np.zeros(len(labels), dtype=[('label', 'S%d' % width), ('entry', '<i8')])
+        for l in sorted(set(labels)):
+            sel = np.nonzero(labels == l)[0]
+            members[l] = sel
+            out['label'][sel] = l.encode()
+            out['entry'][sel] = np.arange(sel.size)
+        return out
+
+    def add_increment(self, inc, t, fields, u_n=None, u_p=None):
+        """fields: name -> [N, ...] array in cell order (x fastest), tensors as natural [N,3,3]; split per phase here.
+        xi_sl / gamma_sl may be wider than a phase's N_sl (padded state arrays): the phase's leading columns are kept."""
+        n = int(np.prod(self.cells))
+        base = '/increment_%d' % inc
+        self.w.group(base, **{'t/s': float(t)})
+        self.w.group(base + '/geometry')
+        for name, a in (('u_n', u_n), ('u_p', u_p)):
+            if a is not None:
+                self._dataset(base + '/geometry/' + name, np.asarray(a, float).reshape(-1, 3), name)
+        for ph in self.phases:
+            sel = self.cells_of_phase.get(ph)
+            if sel is None:
+                continue
+            grp = '%s/phase/%s/mechanical' % (base, ph)
+            self.w.group(grp)
+            for name, a in fields.items():
+                a = np.asarray(a)
+                if a.shape[0] != n:
+                    raise ValueError('%s: %d rows for %d cells' % (name, a.shape[0], n))
+                extra = {}
+                if name in ('xi_sl', 'gamma_sl'):
+                    if ph not in self.n_sl:
+                        continue
+                    a = a[:, :self.n_sl[ph]]
+                if name == 'O' and self.lattice.get(ph):
+                    extra['lattice'] = self.lattice[ph]
+                self._dataset(grp + '/' + name, a[sel], name, **extra)
+        for h in self.homogs:
+            self.w.group('%s/homogenization/%s/mechanical' % (base, h))
+        self.increments.append(int(inc))
+
+    def _dataset(self, path, a, name, **extra):
+        d = _DESCR.get(name)
+        attrs = dict(self._stamp)
+        if d:
+            attrs.update(description=d[0], unit=d[1])
+        attrs.update(extra)
+        self.w.dataset(path, a, **attrs)
+
+    # ---- from the device-resident solver
+    def record(self, rec, solver):
+        """one converged increment of mech.loop_over_loadcase (single rank: the solver holds the whole grid)"""
+        g = solver.g
+        n = int(np.prod(self.cells))
+        if g.n_local != n:
+            raise ValueError('ResultWriter.record needs the whole grid on one rank (gather the slabs and use add_increment)')
+        get = lambda k: g.get_state(k, 9).reshape(n, 3, 3)
+        F, Fp, Fe, Lp, S = get('F'), get('Fp'), get('Fe'), get('Lp'), get('S')
+        P = Fe @ S @ np.swapaxes(np.linalg.inv(Fp), -1, -2)             # phase_mechanical.f90:595 (F_i = I)
+        fields = {'F': F, 'F_e': Fe, 'F_p': Fp, 'L_p': Lp, 'P': P, 'S': S, 'O': orientation_from_Fe(Fe)}
+        ms = int(g.lib.dmk_max_state(g.ctx))
+        if self.n_sl and ms > 0:
+            st = g.get_state('state', ms)
+            width = max(self.n_sl.values())
+            fields['xi_sl'] = st[:, :width]
+        if not hasattr(self, '_x0'):                                       # undeformed coordinates: the same routine on F = I
+            nx, ny, nz = self.cells
+            self._x0 = g.update_coords(g.to_device(np.broadcast_to(np.eye(3), (nz, ny, nx, 3, 3)).copy()))
+        x_n, x_p = solver.update_coords()
+        self.add_increment(rec['inc'], rec['t'], fields, u_n=x_n - self._x0[0], u_p=x_p - self._x0[1])
+
+    def callback(self, every=1):
+        def cb(rec, solver):
+            if rec['inc'] % every == 0:
+                self.record(rec, solver)
+        return cb
+
+    def save(self, path):
+        self.w.save(path)

@@ -158,17 +158,98 @@ class H5File:
 
     @staticmethod
     def _dtype(d):
+        return H5File._dtype_len(d)[0]
+
+    @staticmethod
+    def _dtype_len(d):
+        """(numpy dtype, encoded length) of a datatype message; variable-length strings come back as the 16-byte
+        global-heap reference records (resolved by attrs())"""
         cls, ver = d[0] & 0x0F, d[0] >> 4
         size = struct.unpack_from('<I', d, 4)[0]
-        if d[1] & 1:
+        if cls in (0, 1) and d[1] & 1:
             raise NotImplementedError('big-endian data')
         if cls == 0:
-            return np.dtype('<%s%d' % ('i' if d[1] & 0x08 else 'u', size))
+            return np.dtype('<%s%d' % ('i' if d[1] & 0x08 else 'u', size)), 12
         if cls == 1:
-            return np.dtype('<f%d' % size)
+            return np.dtype('<f%d' % size), 20
         if cls == 3:
-            return np.dtype('S%d' % size)
-        return np.dtype('V%d' % size)               # compound etc.: raw records
+            return np.dtype('S%d' % size), 8
+        if cls == 9:
+            _, n = H5File._dtype_len(d[8:])
+            return np.dtype([('len', '<u4'), ('heap', '<u8'), ('index', '<u4')]), 8 + n
+        if cls == 6 and ver in (1, 2, 3):
+            n_mem = d[1] | (d[2] << 8)
+            pos = 8
+            names, formats, offsets = [], [], []
+            for _ in range(n_mem):
+                end = d.index(b'\0', pos)
+                names.append(d[pos:end].decode())
+                pos = (pos + (end - pos) // 8 * 8 + 8) if ver < 3 else end + 1
+                if ver == 3:
+                    nb = max(1, (int(size).bit_length() + 7) // 8)
+                    offsets.append(int.from_bytes(d[pos:pos + nb], 'little'))
+                    pos += nb
+                else:
+                    offsets.append(struct.unpack_from('<I', d, pos)[0])
+                    pos += 4
+                    if ver == 1:
+                        if d[pos]:
+                            raise NotImplementedError('array members of a version-1 compound type')
+                        pos += 28
+                dt, n = H5File._dtype_len(d[pos:])
+                formats.append(dt)
+                pos += n
+            return np.dtype({'names': names, 'formats': formats, 'offsets': offsets, 'itemsize': size}), pos
+        return np.dtype('V%d' % size), len(d)        # anything else: raw records
+
+    def _global_heap_object(self, addr, index):
+        b = self.b
+        if b[addr:addr + 4] != b'GCOL':
+            raise ValueError('global heap signature')
+        size = struct.unpack_from('<Q', b, addr + 8)[0]
+        pos, end = addr + 16, addr + size
+        while pos + 16 <= end:
+            idx, _, _, n = struct.unpack_from('<HHIQ', b, pos)
+            if idx == index:
+                return b[pos + 16:pos + 16 + n]
+            if idx == 0:
+                break
+            pos += 16 + (n + 7) // 8 * 8
+        raise KeyError('global heap object %d' % index)
+
+    def attrs(self, path='/'):
+        """attributes of a group or dataset: name -> numpy array / scalar / str (version 1-3 attribute messages; fixed-
+        and variable-length strings decoded)"""
+        out = {}
+        for mtype, _, d in self._messages(self._resolve(path)):
+            if mtype != 0x000C:
+                continue
+            ver = d[0]
+            if ver not in (1, 2, 3):
+                raise NotImplementedError('attribute message version %d' % ver)
+            n_name, n_type, n_space = struct.unpack_from('<HHH', d, 2)
+            pos = 8 if ver < 3 else 9
+            rnd = (lambda n: (n + 7) // 8 * 8) if ver == 1 else (lambda n: n)
+            name = d[pos:pos + n_name].split(b'\0')[0].decode()
+            pos += rnd(n_name)
+            t = d[pos:pos + n_type]
+            dtype = self._dtype(t)
+            vlen = (t[0] & 0x0F) == 9
+            pos += rnd(n_type)
+            sp = d[pos:pos + n_space]
+            rank = sp[1]
+            shape = tuple(struct.unpack_from('<%dQ' % rank, sp, 8 if sp[0] == 1 else 4)) if rank else ()
+            pos += rnd(n_space)
+            n = int(np.prod(shape)) if shape else 1
+            a = np.frombuffer(d[pos:pos + n * dtype.itemsize], dtype, n)
+            if vlen:
+                a = np.array([self._global_heap_object(int(r['heap']), int(r['index']))[:int(r['len'])].decode()
+                              for r in a], dtype=object)
+            elif dtype.kind == 'S':
+                a = np.array([x.split(b'\0')[0].decode() for x in a], dtype=object)
+            a = a.reshape(shape)
+            out[name] = a[()] if shape == () else a.copy()
+        return out
 
     @staticmethod
     def _filters(d):
@@ -238,3 +319,251 @@ class H5File:
                 out[sl] = chunk[tuple(slice(0, s.stop - s.start) for s in sl)]
         walk(btree)
         return out
+
+
+# ------------------------------------------------------------------------------------------------------------ writer
+def _pad8(b):
+    return b + b'\0' * (-len(b) % 8)
+
+
+def _encode_dtype(dt):
+    """datatype message of a numpy dtype (version 1 encodings, little endian)"""
+    dt = np.dtype(dt)
+    if dt.kind in 'iu':
+        return struct.pack('<BBBBIHH', 0x10, 0x08 if dt.kind == 'i' else 0, 0, 0, dt.itemsize, 0, 8 * dt.itemsize)
+    if dt.kind == 'f' and dt.itemsize in (4, 8):
+        e, m, bias = ((8, 23, 127), (11, 52, 1023))[dt.itemsize == 8]
+        return struct.pack('<BBBBIHHBBBBI', 0x11, 0x20, 8 * dt.itemsize - 1, 0, dt.itemsize, 0, 8 * dt.itemsize, m, e, 0, m, bias)
+    if dt.kind == 'S':
+        return struct.pack('<BBBBI', 0x13, 0x01, 0, 0, dt.itemsize)                   # null-padded, ASCII
+    if dt.names:
+        out = struct.pack('<BBBBI', 0x16, len(dt.names) & 0xFF, len(dt.names) >> 8, 0, dt.itemsize)
+        for name in dt.names:
+            sub, off = dt.fields[name][:2]
+            if sub.shape:
+                raise NotImplementedError('array members of a compound type')
+            out += _pad8(name.encode() + b'\0') + struct.pack('<IB3xI4x16x', off, 0, 0) + _encode_dtype(sub)
+        return out
+    raise NotImplementedError('HDF5 encoding of dtype %s' % dt)
+
+
+def _encode_space(shape):
+    return struct.pack('<BBB5x', 1, len(shape), 0) + b''.join(struct.pack('<Q', n) for n in shape)
+
+
+def _as_h5_array(v):
+    """numpy array of a type the writer can encode; str and lists of str become fixed-length byte strings"""
+    if isinstance(v, str):
+        v = v.encode()
+    if isinstance(v, bytes):
+        return np.array(v, dtype='S%d' % max(1, len(v)))
+    a = np.asarray(v)
+    if a.dtype.kind in 'UO':
+        enc = [str(x).encode() for x in a.reshape(-1)]
+        a = np.array(enc, dtype='S%d' % max(1, max(map(len, enc), default=1))).reshape(a.shape)
+    if a.dtype.kind == 'b':
+        a = a.astype(np.int8)
+    if a.dtype.byteorder == '>':
+        a = a.astype(a.dtype.newbyteorder('<'))
+    return a
+
+
+class _Node:
+    def __init__(self, data=None):
+        self.data = data                # None: group
+        self.attrs = {}
+        self.children = {}
+
+
+class H5Writer:
+    """Writer of the same classic HDF5 subset H5File reads: superblock 0, symbol-table groups (group B-tree of any depth, leaf
+    K 4 / internal K 16 like libhdf5's defaults), version-1 object headers, contiguous little-endian datasets of integer /
+    float / fixed-length string / compound types, version-1 attributes.  Built in memory, written in one go by save().
+    Written for solver_cpp_b200.dadf5 (DADF5 result files, /root/reference/src/result.f90, src/HDF5_utilities.f90).
+    No libhdf5 / h5py exists in this environment: files are checked by reading them back with H5File, which itself is
+    checked against result files written by real DAMASK (tests/test_hdf5_cpu.py)."""
+    LEAF_K, NODE_K = 4, 16
+
+    def __init__(self):
+        self.root = _Node()
+
+    def _walk(self, path, create):
+        node = self.root
+        for part in [p for p in path.split('/') if p]:
+            if node.data is not None:
+                raise KeyError('%s: a dataset has no children' % path)
+            if part not in node.children:
+                if not create:
+                    raise KeyError(path)
+                node.children[part] = _Node()
+            node = node.children[part]
+        return node
+
+    def group(self, path, **attrs):
+        g = self._walk(path, True)
+        if g.data is not None:
+            raise KeyError('%s is a dataset' % path)
+        g.attrs.update(attrs)
+        return path
+
+    def dataset(self, path, array, **attrs):
+        parent, _, name = path.rstrip('/').rpartition('/')
+        g = self._walk(parent, True)
+        if g.data is not None or name in g.children:
+            raise KeyError('%s exists or lies below a dataset' % path)
+        n = _Node(np.ascontiguousarray(_as_h5_array(array)))
+        _encode_dtype(n.data.dtype)                                         # refuse unsupported element types here
+        n.attrs.update(attrs)
+        g.children[name] = n
+
+    def set_attrs(self, path, **attrs):
+        self._walk(path, False).attrs.update(attrs)
+
+    # ---- serialisation
+    def _alloc(self, blob):
+        addr = len(self.buf)
+        self.buf += _pad8(blob)
+        return addr
+
+    def _header(self, messages):
+        body = b''
+        for mtype, flags, data in messages:
+            data = _pad8(data)
+            if len(data) > 0xFFFF:
+                raise ValueError('object header message of %d bytes (attribute too large)' % len(data))
+            body += struct.pack('<HHB3x', mtype, len(data), flags) + data
+        return self._alloc(struct.pack('<BBHII4x', 1, 0, len(messages), 1, len(body)) + body)
+
+    @staticmethod
+    def _attr_messages(attrs):
+        out = []
+        for name, v in attrs.items():
+            a = _as_h5_array(v)
+            nm, t, sp = name.encode() + b'\0', _encode_dtype(a.dtype), _encode_space(a.shape)
+            out.append((0x000C, 0, struct.pack('<BBHHH', 1, 0, len(nm), len(t), len(sp)) + _pad8(nm) + _pad8(t) + _pad8(sp) +
+                        np.ascontiguousarray(a).tobytes()))
+        return out
+
+    def _write_node(self, node):
+        """-> (object header address, B-tree address, heap address); the latter two 0 for a dataset"""
+        if node.data is not None:
+            a = node.data
+            addr = self._alloc(a.tobytes()) if a.size else UNDEF
+            msgs = [(0x0001, 0, _encode_space(a.shape)), (0x0003, 1, _encode_dtype(a.dtype)),
+                    (0x0005, 1, struct.pack('<BBBBI', 2, 1, 2, 1, 0)),
+                    (0x0008, 0, struct.pack('<BBQQ', 3, 1, addr, a.size * a.dtype.itemsize))]
+            return self._header(msgs + self._attr_messages(node.attrs)), 0, 0
+        # children first, then the local heap of their names, the symbol nodes and the B-tree over them
+        names = sorted(node.children, key=lambda s: s.encode())
+        done = {n: self._write_node(node.children[n]) for n in names}
+        heap = bytearray(8)
+        off = {}
+        for n in names:
+            off[n] = len(heap)
+            heap += _pad8(n.encode() + b'\0')
+        free = len(heap)
+        heap += struct.pack('<QQ', 1, 16)                                   # one free block, end of list
+        data_addr = self._alloc(bytes(heap))
+        heap_addr = self._alloc(b'HEAP' + struct.pack('<B3xQQQ', 0, len(heap), free, data_addr))
+        level = []                                                          # (address, heap offset of the largest name below)
+        for s in range(0, len(names), 2 * self.LEAF_K):
+            part = names[s:s + 2 * self.LEAF_K]
+            blob = b'SNOD' + struct.pack('<BBH', 1, 0, len(part))
+            for n in part:
+                ohdr, bt, hp = done[n]
+                is_group = node.children[n].data is None
+                blob += struct.pack('<QQI4xQQ', off[n], ohdr, 1 if is_group else 0, bt, hp)
+            blob += b'\0' * (8 + 2 * self.LEAF_K * 40 - len(blob))
+            level.append((self._alloc(blob), off[part[-1]]))
+        depth = 0
+        node_size = 24 + (4 * self.NODE_K + 1) * 8
+        while True:
+            groups = [level[s:s + 2 * self.NODE_K] for s in range(0, len(level), 2 * self.NODE_K)] or [[]]
+            base = len(self.buf)
+            addrs = [base + k * node_size for k in range(len(groups))]
+            nxt = []
+            for k, grp in enumerate(groups):
+                first_key = 0 if k == 0 else groups[k - 1][-1][1]
+                blob = b'TREE' + struct.pack('<BBHQQ', 0, depth, len(grp), addrs[k - 1] if k else UNDEF,
+                                             addrs[k + 1] if k + 1 < len(groups) else UNDEF) + struct.pack('<Q', first_key)
+                for child, key in grp:
+                    blob += struct.pack('<QQ', child, key)
+                blob += b'\0' * (node_size - len(blob))
+                assert self._alloc(blob) == addrs[k]
+                nxt.append((addrs[k], grp[-1][1] if grp else 0))
+            if len(nxt) == 1:
+                btree = nxt[0][0]
+                break
+            level, depth = nxt, depth + 1
+        ohdr = self._header([(0x0011, 0, struct.pack('<QQ', btree, heap_addr))] + self._attr_messages(node.attrs))
+        return ohdr, btree, heap_addr
+
+    def tobytes(self):
+        self.buf = bytearray(96)
+        ohdr, btree, heap = self._write_node(self.root)
+        sb = b'\x89HDF\r\n\x1a\n' + struct.pack('<BBBBBBBBHHI', 0, 0, 0, 0, 0, 8, 8, 0, self.LEAF_K, self.NODE_K, 0)
+        sb += struct.pack('<QQQQ', 0, UNDEF, len(self.buf), UNDEF) + struct.pack('<QQI4xQQ', 0, ohdr, 1, btree, heap)
+        self.buf[:96] = sb
+        out = bytes(self.buf)
+        del self.buf
+        return out
+
+    def save(self, path):
+        with open(path, 'wb') as f:
+            f.write(self.tobytes())
+
+
+def check_group_structure(f, path='/'):
+    """Strict walk of a symbol-table group the way libhdf5 searches it (by the B-tree KEYS, which H5File ignores): names in
+    a symbol node sorted and within (left key, right key], sibling pointers consistent, heap free list inside the data
+    segment.  Recurses into sub-groups; returns the number of links visited.  Raises ValueError on any violation."""
+    b = f.b
+    addr = f._resolve(path)
+    sym = [d for t, _, d in f._messages(addr) if t == 0x0011]
+    if not sym:
+        return 0
+    btree, heap = struct.unpack_from('<QQ', sym[0], 0)
+    if b[heap:heap + 4] != b'HEAP':
+        raise ValueError('%s: heap signature' % path)
+    hsize, hfree, hdata = struct.unpack_from('<QQQ', b, heap + 8)
+    pos = hfree
+    while pos != 1:
+        if pos + 16 > hsize:
+            raise ValueError('%s: heap free list leaves the data segment' % path)
+        pos, blk = struct.unpack_from('<QQ', b, hdata + pos)
+        if blk < 16:
+            raise ValueError('%s: heap free block smaller than its header' % path)
+    name_at = lambda off: b[hdata + off:b.index(b'\0', hdata + off)]
+    leaf_k, node_k = struct.unpack_from('<HH', b, 16)
+    count = [0]
+
+    def walk(node, lo, hi, first):
+        if b[node:node + 4] != b'TREE' or b[node + 4] != 0:
+            raise ValueError('%s: group B-tree node expected' % path)
+        level, used = b[node + 5], struct.unpack_from('<H', b, node + 6)[0]
+        if used > 2 * node_k:
+            raise ValueError('%s: B-tree node over-full' % path)
+        keys = [struct.unpack_from('<Q', b, node + 24 + 16 * k)[0] for k in range(used + 1)]
+        kids = [struct.unpack_from('<Q', b, node + 32 + 16 * k)[0] for k in range(used)]
+        if used and (lo is not None and name_at(keys[0]) != lo or hi is not None and name_at(keys[-1]) != hi):
+            raise ValueError('%s: B-tree node keys disagree with the parent' % path)
+        for k, child in enumerate(kids):
+            left, right = name_at(keys[k]), name_at(keys[k + 1])
+            if level > 0:
+                walk(child, left, right, first and k == 0)
+                continue
+            if b[child:child + 4] != b'SNOD':
+                raise ValueError('%s: symbol node signature' % path)
+            n = struct.unpack_from('<H', b, child + 6)[0]
+            if not 0 < n <= 2 * leaf_k:
+                raise ValueError('%s: symbol node with %d entries' % (path, n))
+            names = [name_at(struct.unpack_from('<Q', b, child + 8 + 40 * s)[0]) for s in range(n)]
+            if names != sorted(names) or names[-1] != right or not (names[0] > left or (first and k == 0 and left == b'')):
+                raise ValueError('%s: symbol node names %r outside (%r, %r]' % (path, names, left, right))
+            count[0] += n
+    walk(btree, None, None, True)
+    for k in f.keys(path):
+        q = path.rstrip('/') + '/' + k
+        if f.is_group(q):
+            count[0] += check_group_structure(f, q)
+    return count[0]

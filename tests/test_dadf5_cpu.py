@@ -1,0 +1,135 @@
+"""Result-file output: the HDF5 writer against the reader (which tests/test_hdf5... pins to files written by
+real DAMASK), the strict group-structure walk libhdf5 relies on, and the DADF5 frame written from the reference's own
+input deck against golden set G5 (the frame of the real result file of that deck).  Host-side only."""
+import os
+
+import numpy as np
+import pytest
+import yaml
+
+from solver_cpp_b200 import dadf5
+from solver_cpp_b200.hdf5_min import H5File, H5Writer, check_group_structure
+from solver_cpp_b200.vti import read_vti
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+
+
+def test_writer_round_trip_all_types_and_a_three_level_group_tree(tmp_path):
+    rng = np.random.default_rng(0)
+    w = H5Writer()
+    w.group('/', version=np.int32(3), creator='someone', ratio=0.25)
+    w.group('/geometry', cells=np.array([6, 7, 8], np.int32), size=np.array([.75, .875, 1.]))
+    data = {}
+    for i in range(700):                                     # 700 links: 88 symbol nodes, 3 leaf B-tree nodes, one root above
+        data[i] = rng.standard_normal((5, 3, 3))
+        w.dataset('/many/item_%d/mechanical/F' % i, data[i], unit='1', systems=['[0 1 1]', '(1 1 1)x'])
+    ct = np.zeros((4, 1), dtype=[('label', 'S9'), ('entry', '<i8')])
+    ct['label'], ct['entry'][:, 0] = b'pheno', np.arange(4)
+    w.dataset('/cell_to/phase', ct)
+    w.dataset('/ints', np.arange(-3, 9, dtype=np.int64).reshape(3, 4))
+    w.dataset('/u8', np.arange(7, dtype=np.uint8))
+    w.dataset('/f4', np.linspace(0, 1, 5, dtype=np.float32))
+    w.dataset('/setup/x.yaml', np.array([b'hello: 1\n']))
+    w.dataset('/empty', np.zeros((0, 3)))
+    w.group('/hollow')
+    path = str(tmp_path / 't.hdf5')
+    w.save(path)
+    f = H5File(path)
+    assert f.keys('/') == sorted(['many', 'cell_to', 'ints', 'u8', 'f4', 'setup', 'empty', 'hollow', 'geometry'])
+    assert f.keys('/hollow') == [] and f.is_group('/hollow') and not f.is_group('/ints')
+    assert len(f.keys('/many')) == 700
+    a = f.attrs('/')
+    assert a['version'] == 3 and a['version'].dtype == np.int32 and a['creator'] == 'someone' and a['ratio'] == 0.25
+    assert (f.attrs('/geometry')['cells'] == [6, 7, 8]).all() and (f.attrs('/geometry')['size'] == [.75, .875, 1.]).all()
+    for i in (0, 1, 99, 350, 699):
+        assert np.array_equal(f.read('/many/item_%d/mechanical/F' % i), data[i])
+    at = f.attrs('/many/item_5/mechanical/F')
+    assert at['unit'] == '1' and list(at['systems']) == ['[0 1 1]', '(1 1 1)x']
+    back = f.read('/cell_to/phase')
+    assert back.dtype == ct.dtype and (back == ct).all()
+    assert np.array_equal(f.read('/ints'), np.arange(-3, 9).reshape(3, 4)) and f.read('/ints').dtype == np.int64
+    assert np.array_equal(f.read('/u8'), np.arange(7)) and f.read('/u8').dtype == np.uint8
+    assert np.array_equal(f.read('/f4'), np.linspace(0, 1, 5, dtype=np.float32))
+    assert f.read('/setup/x.yaml')[0] == b'hello: 1\n' and f.read('/empty').shape == (0, 3)
+    assert check_group_structure(f) == 9 + 700 * 3 + 2             # every link found through the B-tree keys
+
+
+def test_structure_check_catches_a_wrong_key(tmp_path):
+    w = H5Writer()
+    for k in range(20):
+        w.dataset('/d%02d' % k, np.arange(3.0))
+    blob = bytearray(w.tobytes())
+    f = H5File.__new__(H5File)
+    f.b = bytes(blob)
+    f.root = f._symbol_entry(56)
+    assert check_group_structure(f) == 20
+    bt = f.root['btree']
+    blob[bt + 24 + 16:bt + 24 + 24] = blob[bt + 24 + 32:bt + 24 + 40]      # key 1 := key 2
+    f.b = bytes(blob)
+    with pytest.raises(ValueError):
+        check_group_structure(f)
+
+
+def test_writer_refuses_what_it_cannot_encode():
+    w = H5Writer()
+    with pytest.raises(NotImplementedError):
+        w.dataset('/c', np.zeros(3, dtype=complex))
+    w = H5Writer()
+    w.dataset('/a', np.zeros(3))
+    with pytest.raises(KeyError):
+        w.dataset('/a', np.zeros(3))
+    with pytest.raises(KeyError):
+        w.dataset('/a/b', np.zeros(3))
+
+
+def test_orientation_from_elastic_deformation_matches_damask_g5():
+    """crystallite_orientations: O computed from F_e equals the O stored by real DAMASK next to that F_e (both phases)"""
+    g5 = np.load(os.path.join(GOLDEN, 'g5_dadf5_frame.npz'))
+    for ph in ('pheno_fcc', 'pheno_bcc'):
+        q = dadf5.orientation_from_Fe(g5['F_e_' + ph])
+        assert np.abs(q - g5['O_' + ph]).max() < 1e-13
+        assert (q[:, 0] >= 0).all()
+
+
+def test_result_frame_from_the_reference_deck_matches_damask_g5(tmp_path):
+    """ResultWriter fed the reference's 12-grain two-phase deck writes the same root / geometry attributes and the same
+    cell_to (label, entry) mappings as DAMASK did, and per-phase datasets land in DAMASK's per-phase order."""
+    g5 = np.load(os.path.join(GOLDEN, 'g5_dadf5_frame.npz'))
+    geo = read_vti(os.path.join(GOLDEN, '12grains6x7x8.vti'))
+    mat_text = open(os.path.join(GOLDEN, '12grains6x7x8.material.yaml')).read()
+    w = dadf5.ResultWriter(geo['cells'], geo['size'], yaml.safe_load(mat_text), geo['material'], origin=geo['origin'],
+                           setup={'material.yaml': mat_text})
+    n = int(np.prod(geo['cells']))
+    # per-cell F_e assembled from the per-phase golden arrays through DAMASK's own mapping
+    Fe = np.zeros((n, 3, 3))
+    for ph in ('pheno_fcc', 'pheno_bcc'):
+        sel = g5['phase_label'] == ph.encode()
+        Fe[sel] = g5['F_e_' + ph][g5['phase_entry'][sel]]
+    xi = np.arange(n * 12, dtype=float).reshape(n, 12)
+    nx, ny, nz = (int(c) for c in geo['cells'])
+    w.add_increment(4, float(g5['t_inc4']), {'F_e': Fe, 'O': dadf5.orientation_from_Fe(Fe), 'xi_sl': xi},
+                    u_n=np.zeros((nz + 1, ny + 1, nx + 1, 3)), u_p=np.zeros((nz, ny, nx, 3)))
+    path = str(tmp_path / 'job.hdf5')
+    w.save(path)
+    f = H5File(path)
+    check_group_structure(f)
+    root, g = f.attrs('/'), f.attrs('/geometry')
+    assert [root['DADF5_version_major'], root['DADF5_version_minor']] == list(g5['version'])
+    assert (g['cells'] == g5['cells']).all() and g['cells'].dtype == np.int32
+    assert np.allclose(g['size'], g5['size'], rtol=1e-15) and np.allclose(g['origin'], g5['origin'])
+    ph, ho = f.read('/cell_to/phase'), f.read('/cell_to/homogenization')
+    assert ph.shape == (n, 1) and ho.shape == (n,)
+    assert (ph['label'].reshape(-1) == g5['phase_label']).all() and (ph['entry'].reshape(-1) == g5['phase_entry']).all()
+    assert (ho['label'] == g5['homog_label']).all() and (ho['entry'] == g5['homog_entry']).all()
+    assert f.attrs('/increment_4')['t/s'] == float(g5['t_inc4'])
+    assert f.keys('/increment_4') == ['geometry', 'homogenization', 'phase']
+    assert f.keys('/increment_4/homogenization') == ['SX']
+    for p in ('pheno_fcc', 'pheno_bcc'):
+        base = '/increment_4/phase/%s/mechanical/' % p
+        assert np.array_equal(f.read(base + 'F_e'), g5['F_e_' + p])
+        assert np.abs(f.read(base + 'O') - g5['O_' + p]).max() < 1e-13
+        assert f.attrs(base + 'O')['lattice'] == g5['lattice_' + p].item().decode()
+        assert f.attrs(base + 'F_e')['unit'] == '1'
+        assert f.read(base + 'xi_sl').shape == (g5['F_e_' + p].shape[0], 12)
+    assert f.read('/increment_4/geometry/u_n').shape == ((nx + 1) * (ny + 1) * (nz + 1), 3)
+    assert f.read('/setup/material.yaml')[0].decode() == mat_text

@@ -175,6 +175,49 @@ def test_g4_job_from_the_reference_input_files(golden_dir):
         assert np.abs(recs[int(inc) - 1]['P_av'] - Pd.mean(0)).max() < 3e-4 * np.abs(Pd.mean(0)).max()
 
 
+def test_g4_result_file_written_from_the_job_matches_damask(golden_dir, tmp_path):
+    """The G4 deck solved on the GPU with solver_cpp_b200.dadf5.ResultWriter as the increment callback: the DADF5 file read
+    back holds F, P, u_p, u_n that agree with the REAL DAMASK result of that deck (golden set G4) at increment 4, P equal
+    to the solver's own P (its mean is P_av), and O consistent with F_e."""
+    from solver_cpp_b200 import job, mech, dadf5
+    from solver_cpp_b200.hdf5_min import H5File, check_group_structure
+    from solver_cpp_b200.vti import read_vti
+    g4 = np.load(os.path.join(golden_dir, 'g4_damask_run.npz'))
+    files = [os.path.join(golden_dir, f) for f in ('6grains6x7x8_single_phase.vti', '6grains6x7x8_single_phase.material.yaml',
+                                                   '6grains6x7x8_tensionY.load.yaml')]
+    geo = read_vti(files[0])
+    w = dadf5.ResultWriter(geo['cells'], geo['size'], yaml.safe_load(open(files[1])), geo['material'], origin=geo['origin'],
+                           setup={'material.yaml': open(files[1]).read(), 'tensionY.yaml': open(files[2]).read()})
+    s, steps = job.load_job(*files)
+    s.init()
+    snap = {}
+    rec_cb = w.callback(every=4)
+
+    def cb(rec, solver):
+        rec_cb(rec, solver)
+        if rec['inc'] == 4:
+            snap['F'] = solver.g.to_natural(solver.field('F')).reshape(-1, 3, 3).copy()
+    recs = mech.loop_over_loadcase(s, steps, callback=cb, max_increments=4)
+    path = str(tmp_path / 'job.hdf5')
+    w.save(path)
+    f = H5File(path)
+    check_group_structure(f)
+    assert f.keys('/') == ['cell_to', 'geometry', 'increment_4', 'setup']
+    assert f.attrs('/increment_4')['t/s'] == pytest.approx(recs[3]['t'])
+    base = '/increment_4/phase/pheno_fcc/mechanical/'
+    F, P, Fe, Fp, O, xi = (f.read(base + k) for k in ('F', 'P', 'F_e', 'F_p', 'O', 'xi_sl'))
+    assert int(g4['increments'][0]) == 4
+    assert np.abs(F - snap['F']).max() < 1e-9                                   # cell order and index order of the tensors
+    assert np.abs(F - g4['F'][0]).max() < 1e-5
+    assert np.abs(Fe @ Fp - F).max() < 1e-12
+    assert _rel(P.mean(0), recs[3]['P_av']) < 1e-9
+    assert np.abs(P - g4['P'][0]).max() < 5e-3 * np.abs(g4['P'][0]).max()
+    assert np.abs(O - dadf5.orientation_from_Fe(Fe)).max() < 1e-14 and xi.shape == (336, 12) and (xi >= 31e6).all()
+    scale = np.abs(g4['u_n'][0]).max()
+    assert np.abs(f.read('/increment_4/geometry/u_p') - g4['u_p'][0]).max() < 1e-4 * scale
+    assert np.abs(f.read('/increment_4/geometry/u_n') - g4['u_n'][0]).max() < 1e-4 * scale
+
+
 def test_g4b_two_phase_job_from_the_reference_input_files(golden_dir):
     """fcc + bcc deck of the reference (12grains6x7x8): two phases, each through the lane-persistent kernel; the first
     four increments against the free-running oracle (iterations identical, 1e-9) and the real DAMASK result at increment 4"""

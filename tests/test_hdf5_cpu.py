@@ -1,0 +1,44 @@
+"""The minimal HDF5 reader against a result file written by real DAMASK through libhdf5
+(tests/golden/damask_written_marc_job.hdf5: the reference's python/tests/resources/Result/check_compile_job1.hdf5, a data
+fixture, unchanged).  The checks are properties of the mesh the file describes, so they do not depend on the reader
+being right: connectivity within the node range, cell centres = mean of the cell's nodes, volumes adding up."""
+import os
+
+import numpy as np
+
+from solver_cpp_b200.hdf5_min import H5File, check_group_structure
+
+PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'damask_written_marc_job.hdf5')
+
+
+def test_tree_and_attributes():
+    f = H5File(PATH)
+    assert f.keys('/') == ['cell_to', 'geometry', 'increment_1', 'increment_2', 'setup']
+    assert check_group_structure(f) == 36
+    a = f.attrs('/')
+    assert a['DADF5_version_major'] == 1 and a['DADF5_version_minor'] == 0
+    assert a['created'] == '2023-02-04 13:32:38+0100' and 'DAMASK_Marc' in a['creator']       # variable-length strings
+    assert f.attrs('/increment_2')['t/s'] == 100.0
+    at = f.attrs('/geometry/v_0')
+    assert at['unit'] == 'm³' and at['description'] == 'initial cell volume'                   # UTF-8
+    assert f.attrs('/geometry/T_c')['VTK_TYPE'] == 'HEXAHEDRON'
+
+
+def test_compound_mapping():
+    ph = H5File(PATH).read('/cell_to/phase')
+    assert ph.dtype.names == ('label', 'entry') and ph.shape == (8, 1)
+    assert (ph['label'] == b'Aluminum_J2isotropic').all() and (ph['entry'].reshape(-1) == np.arange(8)).all()
+
+
+def test_mesh_datasets_are_mutually_consistent():
+    f = H5File(PATH)
+    T, x_n, x_p, v0 = f.read('/geometry/T_c'), f.read('/geometry/x_n'), f.read('/geometry/x_p'), f.read('/geometry/v_0')
+    assert T.shape == (8, 8) and T.dtype == np.int64 and T.min() == 1 and T.max() == x_n.shape[0] == 27
+    assert np.abs(x_n[T - 1].mean(1) - x_p).max() < 1e-12 * np.abs(x_n).max()
+    ext = x_n.max(0) - x_n.min(0)
+    assert abs(v0.sum() - ext.prod()) < 1e-12 * ext.prod()
+    n0, a0 = f.read('/geometry/n_0'), f.read('/geometry/a_0')
+    assert np.abs(np.linalg.norm(n0, axis=-1) - 1).max() < 1e-12
+    assert np.abs((n0 * a0[..., None]).sum(1)).max() < 1e-12 * a0.max()                        # closed cells
+    u_n, u_p = f.read('/increment_2/geometry/u_n'), f.read('/increment_2/geometry/u_p')
+    assert np.abs(u_n[T - 1].mean(1) - u_p).max() < 1e-9 * max(np.abs(u_n).max(), 1e-300)
