@@ -160,7 +160,9 @@ class ResultWriter:
             raise ValueError('ResultWriter.record needs the whole grid on one rank (gather the slabs and use add_increment)')
         get = lambda k: g.get_state(k, 9).reshape(n, 3, 3)
         F, Fp, Fe, Lp, S = get('F'), get('Fp'), get('Fe'), get('Lp'), get('S')
-        P = Fe @ S @ np.swapaxes(np.linalg.inv(Fp), -1, -2)             # phase_mechanical.f90:595 (F_i = I)
+        # phase_mechanical.f90:595: P = F Fp^-1 S Fp^-T with the Fp BEFORE its determinant is normalised (:600), i.e.
+        # Fp^-1 = F^-1 F_e (F_i = I); the stored, normalised F_p differs from it by ~1e-7 (so does DAMASK's own file)
+        P = Fe @ S @ np.swapaxes(np.linalg.solve(F, Fe), -1, -2)
         fields = {'F': F, 'F_e': Fe, 'F_p': Fp, 'L_p': Lp, 'P': P, 'S': S, 'O': orientation_from_Fe(Fe)}
         ms = int(g.lib.dmk_max_state(g.ctx))
         if self.n_sl and ms > 0:

@@ -209,7 +209,9 @@ def test_g4_result_file_written_from_the_job_matches_damask(golden_dir, tmp_path
     assert int(g4['increments'][0]) == 4
     assert np.abs(F - snap['F']).max() < 1e-9                                   # cell order and index order of the tensors
     assert np.abs(F - g4['F'][0]).max() < 1e-5
-    assert np.abs(Fe @ Fp - F).max() < 1e-12
+    # F_e is formed with F_p before its determinant is normalised (phase_mechanical.f90:595-600): the real file shows
+    # the same 2e-7 mismatch
+    assert np.abs(Fe @ Fp - F).max() < 1e-6 and np.abs(np.linalg.det(Fp) - 1).max() < 1e-14
     assert _rel(P.mean(0), recs[3]['P_av']) < 1e-9
     assert np.abs(P - g4['P'][0]).max() < 5e-3 * np.abs(g4['P'][0]).max()
     assert np.abs(O - dadf5.orientation_from_Fe(Fe)).max() < 1e-14 and xi.shape == (336, 12) and (xi >= 31e6).all()
