@@ -62,6 +62,26 @@ def orientation_from_Fe(Fe):
     return om2qu(np.swapaxes(rotational_part(Fe), -1, -2))
 
 
+def gather_slabs(local, group=None):
+    """z-slab pieces of per-cell / per-node arrays -> whole-grid arrays on rank 0 (None elsewhere).  `local`: name -> array
+    whose first axis runs over this rank's cells (x fastest, z slowest: slabs concatenate); the entry 'u_n', if present, is
+    [nz_local + 1, ny + 1, nx + 1, 3]: every rank contributes its lower nz_local node layers, the last rank its top layer too.
+    Plain torch.distributed gather of host arrays (result output is not on the hot path)."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        out = dict(local)
+        return out
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    piece = dict(local)
+    if 'u_n' in piece and rank != world - 1:
+        piece['u_n'] = piece['u_n'][:-1]
+    parts = [None] * world if rank == 0 else None
+    dist.gather_object(piece, parts, dst=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+    if rank != 0:
+        return None
+    return {k: np.concatenate([np.asarray(p[k]) for p in parts], axis=0) for k in piece}
+
+
 class ResultWriter:
     def __init__(self, cells, size, material, material_at, origin=(0.0, 0.0, 0.0), setup=None, call='solver_cpp_b200'):
         """material: parsed material.yaml; material_at: material index of every cell of the WHOLE grid, x fastest"""
@@ -152,12 +172,20 @@ class ResultWriter:
         self.w.dataset(path, a, **attrs)
 
     # ---- from the device-resident solver
-    def record(self, rec, solver):
-        """one converged increment of mech.loop_over_loadcase (single rank: the solver holds the whole grid)"""
+    def record(self, rec, solver, group=None):
+        """one converged increment of mech.loop_over_loadcase.  Multi-rank jobs (z-slabs): a collective call -- every rank
+        passes its solver, rank 0 (the only rank that needs a ResultWriter with a file to save) receives the slabs."""
+        local = self.local_fields(solver)
+        whole = gather_slabs(local, group)
+        if whole is None:
+            return
+        u_n, u_p = whole.pop('u_n'), whole.pop('u_p')
+        self.add_increment(rec['inc'], rec['t'], whole, u_n=u_n, u_p=u_p)
+
+    def local_fields(self, solver):
+        """this rank's cells: the per-point arrays of the constitutive update and the displacements"""
         g = solver.g
-        n = int(np.prod(self.cells))
-        if g.n_local != n:
-            raise ValueError('ResultWriter.record needs the whole grid on one rank (gather the slabs and use add_increment)')
+        n = g.n_local
         get = lambda k: g.get_state(k, 9).reshape(n, 3, 3)
         F, Fp, Fe, Lp, S = get('F'), get('Fp'), get('Fe'), get('Lp'), get('S')
         # phase_mechanical.f90:595: P = F Fp^-1 S Fp^-T with the Fp BEFORE its determinant is normalised (:600), i.e.
@@ -166,19 +194,19 @@ class ResultWriter:
         fields = {'F': F, 'F_e': Fe, 'F_p': Fp, 'L_p': Lp, 'P': P, 'S': S, 'O': orientation_from_Fe(Fe)}
         ms = int(g.lib.dmk_max_state(g.ctx))
         if self.n_sl and ms > 0:
-            st = g.get_state('state', ms)
-            width = max(self.n_sl.values())
-            fields['xi_sl'] = st[:, :width]
+            fields['xi_sl'] = g.get_state('state', ms)[:, :max(self.n_sl.values())]
         if not hasattr(self, '_x0'):                                       # undeformed coordinates: the same routine on F = I
-            nx, ny, nz = self.cells
-            self._x0 = g.update_coords(g.to_device(np.broadcast_to(np.eye(3), (nz, ny, nx, 3, 3)).copy()))
+            nx, ny, _ = self.cells
+            self._x0 = g.update_coords(g.to_device(np.broadcast_to(np.eye(3), (g.nz_local, ny, nx, 3, 3)).copy()))
         x_n, x_p = solver.update_coords()
-        self.add_increment(rec['inc'], rec['t'], fields, u_n=x_n - self._x0[0], u_p=x_p - self._x0[1])
+        fields['u_n'] = x_n - self._x0[0]
+        fields['u_p'] = (x_p - self._x0[1]).reshape(n, 3)
+        return fields
 
-    def callback(self, every=1):
+    def callback(self, every=1, group=None):
         def cb(rec, solver):
             if rec['inc'] % every == 0:
-                self.record(rec, solver)
+                self.record(rec, solver, group)
         return cb
 
     def save(self, path):

@@ -133,3 +133,83 @@ def test_result_frame_from_the_reference_deck_matches_damask_g5(tmp_path):
         assert f.read(base + 'xi_sl').shape == (g5['F_e_' + p].shape[0], 12)
     assert f.read('/increment_4/geometry/u_n').shape == ((nx + 1) * (ny + 1) * (nz + 1), 3)
     assert f.read('/setup/material.yaml')[0].decode() == mat_text
+
+
+# ---- multi-rank gather (gloo, world_size 2): z-slab pieces arrive on rank 0 in whole-grid order
+class _FakeLib:
+    def dmk_max_state(self, ctx):
+        return 24
+
+
+class _FakeGrid:
+    """stands in for GridContext on one z-slab: hands out slices of whole-grid arrays every rank can regenerate"""
+    lib, ctx = _FakeLib(), None
+
+    def __init__(self, cells, z0, z1, seed):
+        nx, ny, nz = cells
+        rng = np.random.default_rng(seed)
+        n = nx * ny * nz
+        self.whole = {k: np.eye(3).reshape(9) + 0.01 * rng.standard_normal((n, 9)) for k in ('F', 'Fp', 'Fe', 'Lp', 'S')}
+        self.whole['state'] = rng.random((n, 24))
+        self.x_n = rng.standard_normal((nz + 1, ny + 1, nx + 1, 3))
+        self.x_p = rng.standard_normal((nz, ny, nx, 3))
+        self.z0, self.z1, self.nz_local, self.n_local = z0, z1, z1 - z0, (z1 - z0) * ny * nx
+        self.sl = slice(z0 * ny * nx, z1 * ny * nx)
+
+    def get_state(self, k, comps):
+        return self.whole[k][self.sl].copy()
+
+    def to_device(self, a):
+        return a
+
+    def update_coords(self, F):                       # called once with F = I for the undeformed coordinates
+        return np.zeros_like(self.x_n[self.z0:self.z1 + 1]), np.zeros_like(self.x_p[self.z0:self.z1])
+
+
+class _FakeSolver:
+    def __init__(self, g):
+        self.g = g
+
+    def update_coords(self):
+        g = self.g
+        return g.x_n[g.z0:g.z1 + 1].copy(), g.x_p[g.z0:g.z1].copy()
+
+
+def _writer():
+    geo = read_vti(os.path.join(GOLDEN, '12grains6x7x8.vti'))
+    mat = yaml.safe_load(open(os.path.join(GOLDEN, '12grains6x7x8.material.yaml')))
+    return dadf5.ResultWriter(geo['cells'], geo['size'], mat, geo['material'], origin=geo['origin']), tuple(int(c) for c in geo['cells'])
+
+
+def _gather_worker(rank, world, port, path):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    from solver_cpp_b200 import parallel
+    w, cells = _writer()
+    z0, z1 = parallel.slab_range(cells[2], world, rank)
+    w.record(dict(inc=3, t=1.5), _FakeSolver(_FakeGrid(cells, z0, z1, 5)))
+    if rank == 0:
+        w.save(path)
+    else:
+        assert w.increments == []
+    dist.destroy_process_group()
+
+
+def test_two_rank_gather_writes_the_same_file_content_as_one_rank(tmp_path):
+    import torch.multiprocessing as mp
+    path2, path1 = str(tmp_path / 'two.hdf5'), str(tmp_path / 'one.hdf5')
+    mp.spawn(_gather_worker, args=(2, 29631, path2), nprocs=2, join=True)
+    w, cells = _writer()
+    w.record(dict(inc=3, t=1.5), _FakeSolver(_FakeGrid(cells, 0, cells[2], 5)))
+    w.save(path1)
+    a, b = H5File(path1), H5File(path2)
+    check_group_structure(b)
+    n_checked = 0
+    for grp in ('/increment_3/geometry', '/increment_3/phase/pheno_fcc/mechanical', '/increment_3/phase/pheno_bcc/mechanical'):
+        assert a.keys(grp) == b.keys(grp)
+        for k in a.keys(grp):
+            assert np.array_equal(a.read(grp + '/' + k), b.read(grp + '/' + k)), (grp, k)
+            n_checked += 1
+    assert n_checked == 2 + 8 + 8
+    assert b.read('/increment_3/geometry/u_n').shape == ((cells[0] + 1) * (cells[1] + 1) * (cells[2] + 1), 3)
