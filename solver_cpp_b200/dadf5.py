@@ -62,24 +62,32 @@ def orientation_from_Fe(Fe):
     return om2qu(np.swapaxes(rotational_part(Fe), -1, -2))
 
 
-def gather_slabs(local, group=None):
+def gather_slabs(local, group=None, device=None):
     """z-slab pieces of per-cell / per-node arrays -> whole-grid arrays on rank 0 (None elsewhere).  `local`: name -> array
-    whose first axis runs over this rank's cells (x fastest, z slowest: slabs concatenate); the entry 'u_n', if present, is
-    [nz_local + 1, ny + 1, nx + 1, 3]: every rank contributes its lower nz_local node layers, the last rank its top layer too.
-    Plain torch.distributed gather of host arrays (result output is not on the hot path)."""
+    whose first axis runs over this rank's cells (x fastest, z slowest: slabs concatenate; equal slabs, parallel.slab_range);
+    the entry 'u_n', if present, is [nz_local + 1, ny + 1, nx + 1, 3]: rank 0 keeps the lower nz_local node layers of every
+    rank and the top layer of the last one.  One all_gather of equally shaped tensors per array (on `device` for an NCCL
+    group, host memory for gloo) -- result output is not on the hot path."""
+    import torch
     import torch.distributed as dist
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
-        out = dict(local)
-        return out
+        return dict(local)
     world, rank = dist.get_world_size(group), dist.get_rank(group)
-    piece = dict(local)
-    if 'u_n' in piece and rank != world - 1:
-        piece['u_n'] = piece['u_n'][:-1]
-    parts = [None] * world if rank == 0 else None
-    dist.gather_object(piece, parts, dst=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
-    if rank != 0:
-        return None
-    return {k: np.concatenate([np.asarray(p[k]) for p in parts], axis=0) for k in piece}
+    if dist.get_backend(group) == 'nccl':
+        dev = torch.device(device) if device is not None else torch.device('cuda', torch.cuda.current_device())
+    else:
+        dev = torch.device('cpu')
+    whole = {}
+    for k in sorted(local):
+        t = torch.from_numpy(np.ascontiguousarray(local[k], dtype=np.float64)).to(dev)
+        parts = [torch.empty_like(t) for _ in range(world)]
+        dist.all_gather(parts, t, group=group)
+        if rank == 0:
+            parts = [p.cpu().numpy() for p in parts]
+            if k == 'u_n':
+                parts = [p[:-1] for p in parts[:-1]] + [parts[-1]]
+            whole[k] = np.concatenate(parts, axis=0)
+    return whole if rank == 0 else None
 
 
 class ResultWriter:
@@ -173,10 +181,14 @@ class ResultWriter:
 
     # ---- from the device-resident solver
     def record(self, rec, solver, group=None):
-        """one converged increment of mech.loop_over_loadcase.  Multi-rank jobs (z-slabs): a collective call -- every rank
-        passes its solver, rank 0 (the only rank that needs a ResultWriter with a file to save) receives the slabs."""
+        """one converged increment of mech.loop_over_loadcase.  For a z-slab solver (solver.g.world_size > 1) a collective
+        call: every rank passes its solver, rank 0 (the only rank that needs to save) receives the slabs.  A whole-grid
+        solver records locally even inside an initialised process group."""
         local = self.local_fields(solver)
-        whole = gather_slabs(local, group)
+        if getattr(solver.g, 'world_size', 1) > 1:              # the SOLVER's decomposition decides, not the process group's size
+            whole = gather_slabs(local, group, getattr(solver.g, 'device', None))
+        else:
+            whole = local
         if whole is None:
             return
         u_n, u_p = whole.pop('u_n'), whole.pop('u_p')

@@ -147,6 +147,7 @@ class _FakeGrid:
 
     def __init__(self, cells, z0, z1, seed):
         nx, ny, nz = cells
+        self.world_size = 1 if (z0, z1) == (0, nz) else nz // (z1 - z0)
         rng = np.random.default_rng(seed)
         n = nx * ny * nz
         self.whole = {k: np.eye(3).reshape(9) + 0.01 * rng.standard_normal((n, 9)) for k in ('F', 'Fp', 'Fe', 'Lp', 'S')}
@@ -191,11 +192,17 @@ def _gather_worker(rank, world, port, path):
     w.record(dict(inc=3, t=1.5), _FakeSolver(_FakeGrid(cells, z0, z1, 5)))
     if rank == 0:
         w.save(path)
+        # a whole-grid solver recorded by ONE rank inside the initialised group must not enter a collective
+        # (tests/mgpu_parity.py compares the slab solver with a single-GPU solver exactly like this)
+        w1, _ = _writer()
+        w1.record(dict(inc=3, t=1.5), _FakeSolver(_FakeGrid(cells, 0, cells[2], 5)))
+        assert w1.increments == [3]
     else:
         assert w.increments == []
     dist.destroy_process_group()
 
 
+@pytest.mark.timeout(180)
 def test_two_rank_gather_writes_the_same_file_content_as_one_rank(tmp_path):
     import torch.multiprocessing as mp
     path2, path1 = str(tmp_path / 'two.hdf5'), str(tmp_path / 'one.hdf5')
