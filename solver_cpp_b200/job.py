@@ -1,6 +1,6 @@
 """A DAMASK grid job from the reference's own input files: geometry (.vti), material.yaml, load.yaml, numerics.yaml --
 what `DAMASK_grid -g .. -m .. -l .. -n ..` parses in main.cpp:31-101, config.cpp:247-430 and discretization_grid.cpp:8-76
-of the reference -- handed to the device-resident solver.  Host-side input plumbing; no result files."""
+of the reference -- handed to the device-resident solver, optionally with a DADF5 result file.  Host-side input / output plumbing."""
 import numpy as np
 import yaml
 
@@ -37,8 +37,28 @@ def load_job(geometry, material, load, numerics=None, world_size=1, rank=0, comm
     return solver, mech.parse_load(ld)
 
 
-def run_job(geometry, material, load, numerics=None, **kw):
-    """the whole load case; one record per converged increment (mech.loop_over_loadcase)"""
+def run_job(geometry, material, load, numerics=None, result=None, **kw):
+    """the whole load case; one record per converged increment (mech.loop_over_loadcase).  `result`: path of a DADF5 result
+    file to write (solver_cpp_b200.dadf5): the increments each load step's `f_out` selects, like DAMASK_grid.f90 does
+    (every f_out-th increment of the step, labelled with the running increment number); rank 0 saves it."""
     solver, steps = load_job(geometry, material, load, numerics, **kw)
     solver.init()
-    return mech.loop_over_loadcase(solver, steps)
+    callback = writer = None
+    if result is not None:
+        from . import dadf5
+        geo = read_vti(geometry)
+        mat = yaml.safe_load(open(material)) if isinstance(material, str) else material
+        setup = {}
+        for path in (material, load, numerics):
+            if isinstance(path, str):
+                setup[path.rsplit('/', 1)[-1]] = open(path).read()
+        writer = dadf5.ResultWriter(geo['cells'], geo['size'], mat, geo['material'], origin=geo['origin'], setup=setup,
+                                    call='solver_cpp_b200.job.run_job -g %s -l %s' % (geometry, load if isinstance(load, str) else '-'))
+
+        def callback(rec, s):
+            if rec['inc_in_step'] % max(1, rec['f_out']) == 0:
+                writer.record(rec, s, getattr(kw.get('comm'), 'group', None))
+    records = mech.loop_over_loadcase(solver, steps, callback=callback)
+    if writer is not None and kw.get('rank', 0) == 0:
+        writer.save(result)
+    return records

@@ -219,7 +219,8 @@ def loop_over_loadcase(solver: MechSolverBasic, steps, max_cut_back=3, callback=
                 else:
                     raise L.DmkError('no solution found for increment %d' % total_inc)
             cut_back_level = max(0, cut_back_level - 1)
-            rec = dict(inc=total_inc, t=t, converged=sol['converged'], iterations=sol['required_iterations'],
+            rec = dict(inc=total_inc, step=l, inc_in_step=inc + 1, f_out=st.get('f_out', 1), t=t, converged=sol['converged'],
+                       iterations=sol['required_iterations'],
                        P_av=solver.get33('P_av'), F_av=solver.get('F_av', 9).reshape(3, 3).T, F_aim=solver.get33('F_aim'))
             records.append(rec)
             if callback:

@@ -220,3 +220,45 @@ def test_two_rank_gather_writes_the_same_file_content_as_one_rank(tmp_path):
             n_checked += 1
     assert n_checked == 2 + 8 + 8
     assert b.read('/increment_3/geometry/u_n').shape == ((cells[0] + 1) * (cells[1] + 1) * (cells[2] + 1), 3)
+
+
+def test_run_job_writes_the_increments_f_out_selects(tmp_path, monkeypatch):
+    """job.run_job(result=...) with the device solver replaced by a stand-in: the file holds the increments the load step's
+    f_out selects (the reference's real result of this deck, f_out 4: increments 4, 8, ...), the input decks under /setup"""
+    from solver_cpp_b200 import job, mech
+    files = [os.path.join(GOLDEN, f) for f in ('12grains6x7x8.vti', '12grains6x7x8.material.yaml', '6grains6x7x8_tensionY.load.yaml')]
+    load = yaml.safe_load(open(files[2]))
+    assert load['loadstep'][0]['f_out'] == 4
+    _, cells = _writer()
+
+    class Stand(_FakeSolver):
+        def init(self):
+            pass
+
+        def forward(self, *a):
+            pass
+
+        def calculate_solution(self):
+            return dict(converged=True, stag_converged=True, terminally_ill=False, required_iterations=2)
+
+        def get33(self, name):
+            return np.eye(3)
+
+        def get(self, name, n=1):
+            return np.zeros(n)
+
+    g = _FakeGrid(cells, 0, cells[2], 9)
+    g.materialpoint_forward = lambda: None
+    steps = mech.parse_load(load)
+    steps[0]['N'], steps[0]['t'] = 9, steps[0]['t'] * 9 / steps[0]['N']
+    monkeypatch.setattr(job, 'load_job', lambda *a, **k: (Stand(g), steps))
+    path = str(tmp_path / 'out.hdf5')
+    recs = job.run_job(*files, result=path)
+    assert len(recs) == 9
+    f = H5File(path)
+    check_group_structure(f)
+    assert f.keys('/') == ['cell_to', 'geometry', 'increment_4', 'increment_8', 'setup']
+    assert f.keys('/setup') == ['12grains6x7x8.material.yaml', '6grains6x7x8_tensionY.load.yaml']
+    assert f.attrs('/increment_8')['t/s'] == pytest.approx(recs[7]['t'])
+    assert f.read('/setup/6grains6x7x8_tensionY.load.yaml')[0].decode() == open(files[2]).read()
+    assert 'run_job' in f.attrs('/')['call']
