@@ -223,3 +223,56 @@ class ResultWriter:
 
     def save(self, path):
         self.w.save(path)
+
+
+class ResultReader:
+    """The reading side, for the same files (ours or DAMASK's own): increments, times, grid, and `place` -- per-phase
+    datasets put back into cell order through /cell_to/phase, what damask.Result.place does
+    (/root/reference/python/damask/_result.py) for single-constituent results."""
+
+    def __init__(self, path):
+        from .hdf5_min import H5File
+        self.f = f = H5File(path)
+        root = f.attrs('/')
+        self.version = (int(root['DADF5_version_major']), int(root['DADF5_version_minor']))
+        self.increments = sorted(int(k.split('_')[1]) for k in f.keys('/') if k.startswith('increment_'))
+        self.times = [float(f.attrs('/increment_%d' % i)['t/s']) for i in self.increments]
+        geo = f.attrs('/geometry')
+        self.cells = tuple(int(c) for c in geo['cells']) if 'cells' in geo else None        # grid solver only
+        self.size = np.asarray(geo['size'], float) if 'size' in geo else None
+        self.origin = np.asarray(geo['origin'], float) if 'origin' in geo else None
+        m = f.read('/cell_to/phase')
+        if m.ndim == 2 and m.shape[1] != 1:
+            raise NotImplementedError('results with %d constituents per cell' % m.shape[1])
+        m = m.reshape(-1)
+        self.phase_label = np.array([l.split(b'\0')[0].decode() for l in m['label']], dtype=object)
+        self.phase_entry = m['entry'].astype(np.int64)
+        self.phases = sorted(set(self.phase_label))
+
+    def datasets(self, inc, phase=None, field='mechanical'):
+        phase = phase or self.phases[0]
+        return self.f.keys('/increment_%d/phase/%s/%s' % (inc, phase, field))
+
+    def get(self, name, inc, field='mechanical'):
+        """phase label -> dataset as stored (the phase's own order); phases without that dataset are left out"""
+        out = {}
+        for ph in self.phases:
+            grp = '/increment_%d/phase/%s/%s' % (inc, ph, field)
+            if name in self.f.keys(grp):
+                out[ph] = self.f.read(grp + '/' + name)
+        if not out:
+            raise KeyError('%s in increment %d' % (name, inc))
+        return out
+
+    def place(self, name, inc, field='mechanical', fill=np.nan):
+        """dataset of every cell in cell order (x fastest); cells of phases that do not have it hold `fill`"""
+        per_phase = self.get(name, inc, field)
+        first = next(iter(per_phase.values()))
+        out = np.full((self.phase_label.size,) + first.shape[1:], fill, dtype=first.dtype if first.dtype.kind == 'f' else float)
+        for ph, a in per_phase.items():
+            sel = self.phase_label == ph
+            out[sel] = a[self.phase_entry[sel]]
+        return out
+
+    def geometry(self, name, inc):
+        return self.f.read('/increment_%d/geometry/%s' % (inc, name))

@@ -17,6 +17,10 @@ R = '/root/reference/python/tests/resources/Result/'
 def main():
     for fn in ('6grains6x7x8_single_phase_tensionY', '12grains6x7x8_tensionY', '4grains2x4x3_compressionY'):
         assert check_group_structure(H5File(R + fn + '.hdf5')) > 100
+    # the reading side (dadf5.ResultReader.place) on the real two-phase file reproduces golden set G4b
+    from solver_cpp_b200 import dadf5
+    rd, g4b = dadf5.ResultReader(R + '12grains6x7x8_tensionY.hdf5'), np.load(os.path.join(HERE, 'g4b_damask_run_two_phase.npz'))
+    assert all(np.array_equal(rd.place(k, 4), g4b[k][0]) for k in ('F', 'P')) and rd.cells == (6, 7, 8)
     f = H5File(R + '12grains6x7x8_tensionY.hdf5')
     out = {}
     root, geo = f.attrs('/'), f.attrs('/geometry')

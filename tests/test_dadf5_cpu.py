@@ -262,3 +262,34 @@ def test_run_job_writes_the_increments_f_out_selects(tmp_path, monkeypatch):
     assert f.attrs('/increment_8')['t/s'] == pytest.approx(recs[7]['t'])
     assert f.read('/setup/6grains6x7x8_tensionY.load.yaml')[0].decode() == open(files[2]).read()
     assert 'run_job' in f.attrs('/')['call']
+
+
+def test_reader_places_per_phase_data_back_into_cell_order(tmp_path):
+    g5 = np.load(os.path.join(GOLDEN, 'g5_dadf5_frame.npz'))
+    w, cells = _writer()
+    n = int(np.prod(cells))
+    rng = np.random.default_rng(2)
+    F = rng.standard_normal((n, 3, 3))
+    xi = rng.random((n, 12))
+    w.add_increment(4, 2.0, {'F': F, 'xi_sl': xi}, u_p=np.zeros((n, 3)))
+    w.add_increment(12, 6.0, {'F': 2 * F})
+    path = str(tmp_path / 'r.hdf5')
+    w.save(path)
+    r = dadf5.ResultReader(path)
+    assert r.version == (1, 0) and r.increments == [4, 12] and r.times == [2.0, 6.0] and r.cells == cells
+    assert r.phases == ['pheno_bcc', 'pheno_fcc'] and (r.phase_entry == g5['phase_entry']).all()
+    assert np.array_equal(r.place('F', 4), F) and np.array_equal(r.place('F', 12), 2 * F)
+    assert np.array_equal(r.place('xi_sl', 4), xi)
+    assert set(r.get('F', 4)) == {'pheno_bcc', 'pheno_fcc'} and r.get('F', 4)['pheno_fcc'].shape == (167, 3, 3)
+    assert r.datasets(4, 'pheno_fcc') == ['F', 'xi_sl'] and r.geometry('u_p', 4).shape == (n, 3)
+    with pytest.raises(KeyError):
+        r.place('P', 4)
+
+
+def test_reader_on_a_file_written_by_damask():
+    """the DAMASK-written fixture (Marc solver, one phase): same reader, same placement"""
+    r = dadf5.ResultReader(os.path.join(GOLDEN, 'damask_written_marc_job.hdf5'))
+    assert r.version == (1, 0) and r.increments == [1, 2] and r.times[1] == 100.0 and r.cells is None
+    assert r.phases == ['Aluminum_J2isotropic']
+    xi = r.place('xi', 2)
+    assert xi.shape == (8,) and np.array_equal(xi, r.get('xi', 2)['Aluminum_J2isotropic']) and (xi > 0).all()
