@@ -91,8 +91,10 @@ def gather_slabs(local, group=None, device=None):
 
 
 class ResultWriter:
-    def __init__(self, cells, size, material, material_at, origin=(0.0, 0.0, 0.0), setup=None, call='solver_cpp_b200'):
-        """material: parsed material.yaml; material_at: material index of every cell of the WHOLE grid, x fastest"""
+    def __init__(self, cells, size, material, material_at, origin=(0.0, 0.0, 0.0), setup=None, call='solver_cpp_b200', path=None):
+        """material: parsed material.yaml; material_at: material index of every cell of the WHOLE grid, x fastest.
+        path: stream the datasets to that file as the increments arrive (save() finishes it) instead of holding the
+        result in host memory until save(path)"""
         self.cells = tuple(int(c) for c in cells)
         self.size = np.asarray(size, float)
         n = int(np.prod(self.cells))
@@ -110,7 +112,7 @@ class ResultWriter:
             if pl.get('type') == 'phenopowerlaw':
                 self.n_sl[k] = int(np.sum(pl.get('N_sl', [0])))
         self.homogs = sorted(set(homog_label))
-        self.w = w = H5Writer()
+        self.w = w = H5Writer(path)
         now = time.strftime('%Y-%m-%d %H:%M:%S%z')
         self._stamp = dict(creator=VERSION, created=now)
         w.group('/', DADF5_version_major=np.int32(1), DADF5_version_minor=np.int32(0), creator=call + ' ' + VERSION, created=now,
@@ -221,7 +223,7 @@ class ResultWriter:
                 self.record(rec, solver, group)
         return cb
 
-    def save(self, path):
+    def save(self, path=None):
         self.w.save(path)
 
 

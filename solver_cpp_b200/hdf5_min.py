@@ -370,7 +370,7 @@ def _as_h5_array(v):
 
 class _Node:
     def __init__(self, data=None):
-        self.data = data                # None: group
+        self.data = data                # None: group; dataset: (shape, dtype, n_bytes, file address of the raw data)
         self.attrs = {}
         self.children = {}
 
@@ -378,14 +378,23 @@ class _Node:
 class H5Writer:
     """Writer of the same classic HDF5 subset H5File reads: superblock 0, symbol-table groups (group B-tree of any depth, leaf
     K 4 / internal K 16 like libhdf5's defaults), version-1 object headers, contiguous little-endian datasets of integer /
-    float / fixed-length string / compound types, version-1 attributes.  Built in memory, written in one go by save().
+    float / fixed-length string / compound types, version-1 attributes.  The raw data of a dataset goes to the file (path
+    given to the constructor) the moment dataset() is called -- a result file of a 256^3 run is larger than one wants to
+    hold in host memory -- the small metadata (groups, headers, attributes) is kept and written by save() / close();
+    without a path everything goes to memory and tobytes() returns the file image.
     Written for solver_cpp_b200.dadf5 (DADF5 result files, /root/reference/src/result.f90, src/HDF5_utilities.f90).
     No libhdf5 / h5py exists in this environment: files are checked by reading them back with H5File, which itself is
     checked against result files written by real DAMASK (tests/test_hdf5_cpu.py)."""
     LEAF_K, NODE_K = 4, 16
 
-    def __init__(self):
+    def __init__(self, path=None):
+        import io
         self.root = _Node()
+        self.path = path
+        self.fh = open(path, 'wb') if path is not None else io.BytesIO()
+        self.fh.write(b'\0' * 96)                      # superblock, filled in at the end
+        self.pos = 96
+        self.closed = False
 
     def _walk(self, path, create):
         node = self.root
@@ -411,8 +420,14 @@ class H5Writer:
         g = self._walk(parent, True)
         if g.data is not None or name in g.children:
             raise KeyError('%s exists or lies below a dataset' % path)
-        n = _Node(np.ascontiguousarray(_as_h5_array(array)))
-        _encode_dtype(n.data.dtype)                                         # refuse unsupported element types here
+        a = np.ascontiguousarray(_as_h5_array(array))
+        _encode_dtype(a.dtype)                                              # refuse unsupported element types here
+        if self.closed:
+            raise ValueError('H5Writer: file already written')
+        raw = a.tobytes()
+        n = _Node((a.shape, a.dtype, len(raw), self.pos if raw else UNDEF))
+        self.fh.write(_pad8(raw))
+        self.pos += len(raw) + (-len(raw) % 8)
         n.attrs.update(attrs)
         g.children[name] = n
 
@@ -421,7 +436,7 @@ class H5Writer:
 
     # ---- serialisation
     def _alloc(self, blob):
-        addr = len(self.buf)
+        addr = self.pos + len(self.buf)
         self.buf += _pad8(blob)
         return addr
 
@@ -447,11 +462,10 @@ class H5Writer:
     def _write_node(self, node):
         """-> (object header address, B-tree address, heap address); the latter two 0 for a dataset"""
         if node.data is not None:
-            a = node.data
-            addr = self._alloc(a.tobytes()) if a.size else UNDEF
-            msgs = [(0x0001, 0, _encode_space(a.shape)), (0x0003, 1, _encode_dtype(a.dtype)),
+            shape, dtype, n_bytes, addr = node.data
+            msgs = [(0x0001, 0, _encode_space(shape)), (0x0003, 1, _encode_dtype(dtype)),
                     (0x0005, 1, struct.pack('<BBBBI', 2, 1, 2, 1, 0)),
-                    (0x0008, 0, struct.pack('<BBQQ', 3, 1, addr, a.size * a.dtype.itemsize))]
+                    (0x0008, 0, struct.pack('<BBQQ', 3, 1, addr, n_bytes))]
             return self._header(msgs + self._attr_messages(node.attrs)), 0, 0
         # children first, then the local heap of their names, the symbol nodes and the B-tree over them
         names = sorted(node.children, key=lambda s: s.encode())
@@ -479,7 +493,7 @@ class H5Writer:
         node_size = 24 + (4 * self.NODE_K + 1) * 8
         while True:
             groups = [level[s:s + 2 * self.NODE_K] for s in range(0, len(level), 2 * self.NODE_K)] or [[]]
-            base = len(self.buf)
+            base = self.pos + len(self.buf)
             addrs = [base + k * node_size for k in range(len(groups))]
             nxt = []
             for k, grp in enumerate(groups):
@@ -498,17 +512,36 @@ class H5Writer:
         ohdr = self._header([(0x0011, 0, struct.pack('<QQ', btree, heap_addr))] + self._attr_messages(node.attrs))
         return ohdr, btree, heap_addr
 
-    def tobytes(self):
-        self.buf = bytearray(96)
+    def close(self):
+        """writes the metadata behind the raw data and the superblock in front; the writer is finished afterwards"""
+        if self.closed:
+            return
+        self.buf = bytearray()
         ohdr, btree, heap = self._write_node(self.root)
-        sb = b'\x89HDF\r\n\x1a\n' + struct.pack('<BBBBBBBBHHI', 0, 0, 0, 0, 0, 8, 8, 0, self.LEAF_K, self.NODE_K, 0)
-        sb += struct.pack('<QQQQ', 0, UNDEF, len(self.buf), UNDEF) + struct.pack('<QQI4xQQ', 0, ohdr, 1, btree, heap)
-        self.buf[:96] = sb
-        out = bytes(self.buf)
+        self.fh.write(bytes(self.buf))
+        eof = self.pos + len(self.buf)
         del self.buf
-        return out
+        sb = b'\x89HDF\r\n\x1a\n' + struct.pack('<BBBBBBBBHHI', 0, 0, 0, 0, 0, 8, 8, 0, self.LEAF_K, self.NODE_K, 0)
+        sb += struct.pack('<QQQQ', 0, UNDEF, eof, UNDEF) + struct.pack('<QQI4xQQ', 0, ohdr, 1, btree, heap)
+        self.fh.seek(0)
+        self.fh.write(sb)
+        self.closed = True
+        if self.path is not None:
+            self.fh.close()
 
-    def save(self, path):
+    def tobytes(self):
+        if self.path is not None:
+            raise ValueError('H5Writer: streaming to %s; tobytes() is for the in-memory mode' % self.path)
+        self.close()
+        return self.fh.getvalue()
+
+    def save(self, path=None):
+        """in-memory mode: write the image to `path`; streaming mode: finish the file given to the constructor"""
+        if self.path is not None:
+            if path is not None and path != self.path:
+                raise ValueError('H5Writer: already streaming to %s' % self.path)
+            self.close()
+            return
         with open(path, 'wb') as f:
             f.write(self.tobytes())
 

@@ -53,6 +53,7 @@ def run_job(geometry, material, load, numerics=None, result=None, **kw):
             if isinstance(path, str):
                 setup[path.rsplit('/', 1)[-1]] = open(path).read()
         writer = dadf5.ResultWriter(geo['cells'], geo['size'], mat, geo['material'], origin=geo['origin'], setup=setup,
+                                    path=result if kw.get('rank', 0) == 0 else None,
                                     call='solver_cpp_b200.job.run_job -g %s -l %s' % (geometry, load if isinstance(load, str) else '-'))
 
         def callback(rec, s):
@@ -60,5 +61,5 @@ def run_job(geometry, material, load, numerics=None, result=None, **kw):
                 writer.record(rec, s, getattr(kw.get('comm'), 'group', None))
     records = mech.loop_over_loadcase(solver, steps, callback=callback)
     if writer is not None and kw.get('rank', 0) == 0:
-        writer.save(result)
+        writer.save()
     return records

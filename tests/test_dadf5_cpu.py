@@ -293,3 +293,27 @@ def test_reader_on_a_file_written_by_damask():
     assert r.phases == ['Aluminum_J2isotropic']
     xi = r.place('xi', 2)
     assert xi.shape == (8,) and np.array_equal(xi, r.get('xi', 2)['Aluminum_J2isotropic']) and (xi > 0).all()
+
+
+def test_streaming_writer_produces_the_same_file_as_the_in_memory_one(tmp_path):
+    def fill(w):
+        rng = np.random.default_rng(1)
+        w.group('/', version=np.int32(1))
+        for i in range(40):
+            w.dataset('/increment_%d/phase/p/mechanical/F' % i, rng.standard_normal((7, 3, 3)), unit='1')
+        w.dataset('/odd', np.arange(5, dtype=np.uint8))                       # 5 bytes: padding between datasets
+        w.dataset('/empty', np.zeros((0, 2)))
+        w.group('/increment_3', **{'t/s': 1.5})
+        return w
+    path = str(tmp_path / 's.hdf5')
+    ws = fill(H5Writer(path))
+    ws.save()
+    image = fill(H5Writer()).tobytes()
+    assert open(path, 'rb').read() == image
+    f = H5File(path)
+    check_group_structure(f)
+    assert f.read('/odd').tolist() == [0, 1, 2, 3, 4] and f.read('/empty').shape == (0, 2)
+    with pytest.raises(ValueError):
+        ws.dataset('/late', np.zeros(3))
+    with pytest.raises(ValueError):
+        H5Writer(str(tmp_path / 'x.hdf5')).tobytes()
