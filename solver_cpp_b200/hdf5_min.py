@@ -12,7 +12,32 @@ import numpy as np
 UNDEF = 0xFFFFFFFFFFFFFFFF
 
 
+def fletcher32(data):
+    """checksum of HDF5's fletcher32 filter (H5_checksum_fletcher32 of libhdf5: big-endian 16-bit words, the two running
+    sums folded to 16 bits after every 360 words, an odd trailing byte taken as the high byte of a last word)"""
+    n = len(data) // 2
+    w = np.frombuffer(data, '>u2', n).astype(np.int64)
+    s1 = s2 = 0
+    for a in range(0, n, 360):
+        blk = w[a:a + 360]
+        m = blk.size
+        s2 += m * s1 + int((blk * np.arange(m, 0, -1)).sum())
+        s1 += int(blk.sum())
+        s1 = (s1 & 0xFFFF) + (s1 >> 16)
+        s2 = (s2 & 0xFFFF) + (s2 >> 16)
+    if len(data) % 2:
+        s1 += data[-1] << 8
+        s2 += s1
+        s1 = (s1 & 0xFFFF) + (s1 >> 16)
+        s2 = (s2 & 0xFFFF) + (s2 >> 16)
+    s1 = (s1 & 0xFFFF) + (s1 >> 16)
+    s2 = (s2 & 0xFFFF) + (s2 >> 16)
+    return ((s2 << 16) | s1) & 0xFFFFFFFF
+
+
 class H5File:
+    verify_checksums = True             # fletcher32-filtered chunks are checked against their stored checksum
+
     def __init__(self, path):
         self.b = open(path, 'rb').read()
         b = self.b
@@ -304,7 +329,9 @@ class H5File:
                         continue
                     fid, cd = filters[k]
                     if fid == 3:
-                        raw = raw[:-4]
+                        raw, stored = raw[:-4], struct.unpack('<I', raw[-4:])[0]
+                        if self.verify_checksums and fletcher32(raw) != stored:
+                            raise ValueError('fletcher32 checksum of a chunk at %d does not match' % child)
                     elif fid == 1:
                         raw = zlib.decompress(raw)
                     elif fid == 2:

@@ -42,3 +42,38 @@ def test_mesh_datasets_are_mutually_consistent():
     assert np.abs((n0 * a0[..., None]).sum(1)).max() < 1e-12 * a0.max()                        # closed cells
     u_n, u_p = f.read('/increment_2/geometry/u_n'), f.read('/increment_2/geometry/u_p')
     assert np.abs(u_n[T - 1].mean(1) - u_p).max() < 1e-9 * max(np.abs(u_n).max(), 1e-300)
+
+
+def test_chunk_checksums_written_by_libhdf5_verify_and_catch_corruption(tmp_path):
+    """every dataset of the fixture is chunked with libhdf5's fletcher32 filter: the reader recomputes the checksum of each
+    chunk it decodes (an independent check of the chunk walk), and a flipped data byte is reported"""
+    import struct
+    from solver_cpp_b200.hdf5_min import fletcher32
+    f = H5File(PATH)
+    assert f.verify_checksums
+    n = 0
+    for grp in ('/geometry', '/increment_1/geometry', '/increment_2/geometry', '/setup'):
+        for k in f.keys(grp):
+            q = grp + '/' + k
+            msgs = f._messages(f._resolve(q))
+            assert [f._filters(d) for t, _, d in msgs if t == 0x000B] == [[(3, ())]]
+            f.read(q)
+            n += 1
+    assert n == 13
+    # corrupt one byte of the x_n chunk (its address from the chunk B-tree)
+    lay = [d for t, _, d in f._messages(f._resolve('/geometry/x_n')) if t == 0x0008][0]
+    btree = struct.unpack_from('<Q', lay, 3)[0]
+    chunk = struct.unpack_from('<Q', f.b, btree + 24 + 8 + 8 * 3)[0]
+    blob = bytearray(f.b)
+    blob[chunk + 5] ^= 0x10
+    bad = H5File.__new__(H5File)
+    bad.b = bytes(blob)
+    bad.root = bad._symbol_entry(56)
+    try:
+        bad.read('/geometry/x_n')
+        raise AssertionError('corruption not detected')
+    except ValueError as e:
+        assert 'fletcher32' in str(e)
+    bad.verify_checksums = False
+    assert bad.read('/geometry/x_n').shape == (27, 3)
+    assert fletcher32(b'') == 0 and fletcher32(b'\x01') == 0x01000100 and fletcher32(b'\x00\x01\x00\x02') == 0x00040003
