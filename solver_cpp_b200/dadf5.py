@@ -179,7 +179,7 @@ class ResultWriter:
         if d:
             attrs.update(description=d[0], unit=d[1])
         attrs.update(extra)
-        self.w.dataset(path, a, **attrs)
+        self.w.dataset(path, a, checksum=True, **attrs)                 # chunked + fletcher32, like the reference's datasets
 
     # ---- from the device-resident solver
     def record(self, rec, solver, group=None):

@@ -404,8 +404,9 @@ class _Node:
 
 class H5Writer:
     """Writer of the same classic HDF5 subset H5File reads: superblock 0, symbol-table groups (group B-tree of any depth, leaf
-    K 4 / internal K 16 like libhdf5's defaults), version-1 object headers, contiguous little-endian datasets of integer /
-    float / fixed-length string / compound types, version-1 attributes.  The raw data of a dataset goes to the file (path
+    K 4 / internal K 16 like libhdf5's defaults), version-1 object headers, little-endian datasets of integer / float /
+    fixed-length string / compound types stored contiguously or (checksum=True) as one fletcher32-filtered chunk the way
+    DAMASK's result datasets are, version-1 attributes.  The raw data of a dataset goes to the file (path
     given to the constructor) the moment dataset() is called -- a result file of a 256^3 run is larger than one wants to
     hold in host memory -- the small metadata (groups, headers, attributes) is kept and written by save() / close();
     without a path everything goes to memory and tobytes() returns the file image.
@@ -442,7 +443,11 @@ class H5Writer:
         g.attrs.update(attrs)
         return path
 
-    def dataset(self, path, array, **attrs):
+    CHUNK_K = 32                        # libhdf5's default for chunk B-trees (not stored in a version-0 superblock)
+
+    def dataset(self, path, array, checksum=False, **attrs):
+        """checksum=True: stored the way DAMASK's result datasets are -- chunked layout, one chunk spanning the dataset,
+        fletcher32 filter (the checksum behind the data) -- instead of contiguous"""
         parent, _, name = path.rstrip('/').rpartition('/')
         g = self._walk(parent, True)
         if g.data is not None or name in g.children:
@@ -452,7 +457,10 @@ class H5Writer:
         if self.closed:
             raise ValueError('H5Writer: file already written')
         raw = a.tobytes()
-        n = _Node((a.shape, a.dtype, len(raw), self.pos if raw else UNDEF))
+        chunked = bool(checksum) and len(raw) > 0 and a.ndim > 0
+        if chunked:
+            raw += struct.pack('<I', fletcher32(raw))
+        n = _Node((a.shape, a.dtype, len(raw), self.pos if raw else UNDEF, chunked))
         self.fh.write(_pad8(raw))
         self.pos += len(raw) + (-len(raw) % 8)
         n.attrs.update(attrs)
@@ -489,10 +497,24 @@ class H5Writer:
     def _write_node(self, node):
         """-> (object header address, B-tree address, heap address); the latter two 0 for a dataset"""
         if node.data is not None:
-            shape, dtype, n_bytes, addr = node.data
-            msgs = [(0x0001, 0, _encode_space(shape)), (0x0003, 1, _encode_dtype(dtype)),
-                    (0x0005, 1, struct.pack('<BBBBI', 2, 1, 2, 1, 0)),
-                    (0x0008, 0, struct.pack('<BBQQ', 3, 1, addr, n_bytes))]
+            shape, dtype, n_bytes, addr, chunked = node.data
+            msgs = [(0x0001, 0, _encode_space(shape)), (0x0003, 1, _encode_dtype(dtype))]
+            if chunked:
+                # chunk B-tree (node type 1) with one entry: key (chunk bytes, filter mask, offsets + 0), child, end key
+                nd = len(shape)
+                key = 8 + 8 * (nd + 1)
+                blob = b'TREE' + struct.pack('<BBHQQ', 1, 0, 1, UNDEF, UNDEF)
+                blob += struct.pack('<II', n_bytes, 0) + struct.pack('<%dQ' % (nd + 1), *([0] * (nd + 1))) + struct.pack('<Q', addr)
+                blob += struct.pack('<II', 0, 0) + struct.pack('<%dQ' % (nd + 1), *(list(shape) + [dtype.itemsize]))
+                blob += b'\0' * (24 + 2 * self.CHUNK_K * 8 + (2 * self.CHUNK_K + 1) * key - len(blob))
+                btree = self._alloc(blob)
+                msgs += [(0x0005, 1, struct.pack('<BBBBI', 2, 3, 2, 1, 0)),
+                         (0x000B, 1, struct.pack('<BB6xHHHH', 1, 1, 3, 16, 0, 0) + b'fletcher32'.ljust(16, b'\0')),
+                         (0x0008, 0, struct.pack('<BBBQ', 3, 2, nd + 1, btree) +
+                          struct.pack('<%dI' % (nd + 1), *(list(shape) + [dtype.itemsize])))]
+            else:
+                msgs += [(0x0005, 1, struct.pack('<BBBBI', 2, 1, 2, 1, 0)),
+                         (0x0008, 0, struct.pack('<BBQQ', 3, 1, addr, n_bytes))]
             return self._header(msgs + self._attr_messages(node.attrs)), 0, 0
         # children first, then the local heap of their names, the symbol nodes and the B-tree over them
         names = sorted(node.children, key=lambda s: s.encode())

@@ -77,3 +77,32 @@ def test_chunk_checksums_written_by_libhdf5_verify_and_catch_corruption(tmp_path
     bad.verify_checksums = False
     assert bad.read('/geometry/x_n').shape == (27, 3)
     assert fletcher32(b'') == 0 and fletcher32(b'\x01') == 0x01000100 and fletcher32(b'\x00\x01\x00\x02') == 0x00040003
+
+
+def test_checksummed_datasets_are_stored_like_libhdf5_stores_them(tmp_path):
+    """H5Writer.dataset(checksum=True) against the DAMASK-written fixture: writing the fixture's own x_n back gives the same
+    fill-value, filter and layout messages and the same chunk B-tree node (header, first key with the chunk size that
+    includes the checksum, end key) as libhdf5 produced -- byte for byte, addresses aside."""
+    import struct
+    from solver_cpp_b200.hdf5_min import H5Writer
+    real = H5File(PATH)
+    x_n = real.read('/geometry/x_n')
+    w = H5Writer()
+    w.dataset('/geometry/x_n', x_n, checksum=True)
+    w.dataset('/plain', x_n)
+    path = str(tmp_path / 'c.hdf5')
+    w.save(path)
+    mine = H5File(path)
+    assert np.array_equal(mine.read('/geometry/x_n'), x_n) and np.array_equal(mine.read('/plain'), x_n)
+    m_real = {t: d for t, _, d in real._messages(real._resolve('/geometry/x_n')) if t in (0x5, 0xB, 0x8)}
+    m_mine = {t: d for t, _, d in mine._messages(mine._resolve('/geometry/x_n')) if t in (0x5, 0xB, 0x8)}
+    assert m_real[0x5] == m_mine[0x5] and m_real[0xB] == m_mine[0xB]
+    assert m_real[0x8][:3] == m_mine[0x8][:3] and m_real[0x8][11:] == m_mine[0x8][11:]
+    key = 8 + 8 * 3
+    node = lambda f, lay: f.b[struct.unpack_from('<Q', lay, 3)[0]:][:24 + key + 8 + key]
+    a, b = node(real, m_real[0x8]), node(mine, m_mine[0x8])
+    assert a[:24 + key] == b[:24 + key] and a[24 + key + 8:] == b[24 + key + 8:]
+    assert struct.unpack_from('<I', b, 24)[0] == x_n.nbytes + 4
+    # and the stored checksum is the one libhdf5 computed for the same bytes
+    chunk = lambda f, n: f.b[struct.unpack_from('<Q', n, 24 + key)[0]:][:x_n.nbytes + 4]
+    assert chunk(real, a) == chunk(mine, b)
