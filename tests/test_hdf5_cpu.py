@@ -106,3 +106,18 @@ def test_checksummed_datasets_are_stored_like_libhdf5_stores_them(tmp_path):
     # and the stored checksum is the one libhdf5 computed for the same bytes
     chunk = lambda f, n: f.b[struct.unpack_from('<Q', n, 24 + key)[0]:][:x_n.nbytes + 4]
     assert chunk(real, a) == chunk(mine, b)
+
+
+def test_attribute_messages_equal_the_ones_libhdf5_wrote():
+    """integer and float scalar attributes: the whole attribute message (name, datatype, dataspace, value) byte for byte"""
+    from solver_cpp_b200.hdf5_min import H5Writer
+    real = H5File(PATH)
+    w = H5Writer()
+    w.group('/', DADF5_version_major=np.int64(1))
+    w.group('/increment_2', **{'t/s': 100.0})
+    mine = H5File.__new__(H5File)
+    mine.b = w.tobytes()
+    mine.root = mine._symbol_entry(56)
+    attr = lambda f, p, name: [d for t, _, d in f._messages(f._resolve(p)) if t == 0x000C and name in d][0]
+    assert attr(real, '/', b'DADF5_version_major') == attr(mine, '/', b'DADF5_version_major')
+    assert attr(real, '/increment_2', b't/s') == attr(mine, '/increment_2', b't/s')
