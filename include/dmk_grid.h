@@ -149,6 +149,11 @@ int dmk_constitutive_response(dmk_ctx* ctx, const double* d_F, double* d_P, doub
  * last dmk_constitutive_response; host outputs, Fortran order; d_dPdF (81 doubles/cell) is optional. */
 int dmk_tangent_response(dmk_ctx* ctx, double dt, double* C_volAvg, double* C_minMaxAvg, double* d_dPdF,
                          long long minmax_cells[2]);
+/* the same reductions on GIVEN device fields, as Spectral::constitutive_response (spectral.cpp:160-218) runs them over
+ * homogenization_P / homogenization_dPdF: d_P records [cell][9], d_dPdF [cell][81] in the reference's Fortran order;
+ * n_cells = cells of this rank's slab; host outputs in Fortran order; minmax_cells = global indices of the two cells */
+int dmk_homogenise(dmk_ctx* ctx, const double* d_P, const double* d_dPdF, long long n_cells, double* P_av, double* C_volAvg,
+                   double* C_minMaxAvg, long long minmax_cells[2]);
 int dmk_materialpoint_forward(dmk_ctx* ctx);                       /* f_materialpoint_forward */
 /* host copy, cell-major [cell][component]: "F","F0","Fp","Fp0","Fe","Lp","Lp0","S","S0" (row-major 3x3), "state","state0",
  * "dep", and "cutbacks" (sub-step cut-backs of each cell in the last response call) */
@@ -217,6 +222,7 @@ int dmk_mech_copy_field(dmk_ctx* ctx, const char* what, double* d_dst);      /* 
 int dmk_mech_capture(dmk_ctx* ctx, int enable);
 int dmk_mech_get_capture(dmk_ctx* ctx, double* F_out, double* r_out, size_t max_evals, size_t* n_evals);
 int dmk_mech_eval_log(dmk_ctx* ctx, double* out, size_t max_rows, size_t* n_rows); /* per evaluation: 9 P_av (row-major), err_div, err_BC, total_iter */
+int dmk_mech_eval_stats(dmk_ctx* ctx, double* out, size_t max_rows, size_t* n_rows); /* per evaluation: cells of this slab whose first sub-step failed (cut back), reserved */
 int dmk_mech_reports(dmk_ctx* ctx, double* out, size_t max_rows, size_t* n_rows);  /* per convergence check: total_iter, err_div, divTol, err_BC, BCTol, reason */
 
 /* ------------------------------------------------------------------ (1) Fortran-named drop-in symbols */

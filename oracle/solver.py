@@ -84,6 +84,8 @@ class MechSolverBasicOracle:
         self.err_div = self.err_BC = 0.0
         self.total_iter = 0
         self.tangent_every_eval = tangent_every_eval
+        self._tangent_dt = None
+        self.log_fields = True        # keep F and r of every evaluation in the log (tests); bench.py's CPU arm switches it off
         self.log = []                 # one dict per residual evaluation
         self.reports = []             # one dict per convergence check
         self.minmax_cells = None
@@ -92,14 +94,31 @@ class MechSolverBasicOracle:
     # ------------------------------------------------------------------ Spectral::constitutive_response
     def constitutive_response(self, F, dt):
         ill = self.con.mechanical_response(F, dt)
+        if not self.tangent_every_eval:
+            # what the device path does (and what bench.py's CPU arm times): dPdF and its reductions are consumed once per
+            # increment (mech_solver_basic.cpp:116, update_gamma = false), so they are formed when asked for, from the state
+            # the LAST evaluation left -- same values, 1/n_evaluations of the work
+            P, _ = self.con.mechanical_response2(dt, tangent=False)
+            self.P_av = sp.rotate2(self.params['R'], P.sum(axis=0) * self.grid.wgt)
+            self._tangent_dt = dt
+            self.P = P.reshape(self.shape)
+            return self.P
         P, dPdF = self.con.mechanical_response2(dt, tangent=True)
         self.P_av, self.C_volAvg, self.C_minMaxAvg, self.minmax_cells = sp.homogenise(P, dPdF, self.grid)
         self.P_av = sp.rotate2(self.params['R'], self.P_av)
         self.P = P.reshape(self.shape)
         return self.P
 
+    def ensure_tangent(self):
+        if self.tangent_every_eval or self._tangent_dt is None:
+            return
+        P, dPdF = self.con.mechanical_response2(self._tangent_dt, tangent=True)
+        _, self.C_volAvg, self.C_minMaxAvg, self.minmax_cells = sp.homogenise(P, dPdF, self.grid)
+        self._tangent_dt = None
+
     def init(self, gamma_pair_cells=None):
         self.constitutive_response(self.F, 0.0)
+        self.ensure_tangent()
         if gamma_pair_cells is not None:            # replay aid: force the two cells that define C_ref (V7)
             _, dPdF = self.con.mechanical_response2(0.0, tangent=True)
             a, b = gamma_pair_cells
@@ -127,7 +146,8 @@ class MechSolverBasicOracle:
         out = sp.gamma_hat_apply(hat, self.xi1st, self.C_ref)
         out[0, 0, 0] = sp.rotate2(R, delta_F_aim, active=True)
         r = sp.fft_backward(out, self.grid.cells, 1.0)
-        self.log.append(dict(F=F.copy(), r=r.copy(), P_av=self.P_av.copy(), err_div=self.err_div, err_BC=self.err_BC,
+        keep = self.log_fields
+        self.log.append(dict(F=F.copy() if keep else None, r=r.copy() if keep else None, P_av=self.P_av.copy(), err_div=self.err_div, err_BC=self.err_BC,
                              div_raw=raw, total_iter=self.total_iter, counters=self.con.counters.copy(),
                              ill=self.con.terminally_ill))
         return r.reshape(-1)
@@ -151,6 +171,7 @@ class MechSolverBasicOracle:
 
     # ------------------------------------------------------------------ calculate_solution
     def calculate_solution(self):
+        self.ensure_tangent()
         self.S = sp.masked_compliance(self.C_volAvg, self.params['R'], self.params['stress_mask'])
         if self.num['update_gamma']:
             self.update_gamma(self.C_minMaxAvg)
@@ -166,6 +187,7 @@ class MechSolverBasicOracle:
 
     # ------------------------------------------------------------------ forward
     def forward(self, cut_back, guess, dt, dt_old, t_remaining, deformation_bc, stress_bc, R):
+        self.ensure_tangent()
         if cut_back:
             self.C_volAvg = self.C_volAvgLastInc; self.C_minMaxAvg = self.C_minMaxAvgLastInc
         else:

@@ -23,8 +23,13 @@
 template <int LAW, int NS, int ND>
 __global__ void __launch_bounds__(DMK_PT_THREADS) dmk_constitutive_kernel(DmkPointArrays pa, int phase, DmkNumDev num,
                                                                           const double* __restrict__ Fin, double* __restrict__ Pout,
-                                                                          double Dt) {
+                                                                          double Dt, const int* __restrict__ list,
+                                                                          const unsigned* __restrict__ list_n, unsigned list_min) {
+  // list == nullptr: every cell of `phase`; else the *list_n cells of list[] (given up by the register-resident kernel), and
+  // only if there are more than list_min of them (fewer go through the nested kernel; the count is read on the device)
   const long long n = pa.n;
+  const long long total = list ? (long long)*list_n : n;
+  if (list && total <= (long long)list_min) return;
   const long long stride = (long long)gridDim.x * blockDim.x;
   DmkCnt cnt = {0, 0, 0, 0, 0, 0};
   unsigned ill = 0, cb0 = 0, lp0 = 0;
@@ -35,7 +40,7 @@ __global__ void __launch_bounds__(DMK_PT_THREADS) dmk_constitutive_kernel(DmkPoi
   m.p.ph = pa.d_phases + phase;
   m.p.C66 = m.p.ph->p.C66;
   const int ns = m.p.ph->p.n_state;
-  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x - stride;
+  long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x - stride, i = 0;
   bool have = false;
   for (;;) {
     while (m.state != M_LP && m.state != M_EXIT) {
@@ -58,8 +63,8 @@ __global__ void __launch_bounds__(DMK_PT_THREADS) dmk_constitutive_kernel(DmkPoi
           if constexpr (ND > 0) { const int nd = m.p.ph->n_dep; for (int k = 0; k < nd; k++) pa.dep[k * n + i] = m.p.dep[k]; }
           have = false;
         }
-        do { i += stride; } while (i < n && pa.phase[i] != phase);
-        if (i >= n) { m.state = M_EXIT; break; }
+        do { j += stride; i = (list && j < total) ? (long long)list[j] : j; } while (j < total && pa.phase[i] != phase);
+        if (j >= total) { m.state = M_EXIT; break; }
 #pragma unroll
         for (int a = 0; a < 3; a++)
 #pragma unroll
@@ -101,8 +106,10 @@ template <int LAW, int NS, int ND>
 __global__ void __launch_bounds__(DMK_PT_THREADS) dmk_constitutive_nested_kernel(DmkPointArrays pa, int phase, DmkNumDev num,
                                                                           const double* __restrict__ Fin, double* __restrict__ Pout,
                                                                           double Dt, const int* __restrict__ list,
-                                                                          const unsigned* __restrict__ list_n) {
-  // list == nullptr: every cell of `phase`; else the *list_n cells of list[] (deferred by the register-resident kernel)
+                                                                          const unsigned* __restrict__ list_n, unsigned list_max) {
+  // list == nullptr: every cell of `phase`; else the *list_n cells of list[] (deferred by the register-resident kernel),
+  // unless there are more than list_max of them (then the lane-scheduled cut-back kernel has taken the list, pheno_fast.cu)
+  if (list && *list_n > list_max) return;
   const long long n = pa.n;
   const long long total = list ? (long long)*list_n : n;
   DmkCnt cnt = {0, 0, 0, 0, 0, 0};
@@ -273,6 +280,21 @@ static int persistent_grid(K kernel, long long n) {
     else KERNEL<DMK_LAW_DISLOTWIN, DMK_MAX_STATE, DMK_MAX_DEP> __VA_ARGS__;                                     \
   } while (0)
 
+// device counter of the cells the register-resident kernel of the last evaluation gave up (their full first sub-step failed:
+// what the reference answers with a cut-back); 0 for phases that run in the reference-order kernel
+const unsigned* dmk_points_given_up_counter(dmk_ctx* c) { return c->pts->d_defer_count; }
+
+// DMK_PHENO_MASS: which kernel takes the deferred list when it is long (see cutback_setting() in pheno_fast.cu):
+//   machine (default)  the reference-order arithmetic (9x9 LU, the oracle's operation order) on the lane-persistent state
+//                      machine (machine_dev.cuh): bit-identical to the nested kernel, so parity on cut-back cells is unchanged
+//   lanes              the register-resident 6x6 formulation with in-lane cut-backs: fastest, follows the oracle on fewer of
+//                      the rounding-chaotic cut-back cells
+//   nested             no special treatment: the one-thread-per-point kernel whatever the length of the list
+int dmk_mass_deferral_setting() {
+  static const int v = [] { const char* e = getenv("DMK_PHENO_MASS"); return !e ? 1 : std::string(e) == "lanes" ? 2 : std::string(e) == "nested" ? 0 : 1; }();
+  return v;
+}
+
 int dmk_wait_staged_input(dmk_ctx* c, const double* d_F) {
   if (c->stage_chunks > 1 && d_F == c->stage_dst) DMK_CUDA_CHECK(cudaStreamWaitEvent(c->stream, c->stage_ev[c->stage_chunks - 1], 0));
   return DMK_OK;
@@ -289,18 +311,24 @@ int dmk_points_constitutive(dmk_ctx* c, const double* d_F, double* d_P, double d
     if (pa.n_cells_of_phase[ph] == 0) continue;
     const int law = pa.law_of_phase[ph], nst = pa.nstate_of_phase[ph];
     bool handled = false, deferred = false;
-    if (!use_generic && nd.integrator == DMK_INTEG_FPI) { int rc = dmk_points_pheno_fast(c, ph, nd, d_F, d_P, dt, &handled, &deferred); if (rc) return rc; }
+    unsigned defer_max = 0xffffffffu;
+    if (!use_generic && nd.integrator == DMK_INTEG_FPI) { int rc = dmk_points_pheno_fast(c, ph, nd, d_F, d_P, dt, &handled, &deferred, &defer_max); if (rc) return rc; }
     if (handled) {
       c->launches++;
       if (deferred) {          // second pass over the deferred cells only (count read on the device: no host round trip)
-        DMK_DISPATCH(dmk_constitutive_nested_kernel, law, nst, <<<148 * 4, DMK_PT_THREADS, 0, c->stream>>>(pa, ph, nd, d_F, d_P, dt, pa.defer_list, pa.d_defer_count));
+        if (defer_max != 0xffffffffu && dmk_mass_deferral_setting() == 1 && nd.integrator == DMK_INTEG_FPI) {
+          // mass deferral (more than defer_max cells): the reference-order arithmetic on the lane-persistent state machine
+          DMK_LAUNCH_PERSISTENT(dmk_constitutive_kernel, law, nst, pa.n, c->stream, (pa, ph, nd, d_F, d_P, dt, pa.defer_list, pa.d_defer_count, defer_max));
+          c->launches++;
+        }
+        DMK_DISPATCH(dmk_constitutive_nested_kernel, law, nst, <<<148 * 4, DMK_PT_THREADS, 0, c->stream>>>(pa, ph, nd, d_F, d_P, dt, pa.defer_list, pa.d_defer_count, defer_max));
         c->launches++;
       }
       continue;
     }
     { int rc = dmk_wait_staged_input(c, d_F); if (rc) return rc; }
-    if (use_machine) DMK_LAUNCH_PERSISTENT(dmk_constitutive_kernel, law, nst, pa.n, c->stream, (pa, ph, nd, d_F, d_P, dt));
-    else DMK_DISPATCH(dmk_constitutive_nested_kernel, law, nst, <<<point_grid(pa.n), DMK_PT_THREADS, 0, c->stream>>>(pa, ph, nd, d_F, d_P, dt, nullptr, nullptr));
+    if (use_machine) DMK_LAUNCH_PERSISTENT(dmk_constitutive_kernel, law, nst, pa.n, c->stream, (pa, ph, nd, d_F, d_P, dt, nullptr, nullptr, 0u));
+    else DMK_DISPATCH(dmk_constitutive_nested_kernel, law, nst, <<<point_grid(pa.n), DMK_PT_THREADS, 0, c->stream>>>(pa, ph, nd, d_F, d_P, dt, nullptr, nullptr, 0u));
     c->launches++;
   }
   DMK_CUDA_CHECK(cudaGetLastError());
@@ -640,18 +668,13 @@ __global__ void dmk_minmax_index_kernel(const double* __restrict__ nrm, long lon
   if (imn != ~0ULL) atomicMin(&idx2[1], imn);
 }
 
-extern "C" int dmk_tangent_response(dmk_ctx* c, double dt, double* C_volAvg, double* C_minMaxAvg, double* d_dPdF,
-                                    long long minmax_cells[2]) {
-  int rc = need_points(c); if (rc) return rc;
-  DmkPointArrays& pa = *c->pts;
-  double* d_sum = c->d_scratch + DMK_SCRATCH_TMP;               // 81
+// arg-max / arg-min of a per-cell norm with the shared tie rule, global over ranks: values within `tol` (relative) of the
+// extreme are ties -> lowest global cell index (oracle/spectral.py select_minmax)
+static int select_minmax(dmk_ctx* c, const double* d_nrm, long long n, long long gidx[2]) {
   double* d_mm = c->d_scratch + DMK_SCRATCH_TMP + 96;           // 2 values + 2 indices
-  if ((rc = dmk_points_tangent(c, dt, d_sum, d_dPdF))) return rc;
-  if (c->P > 1) { if (c->comm.allreduce_sum(c->comm.user, d_sum, 81)) { dmk_set_error("allreduce failed"); return DMK_ERR_STATE; } }
-  // extremes of the norm
   double init[2] = {0.0, INFINITY};
   DMK_CUDA_CHECK(cudaMemcpyAsync(d_mm, init, sizeof init, cudaMemcpyHostToDevice, c->stream));
-  dmk_minmax_value_kernel<<<148 * 4, 256, 0, c->stream>>>(pa.nrm, pa.n, d_mm);
+  dmk_minmax_value_kernel<<<148 * 4, 256, 0, c->stream>>>(d_nrm, n, d_mm);
   c->launches++;
   if (c->P > 1) {
     // max over ranks of (vmax, -vmin)
@@ -673,11 +696,11 @@ extern "C" int dmk_tangent_response(dmk_ctx* c, double dt, double* C_volAvg, dou
   unsigned long long* d_idx = (unsigned long long*)(d_mm + 2);
   DMK_CUDA_CHECK(cudaMemcpyAsync(d_idx, hidx, sizeof hidx, cudaMemcpyHostToDevice, c->stream));
   const long long offset = (long long)c->z_off * c->nx * c->ny;
-  dmk_minmax_index_kernel<<<148 * 4, 256, 0, c->stream>>>(pa.nrm, pa.n, offset, hv[0], hv[1], 1.0e-12, d_idx);
+  dmk_minmax_index_kernel<<<148 * 4, 256, 0, c->stream>>>(d_nrm, n, offset, hv[0], hv[1], 1.0e-12, d_idx);
   c->launches++;
   DMK_CUDA_CHECK(cudaMemcpyAsync(hidx, d_idx, sizeof hidx, cudaMemcpyDeviceToHost, c->stream));
   DMK_CUDA_CHECK(cudaStreamSynchronize(c->stream));
-  long long gidx[2] = {hidx[0] == ~0ULL ? -1 : (long long)hidx[0], hidx[1] == ~0ULL ? -1 : (long long)hidx[1]};
+  gidx[0] = hidx[0] == ~0ULL ? -1 : (long long)hidx[0]; gidx[1] = hidx[1] == ~0ULL ? -1 : (long long)hidx[1];
   if (c->P > 1) {
     // lowest global index over ranks: max of the negated index (exact in a double below 2^53)
     double h[2] = {gidx[0] < 0 ? -9.0e15 : -(double)gidx[0], gidx[1] < 0 ? -9.0e15 : -(double)gidx[1]};
@@ -687,6 +710,20 @@ extern "C" int dmk_tangent_response(dmk_ctx* c, double dt, double* C_volAvg, dou
     DMK_CUDA_CHECK(cudaStreamSynchronize(c->stream));
     gidx[0] = (long long)(-h[0]); gidx[1] = (long long)(-h[1]);
   }
+  return DMK_OK;
+}
+
+extern "C" int dmk_tangent_response(dmk_ctx* c, double dt, double* C_volAvg, double* C_minMaxAvg, double* d_dPdF,
+                                    long long minmax_cells[2]) {
+  int rc = need_points(c); if (rc) return rc;
+  DmkPointArrays& pa = *c->pts;
+  if (c->P > 1 && (!c->has_comm || !c->comm.allreduce_sum || !c->comm.allreduce_max)) { dmk_set_error("no allreduce callbacks (dmk_set_comm)"); return DMK_ERR_STATE; }
+  double* d_sum = c->d_scratch + DMK_SCRATCH_TMP;               // 81
+  if ((rc = dmk_points_tangent(c, dt, d_sum, d_dPdF))) return rc;
+  if (c->P > 1) { if (c->comm.allreduce_sum(c->comm.user, d_sum, 81)) { dmk_set_error("allreduce failed"); return DMK_ERR_STATE; } }
+  long long gidx[2];
+  if ((rc = select_minmax(c, pa.nrm, pa.n, gidx))) return rc;
+  const long long offset = (long long)c->z_off * c->nx * c->ny;
   if (minmax_cells) { minmax_cells[0] = gidx[0]; minmax_cells[1] = gidx[1]; }
   // dPdF of the two selected cells (owner computes, everyone receives through a sum)
   double* d_two = c->d_scratch + DMK_SCRATCH_TMP + 112;          // 2 x 81 -> up to TMP+274: keep inside the MECH gap
@@ -702,5 +739,79 @@ extern "C" int dmk_tangent_response(dmk_ctx* c, double dt, double* C_volAvg, dou
   DMK_CUDA_CHECK(cudaStreamSynchronize(c->stream));
   if (C_volAvg) { for (int k = 0; k < 81; k++) r[k] = hs[k] * c->wgt; c2f3333(r, C_volAvg); }
   if (C_minMaxAvg) { for (int k = 0; k < 81; k++) r[k] = 0.5 * (ht[k] + ht[81 + k]); c2f3333(r, C_minMaxAvg); }
+  return DMK_OK;
+}
+
+// ---- the reductions of Spectral::constitutive_response (/root/reference/src/grid/spectral.cpp:160-218) on GIVEN fields, as
+// the reference runs them over homogenization_P / homogenization_dPdF: P_av = wgt sum P, C_volAvg = wgt sum dPdF,
+// C_minMaxAvg = (dPdF at arg-max ||dPdF||^2 + dPdF at arg-min) / 2.  d_P: records [cell][9] (c = i + 3 j); d_dPdF: [cell][81] in
+// the reference's Fortran order (first index fastest).  Results in Fortran order; n_cells = this rank's cells.
+__global__ void __launch_bounds__(128) dmk_dPdF_reduce_kernel(const double* __restrict__ dPdF, long long n, double* __restrict__ nrm,
+                                                              double* __restrict__ partial) {
+  __shared__ double sh[81];
+  for (int k = threadIdx.x; k < 81; k += blockDim.x) sh[k] = 0.0;
+  __syncthreads();
+  // one warp per cell at a time: lanes over the 81 entries (coalesced), fixed order within a block's cells
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  double acc[3] = {0.0, 0.0, 0.0};
+  for (long long i = (long long)blockIdx.x * nw + warp; i < n; i += (long long)gridDim.x * nw) {
+    double q = 0.0;
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+      const int k = lane + 32 * j;
+      const double v = k < 81 ? dPdF[i * 81 + k] : 0.0;
+      acc[j] += v; q += v * v;
+    }
+    for (int off = 16; off > 0; off >>= 1) q += __shfl_xor_sync(0xffffffffu, q, off);
+    if (lane == 0) nrm[i] = q;
+  }
+  for (int w = 0; w < nw; w++) {                          // warps add their sums one after the other: deterministic
+    if (warp == w) {
+#pragma unroll
+      for (int j = 0; j < 3; j++) { const int k = lane + 32 * j; if (k < 81) sh[k] += acc[j]; }
+    }
+    __syncthreads();
+  }
+  for (int k = threadIdx.x; k < 81; k += blockDim.x) partial[(size_t)blockIdx.x * 81 + k] = sh[k];
+}
+
+extern "C" int dmk_homogenise(dmk_ctx* c, const double* d_P, const double* d_dPdF, long long n_cells, double* P_av, double* C_volAvg,
+                              double* C_minMaxAvg, long long minmax_cells[2]) {
+  if (!c || !d_P || !d_dPdF || n_cells < 1) { dmk_set_error("dmk_homogenise: bad argument"); return DMK_ERR_ARG; }
+  if (c->P > 1 && (!c->has_comm || !c->comm.allreduce_sum || !c->comm.allreduce_max)) { dmk_set_error("no allreduce callbacks (dmk_set_comm)"); return DMK_ERR_STATE; }
+  int rc;
+  double* d_sum9 = c->d_scratch + DMK_SCRATCH_SUM9;
+  double* d_sum = c->d_scratch + DMK_SCRATCH_TMP;                // 81
+  double* partial = c->d_scratch + DMK_SCRATCH_PARTIAL;
+  double* d_nrm = nullptr;
+  DMK_CUDA_CHECK(cudaMalloc((void**)&d_nrm, n_cells * sizeof(double)));
+  if ((rc = dmk_sum_records(c, d_P, n_cells, d_sum9))) { cudaFree(d_nrm); return rc; }
+  const int grid = (int)std::max(1LL, std::min((n_cells + 3) / 4, (long long)DMK_TANGENT_BLOCKS));
+  dmk_dPdF_reduce_kernel<<<grid, 128, 0, c->stream>>>(d_dPdF, n_cells, d_nrm, partial);
+  dmk_sum_partials_kernel<<<1, 96, 0, c->stream>>>(partial, grid, 81, d_sum);
+  c->launches += 2;
+  if (c->P > 1) {
+    if (c->comm.allreduce_sum(c->comm.user, d_sum9, 9) || c->comm.allreduce_sum(c->comm.user, d_sum, 81)) { cudaFree(d_nrm); dmk_set_error("allreduce failed"); return DMK_ERR_STATE; }
+  }
+  long long gidx[2];
+  if ((rc = select_minmax(c, d_nrm, n_cells, gidx))) { cudaFree(d_nrm); return rc; }
+  cudaFree(d_nrm);
+  if (minmax_cells) { minmax_cells[0] = gidx[0]; minmax_cells[1] = gidx[1]; }
+  const long long offset = (long long)c->z_off * c->nx * c->ny;
+  double* d_two = c->d_scratch + DMK_SCRATCH_TMP + 112;
+  DMK_CUDA_CHECK(cudaMemsetAsync(d_two, 0, 162 * sizeof(double), c->stream));
+  for (int k = 0; k < 2; k++) {
+    const long long loc = gidx[k] - offset;
+    if (loc >= 0 && loc < n_cells) DMK_CUDA_CHECK(cudaMemcpyAsync(d_two + 81 * k, d_dPdF + loc * 81, 81 * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+  }
+  if (c->P > 1) { if (c->comm.allreduce_sum(c->comm.user, d_two, 162)) { dmk_set_error("allreduce failed"); return DMK_ERR_STATE; } }
+  double h9[9], hs[81], ht[162];
+  DMK_CUDA_CHECK(cudaMemcpyAsync(h9, d_sum9, sizeof h9, cudaMemcpyDeviceToHost, c->stream));
+  DMK_CUDA_CHECK(cudaMemcpyAsync(hs, d_sum, sizeof hs, cudaMemcpyDeviceToHost, c->stream));
+  DMK_CUDA_CHECK(cudaMemcpyAsync(ht, d_two, sizeof ht, cudaMemcpyDeviceToHost, c->stream));
+  DMK_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+  if (P_av) for (int k = 0; k < 9; k++) P_av[k] = h9[k] * c->wgt;                               // record order == Fortran order
+  if (C_volAvg) for (int k = 0; k < 81; k++) C_volAvg[k] = hs[k] * c->wgt;                       // the field is in Fortran order already
+  if (C_minMaxAvg) for (int k = 0; k < 81; k++) C_minMaxAvg[k] = 0.5 * (ht[k] + ht[81 + k]);
   return DMK_OK;
 }

@@ -62,7 +62,9 @@ struct DmkNumDev {
 int dmk_points_constitutive(dmk_ctx* c, const double* d_F, double* d_P, double dt);
 int dmk_wait_staged_input(dmk_ctx* c, const double* d_F);   // kernels without chunked launches: wait for the whole staged field
 int dmk_points_pheno_fast(dmk_ctx* c, int ph, const DmkNumDev& nd, const double* d_F, double* d_P, double dt, bool* handled,
-                          bool* deferred /*out: cells may be waiting in pa.defer_list*/);
+                          bool* deferred /*out: cells may be waiting in pa.defer_list*/,
+                          unsigned* defer_max /*out: the reference-order kernel takes the list only if it holds at most this many*/);
+int dmk_mass_deferral_setting();     // 0 nested, 1 machine (default), 2 lanes: who takes a long deferred list (constitutive.cu)
 int dmk_points_tangent(dmk_ctx* c, double dt, double* d_Csum81 /*device, row-major sum over local cells*/,
                        double* d_dPdF /*optional [n][81] Fortran order*/);
 int dmk_points_tangent_cell(dmk_ctx* c, double dt, long long cell, double* d_out81 /*row-major*/);

@@ -37,6 +37,7 @@ struct dmk_ctx {
   double* d_Cref;                 // 81, row-major C_ref(l,n,m,o)
   double* d_dc;                   // 9, record order
   double* d_div;                  // 1
+  double* d_div_partial;          // per-CTA divergence sums of the fused z pass (nxr * ny_loc doubles: one per tile at most)
   double* d_scratch;              // small device scratch (>= 4096 doubles)
   double* h_pinned;               // small pinned host scratch (>= 4096 doubles)
   bool gamma_set;
@@ -63,6 +64,7 @@ int dmk_fft_forward_internal(dmk_ctx* c, const double* d_real);
 int dmk_fft_backward_internal(dmk_ctx* c, double* d_real, double scale);
 int dmk_gamma_internal(dmk_ctx* c);     // fused z pass on c->bufA using c->d_dc, accumulating into c->d_div
 double dmk_finish_div(dmk_ctx* c, double raw_sum);
+const unsigned* dmk_points_given_up_counter(dmk_ctx* c);
 int dmk_mech_before_point_forward(dmk_ctx* c);   // computes the pending tangent reductions before state0 <- state
 
 // Fortran-order <-> row-major helpers for small host tensors

@@ -50,6 +50,11 @@ struct DmkGammaParams {
   int ky_offset;               // global ky index of local ky 0 (slab decomposition)
   const double* dc_value;      // device, 9 doubles in record order c = i + 3 j: value written to the k = 0 coefficient
   double* div_accum;           // device, 1 double: += sum_k w_k |P_hat(k) . conj(-xi1st) rescale|^2
+  double* div_partial;         // device, one double per CTA of the pass: the CTA's share of that sum (see dmk_sum_div_partials)
 };
+// Adds the per-CTA divergence sums to *div_accum in a FIXED order (strided per-thread sums, then a fixed tree), so the sum --
+// and with it the convergence test err_div / divTol < 1 and the iteration count -- does not depend on the order in which the
+// CTAs finish (a floating-point atomicAdd per CTA did).
+int dmk_sum_div_partials(const double* partial, int n, double* div_accum, cudaStream_t st);
 int dmk_launch_gamma_zpass(double2* data, const DmkFftPlan& plz, DmkLineMap map, int n0, int n_outer, int KT,
                            const DmkGammaParams& gp, cudaStream_t st, bool imag_xi, const DmkPeerStore* ps = nullptr);

@@ -79,7 +79,7 @@ __global__ void __launch_bounds__(NT, MINB) dmk_fast_gamma_kernel(double2* __res
   }
   __syncthreads();
   fstage<N, R1, R2 * R3, B, true, true>(1, bact, tw, lds, stg);
-  // ---- block reduction of the divergence sum, one atomic per CTA
+  // ---- block reduction of the divergence sum; the CTAs' sums are added up in a fixed order afterwards (dmk_sum_div_partials)
   for (int off = 16; off > 0; off >>= 1) div_local += __shfl_down_sync(0xffffffffu, div_local, off);
   if ((threadIdx.x & 31) == 0) sred[threadIdx.x >> 5] = div_local;
   __syncthreads();
@@ -87,7 +87,7 @@ __global__ void __launch_bounds__(NT, MINB) dmk_fast_gamma_kernel(double2* __res
     double tot = 0.0;
 #pragma unroll
     for (int w = 0; w < NT / 32; w++) tot += sred[w];
-    atomicAdd(gp.div_accum, tot);
+    gp.div_partial[blockIdx.x] = tot;
   }
 }
 
@@ -107,7 +107,7 @@ static int launch_gamma(double2* data, const DmkFftPlan& pl, DmkLineMap map, int
   else { if (ps.remote) DMK_GAMMA_LAUNCH(false, true); else DMK_GAMMA_LAUNCH(false, false); }
 #undef DMK_GAMMA_LAUNCH
   DMK_CUDA_CHECK(cudaGetLastError());
-  return DMK_OK;
+  return dmk_sum_div_partials(gp.div_partial, (int)grid, gp.div_accum, st);
 }
 
 int dmk_fast_gamma_zpass(double2* data, const DmkFftPlan& plz, DmkLineMap map, int n0, int n_outer, const DmkGammaParams& gp,

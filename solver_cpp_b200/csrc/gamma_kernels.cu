@@ -80,8 +80,26 @@ __global__ void __launch_bounds__(256, 2) dmk_gamma_zpass_kernel(double2* __rest
   if (threadIdx.x == 0) {
     double tot = 0.0;
     for (int w = 0; w < (blockDim.x >> 5); w++) tot += sred[w];
-    atomicAdd(gp.div_accum, tot);
+    gp.div_partial[blockIdx.x] = tot;
   }
+}
+
+__global__ void __launch_bounds__(1024) dmk_sum_div_partials_kernel(const double* __restrict__ partial, int n, double* __restrict__ accum) {
+  __shared__ double sh[1024];
+  double a = 0.0;
+  for (int i = threadIdx.x; i < n; i += 1024) a += partial[i];
+  sh[threadIdx.x] = a;
+  __syncthreads();
+  for (int w = 512; w > 0; w >>= 1) {
+    if ((int)threadIdx.x < w) sh[threadIdx.x] += sh[threadIdx.x + w];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *accum += sh[0];
+}
+int dmk_sum_div_partials(const double* partial, int n, double* div_accum, cudaStream_t st) {
+  dmk_sum_div_partials_kernel<<<1, 1024, 0, st>>>(partial, n, div_accum);
+  DMK_CUDA_CHECK(cudaGetLastError());
+  return DMK_OK;
 }
 
 
@@ -120,5 +138,5 @@ int dmk_launch_gamma_zpass(double2* data, const DmkFftPlan& plz, DmkLineMap map,
     dmk_gamma_zpass_kernel<false><<<grid, 256, smem, st>>>(data, plz, map, n0, n_outer, KT, gp);
   }
   DMK_CUDA_CHECK(cudaGetLastError());
-  return DMK_OK;
+  return dmk_sum_div_partials(gp.div_partial, grid, gp.div_accum, st);
 }

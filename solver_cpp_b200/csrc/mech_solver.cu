@@ -43,6 +43,7 @@ struct DmkMech {
   long long minmax_cells[2];
   std::vector<double> log;                           // 12 doubles per evaluation
   std::vector<double> reports;                       // 6 doubles per convergence check
+  std::vector<double> stats;                         // 2 doubles per evaluation: cells of this slab whose first sub-step failed, 0
   int snes_its; int snes_reason;
   bool capture;                                      // test aid: keep host copies of every evaluation's F and r
   std::vector<double> capF, capR;
@@ -150,8 +151,9 @@ __global__ void dmk_mech_aim_kernel(double* __restrict__ blk, double wgt, double
   for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) { double s = 0; for (int k = 0; k < 3; k++) s += t[3 * i + k] * R[3 * k + j]; dc_out[i + 3 * j] = s; }
   *div_in = 0.0;
 }
-__global__ void dmk_mech_collect_kernel(double* __restrict__ blk, const double* __restrict__ div) {
+__global__ void dmk_mech_collect_kernel(double* __restrict__ blk, const double* __restrict__ div, const unsigned* __restrict__ given_up) {
   if (threadIdx.x == 0 && blockIdx.x == 0) {
+    blk[B_OUT + 20] = (double)*given_up;
     for (int a = 0; a < 9; a++) { blk[B_OUT + a] = blk[B_PAV + a]; blk[B_OUT + 9 + a] = blk[B_FAIM + a]; }
     blk[B_OUT + 18] = blk[B_ERRBC]; blk[B_OUT + 19] = *div;
   }
@@ -280,10 +282,11 @@ static int evaluate(dmk_ctx* c, const double* d_F, double* d_r) {
   if (c->P > 1) { if (c->comm.allreduce_sum(c->comm.user, c->d_div, 1)) { dmk_set_error("allreduce failed"); return DMK_ERR_STATE; } }
   if ((rc = dmk_fft_backward_internal(c, d_r, 1.0))) return rc;
   PROF(5);
-  dmk_mech_collect_kernel<<<1, 32, 0, c->stream>>>(m->d_blk, c->d_div);
+  dmk_mech_collect_kernel<<<1, 32, 0, c->stream>>>(m->d_blk, c->d_div, dmk_points_given_up_counter(c));
   c->launches++;
-  DMK_CUDA_CHECK(cudaMemcpyAsync(c->h_pinned, m->d_blk + B_OUT, 20 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  DMK_CUDA_CHECK(cudaMemcpyAsync(c->h_pinned, m->d_blk + B_OUT, 21 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
   DMK_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+  { const double st[2] = {c->h_pinned[20], 0.0}; m->stats.insert(m->stats.end(), st, st + 2); }
   for (int a = 0; a < 9; a++) { m->P_av[a] = c->h_pinned[a]; m->F_aim[a] = c->h_pinned[9 + a]; }
   m->err_BC = c->h_pinned[18]; m->div_raw = c->h_pinned[19];
   if (c->profiling) {      // sections: constitutive | P sum + aim | forward FFT (x, y) | fused z + Gamma + div | inverse FFT (y, x)
@@ -739,6 +742,13 @@ extern "C" int dmk_mech_eval_log(dmk_ctx* c, double* out, size_t max_rows, size_
   const size_t rows = c->mech->log.size() / 12;
   if (n_rows) *n_rows = rows;
   if (out) memcpy(out, c->mech->log.data(), std::min(rows, max_rows) * 12 * sizeof(double));
+  return DMK_OK;
+}
+extern "C" int dmk_mech_eval_stats(dmk_ctx* c, double* out, size_t max_rows, size_t* n_rows) {
+  int rc = need_mech(c); if (rc) return rc;
+  const size_t rows = c->mech->stats.size() / 2;
+  if (n_rows) *n_rows = rows;
+  if (out) memcpy(out, c->mech->stats.data(), std::min(rows, max_rows) * 2 * sizeof(double));
   return DMK_OK;
 }
 extern "C" int dmk_mech_reports(dmk_ctx* c, double* out, size_t max_rows, size_t* n_rows) {

@@ -91,8 +91,15 @@ template <int NSL, int NEXP, int UNR, bool VOTE3, bool CUTBACK>
 __global__ void __launch_bounds__(DMK_PL_THREADS, DMK_PL_MINBLOCKS)
 dmk_pheno_lanes_kernel(const __grid_constant__ DmkPhenoK<NSL> K, DmkPointArrays pa, int phase, DmkNumDev num,
                        const double* __restrict__ Fin, double* __restrict__ Pout, double Dt, long long cell_begin,
-                       long long cell_end, int3 vw) {
-  // cells [cell_begin, cell_end) are this launch's share (whole slab, or one staged z-chunk); *pa.d_work counts from 0
+                       long long cell_end, int3 vw, const int* __restrict__ list, const unsigned* __restrict__ list_n,
+                       unsigned list_min) {
+  // cells [cell_begin, cell_end) are this launch's share (whole slab, or one staged z-chunk); *pa.d_work counts from 0.
+  // list != nullptr: the share is list[0 .. *list_n) instead (the cells an earlier launch gave up), and the launch does
+  // nothing unless there are more than list_min of them (the decision is made on the device: no host round trip)
+  if (list) {
+    cell_begin = 0; cell_end = (long long)*list_n;
+    if (cell_end <= (long long)list_min) return;
+  }
   extern __shared__ double pf_sm[];
   const DmkScr scr = {pf_sm + threadIdx.x, DMK_PL_THREADS};
   const unsigned FULL = 0xffffffffu, lane = threadIdx.x & 31u, lt = (1u << lane) - 1u;
@@ -163,7 +170,7 @@ dmk_pheno_lanes_kernel(const __grid_constant__ DmkPhenoK<NSL> K, DmkPointArrays 
       const int avail = (int)min(32LL, c_end - c_next);
       const int rank = __popc(need & lt);
       if (L.mode == PL_NEED && rank < avail) {
-        const long long i = c_next + rank;
+        const long long i = list ? (long long)list[c_next + rank] : c_next + rank;
         if (pa.phase[i] == phase) { pl_fetch<NSL>(pa, num, i, L); L.mode = PL_RESTART; }
       }
       c_next += min(__popc(need), avail);
@@ -218,10 +225,16 @@ static int3 vote_weights() {
   return v;
 }
 
-// DMK_PHENO_CUTBACK=lanes: failed sub-steps are cut back in-lane (pheno_lanes_dev.cuh) instead of being handed to the
-// reference-order kernel (default)
-static bool cutback_setting() {
-  static const bool v = [] { const char* e = getenv("DMK_PHENO_CUTBACK"); return e && std::string(e) == "lanes"; }();
+// What happens to a point whose full first sub-step fails (the reference cuts back, phase_mechanical.f90:1040-1085):
+//   DMK_PHENO_CUTBACK=lanes    cut back in-lane, in the same launch (pheno_lanes_dev.cuh, CUTBACK = true)
+//   DMK_PHENO_CUTBACK=generic  always handed to the reference-order kernel (one thread per point, 9x9 LU)
+//   default (auto)             handed to the reference-order kernel while such points are few (a running solve: 0 - 2 % of the
+//                              cells); when more than 1/32 of the slab gave up -- the first evaluations after a virgin state,
+//                              where EVERY cell cuts back and the one-thread-per-point kernel needs 3.4 s at 256^3 -- the list
+//                              goes through a lane-scheduled kernel instead (DMK_PHENO_MASS, constitutive.cu).  Both launches
+//                              are issued; each reads the count on the device and returns at once if the list is not its share.
+static int cutback_setting() {
+  static const int v = [] { const char* e = getenv("DMK_PHENO_CUTBACK"); return !e ? 0 : std::string(e) == "lanes" ? 1 : std::string(e) == "generic" ? 2 : 0; }();
   return v;
 }
 
@@ -233,7 +246,7 @@ static bool lanes_setting() {
 
 template <int NSL, int NEXP, int UNR, bool VOTE3, bool CUTBACK>
 static int launch_pheno_lanes(dmk_ctx* c, DmkPointArrays& pa, int ph, const DmkDevPhase& d, const DmkNumDev& nd, const double* d_F,
-                              double* d_P, double dt) {
+                              double* d_P, double dt, bool from_list = false, unsigned list_min = 0) {
   DmkPhenoK<NSL> K;
   dmk_pheno_fast_tables<NSL>(d, K);
   const size_t smem = (size_t)PfOff<NSL>::TOTAL * DMK_PL_THREADS * sizeof(double);
@@ -245,6 +258,12 @@ static int launch_pheno_lanes(dmk_ctx* c, DmkPointArrays& pa, int ph, const DmkD
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, dmk_pheno_lanes_kernel<NSL, NEXP, UNR, VOTE3, CUTBACK>, DMK_PL_THREADS, smem) != cudaSuccess || occ < 1) occ = 1;
     grid = sms * occ;                                  // one resident wave
+  }
+  if (from_list) {                                     // the cells the launch before this one gave up (pa.defer_list), if they are many
+    DMK_CUDA_CHECK(cudaMemsetAsync(pa.d_work, 0, sizeof(unsigned long long), c->stream));
+    dmk_pheno_lanes_kernel<NSL, NEXP, UNR, VOTE3, CUTBACK><<<grid, DMK_PL_THREADS, smem, c->stream>>>(K, pa, ph, nd, d_F, d_P, dt, 0, 0, vote_weights(), pa.defer_list, pa.d_defer_count, list_min);
+    c->launches++;
+    return DMK_OK;
   }
   DMK_CUDA_CHECK(cudaMemsetAsync(pa.d_defer_count, 0, sizeof(unsigned), c->stream));
   // one launch over the slab, or one per staged z-chunk of F, each behind the event of its host-to-device copy
@@ -258,7 +277,7 @@ static int launch_pheno_lanes(dmk_ctx* c, DmkPointArrays& pa, int ph, const DmkD
     DMK_CUDA_CHECK(cudaMemsetAsync(pa.d_work, 0, sizeof(unsigned long long), c->stream));
     const long long warps_needed = (end - first + 31) / 32;
     const int g = (int)std::max(1LL, std::min((long long)grid, (warps_needed + 1) / 2));
-    dmk_pheno_lanes_kernel<NSL, NEXP, UNR, VOTE3, CUTBACK><<<g, DMK_PL_THREADS, smem, c->stream>>>(K, pa, ph, nd, d_F, d_P, dt, first, end, vote_weights());
+    dmk_pheno_lanes_kernel<NSL, NEXP, UNR, VOTE3, CUTBACK><<<g, DMK_PL_THREADS, smem, c->stream>>>(K, pa, ph, nd, d_F, d_P, dt, first, end, vote_weights(), nullptr, nullptr, 0u);
     if (k > 0) c->launches++;
   }
   return DMK_OK;
@@ -266,16 +285,17 @@ static int launch_pheno_lanes(dmk_ctx* c, DmkPointArrays& pa, int ph, const DmkD
 
 // Runs phase `ph` through the register-resident kernel if it qualifies (*handled), else leaves it to the generic kernel.
 int dmk_points_pheno_fast(dmk_ctx* c, int ph, const DmkNumDev& nd, const double* d_F, double* d_P, double dt, bool* handled,
-                          bool* deferred) {
+                          bool* deferred, unsigned* defer_max) {
   DmkPointArrays& pa = *c->pts;
   int nexp = 0;
-  *handled = false; *deferred = false;
+  *handled = false; *deferred = false; *defer_max = 0xffffffffu;
   if (!dmk_pheno_fast_eligible(pa.h_dev_phases[ph], 12, &nexp)) return DMK_OK;       // 12 slip systems: fcc, bcc {110}
   *handled = true; *deferred = defer_setting() > 0;
   const DmkDevPhase& d = pa.h_dev_phases[ph];
   const int u = unroll_setting();
   int rc;
-  const bool cb = cutback_setting();
+  const bool cb = cutback_setting() == 1;
+  const bool adaptive = cutback_setting() == 0 && dmk_pheno_lanes_eligible(nd, true);
   if (lanes_setting() && dmk_pheno_lanes_eligible(nd, cb)) {
     *deferred = !cb;                                    // in-lane cut-backs: nothing is handed to the reference-order kernel
 #define DMK_PL_LAUNCH(NEXP_)                                                                                   \
@@ -289,6 +309,15 @@ int dmk_points_pheno_fast(dmk_ctx* c, int ph, const DmkNumDev& nd, const double*
     rc = (nexp == 20) ? (DMK_PL_LAUNCH(20)) : (DMK_PL_LAUNCH(0));
 #undef DMK_PL_LAUNCH
     if (rc) return rc;
+    if (!cb && adaptive && dmk_mass_deferral_setting() != 0) {       // mass deferral
+      const unsigned many = (unsigned)std::min<long long>(pa.n / 32, 0x7fffffffLL);
+      if (dmk_mass_deferral_setting() == 2) {            // ... through the in-lane cut-back kernel (else: constitutive.cu)
+        rc = (nexp == 20) ? launch_pheno_lanes<12, 20, 1, true, true>(c, pa, ph, d, nd, d_F, d_P, dt, true, many)
+                          : launch_pheno_lanes<12, 0, 1, true, true>(c, pa, ph, d, nd, d_F, d_P, dt, true, many);
+        if (rc) return rc;
+      }
+      *defer_max = many;
+    }
     DMK_CUDA_CHECK(cudaGetLastError());
     return DMK_OK;
   }

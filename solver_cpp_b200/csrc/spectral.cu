@@ -81,6 +81,7 @@ int dmk_spectral_setup(dmk_ctx* c) {
   DMK_CUDA_CHECK(cudaMalloc((void**)&c->d_Cref, (81 + 54) * sizeof(double)));   // C_ref | symmetrised pairs (gamma_point.cuh)
   DMK_CUDA_CHECK(cudaMalloc((void**)&c->d_dc, 9 * sizeof(double)));
   DMK_CUDA_CHECK(cudaMalloc((void**)&c->d_div, sizeof(double)));
+  DMK_CUDA_CHECK(cudaMalloc((void**)&c->d_div_partial, std::max<size_t>(1024, (size_t)c->nxr * c->ny_loc) * sizeof(double)));
   DMK_CUDA_CHECK(cudaMalloc((void**)&c->d_scratch, DMK_SCRATCH_DOUBLES * sizeof(double)));
   DMK_CUDA_CHECK(cudaMallocHost((void**)&c->h_pinned, DMK_SCRATCH_DOUBLES * sizeof(double)));
   // tile widths: keep a tile near 36 KB so several CTAs share an SM and loads overlap butterflies
@@ -96,7 +97,7 @@ void dmk_spectral_teardown(dmk_ctx* c) {
   for (int a = 0; a < 3; a++) { cudaFree(c->xi_own[a]); cudaFree(c->xi_oth[a]); cudaFree(c->nyq[a]); }
   cudaFree(c->bufA); if (c->bufB) cudaFree(c->bufB);
   if (c->p2p) for (int p = 0; p < c->P; p++) if (p != c->rank) { cudaIpcCloseMemHandle(c->peerA[p]); cudaIpcCloseMemHandle(c->peerB[p]); }
-  cudaFree(c->d_Cref); cudaFree(c->d_dc); cudaFree(c->d_div); cudaFree(c->d_scratch);
+  cudaFree(c->d_Cref); cudaFree(c->d_dc); cudaFree(c->d_div); cudaFree(c->d_div_partial); cudaFree(c->d_scratch);
   if (c->h_pinned) cudaFreeHost(c->h_pinned);
 }
 
@@ -273,7 +274,7 @@ static void fill_gamma_params(dmk_ctx* c, DmkGammaParams* gp) {
   gp->xo_x = c->xi_oth[0]; gp->xo_y = c->xi_oth[1]; gp->xo_z = c->xi_oth[2];
   gp->nyq_x = c->nyq[0]; gp->nyq_y = c->nyq[1]; gp->nyq_z = c->nyq[2];
   for (int j = 0; j < 3; j++) gp->rescale[j] = c->rescale[j];
-  gp->nx = c->nx; gp->ky_offset = c->y_off; gp->dc_value = c->d_dc; gp->div_accum = c->d_div;
+  gp->nx = c->nx; gp->ky_offset = c->y_off; gp->dc_value = c->d_dc; gp->div_accum = c->d_div; gp->div_partial = c->d_div_partial;
 }
 
 int dmk_gamma_internal(dmk_ctx* c) {
@@ -281,7 +282,7 @@ int dmk_gamma_internal(dmk_ctx* c) {
   DmkGammaParams gp; fill_gamma_params(c, &gp);
   DmkPeerStore ps; if (c->p2p) ps = peers_inverse(c);
   int rc = dmk_launch_gamma_zpass(zbuf(c), c->plz, map_z(c), c->nxr, c->ny_loc, c->kt_z, gp, c->stream, c->xi_imag, c->p2p ? &ps : nullptr);
-  if (!rc) c->launches++;
+  if (!rc) c->launches += 2;                             // the pass + the fixed-order sum of its per-CTA divergence sums
   return rc;
 }
 

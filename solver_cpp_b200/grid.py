@@ -173,6 +173,14 @@ class GridContext:
         out = (fortran_to_c3333(Cv), fortran_to_c3333(Cm), (cells[0], cells[1]))
         return out + (d,) if materialise else out
 
+    def homogenise(self, P, dPdF):
+        """P_av, C_volAvg, C_minMaxAvg and the two selected cells from GIVEN device fields (Spectral::constitutive_response,
+        spectral.cpp:160-218): P records (nz_local, ny, nx, 9), dPdF (n_local, 81) in the reference's Fortran order"""
+        Pav, Cv, Cm = np.zeros(9), np.zeros(81), np.zeros(81)
+        cells = (C.c_longlong * 2)()
+        L.check(self.lib.dmk_homogenise(self.ctx, _p(P), _p(dPdF), C.c_longlong(self.n_local), _hp(Pav), _hp(Cv), _hp(Cm), cells))
+        return Pav.reshape(3, 3).T, fortran_to_c3333(Cv), fortran_to_c3333(Cm), (cells[0], cells[1])
+
     def materialpoint_forward(self):
         L.check(self.lib.dmk_materialpoint_forward(self.ctx))
 

@@ -156,6 +156,15 @@ class MechSolverBasic:
             L.check(self.lib.dmk_mech_eval_log(self.ctx, _hp(out), C.c_size_t(n.value), C.byref(n)))
         return out
 
+    def eval_stats(self):
+        """per residual evaluation: cells of this slab whose full first sub-step failed (the reference cuts those back)"""
+        n = C.c_size_t()
+        L.check(self.lib.dmk_mech_eval_stats(self.ctx, None, C.c_size_t(0), C.byref(n)))
+        out = np.zeros((n.value, 2))
+        if n.value:
+            L.check(self.lib.dmk_mech_eval_stats(self.ctx, _hp(out), C.c_size_t(n.value), C.byref(n)))
+        return out
+
     def capture(self, enable=True):
         L.check(self.lib.dmk_mech_capture(self.ctx, C.c_int(int(enable))))
 

@@ -234,9 +234,42 @@ def test_tangent_and_homogenisation_match_oracle(phase, rate, noise):
         assert cellsel == sel_o and _rel(Cv, C_vol_o) < 1e-9
 
 
-def test_homogenisation_known_answer_two_cells():
-    """test_spectral.cpp:58-216 of the reference pins P_av = wgt * sum(P) on literal data; here: the device reduction
-    of a random stress field against numpy."""
+def test_g3_homogenisation_literal_through_the_device_reductions(golden_dir):
+    """the literal two-cell P / dPdF fields and expected P_av, C_volAvg, C_minMaxAvg of the reference's own unit test
+    (test_spectral.cpp:58-216, golden set G3) through the DEVICE reductions (dmk_homogenise: record sum, dPdF sum, norm,
+    arg-max / arg-min selection with the tie rule)"""
+    import os
+    g3 = np.load(os.path.join(golden_dir, 'g3_unit_test_literals.npz'))
+    g = _ctx((2, 1, 1), (2e-5, 1e-5, 1e-5))
+    P = g.to_device(np.transpose(g3['hom_P'], (2, 0, 1)).reshape(1, 1, 2, 3, 3))
+    # (i, j, k, l, cell) -> [cell][81] with the first index fastest
+    d = np.ascontiguousarray(np.transpose(g3['hom_dPdF'], (4, 3, 2, 1, 0))).reshape(2, 81)
+    P_av, C_vol, C_mm, sel = g.homogenise(P, torch.from_numpy(d).cuda())
+    for got, key in ((P_av, 'hom_P_av'), (C_vol, 'hom_C_vol_avg'), (C_mm, 'hom_C_minmax_avg')):
+        assert np.abs(got - g3[key]).max() <= 1e-12 * np.abs(g3[key]).max(), key
+    assert sorted(sel) == [0, 1]
+
+
+def test_homogenise_fields_matches_numpy():
+    """dmk_homogenise on a random field against the oracle's numpy reduction (ties: a constant-norm block)"""
+    cells = (6, 7, 8)
+    n = int(np.prod(cells))
+    g = _ctx(cells, (6e-5, 7e-5, 8e-5))
+    rng = np.random.default_rng(2)
+    P = rng.standard_normal((n, 3, 3)) * 1e8
+    dP = rng.standard_normal((n, 3, 3, 3, 3)) * 1e9 + 1e11
+    dP[40:50] = dP[40]                                                        # ties at neither extreme
+    big = np.argmax((dP.reshape(n, -1) ** 2).sum(1))
+    dP[300] = dP[big]                                                         # a tie at the maximum: the lower index wins
+    d = np.ascontiguousarray(np.transpose(dP, (0, 4, 3, 2, 1))).reshape(n, 81)
+    P_av, C_vol, C_mm, sel = g.homogenise(g.to_device(P.reshape(8, 7, 6, 3, 3)), torch.from_numpy(d).cuda())
+    P_av_o, C_vol_o, C_mm_o, sel_o = osp.homogenise(P, dP, osp.Grid(cells, g.size))
+    assert sel == tuple(sel_o) and sel[0] == min(big, 300)
+    assert _rel(P_av, P_av_o) < 1e-13 and _rel(C_vol, C_vol_o) < 1e-13 and _rel(C_mm, C_mm_o) < 1e-15
+
+
+def test_forward_field_removes_the_mean():
+    """MechBase::forward_field with dt = 0 and a zero aim: the field minus its mean (device record sum against numpy)"""
     cells = (6, 7, 8)
     g = _ctx(cells, (6e-5, 7e-5, 8e-5))
     rng = np.random.default_rng(9)

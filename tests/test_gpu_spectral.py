@@ -13,6 +13,11 @@ GRIDS = [((3, 3, 3), (1e-5, 1e-5, 1e-5)), ((6, 7, 8), (6e-5, 7e-5, 8e-5)), ((16,
          ((64, 64, 64), (1e-5,) * 3), ((32, 16, 48), (2e-5, 1e-5, 3e-5))]
 
 
+# thin grids that put every long-line plan of the register-resident passes (128: <16,8,1>, 256: <16,16,1> and the x c2r
+# <8,8,4>, 512: <8,8,8> -- the plan of every 8-GPU number) on each axis in turn, small enough for the oracle
+THIN = [(c, tuple(1e-5 * v / 16 for v in c)) for n in (128, 256, 512) for c in ((n, 16, 16), (16, n, 16), (16, 16, n))]
+
+
 def _ctx(cells, size, **kw):
     from solver_cpp_b200.grid import GridContext
     return GridContext(cells, size, **kw)
@@ -29,7 +34,7 @@ def _stiffness(rng):
     return C + 1e8 * rng.standard_normal((3, 3, 3, 3))
 
 
-@pytest.mark.parametrize('cells,size', GRIDS)
+@pytest.mark.parametrize('cells,size', GRIDS + THIN)
 def test_fft_forward_matches_rfftn(cells, size):
     rng = np.random.default_rng(1)
     nx, ny, nz = cells
@@ -42,7 +47,7 @@ def test_fft_forward_matches_rfftn(cells, size):
     assert np.abs(hat - ref).max() <= 1e-12 * np.abs(ref).max()
 
 
-@pytest.mark.parametrize('cells,size', GRIDS)
+@pytest.mark.parametrize('cells,size', GRIDS + THIN)
 def test_fft_roundtrip_unnormalised(cells, size):
     """test_fft.cpp:11-58 of the reference: forward then backward with wgt = 1/N is the identity."""
     rng = np.random.default_rng(2)
@@ -55,7 +60,7 @@ def test_fft_roundtrip_unnormalised(cells, size):
 
 
 @pytest.mark.parametrize('derivative', [0, 1, 2])
-@pytest.mark.parametrize('cells,size', GRIDS)
+@pytest.mark.parametrize('cells,size', GRIDS + THIN)
 def test_divergence_and_gamma_match_oracle(cells, size, derivative):
     rng = np.random.default_rng(3)
     nx, ny, nz = cells
@@ -74,6 +79,20 @@ def test_divergence_and_gamma_match_oracle(cells, size, derivative):
     out = g.to_natural(d)
     assert abs(rms - rms_ref) <= 1e-12 * max(rms_ref, 1e-300)
     assert np.abs(out - ref).max() <= 1e-11 * max(np.abs(ref).max(), 1e-300)
+
+
+def test_divergence_sum_is_reproducible():
+    """the divergence sum decides `err_div / divTol < 1`, i.e. the iteration count: it must not depend on the order in which
+    the CTAs of the fused pass finish (two-stage reduction in a fixed order, no floating-point atomics)"""
+    cells, size = (64, 64, 64), (1e-5,) * 3
+    rng = np.random.default_rng(11)
+    P = 1e8 * rng.standard_normal((64, 64, 64, 3, 3))
+    g = _ctx(cells, size)
+    g.update_gamma(_stiffness(rng))
+    vals = set()
+    for _ in range(6):
+        vals.add(g.divergence_and_gamma(g.to_device(P), np.zeros((3, 3))))
+    assert len(vals) == 1, vals
 
 
 def test_gamma_dc_only_broadcasts_aim():

@@ -86,7 +86,7 @@ int main(int argc, char** argv) {
   cudaMalloc(&dC, 135 * 8); cudaMemcpy(dC, C.data(), 135 * 8, cudaMemcpyHostToDevice);
   cudaMalloc(&ddc, 9 * 8); cudaMemset(ddc, 0, 72); cudaMalloc(&ddiv, 8); cudaMemset(ddiv, 0, 8);
   gp.C_ref = dC; gp.xi_x = gp.xi_y = gp.xi_z = dxi; gp.xo_x = gp.xo_y = gp.xo_z = done_; gp.nyq_x = gp.nyq_y = gp.nyq_z = dnyq;
-  gp.rescale[0] = gp.rescale[1] = gp.rescale[2] = 1.0; gp.nx = n; gp.ky_offset = 0; gp.dc_value = ddc; gp.div_accum = ddiv;
+  gp.rescale[0] = gp.rescale[1] = gp.rescale[2] = 1.0; gp.nx = n; gp.ky_offset = 0; gp.dc_value = ddc; gp.div_accum = ddiv; { double* dpart; cudaMalloc(&dpart, (size_t)n * n * sizeof(double)); gp.div_partial = dpart; }
 
   if (n == 256) {
     typedef DmkFastPlan<16, 16, 1> A; typedef DmkFastPlan<8, 8, 4> Bp; typedef DmkFastPlan<4, 8, 8> Dp;
