@@ -113,6 +113,8 @@ int dmk_local_cells(const dmk_ctx* ctx, int* nz_local, int* z_offset, int* ny_lo
 int dmk_kernel_launches(const dmk_ctx* ctx, long long* n);        /* kernels launched so far by this context */
 /* CUDA-event section timing of residual evaluations: out[0..4] = accumulated ms of {constitutive kernel, P sum + aim,
  * forward FFT x+y, fused z / Gamma / divergence pass, inverse FFT y+x}, out[5] = evaluations accumulated */
+/* run-time switches for comparison runs and tests: "pheno_mass_deferral" = 0 nested | 1 machine | 2 lanes | -1 default */
+int dmk_set_option(dmk_ctx* ctx, const char* name, int value);
 int dmk_set_profiling(dmk_ctx* ctx, int enable);
 int dmk_get_profile(dmk_ctx* ctx, double out[6], int reset);
 /* measured FP64 FMA throughput of the device (register-resident DFMA chains), TFLOP/s: the constitutive roofline */

@@ -285,14 +285,17 @@ static int persistent_grid(K kernel, long long n) {
 const unsigned* dmk_points_given_up_counter(dmk_ctx* c) { return c->pts->d_defer_count; }
 
 // DMK_PHENO_MASS: which kernel takes the deferred list when it is long (see cutback_setting() in pheno_fast.cu):
-//   machine (default)  the reference-order arithmetic (9x9 LU, the oracle's operation order) on the lane-persistent state
-//                      machine (machine_dev.cuh): bit-identical to the nested kernel, so parity on cut-back cells is unchanged
-//   lanes              the register-resident 6x6 formulation with in-lane cut-backs: fastest, follows the oracle on fewer of
-//                      the rounding-chaotic cut-back cells
-//   nested             no special treatment: the one-thread-per-point kernel whatever the length of the list
-int dmk_mass_deferral_setting() {
-  static const int v = [] { const char* e = getenv("DMK_PHENO_MASS"); return !e ? 1 : std::string(e) == "lanes" ? 2 : std::string(e) == "nested" ? 0 : 1; }();
-  return v;
+//   lanes (default)    the register-resident 6x6 formulation with in-lane cut-backs (pheno_lanes_dev.cuh, CUTBACK = true)
+//   nested             no special treatment: the one-thread-per-point reference-order kernel whatever the length of the list
+//   machine            the reference-order arithmetic on the lane-persistent state machine (machine_dev.cuh)
+// Measured on a virgin-state evaluation of the 128^3 Cu polycrystal, where every cell cuts back (profiles/r02_summary.md):
+// lanes 227 ms, nested 1138 ms, machine 5173 ms (the state machine's per-thread arrays live in local memory).  Such evaluations
+// are rounding-chaotic for ANY build of the reference algorithm -- the homogenised stress of that one evaluation differs by
+// ~1e-3 between any two of the three kernels, and between the oracle and its own FMA build (tests/test_oracle_golden.py) --
+// so the choice is made on speed; dmk_set_option("pheno_mass_deferral") / DMK_PHENO_MASS select the others.
+int dmk_mass_deferral_setting(const dmk_ctx* c) {
+  static const int env = [] { const char* e = getenv("DMK_PHENO_MASS"); return !e ? 2 : std::string(e) == "machine" ? 1 : std::string(e) == "nested" ? 0 : 2; }();
+  return (c && c->opt_mass >= 0) ? c->opt_mass : env;
 }
 
 int dmk_wait_staged_input(dmk_ctx* c, const double* d_F) {
@@ -316,7 +319,7 @@ int dmk_points_constitutive(dmk_ctx* c, const double* d_F, double* d_P, double d
     if (handled) {
       c->launches++;
       if (deferred) {          // second pass over the deferred cells only (count read on the device: no host round trip)
-        if (defer_max != 0xffffffffu && dmk_mass_deferral_setting() == 1 && nd.integrator == DMK_INTEG_FPI) {
+        if (defer_max != 0xffffffffu && dmk_mass_deferral_setting(c) == 1 && nd.integrator == DMK_INTEG_FPI) {
           // mass deferral (more than defer_max cells): the reference-order arithmetic on the lane-persistent state machine
           DMK_LAUNCH_PERSISTENT(dmk_constitutive_kernel, law, nst, pa.n, c->stream, (pa, ph, nd, d_F, d_P, dt, pa.defer_list, pa.d_defer_count, defer_max));
           c->launches++;
@@ -393,7 +396,7 @@ void dmk_points_teardown(dmk_ctx* c) {
   cudaFree(pa->phase); cudaFree(pa->F0); cudaFree(pa->F); cudaFree(pa->Fp0); cudaFree(pa->Fp); cudaFree(pa->Fe);
   cudaFree(pa->Lp0); cudaFree(pa->Lp); cudaFree(pa->S0); cudaFree(pa->S); cudaFree(pa->state0); cudaFree(pa->state);
   if (pa->dep) cudaFree(pa->dep);
-  cudaFree(pa->nrm); cudaFree(pa->cutbacks); cudaFree(pa->lp_iter); cudaFree(pa->defer_list); cudaFree(pa->d_defer_count); cudaFree(pa->d_work); cudaFree(pa->d_phases); cudaFree(pa->d_counters); cudaFree(pa->d_ill);
+  cudaFree(pa->nrm); cudaFree(pa->cutbacks); cudaFree(pa->lp_iter); cudaFree(pa->defer_list); cudaFree(pa->d_defer_count); cudaFree(pa->d_work); if (pa->d_cold) cudaFree(pa->d_cold); cudaFree(pa->d_phases); cudaFree(pa->d_counters); cudaFree(pa->d_ill);
   delete[] pa->h_phases;
   delete[] pa->h_dev_phases;
   delete pa;

@@ -49,6 +49,7 @@ struct dmk_ctx {
   cudaStream_t copy_stream; cudaEvent_t stage_ev[8]; cudaEvent_t stage_begin; int stage_chunks; bool stage_ready;
   const double* stage_dst;        // device field the staged copy fills (the chunked launches apply to this input only)
   dmk_numerics num;
+  int opt_mass;                   // who takes a long list of given-up points: -1 = DMK_PHENO_MASS / default; 0 nested, 1 machine, 2 lanes
   // ---- mechanical solver
   DmkMech* mech;
   // ---- Fortran-named drop-in mirrors (pinned host)

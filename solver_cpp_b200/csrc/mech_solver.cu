@@ -468,6 +468,9 @@ extern "C" int dmk_update_gamma(dmk_ctx* c, const double* C);
 
 extern "C" int dmk_mech_init(dmk_ctx* c, const long long* gamma_pair_cells) {
   if (!c || !c->pts) { dmk_set_error("material not initialised (dmk_material_init)"); return DMK_ERR_STATE; }
+  if (c->P > 1 && (!c->has_comm || !c->comm.allreduce_sum || !c->comm.allreduce_max || !c->comm.alltoall)) {
+    dmk_set_error("%d ranks but no collective callbacks: call dmk_set_comm before dmk_mech_init", c->P); return DMK_ERR_STATE;
+  }
   dmk_mech_teardown(c);
   DmkMech* m = new DmkMech();
   c->mech = m;

@@ -22,7 +22,7 @@ __global__ void __launch_bounds__(DMK_PF_THREADS, DMK_PF_MINBLOCKS)
 dmk_pheno_fast_kernel(const __grid_constant__ DmkPhenoK<NSL> K, DmkPointArrays pa, int phase, DmkNumDev num, int defer_nLp,
                       const double* __restrict__ Fin, double* __restrict__ Pout, double Dt) {
   extern __shared__ double pf_sm[];
-  const DmkScr scr = {pf_sm + threadIdx.x, DMK_PF_THREADS};
+  const DmkScr scr = {pf_sm + threadIdx.x, DMK_PF_THREADS, pf_sm + PfOff<NSL>::TOTAL * DMK_PF_THREADS + threadIdx.x, DMK_PF_THREADS};   // all of it in shared memory
   DmkCnt cnt = {0, 0, 0, 0, 0, 0};
   unsigned ill = 0, ndefer = 0;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < pa.n; i += (long long)gridDim.x * blockDim.x) {
@@ -63,7 +63,7 @@ static int launch_pheno_fast(dmk_ctx* c, DmkPointArrays& pa, int ph, const DmkDe
                              double* d_P, double dt) {
   DmkPhenoK<NSL> K;
   dmk_pheno_fast_tables<NSL>(d, K);
-  const size_t smem = (size_t)PfOff<NSL>::TOTAL * DMK_PF_THREADS * sizeof(double);
+  const size_t smem = (size_t)(PfOff<NSL>::TOTAL + PfOff<NSL>::COLD_TOTAL) * DMK_PF_THREADS * sizeof(double);
   static bool attr_set = false;
   if (!attr_set) {
     DMK_CUDA_CHECK(cudaFuncSetAttribute(dmk_pheno_fast_kernel<NSL, NEXP, UNR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -84,11 +84,11 @@ static int launch_pheno_fast(dmk_ctx* c, DmkPointArrays& pa, int ph, const DmkDe
 // on neighbouring cells (coalesced structure-of-arrays accesses) and no warp is left with a long tail.  No barrier anywhere.
 #define DMK_PL_THREADS 64
 #ifndef DMK_PL_MINBLOCKS
-#define DMK_PL_MINBLOCKS 4
+#define DMK_PL_MINBLOCKS 6
 #endif
 #define DMK_PL_CHUNK 256
-template <int NSL, int NEXP, int UNR, bool VOTE3, bool CUTBACK>
-__global__ void __launch_bounds__(DMK_PL_THREADS, DMK_PL_MINBLOCKS)
+template <int NSL, int NEXP, int UNR, bool VOTE3, bool CUTBACK, int MINB>
+__global__ void __launch_bounds__(DMK_PL_THREADS, MINB)
 dmk_pheno_lanes_kernel(const __grid_constant__ DmkPhenoK<NSL> K, DmkPointArrays pa, int phase, DmkNumDev num,
                        const double* __restrict__ Fin, double* __restrict__ Pout, double Dt, long long cell_begin,
                        long long cell_end, int3 vw, const int* __restrict__ list, const unsigned* __restrict__ list_n,
@@ -101,7 +101,8 @@ dmk_pheno_lanes_kernel(const __grid_constant__ DmkPhenoK<NSL> K, DmkPointArrays 
     if (cell_end <= (long long)list_min) return;
   }
   extern __shared__ double pf_sm[];
-  const DmkScr scr = {pf_sm + threadIdx.x, DMK_PL_THREADS};
+  const DmkScr scr = {pf_sm + threadIdx.x, DMK_PL_THREADS, pa.d_cold + (size_t)blockIdx.x * DMK_PL_THREADS + threadIdx.x,
+                      (long long)gridDim.x * DMK_PL_THREADS};
   const unsigned FULL = 0xffffffffu, lane = threadIdx.x & 31u, lt = (1u << lane) - 1u;
   PlLane<NSL> L;
   L.mode = PL_NEED;
@@ -244,7 +245,14 @@ static bool lanes_setting() {
   return v;
 }
 
-template <int NSL, int NEXP, int UNR, bool VOTE3, bool CUTBACK>
+// DMK_PL_OCC=<4|5|6>: CTAs per SM the lane-persistent kernel is compiled for (register budget 255 / 204 / 168); default
+// DMK_PL_MINBLOCKS = 6: 12 warps per SM (sweep in profiles/r02_summary.md)
+static int occ_setting() {
+  static const int v = [] { const char* e = getenv("DMK_PL_OCC"); const int o = e ? atoi(e) : DMK_PL_MINBLOCKS; return (o == 4 || o == 5) ? o : 6; }();
+  return v;
+}
+
+template <int NSL, int NEXP, int UNR, bool VOTE3, bool CUTBACK, int MINB = DMK_PL_MINBLOCKS>
 static int launch_pheno_lanes(dmk_ctx* c, DmkPointArrays& pa, int ph, const DmkDevPhase& d, const DmkNumDev& nd, const double* d_F,
                               double* d_P, double dt, bool from_list = false, unsigned list_min = 0) {
   DmkPhenoK<NSL> K;
@@ -252,16 +260,25 @@ static int launch_pheno_lanes(dmk_ctx* c, DmkPointArrays& pa, int ph, const DmkD
   const size_t smem = (size_t)PfOff<NSL>::TOTAL * DMK_PL_THREADS * sizeof(double);
   static int grid = 0;
   if (!grid) {
-    DMK_CUDA_CHECK(cudaFuncSetAttribute(dmk_pheno_lanes_kernel<NSL, NEXP, UNR, VOTE3, CUTBACK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    DMK_CUDA_CHECK(cudaFuncSetAttribute(dmk_pheno_lanes_kernel<NSL, NEXP, UNR, VOTE3, CUTBACK, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int dev = 0, sms = 148, occ = 1;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, dmk_pheno_lanes_kernel<NSL, NEXP, UNR, VOTE3, CUTBACK>, DMK_PL_THREADS, smem) != cudaSuccess || occ < 1) occ = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, dmk_pheno_lanes_kernel<NSL, NEXP, UNR, VOTE3, CUTBACK, MINB>, DMK_PL_THREADS, smem) != cudaSuccess || occ < 1) occ = 1;
     grid = sms * occ;                                  // one resident wave
+  }
+  {                                                    // cold part of the per-thread scratch: [k][resident thread], for the largest wave
+    const size_t need = (size_t)grid * DMK_PL_THREADS * PfOff<NSL>::COLD_TOTAL;
+    if (pa.cold_doubles < need) {
+      if (pa.d_cold) DMK_CUDA_CHECK(cudaFree(pa.d_cold));
+      pa.d_cold = nullptr; pa.cold_doubles = 0;
+      DMK_CUDA_CHECK(cudaMalloc((void**)&pa.d_cold, need * sizeof(double)));
+      pa.cold_doubles = need;
+    }
   }
   if (from_list) {                                     // the cells the launch before this one gave up (pa.defer_list), if they are many
     DMK_CUDA_CHECK(cudaMemsetAsync(pa.d_work, 0, sizeof(unsigned long long), c->stream));
-    dmk_pheno_lanes_kernel<NSL, NEXP, UNR, VOTE3, CUTBACK><<<grid, DMK_PL_THREADS, smem, c->stream>>>(K, pa, ph, nd, d_F, d_P, dt, 0, 0, vote_weights(), pa.defer_list, pa.d_defer_count, list_min);
+    dmk_pheno_lanes_kernel<NSL, NEXP, UNR, VOTE3, CUTBACK, MINB><<<grid, DMK_PL_THREADS, smem, c->stream>>>(K, pa, ph, nd, d_F, d_P, dt, 0, 0, vote_weights(), pa.defer_list, pa.d_defer_count, list_min);
     c->launches++;
     return DMK_OK;
   }
@@ -277,7 +294,7 @@ static int launch_pheno_lanes(dmk_ctx* c, DmkPointArrays& pa, int ph, const DmkD
     DMK_CUDA_CHECK(cudaMemsetAsync(pa.d_work, 0, sizeof(unsigned long long), c->stream));
     const long long warps_needed = (end - first + 31) / 32;
     const int g = (int)std::max(1LL, std::min((long long)grid, (warps_needed + 1) / 2));
-    dmk_pheno_lanes_kernel<NSL, NEXP, UNR, VOTE3, CUTBACK><<<g, DMK_PL_THREADS, smem, c->stream>>>(K, pa, ph, nd, d_F, d_P, dt, first, end, vote_weights(), nullptr, nullptr, 0u);
+    dmk_pheno_lanes_kernel<NSL, NEXP, UNR, VOTE3, CUTBACK, MINB><<<g, DMK_PL_THREADS, smem, c->stream>>>(K, pa, ph, nd, d_F, d_P, dt, first, end, vote_weights(), nullptr, nullptr, 0u);
     if (k > 0) c->launches++;
   }
   return DMK_OK;
@@ -298,20 +315,20 @@ int dmk_points_pheno_fast(dmk_ctx* c, int ph, const DmkNumDev& nd, const double*
   const bool adaptive = cutback_setting() == 0 && dmk_pheno_lanes_eligible(nd, true);
   if (lanes_setting() && dmk_pheno_lanes_eligible(nd, cb)) {
     *deferred = !cb;                                    // in-lane cut-backs: nothing is handed to the reference-order kernel
+    const int occ = occ_setting();
 #define DMK_PL_LAUNCH(NEXP_)                                                                                   \
-  (cb ? ((u == 2) ? launch_pheno_lanes<12, NEXP_, 2, true, true>(c, pa, ph, d, nd, d_F, d_P, dt)              \
-                  : launch_pheno_lanes<12, NEXP_, 1, true, true>(c, pa, ph, d, nd, d_F, d_P, dt))             \
+  (cb ? launch_pheno_lanes<12, NEXP_, 1, true, true>(c, pa, ph, d, nd, d_F, d_P, dt)                          \
       : !vote3_setting() ? launch_pheno_lanes<12, NEXP_, 1, false, false>(c, pa, ph, d, nd, d_F, d_P, dt)     \
       : (u == 2)  ? launch_pheno_lanes<12, NEXP_, 2, true, false>(c, pa, ph, d, nd, d_F, d_P, dt)             \
-      : (u == 4)  ? launch_pheno_lanes<12, NEXP_, 4, true, false>(c, pa, ph, d, nd, d_F, d_P, dt)             \
-      : (u == 12) ? launch_pheno_lanes<12, NEXP_, 12, true, false>(c, pa, ph, d, nd, d_F, d_P, dt)            \
-                  : launch_pheno_lanes<12, NEXP_, 1, true, false>(c, pa, ph, d, nd, d_F, d_P, dt))
+      : (occ == 4) ? launch_pheno_lanes<12, NEXP_, 1, true, false, 4>(c, pa, ph, d, nd, d_F, d_P, dt)         \
+      : (occ == 5) ? launch_pheno_lanes<12, NEXP_, 1, true, false, 5>(c, pa, ph, d, nd, d_F, d_P, dt)         \
+                   : launch_pheno_lanes<12, NEXP_, 1, true, false>(c, pa, ph, d, nd, d_F, d_P, dt))
     rc = (nexp == 20) ? (DMK_PL_LAUNCH(20)) : (DMK_PL_LAUNCH(0));
 #undef DMK_PL_LAUNCH
     if (rc) return rc;
-    if (!cb && adaptive && dmk_mass_deferral_setting() != 0) {       // mass deferral
+    if (!cb && adaptive && dmk_mass_deferral_setting(c) != 0) {       // mass deferral
       const unsigned many = (unsigned)std::min<long long>(pa.n / 32, 0x7fffffffLL);
-      if (dmk_mass_deferral_setting() == 2) {            // ... through the in-lane cut-back kernel (else: constitutive.cu)
+      if (dmk_mass_deferral_setting(c) == 2) {            // ... through the in-lane cut-back kernel (else: constitutive.cu)
         rc = (nexp == 20) ? launch_pheno_lanes<12, 20, 1, true, true>(c, pa, ph, d, nd, d_F, d_P, dt, true, many)
                           : launch_pheno_lanes<12, 0, 1, true, true>(c, pa, ph, d, nd, d_F, d_P, dt, true, many);
         if (rc) return rc;

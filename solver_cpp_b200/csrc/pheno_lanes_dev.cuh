@@ -249,12 +249,21 @@ DMK_HD __forceinline__ int pl_state_block(const DmkPhenoK<NSL>& K, const DmkNumD
   double zeta = 1.0;
   if (!init && !nan) {
     double d12 = 0.0, d22 = 0.0, d01 = 0.0;           // damper (:677-690); D = last(1) - last(2)
+    // L1 and D live in the cold (global, L2-resident) part of the scratch: loaded four entries at a time so that the
+    // loads of a batch are in flight together; the sums run in the order k = 0, 1, 2, ... as before
+    static_assert(NST % 4 == 0, "state count: batches of four");
 #pragma unroll 1
-    for (int k = 0; k < NST; k++) {
-      const double l1 = scr(O::L1 + k), dd = scr(O::D + k), dk = pf_dot<NSL>(scr, k);
-      d12 += (dk - l1) * dd;
-      d22 += dd * dd;
-      d01 += dk * l1;
+    for (int k0 = 0; k0 < NST; k0 += 4) {
+      double l1[4], dd[4];
+#pragma unroll
+      for (int j = 0; j < 4; j++) { l1[j] = scr.cold(O::L1 + k0 + j); dd[j] = scr.cold(O::D + k0 + j); }
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        const double dk = pf_dot<NSL>(scr, k0 + j);
+        d12 += (dk - l1[j]) * dd[j];
+        d22 += dd[j] * dd[j];
+        d01 += dk * l1[j];
+      }
     }
     if (fmin(d01, d12) < 0.0 && d22 > 0.0) zeta = 0.75 + 0.25 * tanh(2.0 + 4.0 * d12 / d22);
   }
@@ -263,16 +272,22 @@ DMK_HD __forceinline__ int pl_state_block(const DmkPhenoK<NSL>& K, const DmkNumD
     bool conv = true;
     const double* __restrict__ st0s = (sub ? pa.state : pa.state0) + i;
 #pragma unroll 1
-    for (int k = 0; k < NST; k++) {
-      const double l1 = init ? 0.0 : scr(O::L1 + k);
-      const double d = pf_dot<NSL>(scr, k) * zeta + l1 * (1.0 - zeta);
-      scr(O::D + k) = d - l1;
-      scr(O::L1 + k) = d;
-      double s = scr(O::ST + k);
-      const double r = s - st0s[k * n] - d * dt;      // predictor: s == state0, r = -d dt
-      s -= r;
-      scr(O::ST + k) = s;
-      if (!(fabs(r) <= fmax(K.atol[k], num.eps_rel_state * fabs(s)))) conv = false;
+    for (int k0 = 0; k0 < NST; k0 += 4) {
+      double l1[4], s0[4];
+#pragma unroll
+      for (int j = 0; j < 4; j++) { l1[j] = init ? 0.0 : scr.cold(O::L1 + k0 + j); s0[j] = st0s[(k0 + j) * n]; }
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        const int k = k0 + j;
+        const double d = pf_dot<NSL>(scr, k) * zeta + l1[j] * (1.0 - zeta);
+        scr.cold(O::D + k) = d - l1[j];
+        scr.cold(O::L1 + k) = d;
+        double s = scr(O::ST + k);
+        const double r = s - s0[j] - d * dt;          // predictor: s == state0, r = -d dt
+        s -= r;
+        scr(O::ST + k) = s;
+        if (!(fabs(r) <= fmax(K.atol[k], num.eps_rel_state * fabs(s)))) conv = false;
+      }
     }
     finished = !init && (conv || L.it >= num.N_iter_state_max);   // a loop that runs out leaves broken = .false. (reference)
   }

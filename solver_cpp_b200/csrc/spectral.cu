@@ -92,11 +92,12 @@ int dmk_spectral_setup(dmk_ctx* c) {
   return DMK_OK;
 }
 
+extern "C" int dmk_p2p_disable(dmk_ctx* c);
 void dmk_spectral_teardown(dmk_ctx* c) {
   dmk_fft_plan_destroy(&c->plx); dmk_fft_plan_destroy(&c->ply); dmk_fft_plan_destroy(&c->plz);
   for (int a = 0; a < 3; a++) { cudaFree(c->xi_own[a]); cudaFree(c->xi_oth[a]); cudaFree(c->nyq[a]); }
   cudaFree(c->bufA); if (c->bufB) cudaFree(c->bufB);
-  if (c->p2p) for (int p = 0; p < c->P; p++) if (p != c->rank) { cudaIpcCloseMemHandle(c->peerA[p]); cudaIpcCloseMemHandle(c->peerB[p]); }
+  if (c->p2p) dmk_p2p_disable(c);
   cudaFree(c->d_Cref); cudaFree(c->d_dc); cudaFree(c->d_div); cudaFree(c->d_div_partial); cudaFree(c->d_scratch);
   if (c->h_pinned) cudaFreeHost(c->h_pinned);
 }
@@ -110,6 +111,7 @@ extern "C" int dmk_create(dmk_ctx** out, const dmk_grid_desc* g) {
   dmk_ctx* c = new dmk_ctx();
   memset(c, 0, sizeof(dmk_ctx));
   c->g = *g;
+  c->opt_mass = -1;
   c->nx = g->cells[0]; c->ny = g->cells[1]; c->nz = g->cells[2]; c->nxr = c->nx / 2 + 1;
   c->P = g->world_size < 1 ? 1 : g->world_size; c->rank = g->rank;
   if (c->nx < 1 || c->ny < 1 || c->nz < 1 || c->rank < 0 || c->rank >= c->P) { dmk_set_error("bad grid descriptor"); delete c; return DMK_ERR_ARG; }
@@ -125,7 +127,7 @@ extern "C" int dmk_create(dmk_ctx** out, const dmk_grid_desc* g) {
   if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { dmk_set_error("stream creation failed"); delete c; return DMK_ERR_CUDA; }
   c->own_stream = true;
   int rc = dmk_spectral_setup(c);
-  if (rc) { delete c; return rc; }
+  if (rc) { dmk_spectral_teardown(c); cudaStreamDestroy(c->stream); delete c; return rc; }
   *out = c;
   return DMK_OK;
 }
@@ -164,6 +166,18 @@ extern "C" int dmk_local_cells(const dmk_ctx* c, int* nz_local, int* z_offset, i
 extern "C" int dmk_kernel_launches(const dmk_ctx* c, long long* n) { *n = c->launches; return DMK_OK; }
 // section timing of residual evaluations: out[0..4] = accumulated ms of {constitutive, P sum + aim, forward FFT x+y,
 // fused z/Gamma/div pass, inverse FFT y+x}, out[5] = evaluations accumulated; reset != 0 clears the accumulators
+// run-time switches for comparison runs and tests (the environment variables of DESIGN.md section 9 give the defaults):
+//   "pheno_mass_deferral"  0 nested | 1 machine | 2 lanes | -1 default   (pheno_fast.cu: cutback_setting)
+extern "C" int dmk_set_option(dmk_ctx* c, const char* name, int value) {
+  if (!c || !name) { dmk_set_error("null argument"); return DMK_ERR_ARG; }
+  if (!strcmp(name, "pheno_mass_deferral")) {
+    if (value < -1 || value > 2) { dmk_set_error("pheno_mass_deferral: -1..2"); return DMK_ERR_ARG; }
+    c->opt_mass = value; return DMK_OK;
+  }
+  dmk_set_error("dmk_set_option: unknown option '%s'", name);
+  return DMK_ERR_ARG;
+}
+
 extern "C" int dmk_set_profiling(dmk_ctx* c, int enable) {
   if (enable && !c->ev[0]) { for (int i = 0; i < 8; i++) DMK_CUDA_CHECK(cudaEventCreate(&c->ev[i])); }
   c->profiling = enable != 0;
@@ -572,14 +586,27 @@ extern "C" int dmk_p2p_import(dmk_ctx* c, const unsigned char* all_handles, int*
   if (enabled) *enabled = 0;
   if (c->P < 2 || c->P > DMK_MAX_PEERS || !c->has_comm) { dmk_set_error("fused exchange: needs 2..%d ranks and the collective callbacks", DMK_MAX_PEERS); return DMK_ERR_STATE; }
   if (!fast_len(c->ny) || !fast_len(c->nz) || dmk_fast_disabled()) return DMK_OK;
+  if (c->p2p) dmk_p2p_disable(c);
+  for (int p = 0; p < c->P; p++) c->peerA[p] = c->peerB[p] = nullptr;
+  c->p2p = true;                                       // from here on dmk_p2p_disable closes whatever has been opened
   for (int p = 0; p < c->P; p++) {
     if (p == c->rank) { c->peerA[p] = c->bufA; c->peerB[p] = c->bufB; continue; }
     cudaIpcMemHandle_t h;
     void* ptr = nullptr;
     memcpy(&h, all_handles + (size_t)p * 128, 64);
-    DMK_CUDA_CHECK(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess)); c->peerA[p] = (double2*)ptr;
-    memcpy(&h, all_handles + (size_t)p * 128 + 64, 64);
-    DMK_CUDA_CHECK(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess)); c->peerB[p] = (double2*)ptr;
+    cudaError_t e = cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e == cudaSuccess) {
+      c->peerA[p] = (double2*)ptr;
+      memcpy(&h, all_handles + (size_t)p * 128 + 64, 64);
+      e = cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess);
+      if (e == cudaSuccess) c->peerB[p] = (double2*)ptr;
+    }
+    if (e != cudaSuccess) {                            // handles opened so far are closed again
+      dmk_set_error("fused exchange: cudaIpcOpenMemHandle for rank %d failed: %s", p, cudaGetErrorString(e));
+      cudaGetLastError();
+      dmk_p2p_disable(c);
+      return DMK_ERR_CUDA;
+    }
   }
   // every opened pointer must show its owner's signature (written by dmk_p2p_export before the all-gather)
   bool good = true;
@@ -589,7 +616,6 @@ extern "C" int dmk_p2p_import(dmk_ctx* c, const unsigned char* all_handles, int*
     DMK_CUDA_CHECK(cudaMemcpy(&b, c->peerB[p], sizeof(double), cudaMemcpyDeviceToHost));
     good = (a == p2p_signature(p, 0)) && (b == p2p_signature(p, 1));
   }
-  c->p2p = true;                                       // (so that dmk_p2p_disable closes the handles)
   if (!good) return dmk_p2p_disable(c);
   if (enabled) *enabled = 1;
   return DMK_OK;
@@ -598,7 +624,11 @@ extern "C" int dmk_p2p_import(dmk_ctx* c, const unsigned char* all_handles, int*
 // back to the all-to-all path (the host side calls this on every rank if any rank could not open its peers' buffers)
 extern "C" int dmk_p2p_disable(dmk_ctx* c) {
   if (!c) { dmk_set_error("null argument"); return DMK_ERR_ARG; }
-  if (c->p2p) for (int p = 0; p < c->P; p++) if (p != c->rank) { cudaIpcCloseMemHandle(c->peerA[p]); cudaIpcCloseMemHandle(c->peerB[p]); }
+  if (c->p2p) for (int p = 0; p < c->P; p++) if (p != c->rank) {
+    if (c->peerA[p]) cudaIpcCloseMemHandle(c->peerA[p]);
+    if (c->peerB[p]) cudaIpcCloseMemHandle(c->peerB[p]);
+    c->peerA[p] = c->peerB[p] = nullptr;
+  }
   c->p2p = false;
   return DMK_OK;
 }

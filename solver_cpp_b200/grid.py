@@ -226,6 +226,9 @@ class GridContext:
         for k in d.files:
             self.set_state(k, d[k])
 
+    def set_option(self, name, value):
+        L.check(self.lib.dmk_set_option(self.ctx, name.encode(), C.c_int(int(value))))
+
     # ---- measurement aids
     def set_profiling(self, enable=True):
         L.check(self.lib.dmk_set_profiling(self.ctx, C.c_int(int(enable))))

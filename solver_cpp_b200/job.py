@@ -13,27 +13,34 @@ _DIVCORR = {'none': 0, 'size': 1, 'size+grid': 2, 'grid+size': 2}
 
 
 def read_numerics(path=None):
-    """numerics.yaml -> (lib.Numerics, derivative id, divergence-correction id); defaults: config.h:50-78 of the reference"""
+    """numerics.yaml -> (lib.Numerics, derivative id, divergence-correction id, N_cutback_max); keys and defaults:
+    Config::parse_numerics, config.cpp:360-463 and config.h:50-78 of the reference"""
     d = yaml.safe_load(open(path)) if path else {}
     d = d or {}
     grid = ((d.get('solver') or {}).get('grid') or {})
     fft = grid.get('FFT') or {}
     num = M.make_numerics(((d.get('phase') or {}).get('mechanical')), grid.get('mechanical'))
-    return num, _DERIVATIVE[fft.get('derivative', 'continuous')], _DIVCORR[str(fft.get('divergence_correction', 'size+grid'))]
+    for key, table in (('derivative', _DERIVATIVE), ('divergence_correction', _DIVCORR)):
+        if key in fft and str(fft[key]) not in table:
+            raise ValueError('numerics: FFT.%s must be one of %s' % (key, ', '.join(table)))
+    return (num, _DERIVATIVE[fft.get('derivative', 'continuous')], _DIVCORR[str(fft.get('divergence_correction', 'size+grid'))],
+            int(grid.get('N_cutback_max', 3)))
 
 
 def load_job(geometry, material, load, numerics=None, world_size=1, rank=0, comm=None):
-    """-> (MechSolverBasic on this rank's z-slab, parsed load steps).  `material` / `load` may be paths or parsed dicts."""
+    """-> (MechSolverBasic on this rank's z-slab, parsed load steps).  `material` / `load` may be paths or parsed dicts.
+    The solver carries `max_cut_back` (numerics: solver/grid/N_cutback_max) for loop_over_loadcase."""
     geo = read_vti(geometry)
     mat = yaml.safe_load(open(material)) if isinstance(material, str) else material
     ld = yaml.safe_load(open(load)) if isinstance(load, str) else load
-    num, derivative, divcorr = read_numerics(numerics)
+    num, derivative, divcorr, max_cut_back = read_numerics(numerics)
     cells = tuple(int(c) for c in geo['cells'])
     if int(geo['material'].max()) >= len(mat['material']) or int(geo['material'].min()) < 0:
         raise ValueError('geometry refers to material %d, material.yaml has %d entries' % (int(geo['material'].max()), len(mat['material'])))
     z0, z1 = parallel.slab_range(cells[2], world_size, rank)
     solver = mech.make_solver(cells, tuple(float(s) for s in geo['size']), mat, np.ascontiguousarray(geo['material'][z0:z1]), numerics=num,
                               derivative=derivative, divergence_correction=divcorr, world_size=world_size, rank=rank, comm=comm)
+    solver.max_cut_back = max_cut_back
     return solver, mech.parse_load(ld)
 
 
@@ -59,7 +66,11 @@ def run_job(geometry, material, load, numerics=None, result=None, **kw):
         def callback(rec, s):
             if rec['inc_in_step'] % max(1, rec['f_out']) == 0:
                 writer.record(rec, s, getattr(kw.get('comm'), 'group', None))
-    records = mech.loop_over_loadcase(solver, steps, callback=callback)
-    if writer is not None and kw.get('rank', 0) == 0:
-        writer.save()
+    # the reference finishes its result file after every increment, so what was written before a failure (no solution after
+    # the last cut-back, a CUDA error) stays readable: the file's metadata and superblock are written in any case
+    try:
+        records = mech.loop_over_loadcase(solver, steps, max_cut_back=getattr(solver, 'max_cut_back', 3), callback=callback)
+    finally:
+        if writer is not None and kw.get('rank', 0) == 0:
+            writer.save()
     return records

@@ -309,22 +309,36 @@ def make_numerics(phase_mech=None, grid_mech=None):
     d = dict(NUMERICS_DEFAULTS)
     src = dict(phase_mech or {})
     pl = src.pop('plastic', {}) or {}
-    for k in ('r_cutback_min', 'r_cutback', 'r_increase', 'eps_rel_state', 'N_iter_state_max'):
+    known_top = ('r_cutback_min', 'r_cutback', 'r_increase', 'eps_rel_state', 'N_iter_state_max')
+    known_pl = ('N_iter_Lp_max', 'r_linesearch_Lp', 'eps_rel_Lp', 'eps_abs_Lp', 'f_update_jacobi_Lp')
+    # Li keys (phase_mechanical.f90:285-294) are accepted and unused: no law with Li != 0 is offered on the device path
+    known_ei = ('N_iter_Li_max', 'r_linesearch_Li', 'eps_rel_Li', 'eps_abs_Li', 'f_update_jacobi_Li')
+    ei = src.pop('eigen', {}) or {}
+    for name, dct, known in (('phase/mechanical', src, known_top), ('phase/mechanical/plastic', pl, known_pl + ('integrator_state',)),
+                             ('phase/mechanical/eigen', ei, known_ei)):
+        bad = [k for k in dct if k not in known]
+        if bad:
+            raise L.DmkError('numerics: unknown key(s) %s under %s' % (bad, name))
+    for k in known_top:
         if k in src:
             d[k] = src[k]
-    for k in ('N_iter_Lp_max', 'r_linesearch_Lp', 'eps_rel_Lp', 'eps_abs_Lp', 'f_update_jacobi_Lp'):
+    for k in known_pl:
         if k in pl:
             d[k] = pl[k]
     integ = pl.get('integrator_state', 'FPI')
     if integ not in INTEGRATORS:
         raise L.DmkError('unknown state integrator %s' % integ)
     d['integrator_state'] = INTEGRATORS[integ]
+    # `solver: grid: mechanical:` keys exactly as Config::parse_numerics reads them (config.cpp:386-402)
     g = dict(grid_mech or {})
-    ren = dict(N_iter_min='itmin', N_iter_max='itmax')
+    ren = {'N_iter_min': 'itmin', 'N_iter_max': 'itmax', 'eps_abs_div(P)': 'eps_abs_div', 'eps_rel_div(P)': 'eps_rel_div',
+           'eps_abs_P': 'eps_abs_P', 'eps_rel_P': 'eps_rel_P', 'update_gamma': 'update_gamma',
+           'itmin': 'itmin', 'itmax': 'itmax', 'eps_abs_div': 'eps_abs_div', 'eps_rel_div': 'eps_rel_div'}   # + the struct's own names
     for k, v in g.items():
-        k = ren.get(k, k)
-        if k in d:
-            d[k] = int(v) if k in ('itmin', 'itmax', 'update_gamma') else v
+        if k not in ren:
+            raise L.DmkError('numerics: unknown key %r under solver/grid/mechanical (known: %s)' % (k, ', '.join(sorted(ren))))
+        k = ren[k]
+        d[k] = int(v) if k in ('itmin', 'itmax', 'update_gamma') else float(v)
     n = L.Numerics()
     for k, v in d.items():
         setattr(n, k, v)

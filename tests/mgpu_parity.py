@@ -14,6 +14,10 @@ sys.path.insert(0, ROOT)
 
 def main():
     world, rank, local = int(os.environ['WORLD_SIZE']), int(os.environ['RANK']), int(os.environ['LOCAL_RANK'])
+    # a hang (a rank waiting in a collective the others never enter) must cost a bounded time: after DMK_PARITY_TIMEOUT seconds
+    # every rank dumps the stack of all its threads to stderr and exits
+    import faulthandler
+    faulthandler.dump_traceback_later(float(os.environ.get('DMK_PARITY_TIMEOUT', '240')), exit=True)
     torch.cuda.set_device(local)
     dist.init_process_group('nccl', device_id=torch.device('cuda', local))
     from solver_cpp_b200 import mech, workloads as W, parallel
@@ -72,6 +76,16 @@ def main():
     x_n1, x_p1 = s1.update_coords()
     eX = max(np.abs(x_p - x_p1[z0:z1]).max(), np.abs(x_n - x_n1[z0:z1 + 1]).max()) / max(size)
     ok &= eX < 1e-12
+    # ---- result output of a slab job: rank 0 gathers the slabs over NCCL (solver_cpp_b200.dadf5.gather_slabs)
+    from solver_cpp_b200 import dadf5
+    whole = dadf5.gather_slabs({'F': F.reshape(-1, 9), 'u_n': x_n, 'u_p': x_p.reshape(-1, 3)}, None, s.g.device)
+    if rank == 0:
+        F_all = s1.g.to_natural(s1.field('F')).reshape(-1, 9)
+        eG = max(np.abs(whole['F'] - F_all).max(), np.abs(whole['u_n'] - x_n1).max() / max(size), np.abs(whole['u_p'] - x_p1.reshape(-1, 3)).max() / max(size))
+        ok &= whole['F'].shape == F_all.shape and whole['u_n'].shape == x_n1.shape and eG < 1e-10
+        print('gather_slabs over NCCL: shapes %s %s, max err %.2e' % (whole['F'].shape, whole['u_n'].shape, eG))
+    else:
+        ok &= whole is None
     if rank == 0:
         print('solver: iterations %s vs %s, P_av rel %.2e, F abs %.2e, minmax cells %s vs %s' % (it, it1, eP, eF, sel[0], sel[1]))
         print('update_coords: rel err %.2e (solver ran with the fused exchange: %s)' % (eX, getattr(s.g, 'fused_exchange', False)))

@@ -24,10 +24,14 @@ def _ctx(cells, size):
     return GridContext(cells, size)
 
 
-def _setup(cells, grains, phase, seed=0, num_phase_mech=None):
+def _setup(cells, grains, phase, seed=0, num_phase_mech=None, mass_deferral=0):
+    """mass_deferral = 0: points whose first sub-step fails ALWAYS go to the reference-order kernel, the path whose per-cell
+    parity these tests pin; the default (in-lane cut-backs when more than 1/32 of the cells gave up, i.e. on a virgin-state
+    evaluation) has its own test: test_mass_cutback_evaluation_default_path"""
     from solver_cpp_b200 import workloads as W, material as M
     material, material_at, size = W.polycrystal(cells, grains, phase, seed)
     g = _ctx(cells, size)
+    g.set_option('pheno_mass_deferral', mass_deferral)
     g.material_init(M.Material(material, material_at), M.make_numerics(num_phase_mech) if num_phase_mech else None)
     o = ConstitutiveOracle(material, material_at, num_phase_mech=num_phase_mech)
     return g, o
@@ -232,6 +236,42 @@ def test_tangent_and_homogenisation_match_oracle(phase, rate, noise):
     if clean.all():
         _, C_vol_o, C_mm_o, sel_o = osp.homogenise(P_o, dPdF_o, grid)
         assert cellsel == sel_o and _rel(Cv, C_vol_o) < 1e-9
+
+
+def test_mass_cutback_evaluation_default_path():
+    """Default path on the evaluation the reference-order kernel is slowest at: virgin soft Cu, a strain step that makes EVERY
+    cell cut back.  More than 1/32 of the cells give up their first sub-step, so the list goes through the lane-scheduled
+    in-lane cut-back kernel.  Such an evaluation is rounding-chaotic for any build of the reference algorithm (see
+    test_constitutive_matches_oracle_over_increments): required here is what survives that -- no ill cell, every cell cut back
+    on both sides, identical sub-step bookkeeping in the mean, the homogenised stress of THIS evaluation within 5e-3 of the
+    oracle's (observed ~1e-3, the same as between the three device kernels and between the oracle and its FMA build), and --
+    the property a solve needs -- the NEXT increment, started from either state, back inside 1e-9 per cell on the cells that
+    agreed."""
+    cells = (16, 16, 8)
+    n = int(np.prod(cells))
+    rng = np.random.default_rng(11)
+    seq = _F_sequence(cells, 2, rng, rate=2.0e-3)
+    g, o = _setup(cells, 20, 'Cu_pheno', mass_deferral=-1)
+    ill_o = o.mechanical_response(seq[0].reshape(n, 9), 0.5)
+    P_o, _ = o.mechanical_response2(0.5, tangent=False)
+    c0 = g.counters()
+    P = g.to_natural(g.constitutive_response(g.to_device(seq[0]), 0.5)).reshape(n, 3, 3)
+    c1 = g.counters()
+    assert not ill_o and not g.terminally_ill()
+    assert (o.point_cutbacks > 0).all() and (g.get_state('cutbacks', 1)[:, 0] > 0).all()
+    assert c1['deferred'] - c0['deferred'] == n                                  # every cell gave up its full first sub-step
+    assert _rel(P.mean(0), P_o.mean(0)) < 5e-3
+    err = _pointwise_rel(P, P_o)
+    assert np.median(err) < 1e-2 and err.max() < 0.5
+    same = err < RTOL
+    g.materialpoint_forward(); o.forward()
+    o.mechanical_response(seq[1].reshape(n, 9), 0.5)
+    P_o, _ = o.mechanical_response2(0.5, tangent=False)
+    P = g.to_natural(g.constitutive_response(g.to_device(seq[1]), 0.5)).reshape(n, 3, 3)
+    quiet = (o.point_cutbacks == 0) & (g.get_state('cutbacks', 1)[:, 0] == 0) & (g.get_state('lp_iter', 1)[:, 0] == o.point_lp_iter)
+    if (same & quiet).any():
+        assert _pointwise_rel(P, P_o)[same & quiet].max() < RTOL
+    assert _rel(P.mean(0), P_o.mean(0)) < 5e-3
 
 
 def test_g3_homogenisation_literal_through_the_device_reductions(golden_dir):

