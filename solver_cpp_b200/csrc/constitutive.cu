@@ -396,7 +396,7 @@ void dmk_points_teardown(dmk_ctx* c) {
   cudaFree(pa->phase); cudaFree(pa->F0); cudaFree(pa->F); cudaFree(pa->Fp0); cudaFree(pa->Fp); cudaFree(pa->Fe);
   cudaFree(pa->Lp0); cudaFree(pa->Lp); cudaFree(pa->S0); cudaFree(pa->S); cudaFree(pa->state0); cudaFree(pa->state);
   if (pa->dep) cudaFree(pa->dep);
-  cudaFree(pa->nrm); cudaFree(pa->cutbacks); cudaFree(pa->lp_iter); cudaFree(pa->defer_list); cudaFree(pa->d_defer_count); cudaFree(pa->d_work); if (pa->d_cold) cudaFree(pa->d_cold); cudaFree(pa->d_phases); cudaFree(pa->d_counters); cudaFree(pa->d_ill);
+  cudaFree(pa->nrm); cudaFree(pa->cutbacks); cudaFree(pa->lp_iter); cudaFree(pa->defer_list); cudaFree(pa->d_defer_count); cudaFree(pa->d_work); cudaFree(pa->d_phases); cudaFree(pa->d_counters); cudaFree(pa->d_ill);
   delete[] pa->h_phases;
   delete[] pa->h_dev_phases;
   delete pa;

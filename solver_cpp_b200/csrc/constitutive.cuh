@@ -41,7 +41,6 @@ struct DmkPointArrays {
   int* lp_iter;                        // [n] Lp Newton iterations of each cell in the last response call (diagnostic)
   int* defer_list;                     // [n] cells the register-resident kernel handed to the reference-order kernel
   unsigned* d_defer_count;             // entries of defer_list written by the last register-resident launch
-  double* d_cold; size_t cold_doubles;  // cold part of the lane-persistent kernel's per-thread scratch (pheno_fast_dev.cuh: DmkScr)
   unsigned long long* d_work;          // next unclaimed cell of the lane-persistent kernel's chunk queue (pheno_fast.cu)
   DmkDevPhase* d_phases;               // device array
   dmk_phase* h_phases;                 // host copy

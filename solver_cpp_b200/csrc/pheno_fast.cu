@@ -84,7 +84,7 @@ static int launch_pheno_fast(dmk_ctx* c, DmkPointArrays& pa, int ph, const DmkDe
 // on neighbouring cells (coalesced structure-of-arrays accesses) and no warp is left with a long tail.  No barrier anywhere.
 #define DMK_PL_THREADS 64
 #ifndef DMK_PL_MINBLOCKS
-#define DMK_PL_MINBLOCKS 6
+#define DMK_PL_MINBLOCKS 4
 #endif
 #define DMK_PL_CHUNK 256
 template <int NSL, int NEXP, int UNR, bool VOTE3, bool CUTBACK, int MINB>
@@ -101,8 +101,7 @@ dmk_pheno_lanes_kernel(const __grid_constant__ DmkPhenoK<NSL> K, DmkPointArrays 
     if (cell_end <= (long long)list_min) return;
   }
   extern __shared__ double pf_sm[];
-  const DmkScr scr = {pf_sm + threadIdx.x, DMK_PL_THREADS, pa.d_cold + (size_t)blockIdx.x * DMK_PL_THREADS + threadIdx.x,
-                      (long long)gridDim.x * DMK_PL_THREADS};
+  const DmkScr scr = {pf_sm + threadIdx.x, DMK_PL_THREADS, pf_sm + PfOff<NSL>::TOTAL * DMK_PL_THREADS + threadIdx.x, DMK_PL_THREADS};
   const unsigned FULL = 0xffffffffu, lane = threadIdx.x & 31u, lt = (1u << lane) - 1u;
   PlLane<NSL> L;
   L.mode = PL_NEED;
@@ -245,19 +244,17 @@ static bool lanes_setting() {
   return v;
 }
 
-// DMK_PL_OCC=<4|5|6>: CTAs per SM the lane-persistent kernel is compiled for (register budget 255 / 204 / 168); default
-// DMK_PL_MINBLOCKS = 6: 12 warps per SM (sweep in profiles/r02_summary.md)
-static int occ_setting() {
-  static const int v = [] { const char* e = getenv("DMK_PL_OCC"); const int o = e ? atoi(e) : DMK_PL_MINBLOCKS; return (o == 4 || o == 5) ? o : 6; }();
-  return v;
-}
-
+// CTAs per SM: 4 x 64 threads = 8 warps, bounded by 255 registers and 840 B of shared scratch per thread alike.  Round 2 tried
+// more (profiles/r02_summary.md): with L1 / D of the scratch moved to an L2-resident global array, 456 B per thread, the kernel
+// compiled for 5 (204 registers) and 6 CTAs (168 registers, 336 B stack, 464 B spill stores) ran the 256^3 evaluation in 179.7
+// and 193.7 ms against 168.2 ms for 4 CTAs on the same layout and 160.4 ms with everything in shared memory: the spills and the
+// L2 round trips cost more than 10 or 12 warps per SM hide.
 template <int NSL, int NEXP, int UNR, bool VOTE3, bool CUTBACK, int MINB = DMK_PL_MINBLOCKS>
 static int launch_pheno_lanes(dmk_ctx* c, DmkPointArrays& pa, int ph, const DmkDevPhase& d, const DmkNumDev& nd, const double* d_F,
                               double* d_P, double dt, bool from_list = false, unsigned list_min = 0) {
   DmkPhenoK<NSL> K;
   dmk_pheno_fast_tables<NSL>(d, K);
-  const size_t smem = (size_t)PfOff<NSL>::TOTAL * DMK_PL_THREADS * sizeof(double);
+  const size_t smem = (size_t)(PfOff<NSL>::TOTAL + PfOff<NSL>::COLD_TOTAL) * DMK_PL_THREADS * sizeof(double);
   static int grid = 0;
   if (!grid) {
     DMK_CUDA_CHECK(cudaFuncSetAttribute(dmk_pheno_lanes_kernel<NSL, NEXP, UNR, VOTE3, CUTBACK, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -267,15 +264,7 @@ static int launch_pheno_lanes(dmk_ctx* c, DmkPointArrays& pa, int ph, const DmkD
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, dmk_pheno_lanes_kernel<NSL, NEXP, UNR, VOTE3, CUTBACK, MINB>, DMK_PL_THREADS, smem) != cudaSuccess || occ < 1) occ = 1;
     grid = sms * occ;                                  // one resident wave
   }
-  {                                                    // cold part of the per-thread scratch: [k][resident thread], for the largest wave
-    const size_t need = (size_t)grid * DMK_PL_THREADS * PfOff<NSL>::COLD_TOTAL;
-    if (pa.cold_doubles < need) {
-      if (pa.d_cold) DMK_CUDA_CHECK(cudaFree(pa.d_cold));
-      pa.d_cold = nullptr; pa.cold_doubles = 0;
-      DMK_CUDA_CHECK(cudaMalloc((void**)&pa.d_cold, need * sizeof(double)));
-      pa.cold_doubles = need;
-    }
-  }
+
   if (from_list) {                                     // the cells the launch before this one gave up (pa.defer_list), if they are many
     DMK_CUDA_CHECK(cudaMemsetAsync(pa.d_work, 0, sizeof(unsigned long long), c->stream));
     dmk_pheno_lanes_kernel<NSL, NEXP, UNR, VOTE3, CUTBACK, MINB><<<grid, DMK_PL_THREADS, smem, c->stream>>>(K, pa, ph, nd, d_F, d_P, dt, 0, 0, vote_weights(), pa.defer_list, pa.d_defer_count, list_min);
@@ -315,14 +304,11 @@ int dmk_points_pheno_fast(dmk_ctx* c, int ph, const DmkNumDev& nd, const double*
   const bool adaptive = cutback_setting() == 0 && dmk_pheno_lanes_eligible(nd, true);
   if (lanes_setting() && dmk_pheno_lanes_eligible(nd, cb)) {
     *deferred = !cb;                                    // in-lane cut-backs: nothing is handed to the reference-order kernel
-    const int occ = occ_setting();
 #define DMK_PL_LAUNCH(NEXP_)                                                                                   \
   (cb ? launch_pheno_lanes<12, NEXP_, 1, true, true>(c, pa, ph, d, nd, d_F, d_P, dt)                          \
       : !vote3_setting() ? launch_pheno_lanes<12, NEXP_, 1, false, false>(c, pa, ph, d, nd, d_F, d_P, dt)     \
       : (u == 2)  ? launch_pheno_lanes<12, NEXP_, 2, true, false>(c, pa, ph, d, nd, d_F, d_P, dt)             \
-      : (occ == 4) ? launch_pheno_lanes<12, NEXP_, 1, true, false, 4>(c, pa, ph, d, nd, d_F, d_P, dt)         \
-      : (occ == 5) ? launch_pheno_lanes<12, NEXP_, 1, true, false, 5>(c, pa, ph, d, nd, d_F, d_P, dt)         \
-                   : launch_pheno_lanes<12, NEXP_, 1, true, false>(c, pa, ph, d, nd, d_F, d_P, dt))
+                  : launch_pheno_lanes<12, NEXP_, 1, true, false>(c, pa, ph, d, nd, d_F, d_P, dt))
     rc = (nexp == 20) ? (DMK_PL_LAUNCH(20)) : (DMK_PL_LAUNCH(0));
 #undef DMK_PL_LAUNCH
     if (rc) return rc;

@@ -249,8 +249,8 @@ DMK_HD __forceinline__ int pl_state_block(const DmkPhenoK<NSL>& K, const DmkNumD
   double zeta = 1.0;
   if (!init && !nan) {
     double d12 = 0.0, d22 = 0.0, d01 = 0.0;           // damper (:677-690); D = last(1) - last(2)
-    // L1 and D live in the cold (global, L2-resident) part of the scratch: loaded four entries at a time so that the
-    // loads of a batch are in flight together; the sums run in the order k = 0, 1, 2, ... as before
+    // L1 and D (cold part of the scratch) are loaded four entries at a time so that the loads of a batch are in flight
+    // together; the sums run in the order k = 0, 1, 2, ... as before
     static_assert(NST % 4 == 0, "state count: batches of four");
 #pragma unroll 1
     for (int k0 = 0; k0 < NST; k0 += 4) {
