@@ -24,12 +24,13 @@ template <int LAW, int NS, int ND>
 __global__ void __launch_bounds__(DMK_PT_THREADS) dmk_constitutive_kernel(DmkPointArrays pa, int phase, DmkNumDev num,
                                                                           const double* __restrict__ Fin, double* __restrict__ Pout,
                                                                           double Dt, const int* __restrict__ list,
-                                                                          const unsigned* __restrict__ list_n, unsigned list_min) {
+                                                                          const unsigned* __restrict__ list_n,
+                                                                          const double* __restrict__ list_total, double list_min) {
   // list == nullptr: every cell of `phase`; else the *list_n cells of list[] (given up by the register-resident kernel), and
-  // only if there are more than list_min of them (fewer go through the nested kernel; the count is read on the device)
+  // only if the lists of all ranks together hold more than list_min (fewer go through the nested kernel; read on the device)
   const long long n = pa.n;
   const long long total = list ? (long long)*list_n : n;
-  if (list && total <= (long long)list_min) return;
+  if (list && !(*list_total > list_min)) return;
   const long long stride = (long long)gridDim.x * blockDim.x;
   DmkCnt cnt = {0, 0, 0, 0, 0, 0};
   unsigned ill = 0, cb0 = 0, lp0 = 0;
@@ -106,10 +107,12 @@ template <int LAW, int NS, int ND>
 __global__ void __launch_bounds__(DMK_PT_THREADS) dmk_constitutive_nested_kernel(DmkPointArrays pa, int phase, DmkNumDev num,
                                                                           const double* __restrict__ Fin, double* __restrict__ Pout,
                                                                           double Dt, const int* __restrict__ list,
-                                                                          const unsigned* __restrict__ list_n, unsigned list_max) {
+                                                                          const unsigned* __restrict__ list_n,
+                                                                          const double* __restrict__ list_total, double list_max) {
   // list == nullptr: every cell of `phase`; else the *list_n cells of list[] (deferred by the register-resident kernel),
-  // unless there are more than list_max of them (then the lane-scheduled cut-back kernel has taken the list, pheno_fast.cu)
-  if (list && *list_n > list_max) return;
+  // unless list_max >= 0 and the lists of all ranks together hold more than list_max (then a lane-scheduled kernel has
+  // taken the list, pheno_fast.cu)
+  if (list && list_max >= 0.0 && *list_total > list_max) return;
   const long long n = pa.n;
   const long long total = list ? (long long)*list_n : n;
   DmkCnt cnt = {0, 0, 0, 0, 0, 0};
@@ -283,6 +286,7 @@ static int persistent_grid(K kernel, long long n) {
 // device counter of the cells the register-resident kernel of the last evaluation gave up (their full first sub-step failed:
 // what the reference answers with a cut-back); 0 for phases that run in the reference-order kernel
 const unsigned* dmk_points_given_up_counter(dmk_ctx* c) { return c->pts->d_defer_count; }
+const double* dmk_points_given_up_total(dmk_ctx* c) { return c->pts->d_defer_total; }
 
 // DMK_PHENO_MASS: which kernel takes the deferred list when it is long (see cutback_setting() in pheno_fast.cu):
 //   lanes (default)    the register-resident 6x6 formulation with in-lane cut-backs (pheno_lanes_dev.cuh, CUTBACK = true)
@@ -314,24 +318,24 @@ int dmk_points_constitutive(dmk_ctx* c, const double* d_F, double* d_P, double d
     if (pa.n_cells_of_phase[ph] == 0) continue;
     const int law = pa.law_of_phase[ph], nst = pa.nstate_of_phase[ph];
     bool handled = false, deferred = false;
-    unsigned defer_max = 0xffffffffu;
+    double defer_max = -1.0;
     if (!use_generic && nd.integrator == DMK_INTEG_FPI) { int rc = dmk_points_pheno_fast(c, ph, nd, d_F, d_P, dt, &handled, &deferred, &defer_max); if (rc) return rc; }
     if (handled) {
       c->launches++;
       if (deferred) {          // second pass over the deferred cells only (count read on the device: no host round trip)
-        if (defer_max != 0xffffffffu && dmk_mass_deferral_setting(c) == 1 && nd.integrator == DMK_INTEG_FPI) {
+        if (defer_max >= 0.0 && dmk_mass_deferral_setting(c) == 1 && nd.integrator == DMK_INTEG_FPI) {
           // mass deferral (more than defer_max cells): the reference-order arithmetic on the lane-persistent state machine
-          DMK_LAUNCH_PERSISTENT(dmk_constitutive_kernel, law, nst, pa.n, c->stream, (pa, ph, nd, d_F, d_P, dt, pa.defer_list, pa.d_defer_count, defer_max));
+          DMK_LAUNCH_PERSISTENT(dmk_constitutive_kernel, law, nst, pa.n, c->stream, (pa, ph, nd, d_F, d_P, dt, pa.defer_list, pa.d_defer_count, pa.d_defer_total, defer_max));
           c->launches++;
         }
-        DMK_DISPATCH(dmk_constitutive_nested_kernel, law, nst, <<<148 * 4, DMK_PT_THREADS, 0, c->stream>>>(pa, ph, nd, d_F, d_P, dt, pa.defer_list, pa.d_defer_count, defer_max));
+        DMK_DISPATCH(dmk_constitutive_nested_kernel, law, nst, <<<148 * 4, DMK_PT_THREADS, 0, c->stream>>>(pa, ph, nd, d_F, d_P, dt, pa.defer_list, pa.d_defer_count, pa.d_defer_total, defer_max));
         c->launches++;
       }
       continue;
     }
     { int rc = dmk_wait_staged_input(c, d_F); if (rc) return rc; }
-    if (use_machine) DMK_LAUNCH_PERSISTENT(dmk_constitutive_kernel, law, nst, pa.n, c->stream, (pa, ph, nd, d_F, d_P, dt, nullptr, nullptr, 0u));
-    else DMK_DISPATCH(dmk_constitutive_nested_kernel, law, nst, <<<point_grid(pa.n), DMK_PT_THREADS, 0, c->stream>>>(pa, ph, nd, d_F, d_P, dt, nullptr, nullptr, 0u));
+    if (use_machine) DMK_LAUNCH_PERSISTENT(dmk_constitutive_kernel, law, nst, pa.n, c->stream, (pa, ph, nd, d_F, d_P, dt, nullptr, nullptr, nullptr, 0.0));
+    else DMK_DISPATCH(dmk_constitutive_nested_kernel, law, nst, <<<point_grid(pa.n), DMK_PT_THREADS, 0, c->stream>>>(pa, ph, nd, d_F, d_P, dt, nullptr, nullptr, nullptr, -1.0));
     c->launches++;
   }
   DMK_CUDA_CHECK(cudaGetLastError());
@@ -396,7 +400,7 @@ void dmk_points_teardown(dmk_ctx* c) {
   cudaFree(pa->phase); cudaFree(pa->F0); cudaFree(pa->F); cudaFree(pa->Fp0); cudaFree(pa->Fp); cudaFree(pa->Fe);
   cudaFree(pa->Lp0); cudaFree(pa->Lp); cudaFree(pa->S0); cudaFree(pa->S); cudaFree(pa->state0); cudaFree(pa->state);
   if (pa->dep) cudaFree(pa->dep);
-  cudaFree(pa->nrm); cudaFree(pa->cutbacks); cudaFree(pa->lp_iter); cudaFree(pa->defer_list); cudaFree(pa->d_defer_count); cudaFree(pa->d_work); cudaFree(pa->d_phases); cudaFree(pa->d_counters); cudaFree(pa->d_ill);
+  cudaFree(pa->nrm); cudaFree(pa->cutbacks); cudaFree(pa->lp_iter); cudaFree(pa->defer_list); cudaFree(pa->d_defer_count); cudaFree(pa->d_work); cudaFree(pa->d_defer_total); cudaFree(pa->d_phases); cudaFree(pa->d_counters); cudaFree(pa->d_ill);
   delete[] pa->h_phases;
   delete[] pa->h_dev_phases;
   delete pa;
@@ -483,6 +487,8 @@ extern "C" int dmk_material_init(dmk_ctx* c, const dmk_phase* phases, int n_phas
   DMK_CUDA_CHECK(cudaMalloc((void**)&pa->d_defer_count, sizeof(unsigned)));
   DMK_CUDA_CHECK(cudaMemset(pa->d_defer_count, 0, sizeof(unsigned)));
   DMK_CUDA_CHECK(cudaMalloc((void**)&pa->d_work, sizeof(unsigned long long)));
+  DMK_CUDA_CHECK(cudaMalloc((void**)&pa->d_defer_total, sizeof(double)));
+  DMK_CUDA_CHECK(cudaMemset(pa->d_defer_total, 0, sizeof(double)));
   DMK_CUDA_CHECK(cudaMalloc((void**)&pa->d_phases, n_phases * sizeof(DmkDevPhase)));
   DMK_CUDA_CHECK(cudaMalloc((void**)&pa->d_counters, 16 * sizeof(unsigned long long)));
   DMK_CUDA_CHECK(cudaMalloc((void**)&pa->d_ill, sizeof(int)));

@@ -41,6 +41,7 @@ struct DmkPointArrays {
   int* lp_iter;                        // [n] Lp Newton iterations of each cell in the last response call (diagnostic)
   int* defer_list;                     // [n] cells the register-resident kernel handed to the reference-order kernel
   unsigned* d_defer_count;             // entries of defer_list written by the last register-resident launch
+  double* d_defer_total;               // length of the given-up lists of all ranks (all-reduced), as a double
   unsigned long long* d_work;          // next unclaimed cell of the lane-persistent kernel's chunk queue (pheno_fast.cu)
   DmkDevPhase* d_phases;               // device array
   dmk_phase* h_phases;                 // host copy
@@ -63,7 +64,8 @@ int dmk_points_constitutive(dmk_ctx* c, const double* d_F, double* d_P, double d
 int dmk_wait_staged_input(dmk_ctx* c, const double* d_F);   // kernels without chunked launches: wait for the whole staged field
 int dmk_points_pheno_fast(dmk_ctx* c, int ph, const DmkNumDev& nd, const double* d_F, double* d_P, double dt, bool* handled,
                           bool* deferred /*out: cells may be waiting in pa.defer_list*/,
-                          unsigned* defer_max /*out: the reference-order kernel takes the list only if it holds at most this many*/);
+                          double* defer_max /*out: >= 0: the reference-order kernel takes the list only if *pa.d_defer_total (its
+                                              length over all ranks) is at most this; < 0: always*/);
 int dmk_mass_deferral_setting(const dmk_ctx* c);     // 0 nested, 1 machine, 2 lanes (default): who takes a long deferred list (constitutive.cu)
 int dmk_points_tangent(dmk_ctx* c, double dt, double* d_Csum81 /*device, row-major sum over local cells*/,
                        double* d_dPdF /*optional [n][81] Fortran order*/);

@@ -48,6 +48,11 @@ struct dmk_ctx {
   // when stage_ev[k] fires; the lane-persistent kernel is launched per chunk behind its event (0: F is resident)
   cudaStream_t copy_stream; cudaEvent_t stage_ev[8]; cudaEvent_t stage_begin; int stage_chunks; bool stage_ready;
   const double* stage_dst;        // device field the staged copy fills (the chunked launches apply to this input only)
+  // forward half of the distributed FFT pipelined under the per-point kernel (spectral.cu: dmk_pipe_*): the per-point kernel is
+  // launched per z-chunk, and chunk k's x r2c + y pass (with its stores into the peers' z-pass buffers) run on `pipe_stream`
+  // while chunk k+1 is being integrated
+  bool pipe_on; int pipe_chunks, pipe_done; const double* pipe_src; bool pipe_ready;
+  cudaStream_t pipe_stream; cudaEvent_t pipe_ev[8]; cudaEvent_t pipe_end;
   dmk_numerics num;
   int opt_mass;                   // who takes a long list of given-up points: -1 = DMK_PHENO_MASS / default; 0 nested, 1 machine, 2 lanes
   // ---- mechanical solver
@@ -63,9 +68,17 @@ void dmk_mech_teardown(dmk_ctx* c);
 // full transforms between a real slab field (device) and the z-pass layout in c->bufA
 int dmk_fft_forward_internal(dmk_ctx* c, const double* d_real);
 int dmk_fft_backward_internal(dmk_ctx* c, double* d_real, double scale);
+// pipelined forward half (multi-GPU, fused exchange): begin before the per-point kernel whose OUTPUT d_real is; dmk_pipe_chunk
+// after the per-point launch of every z-chunk; dmk_pipe_end waits for it (*done: the forward transform of d_real is in place)
+int dmk_pipe_begin(dmk_ctx* c, const double* d_real);
+int dmk_pipe_chunk(dmk_ctx* c, int k, int chunks);
+int dmk_pipe_end(dmk_ctx* c, bool* done);
 int dmk_gamma_internal(dmk_ctx* c);     // fused z pass on c->bufA using c->d_dc, accumulating into c->d_div
 double dmk_finish_div(dmk_ctx* c, double raw_sum);
 const unsigned* dmk_points_given_up_counter(dmk_ctx* c);
+const double* dmk_points_given_up_total(dmk_ctx* c);           // ... summed over all ranks, as a double (valid when the mass-deferral decision ran)
+int dmk_fft_forward_finish_pipelined(dmk_ctx* c);
+int dmk_fft_forward_redo_pipelined(dmk_ctx* c, const double* d_real);
 int dmk_mech_before_point_forward(dmk_ctx* c);   // computes the pending tangent reductions before state0 <- state
 
 // Fortran-order <-> row-major helpers for small host tensors

@@ -267,7 +267,17 @@ static int evaluate(dmk_ctx* c, const double* d_F, double* d_r) {
   DmkMech* m = c->mech;
   int rc;
   PROF(0);
+  if ((rc = dmk_pipe_begin(c, d_r))) return rc;                 // multi-GPU: forward x / y passes chunk by chunk under the per-point kernel
   if ((rc = dmk_points_constitutive(c, d_F, d_r, m->dt))) return rc;
+  bool forward_done = false;
+  if ((rc = dmk_pipe_end(c, &forward_done))) return rc;
+  if (forward_done) {
+    // cells integrated AFTER their chunk's launch (given up by the register-resident kernel, then cut back by another one)
+    // make the pipelined transform stale: the host learns the count here (one small read behind the per-point kernel)
+    DMK_CUDA_CHECK(cudaMemcpyAsync(c->h_pinned + 3072, dmk_points_given_up_total(c), sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    DMK_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    if (c->h_pinned[3072] > 0.0) { if ((rc = dmk_fft_forward_redo_pipelined(c, d_r))) return rc; }
+  }
   PROF(1);
   m->tangent_stale = true; m->tangent_dt = m->dt;
   if ((rc = dmk_sum_records(c, d_r, c->n_local, m->d_blk + B_SUM))) return rc;
@@ -275,7 +285,8 @@ static int evaluate(dmk_ctx* c, const double* d_F, double* d_r) {
   dmk_mech_aim_kernel<<<1, 32, 0, c->stream>>>(m->d_blk, c->wgt, c->d_dc, c->d_div);
   c->launches++;
   PROF(2);
-  if ((rc = dmk_fft_forward_internal(c, d_r))) return rc;
+  if (forward_done) { if ((rc = dmk_fft_forward_finish_pipelined(c))) return rc; }
+  else if ((rc = dmk_fft_forward_internal(c, d_r))) return rc;
   PROF(3);
   if ((rc = dmk_gamma_internal(c))) return rc;
   PROF(4);

@@ -92,13 +92,14 @@ __global__ void __launch_bounds__(DMK_PL_THREADS, MINB)
 dmk_pheno_lanes_kernel(const __grid_constant__ DmkPhenoK<NSL> K, DmkPointArrays pa, int phase, DmkNumDev num,
                        const double* __restrict__ Fin, double* __restrict__ Pout, double Dt, long long cell_begin,
                        long long cell_end, int3 vw, const int* __restrict__ list, const unsigned* __restrict__ list_n,
-                       unsigned list_min) {
+                       const double* __restrict__ list_total, double list_min) {
   // cells [cell_begin, cell_end) are this launch's share (whole slab, or one staged z-chunk); *pa.d_work counts from 0.
   // list != nullptr: the share is list[0 .. *list_n) instead (the cells an earlier launch gave up), and the launch does
-  // nothing unless there are more than list_min of them (the decision is made on the device: no host round trip)
+  // nothing unless *list_total -- the length of that list summed over all ranks -- exceeds list_min (the decision is made on
+  // the device: no host round trip; on the GLOBAL count, so that it does not depend on the slab decomposition)
   if (list) {
     cell_begin = 0; cell_end = (long long)*list_n;
-    if (cell_end <= (long long)list_min) return;
+    if (!(*list_total > list_min)) return;
   }
   extern __shared__ double pf_sm[];
   const DmkScr scr = {pf_sm + threadIdx.x, DMK_PL_THREADS, pf_sm + PfOff<NSL>::TOTAL * DMK_PL_THREADS + threadIdx.x, DMK_PL_THREADS};
@@ -251,7 +252,7 @@ static bool lanes_setting() {
 // L2 round trips cost more than 10 or 12 warps per SM hide.
 template <int NSL, int NEXP, int UNR, bool VOTE3, bool CUTBACK, int MINB = DMK_PL_MINBLOCKS>
 static int launch_pheno_lanes(dmk_ctx* c, DmkPointArrays& pa, int ph, const DmkDevPhase& d, const DmkNumDev& nd, const double* d_F,
-                              double* d_P, double dt, bool from_list = false, unsigned list_min = 0) {
+                              double* d_P, double dt, bool from_list = false, double list_min = 0.0) {
   DmkPhenoK<NSL> K;
   dmk_pheno_fast_tables<NSL>(d, K);
   const size_t smem = (size_t)(PfOff<NSL>::TOTAL + PfOff<NSL>::COLD_TOTAL) * DMK_PL_THREADS * sizeof(double);
@@ -267,34 +268,40 @@ static int launch_pheno_lanes(dmk_ctx* c, DmkPointArrays& pa, int ph, const DmkD
 
   if (from_list) {                                     // the cells the launch before this one gave up (pa.defer_list), if they are many
     DMK_CUDA_CHECK(cudaMemsetAsync(pa.d_work, 0, sizeof(unsigned long long), c->stream));
-    dmk_pheno_lanes_kernel<NSL, NEXP, UNR, VOTE3, CUTBACK, MINB><<<grid, DMK_PL_THREADS, smem, c->stream>>>(K, pa, ph, nd, d_F, d_P, dt, 0, 0, vote_weights(), pa.defer_list, pa.d_defer_count, list_min);
+    dmk_pheno_lanes_kernel<NSL, NEXP, UNR, VOTE3, CUTBACK, MINB><<<grid, DMK_PL_THREADS, smem, c->stream>>>(K, pa, ph, nd, d_F, d_P, dt, 0, 0, vote_weights(), pa.defer_list, pa.d_defer_count, pa.d_defer_total, list_min);
     c->launches++;
     return DMK_OK;
   }
   DMK_CUDA_CHECK(cudaMemsetAsync(pa.d_defer_count, 0, sizeof(unsigned), c->stream));
   // one launch over the slab, or one per staged z-chunk of F, each behind the event of its host-to-device copy
-  const int chunks = (c->stage_chunks > 1 && d_F == c->stage_dst) ? c->stage_chunks : 1;
+  const bool staged = c->stage_chunks > 1 && d_F == c->stage_dst;
+  const bool piped = c->pipe_on && d_P == c->pipe_src && pa.n_cells_of_phase[ph] == pa.n;     // the only phase: its chunk is complete after its launch
+  const int chunks = staged ? c->stage_chunks : piped ? c->pipe_chunks : 1;
+  if (staged && piped && c->stage_chunks != c->pipe_chunks) c->pipe_on = false;
   const long long plane = (long long)c->nx * c->ny;
   for (int k = 0; k < chunks; k++) {
     const long long z0 = (long long)c->nz_loc * k / chunks, z1 = (long long)c->nz_loc * (k + 1) / chunks;
     const long long first = z0 * plane, end = z1 * plane;
     if (end <= first) continue;
-    if (chunks > 1) DMK_CUDA_CHECK(cudaStreamWaitEvent(c->stream, c->stage_ev[k], 0));
+    if (staged) DMK_CUDA_CHECK(cudaStreamWaitEvent(c->stream, c->stage_ev[k], 0));
     DMK_CUDA_CHECK(cudaMemsetAsync(pa.d_work, 0, sizeof(unsigned long long), c->stream));
     const long long warps_needed = (end - first + 31) / 32;
     const int g = (int)std::max(1LL, std::min((long long)grid, (warps_needed + 1) / 2));
-    dmk_pheno_lanes_kernel<NSL, NEXP, UNR, VOTE3, CUTBACK, MINB><<<g, DMK_PL_THREADS, smem, c->stream>>>(K, pa, ph, nd, d_F, d_P, dt, first, end, vote_weights(), nullptr, nullptr, 0u);
+    dmk_pheno_lanes_kernel<NSL, NEXP, UNR, VOTE3, CUTBACK, MINB><<<g, DMK_PL_THREADS, smem, c->stream>>>(K, pa, ph, nd, d_F, d_P, dt, first, end, vote_weights(), nullptr, nullptr, nullptr, 0.0);
     if (k > 0) c->launches++;
+    if (piped) { int rc = dmk_pipe_chunk(c, k, chunks); if (rc) return rc; }
   }
   return DMK_OK;
 }
 
 // Runs phase `ph` through the register-resident kernel if it qualifies (*handled), else leaves it to the generic kernel.
+__global__ void dmk_defer_total_kernel(const unsigned* __restrict__ count, double* __restrict__ total) { *total = (double)*count; }
+
 int dmk_points_pheno_fast(dmk_ctx* c, int ph, const DmkNumDev& nd, const double* d_F, double* d_P, double dt, bool* handled,
-                          bool* deferred, unsigned* defer_max) {
+                          bool* deferred, double* defer_max) {
   DmkPointArrays& pa = *c->pts;
   int nexp = 0;
-  *handled = false; *deferred = false; *defer_max = 0xffffffffu;
+  *handled = false; *deferred = false; *defer_max = -1.0;
   if (!dmk_pheno_fast_eligible(pa.h_dev_phases[ph], 12, &nexp)) return DMK_OK;       // 12 slip systems: fcc, bcc {110}
   *handled = true; *deferred = defer_setting() > 0;
   const DmkDevPhase& d = pa.h_dev_phases[ph];
@@ -312,8 +319,20 @@ int dmk_points_pheno_fast(dmk_ctx* c, int ph, const DmkNumDev& nd, const double*
     rc = (nexp == 20) ? (DMK_PL_LAUNCH(20)) : (DMK_PL_LAUNCH(0));
 #undef DMK_PL_LAUNCH
     if (rc) return rc;
+    // the length of the given-up list over ALL ranks (one all-reduce of one double): decides who takes the list -- the same
+    // cells take the same kernel whatever the slab decomposition, so a z-slab job reproduces the single-GPU job bit for bit --
+    // and tells the pipelined forward FFT whether cells changed after their chunk's pass (mech_solver.cu: evaluate)
+    if (cb) DMK_CUDA_CHECK(cudaMemsetAsync(pa.d_defer_total, 0, sizeof(double), c->stream));
+    else {
+      dmk_defer_total_kernel<<<1, 1, 0, c->stream>>>(pa.d_defer_count, pa.d_defer_total);
+      c->launches++;
+      if (c->P > 1) {
+        if (!c->has_comm || !c->comm.allreduce_sum) { dmk_set_error("no allreduce callback (dmk_set_comm)"); return DMK_ERR_STATE; }
+        if (c->comm.allreduce_sum(c->comm.user, pa.d_defer_total, 1)) { dmk_set_error("allreduce failed"); return DMK_ERR_STATE; }
+      }
+    }
     if (!cb && adaptive && dmk_mass_deferral_setting(c) != 0) {       // mass deferral
-      const unsigned many = (unsigned)std::min<long long>(pa.n / 32, 0x7fffffffLL);
+      const double many = (double)(c->n_global / 32);
       if (dmk_mass_deferral_setting(c) == 2) {            // ... through the in-lane cut-back kernel (else: constitutive.cu)
         rc = (nexp == 20) ? launch_pheno_lanes<12, 20, 1, true, true>(c, pa, ph, d, nd, d_F, d_P, dt, true, many)
                           : launch_pheno_lanes<12, 0, 1, true, true>(c, pa, ph, d, nd, d_F, d_P, dt, true, many);

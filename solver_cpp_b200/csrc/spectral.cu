@@ -143,6 +143,7 @@ extern "C" void dmk_destroy(dmk_ctx* c) {
   if (c->m_F0) cudaFreeHost(c->m_F0); if (c->m_F) cudaFreeHost(c->m_F); if (c->m_P) cudaFreeHost(c->m_P);
   if (c->m_dPdF) cudaFreeHost(c->m_dPdF); if (c->m_ill) cudaFreeHost(c->m_ill);
   if (c->ev[0]) for (int i = 0; i < 8; i++) cudaEventDestroy(c->ev[i]);
+  if (c->pipe_ready) { for (int k = 0; k < 8; k++) cudaEventDestroy(c->pipe_ev[k]); cudaEventDestroy(c->pipe_end); cudaStreamDestroy(c->pipe_stream); }
   if (c->stage_ready) { for (int k = 0; k < 8; k++) cudaEventDestroy(c->stage_ev[k]); cudaEventDestroy(c->stage_begin); cudaStreamDestroy(c->copy_stream); }
   if (c->own_stream) cudaStreamDestroy(c->stream);
   delete c;
@@ -257,6 +258,70 @@ int dmk_fft_forward_internal(dmk_ctx* c, const double* d_real) {
     c->launches++;
     if ((rc = exchange(c, c->bufB, c->bufA))) return rc;
   }
+  return DMK_OK;
+}
+
+// ---- forward half pipelined under the per-point kernel (see ctx.h).  Only for the fused exchange over peer memory: there the
+// y pass carries the NVLink traffic of the forward transpose (1.06 GB per GPU at 512^3 on 8), which this hides behind the
+// 160 ms of the constitutive update; DMK_PIPELINE=0 switches it off.
+static bool pipe_wanted(dmk_ctx* c) {
+  static const bool env_on = [] { const char* e = getenv("DMK_PIPELINE"); return !(e && atoi(e) == 0); }();
+  return env_on && c->P > 1 && c->p2p && c->nz_loc >= 2 && c->ny > 1;
+}
+int dmk_pipe_begin(dmk_ctx* c, const double* d_real) {
+  c->pipe_on = false; c->pipe_done = 0;
+  if (!pipe_wanted(c)) return DMK_OK;
+  if (!c->pipe_ready) {
+    DMK_CUDA_CHECK(cudaStreamCreateWithFlags(&c->pipe_stream, cudaStreamNonBlocking));
+    for (int k = 0; k < 8; k++) DMK_CUDA_CHECK(cudaEventCreateWithFlags(&c->pipe_ev[k], cudaEventDisableTiming));
+    DMK_CUDA_CHECK(cudaEventCreateWithFlags(&c->pipe_end, cudaEventDisableTiming));
+    c->pipe_ready = true;
+  }
+  int rc = p2p_barrier(c);                                  // the peers are done reading their bufB (previous inverse)
+  if (rc) return rc;
+  c->pipe_chunks = c->nz_loc >= 8 ? 8 : c->nz_loc;
+  c->pipe_src = d_real;
+  c->pipe_on = true;
+  return DMK_OK;
+}
+int dmk_pipe_chunk(dmk_ctx* c, int k, int chunks) {
+  if (!c->pipe_on) return DMK_OK;
+  if (chunks != c->pipe_chunks || k != c->pipe_done) { c->pipe_on = false; return DMK_OK; }     // not the launch pattern expected: fall back
+  const int z0 = (int)((long long)c->nz_loc * k / chunks), z1 = (int)((long long)c->nz_loc * (k + 1) / chunks);
+  DMK_CUDA_CHECK(cudaEventRecord(c->pipe_ev[k], c->stream));
+  DMK_CUDA_CHECK(cudaStreamWaitEvent(c->pipe_stream, c->pipe_ev[k], 0));
+  if (z1 > z0) {
+    int rc;
+    const size_t row0 = (size_t)z0 * c->ny;
+    if ((rc = dmk_launch_xpass_r2c(c->pipe_src + row0 * c->nx * DMK_NC, c->bufA + row0 * c->nxr * DMK_NC, c->plx, c->ny * (z1 - z0), c->pipe_stream))) return rc;
+    DmkPeerStore ps = peers_forward(c);
+    for (int p = 0; p < c->P; p++) ps.peer[p] += (size_t)z0 * ps.o_stride * DMK_NC;
+    if ((rc = dmk_launch_line_pass(false, c->bufA + row0 * c->nxr * DMK_NC, c->bufB, c->ply, map_y(c, false), map_y(c, true), c->nxr, z1 - z0, c->kt_y, c->pipe_stream, &ps))) return rc;
+    c->launches += 2;
+  }
+  c->pipe_done++;
+  return DMK_OK;
+}
+int dmk_pipe_end(dmk_ctx* c, bool* done) {
+  *done = false;
+  if (!c->pipe_on) return DMK_OK;
+  c->pipe_on = false;
+  if (c->pipe_done != c->pipe_chunks) return DMK_OK;         // the per-point launches were not chunked (other law): normal path
+  DMK_CUDA_CHECK(cudaEventRecord(c->pipe_end, c->pipe_stream));
+  DMK_CUDA_CHECK(cudaStreamWaitEvent(c->stream, c->pipe_end, 0));
+  *done = true;
+  return DMK_OK;
+}
+// the rest of the forward transform after dmk_pipe_end(done): every rank's stores must have landed before the z pass
+int dmk_fft_forward_finish_pipelined(dmk_ctx* c) { return p2p_barrier(c); }
+// forward transform of d_real when the pipelined one has to be repeated (cells were integrated after their chunk's pass): the
+// barrier before the remote stores has been passed already
+int dmk_fft_forward_redo_pipelined(dmk_ctx* c, const double* d_real) {
+  int rc;
+  if ((rc = dmk_launch_xpass_r2c(d_real, c->bufA, c->plx, c->ny * c->nz_loc, c->stream))) return rc;
+  const DmkPeerStore ps = peers_forward(c);
+  if ((rc = dmk_launch_line_pass(false, c->bufA, c->bufB, c->ply, map_y(c, false), map_y(c, true), c->nxr, c->nz_loc, c->kt_y, c->stream, &ps))) return rc;
+  c->launches += 2;
   return DMK_OK;
 }
 

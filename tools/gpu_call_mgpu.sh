@@ -17,3 +17,17 @@ if [ $# -ge 3 ]; then
   tail -3 gpurun_out/r02_bench_solve_n${N}_small.err | cut -c1-400
   cut -c1-3000 gpurun_out/r02_bench_solve_n${N}_small.json
 fi
+if [ "${DMK_MGPU_EVAL:-1}" = "1" ]; then
+  for pipe in 1 0; do
+    DMK_PIPELINE=$pipe timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 2954$N \
+        bench.py --gpus $N --protocol evaluation --steps 5 --warmup 3 --no-cpu > gpurun_out/r02_bench_eval_n${N}_pipe$pipe.json 2> gpurun_out/r02_bench_eval_n${N}_pipe$pipe.err; echo "bench eval N=$N pipeline=$pipe rc=$?"
+    python - <<PY
+import json
+try:
+    d=json.load(open('gpurun_out/r02_bench_eval_n${N}_pipe$pipe.json'))
+    print('N=$N pipeline=$pipe ms/eval %.2f' % d['ms_per_step'], d['kernel_ms'], 'hbm frac %.3f' % d['roofline_hbm']['frac'])
+except Exception as e:
+    print('no line:', e)
+PY
+  done
+fi
