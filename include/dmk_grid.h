@@ -229,6 +229,25 @@ int dmk_mech_reports(dmk_ctx* ctx, double* out, size_t max_rows, size_t* n_rows)
 
 /* ------------------------------------------------------------------ (1) Fortran-named drop-in symbols */
 int dmk_bind_global(dmk_ctx* ctx);
+/* init symbols of the reference's main.cpp:9-14,80-86 and discretization_grid.h:10-19 (csrc/init_dropin.cpp): initBase keeps
+ * the file names (lengths by value, as Fortran character arguments), f_discretization_init the 1-based material index and
+ * the cell-centre coordinates of this rank's cells (x fastest), initDamask reads material.yaml / numerics.yaml, creates
+ * a context for the local slab, initialises the per-point state on the device and binds it (dmk_bound_context) */
+void f_materialpoint_initBase(const char* material_path, int material_path_len, const char* load_path, int load_path_len,
+                              const char* grid_path, int grid_path_len, const char* numerics_path, int numerics_path_len);
+void f_materialpoint_initDamask(void);
+void f_discretization_init(int* material_at, int* n_materialpoints, double* IPcoords0, int* n_ips, double* NodeCoords0,
+                           int* n_nodes, int* shared_nodes_begin);
+void f_discretization_setIPcoords(double* IPcoords0);
+void f_discretization_setNodeCoords(double* NodeCoords);
+void f_discretization_fetch_ip_node_coord_pointers(double** ip_coords_ptr, double** node_coords_ptr);
+void f_CLI_get_geomFilename(char* filename);
+dmk_ctx* dmk_bound_context(void);       /* the context f_materialpoint_initDamask made (NULL if it failed: dmk_last_error) */
+/* material.yaml -> phase tables and, per `material:` entry, phase index and orientation matrix (row-major); numerics.yaml ->
+ * dmk_numerics (a NULL / empty path gives the defaults) -- the C++ twin of solver_cpp_b200/material.py */
+int dmk_material_from_yaml(const char* material_yaml_path, double T, dmk_phase* phases, int max_phases, int* n_phases,
+                           int* phase_of_material, double* O_of_material, int max_materials, int* n_materials);
+int dmk_numerics_from_yaml(const char* numerics_yaml_path, dmk_numerics* num, int* derivative, int* divergence_correction);
 void f_homogenization_fetch_tensor_pointers(double** homogenization_F0, double** homogenization_F,
                                             double** homogenization_P, double** homogenization_dPdF,
                                             void** terminally_ill);

@@ -486,7 +486,7 @@ extern "C" int dmk_material_init(dmk_ctx* c, const dmk_phase* phases, int n_phas
   DMK_CUDA_CHECK(cudaMalloc((void**)&pa->defer_list, n * sizeof(int)));
   DMK_CUDA_CHECK(cudaMalloc((void**)&pa->d_defer_count, sizeof(unsigned)));
   DMK_CUDA_CHECK(cudaMemset(pa->d_defer_count, 0, sizeof(unsigned)));
-  DMK_CUDA_CHECK(cudaMalloc((void**)&pa->d_work, sizeof(unsigned long long)));
+  DMK_CUDA_CHECK(cudaMalloc((void**)&pa->d_work, 8 * sizeof(unsigned long long)));       // one queue per z-chunk launch
   DMK_CUDA_CHECK(cudaMalloc((void**)&pa->d_defer_total, sizeof(double)));
   DMK_CUDA_CHECK(cudaMemset(pa->d_defer_total, 0, sizeof(double)));
   DMK_CUDA_CHECK(cudaMalloc((void**)&pa->d_phases, n_phases * sizeof(DmkDevPhase)));

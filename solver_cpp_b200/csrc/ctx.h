@@ -53,6 +53,7 @@ struct dmk_ctx {
   // while chunk k+1 is being integrated
   bool pipe_on; int pipe_chunks, pipe_done; const double* pipe_src; bool pipe_ready;
   cudaStream_t pipe_stream; cudaEvent_t pipe_ev[8]; cudaEvent_t pipe_end;
+  cudaStream_t chunk_stream[2]; cudaEvent_t pipe_begin;   // the per-point kernel's z-chunks alternate between two streams
   dmk_numerics num;
   int opt_mass;                   // who takes a long list of given-up points: -1 = DMK_PHENO_MASS / default; 0 nested, 1 machine, 2 lanes
   // ---- mechanical solver
@@ -71,7 +72,7 @@ int dmk_fft_backward_internal(dmk_ctx* c, double* d_real, double scale);
 // pipelined forward half (multi-GPU, fused exchange): begin before the per-point kernel whose OUTPUT d_real is; dmk_pipe_chunk
 // after the per-point launch of every z-chunk; dmk_pipe_end waits for it (*done: the forward transform of d_real is in place)
 int dmk_pipe_begin(dmk_ctx* c, const double* d_real);
-int dmk_pipe_chunk(dmk_ctx* c, int k, int chunks);
+int dmk_pipe_chunk(dmk_ctx* c, int k, int chunks, cudaStream_t chunk_stream);
 int dmk_pipe_end(dmk_ctx* c, bool* done);
 int dmk_gamma_internal(dmk_ctx* c);     // fused z pass on c->bufA using c->d_dc, accumulating into c->d_div
 double dmk_finish_div(dmk_ctx* c, double raw_sum);

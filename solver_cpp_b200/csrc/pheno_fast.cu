@@ -91,9 +91,9 @@ template <int NSL, int NEXP, int UNR, bool VOTE3, bool CUTBACK, int MINB>
 __global__ void __launch_bounds__(DMK_PL_THREADS, MINB)
 dmk_pheno_lanes_kernel(const __grid_constant__ DmkPhenoK<NSL> K, DmkPointArrays pa, int phase, DmkNumDev num,
                        const double* __restrict__ Fin, double* __restrict__ Pout, double Dt, long long cell_begin,
-                       long long cell_end, int3 vw, const int* __restrict__ list, const unsigned* __restrict__ list_n,
+                       long long cell_end, int3 vw, unsigned long long* __restrict__ work, const int* __restrict__ list, const unsigned* __restrict__ list_n,
                        const double* __restrict__ list_total, double list_min) {
-  // cells [cell_begin, cell_end) are this launch's share (whole slab, or one staged z-chunk); *pa.d_work counts from 0.
+  // cells [cell_begin, cell_end) are this launch's share (whole slab, or one z-chunk); *work, this launch's queue, counts from 0.
   // list != nullptr: the share is list[0 .. *list_n) instead (the cells an earlier launch gave up), and the launch does
   // nothing unless *list_total -- the length of that list summed over all ranks -- exceeds list_min (the decision is made on
   // the device: no host round trip; on the GLOBAL count, so that it does not depend on the slab decomposition)
@@ -162,7 +162,7 @@ dmk_pheno_lanes_kernel(const __grid_constant__ DmkPhenoK<NSL> K, DmkPointArrays 
     while (need) {
       if (c_next >= c_end) {
         unsigned long long base = 0;
-        if (lane == 0) base = atomicAdd(pa.d_work, (unsigned long long)DMK_PL_CHUNK);
+        if (lane == 0) base = atomicAdd(work, (unsigned long long)DMK_PL_CHUNK);
         base = __shfl_sync(FULL, base, 0) + (unsigned long long)cell_begin;
         if ((long long)base >= cell_end) { drained = true; break; }
         c_next = (long long)base;
@@ -268,29 +268,40 @@ static int launch_pheno_lanes(dmk_ctx* c, DmkPointArrays& pa, int ph, const DmkD
 
   if (from_list) {                                     // the cells the launch before this one gave up (pa.defer_list), if they are many
     DMK_CUDA_CHECK(cudaMemsetAsync(pa.d_work, 0, sizeof(unsigned long long), c->stream));
-    dmk_pheno_lanes_kernel<NSL, NEXP, UNR, VOTE3, CUTBACK, MINB><<<grid, DMK_PL_THREADS, smem, c->stream>>>(K, pa, ph, nd, d_F, d_P, dt, 0, 0, vote_weights(), pa.defer_list, pa.d_defer_count, pa.d_defer_total, list_min);
+    dmk_pheno_lanes_kernel<NSL, NEXP, UNR, VOTE3, CUTBACK, MINB><<<grid, DMK_PL_THREADS, smem, c->stream>>>(K, pa, ph, nd, d_F, d_P, dt, 0, 0, vote_weights(), pa.d_work, pa.defer_list, pa.d_defer_count, pa.d_defer_total, list_min);
     c->launches++;
     return DMK_OK;
   }
   DMK_CUDA_CHECK(cudaMemsetAsync(pa.d_defer_count, 0, sizeof(unsigned), c->stream));
-  // one launch over the slab, or one per staged z-chunk of F, each behind the event of its host-to-device copy
+  // one launch over the slab, or one per z-chunk: staged input (chunk k of F arrives behind stage_ev[k]) and / or the pipelined
+  // forward FFT (spectral.cu: dmk_pipe_*, which transforms chunk k's stress while chunk k+1 is integrated).  Chunks for the
+  // pipeline go to two alternating streams, each with its own work queue: chunk k+1's CTAs move in as chunk k's retire, so
+  // the tail of a chunk (lanes finishing their last cells, ~1 ms) is not paid eight times as with launches in one stream
   const bool staged = c->stage_chunks > 1 && d_F == c->stage_dst;
   const bool piped = c->pipe_on && d_P == c->pipe_src && pa.n_cells_of_phase[ph] == pa.n;     // the only phase: its chunk is complete after its launch
   const int chunks = staged ? c->stage_chunks : piped ? c->pipe_chunks : 1;
   if (staged && piped && c->stage_chunks != c->pipe_chunks) c->pipe_on = false;
+  const bool conc = piped && c->pipe_on && chunks > 1;
   const long long plane = (long long)c->nx * c->ny;
+  DMK_CUDA_CHECK(cudaMemsetAsync(pa.d_work, 0, 8 * sizeof(unsigned long long), c->stream));
+  if (conc) {
+    DMK_CUDA_CHECK(cudaEventRecord(c->pipe_begin, c->stream));
+    for (int q = 0; q < 2; q++) DMK_CUDA_CHECK(cudaStreamWaitEvent(c->chunk_stream[q], c->pipe_begin, 0));
+  }
   for (int k = 0; k < chunks; k++) {
     const long long z0 = (long long)c->nz_loc * k / chunks, z1 = (long long)c->nz_loc * (k + 1) / chunks;
     const long long first = z0 * plane, end = z1 * plane;
-    if (end <= first) continue;
-    if (staged) DMK_CUDA_CHECK(cudaStreamWaitEvent(c->stream, c->stage_ev[k], 0));
-    DMK_CUDA_CHECK(cudaMemsetAsync(pa.d_work, 0, sizeof(unsigned long long), c->stream));
-    const long long warps_needed = (end - first + 31) / 32;
-    const int g = (int)std::max(1LL, std::min((long long)grid, (warps_needed + 1) / 2));
-    dmk_pheno_lanes_kernel<NSL, NEXP, UNR, VOTE3, CUTBACK, MINB><<<g, DMK_PL_THREADS, smem, c->stream>>>(K, pa, ph, nd, d_F, d_P, dt, first, end, vote_weights(), nullptr, nullptr, nullptr, 0.0);
-    if (k > 0) c->launches++;
-    if (piped) { int rc = dmk_pipe_chunk(c, k, chunks); if (rc) return rc; }
+    cudaStream_t st = conc ? c->chunk_stream[k & 1] : c->stream;
+    if (end > first) {
+      if (staged) DMK_CUDA_CHECK(cudaStreamWaitEvent(st, c->stage_ev[k], 0));
+      const long long warps_needed = (end - first + 31) / 32;
+      const int g = (int)std::max(1LL, std::min((long long)grid, (warps_needed + 1) / 2));
+      dmk_pheno_lanes_kernel<NSL, NEXP, UNR, VOTE3, CUTBACK, MINB><<<g, DMK_PL_THREADS, smem, st>>>(K, pa, ph, nd, d_F, d_P, dt, first, end, vote_weights(), pa.d_work + k, nullptr, nullptr, nullptr, 0.0);
+      if (k > 0) c->launches++;
+    }
+    if (piped) { int rc = dmk_pipe_chunk(c, k, chunks, st); if (rc) return rc; }
   }
+  if (conc) for (int k = 0; k < chunks; k++) DMK_CUDA_CHECK(cudaStreamWaitEvent(c->stream, c->pipe_ev[k], 0));
   return DMK_OK;
 }
 

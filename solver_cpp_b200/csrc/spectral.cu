@@ -143,7 +143,11 @@ extern "C" void dmk_destroy(dmk_ctx* c) {
   if (c->m_F0) cudaFreeHost(c->m_F0); if (c->m_F) cudaFreeHost(c->m_F); if (c->m_P) cudaFreeHost(c->m_P);
   if (c->m_dPdF) cudaFreeHost(c->m_dPdF); if (c->m_ill) cudaFreeHost(c->m_ill);
   if (c->ev[0]) for (int i = 0; i < 8; i++) cudaEventDestroy(c->ev[i]);
-  if (c->pipe_ready) { for (int k = 0; k < 8; k++) cudaEventDestroy(c->pipe_ev[k]); cudaEventDestroy(c->pipe_end); cudaStreamDestroy(c->pipe_stream); }
+  if (c->pipe_ready) {
+    for (int k = 0; k < 8; k++) cudaEventDestroy(c->pipe_ev[k]);
+    cudaEventDestroy(c->pipe_end); cudaEventDestroy(c->pipe_begin); cudaStreamDestroy(c->pipe_stream);
+    for (int q = 0; q < 2; q++) cudaStreamDestroy(c->chunk_stream[q]);
+  }
   if (c->stage_ready) { for (int k = 0; k < 8; k++) cudaEventDestroy(c->stage_ev[k]); cudaEventDestroy(c->stage_begin); cudaStreamDestroy(c->copy_stream); }
   if (c->own_stream) cudaStreamDestroy(c->stream);
   delete c;
@@ -272,9 +276,13 @@ int dmk_pipe_begin(dmk_ctx* c, const double* d_real) {
   c->pipe_on = false; c->pipe_done = 0;
   if (!pipe_wanted(c)) return DMK_OK;
   if (!c->pipe_ready) {
-    DMK_CUDA_CHECK(cudaStreamCreateWithFlags(&c->pipe_stream, cudaStreamNonBlocking));
+    int lo = 0, hi = 0;
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);          // the short FFT kernels get the SM slots the per-point kernel's CTAs free first
+    DMK_CUDA_CHECK(cudaStreamCreateWithPriority(&c->pipe_stream, cudaStreamNonBlocking, hi));
     for (int k = 0; k < 8; k++) DMK_CUDA_CHECK(cudaEventCreateWithFlags(&c->pipe_ev[k], cudaEventDisableTiming));
     DMK_CUDA_CHECK(cudaEventCreateWithFlags(&c->pipe_end, cudaEventDisableTiming));
+    DMK_CUDA_CHECK(cudaEventCreateWithFlags(&c->pipe_begin, cudaEventDisableTiming));
+    for (int q = 0; q < 2; q++) DMK_CUDA_CHECK(cudaStreamCreateWithFlags(&c->chunk_stream[q], cudaStreamNonBlocking));
     c->pipe_ready = true;
   }
   int rc = p2p_barrier(c);                                  // the peers are done reading their bufB (previous inverse)
@@ -284,11 +292,11 @@ int dmk_pipe_begin(dmk_ctx* c, const double* d_real) {
   c->pipe_on = true;
   return DMK_OK;
 }
-int dmk_pipe_chunk(dmk_ctx* c, int k, int chunks) {
+int dmk_pipe_chunk(dmk_ctx* c, int k, int chunks, cudaStream_t chunk_stream) {
   if (!c->pipe_on) return DMK_OK;
   if (chunks != c->pipe_chunks || k != c->pipe_done) { c->pipe_on = false; return DMK_OK; }     // not the launch pattern expected: fall back
   const int z0 = (int)((long long)c->nz_loc * k / chunks), z1 = (int)((long long)c->nz_loc * (k + 1) / chunks);
-  DMK_CUDA_CHECK(cudaEventRecord(c->pipe_ev[k], c->stream));
+  DMK_CUDA_CHECK(cudaEventRecord(c->pipe_ev[k], chunk_stream));
   DMK_CUDA_CHECK(cudaStreamWaitEvent(c->pipe_stream, c->pipe_ev[k], 0));
   if (z1 > z0) {
     int rc;

@@ -1,0 +1,151 @@
+"""CPU tests of the library's own YAML reader and C++ material / numerics set-up (csrc/yaml_min.cpp, csrc/init_dropin.cpp), which
+the init symbols of the drop-in boundary use (f_materialpoint_initDamask): against PyYAML and against the Python host's
+solver_cpp_b200.material on the same files."""
+import ctypes as C
+import json
+import os
+import subprocess
+
+import numpy as np
+import pytest
+import yaml
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BUILD = os.path.join(ROOT, 'tests', 'abi', '_build')
+
+
+@pytest.fixture(scope='module')
+def yaml_dump():
+    os.makedirs(BUILD, exist_ok=True)
+    exe = os.path.join(BUILD, 'yaml_dump')
+    src = [os.path.join(ROOT, 'tests', 'abi', 'yaml_dump.cpp'), os.path.join(ROOT, 'solver_cpp_b200', 'csrc', 'yaml_min.cpp')]
+    if not os.path.exists(exe) or any(os.path.getmtime(s) > os.path.getmtime(exe) for s in src):
+        subprocess.run(['g++', '-std=c++17', '-O1', '-o', exe] + src, check=True)
+    return exe
+
+
+def _same(a, b, path=''):
+    if isinstance(b, dict):
+        assert isinstance(a, dict) and [str(k) for k in b] == list(a), path
+        for k in b:
+            _same(a[str(k)], b[k], path + '/' + str(k))
+    elif isinstance(b, list):
+        assert isinstance(a, list) and len(a) == len(b), path
+        for i, (x, y) in enumerate(zip(a, b)):
+            _same(x, y, '%s[%d]' % (path, i))
+    elif b is None:
+        assert a is None, path
+    elif isinstance(b, bool):
+        assert a.lower() in (('true', 'yes', 'on') if b else ('false', 'no', 'off')), path
+    elif isinstance(b, (int, float)):
+        assert float(a) == float(b), (path, a, b)
+    else:
+        assert a == str(b), (path, a, b)
+
+
+TRICKY = """
+# comment line
+---
+solver: {mechanical: spectral_basic}      # flow mapping, trailing comment
+loadstep:
+  - boundary_conditions:
+      mechanical:
+        dot_F: [[1.0e-3, 0, 0],
+                [0, x, 0],
+                [0, 0, x]]
+        P: [ [x, x, x], [x, 0, x], [x, x, 0] ]
+    discretization: {t: 5, N: 10}
+    f_out: 4
+  -   boundary_conditions: {mechanical: {dot_F: [[0, 0, 0], [0, 0, 0], [0, 0, 0]], P: [[x, x, x], [x, x, x], [x, x, x]]}}
+      discretization:
+        t: 1.5
+        N: 3
+phase:
+  "A phase":
+    lattice: cF
+    'C_11,T^2': -9.790e3
+    references:
+      - first line,
+        continued line
+      - https://doi.org/10.1000/x#y
+    empty:
+list_at_key_indent:
+- 1
+- two
+"""
+
+
+def test_reader_matches_pyyaml(yaml_dump, golden_dir, tmp_path):
+    files = [os.path.join(golden_dir, f) for f in sorted(os.listdir(golden_dir)) if f.endswith('.yaml')]
+    p = tmp_path / 'tricky.yaml'
+    p.write_text(TRICKY)
+    files.append(str(p))
+    assert len(files) >= 5
+    for f in files:
+        r = subprocess.run([yaml_dump, f], capture_output=True, text=True)
+        assert r.returncode == 0, (f, r.stderr)
+        _same(json.loads(r.stdout), yaml.safe_load(open(f)), f)
+
+
+def test_reader_rejects_what_it_does_not_understand(yaml_dump, tmp_path):
+    for bad in ('a: [1, 2\n', 'a:\n\t- 1\n', 'a: 1\n  b: 2\n', 'just a line\nanother: 1\n'):
+        p = tmp_path / 'bad.yaml'
+        p.write_text(bad)
+        r = subprocess.run([yaml_dump, str(p)], capture_output=True, text=True)
+        assert r.returncode == 1 and 'YAML' in r.stderr, (bad, r.stdout, r.stderr)
+
+
+def test_cpp_material_setup_equals_python_host(tmp_path, golden_dir):
+    """dmk_material_from_yaml (what f_materialpoint_initDamask uses) against solver_cpp_b200.material on the same material.yaml:
+    every phase table byte for byte, phase index and orientation matrix of every material entry"""
+    from solver_cpp_b200 import lib as L, material as M, workloads as W
+    lib = L.load()
+    decks = []
+    for phase in ('Al_pheno', 'Cu_pheno', 'Al_iso', 'Al_elastic', 'TWIP'):
+        material, _, _ = W.polycrystal((4, 4, 4), 5, phase, 1)
+        p = tmp_path / ('material_%s.yaml' % phase)
+        p.write_text(yaml.safe_dump(material))
+        decks.append((str(p), material))
+    for name in ('material_20grains_Al.yaml', '12grains6x7x8.material.yaml', '6grains6x7x8_single_phase_tensionY.material.yaml'):
+        f = os.path.join(golden_dir, name)
+        if os.path.exists(f):
+            decks.append((f, yaml.safe_load(open(f))))
+    assert len(decks) >= 7
+    for path, material in decks:
+        n_mat = len(material['material'])
+        phases = (L.Phase * L.MAX_PHASES)()
+        nph, nm = C.c_int(), C.c_int()
+        ph_of = np.zeros(n_mat, dtype=np.int32)
+        O = np.zeros((n_mat, 9))
+        rc = lib.dmk_material_from_yaml(path.encode(), C.c_double(M.T_ROOM), phases, C.c_int(L.MAX_PHASES), C.byref(nph),
+                                        ph_of.ctypes.data_as(C.c_void_p), O.ctypes.data_as(C.c_void_p), C.c_int(n_mat), C.byref(nm))
+        assert rc == 0, lib.dmk_last_error()
+        ref = M.Material(material, np.arange(n_mat))
+        assert nph.value == len(ref.phases) and nm.value == n_mat
+        for k in range(nph.value):
+            a, b = bytes(phases[k]), bytes(ref.phases[k])
+            if a != b:                                         # name the first field that differs
+                for fname, _ in L.Phase._fields_:
+                    x, y = np.ctypeslib.as_array(getattr(phases[k], fname)) if hasattr(getattr(phases[k], fname), '_length_') else getattr(phases[k], fname), \
+                        np.ctypeslib.as_array(getattr(ref.phases[k], fname)) if hasattr(getattr(ref.phases[k], fname), '_length_') else getattr(ref.phases[k], fname)
+                    assert np.array_equal(np.asarray(x), np.asarray(y)), (path, k, fname)
+            assert a == b
+        assert np.array_equal(ph_of, ref.phase_of_cell)
+        assert np.array_equal(O, ref.O_of_cell)
+
+
+def test_cpp_numerics_equals_python_host(tmp_path):
+    from solver_cpp_b200 import lib as L, job
+    lib = L.load()
+    p = tmp_path / 'numerics.yaml'
+    p.write_text(yaml.safe_dump({'solver': {'grid': {'N_cutback_max': 5, 'mechanical': {'N_iter_min': 4, 'N_iter_max': 40, 'eps_abs_div(P)': 1e-2,
+                                                                                         'eps_rel_div(P)': 1e-1, 'update_gamma': True},
+                                                     'FFT': {'derivative': 'FWBW_difference', 'divergence_correction': 'size'}}},
+                                 'phase': {'mechanical': {'r_cutback': 0.5, 'plastic': {'integrator_state': 'RK4', 'N_iter_Lp_max': 25}}}}))
+    for path in (None, str(p)):
+        num = L.Numerics()
+        der, div = C.c_int(), C.c_int()
+        rc = lib.dmk_numerics_from_yaml(path.encode() if path else None, C.byref(num), C.byref(der), C.byref(div))
+        assert rc == 0, lib.dmk_last_error()
+        ref, rder, rdiv, _ = job.read_numerics(path)
+        assert bytes(num) == bytes(ref) and (der.value, div.value) == (rder, rdiv)
