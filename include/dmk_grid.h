@@ -242,6 +242,12 @@ void f_discretization_setIPcoords(double* IPcoords0);
 void f_discretization_setNodeCoords(double* NodeCoords);
 void f_discretization_fetch_ip_node_coord_pointers(double** ip_coords_ptr, double** node_coords_ptr);
 void f_CLI_get_geomFilename(char* filename);
+/* geometry file readers of discretization_grid.h:20-22 (VTI.f90:146-266, 473-497): cells / size / origin of a VTK ImageData
+ * file's text, and a cell-data array as 32-bit integers PLUS ONE (material IDs become 1-based); on error cells = -1 /
+ * *dataset_size = -1 and dmk_last_error() has the message */
+void f_VTI_readCellsSizeOrigin(const char* fileContent, int string_size, int* cells, double* size, double* origin);
+void f_VTI_readDataset_int(const char* fileContent, int string_size, const char* label, int label_length, int* dataset_ptr,
+                           int* dataset_size);
 dmk_ctx* dmk_bound_context(void);       /* the context f_materialpoint_initDamask made (NULL if it failed: dmk_last_error) */
 /* material.yaml -> phase tables and, per `material:` entry, phase index and orientation matrix (row-major); numerics.yaml ->
  * dmk_numerics (a NULL / empty path gives the defaults) -- the C++ twin of solver_cpp_b200/material.py */

@@ -267,9 +267,13 @@ int dmk_fft_forward_internal(dmk_ctx* c, const double* d_real) {
 
 // ---- forward half pipelined under the per-point kernel (see ctx.h).  Only for the fused exchange over peer memory: there the
 // y pass carries the NVLink traffic of the forward transpose (1.06 GB per GPU at 512^3 on 8), which this hides behind the
-// 160 ms of the constitutive update; DMK_PIPELINE=0 switches it off.
+// 160 ms of the constitutive update.
 static bool pipe_wanted(dmk_ctx* c) {
-  static const bool env_on = [] { const char* e = getenv("DMK_PIPELINE"); return !(e && atoi(e) == 0); }();
+  // opt-in (DMK_PIPELINE=1).  Measured on 2 x B200, 256 x 256 x 512 (profiles/r02_summary.md): the exposed FFT + Gamma section
+  // drops from 4.39 to 2.55 ms, but the evaluation gets SLOWER, 164.6 against 159.7 ms: the persistent per-point kernel owns
+  // every register of every SM, so the FFT kernels only run in the tails of the z-chunks, and eight chunk tails (lanes finishing
+  // their last cells) cost more than the 1.85 ms they hide.
+  static const bool env_on = [] { const char* e = getenv("DMK_PIPELINE"); return e && atoi(e) == 1; }();
   return env_on && c->P > 1 && c->p2p && c->nz_loc >= 2 && c->ny > 1;
 }
 int dmk_pipe_begin(dmk_ctx* c, const double* d_real) {

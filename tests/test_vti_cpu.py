@@ -47,3 +47,43 @@ def test_rejects_wrong_cell_count(tmp_path):
     open(p, 'w').write(txt)
     with pytest.raises(ValueError):
         vti.read_vti(p)
+
+
+def test_cpp_reader_symbols_match_the_python_reader(golden_dir, tmp_path):
+    """f_VTI_readCellsSizeOrigin / f_VTI_readDataset_int of the C-ABI library (csrc/vti_dropin.cpp: the readers the reference's
+    DiscretizationGrid binds, discretization_grid.h:20-22) on DAMASK-written and self-written files, compressed, plain and
+    ascii: cells, size, origin and the material array PLUS ONE (VTI.f90:494) must equal what vti.py reads"""
+    import ctypes as C
+    lib = C.CDLL(os.path.join(HERE, '..', 'solver_cpp_b200', 'libdamask_grid_b200.so'))
+    lib.dmk_last_error.restype = C.c_char_p
+    rng = np.random.default_rng(1)
+    files = [os.path.join(golden_dir, 'damask_written_4grains2x4x3.vti'), os.path.join(golden_dir, '6grains6x7x8_single_phase.vti')]
+    m = rng.integers(0, 70000, size=(5, 6, 7))
+    for compress in (True, False):
+        p = str(tmp_path / ('w%d.vti' % compress))
+        vti.write_vti(p, m, (7e-5, 6e-5, 5e-5), origin=(0, 2e-6, 0), compress=compress, block=512)
+        files.append(p)
+    p = str(tmp_path / 'ascii.vti')
+    vti.write_vti(p, m, (7e-5, 6e-5, 5e-5), compress=False)
+    txt = open(p).read()
+    a, b = txt.index('format="binary"'), txt.index('</DataArray>')
+    body_start = txt.index('>', a) + 1
+    open(p, 'w').write(txt[:a] + 'format="ascii"' + txt[a + len('format="binary"'):body_start] + '\n' + ' '.join(str(v) for v in m.ravel()) + '\n' + txt[b:])
+    files.append(p)
+    for f in files:
+        ref = vti.read_vti(f)
+        content = open(f, 'rb').read()
+        cells = (C.c_int * 3)(); size = (C.c_double * 3)(); origin = (C.c_double * 3)()
+        lib.f_VTI_readCellsSizeOrigin(content, C.c_int(len(content)), cells, size, origin)
+        assert tuple(cells) == tuple(ref['cells']), lib.dmk_last_error()
+        assert np.allclose(list(size), ref['size'], rtol=1e-15) and np.allclose(list(origin), ref['origin'])
+        n = int(np.prod(ref['cells']))
+        data = np.zeros(n, dtype=np.int32)
+        nn = C.c_int(n)
+        lib.f_VTI_readDataset_int(content, C.c_int(len(content)), b'material', C.c_int(8), data.ctypes.data_as(C.c_void_p), C.byref(nn))
+        assert nn.value == n, lib.dmk_last_error()
+        assert np.array_equal(data, ref['material'].ravel() + 1)
+    bad = open(files[0], 'rb').read().replace(b'ImageData', b'PolyData')
+    cells = (C.c_int * 3)(); size = (C.c_double * 3)(); origin = (C.c_double * 3)()
+    lib.f_VTI_readCellsSizeOrigin(bad, C.c_int(len(bad)), cells, size, origin)
+    assert tuple(cells) == (-1, -1, -1) and b'VTI' in lib.dmk_last_error()
