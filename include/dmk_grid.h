@@ -204,6 +204,12 @@ int dmk_calculate_rate(dmk_ctx* ctx, int heterogeneous, const double* d_field0, 
  * MechSolverBasic::{init, forward, calculate_solution, form_residual, converged} (mech_solver_basic.cpp) with the
  * solution vector, its history (NGMRES, m = 30) and all work fields resident in HBM. */
 int dmk_mech_init(dmk_ctx* ctx, const long long* gamma_pair_cells /* NULL or 2 global cell indices */);
+/* the polarisation variant of the scheme (`solver: mechanical: spectral_polarisation`; upstream DAMASK's
+ * grid_mechanical_spectral_polarisation -- the reference tree parses its numerics only: alpha, beta, eps_abs_curl(F),
+ * eps_rel_curl(F), config.cpp:450-457, config.h:68-71).  Solution vector (F | F_tau): dmk_mech_forward /
+ * dmk_mech_calculate_solution / dmk_mech_get work as for the basic scheme; dmk_mech_form_residual takes and returns
+ * 2 x 9 doubles per cell; fields "F_tau", "F_tau_lastInc" and the scalar "err_curl" are available in addition. */
+int dmk_mech_init_polarisation(dmk_ctx* ctx, double alpha, double beta, double eps_abs_curl, double eps_rel_curl);
 /* BC values / masks / R: row-major 3x3 (index 3*i+j); mask 1 = 'x' (component not controlled) */
 int dmk_mech_forward(dmk_ctx* ctx, int cut_back, int guess, double dt, double dt_old, double t_remaining,
                      const char* deformation_type, const double* deformation_values, const int* deformation_mask,

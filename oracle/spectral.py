@@ -252,3 +252,51 @@ def update_coords(F, grid):
     Xp = np.stack([(ii + 0.5) * step[0], (jj + 0.5) * step[1], (kk + 0.5) * step[2]], axis=-1)
     x_p = np.einsum('lm,zyxm->zyxl', F_avg, Xp) + u
     return x_n, x_p
+
+
+# --------------------------------------------------------------------------------------------- polarisation scheme helpers
+# (upstream DAMASK only: the reference tree has no polarisation solver -- damask_grid.cpp:8-12 accepts `spectral_basic` alone;
+#  its numerics parser does read alpha, beta and the curl tolerances, config.cpp:450-457, config.h:68-71)
+def curl_rms(field_hat, xi1st, grid, scaled_size):
+    """utilities_curlRMS of upstream DAMASK (grid/spectral_utilities.f90): RMS of curl(F) from the transformed field
+    [kz,ky,kx,3,3], the Hermitian half counted like the divergence (interior kx twice, kx = 0 and kx = nx/2 once)."""
+    rescale = np.array(grid.size) / np.array(scaled_size)
+    x = xi1st * rescale                                           # [kz,ky,kx,3]
+    T = field_hat
+    c0 = T[..., 2] * x[..., None, 1] - T[..., 1] * x[..., None, 2]
+    c1 = T[..., 0] * x[..., None, 2] - T[..., 2] * x[..., None, 0]
+    c2 = T[..., 1] * x[..., None, 0] - T[..., 0] * x[..., None, 1]
+    mag = sum((c.real ** 2 + c.imag ** 2).sum(-1) for c in (c0, c1, c2))          # [kz,ky,kx]
+    nxr = grid.nxr
+    total = 2.0 * mag[:, :, 1:nxr - 1].sum() + mag[:, :, 0].sum() + mag[:, :, nxr - 1].sum()
+    rms = np.sqrt(total) * grid.wgt
+    if grid.cells[0] == 1:
+        rms = rms / 2.0
+    return rms, total
+
+
+_NYE = ((0, 0), (1, 1), (2, 2), (0, 1), (1, 2), (2, 0))          # math.f90 MAPNYE: 11 22 33 12 23 31
+_NRM_MANDEL = np.array([1.0, 1.0, 1.0, np.sqrt(2.0), np.sqrt(2.0), np.sqrt(2.0)])
+
+
+def sym3333to66(A):
+    """math_sym3333to66 (weighted): picks the Nye components, no symmetrisation"""
+    idx = np.array(_NYE)
+    M = A[..., idx[:, 0][:, None], idx[:, 1][:, None], idx[:, 0][None, :], idx[:, 1][None, :]]
+    return M * (_NRM_MANDEL[:, None] * _NRM_MANDEL[None, :])
+
+
+def from66toSym3333(M):
+    """math_66toSym3333 (weighted): fills all four index permutations of every Nye pair"""
+    W = M / (_NRM_MANDEL[:, None] * _NRM_MANDEL[None, :])
+    out = np.zeros(M.shape[:-2] + (3, 3, 3, 3))
+    for a, (i, j) in enumerate(_NYE):
+        for b, (k, l) in enumerate(_NYE):
+            v = W[..., a, b]
+            out[..., i, j, k, l] = v; out[..., j, i, k, l] = v; out[..., i, j, l, k] = v; out[..., j, i, l, k] = v
+    return out
+
+
+def invsym3333(A):
+    """math_invSym3333: inverse of a 3x3x3x3 tensor through its weighted 6x6 Nye/Mandel form"""
+    return from66toSym3333(np.linalg.inv(sym3333to66(A)))

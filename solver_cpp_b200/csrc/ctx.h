@@ -74,6 +74,7 @@ int dmk_fft_backward_internal(dmk_ctx* c, double* d_real, double scale);
 int dmk_pipe_begin(dmk_ctx* c, const double* d_real);
 int dmk_pipe_chunk(dmk_ctx* c, int k, int chunks, cudaStream_t chunk_stream);
 int dmk_pipe_end(dmk_ctx* c, bool* done);
+int dmk_spectrum_rms(dmk_ctx* c, const double* d_real, int mode /*0 divergence, 1 curl*/, double* d_accum);   // raw sum, += into *d_accum
 int dmk_gamma_internal(dmk_ctx* c);     // fused z pass on c->bufA using c->d_dc, accumulating into c->d_div
 double dmk_finish_div(dmk_ctx* c, double raw_sum);
 const unsigned* dmk_points_given_up_counter(dmk_ctx* c);

@@ -21,11 +21,18 @@
 #include "ctx.h"
 #include "reduce.cuh"
 #include "constitutive.cuh"
+#include "polarisation.cuh"
 
 #define NGMRES_M 30
 
 struct DmkMech {
-  long long n9;
+  long long n9;                                      // doubles in one tensor field of the slab
+  long long nvec;                                    // doubles in the solution vector: n9 (basic), 2 n9 = (F, F_tau) (polarisation)
+  int scheme;                                        // 0 spectral_basic, 1 spectral_polarisation
+  // polarisation only: work field, materialised tangent, numerics, scaling tensors (row-major)
+  double *W, *dPdF; int* d_singular;
+  double alpha, beta, eps_abs_curl, eps_rel_curl, err_curl;
+  double C_scale[81], S_scale[81], F_av[9];
   double *F, *F_lastInc, *F_dot, *R_field;          // device fields (record layout)
   double *XM, *FM, *XA, *FA, *Xcur, *Fcur;           // NGMRES work vectors
   std::vector<double*> Xdot, Fdot;                   // NGMRES history, allocated on demand
@@ -194,14 +201,14 @@ static int reduce_to_host(dmk_ctx* c, double* d_vals, int n, double* h_out) {
 static int dots(dmk_ctx* c, const double* a, const std::vector<const double*>& bs, double* h_out) {
   if (bs.empty()) return DMK_OK;
   double* d_out = c->d_scratch + DMK_SCRATCH_TMP + 300;
-  int rc = dmk_multi_dot(c, a, bs.data(), (int)bs.size(), c->mech->n9, d_out);
+  int rc = dmk_multi_dot(c, a, bs.data(), (int)bs.size(), c->mech->nvec, d_out);
   if (rc) return rc;
   return reduce_to_host(c, d_out, (int)bs.size(), h_out);
 }
 static int diffnorms2(dmk_ctx* c, const double* x, const std::vector<const double*>& vs, double* h_out) {
   if (vs.empty()) return DMK_OK;
   DmkVecs v; for (int k = 0; k < 32; k++) { v.p[k] = k < (int)vs.size() ? vs[k] : nullptr; v.a[k] = 0; }
-  const long long n = c->mech->n9;
+  const long long n = c->mech->nvec;
   int blocks = (int)std::max(1LL, std::min((n + 255) / 256, (long long)DMK_REDUCE_BLOCKS));
   double* partial = c->d_scratch + DMK_SCRATCH_PARTIAL;
   double* d_out = c->d_scratch + DMK_SCRATCH_TMP + 300;
@@ -213,7 +220,7 @@ static int diffnorms2(dmk_ctx* c, const double* x, const std::vector<const doubl
 }
 static int lincomb(dmk_ctx* c, double* out, const double* x, double c0, const std::vector<const double*>& vs, const double* a) {
   DmkVecs v; for (int k = 0; k < 32; k++) { v.p[k] = k < (int)vs.size() ? vs[k] : nullptr; v.a[k] = k < (int)vs.size() ? a[k] : 0.0; }
-  dmk_lincomb_kernel<<<148 * 8, 256, 0, c->stream>>>(out, x, c0, v, (int)vs.size(), c->mech->n9);
+  dmk_lincomb_kernel<<<148 * 8, 256, 0, c->stream>>>(out, x, c0, v, (int)vs.size(), c->mech->nvec);
   c->launches++;
   DMK_CUDA_CHECK(cudaGetLastError());
   return DMK_OK;
@@ -236,6 +243,7 @@ void dmk_mech_teardown(dmk_ctx* c) {
   DmkMech* m = c->mech;
   if (!m) return;
   cudaFree(m->F); cudaFree(m->F_lastInc); cudaFree(m->F_dot); cudaFree(m->R_field);
+  if (m->W) cudaFree(m->W); if (m->dPdF) cudaFree(m->dPdF); if (m->d_singular) cudaFree(m->d_singular);
   cudaFree(m->XM); cudaFree(m->FM); cudaFree(m->XA); cudaFree(m->FA); cudaFree(m->Xcur); cudaFree(m->Fcur);
   for (double* p : m->Xdot) cudaFree(p);
   for (double* p : m->Fdot) cudaFree(p);
@@ -308,17 +316,93 @@ static int evaluate(dmk_ctx* c, const double* d_F, double* d_r) {
   return DMK_OK;
 }
 
+// ---- polarisation scheme: one evaluation of (r_F, r_F_tau) at (F, F_tau); algorithm and provenance: oracle/polarisation.py,
+// polarisation.cuh (upstream DAMASK's grid_mechanical_spectral_polarisation; the reference tree holds its numerics keys only)
+static int evaluate_polarisation(dmk_ctx* c, const double* d_X, double* d_R) {
+  DmkMech* m = c->mech;
+  const long long n9 = m->n9, n = c->n_local;
+  const double *F = d_X, *Ft = d_X + n9;
+  double *rF = d_R, *rFt = d_R + n9;
+  int rc;
+  double s9[9];
+  // F_av
+  if ((rc = dmk_sum_records(c, F, n, c->d_scratch + DMK_SCRATCH_SUM9))) return rc;
+  if ((rc = reduce_to_host(c, c->d_scratch + DMK_SCRATCH_SUM9, 9, s9))) return rc;
+  for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) m->F_av[3 * i + j] = s9[i + 3 * j] * c->wgt;
+  // T = beta C:(F - I) - alpha F.(C:(F_tau - F - I));  T <- Gamma * T with the DC term rot(beta F_aim)
+  DmkPolParams pp;
+  for (int k = 0; k < 81; k++) pp.C[k] = m->C_scale[k];
+  pp.alpha = m->alpha; pp.beta = m->beta;
+  if ((rc = dmk_pol_pre(F, Ft, m->W, n, pp, c->stream))) return rc;
+  {
+    double aim[9], rot[9];
+    for (int a = 0; a < 9; a++) aim[a] = m->beta * m->F_aim[a];
+    rotate2(m->R, aim, true, rot);
+    double* h = c->h_pinned + 2560;
+    for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) h[i + 3 * j] = rot[3 * i + j];
+    DMK_CUDA_CHECK(cudaMemcpyAsync(c->d_dc, h, 9 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    DMK_CUDA_CHECK(cudaMemsetAsync(c->d_div, 0, sizeof(double), c->stream));
+  }
+  if ((rc = dmk_fft_forward_internal(c, m->W))) return rc;
+  if ((rc = dmk_gamma_internal(c))) return rc;
+  if ((rc = dmk_fft_backward_internal(c, m->W, 1.0))) return rc;
+  // r_F_tau = beta F - T;  constitutive response at F - r_F_tau / beta (P lands in r_F)
+  if ((rc = dmk_pol_rtau(F, m->W, rFt, m->W, n, m->beta, c->stream))) return rc;
+  c->launches += 2;
+  if ((rc = dmk_points_constitutive(c, m->W, rF, m->dt))) return rc;
+  m->tangent_stale = true; m->tangent_dt = m->dt;
+  if ((rc = dmk_sum_records(c, rF, n, c->d_scratch + DMK_SCRATCH_SUM9))) return rc;
+  if ((rc = reduce_to_host(c, c->d_scratch + DMK_SCRATCH_SUM9, 9, s9))) return rc;
+  {
+    double Pm[9];
+    for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) Pm[3 * i + j] = s9[i + 3 * j] * c->wgt;
+    rotate2(m->R, Pm, false, m->P_av);
+  }
+  if ((rc = dmk_points_tangent(c, m->dt, c->d_scratch + DMK_SCRATCH_TMP, m->dPdF))) return rc;
+  // stress boundary condition: F_aim -= S:(P_av - P_aim); err_BC = max |mask ? C:(F_aim - rot(F_av)) : P_av - P_aim|
+  {
+    double dP[9], Fr[9], dFa[9];
+    for (int a = 0; a < 9; a++) dP[a] = m->P_av[a] - m->P_aim[a];
+    for (int a = 0; a < 9; a++) { double s = 0.0; for (int b = 0; b < 9; b++) s += m->S[9 * a + b] * dP[b]; m->F_aim[a] -= s; }
+    rotate2(m->R, m->F_av, false, Fr);
+    for (int a = 0; a < 9; a++) dFa[a] = m->F_aim[a] - Fr[a];
+    double err = 0.0;
+    for (int a = 0; a < 9; a++) {
+      double v = dP[a];
+      if (m->stress_mask[a]) { v = 0.0; for (int b = 0; b < 9; b++) v += m->C_scale[9 * a + b] * dFa[b]; }
+      err = std::max(err, fabs(v));
+    }
+    m->err_BC = err;
+  }
+  // err_div of the stress field (still in r_F), then r_F = (dPdF + C)^-1:(P - F.(C:(F_tau - F - I))) + r_F_tau, then err_curl of F
+  double* d_two = c->d_scratch + DMK_SCRATCH_TMP + 320;
+  DMK_CUDA_CHECK(cudaMemsetAsync(d_two, 0, 2 * sizeof(double), c->stream));
+  if ((rc = dmk_spectrum_rms(c, rF, 0, d_two))) return rc;
+  if ((rc = dmk_pol_rF(F, Ft, m->dPdF, rFt, rF, n, pp, m->d_singular, c->stream))) return rc;
+  c->launches++;
+  if ((rc = dmk_spectrum_rms(c, F, 1, d_two + 1))) return rc;
+  double two[2];
+  if ((rc = reduce_to_host(c, d_two, 2, two))) return rc;
+  m->div_raw = two[0];
+  m->err_div = dmk_finish_div(c, two[0]);
+  m->err_curl = dmk_finish_div(c, two[1]);
+  int sing = 0;
+  DMK_CUDA_CHECK(cudaMemcpy(&sing, m->d_singular, sizeof(int), cudaMemcpyDeviceToHost));
+  if (sing) { dmk_set_error("polarisation residual: dPdF + C_scale is singular in a cell"); return DMK_ERR_STATE; }
+  return DMK_OK;
+}
+
 static int form_residual(dmk_ctx* c, const double* d_F, double* d_r, int nfuncs, int petsc_iter) {
   DmkMech* m = c->mech;
   if (nfuncs == 0 && petsc_iter == 0) m->total_iter = -1;
   if (m->total_iter <= petsc_iter) m->total_iter += 1;
-  int rc = evaluate(c, d_F, d_r);
+  int rc = m->scheme == 1 ? evaluate_polarisation(c, d_F, d_r) : evaluate(c, d_F, d_r);
   if (rc) return rc;
   double rec[12];
   for (int a = 0; a < 9; a++) rec[a] = m->P_av[a];
   rec[9] = m->err_div; rec[10] = m->err_BC; rec[11] = (double)m->total_iter;
   m->log.insert(m->log.end(), rec, rec + 12);
-  if (m->capture) {
+  if (m->capture && m->scheme == 0) {
     const size_t o = m->capF.size();
     m->capF.resize(o + m->n9); m->capR.resize(o + m->n9);
     DMK_CUDA_CHECK(cudaMemcpy(m->capF.data() + o, d_F, m->n9 * sizeof(double), cudaMemcpyDeviceToHost));
@@ -337,6 +421,20 @@ static int converged(dmk_ctx* c, int* reason) {
   const double BCTol = std::max(maxP * n.eps_rel_P, n.eps_abs_P);
   int ill = 0;
   int rc = dmk_terminally_ill(c, &ill, 0); if (rc) return rc;
+  if (m->scheme == 1) {
+    // upstream's polarisation test: three criteria, tolerances from max |P_av| and max |F_aim - I|
+    double aP = 0.0, aF = 0.0;
+    for (int a = 0; a < 9; a++) { aP = std::max(aP, fabs(m->P_av[a])); aF = std::max(aF, fabs(m->F_aim[a] - ((a % 4 == 0) ? 1.0 : 0.0))); }
+    const double dTol = std::max(aP * n.eps_rel_div, n.eps_abs_div), bTol = std::max(aP * n.eps_rel_P, n.eps_abs_P);
+    const double cTol = std::max(aF * m->eps_rel_curl, m->eps_abs_curl);
+    const bool ok = std::max(std::max(m->err_div / dTol, m->err_curl / cTol), m->err_BC / bTol) < 1.0;
+    if ((m->total_iter >= n.itmin && ok) || ill) *reason = 6;
+    else if (m->total_iter >= n.itmax) *reason = -5;
+    else *reason = 0;
+    const double rep[6] = {(double)m->total_iter, m->err_div, dTol, m->err_BC, bTol, (double)*reason};
+    m->reports.insert(m->reports.end(), rep, rep + 6);
+    return DMK_OK;
+  }
   if ((m->total_iter >= n.itmin && std::max(m->err_div / divTol, m->err_BC / BCTol) < 1.0) || ill) *reason = 6;   // SNES_BREAKOUT_INNER_ITER
   else if (m->total_iter >= n.itmax) *reason = -5;                                                                  // SNES_DIVERGED_MAX_IT
   else *reason = 0;
@@ -381,12 +479,12 @@ static void sym_lstsq(std::vector<double> H, int n, const double* b, double* x) 
 
 // ------------------------------------------------------------------------------------------------ NGMRES
 static int hist_vec(dmk_ctx* c, std::vector<double*>& h, int i, double** out) {
-  while ((int)h.size() <= i) { double* p = nullptr; DMK_CUDA_CHECK(cudaMalloc((void**)&p, c->mech->n9 * sizeof(double))); h.push_back(p); }
+  while ((int)h.size() <= i) { double* p = nullptr; DMK_CUDA_CHECK(cudaMalloc((void**)&p, c->mech->nvec * sizeof(double))); h.push_back(p); }
   *out = h[i];
   return DMK_OK;
 }
 static int copy_field(dmk_ctx* c, double* dst, const double* src) {
-  DMK_CUDA_CHECK(cudaMemcpyAsync(dst, src, c->mech->n9 * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+  DMK_CUDA_CHECK(cudaMemcpyAsync(dst, src, c->mech->nvec * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
   return DMK_OK;
 }
 
@@ -477,7 +575,7 @@ static int ngmres_solve(dmk_ctx* c) {
 // ------------------------------------------------------------------------------------------------ C ABI
 extern "C" int dmk_update_gamma(dmk_ctx* c, const double* C);
 
-extern "C" int dmk_mech_init(dmk_ctx* c, const long long* gamma_pair_cells) {
+static int mech_init(dmk_ctx* c, const long long* gamma_pair_cells, int scheme) {
   if (!c || !c->pts) { dmk_set_error("material not initialised (dmk_material_init)"); return DMK_ERR_STATE; }
   if (c->P > 1 && (!c->has_comm || !c->comm.allreduce_sum || !c->comm.allreduce_max || !c->comm.alltoall)) {
     dmk_set_error("%d ranks but no collective callbacks: call dmk_set_comm before dmk_mech_init", c->P); return DMK_ERR_STATE;
@@ -486,13 +584,16 @@ extern "C" int dmk_mech_init(dmk_ctx* c, const long long* gamma_pair_cells) {
   DmkMech* m = new DmkMech();
   c->mech = m;
   m->n9 = c->n_local * 9;
+  m->scheme = scheme;
+  m->nvec = (scheme == 1 ? 2 : 1) * m->n9;               // polarisation: every solution-sized field is (F | F_tau)
+  m->W = m->dPdF = nullptr; m->d_singular = nullptr;
   m->d_blk = c->d_scratch + DMK_SCRATCH_MECH;
   double** fields[] = {&m->F, &m->F_lastInc, &m->F_dot, &m->R_field, &m->XM, &m->FM, &m->XA, &m->FA, &m->Xcur, &m->Fcur};
-  for (double** f : fields) { DMK_CUDA_CHECK(cudaMalloc((void**)f, m->n9 * sizeof(double))); }
+  for (double** f : fields) { DMK_CUDA_CHECK(cudaMalloc((void**)f, m->nvec * sizeof(double))); }
   dmk_fill_identity_kernel<<<148 * 4, 256, 0, c->stream>>>(m->F, c->n_local);
   dmk_fill_identity_kernel<<<148 * 4, 256, 0, c->stream>>>(m->F_lastInc, c->n_local);
   c->launches += 2;
-  DMK_CUDA_CHECK(cudaMemsetAsync(m->F_dot, 0, m->n9 * sizeof(double), c->stream));
+  DMK_CUDA_CHECK(cudaMemsetAsync(m->F_dot, 0, m->nvec * sizeof(double), c->stream));
   const double I3[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
   memcpy(m->F_aim, I3, sizeof I3); memcpy(m->F_aim_lastInc, I3, sizeof I3); memcpy(m->R, I3, sizeof I3);
   memset(m->F_aim_dot, 0, sizeof m->F_aim_dot); memset(m->P_av, 0, sizeof m->P_av); memset(m->P_aim, 0, sizeof m->P_aim);
@@ -529,6 +630,34 @@ extern "C" int dmk_mech_init(dmk_ctx* c, const long long* gamma_pair_cells) {
   return dmk_update_gamma(c, Cf);
 }
 
+extern "C" int dmk_mech_init(dmk_ctx* c, const long long* gamma_pair_cells) { return mech_init(c, gamma_pair_cells, 0); }
+
+// the polarisation variant (solver: mechanical: spectral_polarisation of the load file): alpha, beta and the curl tolerances
+// are the numerics keys the reference parses (config.cpp:450-457; defaults 1, 1, 1e-10, 5e-4); F_tau = 2 F initially,
+// C_scale = C_minMaxAvg, S_scale = its inverse
+static __global__ void dmk_scale_kernel(double* __restrict__ out, const double* __restrict__ in, double s, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) out[i] = s * in[i];
+}
+extern "C" int dmk_mech_init_polarisation(dmk_ctx* c, double alpha, double beta, double eps_abs_curl, double eps_rel_curl) {
+  if (!(beta != 0.0)) { dmk_set_error("polarisation: beta must not be 0"); return DMK_ERR_ARG; }
+  int rc = mech_init(c, nullptr, 1);
+  if (rc) return rc;
+  DmkMech* m = c->mech;
+  m->alpha = alpha; m->beta = beta; m->eps_abs_curl = eps_abs_curl; m->eps_rel_curl = eps_rel_curl; m->err_curl = 0.0;
+  DMK_CUDA_CHECK(cudaMalloc((void**)&m->W, m->n9 * sizeof(double)));
+  DMK_CUDA_CHECK(cudaMalloc((void**)&m->dPdF, (size_t)c->n_local * 81 * sizeof(double)));
+  DMK_CUDA_CHECK(cudaMalloc((void**)&m->d_singular, sizeof(int)));
+  DMK_CUDA_CHECK(cudaMemsetAsync(m->d_singular, 0, sizeof(int), c->stream));
+  dmk_scale_kernel<<<148 * 8, 256, 0, c->stream>>>(m->F + m->n9, m->F, 2.0, m->n9);
+  dmk_scale_kernel<<<148 * 8, 256, 0, c->stream>>>(m->F_lastInc + m->n9, m->F_lastInc, 2.0, m->n9);
+  c->launches += 2;
+  DMK_CUDA_CHECK(cudaGetLastError());
+  memcpy(m->C_scale, m->C_minMaxAvg, sizeof m->C_scale);
+  if (!dmk_invsym3333(m->C_minMaxAvg, m->S_scale)) { dmk_set_error("polarisation: C_minMaxAvg is singular"); return DMK_ERR_STATE; }
+  memset(m->F_av, 0, sizeof m->F_av); m->F_av[0] = m->F_av[4] = m->F_av[8] = 1.0;
+  return DMK_OK;
+}
+
 // deformation_values / masks / R: row-major 3x3; mask 1 = 'x'
 extern "C" int dmk_mech_forward(dmk_ctx* c, int cut_back, int guess, double dt, double dt_old, double t_remaining,
                                 const char* deformation_type, const double* deformation_values, const int* deformation_mask,
@@ -553,8 +682,9 @@ extern "C" int dmk_mech_forward(dmk_ctx* c, int cut_back, int guess, double dt, 
     rotate2(R, m->F_aim_dot, true, rot);
     for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) rec[i + 3 * j] = rot[3 * i + j];
     if ((rc = dmk_calculate_rate(c, guess, m->F_lastInc, m->F, dt_old, rec, m->F_dot))) return rc;
+    if (m->scheme == 1) { if ((rc = dmk_calculate_rate(c, guess, m->F_lastInc + m->n9, m->F + m->n9, dt_old, rec, m->F_dot + m->n9))) return rc; }
     DMK_CUDA_CHECK(cudaStreamSynchronize(c->stream));
-    if ((rc = copy_field(c, m->F_lastInc, m->F))) return rc;
+    if ((rc = copy_field(c, m->F_lastInc, m->F))) return rc;                       // (F | F_tau) in one copy
   }
   for (int a = 0; a < 9; a++) m->F_aim[a] = m->F_aim_lastInc[a] + m->F_aim_dot[a] * dt;
   if (stype == "P") { for (int a = 0; a < 9; a++) if (!stress_mask[a]) m->P_aim[a] += (stress_values[a] - m->P_aim[a]) / t_remaining * dt; }
@@ -564,6 +694,10 @@ extern "C" int dmk_mech_forward(dmk_ctx* c, int cut_back, int guess, double dt, 
   rotate2(R, m->F_aim, true, rot);
   for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) rec[i + 3 * j] = rot[3 * i + j];
   if ((rc = dmk_forward_field(c, dt, m->F_lastInc, m->F_dot, rec, m->F))) return rc;
+  if (m->scheme == 1) {
+    if (guess) { if ((rc = dmk_forward_field(c, dt, m->F_lastInc + m->n9, m->F_dot + m->n9, nullptr, m->F + m->n9))) return rc; }
+    else { if ((rc = dmk_pol_forward_noguess(m->F, m->F + m->n9, c->n_local, m->C_scale, m->S_scale, c->stream))) return rc; c->launches++; }
+  }
   DMK_CUDA_CHECK(cudaStreamSynchronize(c->stream));
   for (int a = 0; a < 9; a++) { m->stress_mask[a] = stress_mask[a]; m->R[a] = R[a]; }
   m->dt = dt;
@@ -575,7 +709,13 @@ extern "C" int dmk_mech_calculate_solution(dmk_ctx* c, dmk_solution_state* out) 
   DmkMech* m = c->mech;
   if ((rc = ensure_tangent(c))) return rc;
   if ((rc = masked_compliance_rm(m->C_volAvg, m->R, m->stress_mask, m->S))) return rc;
-  if (c->num.update_gamma) { double Cf[81]; c2f3333(m->C_minMaxAvg, Cf); if ((rc = dmk_update_gamma(c, Cf))) return rc; }
+  if (c->num.update_gamma) {
+    double Cf[81]; c2f3333(m->C_minMaxAvg, Cf); if ((rc = dmk_update_gamma(c, Cf))) return rc;
+    if (m->scheme == 1) {
+      memcpy(m->C_scale, m->C_minMaxAvg, sizeof m->C_scale);
+      if (!dmk_invsym3333(m->C_minMaxAvg, m->S_scale)) { dmk_set_error("polarisation: C_minMaxAvg is singular"); return DMK_ERR_STATE; }
+    }
+  }
   if ((rc = upload_block(c))) return rc;
   if ((rc = ngmres_solve(c))) return rc;
   int ill = 0;
@@ -591,7 +731,13 @@ extern "C" int dmk_mech_prepare(dmk_ctx* c) {
   DmkMech* m = c->mech;
   if ((rc = ensure_tangent(c))) return rc;
   if ((rc = masked_compliance_rm(m->C_volAvg, m->R, m->stress_mask, m->S))) return rc;
-  if (c->num.update_gamma) { double Cf[81]; c2f3333(m->C_minMaxAvg, Cf); if ((rc = dmk_update_gamma(c, Cf))) return rc; }
+  if (c->num.update_gamma) {
+    double Cf[81]; c2f3333(m->C_minMaxAvg, Cf); if ((rc = dmk_update_gamma(c, Cf))) return rc;
+    if (m->scheme == 1) {
+      memcpy(m->C_scale, m->C_minMaxAvg, sizeof m->C_scale);
+      if (!dmk_invsym3333(m->C_minMaxAvg, m->S_scale)) { dmk_set_error("polarisation: C_minMaxAvg is singular"); return DMK_ERR_STATE; }
+    }
+  }
   return DMK_OK;
 }
 // 3x3 host values in Fortran order: "F_aim", "F_aim_lastInc", "P_aim"
@@ -617,6 +763,15 @@ extern "C" int dmk_mech_set_field_device(dmk_ctx* c, const char* what, const dou
 
 extern "C" int dmk_mech_form_residual(dmk_ctx* c, const double* d_F, double* d_r) {
   int rc = need_mech(c); if (rc) return rc;
+  if (c->mech->scheme == 1) {                               // (F | F_tau) in, (r_F | r_F_tau) out: 2 x 9 doubles per cell
+    if ((rc = evaluate_polarisation(c, d_F, d_r))) return rc;
+    DmkMech* mp = c->mech;
+    double rec[12];
+    for (int a = 0; a < 9; a++) rec[a] = mp->P_av[a];
+    rec[9] = mp->err_div; rec[10] = mp->err_BC; rec[11] = (double)mp->total_iter;
+    mp->log.insert(mp->log.end(), rec, rec + 12);
+    return DMK_OK;
+  }
   if ((rc = upload_block(c))) return rc;
   if ((rc = evaluate(c, d_F, d_r))) return rc;
   DmkMech* m = c->mech;
@@ -630,6 +785,7 @@ extern "C" int dmk_mech_form_residual(dmk_ctx* c, const double* d_F, double* d_r
 extern "C" int dmk_mech_form_residual_host(dmk_ctx* c, const double* F, double* r) {
   int rc = need_mech(c); if (rc) return rc;
   DmkMech* m = c->mech;
+  if (m->scheme == 1) { dmk_set_error("dmk_mech_form_residual_host: basic scheme only (the polarisation residual is evaluated on device vectors)"); return DMK_ERR_UNSUPPORTED; }
   // F goes up in z-chunks on a second stream; the per-point kernel of chunk k starts when chunk k has arrived, so the
   // host-to-device copy (72 B/cell over PCIe) hides behind the constitutive update of the chunks before it
   static const int chunks_setting = [] { const char* e = getenv("DMK_STAGE_CHUNKS"); int v = e ? atoi(e) : 8; return v < 1 ? 1 : (v > 8 ? 8 : v); }();
@@ -681,6 +837,8 @@ extern "C" int dmk_mech_get(dmk_ctx* c, const char* what, double* out, size_t n)
   if (w == "err_div") { out[0] = m->err_div; return DMK_OK; }
   if (w == "err_BC") { out[0] = m->err_BC; return DMK_OK; }
   if (w == "div_raw") { out[0] = m->div_raw; return DMK_OK; }
+  if (w == "err_curl") { out[0] = m->scheme == 1 ? m->err_curl : 0.0; return DMK_OK; }
+  if (w == "scheme") { out[0] = m->scheme; return DMK_OK; }
   if (w == "total_iter") { out[0] = m->total_iter; return DMK_OK; }
   if (w == "snes_its") { out[0] = m->snes_its; return DMK_OK; }
   if (w == "snes_reason") { out[0] = m->snes_reason; return DMK_OK; }
@@ -702,6 +860,10 @@ static double* field_by_name(DmkMech* m, const std::string& w) {
   if (w == "F_lastInc") return m->F_lastInc;
   if (w == "F_dot") return m->F_dot;
   if (w == "r") return m->Fcur;
+  if (m->scheme == 1) {
+    if (w == "F_tau") return m->F + m->n9;
+    if (w == "F_tau_lastInc") return m->F_lastInc + m->n9;
+  }
   return nullptr;
 }
 extern "C" int dmk_mech_get_field(dmk_ctx* c, const char* what, double* host_out) {

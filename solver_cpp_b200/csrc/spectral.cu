@@ -9,6 +9,7 @@
 #include <algorithm>
 #include "ctx.h"
 #include "reduce.cuh"
+#include "gamma_point.cuh"
 
 static thread_local char g_err[1024] = "";
 void dmk_set_error(const char* fmt, ...) {
@@ -385,6 +386,67 @@ static int zpass_plain(dmk_ctx* c, bool inverse) {
   int rc = dmk_launch_line_pass(inverse, zbuf(c), zbuf(c), c->plz, map_z(c), map_z(c), c->nxr, c->ny_loc, c->kt_z, c->stream, remote ? &ps : nullptr);
   if (!rc) c->launches++;
   return rc;
+}
+
+// ---- RMS of the divergence (mode 0) or of the curl (mode 1) of a real tensor field from its full forward transform, as
+// utilities_divergenceRMS / utilities_curlRMS of upstream DAMASK do it for the polarisation scheme (the basic scheme gets its
+// divergence from the fused z pass instead).  Adds the raw sum over this rank's k-points to *d_accum, per-block partial sums
+// added up in a fixed order; the caller all-reduces and finishes with dmk_finish_div.
+template <int MODE>
+__global__ void __launch_bounds__(256) dmk_spectrum_rms_kernel(const double2* __restrict__ hat, DmkGammaParams gp, int nxr, int ny_loc, int nz,
+                                                               double* __restrict__ partial) {
+  __shared__ double sh[8];
+  const long long n = (long long)nz * ny_loc * nxr;
+  const double resc[3] = {gp.rescale[0], gp.rescale[1], gp.rescale[2]};
+  double acc = 0.0;
+  for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += (long long)gridDim.x * blockDim.x) {
+    const int kx = (int)(r % nxr), kyl = (int)((r / nxr) % ny_loc), kz = (int)(r / ((long long)nxr * ny_loc));
+    double2 xi[3];
+    load_xi(gp, kx, kyl + gp.ky_offset, kz, xi);
+    const double2* t = hat + r * DMK_NC;                       // record: T(l,m) at t[l + 3 m]
+    double mag = 0.0;
+    if (MODE == 0) {
+      double2 v[3];
+#pragma unroll
+      for (int m = 0; m < 3; m++) v[m] = make_double2(-xi[m].x * resc[m], xi[m].y * resc[m]);      // conj(-xi_m) resc_m
+#pragma unroll
+      for (int l = 0; l < 3; l++) {
+        double2 p = make_double2(0.0, 0.0);
+#pragma unroll
+        for (int m = 0; m < 3; m++) { const double2 a = __ldg(&t[l + 3 * m]); p.x += a.x * v[m].x - a.y * v[m].y; p.y += a.x * v[m].y + a.y * v[m].x; }
+        mag += p.x * p.x + p.y * p.y;
+      }
+    } else {
+      double2 x[3];
+#pragma unroll
+      for (int m = 0; m < 3; m++) x[m] = make_double2(xi[m].x * resc[m], xi[m].y * resc[m]);
+#pragma unroll
+      for (int l = 0; l < 3; l++) {
+        const double2 a0 = __ldg(&t[l]), a1 = __ldg(&t[l + 3]), a2 = __ldg(&t[l + 6]);
+        const double2 c0 = csub(cmul(a2, x[1]), cmul(a1, x[2])), c1 = csub(cmul(a0, x[2]), cmul(a2, x[0])), c2 = csub(cmul(a1, x[0]), cmul(a0, x[1]));
+        mag += c0.x * c0.x + c0.y * c0.y + c1.x * c1.x + c1.y * c1.y + c2.x * c2.x + c2.y * c2.y;
+      }
+    }
+    const double w = (kx == 0 || kx == nxr - 1) ? 1.0 : 2.0;
+    acc += w * mag;
+  }
+  for (int off = 16; off > 0; off >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, off);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) { double s = 0.0; for (int w = 0; w < 8; w++) s += sh[w]; partial[blockIdx.x] = s; }
+}
+static int zpass_plain(dmk_ctx* c, bool inverse);
+int dmk_spectrum_rms(dmk_ctx* c, const double* d_real, int mode, double* d_accum) {
+  int rc;
+  if ((rc = dmk_fft_forward_internal(c, d_real))) return rc;
+  if ((rc = zpass_plain(c, false))) return rc;
+  DmkGammaParams gp; fill_gamma_params(c, &gp);
+  const int blocks = 1024;
+  if (mode == 0) dmk_spectrum_rms_kernel<0><<<blocks, 256, 0, c->stream>>>(zbuf(c), gp, c->nxr, c->ny_loc, c->nz, c->d_div_partial);
+  else dmk_spectrum_rms_kernel<1><<<blocks, 256, 0, c->stream>>>(zbuf(c), gp, c->nxr, c->ny_loc, c->nz, c->d_div_partial);
+  c->launches++;
+  DMK_CUDA_CHECK(cudaGetLastError());
+  return dmk_sum_div_partials(c->d_div_partial, blocks, d_accum, c->stream);
 }
 
 extern "C" int dmk_fft_forward(dmk_ctx* c, const double* d_real, double* d_fourier) {

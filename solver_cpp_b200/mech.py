@@ -186,6 +186,33 @@ class MechSolverBasic:
         return out
 
 
+class MechSolverPolarisation(MechSolverBasic):
+    """grid_mechanical_spectral_polarisation of upstream DAMASK on the device (the reference tree holds only its numerics keys,
+    config.cpp:450-457): solution vector (F | F_tau), same call surface as MechSolverBasic"""
+
+    def __init__(self, grid, alpha=1.0, beta=1.0, eps_abs_curl=1.0e-10, eps_rel_curl=5.0e-4):
+        super().__init__(grid)
+        self.pol = (alpha, beta, eps_abs_curl, eps_rel_curl)
+
+    def init(self, gamma_pair_cells=None):
+        if gamma_pair_cells is not None:
+            raise L.DmkError('the polarisation solver has no injected reference-stiffness pair')
+        L.check(self.lib.dmk_mech_init_polarisation(self.ctx, *[C.c_double(v) for v in self.pol]))
+
+    def new_vector(self):
+        import torch
+        return torch.empty((2,) + tuple(self.g.field_shape), dtype=torch.float64, device=self.g.device)
+
+    def form_residual(self, X, r=None):
+        """X = (F | F_tau) as one device tensor [2, nz_local, ny, nx, 9] -> (r_F | r_F_tau)"""
+        r = self.new_vector() if r is None else r
+        L.check(self.lib.dmk_mech_form_residual(self.ctx, _p(X), _p(r)))
+        return r
+
+    def form_residual_host(self, F_host, r_host):
+        raise L.DmkError('form_residual_host: basic scheme only')
+
+
 def loop_over_loadcase(solver: MechSolverBasic, steps, max_cut_back=3, callback=None, max_increments=None):
     """DamaskGrid::loop_over_loadcase (damask_grid.cpp:82-196), upstream cut-back bookkeeping (SURVEY 0.1 D10).
     Returns one record per converged increment."""
@@ -238,8 +265,9 @@ def loop_over_loadcase(solver: MechSolverBasic, steps, max_cut_back=3, callback=
 
 
 def make_solver(cells, size, material, material_at, numerics=None, derivative=0, divergence_correction=2, world_size=1, rank=0,
-                comm=None):
-    """GridContext + material + MechSolverBasic for one z-slab (material_at: the slab's cells, x fastest)"""
+                comm=None, scheme='spectral_basic', **scheme_numerics):
+    """GridContext + material + MechSolverBasic (or MechSolverPolarisation: scheme = 'spectral_polarisation', with alpha, beta,
+    eps_abs_curl, eps_rel_curl) for one z-slab (material_at: the slab's cells, x fastest)"""
     g = GridContext(cells, size, derivative=derivative, divergence_correction=divergence_correction, world_size=world_size, rank=rank)
     if comm is not None:
         g.set_comm(comm)
@@ -247,4 +275,8 @@ def make_solver(cells, size, material, material_at, numerics=None, derivative=0,
         if world_size > 1 and parallel.fused_exchange_wanted():
             g.enable_fused_exchange(getattr(comm, 'group', None))
     g.material_init(M.Material(material, material_at), numerics)
+    if scheme == 'spectral_polarisation':
+        return MechSolverPolarisation(g, **scheme_numerics)
+    if scheme != 'spectral_basic':
+        raise L.DmkError('unknown mechanical solver %r (spectral_basic, spectral_polarisation)' % scheme)
     return MechSolverBasic(g)

@@ -314,3 +314,81 @@ def test_fortran_named_dropin_symbols():
     gb.materialpoint_forward()
     assert np.array_equal(ga.get_state('Fp0', 9), gb.get_state('Fp0', 9))
     L.check(lib.dmk_bind_global(None))
+
+
+# ------------------------------------------------------------------------------------------------ polarisation scheme
+# PARITY UNPINNED: the reference tree has no polarisation solver (damask_grid.cpp:8-12) and no fixture for one; the oracle
+# (oracle/polarisation.py) restates upstream DAMASK's grid_mechanical_spectral_polarisation, so these tests are
+# device-vs-oracle self-consistency plus the scheme-independent property that both schemes find the same equilibrium.
+def _polarisation_pair(cells, grains, phase, **num):
+    from solver_cpp_b200 import mech, workloads as W
+    from oracle.polarisation import MechSolverPolarisationOracle
+    material, material_at, size = W.polycrystal(cells, grains, phase, 0)
+    o = MechSolverPolarisationOracle(cells, size, material, material_at, **num)
+    o.log_fields = False
+    o.init()
+    s = mech.make_solver(cells, size, material, material_at, scheme='spectral_polarisation', **num)
+    s.init()
+    return s, o
+
+
+def test_polarisation_residual_matches_oracle():
+    """one evaluation of (r_F, r_F_tau) at a perturbed (F, F_tau): Gamma convolution of the polarisation field, constitutive
+    response at F - r_F_tau / beta, (dPdF + C_scale)^-1 per cell, err_div, err_curl, err_BC"""
+    from solver_cpp_b200 import mech, workloads as W
+    cells = (8, 6, 5)
+    s, o = _polarisation_pair(cells, 7, 'Al_pheno', alpha=1.2, beta=0.9)
+    st, sto = mech.parse_load(W.MIXED_SHEAR)[0], oparse(W.MIXED_SHEAR)[0]
+    s.forward(False, False, 0.5, 1.0, 5.0, st['deformation'], st['stress'], st['R'])
+    s.g.materialpoint_forward()
+    o.forward(False, False, 0.5, 1.0, 5.0, sto['deformation'], sto['stress'], sto['R'])
+    o.con.forward()
+    s.prepare_evaluation()
+    o.S = osp.masked_compliance(o.C_volAvg, o.params['R'], o.params['stress_mask'])
+    rng = np.random.default_rng(4)
+    nz, ny, nx = cells[2], cells[1], cells[0]
+    F = o.F + 1e-4 * rng.standard_normal(o.shape)
+    Ft = o.F_tau + 1e-4 * rng.standard_normal(o.shape)
+    assert _rel(s.g.to_natural(s.field('F')), o.F) < 1e-14 and _rel(s.g.to_natural(s.field('F_tau')), o.F_tau) < 1e-12
+    X = torch.stack([s.g.to_device(F), s.g.to_device(Ft)])
+    R = s.form_residual(X)
+    r = o.form_residual(np.concatenate([F.reshape(-1), Ft.reshape(-1)]), 1, 1)
+    n9 = F.size
+    assert _rel(s.g.to_natural(R[0]), r[:n9].reshape(o.shape)) < 1e-9
+    assert _rel(s.g.to_natural(R[1]), r[n9:].reshape(o.shape)) < 1e-9
+    assert _rel(s.get33('P_av'), o.P_av) < 1e-10 and _rel(s.get33('F_aim'), o.F_aim) < 1e-12
+    for key, ref in (('err_div', o.err_div), ('err_curl', o.err_curl), ('err_BC', o.err_BC)):
+        assert abs(s.get(key)[0] - ref) <= 1e-9 * ref, key
+
+
+def test_polarisation_increment_loop_matches_oracle_and_the_basic_scheme():
+    from solver_cpp_b200 import mech, workloads as W
+    cells, n_inc = (8, 8, 8), 3
+    s, o = _polarisation_pair(cells, 6, 'Al_pheno')
+    recs = mech.loop_over_loadcase(s, mech.parse_load(W.TENSION_X), max_increments=n_inc)
+    orecs = []
+
+    class Stop(Exception):
+        pass
+
+    def cb(rec, solver):
+        orecs.append(rec)
+        if len(orecs) == n_inc:
+            raise Stop()
+    try:
+        run_loadcase(o, oparse(W.TENSION_X), callback=cb)
+    except Stop:
+        pass
+    assert [r['iterations'] for r in recs] == [r['iterations'] for r in orecs]
+    assert [r['converged'] for r in recs] == [r['converged'] for r in orecs] == [True] * n_inc
+    for a, b in zip(recs, orecs):
+        assert _rel(a['P_av'], b['P_av']) < 1e-9 and _rel(a['F_aim'], b['F_aim']) < 1e-9
+    assert _rel(s.g.to_natural(s.field('F')), o.F) < 1e-9 and _rel(s.g.to_natural(s.field('F_tau')), o.F_tau) < 1e-9
+    # the basic scheme on the same problem ends in the same equilibrium (to the solvers' tolerances)
+    material, material_at, size = W.polycrystal(cells, 6, 'Al_pheno', 0)
+    sb = mech.make_solver(cells, size, material, material_at)
+    sb.init()
+    brecs = mech.loop_over_loadcase(sb, mech.parse_load(W.TENSION_X), max_increments=n_inc)
+    for a, b in zip(recs, brecs):
+        assert _rel(a['P_av'], b['P_av']) < 2e-4
+    assert np.abs(s.g.to_natural(s.field('F')) - sb.g.to_natural(sb.field('F'))).max() < 2e-5
