@@ -13,8 +13,9 @@ _DIVCORR = {'none': 0, 'size': 1, 'size+grid': 2, 'grid+size': 2}
 
 
 def read_numerics(path=None):
-    """numerics.yaml -> (lib.Numerics, derivative id, divergence-correction id, N_cutback_max); keys and defaults:
-    Config::parse_numerics, config.cpp:360-463 and config.h:50-78 of the reference"""
+    """numerics.yaml -> (lib.Numerics, derivative id, divergence-correction id, N_cutback_max, polarisation numerics); keys and
+    defaults: Config::parse_numerics, config.cpp:360-463 and config.h:50-78 of the reference (alpha, beta, eps_abs_curl(F),
+    eps_rel_curl(F) of the FFT section are what the polarisation scheme uses)"""
     d = yaml.safe_load(open(path)) if path else {}
     d = d or {}
     grid = ((d.get('solver') or {}).get('grid') or {})
@@ -23,8 +24,10 @@ def read_numerics(path=None):
     for key, table in (('derivative', _DERIVATIVE), ('divergence_correction', _DIVCORR)):
         if key in fft and str(fft[key]) not in table:
             raise ValueError('numerics: FFT.%s must be one of %s' % (key, ', '.join(table)))
+    pol = dict(alpha=float(fft.get('alpha', 1.0)), beta=float(fft.get('beta', 1.0)), eps_abs_curl=float(fft.get('eps_abs_curl(F)', 1.0e-10)),
+               eps_rel_curl=float(fft.get('eps_rel_curl(F)', 5.0e-4)))
     return (num, _DERIVATIVE[fft.get('derivative', 'continuous')], _DIVCORR[str(fft.get('divergence_correction', 'size+grid'))],
-            int(grid.get('N_cutback_max', 3)))
+            int(grid.get('N_cutback_max', 3)), pol)
 
 
 def load_job(geometry, material, load, numerics=None, world_size=1, rank=0, comm=None):
@@ -33,13 +36,15 @@ def load_job(geometry, material, load, numerics=None, world_size=1, rank=0, comm
     geo = read_vti(geometry)
     mat = yaml.safe_load(open(material)) if isinstance(material, str) else material
     ld = yaml.safe_load(open(load)) if isinstance(load, str) else load
-    num, derivative, divcorr, max_cut_back = read_numerics(numerics)
+    num, derivative, divcorr, max_cut_back, pol = read_numerics(numerics)
+    scheme = ((ld.get('solver') or {}).get('mechanical')) or 'spectral_basic'             # damask_grid.cpp:8-12 reads the same key
     cells = tuple(int(c) for c in geo['cells'])
     if int(geo['material'].max()) >= len(mat['material']) or int(geo['material'].min()) < 0:
         raise ValueError('geometry refers to material %d, material.yaml has %d entries' % (int(geo['material'].max()), len(mat['material'])))
     z0, z1 = parallel.slab_range(cells[2], world_size, rank)
     solver = mech.make_solver(cells, tuple(float(s) for s in geo['size']), mat, np.ascontiguousarray(geo['material'][z0:z1]), numerics=num,
-                              derivative=derivative, divergence_correction=divcorr, world_size=world_size, rank=rank, comm=comm)
+                              derivative=derivative, divergence_correction=divcorr, world_size=world_size, rank=rank, comm=comm,
+                              scheme=scheme, **(pol if scheme == 'spectral_polarisation' else {}))
     solver.max_cut_back = max_cut_back
     return solver, mech.parse_load(ld)
 

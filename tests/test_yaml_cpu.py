@@ -147,5 +147,5 @@ def test_cpp_numerics_equals_python_host(tmp_path):
         der, div = C.c_int(), C.c_int()
         rc = lib.dmk_numerics_from_yaml(path.encode() if path else None, C.byref(num), C.byref(der), C.byref(div))
         assert rc == 0, lib.dmk_last_error()
-        ref, rder, rdiv, _ = job.read_numerics(path)
+        ref, rder, rdiv, _, _ = job.read_numerics(path)
         assert bytes(num) == bytes(ref) and (der.value, div.value) == (rder, rdiv)
