@@ -246,6 +246,61 @@ static void pheno_dotState(const pt_t *p, const double *Mp, double *dot) {
   }
 }
 
+/* ------------------------------------------------------------------ kinehardening
+ * phase_mechanical_plastic_kinehardening.f90: kinetics :433-472, LpAndItsTangent :258-295, dotState :301-341,
+ * deltaState :347-379.  State: xi, chi, gamma (follow dotState) | sgn_gamma, chi_flip, gamma_flip (move by deltaState only) */
+static void kh_kinetics(const pt_t *p, const double *Mp, double *dg, double *ddg) {
+  const orc_phase_t *ph = p->ph; int n = ph->n_sl;
+  const double *xi = p->state, *chi = p->state + n;
+  for (int i = 0; i < n; i++) {
+    double tp = ddot(Mp, ph->P_nS_pos[i]) - chi[i], tn = ddot(Mp, ph->P_nS_neg[i]) + chi[i];
+    double tmax = fmax(tp, tn);
+    dg[i] = ((tp > tn) ? 1.0 : -1.0) * ph->dot_gamma_0_sl[i] * pow(tmax / xi[i], ph->n_sl_exp[i]);
+    if (ddg) ddg[i] = deq0(dg[i]) ? 0.0 : dg[i] * ph->n_sl_exp[i] / tmax;
+  }
+}
+static void kh_Lp(const pt_t *p, const double *Mp, double *Lp, double *dLp_dMp) {
+  const orc_phase_t *ph = p->ph;
+  double dg[ORC_MAX_SL], ddg[ORC_MAX_SL];
+  memset(Lp, 0, 9*sizeof(double)); memset(dLp_dMp, 0, 81*sizeof(double));
+  kh_kinetics(p, Mp, dg, ddg);
+  for (int i = 0; i < ph->n_sl; i++) {
+    const double *PnS = (dg[i] > 0.0) ? ph->P_nS_pos[i] : ph->P_nS_neg[i];
+    for (int a = 0; a < 9; a++) Lp[a] += dg[i] * ph->P_sl[i][a];
+    for (int a = 0; a < 9; a++) for (int b = 0; b < 9; b++) dLp_dMp[9*a+b] += ddg[i] * ph->P_sl[i][a] * PnS[b];
+  }
+}
+static void kh_dotState(const pt_t *p, const double *Mp, double *dot) {
+  const orc_phase_t *ph = p->ph; int n = ph->n_sl;
+  const double *gamma = p->state + 2*n, *sgn = p->state + 3*n, *chi_flip = p->state + 4*n, *gamma_flip = p->state + 5*n;
+  double *dot_xi = dot, *dot_chi = dot + n, *dot_gamma = dot + 2*n;
+  kh_kinetics(p, Mp, dot_gamma, NULL);
+  double sumGamma = 0; for (int i = 0; i < n; i++) sumGamma += gamma[i];
+  for (int i = 0; i < n; i++) dot_gamma[i] = fabs(dot_gamma[i]);
+  for (int i = 0; i < n; i++) {
+    double hs = 0; for (int j = 0; j < n; j++) hs += ph->h_sl_sl[i][j] * dot_gamma[j];
+    double x = sumGamma * ph->kh_h_0_xi[i] / ph->xi_inf_sl[i];
+    dot_xi[i] = hs * (ph->kh_h_inf_xi[i] + (ph->kh_h_0_xi[i] - ph->kh_h_inf_xi[i] * (1.0 - x)) * exp(-x));
+    double y = (gamma[i] - gamma_flip[i]) * ph->kh_h_0_chi[i] / (ph->kh_chi_inf[i] + chi_flip[i]);
+    dot_chi[i] = sgn[i] * dot_gamma[i] * (ph->kh_h_inf_chi[i] + (ph->kh_h_0_chi[i] - ph->kh_h_inf_chi[i] * (1.0 - y)) * exp(-y));
+  }
+}
+/* plastic_deltaState (phase_mechanical_plastic.f90:372-413) for kinehardening; returns broken */
+static int kh_deltaState(pt_t *p, const double *Mp) {
+  const orc_phase_t *ph = p->ph; int n = ph->n_sl;
+  double dg[ORC_MAX_SL], dlt[3 * ORC_MAX_SL];
+  double *chi = p->state + n, *gamma = p->state + 2*n, *sgn = p->state + 3*n, *chi_flip = p->state + 4*n, *gamma_flip = p->state + 5*n;
+  kh_kinetics(p, Mp, dg, NULL);
+  for (int i = 0; i < n; i++) {
+    double s = (fabs(dg[i]) <= 1.0e-10) ? sgn[i] : ((dg[i] >= 0.0 && !signbit(dg[i])) ? 1.0 : -1.0);
+    if (!(fabs(s - sgn[i]) <= 0.1)) { dlt[i] = s - sgn[i]; dlt[n + i] = fabs(chi[i]) - chi_flip[i]; dlt[2*n + i] = gamma[i] - gamma_flip[i]; }
+    else { dlt[i] = 0.0; dlt[n + i] = 0.0; dlt[2*n + i] = 0.0; }
+  }
+  if (any_nan(dlt, 3 * n)) return 1;
+  for (int i = 0; i < n; i++) { sgn[i] += dlt[i]; chi_flip[i] += dlt[n + i]; gamma_flip[i] += dlt[2*n + i]; }
+  return 0;
+}
+
 /* ------------------------------------------------------------------ isotropic */
 static void deviatoric(const double *M, double *D) { double tr = (M[0]+M[4]+M[8])/3.0; memcpy(D, M, 9*sizeof(double)); D[0]-=tr; D[4]-=tr; D[8]-=tr; }
 static void iso_Lp(const pt_t *p, const double *Mp, double *Lp, double *dLp_dMp) {
@@ -469,7 +524,8 @@ static void plastic_Lp_tangents(const pt_t *p, const double *S, const double *Fi
   if (p->ph->law == 0) { memset(Lp, 0, 9*sizeof(double)); memset(dLp_dS, 0, 81*sizeof(double)); memset(dLp_dFi, 0, 81*sizeof(double)); return; }
   double Mp[9], FiTFi[9], dM[81];
   Mandel(Fi, S, Mp, FiTFi);
-  if (p->ph->law == 1) iso_Lp(p, Mp, Lp, dM); else if (p->ph->law == 2) pheno_Lp(p, Mp, Lp, dM); else dt_Lp(p, Mp, Lp, dM);
+  if (p->ph->law == 1) iso_Lp(p, Mp, Lp, dM); else if (p->ph->law == 2) pheno_Lp(p, Mp, Lp, dM);
+  else if (p->ph->law == 4) kh_Lp(p, Mp, Lp, dM); else dt_Lp(p, Mp, Lp, dM);
   double FiS[9]; mm(Fi, S, FiS);
   for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) {
     double d[9], dT[9], a[9], b[9];
@@ -502,8 +558,17 @@ static void Li_tangents(const pt_t *p, const double *S, const double *Fi, double
 static void dotState(const pt_t *p, double *dot) {
   if (p->ph->law == 0) return;
   double Mp[9], FiTFi[9]; Mandel(p->Fi, p->S, Mp, FiTFi);
-  if (p->ph->law == 1) iso_dotState(p, Mp, dot); else if (p->ph->law == 2) pheno_dotState(p, Mp, dot); else dt_dotState(p, Mp, dot);
+  if (p->ph->law == 1) iso_dotState(p, Mp, dot); else if (p->ph->law == 2) pheno_dotState(p, Mp, dot);
+  else if (p->ph->law == 4) kh_dotState(p, Mp, dot); else dt_dotState(p, Mp, dot);
 }
+/* plastic_deltaState (phase_mechanical_plastic.f90:372-413): instantaneous state change after a converged state integration;
+ * .false. (0) for every law but kinehardening (nonlocal is not restated); returns broken */
+static int deltaState(pt_t *p) {
+  if (p->ph->law != 4) return 0;
+  double Mp[9], FiTFi[9]; Mandel(p->Fi, p->S, Mp, FiTFi);
+  return kh_deltaState(p, Mp);
+}
+static int n_dot_of(const orc_phase_t *ph) { return ph->n_dot > 0 ? ph->n_dot : ph->n_state; }
 
 /* ------------------------------------------------------------------ integrateStress; returns broken */
 typedef struct { long n_Lp_iter, n_Li_iter, n_stress_calls, n_state_iter, n_substeps, n_cutbacks; } orc_counters_t;
@@ -621,7 +686,7 @@ static double damper(const double *o0, const double *o1, const double *o2, int n
   return 1.0;
 }
 static int integrateStateFPI(pt_t *p, const double *F, const double *Fp0, const double *Fi0, const double *state0, double dt, orc_counters_t *cnt) {
-  const orc_phase_t *ph = p->ph; int n = ph->n_state;
+  const orc_phase_t *ph = p->ph; int n = n_dot_of(ph);             /* 1:sizeDotState */
   double dot[ORC_MAX_STATE], last1[ORC_MAX_STATE], last2[ORC_MAX_STATE], r[ORC_MAX_STATE];
   int broken = 1;
   memset(dot, 0, sizeof dot); memset(last1, 0, sizeof last1); memset(last2, 0, sizeof last2);
@@ -643,7 +708,7 @@ static int integrateStateFPI(pt_t *p, const double *F, const double *Fp0, const 
       p->state[i] -= r[i];
     }
     for (int i = 0; i < n; i++) if (!(fabs(r[i]) <= fmax(ph->atol[i], p->num->eps_rel_state * fabs(p->state[i])))) conv = 0;
-    if (conv) { broken = 0; break; }                 /* plastic_deltaState: .false. for the laws restated here */
+    if (conv) { broken = deltaState(p); break; }     /* :661-664 */
   }
   return broken;
 }
@@ -653,20 +718,22 @@ static int state_converged(const pt_t *p, const double *r, int n) {             
   for (int i = 0; i < n; i++) if (!(fabs(r[i]) <= fmax(p->ph->atol[i], p->num->eps_rel_state * fabs(p->state[i])))) return 0;
   return 1;
 }
-/* integrateStateEuler, phase_mechanical.f90:699-735 (plastic_deltaState: .false. for the laws restated here) */
+/* integrateStateEuler, phase_mechanical.f90:699-735 */
 static int integrateStateEuler(pt_t *p, const double *F, const double *Fp0, const double *Fi0, const double *state0, double dt, orc_counters_t *cnt) {
-  int n = p->ph->n_state; double dot[ORC_MAX_STATE]; memset(dot, 0, sizeof dot);
+  int n = n_dot_of(p->ph); double dot[ORC_MAX_STATE]; memset(dot, 0, sizeof dot);
   dotState(p, dot);
   if (any_nan(dot, n)) return 1;
   for (int i = 0; i < n; i++) p->state[i] = state0[i] + dot[i] * dt;
+  if (deltaState(p)) return 1;
   return integrateStress(p, F, Fp0, Fi0, dt, cnt);
 }
 /* integrateStateAdaptiveEuler, :738-787 */
 static int integrateStateAdaptiveEuler(pt_t *p, const double *F, const double *Fp0, const double *Fi0, const double *state0, double dt, orc_counters_t *cnt) {
-  int n = p->ph->n_state; double dot[ORC_MAX_STATE], r[ORC_MAX_STATE]; memset(dot, 0, sizeof dot);
+  int n = n_dot_of(p->ph); double dot[ORC_MAX_STATE], r[ORC_MAX_STATE]; memset(dot, 0, sizeof dot);
   dotState(p, dot);
   if (any_nan(dot, n)) return 1;
   for (int i = 0; i < n; i++) { r[i] = -dot[i] * 0.5 * dt; p->state[i] = state0[i] + dot[i] * dt; }
+  if (deltaState(p)) return 1;
   if (integrateStress(p, F, Fp0, Fi0, dt, cnt)) return 1;
   dotState(p, dot);
   if (any_nan(dot, n)) return 1;
@@ -678,7 +745,7 @@ static int integrateStateAdaptiveEuler(pt_t *p, const double *F, const double *F
    -- times dt, as the reference has it (:902). */
 static int integrateStateRK(pt_t *p, const double *F_0, const double *F, const double *Fp0, const double *Fi0, const double *state0,
                             double dt, orc_counters_t *cnt, int ns, const double *A, const double *B, const double *C, const double *DB) {
-  int n = p->ph->n_state; double dot[ORC_MAX_STATE], rk[6][ORC_MAX_STATE], Fs[9];
+  int n = n_dot_of(p->ph); double dot[ORC_MAX_STATE], rk[6][ORC_MAX_STATE], Fs[9];
   int broken = 1;
   memset(dot, 0, sizeof dot);
   dotState(p, dot);
@@ -703,6 +770,7 @@ static int integrateStateRK(pt_t *p, const double *F_0, const double *F, const d
     for (int i = 0; i < n; i++) { double s = 0.0; for (int m = 0; m <= ns; m++) s += rk[m][i] * DB[m]; r[i] = s * dt; }
     if (!state_converged(p, r, n)) return 1;
   }
+  if (deltaState(p)) return 1;
   return integrateStress(p, F, Fp0, Fi0, dt, cnt);
 }
 static const double RK4_A[9] = {0.5, 0, 0,  0, 0.5, 0,  0, 0, 1.0};

@@ -16,7 +16,7 @@ import numpy as np
 
 from . import crystal
 from .phase_layout import (Phase, Numerics, PointState, STATE_FIELDS, MAX_SL, MAX_TW,
-                           LAW_NONE, LAW_ISOTROPIC, LAW_PHENOPOWERLAW, LAW_DISLOTWIN)
+                           LAW_NONE, LAW_ISOTROPIC, LAW_PHENOPOWERLAW, LAW_DISLOTWIN, LAW_KINEHARDENING)
 from .build import build
 
 T_ROOM = 293.15            # constants.f90:12
@@ -156,6 +156,30 @@ def make_phase(name, phase_cfg, T=T_ROOM):
         state_init = np.concatenate([xi0_sl, xi0_tw, np.zeros(ns), np.zeros(nt)])
         atol = np.concatenate([np.full(ns + nt, float(pl.get('atol_xi', 1.0))),
                                np.full(ns + nt, float(pl.get('atol_gamma', 1.0e-6)))])
+    elif ptype == 'kinehardening':                   # plastic_kinehardening_init, phase_mechanical_plastic_kinehardening.f90:72-252
+        ph.law = LAW_KINEHARDENING
+        N_sl = list(pl.get('N_sl', []))
+        ns = int(np.sum(N_sl))
+        if ns == 0:
+            raise NotImplementedError('kinehardening without slip')
+        ph.n_sl, ph.n_tw = ns, 0
+        P = crystal.schmid_slip(N_sl, lattice)
+        _set(ph.P_sl, P.reshape(ns, 9))
+        if lattice == 'cI':
+            a_nS = pl.get('a_nonSchmid_110', [])
+            _set(ph.P_nS_pos, crystal.schmid_slip(N_sl, lattice, a_nS, +1).reshape(ns, 9))
+            _set(ph.P_nS_neg, crystal.schmid_slip(N_sl, lattice, a_nS, -1).reshape(ns, 9))
+        else:
+            _set(ph.P_nS_pos, P.reshape(ns, 9)); _set(ph.P_nS_neg, -P.reshape(ns, 9))
+        _set(ph.h_sl_sl, crystal.interaction_slip_slip(N_sl, pl['h_sl-sl'], lattice))
+        _set(ph.dot_gamma_0_sl, _expand(pl['dot_gamma_0'], N_sl)); _set(ph.n_sl_exp, _expand(pl['n'], N_sl))
+        _set(ph.xi_inf_sl, _expand(pl['xi_inf'], N_sl)); _set(ph.kh_chi_inf, _expand(pl['chi_inf'], N_sl))
+        _set(ph.kh_h_0_xi, _expand(pl['h_0_xi'], N_sl)); _set(ph.kh_h_0_chi, _expand(pl['h_0_chi'], N_sl))
+        _set(ph.kh_h_inf_xi, _expand(pl['h_inf_xi'], N_sl)); _set(ph.kh_h_inf_chi, _expand(pl['h_inf_chi'], N_sl))
+        ph.n_dot = 3 * ns
+        state_init = np.concatenate([_expand(pl['xi_0'], N_sl), np.zeros(5 * ns)])
+        atol = np.concatenate([np.full(2 * ns, float(pl.get('atol_xi', 1.0))), np.full(ns, float(pl.get('atol_gamma', 1.0e-6))),
+                               np.zeros(3 * ns)])
     elif ptype == 'dislotwin':
         ph.law = LAW_DISLOTWIN
         N_sl = list(pl.get('N_sl', [])); N_tw = list(pl.get('N_tw', [])); N_tr = list(pl.get('N_tr', []))

@@ -5,6 +5,7 @@ oracle/constitutive.c and its ctypes wrapper: the field tables below generate bo
 Field meaning follows the reference's tParameters containers:
   phenopowerlaw  phase_mechanical_plastic_phenopowerlaw.f90:11-58
   isotropic      phase_mechanical_plastic_isotropic.f90:11-40
+  kinehardening  phase_mechanical_plastic_kinehardening.f90:11-40
   dislotwin      phase_mechanical_plastic_dislotwin.f90:12-92
   numerics       phase_mechanical.f90:277-294
 """
@@ -13,11 +14,12 @@ import ctypes as C
 MAX_SL, MAX_TW, MAX_TR = 48, 12, 12
 MAX_STATE = 3 * MAX_SL + MAX_TW + MAX_TR
 
-LAW_NONE, LAW_ISOTROPIC, LAW_PHENOPOWERLAW, LAW_DISLOTWIN = 0, 1, 2, 3
+LAW_NONE, LAW_ISOTROPIC, LAW_PHENOPOWERLAW, LAW_DISLOTWIN, LAW_KINEHARDENING = 0, 1, 2, 3, 4
 
 # (name, 'i'|'d', shape tuple or ())
 PHASE_FIELDS = [
     ('law', 'i', ()), ('n_sl', 'i', ()), ('n_tw', 'i', ()), ('n_tr', 'i', ()), ('n_state', 'i', ()),
+    ('n_dot', 'i', ()),        # sizeDotState: the leading part of the state that follows dotState; the rest moves by deltaState only
     ('C66', 'd', (36,)),
     ('atol', 'd', (MAX_STATE,)),
     ('state_init', 'd', (MAX_STATE,)),
@@ -51,6 +53,9 @@ PHASE_FIELDS = [
     ('dt_b_tw', 'd', (MAX_TW,)), ('dt_t_tw', 'd', (MAX_TW,)), ('dt_r', 'd', (MAX_TW,)),
     ('dt_pair', 'i', (MAX_TW, 2)),                      # 0-based slip indices
     ('dt_C66_tw', 'd', (MAX_TW, 36)),
+    # ---- kinehardening (phase_mechanical_plastic_kinehardening.f90:11-40; dot_gamma_0_sl, n_sl_exp, xi_inf_sl are shared)
+    ('kh_chi_inf', 'd', (MAX_SL,)), ('kh_h_0_xi', 'd', (MAX_SL,)), ('kh_h_0_chi', 'd', (MAX_SL,)),
+    ('kh_h_inf_xi', 'd', (MAX_SL,)), ('kh_h_inf_chi', 'd', (MAX_SL,)),
 ]
 
 NUM_FIELDS = [
