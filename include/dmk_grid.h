@@ -119,6 +119,9 @@ int dmk_set_profiling(dmk_ctx* ctx, int enable);
 int dmk_get_profile(dmk_ctx* ctx, double out[6], int reset);
 /* measured FP64 FMA throughput of the device (register-resident DFMA chains), TFLOP/s: the constitutive roofline */
 int dmk_fp64_peak(double* tflops);
+/* self-test of the per-point kernel's branch-free reciprocal / square root (csrc/pheno_fast_dev.cuh) against the IEEE
+ * operators on n arguments of random sign-less mantissa and exponent in [2^-lim, 2^lim]: number of results that differ */
+int dmk_selftest_special(long long n, unsigned long long seed, int lim, long long* bad_rcp, long long* bad_sqrt);
 int dmk_sizeof_phase(void);                                       /* sizeof(dmk_phase), for binding checks */
 int dmk_sizeof_numerics(void);
 

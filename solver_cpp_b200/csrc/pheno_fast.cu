@@ -22,7 +22,7 @@ __global__ void __launch_bounds__(DMK_PF_THREADS, DMK_PF_MINBLOCKS)
 dmk_pheno_fast_kernel(const __grid_constant__ DmkPhenoK<NSL> K, DmkPointArrays pa, int phase, DmkNumDev num, int defer_nLp,
                       const double* __restrict__ Fin, double* __restrict__ Pout, double Dt) {
   extern __shared__ double pf_sm[];
-  const DmkScr scr = {pf_sm + threadIdx.x, DMK_PF_THREADS, pf_sm + PfOff<NSL>::TOTAL * DMK_PF_THREADS + threadIdx.x, DMK_PF_THREADS};   // all of it in shared memory
+  const DmkScr scr = {pf_sm + threadIdx.x, DMK_PF_THREADS, pf_sm + PfOff<NSL>::TOTAL * DMK_PF_THREADS + threadIdx.x, DMK_PF_THREADS, &K};   // all of it in shared memory
   DmkCnt cnt = {0, 0, 0, 0, 0, 0};
   unsigned ill = 0, ndefer = 0;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < pa.n; i += (long long)gridDim.x * blockDim.x) {
@@ -49,12 +49,12 @@ static int defer_setting() {
   return v < 0 ? 0 : v;
 }
 
-// DMK_PHENO_UNROLL=<1|2|3|4|12>: unroll factor of the slip-system loops inside the Newton iteration.  Default 1 (rolled):
-// the kernels are instruction-fetch sensitive -- unrolled 12-fold `no_instruction` was the top stall at a 57 %
-// instruction-cache hit rate (128^3 solver iterate 31.3 ms against 28.1 ms rolled); with the three-way vote 1 beats 2
-// (21.1 against 21.6 ms), profiles/r01_summary.md
+// DMK_PHENO_UNROLL=<1|4|12>: unroll factor of the slip-system loops inside the Newton iteration.  Nested schedule: default 1
+// (rolled) -- the kernels are instruction-fetch sensitive, unrolled 12-fold `no_instruction` was the top stall at a 57 %
+// instruction-cache hit rate (128^3 solver iterate 31.3 ms against 28.1 ms rolled), profiles/r01_summary.md.  Lane schedule:
+// default DMK_PL_UNR (per-loop factors chosen for latency hiding, profiles/r02_summary.md); 1 = the rolled instantiation
 static int unroll_setting() {
-  static const int v = [] { const char* e = getenv("DMK_PHENO_UNROLL"); return e ? atoi(e) : 1; }();
+  static const int v = [] { const char* e = getenv("DMK_PHENO_UNROLL"); return e ? atoi(e) : 0; }();
   return v;
 }
 
@@ -82,11 +82,28 @@ static int launch_pheno_fast(dmk_ctx* c, DmkPointArrays& pa, int ph, const DmkDe
 // pheno_lanes_dev.cuh.  One resident wave of 64-thread blocks; a warp claims chunks of DMK_PL_CHUNK consecutive cells from a
 // global queue (one atomic per chunk) and deals them to its lanes as they become free, so neighbouring lanes keep working
 // on neighbouring cells (coalesced structure-of-arrays accesses) and no warp is left with a long tail.  No barrier anywhere.
-#define DMK_PL_THREADS 64
+// Block size: 2 blocks of 128 threads per SM (8 warps, bounded by 255 registers and 840 B of shared scratch per thread alike).
+// With 128-thread blocks the 215 kB of scratch leave room for ONE COPY PER BLOCK OF THE PHASE TABLES in shared memory
+// (DMK_PL_KSMEM): the rolled slip-system loops read their Schmid tensors and coefficients with indexed constant-bank loads
+// (LDC), the indexed-constant cache holds 79 % of them (ncu idc__request_hit_rate) and the misses compete with the
+// instruction-cache misses of this 60 kB kernel for the GPC-level cache, which ran at 88 % of its request rate (gcc__cache_
+// requests_type_{instruction 57 %, constant 30 %}, profiles/r02_summary.md).  From shared memory every table read is one
+// broadcast LDS.
+#ifndef DMK_PL_THREADS
+#define DMK_PL_THREADS 128
+#endif
 #ifndef DMK_PL_MINBLOCKS
-#define DMK_PL_MINBLOCKS 4
+#define DMK_PL_MINBLOCKS (256 / DMK_PL_THREADS)
+#endif
+#ifndef DMK_PL_KSMEM
+#define DMK_PL_KSMEM 1
 #endif
 #define DMK_PL_CHUNK 256
+// unroll factors RRJJCC of the rate / Jacobian / correction loops of the Newton iteration (pheno_fast_dev.cuh: unr_rate ...);
+// DMK_PHENO_UNROLL=1 selects the rolled instantiation for comparison
+#ifndef DMK_PL_UNR
+#define DMK_PL_UNR 1
+#endif
 template <int NSL, int NEXP, int UNR, bool VOTE3, bool CUTBACK, int MINB>
 __global__ void __launch_bounds__(DMK_PL_THREADS, MINB)
 dmk_pheno_lanes_kernel(const __grid_constant__ DmkPhenoK<NSL> K, DmkPointArrays pa, int phase, DmkNumDev num,
@@ -102,8 +119,18 @@ dmk_pheno_lanes_kernel(const __grid_constant__ DmkPhenoK<NSL> K, DmkPointArrays 
     if (!(*list_total > list_min)) return;
   }
   extern __shared__ double pf_sm[];
-  const DmkScr scr = {pf_sm + threadIdx.x, DMK_PL_THREADS, pf_sm + PfOff<NSL>::TOTAL * DMK_PL_THREADS + threadIdx.x, DMK_PL_THREADS};
   const unsigned FULL = 0xffffffffu, lane = threadIdx.x & 31u, lt = (1u << lane) - 1u;
+#if DMK_PL_KSMEM
+  // the block's copy of the phase tables (the only barrier of the kernel); the slip-system loops index this copy (pf_tab),
+  // everything else (elastic constants, compliance) stays an immediate constant-bank operand
+  unsigned* ksm = reinterpret_cast<unsigned*>(pf_sm + (PfOff<NSL>::TOTAL + PfOff<NSL>::COLD_TOTAL) * DMK_PL_THREADS);
+  for (unsigned k = threadIdx.x; k < sizeof(DmkPhenoK<NSL>) / 4; k += DMK_PL_THREADS) ksm[k] = reinterpret_cast<const unsigned*>(&K)[k];
+  __syncthreads();
+  const void* tab = ksm;
+#else
+  const void* tab = &K;
+#endif
+  const DmkScr scr = {pf_sm + threadIdx.x, DMK_PL_THREADS, pf_sm + PfOff<NSL>::TOTAL * DMK_PL_THREADS + threadIdx.x, DMK_PL_THREADS, tab};
   PlLane<NSL> L;
   L.mode = PL_NEED;
   long long c_next = 0, c_end = 0;                      // the warp's current chunk (warp-uniform)
@@ -255,7 +282,8 @@ static int launch_pheno_lanes(dmk_ctx* c, DmkPointArrays& pa, int ph, const DmkD
                               double* d_P, double dt, bool from_list = false, double list_min = 0.0) {
   DmkPhenoK<NSL> K;
   dmk_pheno_fast_tables<NSL>(d, K);
-  const size_t smem = (size_t)(PfOff<NSL>::TOTAL + PfOff<NSL>::COLD_TOTAL) * DMK_PL_THREADS * sizeof(double);
+  static_assert(sizeof(DmkPhenoK<NSL>) % 8 == 0, "phase tables: whole doubles");
+  const size_t smem = (size_t)(PfOff<NSL>::TOTAL + PfOff<NSL>::COLD_TOTAL) * DMK_PL_THREADS * sizeof(double) + (DMK_PL_KSMEM ? sizeof(DmkPhenoK<NSL>) : 0);
   static int grid = 0;
   if (!grid) {
     DMK_CUDA_CHECK(cudaFuncSetAttribute(dmk_pheno_lanes_kernel<NSL, NEXP, UNR, VOTE3, CUTBACK, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -295,7 +323,7 @@ static int launch_pheno_lanes(dmk_ctx* c, DmkPointArrays& pa, int ph, const DmkD
     if (end > first) {
       if (staged) DMK_CUDA_CHECK(cudaStreamWaitEvent(st, c->stage_ev[k], 0));
       const long long warps_needed = (end - first + 31) / 32;
-      const int g = (int)std::max(1LL, std::min((long long)grid, (warps_needed + 1) / 2));
+      const int g = (int)std::max(1LL, std::min((long long)grid, (warps_needed + DMK_PL_THREADS / 32 - 1) / (DMK_PL_THREADS / 32)));
       dmk_pheno_lanes_kernel<NSL, NEXP, UNR, VOTE3, CUTBACK, MINB><<<g, DMK_PL_THREADS, smem, st>>>(K, pa, ph, nd, d_F, d_P, dt, first, end, vote_weights(), pa.d_work + k, nullptr, nullptr, nullptr, 0.0);
       if (k > 0) c->launches++;
     }
@@ -323,10 +351,10 @@ int dmk_points_pheno_fast(dmk_ctx* c, int ph, const DmkNumDev& nd, const double*
   if (lanes_setting() && dmk_pheno_lanes_eligible(nd, cb)) {
     *deferred = !cb;                                    // in-lane cut-backs: nothing is handed to the reference-order kernel
 #define DMK_PL_LAUNCH(NEXP_)                                                                                   \
-  (cb ? launch_pheno_lanes<12, NEXP_, 1, true, true>(c, pa, ph, d, nd, d_F, d_P, dt)                          \
-      : !vote3_setting() ? launch_pheno_lanes<12, NEXP_, 1, false, false>(c, pa, ph, d, nd, d_F, d_P, dt)     \
-      : (u == 2)  ? launch_pheno_lanes<12, NEXP_, 2, true, false>(c, pa, ph, d, nd, d_F, d_P, dt)             \
-                  : launch_pheno_lanes<12, NEXP_, 1, true, false>(c, pa, ph, d, nd, d_F, d_P, dt))
+  (cb ? launch_pheno_lanes<12, NEXP_, DMK_PL_UNR, true, true>(c, pa, ph, d, nd, d_F, d_P, dt)                          \
+      : !vote3_setting() ? launch_pheno_lanes<12, NEXP_, DMK_PL_UNR, false, false>(c, pa, ph, d, nd, d_F, d_P, dt)     \
+      : (u == 1)  ? launch_pheno_lanes<12, NEXP_, 1, true, false>(c, pa, ph, d, nd, d_F, d_P, dt)                      \
+                  : launch_pheno_lanes<12, NEXP_, DMK_PL_UNR, true, false>(c, pa, ph, d, nd, d_F, d_P, dt))
     rc = (nexp == 20) ? (DMK_PL_LAUNCH(20)) : (DMK_PL_LAUNCH(0));
 #undef DMK_PL_LAUNCH
     if (rc) return rc;
@@ -345,8 +373,8 @@ int dmk_points_pheno_fast(dmk_ctx* c, int ph, const DmkNumDev& nd, const double*
     if (!cb && adaptive && dmk_mass_deferral_setting(c) != 0) {       // mass deferral
       const double many = (double)(c->n_global / 32);
       if (dmk_mass_deferral_setting(c) == 2) {            // ... through the in-lane cut-back kernel (else: constitutive.cu)
-        rc = (nexp == 20) ? launch_pheno_lanes<12, 20, 1, true, true>(c, pa, ph, d, nd, d_F, d_P, dt, true, many)
-                          : launch_pheno_lanes<12, 0, 1, true, true>(c, pa, ph, d, nd, d_F, d_P, dt, true, many);
+        rc = (nexp == 20) ? launch_pheno_lanes<12, 20, DMK_PL_UNR, true, true>(c, pa, ph, d, nd, d_F, d_P, dt, true, many)
+                          : launch_pheno_lanes<12, 0, DMK_PL_UNR, true, true>(c, pa, ph, d, nd, d_F, d_P, dt, true, many);
         if (rc) return rc;
       }
       *defer_max = many;
@@ -354,13 +382,41 @@ int dmk_points_pheno_fast(dmk_ctx* c, int ph, const DmkNumDev& nd, const double*
     DMK_CUDA_CHECK(cudaGetLastError());
     return DMK_OK;
   }
-  if (nexp == 20) rc = (u == 1) ? launch_pheno_fast<12, 20, 1>(c, pa, ph, d, nd, d_F, d_P, dt)
+  if (nexp == 20) rc = (u == 12) ? launch_pheno_fast<12, 20, 12>(c, pa, ph, d, nd, d_F, d_P, dt)
                  : (u == 4) ? launch_pheno_fast<12, 20, 4>(c, pa, ph, d, nd, d_F, d_P, dt)
-                            : launch_pheno_fast<12, 20, 12>(c, pa, ph, d, nd, d_F, d_P, dt);
-  else rc = (u == 1) ? launch_pheno_fast<12, 0, 1>(c, pa, ph, d, nd, d_F, d_P, dt)
+                            : launch_pheno_fast<12, 20, 1>(c, pa, ph, d, nd, d_F, d_P, dt);
+  else rc = (u == 12) ? launch_pheno_fast<12, 0, 12>(c, pa, ph, d, nd, d_F, d_P, dt)
           : (u == 4) ? launch_pheno_fast<12, 0, 4>(c, pa, ph, d, nd, d_F, d_P, dt)
-                     : launch_pheno_fast<12, 0, 12>(c, pa, ph, d, nd, d_F, d_P, dt);
+                     : launch_pheno_fast<12, 0, 1>(c, pa, ph, d, nd, d_F, d_P, dt);
   if (rc) return rc;
   DMK_CUDA_CHECK(cudaGetLastError());
+  return DMK_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ self-test (include/dmk_grid.h)
+__global__ void dmk_selftest_special_kernel(long long n, unsigned long long seed, int lim, unsigned long long* bad) {
+  unsigned long long nr = 0, ns = 0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    unsigned long long z = seed + 0x9e3779b97f4a7c15ull * (unsigned long long)(i + 1);       // splitmix64
+    z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull; z = (z ^ (z >> 27)) * 0x94d049bb133111ebull; z ^= z >> 31;
+    const long long e = 1023 - lim + (long long)((z >> 52) % (unsigned long long)(2 * lim + 1));
+    const double x = __longlong_as_double((long long)((z & 0x000fffffffffffffull) | ((unsigned long long)e << 52)));
+    if (!pf_fast_ok(x)) continue;
+    if (__double_as_longlong(pf_rcp_fast(x)) != __double_as_longlong(1.0 / x)) nr++;
+    if (__double_as_longlong(pf_sqrt_fast(x)) != __double_as_longlong(sqrt(x))) ns++;
+  }
+  if (nr) atomicAdd(&bad[0], nr);
+  if (ns) atomicAdd(&bad[1], ns);
+}
+extern "C" int dmk_selftest_special(long long n, unsigned long long seed, int lim, long long* bad_rcp, long long* bad_sqrt) {
+  unsigned long long* d = nullptr;
+  unsigned long long h[2] = {0, 0};
+  DMK_CUDA_CHECK(cudaMalloc((void**)&d, sizeof h));
+  DMK_CUDA_CHECK(cudaMemset(d, 0, sizeof h));
+  dmk_selftest_special_kernel<<<1184, 256>>>(n, seed, lim, d);
+  DMK_CUDA_CHECK(cudaMemcpy(h, d, sizeof h, cudaMemcpyDeviceToHost));
+  cudaFree(d);
+  DMK_CUDA_CHECK(cudaGetLastError());
+  *bad_rcp = (long long)h[0]; *bad_sqrt = (long long)h[1];
   return DMK_OK;
 }

@@ -166,16 +166,27 @@ DMK_HD __forceinline__ int pl_residual(const DmkPhenoK<NSL>& K, const DmkNumDev&
 #pragma unroll (unr_rate(UNR))
   for (int s = 0; s < NSL; s++) {
     double dg, c;
-    pf_rate<NSL, NEXP>(K, s, S, scr(O::RXI + s), dg, c);
+    pf_rate<NSL, NEXP>(pf_tab<NSL>(scr), s, S, scr(O::RXI + s), dg, c);
     scr(O::C + s) = dt * c;
 #pragma unroll
-    for (int a = 0; a < 9; a++) res[a] += dg * K.P[s][a];
+    for (int a = 0; a < 9; a++) res[a] += dg * pf_tab<NSL>(scr).P[s][a];
   }
-  const double atol = fmax(num.eps_rel_Lp * fmax(norm9(L.Lp), norm9(res)), num.eps_abs_Lp);
+  // the three Frobenius norms of the stopping test, their square roots scheduled into each other (pf_sqrt_fast)
+  double n2[3] = {0.0, 0.0, 0.0}, nr[3];
 #pragma unroll
-  for (int a = 0; a < 9; a++) res[a] = L.Lp[a] - res[a];
-  const double rn = norm9(res);
-  if (any_nan9(res)) return PL_FAIL;
+  for (int a = 0; a < 9; a++) { n2[0] += L.Lp[a] * L.Lp[a]; n2[1] += res[a] * res[a]; }
+#pragma unroll
+  for (int a = 0; a < 9; a++) { res[a] = L.Lp[a] - res[a]; n2[2] += res[a] * res[a]; }
+  bool ok = true;
+#pragma unroll
+  for (int k = 0; k < 3; k++) { ok = ok & pf_fast_ok(n2[k]); nr[k] = pf_sqrt_fast(n2[k]); }
+  if (!ok) {
+#pragma unroll
+    for (int k = 0; k < 3; k++) nr[k] = sqrt(n2[k]);
+  }
+  const double atol = fmax(num.eps_rel_Lp * fmax(nr[0], nr[1]), num.eps_abs_Lp);
+  const double rn = nr[2];
+  if (isnan(n2[2])) return PL_FAIL;                   // any_nan9(res)
   if (rn < atol) return PL_DONE;
   if (L.nLp == 1 || rn < L.res_old) {
     L.res_old = rn;
@@ -249,20 +260,20 @@ DMK_HD __forceinline__ int pl_state_block(const DmkPhenoK<NSL>& K, const DmkNumD
   double zeta = 1.0;
   if (!init && !nan) {
     double d12 = 0.0, d22 = 0.0, d01 = 0.0;           // damper (:677-690); D = last(1) - last(2)
-    // L1 and D (cold part of the scratch) are loaded four entries at a time so that the loads of a batch are in flight
+    // L1 and D (cold part of the scratch) are loaded PL_U_STATE entries at a time so that the loads of a batch are in flight
     // together; the sums run in the order k = 0, 1, 2, ... as before
+    constexpr int UB = (NST % PL_U_STATE == 0) ? PL_U_STATE : 4;
     static_assert(NST % 4 == 0, "state count: batches of four");
 #pragma unroll 1
-    for (int k0 = 0; k0 < NST; k0 += 4) {
-      double l1[4], dd[4];
+    for (int k0 = 0; k0 < NST; k0 += UB) {
+      double l1[UB], dd[UB], dk[UB];
 #pragma unroll
-      for (int j = 0; j < 4; j++) { l1[j] = scr.cold(O::L1 + k0 + j); dd[j] = scr.cold(O::D + k0 + j); }
+      for (int j = 0; j < UB; j++) { l1[j] = scr.cold(O::L1 + k0 + j); dd[j] = scr.cold(O::D + k0 + j); dk[j] = pf_dot<NSL>(scr, k0 + j); }
 #pragma unroll
-      for (int j = 0; j < 4; j++) {
-        const double dk = pf_dot<NSL>(scr, k0 + j);
-        d12 += (dk - l1[j]) * dd[j];
+      for (int j = 0; j < UB; j++) {
+        d12 += (dk[j] - l1[j]) * dd[j];
         d22 += dd[j] * dd[j];
-        d01 += dk * l1[j];
+        d01 += dk[j] * l1[j];
       }
     }
     if (fmin(d01, d12) < 0.0 && d22 > 0.0) zeta = 0.75 + 0.25 * tanh(2.0 + 4.0 * d12 / d22);
@@ -271,22 +282,25 @@ DMK_HD __forceinline__ int pl_state_block(const DmkPhenoK<NSL>& K, const DmkNumD
   if (!nan) {
     bool conv = true;
     const double* __restrict__ st0s = (sub ? pa.state : pa.state0) + i;
+    constexpr int UB = (NST % PL_U_STATE == 0) ? PL_U_STATE : 4;
 #pragma unroll 1
-    for (int k0 = 0; k0 < NST; k0 += 4) {
-      double l1[4], s0[4];
+    for (int k0 = 0; k0 < NST; k0 += UB) {
+      double l1[UB], s0[UB], dk[UB], sk[UB];
 #pragma unroll
-      for (int j = 0; j < 4; j++) { l1[j] = init ? 0.0 : scr.cold(O::L1 + k0 + j); s0[j] = st0s[(k0 + j) * n]; }
+      for (int j = 0; j < UB; j++) s0[j] = st0s[(k0 + j) * n];                       // global: issued first, all in flight together
 #pragma unroll
-      for (int j = 0; j < 4; j++) {
+      for (int j = 0; j < UB; j++) { l1[j] = init ? 0.0 : scr.cold(O::L1 + k0 + j); dk[j] = pf_dot<NSL>(scr, k0 + j); sk[j] = scr(O::ST + k0 + j); }
+#pragma unroll
+      for (int j = 0; j < UB; j++) {
         const int k = k0 + j;
-        const double d = pf_dot<NSL>(scr, k) * zeta + l1[j] * (1.0 - zeta);
+        const double d = dk[j] * zeta + l1[j] * (1.0 - zeta);
         scr.cold(O::D + k) = d - l1[j];
         scr.cold(O::L1 + k) = d;
-        double s = scr(O::ST + k);
+        double s = sk[j];
         const double r = s - s0[j] - d * dt;          // predictor: s == state0, r = -d dt
         s -= r;
         scr(O::ST + k) = s;
-        if (!(fabs(r) <= fmax(K.atol[k], num.eps_rel_state * fabs(s)))) conv = false;
+        if (!(fabs(r) <= fmax(pf_tab<NSL>(scr).atol[k], num.eps_rel_state * fabs(s)))) conv = false;
       }
     }
     finished = !init && (conv || L.it >= num.N_iter_state_max);   // a loop that runs out leaves broken = .false. (reference)

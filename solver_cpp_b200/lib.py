@@ -6,7 +6,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, 'libdamask_grid_b200.so')
+# DMK_LIB_PATH: another build of the SAME library (tools/build_variant.py: tuning builds with other compile-time factors)
+LIB_PATH = os.environ.get('DMK_LIB_PATH') or os.path.join(HERE, 'libdamask_grid_b200.so')
 
 MAX_SL, MAX_TW, MAX_PHASES = 24, 12, 8
 MAX_STATE = 3 * MAX_SL + MAX_TW

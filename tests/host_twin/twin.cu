@@ -72,7 +72,7 @@ static int run_point_fast(const DmkDevPhase* ph, const DmkNumDev& num, const dou
   int lpi = 0;
   pa.lp_iter = &lpi;
   double scratch[PfOff<NSL>::TOTAL], cold[PfOff<NSL>::COLD_TOTAL];
-  DmkScr scr = {scratch, 1, cold, 1};
+  DmkScr scr = {scratch, 1, cold, 1, &K};
   DmkCnt cnt = {0, 0, 0, 0, 0, 0};
   int rc;
   if (g_use_fast == 2 && dmk_pheno_lanes_eligible(num, g_defer == 0))

@@ -341,3 +341,17 @@ def test_point_state_restart_round_trip(tmp_path):
     P_b = g2.constitutive_response(g2.to_device(seq[2]), 0.5).cpu().numpy()
     assert np.array_equal(P_a, P_b)
     assert np.array_equal(g.get_state('state', 24), g2.get_state('state', 24))
+
+
+@pytest.mark.gpu
+def test_fast_reciprocal_and_sqrt_are_ieee():
+    """the per-point kernel's branch-free reciprocal / square root (pheno_fast_dev.cuh: the compiler's own fast-path sequences
+    without the inline slow-path call) return the correctly rounded results of 1.0 / x and sqrt(x), bit for bit, over their
+    whole admitted range -- so using them changes no result"""
+    import ctypes as C
+    from solver_cpp_b200 import lib as L
+    lib = L.load()
+    for seed, lim in ((1, 900), (2, 40), (3, 2)):
+        br, bs = C.c_longlong(-1), C.c_longlong(-1)
+        L.check(lib.dmk_selftest_special(C.c_longlong(200_000_000), C.c_ulonglong(seed), C.c_int(lim), C.byref(br), C.byref(bs)))
+        assert (br.value, bs.value) == (0, 0), (seed, lim, br.value, bs.value)
