@@ -108,6 +108,14 @@ int dmk_create(dmk_ctx** ctx, const dmk_grid_desc* grid);
 void dmk_destroy(dmk_ctx* ctx);
 int dmk_set_stream(dmk_ctx* ctx, void* cuda_stream);
 int dmk_set_comm(dmk_ctx* ctx, const dmk_comm* comm);
+/* native NCCL binding (csrc/nccl_comm.cpp): the library issues the collectives itself on its stream -- ncclAllReduce (sum, max)
+ * and the all-to-all of the distributed-FFT transpose as grouped ncclSend / ncclRecv -- in place of the callback table.  One rank
+ * makes the 128-byte ncclUniqueId, the host distributes it by its own means (MPI_Bcast in the reference's driver;
+ * torch.distributed in this repo's Python host), every rank calls dmk_nccl_init (collective).  replaces the exchange of FFTW-MPI's
+ * transposed plans and the MPI_Allreduce calls of spectral.cpp:160-165 / mech_base.cpp:395-402.  libnccl is resolved at run time. */
+int dmk_nccl_unique_id(unsigned char id[128]);
+int dmk_nccl_init(dmk_ctx* ctx, const unsigned char id[128]);
+int dmk_nccl_version(int* version);
 int dmk_synchronize(dmk_ctx* ctx);
 int dmk_local_cells(const dmk_ctx* ctx, int* nz_local, int* z_offset, int* ny_local, int* y_offset);
 int dmk_kernel_launches(const dmk_ctx* ctx, long long* n);        /* kernels launched so far by this context */

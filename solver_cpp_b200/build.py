@@ -44,7 +44,7 @@ def build(force=False, verbose=False):
         for o in outs:
             sys.stderr.write(o)
     if jobs or not os.path.exists(LIB):
-        cmd = [NVCC, '-shared', '-o', LIB] + objs + ['-lcudart', '-lz']        # zlib: compressed geometry files (vti_dropin.cpp)
+        cmd = [NVCC, '-shared', '-o', LIB] + objs + ['-lcudart', '-lz', '-ldl']        # zlib: compressed geometry files (vti_dropin.cpp)
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError('link failed:\n' + r.stderr)

@@ -18,6 +18,7 @@ struct dmk_ctx {
   double wgt;                     // 1 / n_global
   cudaStream_t stream; bool own_stream;
   dmk_comm comm; bool has_comm;
+  void* nccl;                     // native NCCL binding (nccl_comm.cpp), or null: the collectives go through the callback table
   long long launches;
   // optional section timing of one residual evaluation (dmk_set_profiling): events on the context's stream
   bool profiling; cudaEvent_t ev[8]; double prof_ms[8]; long long prof_n;
@@ -66,6 +67,7 @@ int dmk_spectral_setup(dmk_ctx* c);
 void dmk_spectral_teardown(dmk_ctx* c);
 void dmk_points_teardown(dmk_ctx* c);
 void dmk_mech_teardown(dmk_ctx* c);
+void dmk_nccl_teardown(dmk_ctx* c);
 // full transforms between a real slab field (device) and the z-pass layout in c->bufA
 int dmk_fft_forward_internal(dmk_ctx* c, const double* d_real);
 int dmk_fft_backward_internal(dmk_ctx* c, double* d_real, double scale);

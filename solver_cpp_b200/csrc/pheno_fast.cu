@@ -98,6 +98,12 @@ static int launch_pheno_fast(dmk_ctx* c, DmkPointArrays& pa, int ph, const DmkDe
 #ifndef DMK_PL_KSMEM
 #define DMK_PL_KSMEM 1
 #endif
+// DMK_PL_BLOCKVOTE: the vote that picks the next block (residual / Newton step / state block) is taken over the whole thread
+// block instead of per warp, so that all warps of a block run the same code at the same time: the kernel's hot code (28 kB of
+// a 48 kB executed footprint) does not fit the SM's 32 kB instruction cache when 8 warps sit in 8 different places of it
+#ifndef DMK_PL_BLOCKVOTE
+#define DMK_PL_BLOCKVOTE 0
+#endif
 #define DMK_PL_CHUNK 256
 // unroll factors RRJJCC of the rate / Jacobian / correction loops of the Newton iteration (pheno_fast_dev.cuh: unr_rate ...);
 // DMK_PHENO_UNROLL=1 selects the rolled instantiation for comparison
@@ -125,11 +131,15 @@ dmk_pheno_lanes_kernel(const __grid_constant__ DmkPhenoK<NSL> K, DmkPointArrays 
   // everything else (elastic constants, compliance) stays an immediate constant-bank operand
   unsigned* ksm = reinterpret_cast<unsigned*>(pf_sm + (PfOff<NSL>::TOTAL + PfOff<NSL>::COLD_TOTAL) * DMK_PL_THREADS);
   for (unsigned k = threadIdx.x; k < sizeof(DmkPhenoK<NSL>) / 4; k += DMK_PL_THREADS) ksm[k] = reinterpret_cast<const unsigned*>(&K)[k];
+  int* vote_sm = reinterpret_cast<int*>(ksm + sizeof(DmkPhenoK<NSL>) / 4);        // [3][4] (block vote)
+  if (threadIdx.x < 12) vote_sm[threadIdx.x] = 0;
   __syncthreads();
   const void* tab = ksm;
 #else
   const void* tab = &K;
+  static_assert(!DMK_PL_BLOCKVOTE, "the block vote keeps its counters behind the shared-memory tables");
 #endif
+  unsigned trip = 0;
   const DmkScr scr = {pf_sm + threadIdx.x, DMK_PL_THREADS, pf_sm + PfOff<NSL>::TOTAL * DMK_PL_THREADS + threadIdx.x, DMK_PL_THREADS, tab};
   PlLane<NSL> L;
   L.mode = PL_NEED;
@@ -152,11 +162,22 @@ dmk_pheno_lanes_kernel(const __grid_constant__ DmkPhenoK<NSL> K, DmkPointArrays 
     const unsigned bN = VOTE3 ? __ballot_sync(FULL, L.mode == PL_NEWTON) : 0u;
     const unsigned bS = __ballot_sync(FULL, L.mode == PL_INIT || L.mode == PL_CONV || L.mode == PL_RESTART);
     unsigned need = drained ? 0u : __ballot_sync(FULL, L.mode == PL_NEED);
-    if (!(bL | bN | bS | need)) break;
+    int pL = __popc(bL), pN = __popc(bN), pS = __popc(bS) + __popc(need);
+#if DMK_PL_BLOCKVOTE
+    {                                                  // totals over the block: triple-buffered counters, one barrier per trip
+      int* cnt = vote_sm + 4 * (trip % 3u);
+      if (lane == 0) { if (pL) atomicAdd(cnt, pL); if (pN) atomicAdd(cnt + 1, pN); if (pS) atomicAdd(cnt + 2, pS); }
+      __syncthreads();
+      pL = cnt[0]; pN = cnt[1]; pS = cnt[2];
+      if (threadIdx.x < 3) vote_sm[4 * ((trip + 2u) % 3u) + threadIdx.x] = 0;      // next used after the barrier of trip + 1
+      trip++;
+    }
+#endif
+    if (!(pL | pN | pS)) break;
     if constexpr (VOTE3) {
       // the Newton step runs only for the lanes whose residual test failed (2/3 of the Newton lanes), so it is a block of
       // its own in which such lanes accumulate
-      const int cL = vw.x * __popc(bL), cN = vw.y * __popc(bN), cS = vw.z * (__popc(bS) + __popc(need));
+      const int cL = vw.x * pL, cN = vw.y * pN, cS = vw.z * pS;
       if (cN >= cL && cN >= cS) {
         t_lp++; l_lp += __popc(bN);
         if (L.mode == PL_NEWTON) {
@@ -175,7 +196,7 @@ dmk_pheno_lanes_kernel(const __grid_constant__ DmkPhenoK<NSL> K, DmkPointArrays 
         }
         continue;
       }
-    } else if (__popc(bL) >= __popc(bS) + __popc(need)) {
+    } else if (pL >= pS) {
       t_lp++; l_lp += __popc(bL);
       if (L.mode == PL_LP) {
         const int rc = pl_lp_iteration<NSL, NEXP, UNR>(K, num, scr, L);
@@ -283,7 +304,7 @@ static int launch_pheno_lanes(dmk_ctx* c, DmkPointArrays& pa, int ph, const DmkD
   DmkPhenoK<NSL> K;
   dmk_pheno_fast_tables<NSL>(d, K);
   static_assert(sizeof(DmkPhenoK<NSL>) % 8 == 0, "phase tables: whole doubles");
-  const size_t smem = (size_t)(PfOff<NSL>::TOTAL + PfOff<NSL>::COLD_TOTAL) * DMK_PL_THREADS * sizeof(double) + (DMK_PL_KSMEM ? sizeof(DmkPhenoK<NSL>) : 0);
+  const size_t smem = (size_t)(PfOff<NSL>::TOTAL + PfOff<NSL>::COLD_TOTAL) * DMK_PL_THREADS * sizeof(double) + (DMK_PL_KSMEM ? sizeof(DmkPhenoK<NSL>) + 64 : 0);
   static int grid = 0;
   if (!grid) {
     DMK_CUDA_CHECK(cudaFuncSetAttribute(dmk_pheno_lanes_kernel<NSL, NEXP, UNR, VOTE3, CUTBACK, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -141,6 +141,7 @@ extern "C" void dmk_destroy(dmk_ctx* c) {
   dmk_mech_teardown(c);
   dmk_points_teardown(c);
   dmk_spectral_teardown(c);
+  dmk_nccl_teardown(c);
   if (c->m_F0) cudaFreeHost(c->m_F0); if (c->m_F) cudaFreeHost(c->m_F); if (c->m_P) cudaFreeHost(c->m_P);
   if (c->m_dPdF) cudaFreeHost(c->m_dPdF); if (c->m_ill) cudaFreeHost(c->m_ill);
   if (c->ev[0]) for (int i = 0; i < 8; i++) cudaEventDestroy(c->ev[i]);
