@@ -275,5 +275,9 @@ class GridContext:
         return self.fused_exchange
 
     def set_comm(self, comm):
+        """parallel.TorchComm (callback table) or parallel.NcclComm (the library's native NCCL binding)"""
         self._comm_keepalive = comm
-        L.check(self.lib.dmk_set_comm(self.ctx, C.byref(comm.struct)))
+        if hasattr(comm, 'attach'):
+            comm.attach(self)
+        else:
+            L.check(self.lib.dmk_set_comm(self.ctx, C.byref(comm.struct)))

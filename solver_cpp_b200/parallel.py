@@ -70,8 +70,47 @@ class TorchComm:
         self.struct = L.Comm(None, self._a2a, self._sum, self._max)
 
 
+class NcclComm:
+    """the library's own NCCL binding (csrc/nccl_comm.cpp): the collectives are issued by the library on its stream, no Python on
+    the per-evaluation path.  torch.distributed only carries the 128-byte ncclUniqueId from rank 0 to the others, once."""
+
+    def __init__(self, world_size, rank, group=None):
+        self.world_size, self.rank, self.group = world_size, rank, group
+        self.native = False
+        self._fallback = None
+
+    def attach(self, g):
+        lib = g.lib
+        uid = (C.c_ubyte * 128)()
+        ok = 1
+        try:
+            if self.rank == 0:
+                L.check(lib.dmk_nccl_unique_id(uid))
+        except L.DmkError as e:
+            print('solver_cpp_b200: native NCCL unavailable (%s)' % e)
+            ok = 0
+        t = torch.tensor(list(bytes(uid)) + [ok], dtype=torch.uint8, device=g.device)
+        src = dist.get_global_rank(self.group, 0) if self.group is not None else 0
+        dist.broadcast(t, src=src, group=self.group)
+        vals = t.cpu().tolist()
+        if vals[128]:
+            try:
+                L.check(lib.dmk_nccl_init(g.ctx, (C.c_ubyte * 128)(*vals[:128])))
+                self.native = True
+                return
+            except L.DmkError as e:
+                print('solver_cpp_b200: dmk_nccl_init failed on rank %d (%s)' % (self.rank, e))
+                raise
+        self._fallback = TorchComm(self.world_size, self.rank, self.group)       # every rank alike: rank 0's flag decides
+        L.check(lib.dmk_set_comm(g.ctx, C.byref(self._fallback.struct)))
+
+
 def make_comm(world_size, rank, group=None):
-    return TorchComm(world_size, rank, group)
+    """the collectives of a z-slab job: the library's native NCCL binding on GPUs (DMK_COMM=torch: the torch.distributed callback
+    table instead; always that one for CPU / gloo groups, which only the host-logic tests use)"""
+    import os
+    native = os.environ.get('DMK_COMM', 'nccl').lower() != 'torch' and torch.cuda.is_available() and dist.get_backend(group) == 'nccl'
+    return NcclComm(world_size, rank, group) if native else TorchComm(world_size, rank, group)
 
 
 def fused_exchange_wanted():

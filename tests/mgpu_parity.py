@@ -60,6 +60,9 @@ def main():
     _, mat_all, _ = W.polycrystal(cells, 12, 'Al_pheno', 0)
     s = mech.make_solver(cells, size, material, mat_slab, world_size=world, rank=rank, comm=parallel.make_comm(world, rank))
     s.init()
+    if rank == 0:
+        cm = s.g._comm_keepalive
+        print('collectives: %s%s' % (type(cm).__name__, ' (library-native ncclAllReduce / ncclSend / ncclRecv)' if getattr(cm, 'native', False) else ''))
     recs = mech.loop_over_loadcase(s, mech.parse_load(W.TENSION_X), max_increments=2)
     s1 = mech.make_solver(cells, size, material, mat_all)
     s1.init()
