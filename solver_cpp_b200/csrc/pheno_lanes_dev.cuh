@@ -106,7 +106,8 @@ DMK_HD __forceinline__ int pl_substep_begin(const DmkNumDev& num, const DmkPoint
     for (int a = 0; a < 6; a++) S[a] = pa.S0[a * n + i];
     {                                                 // unrolled, pointer bumped: this copy runs at ~4 of 32 lanes
       const double* __restrict__ src = (sub ? pa.state : pa.state0) + i;
-#pragma unroll
+      constexpr int UC = PL_U_COPY;
+#pragma unroll (UC)
       for (int k = 0; k < 2 * NSL; k++) { scr(O::ST + k) = *src; src += n; }
     }
     if (CUTBACK && !(L.sstep > num.r_cutback_min)) {  // terminally ill: what pf_point leaves behind (P of no converged sub-step: 0)
@@ -364,7 +365,8 @@ DMK_HD __forceinline__ int pl_state_block(const DmkPhenoK<NSL>& K, const DmkNumD
   for (int a = 0; a < 6; a++) pa.S[a * n + i] = S[a];
   {
     double* __restrict__ dst = pa.state + i;
-#pragma unroll
+    constexpr int UC = PL_U_COPY;
+#pragma unroll (UC)
     for (int k = 0; k < NST; k++) { *dst = scr(O::ST + k); dst += n; }
   }
   return PL_DONE;
