@@ -382,7 +382,9 @@ def run_solve(args):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0 = time.perf_counter(); t_last[0] = t0
     e0.record()
+    ts0 = s.get('solver_seconds', 12)
     mech.loop_over_loadcase(s, steps, max_increments=K, callback=cb)
+    ts1 = s.get('solver_seconds', 12)
     e1.record()
     barrier()
     wall_ms = (time.perf_counter() - t0) * 1e3
@@ -487,6 +489,10 @@ def run_solve(args):
         'kernel_ms': {'per': 'residual evaluation, mean over the %d evaluations of the timed solve (CUDA events on the solver stream)' % int(prof['evaluations']),
                       'constitutive': con_ms, 'reduce_aim': prof['reduce_aim_ms'] / ne, 'fft_forward_xy': prof['fft_forward_ms'] / ne,
                       'gamma_div_zpass': prof['gamma_zpass_ms'] / ne, 'fft_inverse_yx': prof['fft_inverse_ms'] / ne,
+                      'ngmres_wall_ms_per_iteration': dict(zip(('evaluations', 'dot_products', 'least_squares_host', 'combination_and_distances',
+                                                                'norm_of_F_A', 'XM', 'whole_solve', 'iterations', 'selection_and_allocation',
+                                                                'history_copies', 'convergence_test', 'first_evaluation_and_setup'),
+                                                               [float(1e3 * (ts1[k] - ts0[k]) / max(ts1[7] - ts0[7], 1.0)) for k in range(12)])),
                       'outside_evaluations_ms_per_step': (ms - sum(prof[k] for k in ('constitutive_ms', 'reduce_aim_ms', 'fft_forward_ms', 'gamma_zpass_ms', 'fft_inverse_ms'))) / K},
         # the dominant kernel by time: the per-point constitutive update (FP64 vector pipe; tensor cores do not apply)
         'roofline': {'bound': 'fp64', 'kernel': 'dmk_pheno_lanes_kernel (per-point constitutive update), %.1f %% of the timed solve' % (100.0 * prof['constitutive_ms'] / ms) if phen

@@ -18,6 +18,7 @@
 #include <string>
 #include <vector>
 #include <algorithm>
+#include <chrono>
 #include "ctx.h"
 #include "reduce.cuh"
 #include "constitutive.cuh"
@@ -52,6 +53,7 @@ struct DmkMech {
   std::vector<double> reports;                       // 6 doubles per convergence check
   std::vector<double> stats;                         // 2 doubles per evaluation: cells of this slab whose first sub-step failed, 0
   int snes_its; int snes_reason;
+  double t_solver[12];                               // wall seconds inside ngmres_solve: evaluations, dot products, least squares, combination, norms, copies, total, iterations
   bool capture;                                      // test aid: keep host copies of every evaluation's F and r
   std::vector<double> capF, capR;
 };
@@ -224,6 +226,183 @@ static int lincomb(dmk_ctx* c, double* out, const double* x, double c0, const st
   c->launches++;
   DMK_CUDA_CHECK(cudaGetLastError());
   return DMK_OK;
+}
+
+// ---- fused NGMRES vector operations: ONE pass over the history per operation instead of one pass per history vector (the
+// kernels above read `a` / `x` again for every v_k: 2 nv fields of traffic where nv + 1 suffice; at 256^3 a field is 1.2 GB and
+// the history holds up to 30).  Launch geometry, per-thread summation order and the block / grid reduction trees are those of
+// dmk_multidot_partial_kernel, dmk_lincomb_kernel and dmk_diffnorm_partial_kernel, so every result is bit-identical to theirs.
+#define DMK_VECOP_BLOCKS 1184
+// instantiated widths: the smallest one >= nv runs (at most 3 padded slots, which re-read v_0 from L1)
+#define DMK_VECOP_DISPATCH(L) \
+  if (nv <= 1) L(1) else if (nv <= 2) L(2) else if (nv <= 4) L(4) else if (nv <= 6) L(6) else if (nv <= 8) L(8) \
+  else if (nv <= 12) L(12) else if (nv <= 16) L(16) else if (nv <= 20) L(20) else if (nv <= 24) L(24) \
+  else if (nv <= 28) L(28) else L(32)
+// Both kernels stage their operands through shared memory with cp.async: thread t copies element i of every vector into its own
+// column of a [vector][256] tile (one 8-byte cp.async each, no register held per load), two tiles deep, and reads back only what it
+// copied itself -- so no barrier is needed, and a whole tile (up to 67 kB per SM) is always in flight whatever the register budget;
+// with plain loads ptxas interleaved each load with the FMA that consumes it (two loads in flight per thread).
+__device__ __forceinline__ void dmk_cp_async8(double* smem_dst, const double* gsrc) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void dmk_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void dmk_cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// row b of partial: [k] = f . v_k, [nv + k] = v_piv . v_k (k < nv), [2 nv] = f . f
+template <int NV>
+__global__ void __launch_bounds__(256) dmk_ngmres_dots_kernel(const double* __restrict__ f, DmkVecs v, int nv, int piv, long long n,
+                                                              double* __restrict__ partial) {
+  extern __shared__ double dmk_vec_tile[];                      // [2][NV + 1][256]
+  double acc[2 * NV + 1];
+#pragma unroll
+  for (int k = 0; k < 2 * NV + 1; k++) acc[k] = 0.0;
+  const long long T = (long long)gridDim.x * 256;
+  long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+  auto issue = [&](int st, long long ii) {
+    if (ii < n) {
+      double* d = dmk_vec_tile + (size_t)st * (NV + 1) * 256 + threadIdx.x;
+      dmk_cp_async8(d, f + ii);
+#pragma unroll
+      for (int k = 0; k < NV; k++) dmk_cp_async8(d + (k + 1) * 256, v.p[k] + ii);     // slots >= nv alias v_0 (the host pads the table)
+    }
+    dmk_cp_async_commit();
+  };
+  issue(0, i);
+  int st = 0;
+  for (; i < n; i += T) {
+    issue(st ^ 1, i + T);
+    dmk_cp_async_wait<1>();
+    const double* d = dmk_vec_tile + (size_t)st * (NV + 1) * 256 + threadIdx.x;
+    const double fi = d[0], pi = d[(piv + 1) * 256];
+#pragma unroll
+    for (int k = 0; k < NV; k++) { const double b = d[(k + 1) * 256]; acc[k] += fi * b; acc[NV + k] += pi * b; }
+    acc[2 * NV] += fi * fi;
+    st ^= 1;
+  }
+  dmk_cp_async_wait<0>();
+  __syncthreads();
+  double (*sh)[8] = reinterpret_cast<double (*)[8]>(dmk_vec_tile);                      // [2 NV + 1][8] warp partials (the tiles are dead)
+#pragma unroll
+  for (int j = 0; j < 2 * NV + 1; j++) {
+    double a = acc[j];
+    for (int off = 16; off > 0; off >>= 1) a += __shfl_down_sync(0xffffffffu, a, off);
+    if ((threadIdx.x & 31) == 0) sh[j][threadIdx.x >> 5] = a;
+  }
+  __syncthreads();
+  double* __restrict__ row = partial + (size_t)blockIdx.x * (2 * nv + 1);
+  for (int j = threadIdx.x; j < 2 * nv + 1; j += blockDim.x) {
+    const int src = j < nv ? j : (j < 2 * nv ? NV + (j - nv) : 2 * NV);
+    double t = 0.0;
+    for (int w = 0; w < 8; w++) t += sh[src][w];
+    row[j] = t;
+  }
+}
+// out = c0 x + sum_k a_k v_k; row b of partial: [k] = |out - v_k|^2 (k < nv), [nv] = |out - x|^2
+template <int NV>
+__global__ void __launch_bounds__(256) dmk_ngmres_combine_kernel(double* __restrict__ out, const double* __restrict__ x, double c0, DmkVecs v,
+                                                                 int nv, long long n, double* __restrict__ partial) {
+  extern __shared__ double dmk_vec_tile[];                      // [2][NV + 1][256]
+  double acc[NV + 1];
+#pragma unroll
+  for (int k = 0; k < NV + 1; k++) acc[k] = 0.0;
+  const long long T = (long long)gridDim.x * 256;
+  long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+  auto issue = [&](int st, long long ii) {
+    if (ii < n) {
+      double* d = dmk_vec_tile + (size_t)st * (NV + 1) * 256 + threadIdx.x;
+      dmk_cp_async8(d, x + ii);
+#pragma unroll
+      for (int k = 0; k < NV; k++) dmk_cp_async8(d + (k + 1) * 256, v.p[k] + ii);
+    }
+    dmk_cp_async_commit();
+  };
+  issue(0, i);
+  int st = 0;
+  for (; i < n; i += T) {
+    issue(st ^ 1, i + T);
+    dmk_cp_async_wait<1>();
+    const double* d = dmk_vec_tile + (size_t)st * (NV + 1) * 256 + threadIdx.x;
+    const double xi = d[0];
+    double s = c0 * xi;
+#pragma unroll
+    for (int k = 0; k < NV; k++) if (k < nv) s += v.a[k] * d[(k + 1) * 256];
+    out[i] = s;
+#pragma unroll
+    for (int k = 0; k < NV; k++) { const double e = s - d[(k + 1) * 256]; acc[k] += e * e; }
+    { const double e = s - xi; acc[NV] += e * e; }
+    st ^= 1;
+  }
+  dmk_cp_async_wait<0>();
+  __syncthreads();
+  double (*sh)[8] = reinterpret_cast<double (*)[8]>(dmk_vec_tile);
+#pragma unroll
+  for (int j = 0; j < NV + 1; j++) {
+    double a = acc[j];
+    for (int off = 16; off > 0; off >>= 1) a += __shfl_down_sync(0xffffffffu, a, off);
+    if ((threadIdx.x & 31) == 0) sh[j][threadIdx.x >> 5] = a;
+  }
+  __syncthreads();
+  double* __restrict__ row = partial + (size_t)blockIdx.x * (nv + 1);
+  for (int j = threadIdx.x; j < nv + 1; j += blockDim.x) {
+    const int src = j < nv ? j : NV;
+    double t = 0.0;
+    for (int w = 0; w < 8; w++) t += sh[src][w];
+    row[j] = t;
+  }
+}
+// out = x - f (the un-preconditioned NGMRES candidate X^M); dmk_lincomb_kernel's rounding for c0 = 1, a_0 = -1 (exact either way)
+__global__ void __launch_bounds__(256) dmk_ngmres_xm_kernel(double* __restrict__ out, const double* __restrict__ x, const double* __restrict__ f, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) out[i] = x[i] - f[i];
+}
+template <class K> static int vecop_smem(K kernel, int nvt) {
+  const int bytes = 2 * (nvt + 1) * 256 * (int)sizeof(double);
+  if (bytes > 48 * 1024) DMK_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  return DMK_OK;
+}
+static bool vecops_split() { static const int v = [] { const char* e = getenv("DMK_NGMRES_VECOPS"); return (e && !strcmp(e, "split")) ? 1 : 0; }(); return v != 0; }
+static int vecop_blocks(long long n) { return (int)std::max(1LL, std::min((n + 255) / 256, (long long)DMK_VECOP_BLOCKS)); }
+// xi_k = f . v_k, beta_k = v_piv . v_k (k < nv), nu = f . f -> host (global over ranks), one pass over f and the v_k
+static int ngmres_dots(dmk_ctx* c, const double* f, const std::vector<const double*>& vs, int piv, double* xi, double* beta, double* nu) {
+  const int nv = (int)vs.size();
+  int rc;
+  if (nv < 1 || nv > 32) { dmk_set_error("ngmres_dots: 1..32 vectors"); return DMK_ERR_ARG; }
+  DmkVecs v; for (int k = 0; k < 32; k++) { v.p[k] = vs[k < nv ? k : 0]; v.a[k] = 0; }
+  const long long n = c->mech->nvec;
+  const int blocks = vecop_blocks(n);
+  double* partial = c->d_scratch + DMK_SCRATCH_PARTIAL;
+  double* d_out = c->d_scratch + DMK_SCRATCH_TMP + 300;
+#define DMK_DOTS(NV) { if ((rc = vecop_smem(dmk_ngmres_dots_kernel<NV>, NV))) return rc; \
+    dmk_ngmres_dots_kernel<NV><<<blocks, 256, 2 * (NV + 1) * 256 * sizeof(double), c->stream>>>(f, v, nv, piv, n, partial); }
+  DMK_VECOP_DISPATCH(DMK_DOTS)
+#undef DMK_DOTS
+  dmk_sum_partials_kernel<<<1, 96, 0, c->stream>>>(partial, blocks, 2 * nv + 1, d_out);
+  c->launches += 2;
+  DMK_CUDA_CHECK(cudaGetLastError());
+  double h[65];
+  if ((rc = reduce_to_host(c, d_out, 2 * nv + 1, h))) return rc;
+  for (int k = 0; k < nv; k++) { xi[k] = h[k]; beta[k] = h[nv + k]; }
+  *nu = h[2 * nv];
+  return DMK_OK;
+}
+// out = c0 x + sum a_k v_k and dn_k = |out - v_k|^2 (k < nv), dn_nv = |out - x|^2 -> host, one pass
+static int ngmres_combine(dmk_ctx* c, double* out, const double* x, double c0, const std::vector<const double*>& vs, const double* a, double* dn) {
+  const int nv = (int)vs.size();
+  int rc;
+  if (nv < 1 || nv > 32) { dmk_set_error("ngmres_combine: 1..32 vectors"); return DMK_ERR_ARG; }
+  DmkVecs v; for (int k = 0; k < 32; k++) { v.p[k] = vs[k < nv ? k : 0]; v.a[k] = k < nv ? a[k] : 0.0; }
+  const long long n = c->mech->nvec;
+  const int blocks = vecop_blocks(n);
+  double* partial = c->d_scratch + DMK_SCRATCH_PARTIAL;
+  double* d_out = c->d_scratch + DMK_SCRATCH_TMP + 300;
+#define DMK_COMB(NV) { if ((rc = vecop_smem(dmk_ngmres_combine_kernel<NV>, NV))) return rc; \
+    dmk_ngmres_combine_kernel<NV><<<blocks, 256, 2 * (NV + 1) * 256 * sizeof(double), c->stream>>>(out, x, c0, v, nv, n, partial); }
+  DMK_VECOP_DISPATCH(DMK_COMB)
+#undef DMK_COMB
+  dmk_sum_partials_kernel<<<1, 96, 0, c->stream>>>(partial, blocks, nv + 1, d_out);
+  c->launches += 2;
+  DMK_CUDA_CHECK(cudaGetLastError());
+  return reduce_to_host(c, d_out, nv + 1, dn);
 }
 
 // ------------------------------------------------------------------------------------------------ tangent bookkeeping
@@ -488,8 +667,14 @@ static int copy_field(dmk_ctx* c, double* dst, const double* src) {
   return DMK_OK;
 }
 
+struct DmkLap {                                      // every operation timed here ends in a host synchronisation (reduce_to_host / evaluate)
+  std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+  double lap() { auto t1 = std::chrono::steady_clock::now(); const double d = std::chrono::duration<double>(t1 - t0).count(); t0 = t1; return d; }
+};
 static int ngmres_solve(dmk_ctx* c) {
   DmkMech* m = c->mech;
+  DmkLap lapse, whole;
+  struct Total { DmkMech* m; DmkLap* w; ~Total() { m->t_solver[6] += w->lap(); } } total_guard{m, &whole};
   const double gammaA = 2.0, gammaC = 2.0, epsilonB = 0.1, deltaB = 0.9;
   const int restart_it = 2, max_its = 10000, M = NGMRES_M;
   std::vector<double> Q((size_t)M * M, 0.0);
@@ -507,37 +692,51 @@ static int ngmres_solve(dmk_ctx* c) {
   if ((rc = hist_vec(c, m->Xdot, 0, &x0)) || (rc = hist_vec(c, m->Fdot, 0, &f0))) return rc;
   if ((rc = copy_field(c, x0, X)) || (rc = copy_field(c, f0, Fv))) return rc;
   int k_restart = 1, l = 1, ivec = 0, restart_count = 0;
+  DMK_CUDA_CHECK(cudaStreamSynchronize(c->stream)); m->t_solver[11] += lapse.lap();           // first evaluation and set-up of the history
   for (int k = 1; k <= max_its; k++) {
     // X^M = X - F(X); F^M
-    { std::vector<const double*> v = {Fv}; const double a[1] = {-1.0}; if ((rc = lincomb(c, m->XM, X, 1.0, v, a))) return rc; }
+    if (vecops_split()) { std::vector<const double*> v = {Fv}; const double a[1] = {-1.0}; if ((rc = lincomb(c, m->XM, X, 1.0, v, a))) return rc; }
+    else { dmk_ngmres_xm_kernel<<<DMK_VECOP_BLOCKS, 256, 0, c->stream>>>(m->XM, X, Fv, m->nvec); c->launches++; DMK_CUDA_CHECK(cudaGetLastError()); }
+    DMK_CUDA_CHECK(cudaStreamSynchronize(c->stream)); m->t_solver[5] += lapse.lap();
     if ((rc = form_residual(c, m->XM, m->FM, nfuncs, it))) return rc; nfuncs++;
+    m->t_solver[0] += lapse.lap();
     // nu, xi_i = <F^M, Fdot_i>, beta_i = <Fdot_ivec, Fdot_i>
     std::vector<const double*> fd(l);
     for (int i = 0; i < l; i++) fd[i] = m->Fdot[i];
     std::vector<const double*> b1 = fd; b1.push_back(m->FM);
     std::vector<double> xi(l + 1), beta(l);
-    if ((rc = dots(c, m->FM, b1, xi.data()))) return rc;
+    if (vecops_split()) {
+      if ((rc = dots(c, m->FM, b1, xi.data()))) return rc;
+      if ((rc = dots(c, m->Fdot[ivec], fd, beta.data()))) return rc;
+    } else if ((rc = ngmres_dots(c, m->FM, fd, ivec, xi.data(), beta.data(), &xi[l]))) return rc;
+    m->t_solver[1] += lapse.lap();
     const double nu = xi[l], fMnorm = sqrt(nu);
-    if ((rc = dots(c, m->Fdot[ivec], fd, beta.data()))) return rc;
     for (int i = 0; i < l; i++) { Q[(size_t)i * M + ivec] = beta[i]; Q[(size_t)ivec * M + i] = beta[i]; }
     std::vector<double> H((size_t)l * l), rhs(l), alpha(l);
     for (int i = 0; i < l; i++) { rhs[i] = nu - xi[i]; for (int j = 0; j < l; j++) H[(size_t)i * l + j] = Q[(size_t)i * M + j] - xi[i] - xi[j] + nu; }
     if (l == 1) alpha[0] = (H[0] != 0.0) ? rhs[0] / H[0] : 0.0;
     else sym_lstsq(H, l, rhs.data(), alpha.data());
     double asum = 0.0; for (int i = 0; i < l; i++) asum += alpha[i];
+    m->t_solver[2] += lapse.lap();
     // X^A = (1 - sum alpha) X^M + sum alpha_i Xdot_i ; F^A
+    std::vector<double> dn(l + 1);
     { std::vector<const double*> xd(l); for (int i = 0; i < l; i++) xd[i] = m->Xdot[i];
-      if ((rc = lincomb(c, m->XA, m->XM, 1.0 - asum, xd, alpha.data()))) return rc; }
+      if (vecops_split()) { if ((rc = lincomb(c, m->XA, m->XM, 1.0 - asum, xd, alpha.data()))) return rc; }
+      else if ((rc = ngmres_combine(c, m->XA, m->XM, 1.0 - asum, xd, alpha.data(), dn.data()))) return rc; }   // + the distances used below
+    DMK_CUDA_CHECK(cudaStreamSynchronize(c->stream)); m->t_solver[3] += lapse.lap();
     if ((rc = form_residual(c, m->XA, m->FA, nfuncs, it))) return rc; nfuncs++;
+    m->t_solver[0] += lapse.lap();
     if (fminnorm > fMnorm) fminnorm = fMnorm;
     // norms for selection and restart
     { std::vector<const double*> b = {m->FA}; if ((rc = dots(c, m->FA, b, tmp))) return rc; }
     const double fAnorm = sqrt(tmp[0]);
-    std::vector<const double*> dv(l + 1);
-    for (int i = 0; i < l; i++) dv[i] = m->Xdot[i];
-    dv[l] = m->XM;
-    std::vector<double> dn(l + 1);
-    if ((rc = diffnorms2(c, m->XA, dv, dn.data()))) return rc;
+    if (vecops_split()) {
+      std::vector<const double*> dv(l + 1);
+      for (int i = 0; i < l; i++) dv[i] = m->Xdot[i];
+      dv[l] = m->XM;
+      if ((rc = diffnorms2(c, m->XA, dv, dn.data()))) return rc;
+    }
+    m->t_solver[4] += lapse.lap();
     const double dnorm = sqrt(dn[l]);
     double dminnorm = sqrt(dn[0]);
     for (int i = 1; i < l; i++) dminnorm = std::min(dminnorm, sqrt(dn[i]));
@@ -561,10 +760,14 @@ static int ngmres_solve(dmk_ctx* c) {
       if (fminnorm > fnorm) fminnorm = fnorm;
       double *xs, *fs;
       if ((rc = hist_vec(c, m->Xdot, ivec, &xs)) || (rc = hist_vec(c, m->Fdot, ivec, &fs))) return rc;
+      DMK_CUDA_CHECK(cudaStreamSynchronize(c->stream)); m->t_solver[8] += lapse.lap();      // selection + allocation of history slots
       if ((rc = copy_field(c, xs, X)) || (rc = copy_field(c, fs, Fv))) return rc;
     }
+    DMK_CUDA_CHECK(cudaStreamSynchronize(c->stream)); m->t_solver[9] += lapse.lap();        // history copies
     it = k;
+    m->t_solver[7] += 1.0;
     if ((rc = converged(c, &reason))) return rc;
+    m->t_solver[10] += lapse.lap();                                                          // convergence test
     if (reason) break;
   }
   if (!reason) reason = -5;
@@ -841,6 +1044,7 @@ extern "C" int dmk_mech_get(dmk_ctx* c, const char* what, double* out, size_t n)
   if (w == "scheme") { out[0] = m->scheme; return DMK_OK; }
   if (w == "total_iter") { out[0] = m->total_iter; return DMK_OK; }
   if (w == "snes_its") { out[0] = m->snes_its; return DMK_OK; }
+  if (w == "solver_seconds") { if (n < 12) { dmk_set_error("need 12 doubles"); return DMK_ERR_ARG; } for (int k = 0; k < 12; k++) out[k] = m->t_solver[k]; return DMK_OK; }
   if (w == "snes_reason") { out[0] = m->snes_reason; return DMK_OK; }
   if (w == "minmax_cells") { if (n < 2) { dmk_set_error("need 2 doubles"); return DMK_ERR_ARG; } if ((rc = ensure_tangent(c))) return rc; out[0] = (double)m->minmax_cells[0]; out[1] = (double)m->minmax_cells[1]; return DMK_OK; }
   if (w == "F_av") {
