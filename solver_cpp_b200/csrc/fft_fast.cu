@@ -92,17 +92,34 @@ __global__ void __launch_bounds__(NT, MINB) dmk_fast_xc2r_kernel(const double2* 
   const int np = min(NP, npairs - pair0);
   constexpr int PER = NXR * DMK_NC;
   // Z_k = A_k + i B_k, Z_{N-k} = conj(A_k) + i conj(B_k), natural order
-  for (int t = threadIdx.x; t < np * PER; t += blockDim.x) {
-    const int sub = t / PER, r = t - sub * PER;
-    const int k = r / DMK_NC, c = r - k * DMK_NC;
-    const int ra = 2 * (pair0 + sub);
-    const double2* ia = in + (size_t)ra * PER;
-    double2 A = __ldg(ia + r);
-    double2 Bv = (ra + 1 < nrows) ? __ldg(ia + PER + r) : make_double2(0.0, 0.0);
-    const bool selfconj = (k == 0) || (2 * k == N);
-    if (selfconj) { A.y = 0.0; Bv.y = 0.0; }             // FFTW c2r ignores these imaginary parts
-    s[(sub * N + k) * B + c] = make_double2(A.x - Bv.y, A.y + Bv.x);
-    if (!selfconj) s[(sub * N + N - k) * B + c] = make_double2(A.x + Bv.y, Bv.x - A.y);
+  // UL elements per thread and trip, their 2 UL loads issued together: with one element per trip a thread had two loads in flight
+  // and the pass was bound by load latency (ncu: long_scoreboard the top stall, 51 % of DRAM throughput with 27 warps per SM)
+  constexpr int UL = 4;
+  for (int t0 = threadIdx.x; t0 < np * PER; t0 += UL * blockDim.x) {
+    double2 A[UL], Bv[UL];
+#pragma unroll
+    for (int u = 0; u < UL; u++) {
+      const int t = t0 + u * blockDim.x;
+      if (t < np * PER) {
+        const int sub = t / PER, r = t - sub * PER;
+        const int ra = 2 * (pair0 + sub);
+        const double2* ia = in + (size_t)ra * PER;
+        A[u] = __ldg(ia + r);
+        Bv[u] = (ra + 1 < nrows) ? __ldg(ia + PER + r) : make_double2(0.0, 0.0);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < UL; u++) {
+      const int t = t0 + u * blockDim.x;
+      if (t < np * PER) {
+        const int sub = t / PER, r = t - sub * PER;
+        const int k = r / DMK_NC, c = r - k * DMK_NC;
+        const bool selfconj = (k == 0) || (2 * k == N);
+        if (selfconj) { A[u].y = 0.0; Bv[u].y = 0.0; }   // FFTW c2r ignores these imaginary parts
+        s[(sub * N + k) * B + c] = make_double2(A[u].x - Bv[u].y, A[u].y + Bv[u].x);
+        if (!selfconj) s[(sub * N + N - k) * B + c] = make_double2(A[u].x + Bv[u].y, Bv[u].x - A[u].y);
+      }
+    }
   }
   __syncthreads();
   auto lds = [&](int sub, int p, int col) { return s[(sub * N + p) * B + col]; };
@@ -118,7 +135,22 @@ __global__ void __launch_bounds__(NT, MINB) dmk_fast_xc2r_kernel(const double2* 
   if constexpr (R3 > 1) {
     fstage<N, R2, R3, B, true, false>(np, B, tw, lds, sts);
     __syncthreads();
-    fstage<N, R3, 1, B, true, false>(np, B, tw, lds, stg);
+    // Last stage of a three-stage network: butterfly b holds the frequencies b / R2 + R1 (b % R2) + R1 R2 q, so neighbouring
+    // butterflies stored 72-byte runs R1 * 72 bytes apart (ncu: mio_throttle the second stall reason, 51 % of DRAM throughput).
+    // Item g of the stage therefore takes butterfly R2 (g % R1) + g / R1, whose outputs are the frequencies g + (N / R3) q:
+    // a warp's stores are one contiguous run again, at the price of a two-way bank conflict where two butterflies' reads meet.
+    auto lds3 = [&](int sub, int p, int col) {
+      const int g = p / R3, m = p - g * R3;
+      return s[(sub * N + (R2 * (g % R1) + g / R1) * R3 + m) * B + col];
+    };
+    auto stg3 = [&](int sub, int p, int col, double2 v) {
+      const int g = p / R3, q = p - g * R3;
+      const int ra = 2 * (pair0 + sub);
+      double* a = out + (size_t)ra * NE + (g + (N / R3) * q) * DMK_NC + col;
+      a[0] = v.x * scale;
+      if (ra + 1 < nrows) a[NE] = v.y * scale;
+    };
+    fstage<N, R3, 1, B, true, false>(np, B, tw, lds3, stg3);
   } else {
     fstage<N, R2, 1, B, true, false>(np, B, tw, lds, stg);
   }
@@ -210,7 +242,13 @@ int dmk_fast_xpass_c2r(const double2* in, double* out, const DmkFftPlan& pl, int
     case 32: return launch_xc2r<DmkFastPlan<8, 4, 1>, 4, 144, 4>(in, out, pl, nrows, scale, st);
     case 64: return launch_xc2r<DmkFastPlan<8, 8, 1>, 2, 144, 4>(in, out, pl, nrows, scale, st);
     case 128: return launch_xc2r<DmkFastPlan<16, 8, 1>, 2, 144, 4>(in, out, pl, nrows, scale, st);
-    case 256: return launch_xc2r<DmkFastPlan<8, 8, 4>, 1, 144, 6>(in, out, pl, nrows, scale, st);
+    case 256: {
+      static const int v = [] { const char* e = getenv("DMK_XC2R_PLAN"); return e ? atoi(e) : 16; }();    // comparison runs (tools/gpu_call26.sh: 0.505 ms <8,8,4> x 6 CTAs, 0.44 x 5, 0.43 <16,16,1> x 4)
+      if (v == 16) return launch_xc2r<DmkFastPlan<16, 16, 1>, 1, 144, 4>(in, out, pl, nrows, scale, st);
+      if (v == 163) return launch_xc2r<DmkFastPlan<16, 16, 1>, 1, 144, 3>(in, out, pl, nrows, scale, st);
+      if (v == 5) return launch_xc2r<DmkFastPlan<8, 8, 4>, 1, 144, 5>(in, out, pl, nrows, scale, st);
+      return launch_xc2r<DmkFastPlan<8, 8, 4>, 1, 144, 6>(in, out, pl, nrows, scale, st);
+    }
     case 512: return launch_xc2r<DmkFastPlan<8, 8, 8>, 1, 288, 2>(in, out, pl, nrows, scale, st);
     default: *done = false; return DMK_OK;
   }
