@@ -16,10 +16,25 @@ def fletcher32(data):
     """checksum of HDF5's fletcher32 filter (H5_checksum_fletcher32 of libhdf5: big-endian 16-bit words, the two running
     sums folded to 16 bits after every 360 words, an odd trailing byte taken as the high byte of a last word)"""
     n = len(data) // 2
-    w = np.frombuffer(data, '>u2', n).astype(np.int64)
+    w16 = np.frombuffer(data, '>u2', n)
+    nfull = n // 360
+    # per-block sums of all full blocks at once, slab by slab (no int64 copy of the whole data set); the folding recurrence
+    # over the blocks stays sequential, on two numbers per block
+    S1, S2 = np.empty(nfull, np.int64), np.empty(nfull, np.int64)
+    wts = np.arange(360, 0, -1, dtype=np.int64)
+    SLAB = 1 << 14
+    for b0 in range(0, nfull, SLAB):
+        blk = w16[b0 * 360:min(b0 + SLAB, nfull) * 360].reshape(-1, 360).astype(np.int64)
+        S1[b0:b0 + len(blk)] = blk.sum(1)
+        S2[b0:b0 + len(blk)] = blk @ wts
     s1 = s2 = 0
-    for a in range(0, n, 360):
-        blk = w[a:a + 360]
+    for a1, a2 in zip(S1.tolist(), S2.tolist()):
+        s2 += 360 * s1 + a2
+        s1 += a1
+        s1 = (s1 & 0xFFFF) + (s1 >> 16)
+        s2 = (s2 & 0xFFFF) + (s2 >> 16)
+    if n % 360:
+        blk = w16[nfull * 360:].astype(np.int64)
         m = blk.size
         s2 += m * s1 + int((blk * np.arange(m, 0, -1)).sum())
         s1 += int(blk.sum())
@@ -457,7 +472,9 @@ class H5Writer:
         if self.closed:
             raise ValueError('H5Writer: file already written')
         raw = a.tobytes()
-        chunked = bool(checksum) and len(raw) > 0 and a.ndim > 0
+        # HDF5 caps a chunk at 4 GiB (32-bit chunk size in the B-tree key): larger datasets (F at 512^3 is 9.7 GB) are stored
+        # contiguous, without the checksum, instead of failing at close() after all raw data has been streamed
+        chunked = bool(checksum) and 0 < len(raw) < (1 << 32) - 8 and a.ndim > 0
         if chunked:
             raw += struct.pack('<I', fletcher32(raw))
         n = _Node((a.shape, a.dtype, len(raw), self.pos if raw else UNDEF, chunked))
