@@ -32,7 +32,7 @@ typedef struct dmk_ctx dmk_ctx;
 #define DMK_MAX_STATE (3 * DMK_MAX_SL + DMK_MAX_TW)
 #define DMK_MAX_PHASES 8
 
-enum { DMK_LAW_NONE = 0, DMK_LAW_ISOTROPIC = 1, DMK_LAW_PHENOPOWERLAW = 2, DMK_LAW_DISLOTWIN = 3 };
+enum { DMK_LAW_NONE = 0, DMK_LAW_ISOTROPIC = 1, DMK_LAW_PHENOPOWERLAW = 2, DMK_LAW_DISLOTWIN = 3, DMK_LAW_KINEHARDENING = 4 };
 enum { DMK_DERIVATIVE_CONTINUOUS = 0, DMK_DERIVATIVE_CENTRAL_DIFF = 1, DMK_DERIVATIVE_FWBW_DIFF = 2 };
 enum { DMK_DIVCORR_NONE = 0, DMK_DIVCORR_SIZE = 1, DMK_DIVCORR_SIZE_GRID = 2 };
 
@@ -86,6 +86,10 @@ typedef struct {
   double dt_b_tw[DMK_MAX_TW], dt_t_tw[DMK_MAX_TW], dt_r[DMK_MAX_TW];
   int dt_pair[DMK_MAX_TW][2];              /* 0-based slip pair nucleating twin i (crystal.f90:82-95) */
   double dt_C66_tw[DMK_MAX_TW][36];
+  /* kinehardening (phase_mechanical_plastic_kinehardening.f90:11-40); shares dot_gamma_0_sl, n_sl_exp, xi_inf_sl, h_sl_sl and the
+   * (non-)Schmid tensors with phenopowerlaw.  State: xi | chi | gamma (n_sl each, rates from dotState) followed by
+   * sgn_gamma | chi_flip | gamma_flip (n_sl each, moved only by the deltaState jump): n_state = 6 n_sl, n_sl <= DMK_MAX_STATE / 6 */
+  double kh_chi_inf[DMK_MAX_SL], kh_h_0_xi[DMK_MAX_SL], kh_h_0_chi[DMK_MAX_SL], kh_h_inf_xi[DMK_MAX_SL], kh_h_inf_chi[DMK_MAX_SL];
 } dmk_phase;
 
 /* collective callbacks for world_size > 1 (all stream-ordered on the context's stream; device pointers).

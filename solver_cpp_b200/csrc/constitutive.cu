@@ -268,6 +268,7 @@ static int persistent_grid(K kernel, long long n) {
     else if (law == DMK_LAW_PHENOPOWERLAW && nstate <= 24) KERNEL<DMK_LAW_PHENOPOWERLAW, 24, 0><<<persistent_grid(KERNEL<DMK_LAW_PHENOPOWERLAW, 24, 0>, n), DMK_PT_THREADS, 0, st>>> __VA_ARGS__; \
     else if (law == DMK_LAW_PHENOPOWERLAW && nstate <= 48) KERNEL<DMK_LAW_PHENOPOWERLAW, 48, 0><<<persistent_grid(KERNEL<DMK_LAW_PHENOPOWERLAW, 48, 0>, n), DMK_PT_THREADS, 0, st>>> __VA_ARGS__; \
     else if (law == DMK_LAW_PHENOPOWERLAW) KERNEL<DMK_LAW_PHENOPOWERLAW, 2 * DMK_MAX_SYS, 0><<<persistent_grid(KERNEL<DMK_LAW_PHENOPOWERLAW, 2 * DMK_MAX_SYS, 0>, n), DMK_PT_THREADS, 0, st>>> __VA_ARGS__; \
+    else if (law == DMK_LAW_KINEHARDENING) KERNEL<DMK_LAW_KINEHARDENING, DMK_MAX_STATE, 0><<<persistent_grid(KERNEL<DMK_LAW_KINEHARDENING, DMK_MAX_STATE, 0>, n), DMK_PT_THREADS, 0, st>>> __VA_ARGS__; \
     else if (law == DMK_LAW_DISLOTWIN && nstate <= 48) KERNEL<DMK_LAW_DISLOTWIN, 48, 36><<<persistent_grid(KERNEL<DMK_LAW_DISLOTWIN, 48, 36>, n), DMK_PT_THREADS, 0, st>>> __VA_ARGS__; \
     else KERNEL<DMK_LAW_DISLOTWIN, DMK_MAX_STATE, DMK_MAX_DEP><<<persistent_grid(KERNEL<DMK_LAW_DISLOTWIN, DMK_MAX_STATE, DMK_MAX_DEP>, n), DMK_PT_THREADS, 0, st>>> __VA_ARGS__; \
   } while (0)
@@ -279,6 +280,7 @@ static int persistent_grid(K kernel, long long n) {
     else if (law == DMK_LAW_PHENOPOWERLAW && nstate <= 24) KERNEL<DMK_LAW_PHENOPOWERLAW, 24, 0> __VA_ARGS__;    \
     else if (law == DMK_LAW_PHENOPOWERLAW && nstate <= 48) KERNEL<DMK_LAW_PHENOPOWERLAW, 48, 0> __VA_ARGS__;    \
     else if (law == DMK_LAW_PHENOPOWERLAW) KERNEL<DMK_LAW_PHENOPOWERLAW, 2 * DMK_MAX_SYS, 0> __VA_ARGS__;       \
+    else if (law == DMK_LAW_KINEHARDENING) KERNEL<DMK_LAW_KINEHARDENING, DMK_MAX_STATE, 0> __VA_ARGS__;         \
     else if (law == DMK_LAW_DISLOTWIN && nstate <= 48) KERNEL<DMK_LAW_DISLOTWIN, 48, 36> __VA_ARGS__;           \
     else KERNEL<DMK_LAW_DISLOTWIN, DMK_MAX_STATE, DMK_MAX_DEP> __VA_ARGS__;                                     \
   } while (0)
@@ -382,7 +384,7 @@ static void q_host(const double* C66, const double* pv, double* Q) {
 }
 
 static int check_phase(const dmk_phase& p, int idx) {
-  if (p.law < DMK_LAW_NONE || p.law > DMK_LAW_DISLOTWIN) { dmk_set_error("phase %d: unknown plastic law %d", idx, p.law); return DMK_ERR_ARG; }
+  if (p.law < DMK_LAW_NONE || p.law > DMK_LAW_KINEHARDENING) { dmk_set_error("phase %d: unknown plastic law %d", idx, p.law); return DMK_ERR_ARG; }
   if (p.n_sl < 0 || p.n_sl > DMK_MAX_SL || p.n_tw < 0 || p.n_tw > DMK_MAX_TW) { dmk_set_error("phase %d: too many slip/twin systems", idx); return DMK_ERR_UNSUPPORTED; }
   if (p.law == DMK_LAW_ISOTROPIC && p.iso_dilatation) { dmk_set_error("phase %d: isotropic plasticity with dilatation (Li != 0) is not offered on the device path", idx); return DMK_ERR_UNSUPPORTED; }
   if (p.law == DMK_LAW_DISLOTWIN && p.dt_gamma_0_sb != 0.0) { dmk_set_error("phase %d: dislotwin shear banding is not offered on the device path", idx); return DMK_ERR_UNSUPPORTED; }
@@ -390,6 +392,10 @@ static int check_phase(const dmk_phase& p, int idx) {
   if (p.law == DMK_LAW_ISOTROPIC) expect = 1;
   else if (p.law == DMK_LAW_PHENOPOWERLAW) expect = 2 * (p.n_sl + p.n_tw);
   else if (p.law == DMK_LAW_DISLOTWIN) expect = 3 * p.n_sl + p.n_tw;
+  else if (p.law == DMK_LAW_KINEHARDENING) {
+    if (p.n_sl < 1 || 6 * p.n_sl > DMK_MAX_STATE || p.n_tw != 0) { dmk_set_error("phase %d: kinehardening needs 1..%d slip systems and no twin systems", idx, DMK_MAX_STATE / 6); return DMK_ERR_UNSUPPORTED; }
+    expect = 6 * p.n_sl;
+  }
   if (p.n_state != expect) { dmk_set_error("phase %d: n_state %d, expected %d", idx, p.n_state, expect); return DMK_ERR_ARG; }
   return DMK_OK;
 }

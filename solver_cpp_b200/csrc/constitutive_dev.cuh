@@ -332,6 +332,91 @@ DMK_HD __forceinline__ void pheno_dotState(const DmkPt<LAW, NS, ND>& p, const do
   }
 }
 
+// ================================================================================================ kinehardening
+// phase_mechanical_plastic_kinehardening.f90: kinetics :433-472, LpAndItsTangent :258-295, dotState :301-341, deltaState :347-379.
+// state: xi[ns] | chi[ns] | gamma[ns]   (integrated: n_dot = 3 ns)   | sgn_gamma[ns] | chi_flip[ns] | gamma_flip[ns] (deltaState only)
+template <int LAW, int NS, int ND>
+DMK_HD __forceinline__ void kh_slip_rate(const DmkPt<LAW, NS, ND>& p, const double (&S)[6], int i, double& dg, double& ddg) {
+  const DmkDevPhase& d = *p.ph;
+  const double chi = p.st[d.p.n_sl + i];
+  const double ts = sdot(S, d.p.P_nS_pos[i]);
+  const double tp = ts - chi;
+  const double tn = (d.nonschmid ? sdot(S, d.p.P_nS_neg[i]) : -ts) + chi;
+  const double tmax = fmax(tp, tn);
+  const double n = d.p.n_sl_exp[i];
+  const int ni = d.n_sl_int[i];
+  const double ratio = tmax / p.st[i];
+  dg = ((tp > tn) ? 1.0 : -1.0) * d.p.dot_gamma_0_sl[i] * (ni ? powi(ratio, ni) : pow(ratio, n));
+  ddg = deq0(dg) ? 0.0 : dg * n / tmax;
+}
+template <int LAW, int NS, int ND>
+DMK_HD __forceinline__ void kh_Lp(const DmkPt<LAW, NS, ND>& p, const double (&S)[6], double (&Lp)[9], double* __restrict__ ddg_out) {
+  const dmk_phase& q = p.ph->p;
+#pragma unroll
+  for (int a = 0; a < 9; a++) Lp[a] = 0.0;
+  for (int i = 0; i < q.n_sl; i++) {
+    double dg, ddg;
+    kh_slip_rate(p, S, i, dg, ddg);
+#pragma unroll
+    for (int a = 0; a < 9; a++) Lp[a] += dg * q.P_sl[i][a];
+    ddg_out[i] = ddg;
+    ddg_out[DMK_MAX_SYS + i] = dg;                           // its sign selects the non-Schmid projection of the tangent (:283-287)
+  }
+}
+template <int LAW, int NS, int ND>
+DMK_HD __forceinline__ void kh_jac(const DmkPt<LAW, NS, ND>& p, double dt, const double (&G)[9], const double* __restrict__ ddg,
+                                   double (&J)[81]) {
+  const DmkDevPhase& d = *p.ph;
+  for (int i = 0; i < d.p.n_sl; i++) {
+    const double c = dt * ddg[i];
+    if (c != 0.0) {
+      const double* Qv = (ddg[DMK_MAX_SYS + i] > 0.0) ? d.Q_pos[i] : d.Q_neg[i];
+      double Q[6];
+#pragma unroll
+      for (int b = 0; b < 6; b++) Q[b] = Qv[b];
+      jac_add_system(J, c, d.p.P_sl[i], G, Q);
+    }
+  }
+}
+template <int LAW, int NS, int ND>
+DMK_HD __forceinline__ void kh_dotState(const DmkPt<LAW, NS, ND>& p, const double (&S)[6], double* __restrict__ dot) {
+  const dmk_phase& q = p.ph->p;
+  const int n = q.n_sl;
+  const double *gamma = p.st + 2 * n, *sgn = p.st + 3 * n, *chi_flip = p.st + 4 * n, *gamma_flip = p.st + 5 * n;
+  double *dot_xi = dot, *dot_chi = dot + n, *dot_gamma = dot + 2 * n;
+  for (int i = 0; i < n; i++) { double dg, ddg; kh_slip_rate(p, S, i, dg, ddg); dot_gamma[i] = fabs(dg); }
+  double sumGamma = 0.0;
+  for (int i = 0; i < n; i++) sumGamma += gamma[i];
+  for (int i = 0; i < n; i++) {
+    double hs = 0.0;
+    for (int j = 0; j < n; j++) hs += q.h_sl_sl[i][j] * dot_gamma[j];
+    const double x = sumGamma * q.kh_h_0_xi[i] / q.xi_inf_sl[i];
+    dot_xi[i] = hs * (q.kh_h_inf_xi[i] + (q.kh_h_0_xi[i] - q.kh_h_inf_xi[i] * (1.0 - x)) * exp(-x));
+    const double y = (gamma[i] - gamma_flip[i]) * q.kh_h_0_chi[i] / (q.kh_chi_inf[i] + chi_flip[i]);
+    dot_chi[i] = sgn[i] * dot_gamma[i] * (q.kh_h_inf_chi[i] + (q.kh_h_0_chi[i] - q.kh_h_inf_chi[i] * (1.0 - y)) * exp(-y));
+  }
+}
+// plastic_deltaState (phase_mechanical_plastic.f90:372-413) -> plastic_kinehardening_deltaState: where the shear direction of a
+// system flips, its sense and the back stress / shear reached at the flip are recorded.  Returns broken (a NaN jump).
+template <int LAW, int NS, int ND>
+DMK_HD __forceinline__ bool kh_deltaState(DmkPt<LAW, NS, ND>& p) {
+  const int n = p.ph->p.n_sl;
+  double *chi = p.st + n, *gamma = p.st + 2 * n, *sgn = p.st + 3 * n, *chi_flip = p.st + 4 * n, *gamma_flip = p.st + 5 * n;
+  bool nan = false;
+  double d0[DMK_MAX_STATE / 6], d1[DMK_MAX_STATE / 6], d2[DMK_MAX_STATE / 6];
+  for (int i = 0; i < n; i++) {
+    double dg, ddg;
+    kh_slip_rate(p, p.S, i, dg, ddg);
+    const double s = (fabs(dg) <= 1.0e-10) ? sgn[i] : ((dg >= 0.0 && !signbit(dg)) ? 1.0 : -1.0);     // merge(state, sign(1, dg), dEq0(dg, 1e-10))
+    if (!(fabs(s - sgn[i]) <= 0.1)) { d0[i] = s - sgn[i]; d1[i] = fabs(chi[i]) - chi_flip[i]; d2[i] = gamma[i] - gamma_flip[i]; }
+    else { d0[i] = 0.0; d1[i] = 0.0; d2[i] = 0.0; }
+    nan = nan || isnan(d0[i]) || isnan(d1[i]) || isnan(d2[i]);
+  }
+  if (nan) return true;
+  for (int i = 0; i < n; i++) { sgn[i] += d0[i]; chi_flip[i] += d1[i]; gamma_flip[i] += d2[i]; }
+  return false;
+}
+
 // ================================================================================================ isotropic
 DMK_HD __forceinline__ void deviator(const double (&S)[6], double (&dev)[9], double& sq) {
   const double tr = (S[0] + S[1] + S[2]) / 3.0;
@@ -591,6 +676,19 @@ DMK_HD __forceinline__ void dot_state(const DmkPt<LAW, NS, ND>& p, double* __res
   if constexpr (LAW == DMK_LAW_ISOTROPIC) iso_dotState(p, p.S, dot);
   else if constexpr (LAW == DMK_LAW_PHENOPOWERLAW) pheno_dotState(p, p.S, dot);
   else if constexpr (LAW == DMK_LAW_DISLOTWIN) dt_dotState(p, p.S, dot);
+  else if constexpr (LAW == DMK_LAW_KINEHARDENING) kh_dotState(p, p.S, dot);
+}
+// instantaneous state jump after a converged state integration (phase_mechanical_plastic.f90:372-413): kinehardening only; broken?
+template <int LAW, int NS, int ND>
+DMK_HD __forceinline__ bool delta_state(DmkPt<LAW, NS, ND>& p) {
+  if constexpr (LAW == DMK_LAW_KINEHARDENING) return kh_deltaState(p);
+  else return false;
+}
+// entries of the state vector the integrators move (sizeDotState); the rest changes by delta_state only
+template <int LAW, int NS, int ND>
+DMK_HD __forceinline__ int n_dot_state(const DmkPt<LAW, NS, ND>& p) {
+  if constexpr (LAW == DMK_LAW_KINEHARDENING) return 3 * p.ph->p.n_sl;
+  else return p.ph->p.n_state;
 }
 
 // ------------------------------------------------------------------------------------------------ integrateStress
@@ -626,6 +724,7 @@ DMK_HD __noinline__ bool integrate_stress(DmkPt<LAW, NS, ND>& p, const DmkNumDev
       for (int a = 0; a < 9; a++) Lp_c[a] = 0.0;
     } else if constexpr (LAW == DMK_LAW_ISOTROPIC) iso_Lp(p, S, Lp_c, iso_c, iso_dev, iso_sq);
     else if constexpr (LAW == DMK_LAW_PHENOPOWERLAW) pheno_Lp(p, S, Lp_c, ddg);
+    else if constexpr (LAW == DMK_LAW_KINEHARDENING) kh_Lp(p, S, Lp_c, ddg);
     else dt_Lp(p, S, Lp_c, ddg);
     const double atol = fmax(num.eps_rel_Lp * fmax(norm9(Lpg), norm9(Lp_c)), num.eps_abs_Lp);
 #pragma unroll
@@ -653,6 +752,7 @@ DMK_HD __noinline__ bool integrate_stress(DmkPt<LAW, NS, ND>& p, const DmkNumDev
       if constexpr (LAW == DMK_LAW_ISOTROPIC) iso_jac(p, dt, G, iso_c, iso_dev, iso_sq, J);
       else if constexpr (LAW == DMK_LAW_PHENOPOWERLAW) pheno_jac(p, dt, G, ddg, J);
       else if constexpr (LAW == DMK_LAW_DISLOTWIN) dt_jac(p, dt, G, ddg, J);
+      else if constexpr (LAW == DMK_LAW_KINEHARDENING) kh_jac(p, dt, G, ddg, J);
       if (solve9(J, res)) return true;
 #pragma unroll
       for (int a = 0; a < 9; a++) delta[a] = -res[a];
@@ -680,7 +780,7 @@ DMK_HD __noinline__ bool integrate_stress(DmkPt<LAW, NS, ND>& p, const DmkNumDev
 template <int LAW, int NS, int ND>
 DMK_HD __forceinline__ bool integrate_state_FPI(DmkPt<LAW, NS, ND>& p, const DmkNumDev& num, const double (&F)[9],
                                                     const double (&Fp0)[9], const double* __restrict__ state0, double dt, DmkCnt& cnt) {
-  const int n = p.ph->p.n_state;
+  const int n = n_dot_state(p);                       // 1:sizeDotState
   double dot[NS > 0 ? NS : 1], last1[NS > 0 ? NS : 1], last2[NS > 0 ? NS : 1];
   bool broken = true;
   for (int i = 0; i < n; i++) { dot[i] = 0.0; last1[i] = 0.0; last2[i] = 0.0; }
@@ -711,7 +811,7 @@ DMK_HD __forceinline__ bool integrate_state_FPI(DmkPt<LAW, NS, ND>& p, const Dmk
       p.st[i] -= r;
       if (!(fabs(r) <= fmax(p.ph->p.atol[i], num.eps_rel_state * fabs(p.st[i])))) conv = false;
     }
-    if (conv) { broken = false; break; }
+    if (conv) { broken = delta_state(p); break; }     // :661-664
   }
   return broken;
 }
@@ -728,7 +828,7 @@ template <int LAW, int NS, int ND>
 DMK_HD __noinline__ bool integrate_state_other(DmkPt<LAW, NS, ND>& p, const DmkNumDev& num, const double (&F_0)[9], const double (&F)[9],
                                                const double (&Fp0)[9], const double* __restrict__ state0, double dt, DmkCnt& cnt) {
   constexpr int NSX = NS > 0 ? NS : 1;
-  const int n = p.ph->p.n_state;
+  const int n = n_dot_state(p);
   double dot[NSX];
   for (int i = 0; i < n; i++) dot[i] = 0.0;
   dot_state(p, dot);
@@ -740,6 +840,7 @@ DMK_HD __noinline__ bool integrate_state_other(DmkPt<LAW, NS, ND>& p, const DmkN
   if (num.integrator == DMK_INTEG_EULER || num.integrator == DMK_INTEG_ADAPTIVE_EULER) {
     double r[NSX];
     for (int i = 0; i < n; i++) { r[i] = -dot[i] * 0.5 * dt; p.st[i] = state0[i] + dot[i] * dt; }
+    if (delta_state(p)) return true;                                         // :717-719, :765-767
     if (integrate_stress(p, num, F, Fp0, dt, cnt)) return true;
     if (num.integrator == DMK_INTEG_EULER) return false;
     dot_state(p, dot);
@@ -784,6 +885,7 @@ DMK_HD __noinline__ bool integrate_state_other(DmkPt<LAW, NS, ND>& p, const DmkN
     for (int i = 0; i < n; i++) { double s = 0.0; for (int m = 0; m <= ns; m++) s += rk[m][i] * DB5[m]; r[i] = s * dt; }
     if (!converged(r)) return true;
   }
+  if (delta_state(p)) return true;                                           // :924-926
   return integrate_stress(p, num, F, Fp0, dt, cnt);
 }
 

@@ -206,6 +206,45 @@ void make_phase(const std::string& name, const YamlNode& cfg, double T, dmk_phas
     }
     state_init = xi0_sl; state_init.insert(state_init.end(), xi0_tw.begin(), xi0_tw.end()); state_init.resize(2 * (size_t)(ns + nt), 0.0);
     atol.assign((size_t)(ns + nt), opt_d(pl, "atol_xi", 1.0)); atol.resize(2 * (size_t)(ns + nt), opt_d(pl, "atol_gamma", 1.0e-6));
+  } else if (kind == "kinehardening") {                // plastic_kinehardening_init, phase_mechanical_plastic_kinehardening.f90:72-252
+    const YamlNode& pl = *plp;
+    ph.law = DMK_LAW_KINEHARDENING;
+    const std::vector<int> N_sl = pl.has("N_sl") ? pl.get("N_sl")->as_ints() : std::vector<int>();
+    const int ns = total(N_sl);
+    if (ns < 1 || 6 * ns > DMK_MAX_STATE) bad(where + ": kinehardening needs 1.." + std::to_string(DMK_MAX_STATE / 6) + " slip systems on the device path");
+    ph.n_sl = ns; ph.n_tw = 0;
+    std::vector<double> P((size_t)ns * 9);
+    crystal_check(dmk_crystal_schmid_slip(lat, N_sl.data(), (int)N_sl.size(), P.data()), where);
+    memcpy(ph.P_sl, P.data(), P.size() * sizeof(double));
+    if (lattice == "cI") {
+      const std::vector<double> a_nS = pl.has("a_nonSchmid_110") ? pl.get("a_nonSchmid_110")->as_doubles() : std::vector<double>();
+      const double none = 0.0;
+      crystal_check(dmk_crystal_schmid_slip_ns(lat, N_sl.data(), (int)N_sl.size(), a_nS.empty() ? &none : a_nS.data(), (int)a_nS.size(), +1, P.data()), where);
+      memcpy(ph.P_nS_pos, P.data(), P.size() * sizeof(double));
+      crystal_check(dmk_crystal_schmid_slip_ns(lat, N_sl.data(), (int)N_sl.size(), a_nS.empty() ? &none : a_nS.data(), (int)a_nS.size(), -1, P.data()), where);
+      memcpy(ph.P_nS_neg, P.data(), P.size() * sizeof(double));
+    } else {
+      memcpy(ph.P_nS_pos, P.data(), P.size() * sizeof(double));
+      for (int a = 0; a < ns; a++) for (int k = 0; k < 9; k++) ph.P_nS_neg[a][k] = -P[(size_t)a * 9 + k];
+    }
+    const std::vector<double> h = need(pl, "h_sl-sl", where).as_doubles();
+    std::vector<double> M((size_t)ns * ns);
+    crystal_check(dmk_crystal_interaction("sl-sl", lat, N_sl.data(), (int)N_sl.size(), N_sl.data(), (int)N_sl.size(), h.data(), (int)h.size(), M.data()), where);
+    for (int a = 0; a < ns; a++) for (int b = 0; b < ns; b++) ph.h_sl_sl[a][b] = M[(size_t)a * ns + b];
+    put(ph.dot_gamma_0_sl, fam(pl, "dot_gamma_0", N_sl, nullptr, where), DMK_MAX_SL, "dot_gamma_0");
+    put(ph.n_sl_exp, fam(pl, "n", N_sl, nullptr, where), DMK_MAX_SL, "n");
+    put(ph.xi_inf_sl, fam(pl, "xi_inf", N_sl, nullptr, where), DMK_MAX_SL, "xi_inf");
+    put(ph.kh_chi_inf, fam(pl, "chi_inf", N_sl, nullptr, where), DMK_MAX_SL, "chi_inf");
+    put(ph.kh_h_0_xi, fam(pl, "h_0_xi", N_sl, nullptr, where), DMK_MAX_SL, "h_0_xi");
+    put(ph.kh_h_0_chi, fam(pl, "h_0_chi", N_sl, nullptr, where), DMK_MAX_SL, "h_0_chi");
+    put(ph.kh_h_inf_xi, fam(pl, "h_inf_xi", N_sl, nullptr, where), DMK_MAX_SL, "h_inf_xi");
+    put(ph.kh_h_inf_chi, fam(pl, "h_inf_chi", N_sl, nullptr, where), DMK_MAX_SL, "h_inf_chi");
+    state_init = fam(pl, "xi_0", N_sl, nullptr, where);
+    for (int a = 0; a < ns; a++)
+      if (!(ph.dot_gamma_0_sl[a] > 0.0 && ph.n_sl_exp[a] > 0.0 && state_init[a] > 0.0 && ph.xi_inf_sl[a] > 0.0 && ph.kh_chi_inf[a] > 0.0))
+        bad(where + ": kinehardening: dot_gamma_0, n, xi_0, xi_inf, chi_inf must be positive");        // :164-169
+    state_init.resize(6 * (size_t)ns, 0.0);
+    atol.assign(2 * (size_t)ns, opt_d(pl, "atol_xi", 1.0)); atol.resize(3 * (size_t)ns, opt_d(pl, "atol_gamma", 1.0e-6)); atol.resize(6 * (size_t)ns, 0.0);
   } else if (kind == "dislotwin") {
     const YamlNode& pl = *plp;
     ph.law = DMK_LAW_DISLOTWIN;

@@ -89,13 +89,14 @@ DMK_HD __forceinline__ void machine_substep(DmkMachine<LAW, NS, ND>& m, const Dm
 #pragma unroll
   for (int a = 0; a < 9; a++) m.F[a] = m.F0[a] + m.step * (m.Ft[a] - m.F0in[a]);
   m.dtsub = m.step * Dt;
-  // integrateStateFPI, head
-  for (int i = 0; i < ns; i++) { m.dot[i] = 0.0; m.last1[i] = 0.0; m.last2[i] = 0.0; }
+  // integrateStateFPI, head (over the integrated part of the state, 1:sizeDotState)
+  const int nd = n_dot_state(p);
+  for (int i = 0; i < nd; i++) { m.dot[i] = 0.0; m.last1[i] = 0.0; m.last2[i] = 0.0; }
   dot_state(p, m.dot);
   bool nan = false;
-  for (int i = 0; i < ns; i++) nan = nan || isnan(m.dot[i]);
+  for (int i = 0; i < nd; i++) nan = nan || isnan(m.dot[i]);
   if (nan) { m.converged = false; m.state = M_SUBSTEP; return; }     // broken
-  for (int i = 0; i < ns; i++) p.st[i] = m.state0[i] + m.dot[i] * m.dtsub;
+  for (int i = 0; i < nd; i++) p.st[i] = m.state0[i] + m.dot[i] * m.dtsub;
   m.it = 1;
   m.state = M_STRESS_PRO;
 }
@@ -104,7 +105,7 @@ DMK_HD __forceinline__ void machine_substep(DmkMachine<LAW, NS, ND>& m, const Dm
 template <int LAW, int NS, int ND>
 DMK_HD __forceinline__ void machine_stress_prologue(DmkMachine<LAW, NS, ND>& m, const DmkNumDev& num, DmkCnt& cnt) {
   DmkPt<LAW, NS, ND>& p = m.p;
-  const int ns = p.ph->p.n_state;
+  const int ns = n_dot_state(p);
   if (m.it > num.N_iter_state_max) { m.converged = true; m.state = M_SUBSTEP; return; }   // loop ran out with broken = .false. (as in the reference)
   cnt.state_iter++;
   for (int i = 0; i < ns; i++) { m.last2[i] = (m.it > 1) ? m.last1[i] : 0.0; m.last1[i] = m.dot[i]; }
@@ -140,6 +141,7 @@ DMK_HD __forceinline__ void machine_lp_iteration(DmkMachine<LAW, NS, ND>& m, con
     for (int a = 0; a < 9; a++) Lp_c[a] = 0.0;
   } else if constexpr (LAW == DMK_LAW_ISOTROPIC) iso_Lp(p, m.S, Lp_c, iso_c, iso_dev, iso_sq);
   else if constexpr (LAW == DMK_LAW_PHENOPOWERLAW) pheno_Lp(p, m.S, Lp_c, m.ddg);
+  else if constexpr (LAW == DMK_LAW_KINEHARDENING) kh_Lp(p, m.S, Lp_c, m.ddg);
   else dt_Lp(p, m.S, Lp_c, m.ddg);
   const double atol = fmax(num.eps_rel_Lp * fmax(norm9(m.Lpg), norm9(Lp_c)), num.eps_abs_Lp);
 #pragma unroll
@@ -167,6 +169,7 @@ DMK_HD __forceinline__ void machine_lp_iteration(DmkMachine<LAW, NS, ND>& m, con
     if constexpr (LAW == DMK_LAW_ISOTROPIC) iso_jac(p, dt, G, iso_c, iso_dev, iso_sq, J);
     else if constexpr (LAW == DMK_LAW_PHENOPOWERLAW) pheno_jac(p, dt, G, m.ddg, J);
     else if constexpr (LAW == DMK_LAW_DISLOTWIN) dt_jac(p, dt, G, m.ddg, J);
+    else if constexpr (LAW == DMK_LAW_KINEHARDENING) kh_jac(p, dt, G, m.ddg, J);
     if (solve9(J, res)) { m.converged = false; m.state = M_SUBSTEP; return; }
 #pragma unroll
     for (int a = 0; a < 9; a++) m.delta[a] = -res[a];
@@ -179,7 +182,7 @@ DMK_HD __forceinline__ void machine_lp_iteration(DmkMachine<LAW, NS, ND>& m, con
 template <int LAW, int NS, int ND>
 DMK_HD __forceinline__ void machine_stress_epilogue(DmkMachine<LAW, NS, ND>& m, const DmkNumDev& num) {
   DmkPt<LAW, NS, ND>& p = m.p;
-  const int ns = p.ph->p.n_state;
+  const int ns = n_dot_state(p);
   double invFp_new[9], Fp_new[9], t1[9], Sm[9], t2[9];
   mm3(m.invFp, m.B, invFp_new);
   if (invert33(invFp_new, Fp_new)) { m.converged = false; m.state = M_SUBSTEP; return; }
@@ -212,7 +215,7 @@ DMK_HD __forceinline__ void machine_stress_epilogue(DmkMachine<LAW, NS, ND>& m, 
     p.st[i] -= r;
     if (!(fabs(r) <= fmax(p.ph->p.atol[i], num.eps_rel_state * fabs(p.st[i])))) conv = false;
   }
-  if (conv) { m.converged = true; m.state = M_SUBSTEP; return; }
+  if (conv) { m.converged = !delta_state(p); m.state = M_SUBSTEP; return; }     // :661-664
   m.it++;
   m.state = M_STRESS_PRO;
 }

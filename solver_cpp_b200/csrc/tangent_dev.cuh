@@ -77,6 +77,13 @@ DMK_HD __noinline__ void full_dLp_dMp(DmkPt<LAW, NS, ND>& p, double* __restrict_
         for (int a = 0; a < 9; a++) for (int b = 0; b < 9; b++) dM[9 * a + b] += ddg * d.p.P_tw[i][a] * d.p.P_tw[i][b];
       }
     }
+  } else if constexpr (LAW == DMK_LAW_KINEHARDENING) {           // phase_mechanical_plastic_kinehardening.f90:258-295
+    for (int i = 0; i < d.p.n_sl; i++) {
+      double dg, ddg;
+      kh_slip_rate(p, p.S, i, dg, ddg);
+      const double* PnS = (dg > 0.0) ? d.p.P_nS_pos[i] : d.p.P_nS_neg[i];
+      for (int a = 0; a < 9; a++) for (int b = 0; b < 9; b++) dM[9 * a + b] += ddg * d.p.P_sl[i][a] * PnS[b];
+    }
   } else if constexpr (LAW == DMK_LAW_DISLOTWIN) {
     const int ns = d.p.n_sl, nt = d.p.n_tw;
     double dgs[DMK_MAX_SL];

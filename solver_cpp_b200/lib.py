@@ -60,6 +60,8 @@ class Phase(C.Structure):
         ('dt_n0_sl', _d(MAX_SL, 3)), ('dt_forest', _d(MAX_SL, MAX_SL)),
         ('dt_b_tw', _d(MAX_TW)), ('dt_t_tw', _d(MAX_TW)), ('dt_r', _d(MAX_TW)),
         ('dt_pair', (C.c_int * 2) * MAX_TW), ('dt_C66_tw', _d(MAX_TW, 36)),
+        ('kh_chi_inf', _d(MAX_SL)), ('kh_h_0_xi', _d(MAX_SL)), ('kh_h_0_chi', _d(MAX_SL)), ('kh_h_inf_xi', _d(MAX_SL)),
+        ('kh_h_inf_chi', _d(MAX_SL)),
     ]
 
 

@@ -16,7 +16,7 @@ from . import lib as L
 
 T_ROOM = 293.15                # constants.f90:12
 K_B = 1.380649e-23             # constants.f90:13
-LAW_NONE, LAW_ISOTROPIC, LAW_PHENOPOWERLAW, LAW_DISLOTWIN = 0, 1, 2, 3
+LAW_NONE, LAW_ISOTROPIC, LAW_PHENOPOWERLAW, LAW_DISLOTWIN, LAW_KINEHARDENING = 0, 1, 2, 3, 4
 
 
 def _ia(v):
@@ -233,6 +233,39 @@ def make_phase(cfg, T=T_ROOM):
         state_init = np.concatenate([xi0_sl, xi0_tw, np.zeros(ns), np.zeros(nt)])
         atol = np.concatenate([np.full(ns + nt, float(pl.get('atol_xi', 1.0))),
                                np.full(ns + nt, float(pl.get('atol_gamma', 1.0e-6)))])
+    elif kind == 'kinehardening':                    # plastic_kinehardening_init, phase_mechanical_plastic_kinehardening.f90:72-252
+        ph.law = LAW_KINEHARDENING
+        N_sl = list(pl.get('N_sl', []))
+        ns = int(np.sum(N_sl))
+        if ns == 0:
+            raise L.DmkError('kinehardening without slip systems')
+        if 6 * ns > L.MAX_STATE:
+            raise L.DmkError('kinehardening: at most %d slip systems on the device path' % (L.MAX_STATE // 6))
+        ph.n_sl, ph.n_tw = ns, 0
+        P = schmid_slip(lattice, N_sl)
+        _set(ph.P_sl, P)
+        if lattice == 'cI':
+            a_nS = pl.get('a_nonSchmid_110', [])
+            _set(ph.P_nS_pos, schmid_slip(lattice, N_sl, a_nS, +1))
+            _set(ph.P_nS_neg, schmid_slip(lattice, N_sl, a_nS, -1))
+        else:
+            _set(ph.P_nS_pos, P)
+            _set(ph.P_nS_neg, -P)
+        _set(ph.h_sl_sl, interaction('sl-sl', lattice, N_sl, N_sl, pl['h_sl-sl']))
+        _set(ph.dot_gamma_0_sl, _expand(pl['dot_gamma_0'], N_sl))
+        _set(ph.n_sl_exp, _expand(pl['n'], N_sl))
+        _set(ph.xi_inf_sl, _expand(pl['xi_inf'], N_sl))
+        _set(ph.kh_chi_inf, _expand(pl['chi_inf'], N_sl))
+        _set(ph.kh_h_0_xi, _expand(pl['h_0_xi'], N_sl))
+        _set(ph.kh_h_0_chi, _expand(pl['h_0_chi'], N_sl))
+        _set(ph.kh_h_inf_xi, _expand(pl['h_inf_xi'], N_sl))
+        _set(ph.kh_h_inf_chi, _expand(pl['h_inf_chi'], N_sl))
+        for key in ('dot_gamma_0', 'n', 'xi_0', 'xi_inf', 'chi_inf'):           # the reference's sanity checks (:164-169)
+            if np.any(np.asarray(pl[key], float) <= 0.0):
+                raise L.DmkError('kinehardening: %s must be positive' % key)
+        state_init = np.concatenate([_expand(pl['xi_0'], N_sl), np.zeros(5 * ns)])
+        atol = np.concatenate([np.full(2 * ns, float(pl.get('atol_xi', 1.0))), np.full(ns, float(pl.get('atol_gamma', 1.0e-6))),
+                               np.zeros(3 * ns)])
     elif kind == 'dislotwin':
         ph.law = LAW_DISLOTWIN
         N_sl, N_tw, N_tr = list(pl.get('N_sl', [])), list(pl.get('N_tw', [])), list(pl.get('N_tr', []))

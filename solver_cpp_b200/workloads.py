@@ -34,12 +34,18 @@ DISLOTWIN_TWIP = {'type': 'dislotwin', 'N_sl': [12], 'f_edge': [1.0], 'b_sl': [2
                   'T_ref': 293.15, 'Gamma_sf': 2.833e-2, 'Gamma_sf,T': 1.214e-4, 'Gamma_sf,T^2': 1.473e-7,
                   'x_c': 1.0e-9, 'V_cs': 1.67e-29, 'D': 5.0e-5}                                        # dislotwin_TWIP-TRIP.yaml, N_tr removed
 
+HOOKE_AISI304 = {'type': 'Hooke', 'C_11': 204.6e9, 'C_12': 137.7e9, 'C_44': 126.2e9}                     # Hooke_AISI304.yaml
+KINEHARDENING_317L = {'type': 'kinehardening', 'N_sl': [12], 'xi_0': [0.070e9], 'xi_inf': [0.015e9], 'h_0_xi': [0.065e9],
+                      'h_inf_xi': [0.045e9], 'chi_inf': [0.027e9], 'h_0_chi': [55e9], 'h_inf_chi': [1.3e9], 'n': [20],
+                      'dot_gamma_0': [1e-4], 'h_sl-sl': [1, 1, 1, 1, 1, 1, 1]}                          # kinehardening_317L.yaml
+
 PHASES = {
     'Al_pheno': {'lattice': 'cF', 'mechanical': {'elastic': HOOKE_AL, 'plastic': PHENO_AL}},
     'Cu_pheno': {'lattice': 'cF', 'mechanical': {'elastic': HOOKE_CU, 'plastic': PHENO_CU}},
     'Al_iso': {'lattice': 'cF', 'mechanical': {'elastic': HOOKE_AL_T, 'plastic': ISOTROPIC}},
     'Al_elastic': {'lattice': 'cF', 'mechanical': {'elastic': HOOKE_AL_T}},
     'TWIP': {'lattice': 'cF', 'mechanical': {'elastic': HOOKE_TWIP, 'plastic': DISLOTWIN_TWIP}},
+    'Steel_kine': {'lattice': 'cF', 'mechanical': {'elastic': HOOKE_AISI304, 'plastic': KINEHARDENING_317L}},
 }
 
 TENSION_X = {'solver': {'mechanical': 'spectral_basic'},

@@ -138,6 +138,7 @@ generic:
     case DMK_LAW_NONE: return run_point<DMK_LAW_NONE, 0, 0>(ARGS);
     case DMK_LAW_ISOTROPIC: return run_point<DMK_LAW_ISOTROPIC, 1, 0>(ARGS);
     case DMK_LAW_PHENOPOWERLAW: return run_point<DMK_LAW_PHENOPOWERLAW, 2 * DMK_MAX_SYS, 0>(ARGS);
+    case DMK_LAW_KINEHARDENING: return run_point<DMK_LAW_KINEHARDENING, DMK_MAX_STATE, 0>(ARGS);
     default: return run_point<DMK_LAW_DISLOTWIN, DMK_MAX_STATE, DMK_MAX_DEP>(ARGS);
   }
 }

@@ -241,3 +241,55 @@ def test_other_state_integrators_match_oracle(integrator, phase, rate):
         o.forward()
     if phase == 'Al_pheno' and integrator != 'AdaptiveEuler':      # (soft isotropic Al cuts back on most points with the explicit schemes)
         assert n_clean > n
+
+
+def test_twin_matches_oracle_kinehardening_with_load_reversal():
+    """kinehardening (phase_mechanical_plastic_kinehardening.f90; parameters of kinehardening_317L.yaml) through the product's
+    device functions against the oracle on a tension -> unloading -> compression path: the shear direction of the active
+    systems flips on the way back, so the deltaState jump (sgn_gamma, chi_flip, gamma_flip) is exercised, not just dotState.
+    The law has no fixture in the reference tree: oracle-vs-product parity only (unpinned)."""
+    import twin
+    from solver_cpp_b200 import workloads as W, material as M
+    lib = twin.build()
+    cells = (4, 3, 3)
+    material, material_at, size = W.polycrystal(cells, 6, 'Steel_kine', 0)
+    o = ConstitutiveOracle(material, material_at)
+    m = M.Material(material, material_at)
+    num = M.make_numerics()
+    n = int(np.prod(cells))
+    ns = o.phases[0].n_state
+    nsl = o.phases[0].n_sl
+    assert ns == 6 * nsl and m.phases[0].n_state == ns
+    rng = np.random.default_rng(5)
+    fluct = rng.standard_normal((n, 3, 3))
+    Lp = np.zeros((n, 9))
+    dep = np.zeros((n, 1))
+    atol = np.ctypeslib.as_array(o.phases[0].atol)[:ns].copy()
+    atol[atol == 0.0] = 1e-300                            # the deltaState part has no tolerance: exact zeros must stay exact zeros
+    compared = 0
+    for k, e in enumerate([1.5e-3, 3.0e-3, 4.5e-3, 3.0e-3, 1.5e-3, 0.0, -1.5e-3, -3.0e-3]):
+        F = np.eye(3) + np.diag([e, -0.3 * e, -0.3 * e]) + 1.0e-4 * (k + 1) * fluct
+        snap = o.snapshot()
+        assert not o.mechanical_response(F.reshape(n, 9), 0.5)
+        P_o, dPdF_o = o.mechanical_response2(0.5, tangent=True)
+        for i in range(n):
+            r = twin.run_point(lib, m.phases[0], num, snap['F0'][i], F[i].reshape(9), snap['Fp0'][i], snap['Lp0'][i], Lp[i],
+                               snap['S0'][i][V6], snap['state0'][i][:ns], dep[i], 0.5, tangent=True)
+            Lp[i] = r['Lp']
+            assert r['ok']
+            if o.point_cutbacks[i]:
+                continue
+            err = np.abs(r['P'] - o.a['P'][i]).max() / np.abs(o.a['P'][i]).max()
+            err = max(err, np.abs(r['Fp'] - o.a['Fp'][i]).max())
+            # state: 1e-9 relative, or -- chi runs through zero on the way back -- a thousandth of the integrator's own absolute tolerance
+            ds = np.abs(r['state'][:ns] - o.a['state'][i, :ns])
+            ok_state = (ds <= 1e-9 * np.maximum(np.abs(o.a['state'][i, :ns]), atol)) | (ds <= 1e-3 * atol)
+            et = np.abs(r['dPdF'] - dPdF_o[i].reshape(81)).max() / np.abs(dPdF_o[i]).max()
+            assert err < 1e-9 and ok_state.all() and et < 1e-8, (k, i, err, ds.max(), et)
+            compared += 1
+        o.forward()
+    st = o.a['state'][:, :ns]
+    sgn, chi_flip = st[:, 3 * nsl:4 * nsl], st[:, 4 * nsl:5 * nsl]
+    assert compared > 0.8 * 8 * n
+    assert (sgn > 0.5).any() and (sgn < -0.5).any() and (chi_flip > 0.0).any()      # directions were set and flipped
+    assert np.abs(st[:, nsl:2 * nsl]).max() > 1e5                                   # a back stress developed
