@@ -291,7 +291,14 @@ int dmk_fast_gamma_zpass(double2* data, const DmkFftPlan& plz, DmkLineMap map, i
     case 32: return launch_gamma<DmkFastPlan<8, 4, 1>, 4, 160, 2>(data, plz, map, n0, n_outer, gp, st, imag_xi, ps);
     case 64: return launch_gamma<DmkFastPlan<8, 8, 1>, 4, 160, 2>(data, plz, map, n0, n_outer, gp, st, imag_xi, ps);
     case 128: return launch_gamma<DmkFastPlan<16, 8, 1>, 4, 192, 2>(data, plz, map, n0, n_outer, gp, st, imag_xi, ps);
-    case 256: return launch_gamma<DmkFastPlan<16, 16, 1>, 2, 192, 2>(data, plz, map, n0, n_outer, gp, st, imag_xi, ps);
+    case 256: {
+      static const int v = [] { const char* e = getenv("DMK_GZ_VARIANT"); return e ? atoi(e) : 0; }();        // comparison runs
+      if (v == 1) return launch_gamma<DmkFastPlan<16, 16, 1>, 2, 192, 3>(data, plz, map, n0, n_outer, gp, st, imag_xi, ps);
+      if (v == 2) return launch_gamma<DmkFastPlan<16, 16, 1>, 1, 96, 5>(data, plz, map, n0, n_outer, gp, st, imag_xi, ps);
+      if (v == 3) return launch_gamma<DmkFastPlan<16, 16, 1>, 1, 96, 6>(data, plz, map, n0, n_outer, gp, st, imag_xi, ps);
+      if (v == 4) return launch_gamma<DmkFastPlan<16, 16, 1>, 1, 160, 3>(data, plz, map, n0, n_outer, gp, st, imag_xi, ps);
+      return launch_gamma<DmkFastPlan<16, 16, 1>, 2, 192, 2>(data, plz, map, n0, n_outer, gp, st, imag_xi, ps);
+    }
     case 512: return launch_gamma<DmkFastPlan<8, 8, 8>, 1, 192, 2>(data, plz, map, n0, n_outer, gp, st, imag_xi, ps);
     default: *done = false; return DMK_OK;
   }

@@ -56,6 +56,7 @@ def test_g1_fortran_run_reproduced_on_the_gpu(golden_dir):
     ('Cu_pheno', (16, 16, 16), 2, 2e-7, 'MIXED_SHEAR'),    # C4's material and load
     ('Al_pheno', (16, 16, 16), 3, 1e-9, 'MIXED_SHEAR'),
     ('TWIP', (12, 10, 8), 2, 1e-9, 'TENSION_X'),           # C5's material
+    ('Steel_kine', (12, 10, 8), 5, 1e-7, 'TENSION_X'),     # kinehardening (317L) into first yield
 ])
 def test_increment_loop_matches_free_running_oracle(phase, cells, n_inc, tol, load):
     """BASELINE config C1 (16^3, 20 grains, phenopowerlaw Al, tensionX): homogenised P and F per increment within 1e-9
