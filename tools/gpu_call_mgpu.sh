@@ -6,7 +6,7 @@ N=${1:-2}
 shift
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=index,name --format=csv,noheader | head -8
-for cfg in p2p:nccl nccl:nccl p2p:torch; do
+for cfg in ${DMK_MGPU_CFGS:-p2p:nccl nccl:nccl p2p:torch}; do
   ex=${cfg%%:*}; cm=${cfg##*:}
   DMK_EXCHANGE=$ex DMK_COMM=$cm DMK_PARITY_TIMEOUT=200 timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 2951$N \
       tests/mgpu_parity.py > gpurun_out/r02_mgpu_parity_n${N}_${ex}_${cm}.log 2>&1; echo "parity N=$N exchange=$ex collectives=$cm rc=$?"
