@@ -32,7 +32,7 @@ typedef struct dmk_ctx dmk_ctx;
 #define DMK_MAX_STATE (3 * DMK_MAX_SL + DMK_MAX_TW)
 #define DMK_MAX_PHASES 8
 
-enum { DMK_LAW_NONE = 0, DMK_LAW_ISOTROPIC = 1, DMK_LAW_PHENOPOWERLAW = 2, DMK_LAW_DISLOTWIN = 3, DMK_LAW_KINEHARDENING = 4 };
+enum { DMK_LAW_NONE = 0, DMK_LAW_ISOTROPIC = 1, DMK_LAW_PHENOPOWERLAW = 2, DMK_LAW_DISLOTWIN = 3, DMK_LAW_KINEHARDENING = 4, DMK_LAW_DISLOTUNGSTEN = 5 };
 enum { DMK_DERIVATIVE_CONTINUOUS = 0, DMK_DERIVATIVE_CENTRAL_DIFF = 1, DMK_DERIVATIVE_FWBW_DIFF = 2 };
 enum { DMK_DIVCORR_NONE = 0, DMK_DIVCORR_SIZE = 1, DMK_DIVCORR_SIZE_GRID = 2 };
 
@@ -90,6 +90,11 @@ typedef struct {
    * (non-)Schmid tensors with phenopowerlaw.  State: xi | chi | gamma (n_sl each, rates from dotState) followed by
    * sgn_gamma | chi_flip | gamma_flip (n_sl each, moved only by the deltaState jump): n_state = 6 n_sl, n_sl <= DMK_MAX_STATE / 6 */
   double kh_chi_inf[DMK_MAX_SL], kh_h_0_xi[DMK_MAX_SL], kh_h_0_chi[DMK_MAX_SL], kh_h_inf_xi[DMK_MAX_SL], kh_h_inf_chi[DMK_MAX_SL];
+  /* dislotungsten (phase_mechanical_plastic_dislotungsten.f90:10-47).  State rho_mob | rho_dip | gamma_sl (3 n_sl), dependent
+   * state Lambda_sl | tau_pass.  b_sl, i_sl, p, q, B, d_caron, the forest projection, mu, nu, kB T, Q_cl, D and the dipole switch are
+   * the dislotwin members above (dt_*), Q_s is dt_Q_sl, tau_Peierls is dt_tau_0; the law's own: kink-pair height and width,
+   * attempt frequency, atomic volume f_at b^3, self-diffusion prefactor */
+  double tu_h[DMK_MAX_SL], tu_w[DMK_MAX_SL], tu_omega[DMK_MAX_SL], tu_f_at[DMK_MAX_SL], tu_D_0;
 } dmk_phase;
 
 /* collective callbacks for world_size > 1 (all stream-ordered on the context's stream; device pointers).

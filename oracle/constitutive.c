@@ -514,8 +514,80 @@ static void dt_dependentState(pt_t *p) {
   }
 }
 
+/* ------------------------------------------------------------------ dislotungsten
+ * phase_mechanical_plastic_dislotungsten.f90: kinetics :444-528, LpAndItsTangent :270-310, dotState :316-378, dependentState :384-405.
+ * State: rho_mob | rho_dip | gamma_sl; dependent: Lambda_sl | tau_pass (the dislotwin slots with n_tw = 0).  b_sl, i_sl, p, q, B,
+ * d_caron, the forest projection, mu, nu, kB T, Q_cl and D live in the dislotwin fields (dt_*), Q_s in dt_Q_sl, tau_Peierls in
+ * dt_tau_0, the dipole switch in dt_omit_dipoles; h, w, omega, f_at and D_0 are the law's own (tu_*). */
+static void tu_kinetics(const pt_t *p, const double *Mp, double *dg, double *ddg, double *tau_out) {
+  const orc_phase_t *ph = p->ph; const double *rho_mob = p->state;
+  const double *Lambda = DEP_LAMBDA_SL(p), *tau_pass = DEP_TAU_PASS(p);
+  for (int i = 0; i < ph->n_sl; i++) {
+    double tp = ddot(Mp, ph->P_nS_pos[i]), tn = ddot(Mp, ph->P_nS_neg[i]);
+    double tau_eff = fmax(fmax(tp, tn) - tau_pass[i], 0.0);                       /* math_clip(left = 0) */
+    if (tau_out) tau_out[i] = tau_eff;
+    if (tau_eff > TOL_MATH_CHECK) {
+      double sr = tau_eff / ph->dt_tau_0[i], srp = pow(sr, ph->dt_p[i]), srpm1 = pow(sr, ph->dt_p[i] - 1.0);
+      double BR = ph->dt_Q_sl[i] / ph->dt_kB_T, effL = Lambda[i] - ph->tu_w[i];
+      double t_n = ph->dt_b_sl[i] * exp(BR * pow(1.0 - srp, ph->dt_q[i])) / (ph->tu_omega[i] * effL);
+      double t_k = effL * ph->dt_B[i] / (2.0 * ph->dt_b_sl[i] * tau_eff);
+      dg[i] = rho_mob[i] * ph->dt_b_sl[i] * ph->tu_h[i] / (t_n + t_k) * ((tp > tn) ? 1.0 : -1.0);
+      if (ddg) {
+        double dtn = -1.0 * t_n * BR * ph->dt_p[i] * ph->dt_q[i] * pow(1.0 - srp, ph->dt_q[i] - 1.0) * srpm1 / ph->dt_tau_0[i];
+        double dtk = -1.0 * t_k / tau_eff;
+        ddg[i] = -1.0 * dg[i] * (dtn + dtk) / (t_n + t_k);
+      }
+    } else { dg[i] = 0.0; if (ddg) ddg[i] = 0.0; }
+  }
+}
+static void tu_Lp(const pt_t *p, const double *Mp, double *Lp, double *dLp_dMp) {
+  const orc_phase_t *ph = p->ph;
+  double dg[ORC_MAX_SL], ddg[ORC_MAX_SL];
+  memset(Lp, 0, 9*sizeof(double)); memset(dLp_dMp, 0, 81*sizeof(double));
+  tu_kinetics(p, Mp, dg, ddg, NULL);
+  for (int i = 0; i < ph->n_sl; i++) {
+    const double *PnS = (dg[i] > 0.0) ? ph->P_nS_pos[i] : ph->P_nS_neg[i];
+    for (int a = 0; a < 9; a++) Lp[a] += dg[i] * ph->P_sl[i][a];
+    for (int a = 0; a < 9; a++) for (int b = 0; b < 9; b++) dLp_dMp[9*a+b] += ddg[i] * ph->P_sl[i][a] * PnS[b];
+  }
+}
+static void tu_dotState(const pt_t *p, const double *Mp, double *dot) {
+  const orc_phase_t *ph = p->ph; int ns = ph->n_sl;
+  const double *rho_mob = p->state, *rho_dip = p->state + ns, *Lambda = DEP_LAMBDA_SL(p);
+  double *dot_mob = dot, *dot_dip = dot + ns, *dot_gamma = dot + 2*ns;
+  double mu = ph->dt_mu, nu = ph->dt_nu, kT = ph->dt_kB_T, tau_eff[ORC_MAX_SL];
+  tu_kinetics(p, Mp, dot_gamma, NULL, tau_eff);
+  for (int i = 0; i < ns; i++) dot_gamma[i] = fabs(dot_gamma[i]);
+  for (int i = 0; i < ns; i++) {
+    double form, climb;
+    if (deq0(dot_gamma[i])) { form = 0.0; climb = 0.0; }
+    else {
+      double d_hat = mu * ph->dt_b_sl[i] / (8.0 * PI_ * (1.0 - nu) * tau_eff[i]);
+      d_hat = fmax(d_hat, ph->dt_d_caron[i]);            /* math_clip: left = d_caron, then right = Lambda_sl (math.f90:1316-1329) */
+      d_hat = fmin(d_hat, Lambda[i]);
+      form = ph->dt_omit_dipoles ? 0.0 : dot_gamma[i] * 2.0 * (d_hat - ph->dt_d_caron[i]) / ph->dt_b_sl[i] * rho_mob[i];
+      double v_cl = (3.0 * mu * ph->tu_D_0 * exp(-ph->dt_Q_cl / kT) * ph->tu_f_at[i] / (2.0 * PI_ * kT)) * (1.0 / (d_hat + ph->dt_d_caron[i]));
+      climb = (4.0 * v_cl * rho_dip[i]) / (d_hat - ph->dt_d_caron[i]);
+    }
+    dot_mob[i] = dot_gamma[i] / (ph->dt_b_sl[i] * Lambda[i]) - form - dot_gamma[i] * 2.0 * ph->dt_d_caron[i] / ph->dt_b_sl[i] * rho_mob[i];
+    dot_dip[i] = form - climb - dot_gamma[i] * 2.0 * ph->dt_d_caron[i] / ph->dt_b_sl[i] * rho_dip[i];
+  }
+}
+static void tu_dependentState(pt_t *p) {
+  const orc_phase_t *ph = p->ph; int ns = ph->n_sl;
+  const double *rho_mob = p->state, *rho_dip = p->state + ns;
+  double *Lambda = DEP_LAMBDA_SL(p), *tau_pass = DEP_TAU_PASS(p);
+  for (int i = 0; i < ns; i++) {
+    double hp = 0, s = 0;
+    for (int j = 0; j < ns; j++) { hp += ph->h_sl_sl[i][j] * (rho_mob[j] + rho_dip[j]); s += ph->dt_forest[i][j] * (rho_mob[j] + rho_dip[j]); }
+    tau_pass[i] = ph->dt_mu * ph->dt_b_sl[i] * sqrt(hp);
+    double inv = 1.0 / ph->dt_D + sqrt(s) / ph->dt_i_sl[i];
+    Lambda[i] = pow(inv, -1.0);
+  }
+}
+
 /* ------------------------------------------------------------------ dispatchers */
-static void dependentState(pt_t *p) { if (p->ph->law == 3) dt_dependentState(p); }
+static void dependentState(pt_t *p) { if (p->ph->law == 3) dt_dependentState(p); else if (p->ph->law == 5) tu_dependentState(p); }
 
 static void Mandel(const double *Fi, const double *S, double *Mp, double *FiTFi) {
   double FiT[9]; tr3(Fi, FiT); mm(FiT, Fi, FiTFi); mm(FiTFi, S, Mp);
@@ -525,7 +597,7 @@ static void plastic_Lp_tangents(const pt_t *p, const double *S, const double *Fi
   double Mp[9], FiTFi[9], dM[81];
   Mandel(Fi, S, Mp, FiTFi);
   if (p->ph->law == 1) iso_Lp(p, Mp, Lp, dM); else if (p->ph->law == 2) pheno_Lp(p, Mp, Lp, dM);
-  else if (p->ph->law == 4) kh_Lp(p, Mp, Lp, dM); else dt_Lp(p, Mp, Lp, dM);
+  else if (p->ph->law == 4) kh_Lp(p, Mp, Lp, dM); else if (p->ph->law == 5) tu_Lp(p, Mp, Lp, dM); else dt_Lp(p, Mp, Lp, dM);
   double FiS[9]; mm(Fi, S, FiS);
   for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) {
     double d[9], dT[9], a[9], b[9];
@@ -559,7 +631,7 @@ static void dotState(const pt_t *p, double *dot) {
   if (p->ph->law == 0) return;
   double Mp[9], FiTFi[9]; Mandel(p->Fi, p->S, Mp, FiTFi);
   if (p->ph->law == 1) iso_dotState(p, Mp, dot); else if (p->ph->law == 2) pheno_dotState(p, Mp, dot);
-  else if (p->ph->law == 4) kh_dotState(p, Mp, dot); else dt_dotState(p, Mp, dot);
+  else if (p->ph->law == 4) kh_dotState(p, Mp, dot); else if (p->ph->law == 5) tu_dotState(p, Mp, dot); else dt_dotState(p, Mp, dot);
 }
 /* plastic_deltaState (phase_mechanical_plastic.f90:372-413): instantaneous state change after a converged state integration;
  * .false. (0) for every law but kinehardening (nonlocal is not restated); returns broken */

@@ -16,7 +16,7 @@ import numpy as np
 
 from . import crystal
 from .phase_layout import (Phase, Numerics, PointState, STATE_FIELDS, MAX_SL, MAX_TW,
-                           LAW_NONE, LAW_ISOTROPIC, LAW_PHENOPOWERLAW, LAW_DISLOTWIN, LAW_KINEHARDENING)
+                           LAW_NONE, LAW_ISOTROPIC, LAW_PHENOPOWERLAW, LAW_DISLOTWIN, LAW_KINEHARDENING, LAW_DISLOTUNGSTEN)
 from .build import build
 
 T_ROOM = 293.15            # constants.f90:12
@@ -180,6 +180,37 @@ def make_phase(name, phase_cfg, T=T_ROOM):
         state_init = np.concatenate([_expand(pl['xi_0'], N_sl), np.zeros(5 * ns)])
         atol = np.concatenate([np.full(2 * ns, float(pl.get('atol_xi', 1.0))), np.full(ns, float(pl.get('atol_gamma', 1.0e-6))),
                                np.zeros(3 * ns)])
+    elif ptype == 'dislotungsten':                   # plastic_dislotungsten_init, phase_mechanical_plastic_dislotungsten.f90:79-268
+        ph.law = LAW_DISLOTUNGSTEN
+        N_sl = list(pl.get('N_sl', []))
+        ns = int(np.sum(N_sl))
+        if ns == 0:
+            raise NotImplementedError('dislotungsten without slip')
+        ph.n_sl, ph.n_tw = ns, 0
+        bound = pl.get('isotropic_bound', 'isostrain')
+        ph.dt_mu = crystal.isotropic_mu(C66, bound); ph.dt_nu = crystal.isotropic_nu(C66, bound)
+        ph.dt_kB_T = K_B * T
+        P = crystal.schmid_slip(N_sl, lattice)
+        _set(ph.P_sl, P.reshape(ns, 9))
+        if lattice == 'cI':
+            a_nS = pl.get('a_nonSchmid_110', [])
+            _set(ph.P_nS_pos, crystal.schmid_slip(N_sl, lattice, a_nS, +1).reshape(ns, 9))
+            _set(ph.P_nS_neg, crystal.schmid_slip(N_sl, lattice, a_nS, -1).reshape(ns, 9))
+        else:
+            _set(ph.P_nS_pos, P.reshape(ns, 9)); _set(ph.P_nS_neg, -P.reshape(ns, 9))
+        ph.dt_omit_dipoles = int(bool(pl.get('no_dipole_formation', False)))
+        ph.dt_D = pl['D']; ph.tu_D_0 = pl['D_0']; ph.dt_Q_cl = pl['Q_cl']
+        nf = len(N_sl)
+        f_edge = _expand(pl.get('f_edge', [0.5] * nf), N_sl)
+        b_sl = _expand(pl['b_sl'], N_sl)
+        _set(ph.dt_b_sl, b_sl); _set(ph.dt_Q_sl, _expand(pl['Q_s'], N_sl)); _set(ph.dt_i_sl, _expand(pl['i_sl'], N_sl))
+        _set(ph.dt_tau_0, _expand(pl['tau_Peierls'], N_sl)); _set(ph.dt_p, _expand(pl['p_sl'], N_sl)); _set(ph.dt_q, _expand(pl['q_sl'], N_sl))
+        _set(ph.tu_h, _expand(pl['h'], N_sl)); _set(ph.tu_w, _expand(pl['w'], N_sl)); _set(ph.tu_omega, _expand(pl['omega'], N_sl))
+        _set(ph.dt_B, _expand(pl['B'], N_sl)); _set(ph.dt_d_caron, b_sl * float(pl['D_a'])); _set(ph.tu_f_at, b_sl ** 3 * float(pl['f_at']))
+        _set(ph.h_sl_sl, crystal.interaction_slip_slip(N_sl, pl['h_sl-sl'], lattice))
+        _set(ph.dt_forest, crystal.forest_projection(N_sl, lattice, f_edge))
+        state_init = np.concatenate([_expand(pl['rho_mob_0'], N_sl), _expand(pl['rho_dip_0'], N_sl), np.zeros(ns)])
+        atol = np.concatenate([np.full(2 * ns, float(pl.get('atol_rho', 1.0))), np.full(ns, float(pl.get('atol_gamma', 1.0e-6)))])
     elif ptype == 'dislotwin':
         ph.law = LAW_DISLOTWIN
         N_sl = list(pl.get('N_sl', [])); N_tw = list(pl.get('N_tw', [])); N_tr = list(pl.get('N_tr', []))

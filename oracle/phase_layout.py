@@ -14,7 +14,7 @@ import ctypes as C
 MAX_SL, MAX_TW, MAX_TR = 48, 12, 12
 MAX_STATE = 3 * MAX_SL + MAX_TW + MAX_TR
 
-LAW_NONE, LAW_ISOTROPIC, LAW_PHENOPOWERLAW, LAW_DISLOTWIN, LAW_KINEHARDENING = 0, 1, 2, 3, 4
+LAW_NONE, LAW_ISOTROPIC, LAW_PHENOPOWERLAW, LAW_DISLOTWIN, LAW_KINEHARDENING, LAW_DISLOTUNGSTEN = 0, 1, 2, 3, 4, 5
 
 # (name, 'i'|'d', shape tuple or ())
 PHASE_FIELDS = [
@@ -56,6 +56,9 @@ PHASE_FIELDS = [
     # ---- kinehardening (phase_mechanical_plastic_kinehardening.f90:11-40; dot_gamma_0_sl, n_sl_exp, xi_inf_sl are shared)
     ('kh_chi_inf', 'd', (MAX_SL,)), ('kh_h_0_xi', 'd', (MAX_SL,)), ('kh_h_0_chi', 'd', (MAX_SL,)),
     ('kh_h_inf_xi', 'd', (MAX_SL,)), ('kh_h_inf_chi', 'd', (MAX_SL,)),
+    # ---- dislotungsten (phase_mechanical_plastic_dislotungsten.f90:10-47; b_sl, i_sl, p, q, B, d_caron, Q_s -> dt_Q_sl,
+    #      tau_Peierls -> dt_tau_0, forest projection, mu, nu, kB T, Q_cl, D and the dipole switch are the dislotwin fields)
+    ('tu_h', 'd', (MAX_SL,)), ('tu_w', 'd', (MAX_SL,)), ('tu_omega', 'd', (MAX_SL,)), ('tu_f_at', 'd', (MAX_SL,)), ('tu_D_0', 'd', ()),
 ]
 
 NUM_FIELDS = [

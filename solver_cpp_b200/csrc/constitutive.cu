@@ -269,6 +269,7 @@ static int persistent_grid(K kernel, long long n) {
     else if (law == DMK_LAW_PHENOPOWERLAW && nstate <= 48) KERNEL<DMK_LAW_PHENOPOWERLAW, 48, 0><<<persistent_grid(KERNEL<DMK_LAW_PHENOPOWERLAW, 48, 0>, n), DMK_PT_THREADS, 0, st>>> __VA_ARGS__; \
     else if (law == DMK_LAW_PHENOPOWERLAW) KERNEL<DMK_LAW_PHENOPOWERLAW, 2 * DMK_MAX_SYS, 0><<<persistent_grid(KERNEL<DMK_LAW_PHENOPOWERLAW, 2 * DMK_MAX_SYS, 0>, n), DMK_PT_THREADS, 0, st>>> __VA_ARGS__; \
     else if (law == DMK_LAW_KINEHARDENING) KERNEL<DMK_LAW_KINEHARDENING, DMK_MAX_STATE, 0><<<persistent_grid(KERNEL<DMK_LAW_KINEHARDENING, DMK_MAX_STATE, 0>, n), DMK_PT_THREADS, 0, st>>> __VA_ARGS__; \
+    else if (law == DMK_LAW_DISLOTUNGSTEN) KERNEL<DMK_LAW_DISLOTUNGSTEN, 3 * DMK_MAX_SL, 2 * DMK_MAX_SL><<<persistent_grid(KERNEL<DMK_LAW_DISLOTUNGSTEN, 3 * DMK_MAX_SL, 2 * DMK_MAX_SL>, n), DMK_PT_THREADS, 0, st>>> __VA_ARGS__; \
     else if (law == DMK_LAW_DISLOTWIN && nstate <= 48) KERNEL<DMK_LAW_DISLOTWIN, 48, 36><<<persistent_grid(KERNEL<DMK_LAW_DISLOTWIN, 48, 36>, n), DMK_PT_THREADS, 0, st>>> __VA_ARGS__; \
     else KERNEL<DMK_LAW_DISLOTWIN, DMK_MAX_STATE, DMK_MAX_DEP><<<persistent_grid(KERNEL<DMK_LAW_DISLOTWIN, DMK_MAX_STATE, DMK_MAX_DEP>, n), DMK_PT_THREADS, 0, st>>> __VA_ARGS__; \
   } while (0)
@@ -281,6 +282,7 @@ static int persistent_grid(K kernel, long long n) {
     else if (law == DMK_LAW_PHENOPOWERLAW && nstate <= 48) KERNEL<DMK_LAW_PHENOPOWERLAW, 48, 0> __VA_ARGS__;    \
     else if (law == DMK_LAW_PHENOPOWERLAW) KERNEL<DMK_LAW_PHENOPOWERLAW, 2 * DMK_MAX_SYS, 0> __VA_ARGS__;       \
     else if (law == DMK_LAW_KINEHARDENING) KERNEL<DMK_LAW_KINEHARDENING, DMK_MAX_STATE, 0> __VA_ARGS__;         \
+    else if (law == DMK_LAW_DISLOTUNGSTEN) KERNEL<DMK_LAW_DISLOTUNGSTEN, 3 * DMK_MAX_SL, 2 * DMK_MAX_SL> __VA_ARGS__; \
     else if (law == DMK_LAW_DISLOTWIN && nstate <= 48) KERNEL<DMK_LAW_DISLOTWIN, 48, 36> __VA_ARGS__;           \
     else KERNEL<DMK_LAW_DISLOTWIN, DMK_MAX_STATE, DMK_MAX_DEP> __VA_ARGS__;                                     \
   } while (0)
@@ -384,7 +386,7 @@ static void q_host(const double* C66, const double* pv, double* Q) {
 }
 
 static int check_phase(const dmk_phase& p, int idx) {
-  if (p.law < DMK_LAW_NONE || p.law > DMK_LAW_KINEHARDENING) { dmk_set_error("phase %d: unknown plastic law %d", idx, p.law); return DMK_ERR_ARG; }
+  if (p.law < DMK_LAW_NONE || p.law > DMK_LAW_DISLOTUNGSTEN) { dmk_set_error("phase %d: unknown plastic law %d", idx, p.law); return DMK_ERR_ARG; }
   if (p.n_sl < 0 || p.n_sl > DMK_MAX_SL || p.n_tw < 0 || p.n_tw > DMK_MAX_TW) { dmk_set_error("phase %d: too many slip/twin systems", idx); return DMK_ERR_UNSUPPORTED; }
   if (p.law == DMK_LAW_ISOTROPIC && p.iso_dilatation) { dmk_set_error("phase %d: isotropic plasticity with dilatation (Li != 0) is not offered on the device path", idx); return DMK_ERR_UNSUPPORTED; }
   if (p.law == DMK_LAW_DISLOTWIN && p.dt_gamma_0_sb != 0.0) { dmk_set_error("phase %d: dislotwin shear banding is not offered on the device path", idx); return DMK_ERR_UNSUPPORTED; }
@@ -392,6 +394,10 @@ static int check_phase(const dmk_phase& p, int idx) {
   if (p.law == DMK_LAW_ISOTROPIC) expect = 1;
   else if (p.law == DMK_LAW_PHENOPOWERLAW) expect = 2 * (p.n_sl + p.n_tw);
   else if (p.law == DMK_LAW_DISLOTWIN) expect = 3 * p.n_sl + p.n_tw;
+  else if (p.law == DMK_LAW_DISLOTUNGSTEN) {
+    if (p.n_sl < 1 || p.n_tw != 0) { dmk_set_error("phase %d: dislotungsten needs slip systems and no twin systems", idx); return DMK_ERR_UNSUPPORTED; }
+    expect = 3 * p.n_sl;
+  }
   else if (p.law == DMK_LAW_KINEHARDENING) {
     if (p.n_sl < 1 || 6 * p.n_sl > DMK_MAX_STATE || p.n_tw != 0) { dmk_set_error("phase %d: kinehardening needs 1..%d slip systems and no twin systems", idx, DMK_MAX_STATE / 6); return DMK_ERR_UNSUPPORTED; }
     expect = 6 * p.n_sl;
@@ -418,14 +424,14 @@ __global__ void dmk_init_dependent_kernel(DmkPointArrays pa, int phase) {
   const long long n = pa.n;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     if (pa.phase[i] != phase) continue;
-    if constexpr (LAW == DMK_LAW_DISLOTWIN) {
+    if constexpr (LAW == DMK_LAW_DISLOTWIN || LAW == DMK_LAW_DISLOTUNGSTEN) {
       DmkPt<LAW, NS, ND> p;
       DmkPtStore<LAW, NS, ND> pstore;
       dmk_pt_bind(p, pstore);
       p.ph = pa.d_phases + phase;
       const int ns = p.ph->p.n_state, nd = p.ph->n_dep;
       for (int k = 0; k < ns; k++) p.st[k] = pa.state[k * n + i];
-      dt_dependentState(p);
+      if constexpr (LAW == DMK_LAW_DISLOTWIN) dt_dependentState(p); else tu_dependentState(p);
       for (int k = 0; k < nd; k++) pa.dep[k * n + i] = p.dep[k];
     }
   }
@@ -465,7 +471,7 @@ extern "C" int dmk_material_init(dmk_ctx* c, const dmk_phase* phases, int n_phas
     for (int a = 0; a < p.n_sl; a++) d.n_sl_int[a] = small_int(p.n_sl_exp[a]);
     for (int a = 0; a < p.n_tw; a++) d.n_tw_int[a] = small_int(p.n_tw_exp[a]);
     d.iso_n_int = small_int(p.iso_n);
-    d.n_dep = (p.law == DMK_LAW_DISLOTWIN) ? 2 * p.n_sl + p.n_tw : 0;
+    d.n_dep = (p.law == DMK_LAW_DISLOTWIN) ? 2 * p.n_sl + p.n_tw : (p.law == DMK_LAW_DISLOTUNGSTEN) ? 2 * p.n_sl : 0;
     pa->law_of_phase[i] = p.law; pa->nstate_of_phase[i] = p.n_state; pa->nsys_of_phase[i] = p.n_sl + p.n_tw;
     max_state = std::max(max_state, p.n_state); max_dep = std::max(max_dep, d.n_dep);
   }
@@ -522,9 +528,10 @@ extern "C" int dmk_material_init(dmk_ctx* c, const dmk_phase* phases, int n_phas
   }
   // crystallite_init: dependent state from the initial state (phase.f90:564)
   for (int i = 0; i < n_phases; i++) {
-    if (pa->law_of_phase[i] != DMK_LAW_DISLOTWIN || pa->n_cells_of_phase[i] == 0) continue;
+    if ((pa->law_of_phase[i] != DMK_LAW_DISLOTWIN && pa->law_of_phase[i] != DMK_LAW_DISLOTUNGSTEN) || pa->n_cells_of_phase[i] == 0) continue;
     const int grid = point_grid(n);
-    if (pa->nstate_of_phase[i] <= 48) dmk_init_dependent_kernel<DMK_LAW_DISLOTWIN, 48, 36><<<grid, DMK_PT_THREADS, 0, c->stream>>>(*pa, i);
+    if (pa->law_of_phase[i] == DMK_LAW_DISLOTUNGSTEN) dmk_init_dependent_kernel<DMK_LAW_DISLOTUNGSTEN, 3 * DMK_MAX_SL, 2 * DMK_MAX_SL><<<grid, DMK_PT_THREADS, 0, c->stream>>>(*pa, i);
+    else if (pa->nstate_of_phase[i] <= 48) dmk_init_dependent_kernel<DMK_LAW_DISLOTWIN, 48, 36><<<grid, DMK_PT_THREADS, 0, c->stream>>>(*pa, i);
     else dmk_init_dependent_kernel<DMK_LAW_DISLOTWIN, DMK_MAX_STATE, DMK_MAX_DEP><<<grid, DMK_PT_THREADS, 0, c->stream>>>(*pa, i);
     c->launches++;
   }

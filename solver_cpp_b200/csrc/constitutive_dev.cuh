@@ -670,6 +670,84 @@ DMK_HD __forceinline__ void dt_dotState(const DmkPt<LAW, NS, ND>& p, const doubl
   }
 }
 
+// ================================================================================================ dislotungsten
+// phase_mechanical_plastic_dislotungsten.f90: kinetics :444-528, LpAndItsTangent :270-310, dotState :316-378, dependentState :384-405.
+// state: rho_mob[ns] | rho_dip[ns] | gamma_sl[ns] ;  dep: Lambda_sl[ns] | tau_pass[ns]
+template <int LAW, int NS, int ND>
+DMK_HD __forceinline__ void tu_dependentState(DmkPt<LAW, NS, ND>& p) {
+  const dmk_phase& q = p.ph->p;
+  const int ns = q.n_sl;
+  double* Lambda_sl = p.dep; double* tau_pass = p.dep + ns;
+  for (int i = 0; i < ns; i++) {
+    double hp = 0.0, s = 0.0;
+    for (int j = 0; j < ns; j++) { const double rho = p.st[j] + p.st[ns + j]; hp += q.h_sl_sl[i][j] * rho; s += q.dt_forest[i][j] * rho; }
+    tau_pass[i] = q.dt_mu * q.dt_b_sl[i] * sqrt(hp);
+    Lambda_sl[i] = 1.0 / (1.0 / q.dt_D + sqrt(s) / q.dt_i_sl[i]);
+  }
+}
+// one slip system: shear rate, d(shear rate)/d(tau) (want_d) and the effective resolved stress
+template <int LAW, int NS, int ND>
+DMK_HD __forceinline__ void tu_slip_rate(const DmkPt<LAW, NS, ND>& p, const double (&S)[6], int i, bool want_d, double& dg, double& ddg,
+                                         double& tau_eff) {
+  const DmkDevPhase& d = *p.ph;
+  const dmk_phase& q = d.p;
+  const double tp = sdot(S, q.P_nS_pos[i]);
+  const double tn = d.nonschmid ? sdot(S, q.P_nS_neg[i]) : -tp;
+  tau_eff = fmax(fmax(tp, tn) - p.dep[q.n_sl + i], 0.0);               // math_clip(left = 0)
+  dg = 0.0; ddg = 0.0;
+  if (tau_eff > DMK_TOL_MATH_CHECK) {
+    const double sr = tau_eff / q.dt_tau_0[i], srp = pow(sr, q.dt_p[i]);
+    const double BR = q.dt_Q_sl[i] / q.dt_kB_T, effL = p.dep[i] - q.tu_w[i];
+    const double om = 1.0 - srp, omq = pow(om, q.dt_q[i]);
+    const double t_n = q.dt_b_sl[i] * exp(BR * omq) / (q.tu_omega[i] * effL);
+    const double t_k = effL * q.dt_B[i] / (2.0 * q.dt_b_sl[i] * tau_eff);
+    dg = p.st[i] * q.dt_b_sl[i] * q.tu_h[i] / (t_n + t_k) * ((tp > tn) ? 1.0 : -1.0);
+    if (want_d) {
+      // (1 - sr^p)^(q-1) = (1 - sr^p)^q / (1 - sr^p) and sr^(p-1) = sr^p / sr, as in dt_slip_rate
+      const double dtn = -1.0 * t_n * BR * q.dt_p[i] * q.dt_q[i] * (omq / om) * (srp / sr) / q.dt_tau_0[i];
+      const double dtk = -1.0 * t_k / tau_eff;
+      ddg = -1.0 * dg * (dtn + dtk) / (t_n + t_k);
+    }
+  }
+}
+template <int LAW, int NS, int ND>
+DMK_HD __forceinline__ void tu_Lp(const DmkPt<LAW, NS, ND>& p, const double (&S)[6], double (&Lp)[9], double* __restrict__ ddg_out) {
+  const dmk_phase& q = p.ph->p;
+#pragma unroll
+  for (int a = 0; a < 9; a++) Lp[a] = 0.0;
+  for (int i = 0; i < q.n_sl; i++) {
+    double dg, ddg, te;
+    tu_slip_rate(p, S, i, true, dg, ddg, te);
+#pragma unroll
+    for (int a = 0; a < 9; a++) Lp[a] += dg * q.P_sl[i][a];
+    ddg_out[i] = ddg;
+    ddg_out[DMK_MAX_SYS + i] = dg;                           // its sign selects the non-Schmid projection of the tangent (:297)
+  }
+}
+template <int LAW, int NS, int ND>
+DMK_HD __forceinline__ void tu_dotState(const DmkPt<LAW, NS, ND>& p, const double (&S)[6], double* __restrict__ dot) {
+  const dmk_phase& q = p.ph->p;
+  const int ns = q.n_sl;
+  const double mu = q.dt_mu, nu = q.dt_nu, kT = q.dt_kB_T;
+  for (int i = 0; i < ns; i++) {
+    double dg, ddg, tau_eff;
+    tu_slip_rate(p, S, i, false, dg, ddg, tau_eff);
+    const double adg = fabs(dg);
+    const double b = q.dt_b_sl[i], dc = q.dt_d_caron[i], Lambda = p.dep[i];
+    double form = 0.0, climb = 0.0;
+    if (!deq0(adg)) {
+      double d_hat = mu * b / (8.0 * DMK_PI * (1.0 - nu) * tau_eff);
+      d_hat = fmin(fmax(d_hat, dc), Lambda);                 // math_clip(left = d_caron, right = Lambda_sl)
+      form = q.dt_omit_dipoles ? 0.0 : adg * 2.0 * (d_hat - dc) / b * p.st[i];
+      const double v_cl = (3.0 * mu * q.tu_D_0 * exp(-q.dt_Q_cl / kT) * q.tu_f_at[i] / (2.0 * DMK_PI * kT)) * (1.0 / (d_hat + dc));
+      climb = (4.0 * v_cl * p.st[ns + i]) / (d_hat - dc);
+    }
+    dot[i] = adg / (b * Lambda) - form - adg * 2.0 * dc / b * p.st[i];
+    dot[ns + i] = form - climb - adg * 2.0 * dc / b * p.st[ns + i];
+    dot[2 * ns + i] = adg;
+  }
+}
+
 // ================================================================================================ dispatch
 template <int LAW, int NS, int ND>
 DMK_HD __forceinline__ void dot_state(const DmkPt<LAW, NS, ND>& p, double* __restrict__ dot) {
@@ -677,6 +755,13 @@ DMK_HD __forceinline__ void dot_state(const DmkPt<LAW, NS, ND>& p, double* __res
   else if constexpr (LAW == DMK_LAW_PHENOPOWERLAW) pheno_dotState(p, p.S, dot);
   else if constexpr (LAW == DMK_LAW_DISLOTWIN) dt_dotState(p, p.S, dot);
   else if constexpr (LAW == DMK_LAW_KINEHARDENING) kh_dotState(p, p.S, dot);
+  else if constexpr (LAW == DMK_LAW_DISLOTUNGSTEN) tu_dotState(p, p.S, dot);
+}
+// plastic_dependentState (phase_mechanical_plastic.f90): derived quantities of the laws that have them, before every stress integration
+template <int LAW, int NS, int ND>
+DMK_HD __forceinline__ void dependent_state(DmkPt<LAW, NS, ND>& p) {
+  if constexpr (LAW == DMK_LAW_DISLOTWIN) { dt_dependentState(p); dt_homogenized_C66(p); }
+  else if constexpr (LAW == DMK_LAW_DISLOTUNGSTEN) tu_dependentState(p);
 }
 // instantaneous state jump after a converged state integration (phase_mechanical_plastic.f90:372-413): kinehardening only; broken?
 template <int LAW, int NS, int ND>
@@ -697,7 +782,7 @@ template <int LAW, int NS, int ND>
 DMK_HD __noinline__ bool integrate_stress(DmkPt<LAW, NS, ND>& p, const DmkNumDev& num, const double (&F)[9],
                                               const double (&Fp0)[9], double dt, DmkCnt& cnt) {
   cnt.stress_calls++;
-  if constexpr (LAW == DMK_LAW_DISLOTWIN) { dt_dependentState(p); dt_homogenized_C66(p); }
+  dependent_state(p);
   double Lpg[9], invFp[9], A[9];
 #pragma unroll
   for (int a = 0; a < 9; a++) Lpg[a] = p.Lp[a];
@@ -725,6 +810,7 @@ DMK_HD __noinline__ bool integrate_stress(DmkPt<LAW, NS, ND>& p, const DmkNumDev
     } else if constexpr (LAW == DMK_LAW_ISOTROPIC) iso_Lp(p, S, Lp_c, iso_c, iso_dev, iso_sq);
     else if constexpr (LAW == DMK_LAW_PHENOPOWERLAW) pheno_Lp(p, S, Lp_c, ddg);
     else if constexpr (LAW == DMK_LAW_KINEHARDENING) kh_Lp(p, S, Lp_c, ddg);
+    else if constexpr (LAW == DMK_LAW_DISLOTUNGSTEN) tu_Lp(p, S, Lp_c, ddg);
     else dt_Lp(p, S, Lp_c, ddg);
     const double atol = fmax(num.eps_rel_Lp * fmax(norm9(Lpg), norm9(Lp_c)), num.eps_abs_Lp);
 #pragma unroll
@@ -752,7 +838,7 @@ DMK_HD __noinline__ bool integrate_stress(DmkPt<LAW, NS, ND>& p, const DmkNumDev
       if constexpr (LAW == DMK_LAW_ISOTROPIC) iso_jac(p, dt, G, iso_c, iso_dev, iso_sq, J);
       else if constexpr (LAW == DMK_LAW_PHENOPOWERLAW) pheno_jac(p, dt, G, ddg, J);
       else if constexpr (LAW == DMK_LAW_DISLOTWIN) dt_jac(p, dt, G, ddg, J);
-      else if constexpr (LAW == DMK_LAW_KINEHARDENING) kh_jac(p, dt, G, ddg, J);
+      else if constexpr (LAW == DMK_LAW_KINEHARDENING || LAW == DMK_LAW_DISLOTUNGSTEN) kh_jac(p, dt, G, ddg, J);   // same rank-one form
       if (solve9(J, res)) return true;
 #pragma unroll
       for (int a = 0; a < 9; a++) delta[a] = -res[a];

@@ -245,6 +245,57 @@ void make_phase(const std::string& name, const YamlNode& cfg, double T, dmk_phas
         bad(where + ": kinehardening: dot_gamma_0, n, xi_0, xi_inf, chi_inf must be positive");        // :164-169
     state_init.resize(6 * (size_t)ns, 0.0);
     atol.assign(2 * (size_t)ns, opt_d(pl, "atol_xi", 1.0)); atol.resize(3 * (size_t)ns, opt_d(pl, "atol_gamma", 1.0e-6)); atol.resize(6 * (size_t)ns, 0.0);
+  } else if (kind == "dislotungsten") {                // plastic_dislotungsten_init, phase_mechanical_plastic_dislotungsten.f90:79-268
+    const YamlNode& pl = *plp;
+    ph.law = DMK_LAW_DISLOTUNGSTEN;
+    const std::vector<int> N_sl = pl.has("N_sl") ? pl.get("N_sl")->as_ints() : std::vector<int>();
+    const int ns = total(N_sl);
+    if (ns < 1 || ns > DMK_MAX_SL) bad(where + ": dislotungsten needs 1.." + std::to_string(DMK_MAX_SL) + " slip systems");
+    ph.n_sl = ns; ph.n_tw = 0;
+    const std::string bound = pl.has("isotropic_bound") ? pl.get("isotropic_bound")->scalar : "isostrain";
+    ph.dt_mu = isotropic_mu(ph.C66, bound); ph.dt_nu = isotropic_nu(ph.C66, bound);
+    ph.dt_kB_T = K_B * T;
+    std::vector<double> P((size_t)ns * 9);
+    crystal_check(dmk_crystal_schmid_slip(lat, N_sl.data(), (int)N_sl.size(), P.data()), where);
+    memcpy(ph.P_sl, P.data(), P.size() * sizeof(double));
+    if (lattice == "cI") {
+      const std::vector<double> a_nS = pl.has("a_nonSchmid_110") ? pl.get("a_nonSchmid_110")->as_doubles() : std::vector<double>();
+      const double none = 0.0;
+      crystal_check(dmk_crystal_schmid_slip_ns(lat, N_sl.data(), (int)N_sl.size(), a_nS.empty() ? &none : a_nS.data(), (int)a_nS.size(), +1, P.data()), where);
+      memcpy(ph.P_nS_pos, P.data(), P.size() * sizeof(double));
+      crystal_check(dmk_crystal_schmid_slip_ns(lat, N_sl.data(), (int)N_sl.size(), a_nS.empty() ? &none : a_nS.data(), (int)a_nS.size(), -1, P.data()), where);
+      memcpy(ph.P_nS_neg, P.data(), P.size() * sizeof(double));
+    } else {
+      memcpy(ph.P_nS_pos, P.data(), P.size() * sizeof(double));
+      for (int a = 0; a < ns; a++) for (int k = 0; k < 9; k++) ph.P_nS_neg[a][k] = -P[(size_t)a * 9 + k];
+    }
+    ph.dt_omit_dipoles = opt_b(pl, "no_dipole_formation", false) ? 1 : 0;
+    ph.dt_D = need(pl, "D", where).as_double(); ph.tu_D_0 = need(pl, "D_0", where).as_double(); ph.dt_Q_cl = need(pl, "Q_cl", where).as_double();
+    const double half = 0.5;
+    const std::vector<double> f_edge = fam(pl, "f_edge", N_sl, &half, where);
+    const std::vector<double> rho_mob_0 = fam(pl, "rho_mob_0", N_sl, nullptr, where), rho_dip_0 = fam(pl, "rho_dip_0", N_sl, nullptr, where);
+    const std::vector<double> b_sl = fam(pl, "b_sl", N_sl, nullptr, where);
+    put(ph.dt_b_sl, b_sl, DMK_MAX_SL, "b_sl"); put(ph.dt_Q_sl, fam(pl, "Q_s", N_sl, nullptr, where), DMK_MAX_SL, "Q_s");
+    put(ph.dt_i_sl, fam(pl, "i_sl", N_sl, nullptr, where), DMK_MAX_SL, "i_sl"); put(ph.dt_tau_0, fam(pl, "tau_Peierls", N_sl, nullptr, where), DMK_MAX_SL, "tau_Peierls");
+    put(ph.dt_p, fam(pl, "p_sl", N_sl, nullptr, where), DMK_MAX_SL, "p_sl"); put(ph.dt_q, fam(pl, "q_sl", N_sl, nullptr, where), DMK_MAX_SL, "q_sl");
+    put(ph.dt_B, fam(pl, "B", N_sl, nullptr, where), DMK_MAX_SL, "B");
+    put(ph.tu_h, fam(pl, "h", N_sl, nullptr, where), DMK_MAX_SL, "h"); put(ph.tu_w, fam(pl, "w", N_sl, nullptr, where), DMK_MAX_SL, "w");
+    put(ph.tu_omega, fam(pl, "omega", N_sl, nullptr, where), DMK_MAX_SL, "omega");
+    const double D_a = need(pl, "D_a", where).as_double(), f_at = need(pl, "f_at", where).as_double();
+    for (int a = 0; a < ns; a++) { ph.dt_d_caron[a] = b_sl[a] * D_a; ph.tu_f_at[a] = b_sl[a] * b_sl[a] * b_sl[a] * f_at; }
+    {
+      const std::vector<double> h = need(pl, "h_sl-sl", where).as_doubles();
+      std::vector<double> M((size_t)ns * ns);
+      crystal_check(dmk_crystal_interaction("sl-sl", lat, N_sl.data(), (int)N_sl.size(), N_sl.data(), (int)N_sl.size(), h.data(), (int)h.size(), M.data()), where);
+      for (int a = 0; a < ns; a++) for (int b = 0; b < ns; b++) ph.h_sl_sl[a][b] = M[(size_t)a * ns + b];
+      crystal_check(dmk_crystal_forest_projection(lat, N_sl.data(), (int)N_sl.size(), f_edge.data(), M.data()), where);
+      for (int a = 0; a < ns; a++) for (int b = 0; b < ns; b++) ph.dt_forest[a][b] = M[(size_t)a * ns + b];
+    }
+    bool okp = ph.tu_D_0 >= 0.0 && ph.dt_Q_cl > 0.0 && D_a >= 0.0 && f_at > 0.0;                         // :205-215
+    for (int a = 0; a < ns; a++) okp = okp && rho_mob_0[a] >= 0.0 && rho_dip_0[a] >= 0.0 && b_sl[a] > 0.0 && ph.dt_Q_sl[a] > 0.0 && ph.dt_tau_0[a] >= 0.0 && ph.dt_B[a] >= 0.0;
+    if (!okp) bad(where + ": dislotungsten: parameter out of range");
+    state_init = rho_mob_0; state_init.insert(state_init.end(), rho_dip_0.begin(), rho_dip_0.end()); state_init.resize(3 * (size_t)ns, 0.0);
+    atol.assign(2 * (size_t)ns, opt_d(pl, "atol_rho", 1.0)); atol.resize(3 * (size_t)ns, opt_d(pl, "atol_gamma", 1.0e-6));
   } else if (kind == "dislotwin") {
     const YamlNode& pl = *plp;
     ph.law = DMK_LAW_DISLOTWIN;

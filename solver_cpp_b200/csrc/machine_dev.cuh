@@ -110,7 +110,7 @@ DMK_HD __forceinline__ void machine_stress_prologue(DmkMachine<LAW, NS, ND>& m, 
   cnt.state_iter++;
   for (int i = 0; i < ns; i++) { m.last2[i] = (m.it > 1) ? m.last1[i] : 0.0; m.last1[i] = m.dot[i]; }
   cnt.stress_calls++;
-  if constexpr (LAW == DMK_LAW_DISLOTWIN) { dt_dependentState(p); dt_homogenized_C66(p); }
+  dependent_state(p);
 #pragma unroll
   for (int a = 0; a < 9; a++) m.Lpg[a] = p.Lp[a];
   if (invert33(m.Fp0, m.invFp)) { m.converged = false; m.state = M_SUBSTEP; return; }
@@ -142,6 +142,7 @@ DMK_HD __forceinline__ void machine_lp_iteration(DmkMachine<LAW, NS, ND>& m, con
   } else if constexpr (LAW == DMK_LAW_ISOTROPIC) iso_Lp(p, m.S, Lp_c, iso_c, iso_dev, iso_sq);
   else if constexpr (LAW == DMK_LAW_PHENOPOWERLAW) pheno_Lp(p, m.S, Lp_c, m.ddg);
   else if constexpr (LAW == DMK_LAW_KINEHARDENING) kh_Lp(p, m.S, Lp_c, m.ddg);
+  else if constexpr (LAW == DMK_LAW_DISLOTUNGSTEN) tu_Lp(p, m.S, Lp_c, m.ddg);
   else dt_Lp(p, m.S, Lp_c, m.ddg);
   const double atol = fmax(num.eps_rel_Lp * fmax(norm9(m.Lpg), norm9(Lp_c)), num.eps_abs_Lp);
 #pragma unroll
@@ -169,7 +170,7 @@ DMK_HD __forceinline__ void machine_lp_iteration(DmkMachine<LAW, NS, ND>& m, con
     if constexpr (LAW == DMK_LAW_ISOTROPIC) iso_jac(p, dt, G, iso_c, iso_dev, iso_sq, J);
     else if constexpr (LAW == DMK_LAW_PHENOPOWERLAW) pheno_jac(p, dt, G, m.ddg, J);
     else if constexpr (LAW == DMK_LAW_DISLOTWIN) dt_jac(p, dt, G, m.ddg, J);
-    else if constexpr (LAW == DMK_LAW_KINEHARDENING) kh_jac(p, dt, G, m.ddg, J);
+    else if constexpr (LAW == DMK_LAW_KINEHARDENING || LAW == DMK_LAW_DISLOTUNGSTEN) kh_jac(p, dt, G, m.ddg, J);
     if (solve9(J, res)) { m.converged = false; m.state = M_SUBSTEP; return; }
 #pragma unroll
     for (int a = 0; a < 9; a++) m.delta[a] = -res[a];

@@ -84,6 +84,13 @@ DMK_HD __noinline__ void full_dLp_dMp(DmkPt<LAW, NS, ND>& p, double* __restrict_
       const double* PnS = (dg > 0.0) ? d.p.P_nS_pos[i] : d.p.P_nS_neg[i];
       for (int a = 0; a < 9; a++) for (int b = 0; b < 9; b++) dM[9 * a + b] += ddg * d.p.P_sl[i][a] * PnS[b];
     }
+  } else if constexpr (LAW == DMK_LAW_DISLOTUNGSTEN) {           // phase_mechanical_plastic_dislotungsten.f90:270-310
+    for (int i = 0; i < d.p.n_sl; i++) {
+      double dg, ddg, te;
+      tu_slip_rate(p, p.S, i, true, dg, ddg, te);
+      const double* PnS = (dg > 0.0) ? d.p.P_nS_pos[i] : d.p.P_nS_neg[i];
+      for (int a = 0; a < 9; a++) for (int b = 0; b < 9; b++) dM[9 * a + b] += ddg * d.p.P_sl[i][a] * PnS[b];
+    }
   } else if constexpr (LAW == DMK_LAW_DISLOTWIN) {
     const int ns = d.p.n_sl, nt = d.p.n_tw;
     double dgs[DMK_MAX_SL];

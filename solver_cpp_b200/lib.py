@@ -62,6 +62,7 @@ class Phase(C.Structure):
         ('dt_pair', (C.c_int * 2) * MAX_TW), ('dt_C66_tw', _d(MAX_TW, 36)),
         ('kh_chi_inf', _d(MAX_SL)), ('kh_h_0_xi', _d(MAX_SL)), ('kh_h_0_chi', _d(MAX_SL)), ('kh_h_inf_xi', _d(MAX_SL)),
         ('kh_h_inf_chi', _d(MAX_SL)),
+        ('tu_h', _d(MAX_SL)), ('tu_w', _d(MAX_SL)), ('tu_omega', _d(MAX_SL)), ('tu_f_at', _d(MAX_SL)), ('tu_D_0', C.c_double),
     ]
 
 

@@ -16,7 +16,7 @@ from . import lib as L
 
 T_ROOM = 293.15                # constants.f90:12
 K_B = 1.380649e-23             # constants.f90:13
-LAW_NONE, LAW_ISOTROPIC, LAW_PHENOPOWERLAW, LAW_DISLOTWIN, LAW_KINEHARDENING = 0, 1, 2, 3, 4
+LAW_NONE, LAW_ISOTROPIC, LAW_PHENOPOWERLAW, LAW_DISLOTWIN, LAW_KINEHARDENING, LAW_DISLOTUNGSTEN = 0, 1, 2, 3, 4, 5
 
 
 def _ia(v):
@@ -266,6 +266,43 @@ def make_phase(cfg, T=T_ROOM):
         state_init = np.concatenate([_expand(pl['xi_0'], N_sl), np.zeros(5 * ns)])
         atol = np.concatenate([np.full(2 * ns, float(pl.get('atol_xi', 1.0))), np.full(ns, float(pl.get('atol_gamma', 1.0e-6))),
                                np.zeros(3 * ns)])
+    elif kind == 'dislotungsten':                    # plastic_dislotungsten_init, phase_mechanical_plastic_dislotungsten.f90:79-268
+        ph.law = LAW_DISLOTUNGSTEN
+        N_sl = list(pl.get('N_sl', []))
+        ns = int(np.sum(N_sl))
+        if ns == 0:
+            raise L.DmkError('dislotungsten without slip systems')
+        ph.n_sl, ph.n_tw = ns, 0
+        bound = pl.get('isotropic_bound', 'isostrain')
+        ph.dt_mu, ph.dt_nu = isotropic_mu(C66, bound), isotropic_nu(C66, bound)
+        ph.dt_kB_T = K_B * T
+        P = schmid_slip(lattice, N_sl)
+        _set(ph.P_sl, P)
+        if lattice == 'cI':
+            a_nS = pl.get('a_nonSchmid_110', [])
+            _set(ph.P_nS_pos, schmid_slip(lattice, N_sl, a_nS, +1))
+            _set(ph.P_nS_neg, schmid_slip(lattice, N_sl, a_nS, -1))
+        else:
+            _set(ph.P_nS_pos, P)
+            _set(ph.P_nS_neg, -P)
+        ph.dt_omit_dipoles = int(bool(pl.get('no_dipole_formation', False)))
+        ph.dt_D, ph.tu_D_0, ph.dt_Q_cl = pl['D'], pl['D_0'], pl['Q_cl']
+        f_edge = _expand(pl.get('f_edge', [0.5] * len(N_sl)), N_sl)
+        rho_mob_0, rho_dip_0 = _expand(pl['rho_mob_0'], N_sl), _expand(pl['rho_dip_0'], N_sl)
+        b_sl = _expand(pl['b_sl'], N_sl)
+        _set(ph.dt_b_sl, b_sl); _set(ph.dt_Q_sl, _expand(pl['Q_s'], N_sl)); _set(ph.dt_i_sl, _expand(pl['i_sl'], N_sl))
+        _set(ph.dt_tau_0, _expand(pl['tau_Peierls'], N_sl)); _set(ph.dt_p, _expand(pl['p_sl'], N_sl))
+        _set(ph.dt_q, _expand(pl['q_sl'], N_sl)); _set(ph.dt_B, _expand(pl['B'], N_sl))
+        _set(ph.tu_h, _expand(pl['h'], N_sl)); _set(ph.tu_w, _expand(pl['w'], N_sl)); _set(ph.tu_omega, _expand(pl['omega'], N_sl))
+        _set(ph.dt_d_caron, b_sl * float(pl['D_a'])); _set(ph.tu_f_at, b_sl ** 3 * float(pl['f_at']))
+        _set(ph.h_sl_sl, interaction('sl-sl', lattice, N_sl, N_sl, pl['h_sl-sl']))
+        _set(ph.dt_forest, forest_projection(lattice, N_sl, f_edge))
+        if ph.tu_D_0 < 0.0 or ph.dt_Q_cl <= 0.0 or np.any(rho_mob_0 < 0.0) or np.any(rho_dip_0 < 0.0) or np.any(b_sl <= 0.0) \
+                or np.any(np.asarray(pl['Q_s'], float) <= 0.0) or np.any(np.asarray(pl['tau_Peierls'], float) < 0.0) \
+                or np.any(np.asarray(pl['B'], float) < 0.0) or float(pl['D_a']) < 0.0 or float(pl['f_at']) <= 0.0:
+            raise L.DmkError('dislotungsten: parameter out of range')                   # the reference's sanity checks (:205-215)
+        state_init = np.concatenate([rho_mob_0, rho_dip_0, np.zeros(ns)])
+        atol = np.concatenate([np.full(2 * ns, float(pl.get('atol_rho', 1.0))), np.full(ns, float(pl.get('atol_gamma', 1.0e-6)))])
     elif kind == 'dislotwin':
         ph.law = LAW_DISLOTWIN
         N_sl, N_tw, N_tr = list(pl.get('N_sl', [])), list(pl.get('N_tw', [])), list(pl.get('N_tr', []))

@@ -38,6 +38,13 @@ HOOKE_AISI304 = {'type': 'Hooke', 'C_11': 204.6e9, 'C_12': 137.7e9, 'C_44': 126.
 KINEHARDENING_317L = {'type': 'kinehardening', 'N_sl': [12], 'xi_0': [0.070e9], 'xi_inf': [0.015e9], 'h_0_xi': [0.065e9],
                       'h_inf_xi': [0.045e9], 'chi_inf': [0.027e9], 'h_0_chi': [55e9], 'h_inf_chi': [1.3e9], 'n': [20],
                       'dot_gamma_0': [1e-4], 'h_sl-sl': [1, 1, 1, 1, 1, 1, 1]}                          # kinehardening_317L.yaml
+HOOKE_W = {'type': 'Hooke', 'C_11': 524.3e9, 'C_11,T': -4.794e7, 'C_12': 205.1e9, 'C_12,T': -2.836e6, 'C_44': 160.7e9,
+           'C_44,T': -1.269e7, 'T_ref': 293.15}                                                        # Hooke_W.yaml
+DISLOTUNGSTEN_W = {'type': 'dislotungsten', 'N_sl': [12], 'b_sl': [2.72e-10], 'rho_mob_0': [1.0e9], 'rho_dip_0': [1.0],
+                   'Q_s': [2.61154e-19], 'B': [8.3e-5], 'omega': [9.1e11], 'p_sl': [0.86], 'q_sl': [1.69], 'tau_Peierls': [2.03e9],
+                   'h': [2.566e-10], 'h_sl-sl': [0.009, 0.72, 0.009, 0.05, 0.05, 0.06, 0.09], 'w': [2.992e-9],
+                   'a_nonSchmid_110': [0.0, 0.56, 0.75], 'i_sl': [1], 'D': 1.0e20, 'D_a': 1.0, 'D_0': 0.0, 'f_at': 1,
+                   'Q_cl': 1.0}                                                                        # dislotungsten_W.yaml
 
 PHASES = {
     'Al_pheno': {'lattice': 'cF', 'mechanical': {'elastic': HOOKE_AL, 'plastic': PHENO_AL}},
@@ -45,6 +52,7 @@ PHASES = {
     'Al_iso': {'lattice': 'cF', 'mechanical': {'elastic': HOOKE_AL_T, 'plastic': ISOTROPIC}},
     'Al_elastic': {'lattice': 'cF', 'mechanical': {'elastic': HOOKE_AL_T}},
     'TWIP': {'lattice': 'cF', 'mechanical': {'elastic': HOOKE_TWIP, 'plastic': DISLOTWIN_TWIP}},
+    'W_tungsten': {'lattice': 'cI', 'mechanical': {'elastic': HOOKE_W, 'plastic': DISLOTUNGSTEN_W}},
     'Steel_kine': {'lattice': 'cF', 'mechanical': {'elastic': HOOKE_AISI304, 'plastic': KINEHARDENING_317L}},
 }
 

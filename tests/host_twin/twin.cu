@@ -107,7 +107,7 @@ extern "C" int twin_point(const dmk_phase* phase, const dmk_numerics* n, const d
   for (int a = 0; a < p.n_sl; a++) d.n_sl_int[a] = small_int(p.n_sl_exp[a]);
   for (int a = 0; a < p.n_tw; a++) d.n_tw_int[a] = small_int(p.n_tw_exp[a]);
   d.iso_n_int = small_int(p.iso_n);
-  d.nonschmid = nons; d.n_dep = (p.law == DMK_LAW_DISLOTWIN) ? 2 * p.n_sl + p.n_tw : 0;
+  d.nonschmid = nons; d.n_dep = (p.law == DMK_LAW_DISLOTWIN) ? 2 * p.n_sl + p.n_tw : (p.law == DMK_LAW_DISLOTUNGSTEN) ? 2 * p.n_sl : 0;
   DmkNumDev nd;
   nd.r_cutback_min = n->r_cutback_min; nd.r_cutback = n->r_cutback; nd.r_increase = n->r_increase; nd.eps_rel_state = n->eps_rel_state;
   nd.N_iter_state_max = n->N_iter_state_max; nd.N_iter_Lp_max = n->N_iter_Lp_max; nd.r_linesearch_Lp = n->r_linesearch_Lp;
@@ -139,6 +139,7 @@ generic:
     case DMK_LAW_ISOTROPIC: return run_point<DMK_LAW_ISOTROPIC, 1, 0>(ARGS);
     case DMK_LAW_PHENOPOWERLAW: return run_point<DMK_LAW_PHENOPOWERLAW, 2 * DMK_MAX_SYS, 0>(ARGS);
     case DMK_LAW_KINEHARDENING: return run_point<DMK_LAW_KINEHARDENING, DMK_MAX_STATE, 0>(ARGS);
+    case DMK_LAW_DISLOTUNGSTEN: return run_point<DMK_LAW_DISLOTUNGSTEN, 3 * DMK_MAX_SL, 2 * DMK_MAX_SL>(ARGS);
     default: return run_point<DMK_LAW_DISLOTWIN, DMK_MAX_STATE, DMK_MAX_DEP>(ARGS);
   }
 }

@@ -170,6 +170,55 @@ def test_kinehardening_matches_oracle_through_a_load_reversal(integrator):
     assert np.abs(st[:, nsl:2 * nsl]).max() > 1e5                                   # a back stress developed
 
 
+def test_dislotungsten_matches_oracle_through_first_yield():
+    """dislotungsten (phase_mechanical_plastic_dislotungsten.f90; cI tungsten, parameters and non-Schmid coefficients of
+    dislotungsten_W.yaml; unpinned: no fixture in the reference tree) in the reference-order kernel against the oracle from the
+    elastic range through first yield (P11 about 2 GPa, where this parameter set stays integrable): P 1e-9, state and the
+    dependent state (Lambda_sl, tau_pass; carried from call to call in HBM) 1e-9, equal Lp iteration counts, tangent 1e-8."""
+    cells, dt = (8, 6, 5), 1.0
+    g, o = _setup(cells, 9, 'W_tungsten')
+    n = int(np.prod(cells))
+    ns, nsl = o.phases[0].n_state, o.phases[0].n_sl
+    assert ns == 3 * nsl
+    nd = 2 * nsl
+    atol = np.ctypeslib.as_array(o.phases[0].atol)[:ns].copy()
+    dep0 = g.get_state('dep', int(g.lib.dmk_max_dep(g.ctx)))[:, :nd]
+    assert _rel(dep0, o.a['dep'][:, :nd]) < 1e-13                        # crystallite_init: dependent state of the initial state
+    rng = np.random.default_rng(9)
+    nx, ny, nz = cells
+    fluct = rng.standard_normal((nz, ny, nx, 3, 3))
+    clean = np.ones(n, bool)
+    compared = 0
+    for k, e in enumerate([1.5e-3, 3.0e-3, 4.0e-3, 4.4e-3, 4.8e-3, 5.1e-3]):
+        F = np.eye(3) + np.diag([e, -0.3 * e, -0.3 * e]) + 5.0e-5 * (k + 1) * fluct
+        ill_o = o.mechanical_response(F.reshape(n, 9), dt)
+        P_o, dPdF_o = o.mechanical_response2(dt, tangent=(k == 4))
+        P = g.to_natural(g.constitutive_response(g.to_device(F), dt)).reshape(n, 3, 3)
+        assert g.terminally_ill() == ill_o and not ill_o
+        clean &= (o.point_cutbacks == 0) & (g.get_state('cutbacks', 1)[:, 0] == 0)
+        same = clean & (g.get_state('lp_iter', 1)[:, 0] == o.point_lp_iter)
+        assert clean.mean() > 0.5 and same.sum() >= 0.98 * clean.sum(), (k, clean.mean(), same.sum() / max(clean.sum(), 1))
+        err = _pointwise_rel(P, P_o)
+        assert (err[same] < RTOL).all() and (err[clean] < 1e-6).all(), (k, err[same].max(), err[clean].max())
+        st, st_o = g.get_state('state', o.max_state)[:, :ns], o.a['state'][:, :ns]
+        es = np.abs(st - st_o) / np.maximum(np.abs(st_o), atol)
+        assert (es[same] < 10 * RTOL).all(), (k, es[same].max())
+        dep = g.get_state('dep', int(g.lib.dmk_max_dep(g.ctx)))[:, :nd]
+        assert (_pointwise_rel(dep, o.a['dep'][:, :nd])[same] < 10 * RTOL).all()
+        if k == 4:
+            from solver_cpp_b200.grid import fortran_to_c3333
+            _, _, _, d = g.tangent_response(dt, materialise=True)
+            dP = np.stack([fortran_to_c3333(r) for r in d.cpu().numpy()])
+            et = _pointwise_rel(dP, dPdF_o)
+            assert (et[same] < 1e-8).all(), (k, et[same].max())
+        compared += int(same.sum())
+        clean &= same
+        g.materialpoint_forward()
+        o.forward()
+    assert compared > 0.5 * 6 * n
+    assert np.abs(o.a['Lp']).max() > 1e-6 and o.a['state'][:, :nsl].max() > 10 * 1.0e9       # plastic flow, dislocations multiplied
+
+
 def test_newton_decisions_rarely_flip_on_a_solver_iterate():
     """Cu polycrystal, homogeneous pre-strain, then a smooth in-grain fluctuation of the size a running solve produces
     (no cut-backs; every third cell needs the line search): per-cell Lp iteration counts equal the oracle's on all but

@@ -293,3 +293,51 @@ def test_twin_matches_oracle_kinehardening_with_load_reversal():
     assert compared > 0.8 * 8 * n
     assert (sgn > 0.5).any() and (sgn < -0.5).any() and (chi_flip > 0.0).any()      # directions were set and flipped
     assert np.abs(st[:, nsl:2 * nsl]).max() > 1e5                                   # a back stress developed
+
+
+def test_twin_matches_oracle_dislotungsten():
+    """dislotungsten (phase_mechanical_plastic_dislotungsten.f90; cI tungsten with the non-Schmid coefficients of
+    dislotungsten_W.yaml) through the product's device functions against the oracle, from the elastic range through first yield
+    (P11 about 2 GPa): kinetics with kink-pair nucleation and phonon drag, dislocation multiplication, the dependent state
+    (Lambda_sl, tau_pass) carried from call to call, and the tangent.  No fixture in the reference tree: unpinned."""
+    import twin
+    from solver_cpp_b200 import workloads as W, material as M
+    lib = twin.build()
+    cells = (4, 3, 3)
+    material, material_at, size = W.polycrystal(cells, 6, 'W_tungsten', 0)
+    o = ConstitutiveOracle(material, material_at)
+    m = M.Material(material, material_at)
+    num = M.make_numerics()
+    n = int(np.prod(cells))
+    ns, nsl = o.phases[0].n_state, o.phases[0].n_sl
+    assert ns == 3 * nsl and m.phases[0].n_state == ns
+    nd = 2 * nsl
+    dep = o.a['dep'][:, :nd].copy()
+    assert (dep[:, :nsl] > 0.0).all() and (dep[:, nsl:] > 0.0).all()          # crystallite_init: dependent state of the initial state
+    rng = np.random.default_rng(9)
+    fluct = rng.standard_normal((n, 3, 3))
+    Lp = np.zeros((n, 9))
+    atol = np.ctypeslib.as_array(o.phases[0].atol)[:ns].copy()
+    compared = 0
+    for k, e in enumerate([1.5e-3, 3.0e-3, 4.0e-3, 4.4e-3, 4.8e-3, 5.1e-3, 5.4e-3]):   # (the W parameter set turns ill soon after yield)
+        F = np.eye(3) + np.diag([e, -0.3 * e, -0.3 * e]) + 5.0e-5 * (k + 1) * fluct
+        snap = o.snapshot()
+        assert not o.mechanical_response(F.reshape(n, 9), 1.0)
+        P_o, dPdF_o = o.mechanical_response2(1.0, tangent=True)
+        for i in range(n):
+            r = twin.run_point(lib, m.phases[0], num, snap['F0'][i], F[i].reshape(9), snap['Fp0'][i], snap['Lp0'][i], Lp[i],
+                               snap['S0'][i][V6], snap['state0'][i][:ns], dep[i], 1.0, tangent=True)
+            Lp[i] = r['Lp']; dep[i] = r['dep']
+            assert r['ok']
+            if o.point_cutbacks[i]:
+                continue
+            err = np.abs(r['P'] - o.a['P'][i]).max() / np.abs(o.a['P'][i]).max()
+            err = max(err, np.abs(r['Fp'] - o.a['Fp'][i]).max())
+            err = max(err, (np.abs(r['state'][:ns] - o.a['state'][i, :ns]) / np.maximum(np.abs(o.a['state'][i, :ns]), atol)).max())
+            err = max(err, (np.abs(r['dep'][:nd] - o.a['dep'][i, :nd]) / np.abs(o.a['dep'][i, :nd])).max())
+            et = np.abs(r['dPdF'] - dPdF_o[i].reshape(81)).max() / np.abs(dPdF_o[i]).max()
+            assert err < 1e-9 and et < 1e-8, (k, i, err, et)
+            compared += 1
+        o.forward()
+    assert compared > 0.7 * 7 * n
+    assert np.abs(o.a['Lp']).max() > 1e-6 and o.a['state'][:, :nsl].max() > 10 * 1.0e9       # plastic flow, dislocations multiplied
