@@ -164,6 +164,15 @@ void dmk_qu2om(const double q[4], double om[9] /* row-major */);
 int dmk_material_init(dmk_ctx* ctx, const dmk_phase* phases, int n_phases, const int* phase_of_cell,
                       const double* O_of_cell /* [n_local][9] row-major rotation matrices (Fp0) */,
                       const dmk_numerics* num);
+/* isostrain homogenisation (homogenization_mechanical_isostrain.f90:36-45 + mechanical_homogenize, homogenization_mechanical.f90:
+ * 125-145): n_constituents material points per cell, every one of them sees the cell's deformation gradient, the cell's P and dPdF
+ * are the volume-fraction weighted sums.  Point k * n_local_cells + cell is constituent k of the cell: phase_of_point [n_const *
+ * cells], O_of_point [..][9] row-major, v_of_point [..] (positive, summing to 1 per cell).  Per-point arrays (dmk_get_state /
+ * dmk_set_state) then hold n_const * cells rows; every field crossing the boundary stays per cell.  n_constituents = 1 is
+ * dmk_material_init. */
+int dmk_material_init_constituents(dmk_ctx* ctx, const dmk_phase* phases, int n_phases, int n_constituents, const int* phase_of_point,
+                                   const double* O_of_point, const double* v_of_point, const dmk_numerics* num);
+int dmk_n_constituents(dmk_ctx* ctx);
 /* f_homogenization_mechanical_response + _response2 (P only): integrate every local cell from its *0 state to the
  * deformation gradient field d_F; writes d_P, the ill flag, and the slab's sum of P. */
 int dmk_constitutive_response(dmk_ctx* ctx, const double* d_F, double* d_P, double dt);
@@ -279,6 +288,11 @@ dmk_ctx* dmk_bound_context(void);       /* the context f_materialpoint_initDamas
  * dmk_numerics (a NULL / empty path gives the defaults) -- the C++ twin of solver_cpp_b200/material.py */
 int dmk_material_from_yaml(const char* material_yaml_path, double T, dmk_phase* phases, int max_phases, int* n_phases,
                            int* phase_of_material, double* O_of_material, int max_materials, int* n_materials);
+/* ... with several constituents per material entry (material.f90:135-161; homogenisation types pass and isostrain): entry (m, k)
+ * of the per-material tables sits at m * max_constituents + k; v = volume fraction (the fractions of an entry sum to 1) */
+int dmk_material_constituents_from_yaml(const char* material_yaml_path, double T, dmk_phase* phases, int max_phases, int* n_phases,
+                                        int max_constituents, int* n_constituents_of_material, int* phase_of_material,
+                                        double* O_of_material, double* v_of_material, int max_materials, int* n_materials);
 int dmk_numerics_from_yaml(const char* numerics_yaml_path, dmk_numerics* num, int* derivative, int* divergence_correction);
 void f_homogenization_fetch_tensor_pointers(double** homogenization_F0, double** homogenization_F,
                                             double** homogenization_P, double** homogenization_dPdF,

@@ -274,29 +274,56 @@ def make_phase(name, phase_cfg, T=T_ROOM):
 
 
 class ConstitutiveOracle:
-    """Holds the per-point state of all cells (one constituent per cell) and exposes the six
-    reference entry points (homogenization.f90:219-324,491-510; materialpoint.f90:208)."""
+    """Holds the per-point state of all material points and exposes the six reference entry points
+    (homogenization.f90:219-324,491-510; materialpoint.f90:208).
+
+    Homogenisation: "pass" (one constituent per cell) or "isostrain" (homogenization_mechanical_isostrain.f90:36-45: every
+    constituent of a cell sees the cell's F; mechanical_homogenize, homogenization_mechanical.f90:125-145: P and dPdF of the cell
+    are the sums over the constituents weighted by their volume fractions, constituent 1 first).  Material point
+    k * n_cells + cell is constituent k of the cell; all materials in use must have the same number of constituents."""
 
     def __init__(self, material, material_at, num_phase_mech=None, T=T_ROOM, threads=None):
         self.lib = C.CDLL(build())
         assert self.lib.orc_sizeof_phase() == C.sizeof(Phase), 'struct layout mismatch'
         assert self.lib.orc_sizeof_num() == C.sizeof(Numerics)
         material_at = np.asarray(material_at).reshape(-1)
-        self.n = n = material_at.size
+        self.n_cells = material_at.size
         phase_names = list(material['phase'].keys())
         self.phase_names = phase_names
         self.phases = (Phase * len(phase_names))(*[make_phase(k, material['phase'][k], T) for k in phase_names])
         self.num = make_numerics(num_phase_mech)
         mats = material['material']
-        ph_of_mat = np.empty(len(mats), dtype=np.int32)
-        O_of_mat = np.empty((len(mats), 3, 3))
-        for m, entry in enumerate(mats):
+        used = np.unique(material_at)
+        counts = {len(mats[m]['constituents']) for m in used}
+        if len(counts) != 1:
+            raise NotImplementedError('materials with different numbers of constituents in one grid')
+        self.n_const = nc = counts.pop()
+        ph_of_mat = np.zeros((len(mats), nc), dtype=np.int32)
+        O_of_mat = np.tile(np.eye(3), (len(mats), nc, 1, 1))
+        v_of_mat = np.zeros((len(mats), nc))
+        for m in used:
+            entry = mats[m]
             cons = entry['constituents']
-            if len(cons) != 1:
-                raise NotImplementedError('only single-constituent (pass) homogenization')
-            ph_of_mat[m] = phase_names.index(cons[0]['phase'])
-            O_of_mat[m] = crystal.qu2om(cons[0]['O'])
-        self.phase_of = np.ascontiguousarray(ph_of_mat[material_at])
+            homog = material.get('homogenization', {}).get(entry.get('homogenization'), None)
+            if homog is not None:
+                # material.f90:145 (IO_error 148) and the mechanical types this oracle restates
+                if int(homog.get('N_constituents', len(cons))) != len(cons):
+                    raise ValueError('material %d: %d constituents, homogenization asks for %s' % (m, len(cons), homog['N_constituents']))
+                htype = homog.get('mechanical', {}).get('type', 'pass')
+                if htype not in ('pass', 'isostrain') or (htype == 'pass' and len(cons) != 1):
+                    raise NotImplementedError('mechanical homogenization %s with %d constituents' % (htype, len(cons)))
+            for k, con in enumerate(cons):
+                ph_of_mat[m, k] = phase_names.index(con['phase'])
+                O_of_mat[m, k] = crystal.qu2om(con['O'])
+                v_of_mat[m, k] = float(con.get('v', 1.0))
+            if abs(v_of_mat[m].sum() - 1.0) > 1.0e-9:                # material.f90:161 (IO_error 153)
+                raise ValueError('material %d: volume fractions sum to %r' % (m, v_of_mat[m].sum()))
+        self.n = n = self.n_cells * nc                                # material points
+        # point k * n_cells + cell
+        self.v_of = np.ascontiguousarray(v_of_mat[material_at].T.reshape(n))
+        O_of_pt = np.ascontiguousarray(O_of_mat[material_at].transpose(1, 0, 2, 3).reshape(n, 3, 3))
+        ph_of_pt = ph_of_mat[material_at].T.reshape(n)
+        self.phase_of = np.ascontiguousarray(ph_of_pt)
         self.max_state = max(1, max(p.n_state for p in self.phases))
         self.max_dep = max(1, max(2 * p.n_sl + p.n_tw for p in self.phases))
         eye = np.broadcast_to(np.eye(3).reshape(9), (n, 9))
@@ -306,10 +333,10 @@ class ConstitutiveOracle:
         self.a['state'] = np.zeros((n, self.max_state)); self.a['state0'] = np.zeros((n, self.max_state))
         self.a['dep'] = np.zeros((n, self.max_dep))
         # mechanical_init: F = I, Fp = O_0, Fe = V_e0 Fp^T (V_e0 = I), Fi = I; *0 = current
-        Fp = O_of_mat[material_at].reshape(n, 9)
+        Fp = O_of_pt.reshape(n, 9)
         self.a['F'][:] = eye; self.a['F0'][:] = eye
         self.a['Fp'][:] = Fp; self.a['Fp0'][:] = Fp
-        self.a['Fe'][:] = O_of_mat[material_at].transpose(0, 2, 1).reshape(n, 9)
+        self.a['Fe'][:] = O_of_pt.transpose(0, 2, 1).reshape(n, 9)
         self.a['Fi'][:] = eye; self.a['Fi0'][:] = eye
         for i, p in enumerate(self.phases):
             sel = self.phase_of == i
@@ -328,9 +355,14 @@ class ConstitutiveOracle:
         self.terminally_ill = False
         self.threads = threads
 
-    # f_homogenization_mechanical_response
+    # f_homogenization_mechanical_response (mechanical_partition: homogenization_mechanical.f90:95-122)
     def mechanical_response(self, F, dt, cell_start=0, cell_end=None):
-        F = np.ascontiguousarray(np.asarray(F, float).reshape(self.n, 9))
+        F = np.ascontiguousarray(np.asarray(F, float).reshape(self.n_cells, 9))
+        if self.n_const > 1:
+            if cell_start != 0 or cell_end not in (None, self.n_cells):
+                raise NotImplementedError('cell ranges with several constituents per cell')
+            F = np.ascontiguousarray(np.tile(F, (self.n_const, 1)))  # isostrain_partitionDeformation: F = spread(avgF)
+            cell_end = self.n
         cell_end = self.n if cell_end is None else cell_end
         cnt = np.zeros(6, dtype=np.int64)
         self.point_cutbacks[:] = 0
@@ -346,14 +378,27 @@ class ConstitutiveOracle:
             self.terminally_ill = True
         return bool(ill)
 
-    # f_homogenization_mechanical_response2
+    # f_homogenization_mechanical_response2 (mechanical_homogenize: homogenization_mechanical.f90:125-145)
     def mechanical_response2(self, dt, tangent=True):
         P = np.zeros((self.n, 9))
         dPdF = np.zeros((self.n, 81)) if tangent else None
         self.lib.orc_mechanical_response2(self.phases, C.byref(self.num), C.byref(self.st), C.c_double(dt),
                                           C.c_int(0), C.c_int(self.n), P.ctypes.data_as(C.POINTER(C.c_double)),
                                           dPdF.ctypes.data_as(C.POINTER(C.c_double)) if tangent else None)
-        return P.reshape(self.n, 3, 3), (dPdF.reshape(self.n, 3, 3, 3, 3) if tangent else None)
+        if self.n_const > 1:
+            nc, m = self.n_const, self.n_cells
+            v = self.v_of.reshape(nc, m, 1)
+            Pp = P.reshape(nc, m, 9)
+            P = Pp[0] * v[0]
+            for k in range(1, nc):
+                P = P + Pp[k] * v[k]
+            if tangent:
+                Tp = dPdF.reshape(nc, m, 81)
+                dPdF = Tp[0] * v[0]
+                for k in range(1, nc):
+                    dPdF = dPdF + Tp[k] * v[k]
+        m = self.n_cells
+        return P.reshape(m, 3, 3), (dPdF.reshape(m, 3, 3, 3, 3) if tangent else None)
 
     # f_materialpoint_forward
     def forward(self):

@@ -290,6 +290,7 @@ static int persistent_grid(K kernel, long long n) {
 // device counter of the cells the register-resident kernel of the last evaluation gave up (their full first sub-step failed:
 // what the reference answers with a cut-back); 0 for phases that run in the reference-order kernel
 const unsigned* dmk_points_given_up_counter(dmk_ctx* c) { return c->pts->d_defer_count; }
+bool dmk_points_single_constituent(const dmk_ctx* c) { return !c->pts || c->pts->n_const <= 1; }
 const double* dmk_points_given_up_total(dmk_ctx* c) { return c->pts->d_defer_total; }
 
 // DMK_PHENO_MASS: which kernel takes the deferred list when it is long (see cutback_setting() in pheno_fast.cu):
@@ -311,7 +312,41 @@ int dmk_wait_staged_input(dmk_ctx* c, const double* d_F) {
   return DMK_OK;
 }
 
+// ---- isostrain homogenisation (N_constituents > 1): homogenization_mechanical_isostrain.f90:36-45 (every constituent sees the
+// cell's F) and mechanical_homogenize (homogenization_mechanical.f90:125-145: P = sum_co v_co P_co, dPdF alike)
+__global__ void dmk_isostrain_partition_kernel(const double* __restrict__ F, double* __restrict__ Fpt, long long n_cells9, int n_const) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_cells9; i += (long long)gridDim.x * blockDim.x) {
+    const double f = F[i];
+    for (int k = 0; k < n_const; k++) Fpt[k * n_cells9 + i] = f;
+  }
+}
+// out[cell][w] = sum_k v[k n_cells + cell] * in[k n_cells + cell][w]   (w < width: 9 for P, 81 for dPdF), constituents in order
+__global__ void dmk_isostrain_average_kernel(const double* __restrict__ in, const double* __restrict__ v, double* __restrict__ out,
+                                             long long n_cells, int n_const, int width) {
+  const long long total = n_cells * width;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long cell = i / width;
+    // the reference's sequence, each product and each sum rounded on its own (no contraction into FMAs)
+    double s = __dmul_rn(in[i], v[cell]);
+    for (int k = 1; k < n_const; k++) s = __dadd_rn(s, __dmul_rn(in[k * total + i], v[k * n_cells + cell]));
+    out[i] = s;
+  }
+}
+
+static int points_constitutive_core(dmk_ctx* c, const double* d_F, double* d_P, double dt);
 int dmk_points_constitutive(dmk_ctx* c, const double* d_F, double* d_P, double dt) {
+  DmkPointArrays& pa = *c->pts;
+  if (pa.n_const <= 1) return points_constitutive_core(c, d_F, d_P, dt);
+  int rc = dmk_wait_staged_input(c, d_F); if (rc) return rc;         // the whole field must have arrived before it is partitioned
+  dmk_isostrain_partition_kernel<<<148 * 8, 256, 0, c->stream>>>(d_F, pa.Fpt, pa.n_cells * 9, pa.n_const);
+  c->launches++;
+  if ((rc = points_constitutive_core(c, pa.Fpt, pa.Ppt, dt))) return rc;
+  dmk_isostrain_average_kernel<<<148 * 8, 256, 0, c->stream>>>(pa.Ppt, pa.v, d_P, pa.n_cells, pa.n_const, 9);
+  c->launches++;
+  DMK_CUDA_CHECK(cudaGetLastError());
+  return DMK_OK;
+}
+static int points_constitutive_core(dmk_ctx* c, const double* d_F, double* d_P, double dt) {
   DmkPointArrays& pa = *c->pts;
   const DmkNumDev nd = num_dev(c->num);
   // two formulations of the same arithmetic (bit-identical, tests/host_twin): lane-persistent state machine | nested loops
@@ -412,6 +447,9 @@ void dmk_points_teardown(dmk_ctx* c) {
   cudaFree(pa->phase); cudaFree(pa->F0); cudaFree(pa->F); cudaFree(pa->Fp0); cudaFree(pa->Fp); cudaFree(pa->Fe);
   cudaFree(pa->Lp0); cudaFree(pa->Lp); cudaFree(pa->S0); cudaFree(pa->S); cudaFree(pa->state0); cudaFree(pa->state);
   if (pa->dep) cudaFree(pa->dep);
+  if (pa->v) cudaFree(pa->v);
+  if (pa->Fpt) cudaFree(pa->Fpt);
+  if (pa->Ppt) cudaFree(pa->Ppt);
   cudaFree(pa->nrm); cudaFree(pa->cutbacks); cudaFree(pa->lp_iter); cudaFree(pa->defer_list); cudaFree(pa->d_defer_count); cudaFree(pa->d_work); cudaFree(pa->d_defer_total); cudaFree(pa->d_phases); cudaFree(pa->d_counters); cudaFree(pa->d_ill);
   delete[] pa->h_phases;
   delete[] pa->h_dev_phases;
@@ -437,8 +475,22 @@ __global__ void dmk_init_dependent_kernel(DmkPointArrays pa, int phase) {
   }
 }
 
+static int material_init_impl(dmk_ctx* c, const dmk_phase* phases, int n_phases, int n_const, const int* phase_of_cell,
+                              const double* O_of_cell, const double* v_of_point, const dmk_numerics* num);
 extern "C" int dmk_material_init(dmk_ctx* c, const dmk_phase* phases, int n_phases, const int* phase_of_cell,
                                  const double* O_of_cell, const dmk_numerics* num) {
+  return material_init_impl(c, phases, n_phases, 1, phase_of_cell, O_of_cell, nullptr, num);
+}
+extern "C" int dmk_material_init_constituents(dmk_ctx* c, const dmk_phase* phases, int n_phases, int n_constituents,
+                                              const int* phase_of_point, const double* O_of_point, const double* v_of_point,
+                                              const dmk_numerics* num) {
+  if (n_constituents < 1 || n_constituents > 16) { dmk_set_error("1..16 constituents per cell supported"); return DMK_ERR_UNSUPPORTED; }
+  if (n_constituents > 1 && !v_of_point) { dmk_set_error("null argument"); return DMK_ERR_ARG; }
+  return material_init_impl(c, phases, n_phases, n_constituents, phase_of_point, O_of_point, v_of_point, num);
+}
+extern "C" int dmk_n_constituents(dmk_ctx* c) { return (c && c->pts) ? c->pts->n_const : 0; }
+static int material_init_impl(dmk_ctx* c, const dmk_phase* phases, int n_phases, int n_const, const int* phase_of_cell,
+                              const double* O_of_cell, const double* v_of_point, const dmk_numerics* num) {
   if (!c || !phases || !phase_of_cell || !O_of_cell || !num) { dmk_set_error("null argument"); return DMK_ERR_ARG; }
   if (n_phases < 1 || n_phases > DMK_MAX_PHASES) { dmk_set_error("1..%d phases supported", DMK_MAX_PHASES); return DMK_ERR_UNSUPPORTED; }
   for (int i = 0; i < n_phases; i++) { int rc = check_phase(phases[i], i); if (rc) return rc; }
@@ -447,8 +499,9 @@ extern "C" int dmk_material_init(dmk_ctx* c, const dmk_phase* phases, int n_phas
   DmkPointArrays* pa = new DmkPointArrays();
   memset(pa, 0, sizeof *pa);
   c->pts = pa;
-  const long long n = c->n_local;
+  const long long n = c->n_local * n_const;           // material points of this slab
   pa->n = n; pa->n_phases = n_phases;
+  pa->n_const = n_const; pa->n_cells = c->n_local;
   pa->h_phases = new dmk_phase[n_phases];
   memcpy(pa->h_phases, phases, sizeof(dmk_phase) * n_phases);
   std::vector<DmkDevPhase> dev(n_phases);
@@ -490,6 +543,16 @@ extern "C" int dmk_material_init(dmk_ctx* c, const dmk_phase* phases, int n_phas
       (rc = dalloc(&pa->S, 6 * n)) || (rc = dalloc(&pa->state0, (size_t)max_state * n)) || (rc = dalloc(&pa->state, (size_t)max_state * n)) ||
       (rc = dalloc(&pa->nrm, n))) return rc;
   if (max_dep > 0) { if ((rc = dalloc(&pa->dep, (size_t)max_dep * n))) return rc; DMK_CUDA_CHECK(cudaMemset(pa->dep, 0, (size_t)max_dep * n * sizeof(double))); }
+  if (n_const > 1) {
+    for (long long cell = 0; cell < c->n_local; cell++) {
+      double sv = 0.0;
+      for (int k = 0; k < n_const; k++) { const double vk = v_of_point[k * c->n_local + cell]; if (!(vk > 0.0)) { dmk_set_error("cell %lld: volume fraction %g of constituent %d", cell, vk, k); return DMK_ERR_ARG; } sv += vk; }
+      if (fabs(sv - 1.0) > 1.0e-9) { dmk_set_error("cell %lld: volume fractions sum to %.12g", cell, sv); return DMK_ERR_ARG; }   // material.f90: sum(v) must be 1
+    }
+    if ((rc = dalloc(&pa->v, n)) || (rc = dalloc(&pa->Fpt, 9 * n)) || (rc = dalloc(&pa->Ppt, 9 * n))) return rc;
+    DMK_CUDA_CHECK(cudaMemcpy(pa->v, v_of_point, n * sizeof(double), cudaMemcpyHostToDevice));
+    DMK_CUDA_CHECK(cudaMemset(pa->Ppt, 0, 9 * n * sizeof(double)));
+  }
   DMK_CUDA_CHECK(cudaMalloc((void**)&pa->phase, n * sizeof(int)));
   DMK_CUDA_CHECK(cudaMalloc((void**)&pa->cutbacks, n * sizeof(int)));
   DMK_CUDA_CHECK(cudaMemset(pa->cutbacks, 0, n * sizeof(int)));
@@ -735,12 +798,40 @@ static int select_minmax(dmk_ctx* c, const double* d_nrm, long long n, long long
   return DMK_OK;
 }
 
+// dPdF of every CELL of the slab ([cell][81], the reference's Fortran order): the points' tangents, averaged over the constituents
+// with their volume fractions under isostrain homogenisation.  d_Csum81 (may be null under isostrain) receives the plain sum over
+// the material points in the kernel's own index order.
+int dmk_cells_tangent(dmk_ctx* c, double dt, double* d_Csum81, double* d_cell_dPdF) {
+  DmkPointArrays& pa = *c->pts;
+  if (pa.n_const <= 1) return dmk_points_tangent(c, dt, d_Csum81, d_cell_dPdF);
+  double* d_pt = nullptr;
+  if (cudaMalloc((void**)&d_pt, (size_t)pa.n * 81 * sizeof(double)) != cudaSuccess) { cudaGetLastError(); dmk_set_error("out of device memory (point tangents)"); return DMK_ERR_CUDA; }
+  int rc = dmk_points_tangent(c, dt, d_Csum81 ? d_Csum81 : c->d_scratch + DMK_SCRATCH_TMP, d_pt);
+  if (!rc) {
+    dmk_isostrain_average_kernel<<<148 * 8, 256, 0, c->stream>>>(d_pt, pa.v, d_cell_dPdF, pa.n_cells, pa.n_const, 81);
+    c->launches++;
+    if (cudaStreamSynchronize(c->stream) != cudaSuccess) { dmk_set_error("isostrain tangent average failed"); rc = DMK_ERR_CUDA; }
+  }
+  cudaFree(d_pt);
+  return rc;
+}
+
 extern "C" int dmk_tangent_response(dmk_ctx* c, double dt, double* C_volAvg, double* C_minMaxAvg, double* d_dPdF,
                                     long long minmax_cells[2]) {
   int rc = need_points(c); if (rc) return rc;
   DmkPointArrays& pa = *c->pts;
   if (c->P > 1 && (!c->has_comm || !c->comm.allreduce_sum || !c->comm.allreduce_max)) { dmk_set_error("no allreduce callbacks (dmk_set_comm)"); return DMK_ERR_STATE; }
   double* d_sum = c->d_scratch + DMK_SCRATCH_TMP;               // 81
+  if (pa.n_const > 1) {
+    // isostrain: dPdF of a cell = sum_co v_co dPdF_co (homogenization_mechanical.f90:125-145).  The per-point tangents are
+    // materialised, averaged per cell, and the reference's reductions run on the cell field (dmk_homogenise)
+    double* d_cell = d_dPdF;
+    if (!d_cell) { if (cudaMalloc((void**)&d_cell, (size_t)pa.n_cells * 81 * sizeof(double)) != cudaSuccess) { cudaGetLastError(); dmk_set_error("out of device memory (cell tangents)"); return DMK_ERR_CUDA; } }
+    rc = dmk_cells_tangent(c, dt, d_sum, d_cell);
+    if (!rc) rc = dmk_homogenise(c, pa.Ppt, d_cell, pa.n_cells, nullptr, C_volAvg, C_minMaxAvg, minmax_cells);
+    if (d_cell != d_dPdF) cudaFree(d_cell);
+    return rc;
+  }
   if ((rc = dmk_points_tangent(c, dt, d_sum, d_dPdF))) return rc;
   if (c->P > 1) { if (c->comm.allreduce_sum(c->comm.user, d_sum, 81)) { dmk_set_error("allreduce failed"); return DMK_ERR_STATE; } }
   long long gidx[2];

@@ -50,6 +50,13 @@ struct DmkPointArrays {
   unsigned long long* d_counters;      // 16: Lp iters, Li iters, stress calls, state iters, substeps, cutbacks, ill cells, deferred cells | 8 lane-schedule statistics
   int* d_ill;                          // device flag (OR of broken cells since the last reset)
   long long n_cells_of_phase[DMK_MAX_PHASES];
+  // isostrain homogenisation (homogenization_mechanical_isostrain.f90; N_constituents > 1): n = n_const * n_cells material points,
+  // point k * n_cells + cell is constituent k of the cell.  All per-point arrays above are sized by n; the cell fields crossing
+  // the boundary are partitioned into / homogenised from the point fields below.  n_const = 1: n == n_cells, nothing allocated
+  int n_const;
+  long long n_cells;
+  double* v;                           // [n] volume fraction of each point within its cell
+  double *Fpt, *Ppt;                   // [n][9] records: partitioned deformation gradient, per-point first Piola-Kirchhoff stress
 };
 
 struct DmkNumDev {
@@ -69,4 +76,5 @@ int dmk_points_pheno_fast(dmk_ctx* c, int ph, const DmkNumDev& nd, const double*
 int dmk_mass_deferral_setting(const dmk_ctx* c);     // 0 nested, 1 machine, 2 lanes (default): who takes a long deferred list (constitutive.cu)
 int dmk_points_tangent(dmk_ctx* c, double dt, double* d_Csum81 /*device, row-major sum over local cells*/,
                        double* d_dPdF /*optional [n][81] Fortran order*/);
+int dmk_cells_tangent(dmk_ctx* c, double dt, double* d_Csum81 /*may be null under isostrain*/, double* d_cell_dPdF /*[cell][81] Fortran order, homogenised over the constituents*/);
 int dmk_points_tangent_cell(dmk_ctx* c, double dt, long long cell, double* d_out81 /*row-major*/);

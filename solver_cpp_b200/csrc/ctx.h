@@ -80,6 +80,7 @@ int dmk_spectrum_rms(dmk_ctx* c, const double* d_real, int mode /*0 divergence, 
 int dmk_gamma_internal(dmk_ctx* c);     // fused z pass on c->bufA using c->d_dc, accumulating into c->d_div
 double dmk_finish_div(dmk_ctx* c, double raw_sum);
 const unsigned* dmk_points_given_up_counter(dmk_ctx* c);
+bool dmk_points_single_constituent(const dmk_ctx* c);        // false: isostrain homogenisation with N_constituents > 1 (constitutive.cu)
 const double* dmk_points_given_up_total(dmk_ctx* c);           // ... summed over all ranks, as a double (valid when the mass-deferral decision ran)
 int dmk_fft_forward_finish_pipelined(dmk_ctx* c);
 int dmk_fft_forward_redo_pipelined(dmk_ctx* c, const double* d_real);

@@ -18,9 +18,15 @@ static double* g_dP = nullptr;     // device staging: P records
 static double* g_dT = nullptr;     // device staging: dPdF records (81 per cell)
 static long long g_n = 0;
 
-__global__ void dmk_records_to_soa_kernel(const double* __restrict__ rec, double* __restrict__ soa, long long n) {
+// cell records -> the per-point component planes; under isostrain homogenisation every constituent of a cell (point k * n + cell)
+// receives the cell's tensor (homogenization_mechanical_isostrain.f90:36-45)
+__global__ void dmk_records_to_soa_kernel(const double* __restrict__ rec, double* __restrict__ soa, long long n, int n_const) {
+  const long long stride = n * n_const;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
-    for (int a = 0; a < 3; a++) for (int b = 0; b < 3; b++) soa[(3 * a + b) * n + i] = rec[i * 9 + a + 3 * b];
+    for (int a = 0; a < 3; a++) for (int b = 0; b < 3; b++) {
+      const double x = rec[i * 9 + a + 3 * b];
+      for (int k = 0; k < n_const; k++) soa[(3 * a + b) * stride + k * n + i] = x;
+    }
 }
 
 extern "C" int dmk_bind_global(dmk_ctx* c) {
@@ -66,7 +72,7 @@ extern "C" void f_homogenization_mechanical_response(double* delta_t, int* cell_
   const size_t bytes = 9 * (size_t)g_n * sizeof(double);
   // the caller owns F0 and F (mech_solver_basic.cpp:196-206): F0 is re-read every call, like the Fortran module array
   if (cudaMemcpyAsync(g_dF, c->m_F0, bytes, cudaMemcpyHostToDevice, c->stream) != cudaSuccess) { fail("h2d"); return; }
-  dmk_records_to_soa_kernel<<<148 * 4, 256, 0, c->stream>>>(g_dF, c->pts->F0, g_n);
+  dmk_records_to_soa_kernel<<<148 * 4, 256, 0, c->stream>>>(g_dF, c->pts->F0, g_n, c->pts->n_const);
   c->launches++;
   if (cudaMemcpyAsync(g_dF, c->m_F, bytes, cudaMemcpyHostToDevice, c->stream) != cudaSuccess) { fail("h2d"); return; }
   if (dmk_points_constitutive(c, g_dF, g_dP, *delta_t)) { fail("kernel"); return; }
@@ -82,7 +88,7 @@ extern "C" void f_homogenization_mechanical_response2(double* delta_t, int* FEso
   if (!c || !c->m_F) { dmk_set_error("f_homogenization_mechanical_response2: no bound context"); return; }
   (void)FEsolving_execIP; (void)FEsolving_execElem;
   double* d_sum = c->d_scratch + DMK_SCRATCH_TMP;
-  if (dmk_points_tangent(c, *delta_t, d_sum, g_dT)) { fail("tangent"); return; }
+  if (dmk_cells_tangent(c, *delta_t, d_sum, g_dT)) { fail("tangent"); return; }           // homogenised over the constituents (mechanical_homogenize)
   if (cudaMemcpyAsync(c->m_P, g_dP, 9 * (size_t)g_n * sizeof(double), cudaMemcpyDeviceToHost, c->stream) != cudaSuccess) { fail("d2h"); return; }
   if (cudaMemcpyAsync(c->m_dPdF, g_dT, 81 * (size_t)g_n * sizeof(double), cudaMemcpyDeviceToHost, c->stream) != cudaSuccess) { fail("d2h"); return; }
   if (cudaStreamSynchronize(c->stream) != cudaSuccess) fail("sync");

@@ -466,10 +466,15 @@ void grid_from_ip_coords(const std::vector<double>& x, long long n, int cells[3]
 
 }  // namespace
 
-// material.yaml (parsed) -> phase tables and per-material phase index / orientation matrix (row-major 3x3, Fp0 = O)
-extern "C" int dmk_material_from_yaml(const char* material_yaml_path, double T, dmk_phase* phases, int max_phases, int* n_phases,
-                                      int* phase_of_material, double* O_of_material, int max_materials, int* n_materials) {
+// material.yaml (parsed) -> phase tables and, per material entry, its constituents: phase index, orientation matrix (row-major
+// 3x3, Fp0 = O) and volume fraction.  Entry (m, k) of the per-material tables sits at m * max_constituents + k.  Checks of
+// material.f90:145,161: the number of constituents is the homogenization's N_constituents, their fractions sum to 1; mechanical
+// homogenisation types offered: pass (one constituent), isostrain.
+extern "C" int dmk_material_constituents_from_yaml(const char* material_yaml_path, double T, dmk_phase* phases, int max_phases, int* n_phases,
+                                                   int max_constituents, int* n_constituents_of_material, int* phase_of_material,
+                                                   double* O_of_material, double* v_of_material, int max_materials, int* n_materials) {
   try {
+    if (!material_yaml_path || !phases || !n_phases || !n_constituents_of_material || !phase_of_material || !O_of_material || !v_of_material || !n_materials || max_constituents < 1) bad("dmk_material_constituents_from_yaml: null argument");
     auto root = yaml_parse_file(material_yaml_path);
     const YamlNode& ph = need(*root, "phase", "material.yaml");
     if (!ph.is_map() || ph.map.empty()) bad("material.yaml: `phase` must be a non-empty mapping");
@@ -479,17 +484,39 @@ extern "C" int dmk_material_from_yaml(const char* material_yaml_path, double T, 
     const YamlNode& mats = need(*root, "material", "material.yaml");
     if (!mats.is_seq()) bad("material.yaml: `material` must be a sequence");
     if ((int)mats.seq.size() > max_materials) bad("material.yaml: too many materials for the caller's buffers");
+    const YamlNode* homs = root->get("homogenization");
     for (size_t m = 0; m < mats.seq.size(); m++) {
       const YamlNode& cons = need(*mats.seq[m], "constituents", "material entry");
-      if (!cons.is_seq() || cons.seq.size() != 1) bad("only single-constituent (pass) homogenisation is offered");
-      const std::string name = need(*cons.seq[0], "phase", "constituent").scalar;
-      int idx = -1;
-      for (size_t i = 0; i < ph.map.size(); i++) if (ph.map[i].first == name) idx = (int)i;
-      if (idx < 0) bad("material entry refers to unknown phase " + name);
-      phase_of_material[m] = idx;
-      const std::vector<double> q = need(*cons.seq[0], "O", "constituent").as_doubles();
-      if (q.size() != 4) bad("constituent orientation O needs 4 quaternion components");
-      dmk_qu2om(q.data(), O_of_material + 9 * m);
+      if (!cons.is_seq() || cons.seq.empty()) bad("material entry without constituents");
+      const int nc = (int)cons.seq.size();
+      if (nc > max_constituents) bad("material entry " + std::to_string(m) + ": " + std::to_string(nc) + " constituents, the caller's buffers hold " + std::to_string(max_constituents));
+      const YamlNode* hname = mats.seq[m]->get("homogenization");
+      const YamlNode* hom = (homs && homs->is_map() && hname) ? homs->get(hname->scalar) : nullptr;
+      if (hom) {
+        const YamlNode* ncn = hom->get("N_constituents");
+        if (ncn && ncn->as_int() != nc) bad("material entry " + std::to_string(m) + ": " + std::to_string(nc) + " constituents, its homogenization asks for " + ncn->scalar);
+        const YamlNode* mech = hom->get("mechanical");
+        const YamlNode* type = mech ? mech->get("type") : nullptr;
+        const std::string t = type ? type->scalar : std::string("pass");
+        if ((t != "pass" && t != "isostrain") || (t == "pass" && nc != 1)) bad("mechanical homogenisation " + t + " with " + std::to_string(nc) + " constituents is not offered (pass, isostrain)");
+      } else if (nc != 1) bad("material entry " + std::to_string(m) + ": several constituents without a homogenization entry");
+      n_constituents_of_material[m] = nc;
+      double sv = 0.0;
+      for (int k = 0; k < nc; k++) {
+        const size_t at = m * (size_t)max_constituents + (size_t)k;
+        const std::string name = need(*cons.seq[(size_t)k], "phase", "constituent").scalar;
+        int idx = -1;
+        for (size_t i = 0; i < ph.map.size(); i++) if (ph.map[i].first == name) idx = (int)i;
+        if (idx < 0) bad("material entry refers to unknown phase " + name);
+        phase_of_material[at] = idx;
+        const std::vector<double> q = need(*cons.seq[(size_t)k], "O", "constituent").as_doubles();
+        if (q.size() != 4) bad("constituent orientation O needs 4 quaternion components");
+        dmk_qu2om(q.data(), O_of_material + 9 * at);
+        const YamlNode* vn = cons.seq[(size_t)k]->get("v");
+        v_of_material[at] = vn ? vn->as_double() : 1.0;
+        sv += v_of_material[at];
+      }
+      if (fabs(sv - 1.0) > 1.0e-9) bad("material entry " + std::to_string(m) + ": volume fractions of the constituents do not sum to 1");
     }
     *n_materials = (int)mats.seq.size();
     return DMK_OK;
@@ -497,6 +524,18 @@ extern "C" int dmk_material_from_yaml(const char* material_yaml_path, double T, 
     dmk_set_error("%s", e.what());
     return DMK_ERR_ARG;
   }
+}
+
+// the single-constituent form: per-material phase index / orientation matrix
+extern "C" int dmk_material_from_yaml(const char* material_yaml_path, double T, dmk_phase* phases, int max_phases, int* n_phases,
+                                      int* phase_of_material, double* O_of_material, int max_materials, int* n_materials) {
+  if (max_materials < 0) { dmk_set_error("dmk_material_from_yaml: bad argument"); return DMK_ERR_ARG; }
+  std::vector<int> nc((size_t)max_materials + 1);
+  std::vector<double> v((size_t)max_materials + 1);
+  // one slot per material: an entry with more constituents is refused by the general reader
+  int rc = dmk_material_constituents_from_yaml(material_yaml_path, T, phases, max_phases, n_phases, 1, nc.data(), phase_of_material,
+                                               O_of_material, v.data(), max_materials, n_materials);
+  return rc;
 }
 
 extern "C" int dmk_numerics_from_yaml(const char* numerics_yaml_path, dmk_numerics* num, int* derivative, int* divergence_correction) {
@@ -558,9 +597,13 @@ extern "C" void f_materialpoint_initDamask(void) {
     const YamlNode* mats = root->get("material");
     const int file_mats = (mats && mats->is_seq()) ? (int)mats->seq.size() : 0;
     if (max_mat > file_mats) bad("geometry refers to material " + std::to_string(max_mat) + ", material.yaml has " + std::to_string(file_mats) + " entries");
-    std::vector<int> ph_of_mat((size_t)file_mats);
-    std::vector<double> O_of_mat(9 * (size_t)file_mats);
-    if (dmk_material_from_yaml(g_init.material_path.c_str(), T_ROOM, phases.data(), DMK_MAX_PHASES, &n_phases, ph_of_mat.data(), O_of_mat.data(), file_mats, &n_mat)) return;
+    // constituents per material entry: the widest entry sizes the tables
+    int max_const = 1;
+    for (int m = 0; m < file_mats; m++) { const YamlNode* cs = mats->seq[(size_t)m]->get("constituents"); if (cs && cs->is_seq()) max_const = std::max(max_const, (int)cs->seq.size()); }
+    std::vector<int> nc_of_mat((size_t)file_mats), ph_of_mat((size_t)file_mats * max_const);
+    std::vector<double> O_of_mat(9 * (size_t)file_mats * max_const), v_of_mat((size_t)file_mats * max_const);
+    if (dmk_material_constituents_from_yaml(g_init.material_path.c_str(), T_ROOM, phases.data(), DMK_MAX_PHASES, &n_phases, max_const, nc_of_mat.data(),
+                                            ph_of_mat.data(), O_of_mat.data(), v_of_mat.data(), file_mats, &n_mat)) return;
     dmk_numerics num;
     int derivative = 0, divcorr = 0;
     const std::string np = file_exists(g_init.numerics_path) ? g_init.numerics_path : std::string();
@@ -570,17 +613,27 @@ extern "C" void f_materialpoint_initDamask(void) {
     grid_from_ip_coords(g_init.ip_coords, n, g.cells, g.size);
     g.world_size = 1; g.rank = 0;                   // the driver's own MPI decomposition stays with the driver: this is ITS slab
     g.derivative = derivative; g.divergence_correction = divcorr;
-    std::vector<int> phase_of_cell((size_t)n);
-    std::vector<double> O_of_cell(9 * (size_t)n);
+    // every material in use must bring the same number of constituents (point k * n + cell is constituent k of the cell)
+    int n_const = 0;
     for (long long i = 0; i < n; i++) {
       const int m = g_init.material_at[(size_t)i];
       if (m < 0) bad("negative material index");
-      phase_of_cell[(size_t)i] = ph_of_mat[(size_t)m];
-      memcpy(&O_of_cell[9 * (size_t)i], &O_of_mat[9 * (size_t)m], 9 * sizeof(double));
+      if (n_const == 0) n_const = nc_of_mat[(size_t)m];
+      else if (nc_of_mat[(size_t)m] != n_const) bad("materials with different numbers of constituents in one grid are not offered");
     }
+    std::vector<int> phase_of_point((size_t)n * n_const);
+    std::vector<double> O_of_point(9 * (size_t)n * n_const), v_of_point((size_t)n * n_const);
+    for (int k = 0; k < n_const; k++)
+      for (long long i = 0; i < n; i++) {
+        const size_t at = (size_t)g_init.material_at[(size_t)i] * max_const + (size_t)k, pt = (size_t)k * n + (size_t)i;
+        phase_of_point[pt] = ph_of_mat[at];
+        v_of_point[pt] = v_of_mat[at];
+        memcpy(&O_of_point[9 * pt], &O_of_mat[9 * at], 9 * sizeof(double));
+      }
     dmk_ctx* c = nullptr;
     if (dmk_create(&c, &g)) return;
-    if (dmk_material_init(c, phases.data(), n_phases, phase_of_cell.data(), O_of_cell.data(), &num) || dmk_bind_global(c)) { dmk_destroy(c); return; }
+    if (dmk_material_init_constituents(c, phases.data(), n_phases, n_const, phase_of_point.data(), O_of_point.data(), v_of_point.data(), &num) ||
+        dmk_bind_global(c)) { dmk_destroy(c); return; }
     g_init.ctx = c;
   } catch (const std::exception& e) {
     dmk_set_error("%s", e.what());

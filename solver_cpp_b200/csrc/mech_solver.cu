@@ -813,6 +813,7 @@ static int mech_init(dmk_ctx* c, const long long* gamma_pair_cells, int scheme) 
   for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) m->P_av[3 * i + j] = s9[i + 3 * j] * c->wgt;
   m->tangent_stale = true; m->tangent_dt = 0.0;
   if ((rc = ensure_tangent(c))) return rc;
+  if (gamma_pair_cells && !dmk_points_single_constituent(c)) { dmk_set_error("forced reference-stiffness cells with N_constituents > 1 are not offered"); return DMK_ERR_UNSUPPORTED; }
   if (gamma_pair_cells) {
     // replay aid: force the two cells whose tangents define the reference stiffness
     double* d_two = c->d_scratch + DMK_SCRATCH_TMP + 112;
@@ -843,6 +844,7 @@ static __global__ void dmk_scale_kernel(double* __restrict__ out, const double* 
 }
 extern "C" int dmk_mech_init_polarisation(dmk_ctx* c, double alpha, double beta, double eps_abs_curl, double eps_rel_curl) {
   if (!(beta != 0.0)) { dmk_set_error("polarisation: beta must not be 0"); return DMK_ERR_ARG; }
+  if (c && !dmk_points_single_constituent(c)) { dmk_set_error("polarisation scheme with N_constituents > 1 is not offered"); return DMK_ERR_UNSUPPORTED; }
   int rc = mech_init(c, nullptr, 1);
   if (rc) return rc;
   DmkMech* m = c->mech;

@@ -326,8 +326,8 @@ static int launch_pheno_lanes(dmk_ctx* c, DmkPointArrays& pa, int ph, const DmkD
   // forward FFT (spectral.cu: dmk_pipe_*, which transforms chunk k's stress while chunk k+1 is integrated).  Chunks for the
   // pipeline go to two alternating streams, each with its own work queue: chunk k+1's CTAs move in as chunk k's retire, so
   // the tail of a chunk (lanes finishing their last cells, ~1 ms) is not paid eight times as with launches in one stream
-  const bool staged = c->stage_chunks > 1 && d_F == c->stage_dst;
-  const bool piped = c->pipe_on && d_P == c->pipe_src && pa.n_cells_of_phase[ph] == pa.n;     // the only phase: its chunk is complete after its launch
+  const bool staged = c->stage_chunks > 1 && d_F == c->stage_dst && pa.n_const == 1;
+  const bool piped = c->pipe_on && d_P == c->pipe_src && pa.n_cells_of_phase[ph] == pa.n && pa.n_const == 1;     // the only phase: its chunk is complete after its launch
   const int chunks = staged ? c->stage_chunks : piped ? c->pipe_chunks : 1;
   if (staged && piped && c->stage_chunks != c->pipe_chunks) c->pipe_on = false;
   const bool conc = piped && c->pipe_on && chunks > 1;
@@ -339,7 +339,7 @@ static int launch_pheno_lanes(dmk_ctx* c, DmkPointArrays& pa, int ph, const DmkD
   }
   for (int k = 0; k < chunks; k++) {
     const long long z0 = (long long)c->nz_loc * k / chunks, z1 = (long long)c->nz_loc * (k + 1) / chunks;
-    const long long first = z0 * plane, end = z1 * plane;
+    const long long first = z0 * plane, end = (chunks == 1) ? pa.n : z1 * plane;     // one launch: every material point (isostrain: n_const per cell)
     cudaStream_t st = conc ? c->chunk_stream[k & 1] : c->stream;
     if (end > first) {
       if (staged) DMK_CUDA_CHECK(cudaStreamWaitEvent(st, c->stage_ev[k], 0));

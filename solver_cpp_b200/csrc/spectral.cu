@@ -276,7 +276,7 @@ static bool pipe_wanted(dmk_ctx* c) {
   // every register of every SM, so the FFT kernels only run in the tails of the z-chunks, and eight chunk tails (lanes finishing
   // their last cells) cost more than the 1.85 ms they hide.
   static const bool env_on = [] { const char* e = getenv("DMK_PIPELINE"); return e && atoi(e) == 1; }();
-  return env_on && c->P > 1 && c->p2p && c->nz_loc >= 2 && c->ny > 1;
+  return env_on && c->P > 1 && c->p2p && c->nz_loc >= 2 && c->ny > 1 && dmk_points_single_constituent(c);
 }
 int dmk_pipe_begin(dmk_ctx* c, const double* d_real) {
   c->pipe_on = false; c->pipe_done = 0;

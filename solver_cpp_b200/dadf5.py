@@ -102,6 +102,8 @@ class ResultWriter:
         if material_at.size != n:
             raise ValueError('material_at has %d entries for %d cells' % (material_at.size, n))
         mats = material['material']
+        if any(len(mats[m]['constituents']) != 1 for m in np.unique(material_at)):
+            raise NotImplementedError('DADF5 output of materials with several constituents per cell (isostrain) is not offered')
         self.phase_label = np.array([m['constituents'][0]['phase'] for m in mats], dtype=object)[material_at]
         homog_label = np.array([m['homogenization'] for m in mats], dtype=object)[material_at]
         self.phases = list(material['phase'].keys())

@@ -151,12 +151,21 @@ class GridContext:
         from . import material as M
         if self.lib.dmk_sizeof_phase() != C.sizeof(L.Phase) or self.lib.dmk_sizeof_numerics() != C.sizeof(L.Numerics):
             raise L.DmkError('ctypes layout of dmk_phase / dmk_numerics does not match the library')
-        if material.phase_of_cell.size != self.n_local:
-            raise L.DmkError('material has %d cells, slab has %d' % (material.phase_of_cell.size, self.n_local))
+        if material.n_cells != self.n_local:
+            raise L.DmkError('material has %d cells, slab has %d' % (material.n_cells, self.n_local))
         self.numerics = numerics if numerics is not None else M.make_numerics()
         self._material = material
-        L.check(self.lib.dmk_material_init(self.ctx, material.phases, C.c_int(len(material.phases)),
-                                           _hp(material.phase_of_cell), _hp(material.O_of_cell), C.byref(self.numerics)))
+        self.n_constituents = material.n_constituents
+        self.n_points = self.n_local * self.n_constituents       # rows of the per-point arrays (get_state / set_state)
+        if self.n_constituents == 1:
+            L.check(self.lib.dmk_material_init(self.ctx, material.phases, C.c_int(len(material.phases)),
+                                               _hp(material.phase_of_cell), _hp(material.O_of_cell), C.byref(self.numerics)))
+        else:
+            # isostrain homogenisation: point k * n_local + cell is constituent k of the cell
+            L.check(self.lib.dmk_material_init_constituents(self.ctx, material.phases, C.c_int(len(material.phases)),
+                                                            C.c_int(self.n_constituents), _hp(material.phase_of_point),
+                                                            _hp(material.O_of_point), _hp(material.v_of_point),
+                                                            C.byref(self.numerics)))
 
     # ---- f_homogenization_mechanical_response (+ P of _response2)
     def constitutive_response(self, F, dt, P=None):
@@ -200,7 +209,7 @@ class GridContext:
         return dict(zip(('lp_trips', 'lp_lanes', 'sb_trips', 'sb_lanes', 'refill_trips', 'refill_lanes'), list(a)[:6]))
 
     def get_state(self, name, comps):
-        out = np.zeros((self.n_local, comps))
+        out = np.zeros((getattr(self, 'n_points', self.n_local), comps))
         L.check(self.lib.dmk_get_state(self.ctx, name.encode(), _hp(out), C.c_size_t(out.size)))
         return out
 

@@ -416,21 +416,53 @@ def make_numerics(phase_mech=None, grid_mech=None):
 
 
 class Material:
-    """phases + per-cell assignment for one z-slab"""
+    """phases + per-point assignment for one z-slab.
+
+    One constituent per cell ("pass" homogenisation) or several ("isostrain", homogenization_mechanical_isostrain.f90:36-45):
+    material point k * n_cells + cell is constituent k of the cell.  All materials in use must have the same number of
+    constituents; their volume fractions sum to 1 (material.f90:145,161)."""
 
     def __init__(self, material, material_at, T=T_ROOM):
         names = list(material['phase'].keys())
         self.phase_names = names
         self.phases = (L.Phase * len(names))(*[make_phase(material['phase'][k], T) for k in names])
         mats = material['material']
-        ph_of_mat = np.empty(len(mats), dtype=np.int32)
-        O_of_mat = np.empty((len(mats), 9))
-        for m, entry in enumerate(mats):
-            cons = entry['constituents']
-            if len(cons) != 1:
-                raise L.DmkError('only single-constituent (pass) homogenisation is offered')
-            ph_of_mat[m] = names.index(cons[0]['phase'])
-            O_of_mat[m] = qu2om(cons[0]['O']).reshape(9)
         material_at = np.asarray(material_at).reshape(-1)
-        self.phase_of_cell = np.ascontiguousarray(ph_of_mat[material_at], dtype=np.int32)
-        self.O_of_cell = np.ascontiguousarray(O_of_mat[material_at])
+        used = np.unique(material_at)
+        if used.size and (used[0] < 0 or used[-1] >= len(mats)):
+            raise L.DmkError('more materials requested than found in the material configuration')      # material.f90:116
+        counts = {len(mats[m]['constituents']) for m in used}
+        if len(counts) != 1:
+            raise L.DmkError('materials with different numbers of constituents in one grid are not offered')
+        self.n_constituents = nc = counts.pop()
+        ph_of_mat = np.zeros((len(mats), nc), dtype=np.int32)
+        O_of_mat = np.tile(np.eye(3).reshape(9), (len(mats), nc, 1))
+        v_of_mat = np.zeros((len(mats), nc))
+        for m in used:
+            entry = mats[m]
+            cons = entry['constituents']
+            homog = (material.get('homogenization') or {}).get(entry.get('homogenization'))
+            if homog is not None:
+                if int(homog.get('N_constituents', len(cons))) != len(cons):
+                    raise L.DmkError('material %d: %d constituents, its homogenization asks for %s'
+                                     % (m, len(cons), homog.get('N_constituents')))
+                htype = (homog.get('mechanical') or {}).get('type', 'pass')
+                if htype not in ('pass', 'isostrain') or (htype == 'pass' and len(cons) != 1):
+                    raise L.DmkError('mechanical homogenisation %r with %d constituents is not offered (pass, isostrain)'
+                                     % (htype, len(cons)))
+            elif len(cons) != 1:
+                raise L.DmkError('material %d: %d constituents without a homogenization entry' % (m, len(cons)))
+            for k, con in enumerate(cons):
+                ph_of_mat[m, k] = names.index(con['phase'])
+                O_of_mat[m, k] = qu2om(con['O']).reshape(9)
+                v_of_mat[m, k] = float(con.get('v', 1.0))
+            if abs(v_of_mat[m].sum() - 1.0) > 1.0e-9:
+                raise L.DmkError('material %d: volume fractions of the constituents sum to %r' % (m, v_of_mat[m].sum()))
+        n = material_at.size
+        self.n_cells = n
+        self.phase_of_point = np.ascontiguousarray(ph_of_mat[material_at].T.reshape(nc * n), dtype=np.int32)
+        self.O_of_point = np.ascontiguousarray(O_of_mat[material_at].transpose(1, 0, 2).reshape(nc * n, 9))
+        self.v_of_point = np.ascontiguousarray(v_of_mat[material_at].T.reshape(nc * n))
+        # one constituent per cell: the per-cell names of dmk_material_init
+        self.phase_of_cell = self.phase_of_point
+        self.O_of_cell = self.O_of_point

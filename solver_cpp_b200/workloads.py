@@ -120,6 +120,29 @@ def polycrystal(cells, grains, phase, seed=0, z_range=None):
     return material, voronoi_material_at(cells, size, seeds, z_range), size
 
 
+def taylor_polycrystal(cells, grains, phases, n_constituents, seed=0, z_range=None):
+    """polycrystal whose every material entry is a Taylor (isostrain) aggregate of n_constituents crystallites: random
+    orientations, random volume fractions summing to 1, the phases taken in turn from `phases` (names in PHASES)
+    -> (material dict in material.yaml form, material_at for the slab, size)"""
+    rng = np.random.default_rng(seed)
+    size = grid_size(cells)
+    seeds = rng.random((grains, 3)) * np.asarray(size)
+    phases = [phases] if isinstance(phases, str) else list(phases)
+    mats = []
+    for _ in range(grains):
+        quats = random_orientations(n_constituents, rng)
+        v = 0.2 + rng.random(n_constituents)
+        v = v / v.sum()
+        v[-1] = 1.0 - v[:-1].sum()
+        mats.append({'homogenization': 'Taylor',
+                     'constituents': [{'phase': phases[k % len(phases)], 'v': float(v[k]), 'O': [float(x) for x in quats[k]]}
+                                      for k in range(n_constituents)]})
+    material = {'homogenization': {'Taylor': {'N_constituents': n_constituents, 'mechanical': {'type': 'isostrain'}}},
+                'phase': {ph: PHASES[ph] for ph in dict.fromkeys(phases)},
+                'material': mats}
+    return material, voronoi_material_at(cells, size, seeds, z_range), size
+
+
 def config(name, seed=0, z_range=None, cells=None):
     c = dict(CONFIGS[name])
     if cells is not None:
