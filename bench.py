@@ -117,10 +117,11 @@ class ClockSampler(threading.Thread):
 
 # ------------------------------------------------------------------------------------------------ CPU arm (oracle port)
 def cpu_sample_cells(K, budget_s=75.0):
-    """edge of the cubic CPU sample so that K solved increments stay near budget_s (about 6 us per cell and evaluation on
-    16 host cores; the 20^3 sample needs 539 evaluations for the first three increments of C3, most of them in increment 1, ~45 per later one)"""
+    """edge of the cubic CPU sample so that K solved increments stay near budget_s (measured on the GPU box's 16 host threads:
+    14.3 us per cell and evaluation -- 539 evaluations of the 20^3 sample in 61.6 s for the first three increments of C3, most
+    of them in increment 1, ~45 per later one; profiles/r02_bench_n1.json)"""
     evals = {1: 380.0, 2: 470.0}.get(K, 540.0) + 45.0 * max(K - 3, 0)      # increment 1 of C3 is the long one (two attempts end at itmax)
-    n = budget_s / (evals * 6.0e-6)
+    n = budget_s / (evals * 14.3e-6)
     edge = int(round(n ** (1.0 / 3.0) / 4.0)) * 4
     return (max(16, min(40, edge)),) * 3
 
