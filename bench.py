@@ -684,6 +684,21 @@ def main():
     ap.add_argument('--cells', type=int, nargs=3, default=None)
     ap.add_argument('--no-cpu', action='store_true')
     args = ap.parse_args()
+    # bounded time: a rank that waits for ever (a peer that died, a collective that never completes) ends the run with a
+    # diagnostic instead of holding the GPUs until the caller's own limit; DMK_BENCH_TIMEOUT_S = 0 turns the guard off
+    limit = float(os.environ.get('DMK_BENCH_TIMEOUT_S', '2700'))
+    if limit > 0:
+        import faulthandler
+        import threading
+
+        def expired():
+            sys.stderr.write('bench.py: rank %s still running after %.0f s (DMK_BENCH_TIMEOUT_S); stacks follow\n' % (os.environ.get('RANK', '0'), limit))
+            faulthandler.dump_traceback(file=sys.stderr, all_threads=True)
+            sys.stderr.flush()
+            os._exit(124)
+        guard = threading.Timer(limit, expired)
+        guard.daemon = True
+        guard.start()
     if args.impl == 'reference':
         run_reference(args)
     elif args.protocol == 'solve':
