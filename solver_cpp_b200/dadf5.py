@@ -7,10 +7,11 @@ on top of hdf5_min.H5Writer; nothing here is on the hot path.
     mech.loop_over_loadcase(solver, steps, callback=w.callback(every=4))
     w.save('job.hdf5')
 
-Layout written (everything damask.Result reads for a single-constituent grid job):
+Layout written (everything damask.Result reads for a grid job; C = constituents per cell, 1 unless isostrain):
     / attrs DADF5_version_major/minor, creator, created, call
     /geometry attrs cells, size, origin
-    /cell_to/phase [N,1], /cell_to/homogenization [N]: compound (label, entry)
+    /cell_to/phase [N,C], /cell_to/homogenization [N]: compound (label, entry); entries of a phase count its material points
+        cell by cell, constituent by constituent (material.f90:177-203)
     /setup/<file name>: the input decks as strings
     /increment_<n> attr t/s
         geometry/u_n [(nx+1)(ny+1)(nz+1),3], u_p [N,3]
@@ -102,9 +103,13 @@ class ResultWriter:
         if material_at.size != n:
             raise ValueError('material_at has %d entries for %d cells' % (material_at.size, n))
         mats = material['material']
-        if any(len(mats[m]['constituents']) != 1 for m in np.unique(material_at)):
-            raise NotImplementedError('DADF5 output of materials with several constituents per cell (isostrain) is not offered')
-        self.phase_label = np.array([m['constituents'][0]['phase'] for m in mats], dtype=object)[material_at]
+        counts = {len(mats[m]['constituents']) for m in np.unique(material_at)}
+        if len(counts) != 1:
+            raise NotImplementedError('DADF5 output of materials with different numbers of constituents in one grid')
+        self.n_const = nc = counts.pop()
+        # phase label of every material point, [N, C]: constituent co of cell ce
+        lab = np.array([[c['phase'] for c in m['constituents']][:nc] + [''] * max(0, nc - len(m['constituents'])) for m in mats], dtype=object)
+        self.phase_label = lab.reshape(len(mats), nc)[material_at]
         homog_label = np.array([m['homogenization'] for m in mats], dtype=object)[material_at]
         self.phases = list(material['phase'].keys())
         self.lattice = {k: (v or {}).get('lattice') for k, v in material['phase'].items()}
@@ -123,8 +128,10 @@ class ResultWriter:
         w.group('/cell_to', description='mappings to place data in space')
         w.group('/setup', description='input data used to run the simulation')
         self.cells_of_phase = {}
-        ph_map = self._mapping(self.phase_label, self.cells_of_phase)
-        w.dataset('/cell_to/phase', ph_map.reshape(n, 1), description='cell ID and constituent ID to phase results', **self._stamp)
+        # material.f90:177-203 counts a phase's entries over the cells and, within a cell, over its constituents: the flat
+        # (cell, constituent) order; cells_of_phase holds each phase's flat indices ce * C + co
+        ph_map = self._mapping(self.phase_label.reshape(-1), self.cells_of_phase)
+        w.dataset('/cell_to/phase', ph_map.reshape(n, nc), description='cell ID and constituent ID to phase results', **self._stamp)
         w.dataset('/cell_to/homogenization', self._mapping(homog_label, {}), description='cell ID to homogenization results',
                   **self._stamp)
         for name, text in (setup or {}).items():
@@ -144,9 +151,15 @@ class ResultWriter:
         return out
 
     def add_increment(self, inc, t, fields, u_n=None, u_p=None):
-        """fields: name -> [N, ...] array in cell order (x fastest), tensors as natural [N,3,3]; split per phase here.
+        """fields: name -> [N, ...] array in cell order (x fastest), tensors as natural [N,3,3]; split per phase here.  With C > 1
+        constituents per cell: [N, C, ...], constituent co of cell ce at [ce, co].
         xi_sl / gamma_sl may be wider than a phase's N_sl (padded state arrays): the phase's leading columns are kept."""
         n = int(np.prod(self.cells))
+        nc = self.n_const
+        for name, a in fields.items():                                     # refuse before anything of the increment is written
+            a = np.asarray(a)
+            if a.shape[0] != n or (nc > 1 and (a.ndim < 2 or a.shape[1] != nc)):
+                raise ValueError('%s: shape %s for %d cells with %d constituent(s)' % (name, a.shape, n, nc))
         base = '/increment_%d' % inc
         self.w.group(base, **{'t/s': float(t)})
         self.w.group(base + '/geometry')
@@ -161,8 +174,8 @@ class ResultWriter:
             self.w.group(grp)
             for name, a in fields.items():
                 a = np.asarray(a)
-                if a.shape[0] != n:
-                    raise ValueError('%s: %d rows for %d cells' % (name, a.shape[0], n))
+                if nc > 1:
+                    a = a.reshape((n * nc,) + a.shape[2:])                 # flat (cell, constituent) order
                 extra = {}
                 if name in ('xi_sl', 'gamma_sl'):
                     if ph not in self.n_sl:
@@ -202,7 +215,12 @@ class ResultWriter:
         """this rank's cells: the per-point arrays of the constitutive update and the displacements"""
         g = solver.g
         n = g.n_local
-        get = lambda k: g.get_state(k, 9).reshape(n, 3, 3)
+        nc = getattr(g, 'n_constituents', 1)
+        if nc != self.n_const:
+            raise ValueError('solver has %d constituent(s) per cell, the result file was laid out for %d' % (nc, self.n_const))
+        # per-point arrays: point k * n + cell is constituent k of the cell -> [cell, constituent, ...] (slabs concatenate)
+        cellwise = (lambda a: a) if nc == 1 else (lambda a: np.ascontiguousarray(np.swapaxes(a.reshape((nc, n) + a.shape[1:]), 0, 1)))
+        get = lambda k: g.get_state(k, 9).reshape(n * nc, 3, 3)
         F, Fp, Fe, Lp, S = get('F'), get('Fp'), get('Fe'), get('Lp'), get('S')
         # phase_mechanical.f90:595: P = F Fp^-1 S Fp^-T with the Fp BEFORE its determinant is normalised (:600), i.e.
         # Fp^-1 = F^-1 F_e (F_i = I); the stored, normalised F_p differs from it by ~1e-7 (so does DAMASK's own file)
@@ -211,6 +229,7 @@ class ResultWriter:
         ms = int(g.lib.dmk_max_state(g.ctx))
         if self.n_sl and ms > 0:
             fields['xi_sl'] = g.get_state('state', ms)[:, :max(self.n_sl.values())]
+        fields = {k: cellwise(v) for k, v in fields.items()}
         if not hasattr(self, '_x0'):                                       # undeformed coordinates: the same routine on F = I
             nx, ny, _ = self.cells
             self._x0 = g.update_coords(g.to_device(np.broadcast_to(np.eye(3), (g.nz_local, ny, nx, 3, 3)).copy()))
@@ -232,7 +251,7 @@ class ResultWriter:
 class ResultReader:
     """The reading side, for the same files (ours or DAMASK's own): increments, times, grid, and `place` -- per-phase
     datasets put back into cell order through /cell_to/phase, what damask.Result.place does
-    (/root/reference/python/damask/_result.py) for single-constituent results."""
+    (/root/reference/python/damask/_result.py); several constituents per cell come back as an extra axis."""
 
     def __init__(self, path):
         from .hdf5_min import H5File
@@ -246,11 +265,13 @@ class ResultReader:
         self.size = np.asarray(geo['size'], float) if 'size' in geo else None
         self.origin = np.asarray(geo['origin'], float) if 'origin' in geo else None
         m = f.read('/cell_to/phase')
-        if m.ndim == 2 and m.shape[1] != 1:
-            raise NotImplementedError('results with %d constituents per cell' % m.shape[1])
+        self.n_const = int(m.shape[1]) if m.ndim == 2 else 1
+        n_cells = m.shape[0]
         m = m.reshape(-1)
+        # flat (cell, constituent) order; with one constituent per cell simply the cells
         self.phase_label = np.array([l.split(b'\0')[0].decode() for l in m['label']], dtype=object)
         self.phase_entry = m['entry'].astype(np.int64)
+        self.n_cells = n_cells
         self.phases = sorted(set(self.phase_label))
 
     def datasets(self, inc, phase=None, field='mechanical'):
@@ -269,13 +290,16 @@ class ResultReader:
         return out
 
     def place(self, name, inc, field='mechanical', fill=np.nan):
-        """dataset of every cell in cell order (x fastest); cells of phases that do not have it hold `fill`"""
+        """dataset of every cell in cell order (x fastest), [N, ...]; with C > 1 constituents per cell [N, C, ...]; material
+        points of phases that do not have it hold `fill`"""
         per_phase = self.get(name, inc, field)
         first = next(iter(per_phase.values()))
         out = np.full((self.phase_label.size,) + first.shape[1:], fill, dtype=first.dtype if first.dtype.kind == 'f' else float)
         for ph, a in per_phase.items():
             sel = self.phase_label == ph
             out[sel] = a[self.phase_entry[sel]]
+        if self.n_const > 1:
+            out = out.reshape((self.n_cells, self.n_const) + out.shape[1:])
         return out
 
     def geometry(self, name, inc):

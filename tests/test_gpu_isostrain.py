@@ -160,3 +160,33 @@ def test_isostrain_through_the_fortran_named_symbols():
         assert np.array_equal(ga.get_state('Fp0', 9), gb.get_state('Fp0', 9))
     finally:
         L.check(lib.dmk_bind_global(None))
+
+
+def test_isostrain_result_file_from_the_solver(tmp_path):
+    """DADF5 output of a Taylor-aggregate job: every constituent's datasets through /cell_to/phase [N, C]; each constituent
+    carries the cell's F, and the volume-fraction weighted mean of the written P is the solver's homogenised stress"""
+    from solver_cpp_b200 import mech, workloads as W, material as M
+    from solver_cpp_b200.dadf5 import ResultWriter, ResultReader
+    cells = (6, 5, 4)
+    n, nc = int(np.prod(cells)), 2
+    material, material_at, size = W.taylor_polycrystal(cells, 7, ['Al_pheno', 'Cu_pheno'], nc, seed=5)
+    s = mech.make_solver(cells, size, material, material_at)
+    s.init()
+    w = ResultWriter(cells, size, material, material_at)
+    recs = mech.loop_over_loadcase(s, mech.parse_load(W.TENSION_X), max_increments=2, callback=w.callback())
+    path = str(tmp_path / 'taylor.hdf5')
+    w.save(path)
+    r = ResultReader(path)
+    assert r.n_const == nc and r.increments == [1, 2]
+    F = r.place('F', 2)
+    assert F.shape == (n, nc, 3, 3)
+    F_cell = s.g.to_natural(s.field('F')).reshape(n, 3, 3)
+    assert np.array_equal(F[:, 0], F[:, 1])                                       # isostrain
+    assert np.abs(F[:, 0] - F_cell).max() < 1e-12
+    Fp = r.place('F_p', 2)
+    assert np.array_equal(np.swapaxes(Fp, 0, 1).reshape(nc * n, 3, 3), s.g.get_state('Fp', 9).reshape(nc * n, 3, 3))
+    assert np.abs(Fp[:, 0] - Fp[:, 1]).max() > 1e-3                                # two different crystallites per cell
+    v = M.Material(material, material_at).v_of_point.reshape(nc, n).T            # [cell, constituent]
+    P_av = (r.place('P', 2) * v[:, :, None, None]).sum(1).mean(0)
+    assert _rel(P_av, recs[-1]['P_av']) < 1e-6
+    assert r.place('xi_sl', 2).shape == (n, nc, 12)

@@ -144,6 +144,38 @@ def test_refusals():
     if len(np.unique(material_at)) == 2:
         with pytest.raises(L.DmkError):
             M.Material(bad, material_at)
-    from solver_cpp_b200.dadf5 import ResultWriter
-    with pytest.raises(NotImplementedError):
-        ResultWriter(cells, (1e-5,) * 3, material, material_at)
+
+
+def test_result_file_with_several_constituents_round_trips(tmp_path):
+    """/cell_to/phase [N, C] with the entry counters of material.f90:177-203 (per phase: cell by cell, constituent by
+    constituent), per-phase datasets in that order, and the reader's place() back to [N, C, ...]"""
+    from solver_cpp_b200.dadf5 import ResultWriter, ResultReader
+    cells = (4, 3, 2)
+    n, nc = int(np.prod(cells)), 3
+    material, material_at, size = W.taylor_polycrystal(cells, 5, ['Al_pheno', 'Cu_pheno'], nc, seed=6)
+    w = ResultWriter(cells, size, material, material_at)
+    rng = np.random.default_rng(1)
+    F = rng.standard_normal((n, nc, 3, 3)); xi = rng.standard_normal((n, nc, 24)); O = rng.standard_normal((n, nc, 4))
+    u_p = rng.standard_normal((n, 3)); u_n = rng.standard_normal(((cells[0] + 1) * (cells[1] + 1) * (cells[2] + 1), 3))
+    w.add_increment(4, 2.0, {'F': F, 'xi_sl': xi, 'O': O}, u_n=u_n, u_p=u_p)
+    with pytest.raises(ValueError):
+        w.add_increment(5, 2.5, {'F': F[:, :2]})
+    path = str(tmp_path / 'taylor.hdf5')
+    w.save(path)
+    r = ResultReader(path)
+    assert r.n_const == nc and r.n_cells == n and r.increments == [4] and r.times == [2.0]
+    # the reference's counting rule, literally
+    counter = {}
+    lab = np.empty((n, nc), dtype=object); ent = np.zeros((n, nc), dtype=np.int64)
+    for ce in range(n):
+        for co in range(nc):
+            ph = material['material'][material_at[ce]]['constituents'][co]['phase']
+            lab[ce, co] = ph
+            ent[ce, co] = counter.get(ph, 0)                       # 0-based in the file (result.f90 writes entry - 1)
+            counter[ph] = counter.get(ph, 0) + 1
+    assert np.array_equal(r.phase_label.reshape(n, nc), lab) and np.array_equal(r.phase_entry.reshape(n, nc), ent)
+    assert np.array_equal(r.place('F', 4), F) and np.array_equal(r.place('O', 4), O)
+    assert np.array_equal(r.place('xi_sl', 4), xi[..., :12])       # N_sl = 12 of both phases
+    per_phase = r.get('F', 4)
+    assert {k: v.shape[0] for k, v in per_phase.items()} == counter
+    assert np.array_equal(r.geometry('u_p', 4), u_p)
