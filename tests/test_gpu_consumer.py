@@ -34,14 +34,17 @@ def _rel(a, b):
     return np.abs(np.asarray(a) - np.asarray(b)).max() / max(np.abs(np.asarray(b)).max(), 1e-300)
 
 
-@pytest.mark.parametrize('phase', ['Al_pheno', 'TWIP'])
+@pytest.mark.parametrize('phase', ['Al_pheno', 'TWIP', 'taylor'])     # taylor: isostrain aggregates of 2 Al crystallites through the init trio
 def test_cpp_consumer_matches_python_host(tmp_path, phase):
     import __graft_entry__ as ge
     exe = ge.build_consumer()
     from solver_cpp_b200 import workloads as W, material as M, mech
     from solver_cpp_b200.grid import GridContext, fortran_to_c3333
     nx, ny, nz, n_mat = 8, 6, 4, 7
-    material, _, _ = W.polycrystal((nx, ny, nz), n_mat, phase, 3)
+    if phase == 'taylor':
+        material, _, _ = W.taylor_polycrystal((nx, ny, nz), n_mat, ['Al_pheno'], 2, 3)
+    else:
+        material, _, _ = W.polycrystal((nx, ny, nz), n_mat, phase, 3)
     path = tmp_path / 'material.yaml'
     path.write_text(yaml.safe_dump(material))
     r = subprocess.run([exe, str(path), str(nx), str(ny), str(nz), str(n_mat), str(tmp_path / 'no_numerics.yaml')], capture_output=True, text=True, timeout=300)
