@@ -1,5 +1,5 @@
 """Extracts golden set G3 -- the literal inputs and expected values of the reference's own C++ unit tests of the hot path
-(/root/reference/src/grid/test/test_mech_base.cpp, test_spectral.cpp) -- into tests/golden/g3_unit_test_literals.npz.
+(/root/reference/src/grid/test/test_mech_base.cpp, test_spectral.cpp, test_mech_solver_basic.cpp) -- into tests/golden/g3_unit_test_literals.npz.
 Run in the build container (the reference tree is not present on the GPU box):  python tests/golden/make_golden_g3.py"""
 import os
 import re
@@ -7,6 +7,7 @@ import numpy as np
 
 REF = '/root/reference/src/grid/test/test_mech_base.cpp'
 REF_SPECTRAL = '/root/reference/src/grid/test/test_spectral.cpp'
+REF_SOLVER = '/root/reference/src/grid/test/test_mech_solver_basic.cpp'
 OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'g3_unit_test_literals.npz')
 
 
@@ -51,6 +52,40 @@ def main():
     out['hom_P_av'] = set_values(b, 'expected_P_av')
     out['hom_C_vol_avg'] = set_values(b, 'expected_C_vol_avg')
     out['hom_C_minmax_avg'] = set_values(b, 'expected_C_minmax_avg')
+    # xi tables of Spectral::init on the 2 x 1 x 1 mock grid (test_spectral.cpp:15-48; geom_size = cells * 1e-5, conftest.h:39)
+    b = test_body(open(REF_SPECTRAL).read(), 'SpectralTestInit')
+    out['xi_cells'] = np.array([int(v) for v in re.search(r'mock_grid\(std::array<int, 3>\{(\d+),(\d+),(\d+)\}\)', b).groups()])
+    out['xi_expected_1st'] = set_values(b, 'expected_xi1st')              # (3, nx/2+1, nz, ny)
+    out['xi_expected_2nd'] = set_values(b, 'expected_xi2nd')
+    # forward_field / calculate_rate literals (test_mech_base.cpp:199-237, 492-545)
+    b = test_body(src, 'MechBaseTestForwardField')
+    out['ff_field_last_inc'] = set_values(b, 'field_last_inc')            # (3, 3, nx, ny, nz)
+    out['ff_rate'] = set_values(b, 'rate')
+    out['ff_aim'] = set_values(b, 'aim')
+    out['ff_delta_t'] = float(re.search(r'double delta_t = ([0-9.eE+-]+);', b).group(1))
+    out['ff_expected'] = set_values(b, 'expected_forwarded_field')
+    b = test_body(src, 'TestCalculateRate')
+    out['cr_field'] = set_values(b, 'field')
+    out['cr_field_0'] = set_values(b, 'field_0')
+    out['cr_av_rate'] = set_values(b, 'avRate')
+    out['cr_expected'] = set_values(b, 'expected_rate')
+    m = re.search(r'calculate_rate\((true|false), field_0, field, ([0-9.eE+-]+), avRate\)', b)
+    out['cr_heterogeneous'] = m.group(1) == 'true'
+    out['cr_delta_t'] = float(m.group(2))
+    # residual glue with mocked constitutive response, divergence and Gamma (test_mech_solver_basic.cpp:232-376)
+    b = test_body(open(REF_SOLVER).read(), 'TestFormResidual')
+    out['fr_F'] = set_values(b, 'F')                                      # (3, 3, 2, 1, 1)
+    out['fr_S'] = set_values(b, 'mech_basic.S')
+    out['fr_P_av_before'] = set_values(b, 'mech_basic.P_av')
+    out['fr_P'] = set_values(b, 'mocked_constitutive_response_P')
+    out['fr_expected_gamma_aim'] = set_values(b, 'expected_rotated')
+    out['fr_expected_F_aim'] = set_values(b, 'expected_F_aim')
+    m = re.search(r'mech_basic\.F_aim <<([^;]+);', b)
+    out['fr_F_aim'] = np.array([float(v) for v in m.group(1).replace('\n', ' ').split(',')]).reshape(3, 3)
+    m = re.search(r'stress_mask <<([^;]+);', b)
+    out['fr_stress_mask'] = np.array([v.strip() == 'true' for v in m.group(1).replace('\n', ' ').split(',')]).reshape(3, 3)
+    out['fr_err_BC'] = float(re.search(r'EXPECT_EQ\(mech_basic\.err_BC,\s*([0-9.eE+-]+)\)', b).group(1))
+    out['fr_err_div'] = float(re.search(r'EXPECT_EQ\(mech_basic\.err_div,\s*([0-9.eE+-]+)\)', b).group(1))
     np.savez(OUT, **out)
     for k, v in out.items():
         print(k, np.shape(v))

@@ -140,6 +140,93 @@ def test_g3_homogenisation_unit_test_literal(g3):
         assert np.abs(got - g3[key]).max() <= 1e-12 * np.abs(g3[key]).max(), key
 
 
+def test_g3_xi_tables_unit_test_literal(g3):
+    """test_spectral.cpp:15-48 (SpectralTestInit): 2x1x1 grid of size 2e-5 x 1e-5 x 1e-5: xi2nd(0, kx=1) = i 314159.2653589793,
+    xi1st identically zero (the only non-zero frequency is the Nyquist one)."""
+    cells = tuple(int(c) for c in g3['xi_cells'])
+    grid = sp.Grid(cells, tuple(1e-5 * c for c in cells))
+    xi1, xi2 = sp.xi_tables(grid, 0)
+    lit1 = np.transpose(g3['xi_expected_1st'], (2, 3, 1, 0))           # (3, kx, kz, ky) -> [kz, ky, kx, 3]
+    lit2 = np.transpose(g3['xi_expected_2nd'], (2, 3, 1, 0))
+    assert (xi1 == lit1).all()
+    assert np.abs(xi2 - lit2).max() <= 1e-8                            # the reference compares with tensor_eq(eps = 1e-8)
+    assert abs(xi2[0, 0, 1, 0].imag - 314159.2653589793) <= 1e-15 * 314159.2653589793
+
+
+def _fld(a):
+    return np.transpose(a, (4, 3, 2, 0, 1))                            # (i, j, x, y, z) -> [z, y, x, i, j]
+
+
+def test_g3_forward_field_and_calculate_rate_unit_test_literals(g3):
+    """test_mech_base.cpp:199-237 (MechBaseTestForwardField) and :492-545 (TestCalculateRate)"""
+    grid = sp.Grid((2, 1, 1), (2e-5, 1e-5, 1e-5))
+    got = sp.forward_field(float(g3['ff_delta_t']), _fld(g3['ff_field_last_inc']), _fld(g3['ff_rate']), grid, aim=g3['ff_aim'])
+    assert np.abs(got - _fld(g3['ff_expected'])).max() <= 1e-15
+    rate = sp.calculate_rate(bool(g3['cr_heterogeneous']), _fld(g3['cr_field_0']), _fld(g3['cr_field']), float(g3['cr_delta_t']),
+                             g3['cr_av_rate'])
+    exp = _fld(g3['cr_expected'])
+    assert np.abs(rate - exp).max() <= 1e-17                           # literals printed to 17 digits
+    assert (rate[exp == 0] == 0).all()
+    # the homogeneous branch hands out the average rate
+    assert np.array_equal(sp.calculate_rate(False, _fld(g3['cr_field_0']), _fld(g3['cr_field']), 1.0, g3['cr_av_rate'])[0, 0, 1], g3['cr_av_rate'])
+
+
+def test_g3_form_residual_glue_unit_test_literal(g3):
+    """test_mech_solver_basic.cpp:232-376 (TestFormResidual): with the constitutive response mocked to a literal P field on
+    the 2x1x1 grid, the residual glue must give err_div = 0, err_BC = 11717501649.529392 (EXPECT_EQ, exact), the literal
+    F_aim, and hand the literal rotated Delta F_aim to the Gamma convolution -- which on this grid (xi1st = 0) returns it in
+    every cell.  The reference test also mocks divergence and Gamma; here the oracle's own run on the literal field."""
+    from oracle.solver import MechSolverBasicOracle
+    from solver_cpp_b200 import workloads as W
+    cells = (2, 1, 1)
+    material, material_at, _ = W.polycrystal(cells, 2, 'Al_pheno', 0)
+    o = MechSolverBasicOracle(cells, (2e-5, 1e-5, 1e-5), material, material_at, tangent_every_eval=False)
+    P_lit = _fld(g3['fr_P']).reshape(2, 3, 3)
+
+    class MockedResponse:                                              # EXPECT_CALL(spectral, constitutive_response).WillOnce(Return(P))
+        counters = np.zeros(6, dtype=np.int64)
+        terminally_ill = False
+
+        def mechanical_response(self, F, dt):
+            return False
+
+        def mechanical_response2(self, dt, tangent=True):
+            return P_lit.copy(), None
+    o.con = MockedResponse()
+    o.S = g3['fr_S'].copy()
+    o.P_av = g3['fr_P_av_before'].copy()
+    o.F_aim = g3['fr_F_aim'].copy()
+    o.P_aim = np.zeros((3, 3))
+    o.params = dict(stress_mask=g3['fr_stress_mask'].copy(), R=np.eye(3), dt=1.0)
+    o.C_ref = np.einsum('ik,jl->ijkl', np.eye(3), np.eye(3)) * 1.0e11
+    r = o.form_residual(_fld(g3['fr_F']).reshape(-1), 0, 0).reshape(2, 3, 3)
+    assert o.err_div == float(g3['fr_err_div']) == 0.0
+    assert o.err_BC == float(g3['fr_err_BC'])                          # exact, like the reference's EXPECT_EQ
+    assert np.abs(o.P_av - g3['fr_P_av_before']).max() <= 2e-6         # the literal P_av is the mean of the literal P (1.2e10 Pa)
+    assert np.abs(o.F_aim - g3['fr_expected_F_aim']).max() <= 1e-8     # tensor_eq's eps
+    assert np.abs(o.F_aim - g3['fr_expected_F_aim']).max() <= 5e-16
+    for cell in range(2):
+        assert np.abs(r[cell] - g3['fr_expected_gamma_aim']).max() <= 5e-17
+
+
+def test_converged_reports_a_positive_reason_on_zero_errors():
+    """test_mech_solver_basic.cpp:91-102 (TestConverged): total_iter = 1, zero errors -> converged.  (The reference test expects
+    the enum value 2; mech_solver_basic.cpp:264 assigns SNES_BREAKOUT_INNER_ITER, 6 in PETSc 3.18's enum -- any positive
+    reason ends the SNES loop as converged, which is what is pinned here.)"""
+    from oracle.solver import MechSolverBasicOracle, SNES_BREAKOUT_INNER_ITER
+    from solver_cpp_b200 import workloads as W
+    cells = (2, 1, 1)
+    material, material_at, _ = W.polycrystal(cells, 2, 'Al_pheno', 0)
+    o = MechSolverBasicOracle(cells, (2e-5, 1e-5, 1e-5), material, material_at)
+    o.total_iter = 1
+    o.err_div = o.err_BC = 0.0
+    assert o.converged(4) == SNES_BREAKOUT_INNER_ITER > 0
+    o.total_iter = 0                                                   # below itmin = 1: keep iterating
+    assert o.converged(0) == 0
+    o.total_iter = o.num['itmax']; o.err_BC = 1.0e30
+    assert o.converged(0) < 0
+
+
 def test_g4_real_damask_run_reproduced_within_solver_tolerance(golden_dir):
     """Golden set G4: a real DAMASK_grid (3.0.0-alpha7) result file shipped with the reference
     (python/tests/resources/Result/6grains6x7x8_single_phase_tensionY.hdf5; non-cubic 6x7x8 grid, mixed boundary
