@@ -52,7 +52,7 @@ def parse_load(load):
             step['R'] = M.qu2om(mech['R'])
         d = st['discretization']
         step.update(t=float(d['t']), N=int(d['N']), r=float(d.get('r', 1)), estimate_rate=bool(st.get('estimate_rate', True)),
-                    f_out=int(st.get('f_out', 1)))
+                    f_out=int(st.get('f_out', 1)), f_restart=int(st.get('f_restart', 0)))             # config.h:93-95 defaults
         steps.append(step)
     return steps
 

@@ -77,6 +77,70 @@ CONFIGS = {
 }
 
 
+# The reference's own 16^3 deck (BASELINE.json configs[0], "20grains16x16x16 tensionX"): seed positions of
+# examples/grid/20grains.seeds (in units of the box; the geometry is their periodic Voronoi tessellation on 16^3 cells of a unit
+# cube) and the 20 orientations of examples/grid/material.yaml (unit quaternions; its phase is PHASES['Al_pheno']).  Pinned:
+# tests/test_oracle_golden.py compares the tessellation with the 16^3 VTI text the reference's own reader test embeds
+# (test_discretization_grid.cpp:103-124 -> tests/golden/g6_unit_test_geometry.vti: all 4096 cells equal) and the tables with
+# the decks under tests/golden.
+REFERENCE_20GRAINS_SEEDS = (
+    (0.375488, 0.161813, 0.891040),
+    (0.187988, 0.849313, 0.953540),
+    (0.750488, 0.349313, 0.953540),
+    (0.312988, 0.099313, 0.891040),
+    (0.562988, 0.536813, 0.703540),
+    (0.750488, 0.036813, 0.641040),
+    (0.812988, 0.724313, 0.016040),
+    (0.187988, 0.161813, 0.266040),
+    (0.562988, 0.286813, 0.203540),
+    (0.937988, 0.599313, 0.953540),
+    (0.937988, 0.349313, 0.578540),
+    (0.812988, 0.661813, 0.453540),
+    (0.125488, 0.411813, 0.203540),
+    (0.625488, 0.224313, 0.578540),
+    (0.687988, 0.161813, 0.891040),
+    (0.625488, 0.161813, 0.766040),
+    (0.437988, 0.724313, 0.266040),
+    (0.437988, 0.099313, 0.641040),
+    (0.937988, 0.911813, 0.828540),
+    (0.437988, 0.411813, 0.516040),
+)
+REFERENCE_20GRAINS_O = (
+    (1.0, 0.0, 0.0, 0.0),
+    (0.7936696712125002, -0.28765777461664166, -0.3436487135089419, 0.4113964260949434),
+    (0.3986143167493579, -0.7014883552495493, 0.2154871765709027, 0.5500781677772945),
+    (0.28645844315788244, -0.022571491243423537, -0.467933059311115, -0.8357456192708106),
+    (0.33012772942625784, -0.6781865350268957, 0.6494525351030648, 0.09638521992649676),
+    (0.43596817439583935, -0.5982537129781701, 0.046599032277502436, 0.6707106499919265),
+    (0.169734823419553, -0.699615227367322, -0.6059581215838098, -0.33844257746495854),
+    (0.9698864809294915, 0.1729052643205874, -0.15948307917616958, 0.06315956884687175),
+    (0.46205660912967883, 0.3105054068891252, -0.617849551030653, 0.555294529545738),
+    (0.4512443497461787, -0.7636045534540555, -0.04739348426715133, -0.45939142396805815),
+    (0.2161856212656443, -0.6581450184826598, -0.5498086209601588, 0.4667112513346289),
+    (0.8753220715350803, -0.4561599367657419, -0.13298279533852678, -0.08969369719975541),
+    (0.11908260752431069, 0.18266024809834172, -0.7144822594012615, -0.664807992845101),
+    (0.751104669484278, 0.5585633382623958, -0.34579336397009175, 0.06538900566860861),
+    (0.08740438971703973, 0.8991264096610437, -0.4156704205935976, 0.10559485570696363),
+    (0.5584325870096193, 0.6016408353068798, -0.14280340445801173, 0.5529814994483859),
+    (0.4052725440888093, 0.25253073423599154, 0.5693263597910454, -0.669215876471182),
+    (0.7570164606888676, 0.15265448024694664, -0.5998021466848317, 0.20942796551297105),
+    (0.6987659297138081, -0.132172211261028, -0.19693254724422338, 0.6748883269678543),
+    (0.7729330445886478, 0.21682179052722322, -0.5207379472917645, 0.2905078484066341),
+)
+
+
+def reference_20grains(cells=(16, 16, 16), z_range=None):
+    """-> (material dict, material_at of the slab, size) of the reference's example deck examples/grid/{20grains.seeds,
+    material.yaml}; other `cells` re-discretise the same 20 seeds"""
+    size = (1.0, 1.0, 1.0)
+    material = {'homogenization': {'SX': {'N_constituents': 1, 'mechanical': {'type': 'pass'}}},
+                'phase': {'Aluminum': PHASES['Al_pheno']},
+                'material': [{'homogenization': 'SX', 'constituents': [{'phase': 'Aluminum', 'v': 1.0, 'O': list(q)}]}
+                             for q in REFERENCE_20GRAINS_O]}
+    seeds = np.asarray(REFERENCE_20GRAINS_SEEDS, float) * np.asarray(size)
+    return material, voronoi_material_at(cells, size, seeds, z_range), size
+
+
 def random_orientations(n, rng):
     q = rng.standard_normal((n, 4))
     q /= np.linalg.norm(q, axis=1, keepdims=True)

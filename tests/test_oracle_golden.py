@@ -301,3 +301,77 @@ def test_g4b_two_phase_real_damask_run_within_solver_tolerance(golden_dir):
         assert np.abs(F - g4['F'][k]).max() < 1e-5
         assert np.abs(P - Pd).max() < 6e-4 * np.abs(Pd).max()
         assert np.abs(P.mean(0) - Pd.mean(0)).max() < 3e-4 * np.abs(Pd.mean(0)).max()
+
+
+def test_g6_cell_centre_and_node_coordinates_unit_test_literals(golden_dir):
+    """test_discretization_grid.cpp:70-101 (TestCalculateIpCoords0 / TestCalculateNodes0): undeformed cell centres and nodes
+    of the 2x1x1 grid of size 2e-5 x 1e-5 x 1e-5, x fastest.  The oracle has no separate routine for them: they are what
+    update_coords (mech_base.cpp:45-154) returns at F = I, which is how the result writer obtains them."""
+    g6 = np.load(os.path.join(golden_dir, 'g6_discretization_literals.npz'))
+    cells = tuple(int(c) for c in g6['coords_cells'])
+    grid = sp.Grid(cells, tuple(float(s) for s in g6['coords_size']))
+    nx, ny, nz = cells
+    x_n, x_p = sp.update_coords(np.broadcast_to(np.eye(3), (nz, ny, nx, 3, 3)).copy(), grid)
+    assert np.abs(x_p.reshape(-1, 3).T - g6['ip_coords0']).max() <= 1e-20
+    assert np.abs(x_n.reshape(-1, 3).T - g6['node_coords0']).max() <= 1e-20
+
+
+def test_g6_voronoi_generator_reproduces_the_reference_geometry(golden_dir):
+    """The 16^3 VTI text embedded in the reference's reader test (test_discretization_grid.cpp:103-124) is the periodic Voronoi
+    tessellation of examples/grid/20grains.seeds (damask.Grid.from_Voronoi_tessellation, python/damask/_grid.py:563-571).
+    solver_cpp_b200.workloads.voronoi_material_at -- the generator of every synthetic polycrystal in bench.py and the tests --
+    must give the same material ID in all 4096 cells, and workloads.reference_20grains() (BASELINE.json configs[0]) must be
+    that deck: seeds of 20grains.seeds, orientations and phase of examples/grid/material.yaml."""
+    import importlib.util
+    import yaml
+    from solver_cpp_b200 import workloads as W
+    spec = importlib.util.spec_from_file_location('dmk_vti', os.path.join(os.path.dirname(golden_dir), '..', 'solver_cpp_b200', 'vti.py'))
+    vti = importlib.util.module_from_spec(spec); spec.loader.exec_module(vti)
+    geo = vti.read_vti(os.path.join(golden_dir, 'g6_unit_test_geometry.vti'))
+    rows = [l.split() for l in open(os.path.join(golden_dir, '20grains.seeds'))]
+    seeds = np.array([[float(v) for v in r] for r in rows if len(r) == 6 and r[0].replace('.', '').isdigit()])
+    assert seeds.shape == (20, 6)
+    assert np.array_equal(np.asarray(W.REFERENCE_20GRAINS_SEEDS), seeds[:, :3])
+    got = W.voronoi_material_at((16, 16, 16), tuple(geo['size']), seeds[:, :3] * geo['size'])
+    assert np.array_equal(got, geo['material'].ravel())
+    # slabs of the same tessellation (what each rank of a multi-GPU job computes for itself)
+    parts = [W.voronoi_material_at((16, 16, 16), tuple(geo['size']), seeds[:, :3] * geo['size'], z_range=(a, b)) for a, b in ((0, 5), (5, 16))]
+    assert np.array_equal(np.concatenate(parts), got)
+    material, material_at, size = W.reference_20grains()
+    assert np.array_equal(material_at, got) and size == (1.0, 1.0, 1.0)
+    deck = yaml.safe_load(open(os.path.join(golden_dir, 'material_20grains_Al.yaml')))
+    assert [m['constituents'][0]['O'] for m in material['material']] == [m['constituents'][0]['O'] for m in deck['material']]
+    ours, theirs = material['phase']['Aluminum'], deck['phase']['Aluminum']
+    assert ours['lattice'] == theirs['lattice'] and ours['mechanical']['elastic'] == theirs['mechanical']['elastic']
+    assert ours['mechanical']['plastic'] == {k: v for k, v in theirs['mechanical']['plastic'].items() if k != 'output'}
+
+
+def test_reference_16cubed_deck_solves_like_the_recorded_27_cell_run():
+    """BASELINE.json configs[0] (the reference's own example deck, workloads.reference_20grains: 16^3 cells, 20 grains, Al
+    phenopowerlaw, tensionX with the example numerics N_iter_min 4 / N_iter_max 40) through the oracle's solver.  No recorded
+    output of this deck exists in the reference tree; the recorded Fortran run G1 is the same material and load on 27 cells with
+    the same 20 orientations, so the homogenised stress-strain curve must lie close to G1's (35.24, 64.66, 72.95 MPa)."""
+    from oracle.solver import MechSolverBasicOracle, run_loadcase, parse_load as oparse
+    from solver_cpp_b200 import workloads as W
+    material, material_at, size = W.reference_20grains()
+    o = MechSolverBasicOracle((16, 16, 16), size, material, material_at, tangent_every_eval=False, grid_mech=dict(itmin=4, itmax=40))
+    o.log_fields = False
+    o.init()
+    recs = []
+
+    class Stop(Exception):
+        pass
+
+    def cb(rec, s):
+        recs.append(rec)
+        if len(recs) == 3:
+            raise Stop
+    try:
+        run_loadcase(o, oparse(W.TENSION_X), callback=cb)
+    except Stop:
+        pass
+    assert [r['converged'] for r in recs] == [True] * 3 and all(4 <= r['iterations'] <= 12 for r in recs)
+    P11 = np.array([r['P_av'][0, 0] for r in recs]) * 1e-6
+    assert np.abs(P11 / np.array([35.2362, 64.6648, 72.9485]) - 1.0).max() < 0.03
+    for r in recs:                                                     # uniaxial stress state of tensionX
+        assert abs(r['P_av'][1, 1]) < 1e-3 * r['P_av'][0, 0] and abs(r['P_av'][2, 2]) < 1e-3 * r['P_av'][0, 0]

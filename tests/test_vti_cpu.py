@@ -87,3 +87,31 @@ def test_cpp_reader_symbols_match_the_python_reader(golden_dir, tmp_path):
     cells = (C.c_int * 3)(); size = (C.c_double * 3)(); origin = (C.c_double * 3)()
     lib.f_VTI_readCellsSizeOrigin(bad, C.c_int(len(bad)), cells, size, origin)
     assert tuple(cells) == (-1, -1, -1) and b'VTI' in lib.dmk_last_error()
+
+
+def test_g6_geometry_text_of_the_reference_unit_test(golden_dir):
+    """the VTI text embedded in the reference's own reader test (test_discretization_grid.cpp:103-124, extracted by
+    tests/golden/make_golden_g6.py) with the expectations of TestVTI_readCellsSizeOrigin (:127-139): cells 16^3, origin 0,
+    size 1; TestVTI_readDataset_int (:141-149) reads 16^3 material IDs -- the file declares RangeMin 0 / RangeMax 19 -- into a
+    32-bit array, PLUS ONE.  Through the library's f_VTI_* symbols (what DiscretizationGrid binds) and the Python reader."""
+    import ctypes as C
+    g6 = np.load(os.path.join(golden_dir, 'g6_discretization_literals.npz'))
+    path = os.path.join(golden_dir, 'g6_unit_test_geometry.vti')
+    content = open(path, 'rb').read()
+    lib = C.CDLL(os.path.join(HERE, '..', 'solver_cpp_b200', 'libdamask_grid_b200.so'))
+    lib.dmk_last_error.restype = C.c_char_p
+    cells = (C.c_int * 3)(); size = (C.c_double * 3)(); origin = (C.c_double * 3)()
+    lib.f_VTI_readCellsSizeOrigin(content, C.c_int(len(content)), cells, size, origin)
+    assert list(cells) == g6['vti_expected_cells'].tolist(), lib.dmk_last_error()          # EXPECT_EQ: exact
+    assert list(size) == g6['vti_expected_size'].tolist() and list(origin) == g6['vti_expected_origin'].tolist()
+    n = 16 * 16 * 16
+    data = np.zeros(n, dtype=np.int32)
+    nn = C.c_int(n)
+    lib.f_VTI_readDataset_int(content, C.c_int(len(content)), b'material', C.c_int(8), data.ctypes.data_as(C.c_void_p), C.byref(nn))
+    assert nn.value == n, lib.dmk_last_error()
+    assert data.min() == 1 and data.max() == 20 and np.unique(data).size == 20
+    d = vti.read_vti(path)
+    assert tuple(d['cells']) == (16, 16, 16) and list(d['size']) == [1.0, 1.0, 1.0] and list(d['origin']) == [0.0, 0.0, 0.0]
+    assert np.array_equal(d['material'].ravel() + 1, data)
+    # a Voronoi tessellation: every grain is a sizeable share of the 4096 cells
+    assert np.bincount(d['material'].ravel()).min() > 40
