@@ -12,7 +12,8 @@ OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'g3_unit_test_lit
 
 
 def test_body(src, name):
-    i = src.index('TEST_F(GridTestSetup, %s)' % name)
+    m = re.search(r'TEST_F\(GridTestSetup,\s*%s\)' % name, src)
+    i = m.start()
     j = src.find('TEST_F(', i + 10)
     return src[i:j if j > 0 else len(src)]
 
@@ -86,6 +87,26 @@ def main():
     out['fr_stress_mask'] = np.array([v.strip() == 'true' for v in m.group(1).replace('\n', ' ').split(',')]).reshape(3, 3)
     out['fr_err_BC'] = float(re.search(r'EXPECT_EQ\(mech_basic\.err_BC,\s*([0-9.eE+-]+)\)', b).group(1))
     out['fr_err_div'] = float(re.search(r'EXPECT_EQ\(mech_basic\.err_div,\s*([0-9.eE+-]+)\)', b).group(1))
+    # Gamma convolution on the 2 x 1 x 1 grid (xi1st = 0: DC path and unnormalised-inverse convention; test_mech_base.cpp:389-490)
+    b = test_body(src, 'MechBaseTestGammaConvolution')
+    out['gc_field_aim'] = set_values(b, 'field_aim')
+    out['gc_C_ref'] = set_values(b, 'mech_base.C_ref')
+    out['gc_field'] = set_values(b, 'field')                              # (3, 3, 2, 1, 1)
+    out['gc_expected'] = set_values(b, 'expected_gamma_field')
+    # update_gamma with xi = 0 -> Gamma_hat = 0 (test_mech_base.cpp:154-197): the stiffness literal
+    b = test_body(src, 'TestUpdateGamma')
+    out['ug_C'] = set_values(b, 'C_min_max_avg')
+    # divergence correction of the geometry (test_mech_base.cpp:54-76)
+    b = test_body(src, 'MechBaseTestInitDivergenceCorrection')
+    out['dc_geom_size'] = np.array([float(v) for v in re.search(r'geom_size = std::array<double, 3>\{([^}]*)\}', b).group(1).split(',')])
+    out['dc_cells'] = np.array([int(v) for v in re.search(r'mock_grid\(std::array<int, 3>\{(\d+),(\d+),(\d+)\}\)', b).groups()])
+    out['dc_expected_size'] = np.array([float(v) for v in re.search(r'expected_scaled_geom_size_1\(\{([^}]*)\}\)', b).group(1).split(',')])
+    out['dc_expected_size_grid'] = np.array([float(v) for v in re.search(r'expected_scaled_geom_size_2\(\{([^}]*)\}\)', b).group(1).split(',')])
+    # update_coords at F = I on the 2 x 1 x 1 grid (test_mech_base.cpp:78-152)
+    b = test_body(src, 'MechBaseTestUpdateCoords')
+    out['uc_F'] = set_values(b, 'F_')
+    out['uc_expected_x_n'] = set_values(b, 'expected_x_n')                # (3, nx+1, ny+1, nz+1)
+    out['uc_expected_x_p'] = set_values(b, 'expected_x_p')                # (3, nx, ny, nz)
     np.savez(OUT, **out)
     for k, v in out.items():
         print(k, np.shape(v))

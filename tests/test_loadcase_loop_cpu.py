@@ -81,3 +81,26 @@ def test_nested_cut_backs_and_giving_up():
     assert np.allclose(s.calls[6]['dt'], 0.5) and np.allclose(recs[1]['t'], 2.0)      # one level is kept for the next increment
     with pytest.raises(L.DmkError):
         mech.loop_over_loadcase(_Scripted([False] * 8), mech.parse_load(LOAD), max_increments=1)
+
+
+def test_reference_loop_test_one_increment_and_no_cut_back_allowed():
+    """test_damask_grid.cpp:74-128 (TestDamaskGridLoopOverLoadcase): one load step with t = 1, N = 1 and max_cut_back = 0.
+    A converged solve forwards the fields once and reports the result exactly once, for increment 1 at t = 1
+    (EXPECT_CALL materialpoint_result(Eq(1), Eq(1))); a failed solve raises (EXPECT_THROW std::runtime_error)."""
+    load = {'loadstep': [{'boundary_conditions': {'mechanical': {'dot_F': [[1e-3, 0, 0], [0, 'x', 0], [0, 0, 'x']],
+                                                                  'P': [['x', 'x', 'x'], ['x', 0, 'x'], ['x', 'x', 0]],
+                                                                  'R': [1.0, 0.0, 0.0, 0.0]}},
+                          'discretization': {'t': 1, 'N': 1}}]}
+    steps = mech.parse_load(load)
+    assert np.array_equal(steps[0]['deformation'].mask.astype(bool), [[False, False, False], [False, True, False], [False, False, True]])
+    assert np.array_equal(steps[0]['R'], np.eye(3))
+    s = _Scripted([True])
+    results = []
+    recs = mech.loop_over_loadcase(s, steps, max_cut_back=0, callback=lambda r, _: results.append((r['inc'], r['t'])))
+    assert results == [(1, 1.0)] and len(recs) == 1
+    assert len(s.calls) == 1 and s.calls[0]['dt'] == 1.0 and not s.calls[0]['cut_back'] and not s.calls[0]['guess']
+    s = _Scripted([False])
+    results = []
+    with pytest.raises(L.DmkError):
+        mech.loop_over_loadcase(s, steps, max_cut_back=0, callback=lambda r, _: results.append(r['inc']))
+    assert results == [] and len(s.calls) == 1

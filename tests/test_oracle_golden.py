@@ -227,6 +227,83 @@ def test_converged_reports_a_positive_reason_on_zero_errors():
     assert o.converged(0) < 0
 
 
+def test_g3_gamma_convolution_and_update_gamma_unit_test_literals(g3):
+    """test_mech_base.cpp:389-490 (MechBaseTestGammaConvolution): literal stress field, literal C_ref, xi1st = 0 on the 2x1x1
+    grid -> every cell holds field_aim (DC path, unnormalised inverse).  :154-197 (TestUpdateGamma): with xi = 0 the Gamma
+    operator of any stiffness is zero -- here: applying it returns zero at every frequency."""
+    grid = sp.Grid((2, 1, 1), (2e-5, 1e-5, 1e-5))
+    xi1, _ = sp.xi_tables(grid, 0)
+    assert (xi1 == 0).all()
+    got = sp.gamma_convolution(_fld(g3['gc_field']), g3['gc_field_aim'], xi1, g3['gc_C_ref'], grid)
+    exp = _fld(g3['gc_expected'])
+    assert np.abs(got - exp).max() <= 1e-20 and (got[exp == 0] == 0).all()
+    hat = sp.fft_forward(_fld(g3['gc_field']))
+    for C in (g3['ug_C'], g3['gc_C_ref']):
+        assert (sp.gamma_hat_apply(hat, xi1, C) == 0).all()
+
+
+def test_g3_divergence_correction_unit_test_literals(g3):
+    """test_mech_base.cpp:54-76 (MechBaseTestInitDivergenceCorrection): geometry 3 x 4 x 5 on 2 x 1 x 1 cells -> scaled
+    geometry for divergence_correction none / size / size+grid (ASSERT_EQ: exact)"""
+    grid = sp.Grid(tuple(int(c) for c in g3['dc_cells']), tuple(float(v) for v in g3['dc_geom_size']))
+    assert sp.scaled_geom_size(grid, sp.DIVCORR_NONE).tolist() == g3['dc_geom_size'].tolist()
+    assert sp.scaled_geom_size(grid, sp.DIVCORR_SIZE).tolist() == g3['dc_expected_size'].tolist()
+    # size+grid: the test's literal (0.6, 0.8, 1) contradicts the code it tests -- mech_base.cpp:20-31 (and upstream DAMASK,
+    # grid_mechanical_spectral_*: the axis that is neither minloc nor maxloc of size / cells) normalises by the MIDDLE one of
+    # size / cells = (1.5, 4, 5), i.e. by axis 1: size / 4 * cells[1] = (0.75, 1, 1.25); the literal is size / 5, the largest.
+    # The oracle follows the code; the literal is kept in the fixture to document the discrepancy.
+    assert g3['dc_expected_size_grid'].tolist() == [0.6, 0.8, 1.0]
+    assert sp.scaled_geom_size(grid, sp.DIVCORR_SIZE_GRID).tolist() == [0.75, 1.0, 1.25]
+
+
+def test_g3_update_coords_unit_test_literal(g3):
+    """test_mech_base.cpp:78-152 (MechBaseTestUpdateCoords): F = I on the 2x1x1 grid -> undeformed nodes (3, nx+1, ny+1, nz+1)
+    and cell centres (3, nx, ny, nz)"""
+    grid = sp.Grid((2, 1, 1), (2e-5, 1e-5, 1e-5))
+    x_n, x_p = sp.update_coords(_fld(g3['uc_F']), grid)
+    assert np.abs(np.transpose(x_n, (3, 2, 1, 0)) - g3['uc_expected_x_n']).max() <= 1e-20
+    assert np.abs(np.transpose(x_p, (3, 2, 1, 0)) - g3['uc_expected_x_p']).max() <= 1e-20
+
+
+def test_solver_init_and_forward_unit_test_literals():
+    """test_mech_solver_basic.cpp:32-89 (TestMechSolverBasicInit): after init F_last_inc (and homogenization_F0) are the identity in
+    every cell.  :159-231 (TestBasicForward): forward(cut_back = false, guess = false, dt = 100.2, dt_old = 1, t_remaining = 1002)
+    with dot_F_11 = 1e-3 from F = I gives F_aim_11 = 1.1002000000000001, the forwarded field equal to the aim in both cells, and
+    params.delta_t = 100.2, the rotation unchanged."""
+    from oracle.solver import MechSolverBasicOracle, parse_load as oparse
+    from solver_cpp_b200 import workloads as W
+    cells = (2, 1, 1)
+    material, material_at, _ = W.polycrystal(cells, 2, 'Al_pheno', 0)
+    o = MechSolverBasicOracle(cells, (2e-5, 1e-5, 1e-5), material, material_at)
+    o.init()
+    I = np.broadcast_to(np.eye(3), (1, 1, 2, 3, 3))
+    assert np.array_equal(o.F_last_inc, I) and np.array_equal(o.F, I)
+    assert np.array_equal(o.con.a['F0'].reshape(2, 3, 3), I.reshape(2, 3, 3))
+    st = oparse({'loadstep': [{'boundary_conditions': {'mechanical': {'dot_F': [[1e-3, 0, 0], [0, 'x', 0], [0, 0, 'x']],
+                                                                       'P': [['x', 'x', 'x'], ['x', 0, 'x'], ['x', 'x', 0]],
+                                                                       'R': [1.0, 0.0, 0.0, 0.0]}},
+                               'discretization': {'t': 1002, 'N': 10}}]})[0]
+    o.forward(False, False, 100.2, 1, 1002, st['deformation'], st['stress'], st['R'])
+    expected_aim = np.diag([1.1002000000000001, 1.0, 1.0])
+    assert np.array_equal(o.F_aim, expected_aim)
+    assert np.array_equal(o.F_last_inc, I)
+    assert np.abs(o.F - expected_aim).max() <= 2.3e-16                # tensor_eq(F, forwarded_field)
+    assert o.params['dt'] == 100.2 and np.array_equal(o.params['R'], np.eye(3))
+    assert np.array_equal(o.params['stress_mask'], [[True, True, True], [True, False, True], [True, True, False]])
+
+
+def test_fft_round_trip_of_the_reference_unit_test():
+    """test_fft.cpp:10-58 (TestInitForwardBackwardCopy / ...DirectAssignment): 2x1x1 cells, 3x3 components, random data in
+    (1, 1000): forward (unnormalised) then backward with wgt = 1/N = 0.5 returns the field (tensor_eq: 1e-8 absolute)."""
+    rng = np.random.default_rng(2)
+    field = rng.uniform(1.0, 1000.0, size=(1, 1, 2, 3, 3))
+    hat = sp.fft_forward(field)
+    assert hat.shape == (1, 1, 2, 3, 3)                                # nx/2 + 1 = 2 complex coefficients along x
+    assert np.abs(hat[0, 0, 0].real - field.sum(axis=(0, 1, 2))).max() <= 1e-12 * 2000.0      # unnormalised: DC = sum
+    back = sp.fft_backward(hat, (2, 1, 1), 0.5)
+    assert np.abs(back - field).max() <= 1e-12
+
+
 def test_g4_real_damask_run_reproduced_within_solver_tolerance(golden_dir):
     """Golden set G4: a real DAMASK_grid (3.0.0-alpha7) result file shipped with the reference
     (python/tests/resources/Result/6grains6x7x8_single_phase_tensionY.hdf5; non-cubic 6x7x8 grid, mixed boundary
