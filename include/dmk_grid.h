@@ -255,6 +255,36 @@ int dmk_mech_get_field(dmk_ctx* ctx, const char* what, double* host_out);  /* "F
 int dmk_mech_set_field(dmk_ctx* ctx, const char* what, const double* host_in);
 int dmk_mech_device_field(dmk_ctx* ctx, const char* what, double** d_ptr);  /* device pointer of "F","F_lastInc","F_dot","r" */
 int dmk_mech_copy_field(dmk_ctx* ctx, const char* what, double* d_dst);      /* device-to-device copy of a solver field */
+/* ------------------------------------------------------------------ load case: Config::parse_load + DamaskGrid::loop_over_loadcase
+ * One load step (Config::LoadStep, config.h:74-96).  Values / masks / R row-major 3x3; mask 1 = 'x' (component not controlled
+ * by this boundary condition); R = the rotation of the load frame as a matrix (the file gives a quaternion w, x, y, z). */
+typedef struct {
+  char deformation_type[8];                       /* "F", "dot_F" or "L" */
+  double deformation_values[9]; int deformation_mask[9];
+  char stress_type[8];                            /* "P" or "dot_P" */
+  double stress_values[9]; int stress_mask[9];
+  double R[9];
+  double t, r; int N;                             /* discretization: time, geometric ratio of the time steps (1: equal), increments */
+  int estimate_rate, f_out, f_restart;
+} dmk_load_step;
+typedef struct { int inc, step, inc_in_step, f_out; double t; int converged, iterations; } dmk_increment_record;
+/* what the increment loop asks of the solver underneath; all return 0 or an error code that ends the loop */
+typedef struct {
+  void* user;
+  int (*forward)(void* user, int cut_back, int guess, double dt, double dt_old, double t_remaining, const dmk_load_step* step);
+  int (*materialpoint_forward)(void* user);
+  int (*calculate_solution)(void* user, dmk_solution_state* out);
+  int (*result)(void* user, const dmk_increment_record* rec);      /* may be NULL; called for the increments f_out selects */
+} dmk_loop_ops;
+/* Config::parse_load (config.cpp:247-358): load file -> load steps; mechanical_solver (may be NULL) receives solver/mechanical */
+int dmk_load_from_yaml(const char* load_yaml_path, dmk_load_step* steps, int max_steps, int* n_steps, char* mechanical_solver,
+                       int solver_name_capacity);
+/* DamaskGrid::loop_over_loadcase (damask_grid.cpp:82-196) with upstream DAMASK's cut-back bookkeeping.  ops = NULL: the context's
+ * own solver (dmk_mech_forward / dmk_materialpoint_forward / dmk_mech_calculate_solution; dmk_mech_init must have run); otherwise
+ * ctx may be NULL.  max_increments <= 0: the whole load case.  Up to max_records records are stored (records may be NULL);
+ * DMK_ERR_STATE when an increment finds no solution at the last cut-back level. */
+int dmk_loop_over_loadcase(dmk_ctx* ctx, const dmk_load_step* steps, int n_steps, int max_cut_back, int max_increments,
+                           const dmk_loop_ops* ops, dmk_increment_record* records, int max_records, int* n_records);
 /* test aid: keep host copies of the F handed to and the r returned by every residual evaluation of the solver */
 int dmk_mech_capture(dmk_ctx* ctx, int enable);
 int dmk_mech_get_capture(dmk_ctx* ctx, double* F_out, double* r_out, size_t max_evals, size_t* n_evals);

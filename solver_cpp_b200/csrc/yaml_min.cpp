@@ -185,6 +185,14 @@ struct Parser {
       while (lead < rest.size() && rest[lead] == ' ') lead++;
       rest = rest.substr(lead);
       if (rest.empty()) { i++; n->seq.push_back(block(ind + 1)); continue; }
+      if (rest[0] == '-' && (rest.size() == 1 || rest[1] == ' ')) {
+        // "- - item": a nested block sequence whose first entry sits on the dash line (how PyYAML's block style writes a
+        // matrix); re-read the line as that sequence
+        L[i].indent = ind + 2 + (int)lead;
+        L[i].text = rest;
+        n->seq.push_back(sequence(L[i].indent));
+        continue;
+      }
       const bool flow = rest[0] == '[' || rest[0] == '{';
       if (!flow && key_colon(rest) != std::string::npos) {
         // "- key: value": a mapping whose first entry sits on the dash line; re-read the line as that entry

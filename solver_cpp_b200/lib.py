@@ -80,6 +80,31 @@ class SolutionState(C.Structure):
                 ('terminally_ill', C.c_int)]
 
 
+class LoadStep(C.Structure):
+    """dmk_load_step (Config::LoadStep, config.h:74-96): values / masks / R row-major 3x3, mask 1 = 'x'"""
+    _fields_ = [('deformation_type', C.c_char * 8), ('deformation_values', C.c_double * 9), ('deformation_mask', C.c_int * 9),
+                ('stress_type', C.c_char * 8), ('stress_values', C.c_double * 9), ('stress_mask', C.c_int * 9),
+                ('R', C.c_double * 9), ('t', C.c_double), ('r', C.c_double), ('N', C.c_int),
+                ('estimate_rate', C.c_int), ('f_out', C.c_int), ('f_restart', C.c_int)]
+
+
+class IncrementRecord(C.Structure):
+    _fields_ = [('inc', C.c_int), ('step', C.c_int), ('inc_in_step', C.c_int), ('f_out', C.c_int), ('t', C.c_double),
+                ('converged', C.c_int), ('iterations', C.c_int)]
+
+
+LOOP_FORWARD = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.POINTER(LoadStep))
+LOOP_POINT_FORWARD = C.CFUNCTYPE(C.c_int, C.c_void_p)
+LOOP_SOLVE = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(SolutionState))
+LOOP_RESULT = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(IncrementRecord))
+
+
+class LoopOps(C.Structure):
+    """dmk_loop_ops: what dmk_loop_over_loadcase asks of the solver underneath"""
+    _fields_ = [('user', C.c_void_p), ('forward', LOOP_FORWARD), ('materialpoint_forward', LOOP_POINT_FORWARD),
+                ('calculate_solution', LOOP_SOLVE), ('result', LOOP_RESULT)]
+
+
 class DmkError(RuntimeError):
     pass
 

@@ -104,3 +104,137 @@ def test_reference_loop_test_one_increment_and_no_cut_back_allowed():
     with pytest.raises(L.DmkError):
         mech.loop_over_loadcase(s, steps, max_cut_back=0, callback=lambda r, _: results.append(r['inc']))
     assert results == [] and len(s.calls) == 1
+
+
+# ------------------------------------------------------------------------------------------------ the library's C++ twin
+# dmk_load_from_yaml / dmk_loop_over_loadcase (csrc/loadcase.cpp: Config::parse_load, config.cpp:247-358, and
+# DamaskGrid::loop_over_loadcase, damask_grid.cpp:82-196, compiled like the originals) against the Python host on the same decks
+# and the same scripted solver outcomes
+def _c_steps(load, tmp_path):
+    import ctypes as C
+    import yaml
+    p = tmp_path / 'load.yaml'
+    p.write_text(yaml.safe_dump(load, sort_keys=False))
+    lib = L.load()
+    steps = (L.LoadStep * 8)()
+    n = C.c_int()
+    name = C.create_string_buffer(32)
+    rc = lib.dmk_load_from_yaml(str(p).encode(), steps, C.c_int(8), C.byref(n), name, C.c_int(32))
+    assert rc == 0, lib.dmk_last_error()
+    return steps, n.value, name.value.decode()
+
+
+@pytest.mark.parametrize('deck', ['two_steps', 'tension_x', 'mixed_shear', 'reference_parser_test'])
+def test_cpp_load_reader_equals_python_host(deck, tmp_path):
+    from solver_cpp_b200 import workloads as W
+    load = {'two_steps': dict(LOAD, solver={'mechanical': 'spectral_polarisation'}), 'tension_x': W.TENSION_X, 'mixed_shear': W.MIXED_SHEAR,
+            'reference_parser_test': {'solver': {'mechanical': 'spectral_basic'}, 'loadstep': [
+                {'boundary_conditions': {'mechanical': {'dot_F': [[1.0e-3, 1, 0], [0, 'x', 0], [2, 0, 'x']],
+                                                        'P': [['x', 'x', 'x'], ['x', 0, 'x'], ['x', 'x', 0]], 'R': [1, 2, 3, 4]}},
+                 'discretization': {'t': 60, 'N': 120, 'r': 2}, 'estimate_rate': False, 'f_out': 4, 'f_restart': 10}]}}[deck]
+    steps, n, solver = _c_steps(load, tmp_path)
+    ref = mech.parse_load(load)
+    assert n == len(ref) and solver == (load.get('solver') or {}).get('mechanical', 'spectral_basic')
+    for c, p in zip(steps, ref):
+        assert c.deformation_type.decode() == p['deformation'].type and c.stress_type.decode() == p['stress'].type
+        assert np.array_equal(np.array(c.deformation_values).reshape(3, 3), p['deformation'].values)
+        assert np.array_equal(np.array(c.deformation_mask).reshape(3, 3).astype(bool), p['deformation'].mask.astype(bool))
+        assert np.array_equal(np.array(c.stress_values).reshape(3, 3), p['stress'].values)
+        assert np.array_equal(np.array(c.stress_mask).reshape(3, 3).astype(bool), p['stress'].mask.astype(bool))
+        assert np.array_equal(np.array(c.R).reshape(3, 3), p['R'])
+        assert (c.t, c.r, c.N, bool(c.estimate_rate), c.f_out, c.f_restart) == (p['t'], p['r'], p['N'], p['estimate_rate'], p['f_out'], p['f_restart'])
+
+
+def test_cpp_load_reader_refusals(tmp_path):
+    import ctypes as C
+    import yaml
+    lib = L.load()
+    steps = (L.LoadStep * 2)()
+    n = C.c_int()
+    good = LOAD['loadstep'][0]
+
+    def rc_of(load):
+        p = tmp_path / 'bad.yaml'
+        p.write_text(yaml.safe_dump(load, sort_keys=False))
+        return lib.dmk_load_from_yaml(str(p).encode(), steps, C.c_int(2), C.byref(n), None, C.c_int(0))
+    assert rc_of({'loadstep': [good]}) == 0
+    assert rc_of({'solver': {'mechanical': 'spectral_basic'}}) != 0 and b'loadstep' in lib.dmk_last_error()
+    both = {'boundary_conditions': {'mechanical': dict(good['boundary_conditions']['mechanical'], F=[[1, 0, 0], [0, 'x', 0], [0, 0, 'x']])},
+            'discretization': good['discretization']}
+    assert rc_of({'loadstep': [both]}) != 0 and b'Only one deformation' in lib.dmk_last_error()
+    no_stress = {'boundary_conditions': {'mechanical': {'dot_F': good['boundary_conditions']['mechanical']['dot_F']}}, 'discretization': good['discretization']}
+    assert rc_of({'loadstep': [no_stress]}) != 0 and b'Stress specification required' in lib.dmk_last_error()
+    overlap = {'boundary_conditions': {'mechanical': {'dot_F': [[1e-3, 0, 0], [0, 0, 0], [0, 0, 'x']], 'P': good['boundary_conditions']['mechanical']['P']}},
+               'discretization': good['discretization']}
+    assert rc_of({'loadstep': [overlap]}) != 0 and b'exactly one' in lib.dmk_last_error()
+    assert rc_of({'loadstep': [good, good, good]}) != 0                     # more steps than the buffer holds
+    assert lib.dmk_load_from_yaml(str(tmp_path / 'missing.yaml').encode(), steps, C.c_int(2), C.byref(n), None, C.c_int(0)) != 0
+
+
+def _run_cpp_loop(outcomes, steps, n_steps, max_cut_back=3, max_increments=0):
+    """the C++ loop above a scripted solver (ctypes callbacks): -> (rc, records, calls, forwards, results)"""
+    import ctypes as C
+    lib = L.load()
+    outcomes = list(outcomes)
+    calls, results = [], []
+    forwards = [0]
+
+    def forward(user, cut_back, guess, dt, dt_old, t_remaining, st):
+        calls.append(dict(cut_back=bool(cut_back), guess=bool(guess), dt=dt, dt_prev=dt_old, t_remaining=t_remaining,
+                          kind=st.contents.deformation_type.decode()))
+        return 0
+
+    def point_forward(user):
+        forwards[0] += 1
+        return 0
+
+    def solve(user, out):
+        ok = outcomes.pop(0) if outcomes else True
+        out.contents.converged = int(ok); out.contents.stag_converged = 1; out.contents.terminally_ill = 0
+        out.contents.required_iterations = 3 if ok else 40
+        return 0
+
+    def result(user, rec):
+        results.append((rec.contents.inc, rec.contents.t))
+        return 0
+    ops = L.LoopOps(None, L.LOOP_FORWARD(forward), L.LOOP_POINT_FORWARD(point_forward), L.LOOP_SOLVE(solve), L.LOOP_RESULT(result))
+    recs = (L.IncrementRecord * 32)()
+    n = C.c_int()
+    rc = lib.dmk_loop_over_loadcase(None, steps, C.c_int(n_steps), C.c_int(max_cut_back), C.c_int(max_increments), C.byref(ops),
+                                    recs, C.c_int(32), C.byref(n))
+    return rc, [recs[i] for i in range(n.value)], calls, forwards[0], results
+
+
+@pytest.mark.parametrize('outcomes,max_increments', [([], None), ([True, False, True, True], 4), ([False, False, True, True, True, True], 2),
+                                                     ([True, True, False, False, False, True] + [True] * 12, None)])
+def test_cpp_loop_equals_python_loop_on_scripted_outcomes(outcomes, max_increments, tmp_path):
+    steps, n_steps, _ = _c_steps(LOAD, tmp_path)
+    s = _Scripted(outcomes)
+    seen = []
+    recs = mech.loop_over_loadcase(s, mech.parse_load(LOAD), max_increments=max_increments,
+                                   callback=lambda r, _: seen.append((r['inc'], r['t'])) if r['inc_in_step'] % r['f_out'] == 0 else None)
+    rc, crecs, calls, forwards, results = _run_cpp_loop(outcomes, steps, n_steps, max_increments=max_increments or 0)
+    assert rc == 0, L.load().dmk_last_error()
+    assert [(r.inc, r.step, r.inc_in_step, r.f_out, bool(r.converged), r.iterations) for r in crecs] == \
+           [(r['inc'], r['step'], r['inc_in_step'], r['f_out'], r['converged'], r['iterations']) for r in recs]
+    assert [r.t for r in crecs] == [r['t'] for r in recs]                    # the same floating-point bookkeeping
+    assert forwards == s.g.forwards and len(calls) == len(s.calls)
+    for a, b in zip(calls, s.calls):
+        assert (a['cut_back'], a['guess'], a['dt'], a['dt_prev'], a['t_remaining']) == (b['cut_back'], b['guess'], b['dt'], b['dt_prev'], b['t_remaining'])
+    assert results == seen
+
+
+def test_cpp_loop_gives_up_like_the_reference_and_checks_its_arguments(tmp_path):
+    lib = L.load()
+    steps, n_steps, _ = _c_steps(LOAD, tmp_path)
+    rc, recs, calls, forwards, results = _run_cpp_loop([False] * 8, steps, n_steps, max_cut_back=3, max_increments=1)
+    assert rc != 0 and b'no solution found for increment 1' in lib.dmk_last_error() and recs == [] and results == []
+    assert len(calls) == 4 and [c['dt'] for c in calls] == [1.0, 0.5, 0.25, 0.125]
+    # test_damask_grid.cpp:74-128: max_cut_back = 0 -> one failed solve ends the run
+    rc, _, calls, _, _ = _run_cpp_loop([False], steps, n_steps, max_cut_back=0)
+    assert rc != 0 and len(calls) == 1
+    # without a table of operations the loop drives the context's own solver: no context, no run
+    import ctypes as C
+    n = C.c_int()
+    assert lib.dmk_loop_over_loadcase(None, steps, C.c_int(n_steps), C.c_int(3), C.c_int(0), None, None, C.c_int(0), C.byref(n)) != 0
+    assert b'neither a context' in lib.dmk_last_error()

@@ -72,6 +72,12 @@ phase:
 list_at_key_indent:
 - 1
 - two
+matrix_in_block_style:
+- - 1.0e-3
+  - x
+- - -2
+  - - nested
+    - 4
 """
 
 
