@@ -324,6 +324,10 @@ int dmk_material_constituents_from_yaml(const char* material_yaml_path, double T
                                         int max_constituents, int* n_constituents_of_material, int* phase_of_material,
                                         double* O_of_material, double* v_of_material, int max_materials, int* n_materials);
 int dmk_numerics_from_yaml(const char* numerics_yaml_path, dmk_numerics* num, int* derivative, int* divergence_correction);
+/* the grid-level keys of Config::parse_numerics (config.cpp:379-384, 449-457): limits of the increment loop (N_cutback_max is
+ * dmk_loop_over_loadcase's max_cut_back) and the polarisation scheme's parameters (dmk_mech_init_polarisation) */
+typedef struct { int N_staggered_iter_max, N_cutback_max; double alpha, beta, eps_abs_curl, eps_rel_curl; } dmk_grid_numerics;
+int dmk_grid_numerics_from_yaml(const char* numerics_yaml_path, dmk_grid_numerics* out);
 void f_homogenization_fetch_tensor_pointers(double** homogenization_F0, double** homogenization_F,
                                             double** homogenization_P, double** homogenization_dPdF,
                                             void** terminally_ill);

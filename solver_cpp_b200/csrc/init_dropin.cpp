@@ -389,6 +389,13 @@ void default_numerics(dmk_numerics& n) {
 void read_numerics(const YamlNode& root, dmk_numerics& n, int* derivative, int* divcorr) {
   if (const YamlNode* solver = root.get("solver")) if (const YamlNode* grid = solver->get("grid")) {
     if (const YamlNode* m = grid->get("mechanical")) {
+      // a key the parser does not know must not be dropped silently (the Python host refuses it as well)
+      static const char* known[] = {"N_iter_min", "N_iter_max", "eps_abs_div(P)", "eps_rel_div(P)", "eps_abs_P", "eps_rel_P", "update_gamma"};
+      if (m->is_map()) for (const auto& kv : m->map) {
+        bool ok = false;
+        for (const char* k : known) ok = ok || kv.first == k;
+        if (!ok) bad("numerics: unknown key '" + kv.first + "' under solver/grid/mechanical");
+      }
       if (m->has("N_iter_min")) n.itmin = (int)m->get("N_iter_min")->as_int();
       if (m->has("N_iter_max")) n.itmax = (int)m->get("N_iter_max")->as_int();
       if (m->has("eps_abs_div(P)")) n.eps_abs_div = m->get("eps_abs_div(P)")->as_double();
@@ -536,6 +543,33 @@ extern "C" int dmk_material_from_yaml(const char* material_yaml_path, double T, 
   int rc = dmk_material_constituents_from_yaml(material_yaml_path, T, phases, max_phases, n_phases, 1, nc.data(), phase_of_material,
                                                O_of_material, v.data(), max_materials, n_materials);
   return rc;
+}
+
+// the grid-level keys of Config::parse_numerics (config.cpp:379-384, 449-457; defaults config.h:60-75): staggered-iteration and
+// cut-back limits of the increment loop, and the polarisation scheme's parameters
+extern "C" int dmk_grid_numerics_from_yaml(const char* numerics_yaml_path, dmk_grid_numerics* out) {
+  try {
+    if (!out) bad("dmk_grid_numerics_from_yaml: null argument");
+    out->N_staggered_iter_max = 10; out->N_cutback_max = 3;
+    out->alpha = 1.0; out->beta = 1.0; out->eps_abs_curl = 1.0e-10; out->eps_rel_curl = 5.0e-4;
+    if (!numerics_yaml_path || !*numerics_yaml_path) return DMK_OK;
+    auto root = yaml_parse_file(numerics_yaml_path);
+    const YamlNode* solver = root->get("solver");
+    const YamlNode* grid = solver ? solver->get("grid") : nullptr;
+    if (!grid) return DMK_OK;
+    if (grid->has("N_staggered_iter_max")) out->N_staggered_iter_max = (int)grid->get("N_staggered_iter_max")->as_int();
+    if (grid->has("N_cutback_max")) out->N_cutback_max = (int)grid->get("N_cutback_max")->as_int();
+    if (const YamlNode* f = grid->get("FFT")) {
+      if (f->has("alpha")) out->alpha = f->get("alpha")->as_double();
+      if (f->has("beta")) out->beta = f->get("beta")->as_double();
+      if (f->has("eps_abs_curl(F)")) out->eps_abs_curl = f->get("eps_abs_curl(F)")->as_double();
+      if (f->has("eps_rel_curl(F)")) out->eps_rel_curl = f->get("eps_rel_curl(F)")->as_double();
+    }
+    return DMK_OK;
+  } catch (const std::exception& e) {
+    dmk_set_error("%s", e.what());
+    return DMK_ERR_ARG;
+  }
 }
 
 extern "C" int dmk_numerics_from_yaml(const char* numerics_yaml_path, dmk_numerics* num, int* derivative, int* divergence_correction) {

@@ -80,6 +80,12 @@ class SolutionState(C.Structure):
                 ('terminally_ill', C.c_int)]
 
 
+class GridNumerics(C.Structure):
+    """dmk_grid_numerics: the grid-level keys of Config::parse_numerics (config.cpp:379-384, 449-457)"""
+    _fields_ = [('N_staggered_iter_max', C.c_int), ('N_cutback_max', C.c_int), ('alpha', C.c_double), ('beta', C.c_double),
+                ('eps_abs_curl', C.c_double), ('eps_rel_curl', C.c_double)]
+
+
 class LoadStep(C.Structure):
     """dmk_load_step (Config::LoadStep, config.h:74-96): values / masks / R row-major 3x3, mask 1 = 'x'"""
     _fields_ = [('deformation_type', C.c_char * 8), ('deformation_values', C.c_double * 9), ('deformation_mask', C.c_int * 9),

@@ -153,5 +153,19 @@ def test_cpp_numerics_equals_python_host(tmp_path):
         der, div = C.c_int(), C.c_int()
         rc = lib.dmk_numerics_from_yaml(path.encode() if path else None, C.byref(num), C.byref(der), C.byref(div))
         assert rc == 0, lib.dmk_last_error()
-        ref, rder, rdiv, _, _ = job.read_numerics(path)
+        ref, rder, rdiv, rcut, rpol = job.read_numerics(path)
         assert bytes(num) == bytes(ref) and (der.value, div.value) == (rder, rdiv)
+        gn = L.GridNumerics()
+        assert lib.dmk_grid_numerics_from_yaml(path.encode() if path else None, C.byref(gn)) == 0, lib.dmk_last_error()
+        assert gn.N_cutback_max == rcut == (5 if path else 3) and gn.N_staggered_iter_max == 10
+        assert dict(alpha=gn.alpha, beta=gn.beta, eps_abs_curl=gn.eps_abs_curl, eps_rel_curl=gn.eps_rel_curl) == rpol
+    # a key the parser does not know is refused by both sides (config.cpp:386-402 knows seven)
+    p.write_text(yaml.safe_dump({'solver': {'grid': {'mechanical': {'eps_div': 1e-2}}}}))
+    assert lib.dmk_numerics_from_yaml(str(p).encode(), C.byref(num), C.byref(der), C.byref(div)) != 0
+    assert b"unknown key 'eps_div'" in lib.dmk_last_error()
+    with pytest.raises(L.DmkError):
+        job.read_numerics(str(p))
+    p.write_text(yaml.safe_dump({'solver': {'grid': {'N_staggered_iter_max': 7, 'FFT': {'alpha': 1.5, 'beta': 0.5, 'eps_abs_curl(F)': 1e-8, 'eps_rel_curl(F)': 1e-3}}}}))
+    assert lib.dmk_grid_numerics_from_yaml(str(p).encode(), C.byref(gn)) == 0
+    assert (gn.N_staggered_iter_max, gn.N_cutback_max, gn.alpha, gn.beta, gn.eps_abs_curl, gn.eps_rel_curl) == (7, 3, 1.5, 0.5, 1e-8, 1e-3)
+    assert job.read_numerics(str(p))[4] == dict(alpha=1.5, beta=0.5, eps_abs_curl=1e-8, eps_rel_curl=1e-3)
