@@ -26,6 +26,15 @@ extern "C" {
 
 typedef struct dmk_ctx dmk_ctx;
 
+/* ---- return codes of every int-returning dmk_* entry point; dmk_last_error() holds the message of the last failure */
+#ifndef DMK_OK
+#define DMK_OK 0
+#define DMK_ERR_CUDA 1           /* a CUDA call failed, or no CUDA device (there is no CPU path) */
+#define DMK_ERR_ARG 2            /* bad argument, unreadable or malformed input file */
+#define DMK_ERR_UNSUPPORTED 3    /* valid input the device path does not offer (other laws / lattices, RGC, ...) */
+#define DMK_ERR_STATE 4          /* call out of order, failed collective, or no solution found for an increment */
+#endif
+
 /* ---- limits of the device constitutive kernels */
 #define DMK_MAX_SL 24
 #define DMK_MAX_TW 12

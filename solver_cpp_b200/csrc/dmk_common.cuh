@@ -4,11 +4,14 @@
 #include <cstdio>
 #include <cstdint>
 
+// return codes: the same values as include/dmk_grid.h publishes (guarded there, so that either order of inclusion works)
+#ifndef DMK_OK
 #define DMK_OK 0
 #define DMK_ERR_CUDA 1
 #define DMK_ERR_ARG 2
 #define DMK_ERR_UNSUPPORTED 3
 #define DMK_ERR_STATE 4
+#endif
 
 // record = the 9 tensor components of one grid point / k-point, component index c = i + 3*j
 // (Fortran order of the reference's F(3,3,x,y,z) arrays: /root/reference/src/grid/spectral.cpp:143)

@@ -112,3 +112,22 @@ def test_material_tables_match_oracle_phase_setup():
             assert np.allclose(x[sl], y[sl], rtol=1e-14, atol=1e-15 * max(np.abs(y[sl]).max(), 1e-300)), (name, f)
         for f in ('iso_xi_inf', 'iso_n', 'iso_a', 'dt_mu', 'dt_nu', 'dt_kB_T', 'dt_Gamma_sf', 'dt_omega', 'dt_D', 'dt_L_tw', 'dt_x_c'):
             assert np.isclose(getattr(a, f), getattr(b, f), rtol=1e-14, atol=0), (name, f)
+
+
+def test_native_driver_reaches_the_device_and_refuses_without_one(golden_dir):
+    """tests/abi/native_driver.cpp (the reference's main.cpp reduced to calls into the library, all C++): on a box without a GPU
+    it must read the geometry through the f_VTI_* symbols, hand the cells to f_discretization_init, parse material.yaml -- and
+    then fail loudly at the context: there is no CPU path to fall back to."""
+    import subprocess
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip('GPU present')
+    import __graft_entry__ as ge
+    exe = ge.build_native_driver()
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 2 and 'usage' in r.stderr
+    r = subprocess.run([exe, os.path.join(golden_dir, 'g6_unit_test_geometry.vti'), os.path.join(golden_dir, 'material_20grains_Al.yaml'),
+                        os.path.join(golden_dir, 'load_tensionX.yaml')], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 1 and 'no CUDA device' in r.stderr and 'NATIVE_DRIVER_OK' not in r.stdout
+    r = subprocess.run([exe, os.path.join(golden_dir, 'material_20grains_Al.yaml'), 'x', 'y'], capture_output=True, text=True)
+    assert r.returncode == 1 and 'f_VTI_readCellsSizeOrigin' in r.stderr         # not a geometry file

@@ -85,3 +85,31 @@ def test_cpp_consumer_matches_python_host(tmp_path, phase):
         assert abs(e['level2_r_sq'][0] - float((rh ** 2).sum())) <= 1e-11 * float((rh ** 2).sum())
         Fh = Fh - rh
     assert int(got['math_invert_err'][0]) == 0 and abs(got['math_invert_00'][0] - np.linalg.inv(np.array([[4., 1, 0], [1, 3, 1], [0, 1, 2]]))[0, 0]) < 1e-15
+
+
+@pytest.mark.skipif(os.environ.get('DMK_TEST_NATIVE_DRIVER') != '1',
+                    reason='tests/abi/native_driver.cpp was written after the GPU budget of round 2 was spent: compiled, linked and run up to '
+                           'the device on CPU (tests/test_abi_cpu.py), not yet run on a GPU; set DMK_TEST_NATIVE_DRIVER=1 to run it')
+def test_native_cpp_driver_solves_the_reference_deck_like_the_python_host(golden_dir, tmp_path):
+    """the whole job in C++ (geometry -> init trio -> dmk_mech_init -> dmk_loop_over_loadcase) on the reference's own 16^3 deck
+    against the Python host's loop on the same input: iteration counts equal, P_av and F_aim to 1e-12"""
+    import __graft_entry__ as ge
+    exe = ge.build_native_driver()
+    from solver_cpp_b200 import job
+    deck = [os.path.join(golden_dir, f) for f in ('g6_unit_test_geometry.vti', 'material_20grains_Al.yaml', 'load_tensionX.yaml')]
+    load = yaml.safe_load(open(deck[2]))
+    load['loadstep'][0]['f_out'] = 1
+    lp = tmp_path / 'load.yaml'
+    lp.write_text(yaml.safe_dump(load, default_flow_style=None))
+    r = subprocess.run([exe, deck[0], deck[1], str(lp), '', '3'], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and 'NATIVE_DRIVER_OK 3 increments' in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+    rows = [[float(v) for v in l.split()[1:]] for l in r.stdout.splitlines() if l.startswith('increment ')]
+    solver, steps = job.load_job(deck[0], deck[1], str(lp))
+    solver.init()
+    from solver_cpp_b200 import mech
+    recs = mech.loop_over_loadcase(solver, steps, max_increments=3)
+    assert len(rows) == len(recs) == 3
+    for row, rec in zip(rows, recs):
+        assert (int(row[0]), int(row[2])) == (rec['inc'], rec['iterations']) and row[1] == rec['t']
+        assert _rel(np.array(row[3:12]).reshape(3, 3), rec['P_av']) < 1e-12
+        assert _rel(np.array(row[12:21]).reshape(3, 3), rec['F_aim']) < 1e-12
