@@ -131,3 +131,16 @@ def test_native_driver_reaches_the_device_and_refuses_without_one(golden_dir):
     assert r.returncode == 1 and 'no CUDA device' in r.stderr and 'NATIVE_DRIVER_OK' not in r.stdout
     r = subprocess.run([exe, os.path.join(golden_dir, 'material_20grains_Al.yaml'), 'x', 'y'], capture_output=True, text=True)
     assert r.returncode == 1 and 'f_VTI_readCellsSizeOrigin' in r.stderr         # not a geometry file
+
+
+def test_public_header_is_plain_c(tmp_path):
+    """the boundary is a C ABI: include/dmk_grid.h must compile as C99 (what a cgo / Fortran-bind(C) / ctypes binding generator
+    would read), with the return codes and the load-case types it declares"""
+    import subprocess
+    src = tmp_path / 'c_abi.c'
+    src.write_text('#include "dmk_grid.h"\\n'
+                   'int main(void) { dmk_load_step s; dmk_loop_ops o; dmk_grid_numerics g; dmk_numerics n; dmk_phase p;\\n'
+                   '  (void)s; (void)o; (void)g; (void)n; (void)p; return DMK_OK + 0 * (DMK_ERR_CUDA + DMK_ERR_ARG + DMK_ERR_UNSUPPORTED + DMK_ERR_STATE); }\\n')
+    r = subprocess.run(['gcc', '-std=c99', '-Wall', '-Wextra', '-pedantic', '-Werror', '-I', os.path.join(ROOT, 'include'), '-fsyntax-only', str(src)],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
