@@ -138,9 +138,9 @@ def test_public_header_is_plain_c(tmp_path):
     would read), with the return codes and the load-case types it declares"""
     import subprocess
     src = tmp_path / 'c_abi.c'
-    src.write_text('#include "dmk_grid.h"\\n'
-                   'int main(void) { dmk_load_step s; dmk_loop_ops o; dmk_grid_numerics g; dmk_numerics n; dmk_phase p;\\n'
-                   '  (void)s; (void)o; (void)g; (void)n; (void)p; return DMK_OK + 0 * (DMK_ERR_CUDA + DMK_ERR_ARG + DMK_ERR_UNSUPPORTED + DMK_ERR_STATE); }\\n')
+    src.write_text('#include "dmk_grid.h"\n'
+                   'int main(void) { dmk_load_step s; dmk_loop_ops o; dmk_grid_numerics g; dmk_numerics n; dmk_phase p;\n'
+                   '  (void)s; (void)o; (void)g; (void)n; (void)p; return DMK_OK + 0 * (DMK_ERR_CUDA + DMK_ERR_ARG + DMK_ERR_UNSUPPORTED + DMK_ERR_STATE); }\n')
     r = subprocess.run(['gcc', '-std=c99', '-Wall', '-Wextra', '-pedantic', '-Werror', '-I', os.path.join(ROOT, 'include'), '-fsyntax-only', str(src)],
                        capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
