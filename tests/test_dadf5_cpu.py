@@ -317,3 +317,35 @@ def test_streaming_writer_produces_the_same_file_as_the_in_memory_one(tmp_path):
         ws.dataset('/late', np.zeros(3))
     with pytest.raises(ValueError):
         H5Writer(str(tmp_path / 'x.hdf5')).tobytes()
+
+
+def test_g7_multi_constituent_mappings_equal_a_file_damask_wrote(tmp_path):
+    """Golden set G7: real DAMASK's /cell_to/phase [24, 8] and /cell_to/homogenization of a job with 8 constituents per cell
+    (python/tests/resources/Result/4grains2x4x3_compressionY.hdf5, extracted by tests/golden/make_golden_g7.py).  The writer,
+    given the same geometry and the constituents' phases, must produce the same (label, entry) for every constituent of every
+    cell -- the entry counters of material.f90:177-203 -- and the reader must hand the constituents back as an axis."""
+    from solver_cpp_b200 import vti
+    from solver_cpp_b200.hdf5_min import H5File
+    g7 = np.load(os.path.join(GOLDEN, 'g7_multi_constituent_mapping.npz'))
+    geo = vti.read_vti(os.path.join(GOLDEN, 'damask_written_4grains2x4x3.vti'))
+    assert 'DAMASK_grid' in str(g7['creator'])
+    material = {'homogenization': {'RGC': {'N_constituents': 8, 'mechanical': {'type': 'RGC'}}},
+                'phase': {p: {'lattice': 'cF'} for p in ('A', 'B', 'C')},
+                'material': [{'homogenization': str(h), 'constituents': [{'phase': str(p), 'v': float(v), 'O': [1.0, 0.0, 0.0, 0.0]} for p, v in zip(ps, vs)]}
+                             for h, ps, vs in zip(g7['material_homogenization'], g7['material_phase'], g7['material_v'])]}
+    w = dadf5.ResultWriter(geo['cells'], geo['size'], material, geo['material'], origin=geo['origin'])
+    n = 24
+    rng = np.random.default_rng(0)
+    F = rng.standard_normal((n, 8, 3, 3))
+    w.add_increment(10, 5.0, {'F': F})
+    path = str(tmp_path / 'rgc_layout.hdf5')
+    w.save(path)
+    f = H5File(path)
+    ph, ho = f.read('/cell_to/phase'), f.read('/cell_to/homogenization')
+    assert ph.shape == (24, 8)
+    assert np.array_equal(ph['label'].astype('S8'), g7['cell_to_phase_label']) and np.array_equal(ph['entry'], g7['cell_to_phase_entry'])
+    assert np.array_equal(ho['label'].astype('S8'), g7['cell_to_homogenization_label']) and np.array_equal(ho['entry'], g7['cell_to_homogenization_entry'])
+    for p in ('A', 'B', 'C'):
+        assert f.read('/increment_10/phase/%s/mechanical/F' % p).shape[0] == int(g7['rows_' + p])
+    r = dadf5.ResultReader(path)
+    assert r.n_const == 8 and np.array_equal(r.place('F', 10), F)
