@@ -349,3 +349,39 @@ def test_g7_multi_constituent_mappings_equal_a_file_damask_wrote(tmp_path):
         assert f.read('/increment_10/phase/%s/mechanical/F' % p).shape[0] == int(g7['rows_' + p])
     r = dadf5.ResultReader(path)
     assert r.n_const == 8 and np.array_equal(r.place('F', 10), F)
+
+
+REF_RESULT = '/root/reference/python/tests/resources/Result'
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(REF_RESULT, '4grains2x4x3_compressionY.hdf5')),
+                    reason='needs the reference tree (present in the build container only; 1 MB result file not copied into the repo)')
+def test_reader_places_constituents_like_damask_own_python_library():
+    """The reference stores what its own damask.Result.place returns for the 8-constituent result file
+    4grains2x4x3_compressionY.hdf5 (python/tests/test_Result.py:530-554, pickles under resources/Result/place/: constituent 1 of
+    every cell, masked where a phase lacks the dataset).  ResultReader.place(...)[:, 1] on the same file must be that array:
+    exactly at increment 0 -- where F_e of the other seven constituents differs by O(1), so the placement is unambiguous -- and
+    within the drift of the stored pickles later on (they stem from a re-run of the job: 5e-15 at increment 2, 2e-9 at 10)."""
+    import bz2
+    import pickle
+    r = dadf5.ResultReader(os.path.join(REF_RESULT, '4grains2x4x3_compressionY.hdf5'))
+    assert r.n_const == 8 and r.n_cells == 24 and r.increments == [0, 2, 4, 6, 8, 10]
+    with bz2.BZ2File(os.path.join(REF_RESULT, 'place', 'test_place[0].pbz2')) as f:
+        ref = pickle.load(f)
+    tol = {0: 0.0, 2: 1e-13, 4: 1e-11, 6: 1e-10, 8: 1e-9, 10: 1e-8}
+    for inc in r.increments:
+        for name in ('F', 'F_e', 'F_p', 'L_p'):
+            a = ref['increment_%d' % inc]['phase'][name]
+            mask = np.ma.getmaskarray(a)
+            ours = r.place(name, inc)
+            assert ours.shape == (24, 8, 3, 3)
+            assert np.isnan(ours[:, 1][mask]).all() and not np.isnan(ours[:, 1][~mask]).any()      # phase C carries F only
+            assert np.abs(ours[:, 1][~mask] - a.data[~mask]).max() <= tol[inc], (inc, name)
+            if name == 'F_e' and inc == 0:
+                others = [np.nanmax(np.abs(ours[:, k] - a.data)) for k in (0, 3, 4, 6, 7)]
+                assert min(others) > 1.0                                                           # any other constituent is O(1) away
+    with bz2.BZ2File(os.path.join(REF_RESULT, 'place', 'test_place[7].pbz2')) as f:
+        ref = pickle.load(f)
+    for inc in r.increments:
+        for name in ('u_p', 'u_n'):
+            assert np.abs(r.geometry(name, inc) - ref['increment_%d' % inc]['geometry'][name]).max() <= 1e-10
