@@ -87,9 +87,9 @@ def test_cpp_consumer_matches_python_host(tmp_path, phase):
     assert int(got['math_invert_err'][0]) == 0 and abs(got['math_invert_00'][0] - np.linalg.inv(np.array([[4., 1, 0], [1, 3, 1], [0, 1, 2]]))[0, 0]) < 1e-15
 
 
-@pytest.mark.skipif(os.environ.get('DMK_TEST_NATIVE_DRIVER') != '1',
+@pytest.mark.skipif(os.environ.get('DMK_TEST_UNVERIFIED') != '1',
                     reason='tests/abi/native_driver.cpp was written after the GPU budget of round 2 was spent: compiled, linked and run up to '
-                           'the device on CPU (tests/test_abi_cpu.py), not yet run on a GPU; set DMK_TEST_NATIVE_DRIVER=1 to run it')
+                           'the device on CPU (tests/test_abi_cpu.py), not yet run on a GPU; set DMK_TEST_UNVERIFIED=1 to run it')
 def test_native_cpp_driver_solves_the_reference_deck_like_the_python_host(golden_dir, tmp_path):
     """the whole job in C++ (geometry -> init trio -> dmk_mech_init -> dmk_loop_over_loadcase) on the reference's own 16^3 deck
     against the Python host's loop on the same input: iteration counts equal, P_av and F_aim to 1e-12"""

@@ -304,6 +304,66 @@ def test_fft_round_trip_of_the_reference_unit_test():
     assert np.abs(back - field).max() <= 1e-12
 
 
+def test_forward_boundary_condition_types():
+    """MechSolverBasic::forward (mech_solver_basic.cpp:163-220) for the deformation types F / dot_F / L and the stress types
+    P / dot_P.  Two lines of the C++ port are not followed (upstream DAMASK's grid_mechanical_spectral_basic_forward is): its "L"
+    branch repeats the "F" formula (:188-189; upstream: L . F_aim_lastInc), and its P_aim update selects the components the mask
+    marks 'x' (:205-209; upstream: the stress-controlled ones).  Properties pinned here: an F target is reached exactly at the end
+    of its load step however the step is discretised, L gives the rate L . F_aim, P ramps linearly to its target, dot_P integrates."""
+    from oracle.solver import MechSolverBasicOracle, parse_load as oparse
+    from solver_cpp_b200 import workloads as W
+    cells = (2, 1, 1)
+    material, material_at, _ = W.polycrystal(cells, 2, 'Al_pheno', 0)
+
+    def fresh():
+        o = MechSolverBasicOracle(cells, (2e-5, 1e-5, 1e-5), material, material_at)
+        o.init()
+        return o
+
+    def step_of(mech):
+        return oparse({'loadstep': [{'boundary_conditions': {'mechanical': mech}, 'discretization': {'t': 4.0, 'N': 4}}]})[0]
+    X = 'x'
+    # F: target reached at the end of the step, for equal and for unequal time steps
+    target = [[1.02, 0.01, 0], [0, X, 0], [0, 0, X]]
+    st = step_of({'F': target, 'P': [[X, X, X], [X, 0, X], [X, X, 0]]})
+    for dts in ([1.0, 1.0, 1.0, 1.0], [0.5, 1.5, 0.25, 1.75]):
+        o, t = fresh(), 0.0
+        for dt in dts:
+            o.forward(False, False, dt, 1.0, 4.0 - t, st['deformation'], st['stress'], st['R'])
+            t += dt
+        assert abs(o.F_aim[0, 0] - 1.02) < 1e-15 and abs(o.F_aim[0, 1] - 0.01) < 1e-16 and o.F_aim[1, 1] == 1.0
+        assert np.abs(o.F.mean(axis=(0, 1, 2)) - o.F_aim).max() < 1e-15        # the field follows its aim
+    # L: rate = L . F_aim_lastInc on the controlled components
+    L = np.array([[1e-3, 2e-3, 0], [0, 0, 0], [0, 0, 0]])
+    st = step_of({'L': [[1e-3, 2e-3, 0], [0, X, 0], [0, 0, X]], 'P': [[X, X, X], [X, 0, X], [X, X, 0]]})
+    o = fresh()
+    o.F_aim = np.array([[1.1, 0.0, 0.0], [0.0, 0.9, 0.0], [0.0, 0.0, 1.0]])
+    o.forward(False, False, 0.5, 1.0, 4.0, st['deformation'], st['stress'], st['R'])
+    expect = np.where(st['deformation'].mask, 0.0, L @ np.diag([1.1, 0.9, 1.0]))
+    assert np.array_equal(o.F_aim_dot, expect) and np.abs(o.F_aim - (np.diag([1.1, 0.9, 1.0]) + 0.5 * expect)).max() < 1e-16
+    assert o.F_aim_dot[0, 1] == 2e-3 * 0.9                                      # not the "F" formula of the C++ port
+    # P ramps to its target over the step; dot_P integrates; components marked x stay untouched
+    st = step_of({'dot_F': [[1e-3, 0, 0], [0, X, 0], [0, 0, X]], 'P': [[X, X, X], [X, 4.0e6, X], [X, X, -2.0e6]]})
+    o, t = fresh(), 0.0
+    o.P_aim[0, 0] = 7.0
+    for dt in (0.5, 1.5, 0.25, 1.75):
+        o.forward(False, False, dt, 1.0, 4.0 - t, st['deformation'], st['stress'], st['R'])
+        t += dt
+        assert abs(o.P_aim[1, 1] - 4.0e6 * t / 4.0) < 1e-8 and abs(o.P_aim[2, 2] + 2.0e6 * t / 4.0) < 1e-8 and o.P_aim[0, 0] == 7.0
+    st = step_of({'dot_F': [[1e-3, 0, 0], [0, X, 0], [0, 0, X]], 'dot_P': [[X, X, X], [X, 1.0e6, X], [X, X, 0]]})
+    o = fresh()
+    for k in range(3):
+        o.forward(False, False, 0.5, 1.0, 4.0 - 0.5 * k, st['deformation'], st['stress'], st['R'])
+    assert o.P_aim[1, 1] == 1.5e6 and o.P_aim[2, 2] == 0.0
+    # a cut-back repeats the step from the same F_aim_lastInc with the smaller dt
+    st = step_of({'dot_F': [[1e-3, 0, 0], [0, X, 0], [0, 0, X]], 'P': [[X, X, X], [X, 0, X], [X, X, 0]]})
+    o = fresh()
+    o.forward(False, False, 1.0, 1.0, 4.0, st['deformation'], st['stress'], st['R'])
+    assert o.F_aim[0, 0] == 1.001
+    o.forward(True, False, 0.5, 1.0, 4.0, st['deformation'], st['stress'], st['R'])
+    assert o.F_aim[0, 0] == 1.0005 and np.array_equal(o.F_aim_last_inc, np.eye(3))
+
+
 def test_g4_real_damask_run_reproduced_within_solver_tolerance(golden_dir):
     """Golden set G4: a real DAMASK_grid (3.0.0-alpha7) result file shipped with the reference
     (python/tests/resources/Result/6grains6x7x8_single_phase_tensionY.hdf5; non-cubic 6x7x8 grid, mixed boundary
