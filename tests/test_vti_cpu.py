@@ -115,3 +115,35 @@ def test_g6_geometry_text_of_the_reference_unit_test(golden_dir):
     assert np.array_equal(d['material'].ravel() + 1, data)
     # a Voronoi tessellation: every grain is a sizeable share of the 4096 cells
     assert np.bincount(d['material'].ravel()).min() > 40
+
+
+def test_every_damask_written_geometry_of_the_reference_tree_reads_alike():
+    """all .vti files under the reference tree (34: the fixtures of upstream DAMASK's own Grid / Result tests, written by its
+    tooling with and without compression, several data types, non-cubic grids): the Python reader and the library's f_VTI_*
+    symbols must agree on cells, size, origin and every material ID, and the IDs' range must be the RangeMin / RangeMax the file
+    declares.  Reads the reference tree, so it runs in the build container only."""
+    import ctypes as C
+    import glob
+    import re
+    import pytest
+    files = sorted(glob.glob('/root/reference/**/*.vti', recursive=True))
+    if not files:
+        pytest.skip('needs the reference tree')
+    assert len(files) >= 30
+    lib = C.CDLL(os.path.join(HERE, '..', 'solver_cpp_b200', 'libdamask_grid_b200.so'))
+    lib.dmk_last_error.restype = C.c_char_p
+    for f in files:
+        content = open(f, 'rb').read()
+        d = vti.read_vti(f)
+        cells = (C.c_int * 3)(); size = (C.c_double * 3)(); origin = (C.c_double * 3)()
+        lib.f_VTI_readCellsSizeOrigin(content, C.c_int(len(content)), cells, size, origin)
+        assert tuple(cells) == tuple(d['cells']), (f, lib.dmk_last_error())
+        assert np.allclose(list(size), d['size'], rtol=1e-15) and np.allclose(list(origin), d['origin'], rtol=1e-15, atol=0), f
+        n = int(np.prod(d['cells']))
+        data = np.zeros(n, dtype=np.int32)
+        nn = C.c_int(n)
+        lib.f_VTI_readDataset_int(content, C.c_int(len(content)), b'material', C.c_int(8), data.ctypes.data_as(C.c_void_p), C.byref(nn))
+        assert nn.value == n and np.array_equal(data, d['material'].ravel() + 1), (f, lib.dmk_last_error())
+        m = re.search(rb'Name="material"[^>]*RangeMin="([^"]+)"[^>]*RangeMax="([^"]+)"', content)
+        if m:
+            assert (float(m.group(1)), float(m.group(2))) == (d['material'].min(), d['material'].max()), f
