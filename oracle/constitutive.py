@@ -206,7 +206,7 @@ def make_phase(name, phase_cfg, T=T_ROOM):
         _set(ph.dt_b_sl, b_sl); _set(ph.dt_Q_sl, _expand(pl['Q_s'], N_sl)); _set(ph.dt_i_sl, _expand(pl['i_sl'], N_sl))
         _set(ph.dt_tau_0, _expand(pl['tau_Peierls'], N_sl)); _set(ph.dt_p, _expand(pl['p_sl'], N_sl)); _set(ph.dt_q, _expand(pl['q_sl'], N_sl))
         _set(ph.tu_h, _expand(pl['h'], N_sl)); _set(ph.tu_w, _expand(pl['w'], N_sl)); _set(ph.tu_omega, _expand(pl['omega'], N_sl))
-        _set(ph.dt_B, _expand(pl['B'], N_sl)); _set(ph.dt_d_caron, b_sl * float(pl['D_a'])); _set(ph.tu_f_at, b_sl ** 3 * float(pl['f_at']))
+        _set(ph.dt_B, _expand(pl['B'], N_sl)); _set(ph.dt_d_caron, b_sl * float(pl['D_a'])); _set(ph.tu_f_at, b_sl * b_sl * b_sl * float(pl['f_at']))    # b_sl**3 as gfortran evaluates it: two products, not pow()
         _set(ph.h_sl_sl, crystal.interaction_slip_slip(N_sl, pl['h_sl-sl'], lattice))
         _set(ph.dt_forest, crystal.forest_projection(N_sl, lattice, f_edge))
         state_init = np.concatenate([_expand(pl['rho_mob_0'], N_sl), _expand(pl['rho_dip_0'], N_sl), np.zeros(ns)])

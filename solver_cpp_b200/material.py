@@ -294,7 +294,7 @@ def make_phase(cfg, T=T_ROOM):
         _set(ph.dt_tau_0, _expand(pl['tau_Peierls'], N_sl)); _set(ph.dt_p, _expand(pl['p_sl'], N_sl))
         _set(ph.dt_q, _expand(pl['q_sl'], N_sl)); _set(ph.dt_B, _expand(pl['B'], N_sl))
         _set(ph.tu_h, _expand(pl['h'], N_sl)); _set(ph.tu_w, _expand(pl['w'], N_sl)); _set(ph.tu_omega, _expand(pl['omega'], N_sl))
-        _set(ph.dt_d_caron, b_sl * float(pl['D_a'])); _set(ph.tu_f_at, b_sl ** 3 * float(pl['f_at']))
+        _set(ph.dt_d_caron, b_sl * float(pl['D_a'])); _set(ph.tu_f_at, b_sl * b_sl * b_sl * float(pl['f_at']))    # b_sl**3 as gfortran evaluates it: two products, not pow()
         _set(ph.h_sl_sl, interaction('sl-sl', lattice, N_sl, N_sl, pl['h_sl-sl']))
         _set(ph.dt_forest, forest_projection(lattice, N_sl, f_edge))
         if ph.tu_D_0 < 0.0 or ph.dt_Q_cl <= 0.0 or np.any(rho_mob_0 < 0.0) or np.any(rho_dip_0 < 0.0) or np.any(b_sl <= 0.0) \

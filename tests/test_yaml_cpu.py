@@ -107,7 +107,7 @@ def test_cpp_material_setup_equals_python_host(tmp_path, golden_dir):
     from solver_cpp_b200 import lib as L, material as M, workloads as W
     lib = L.load()
     decks = []
-    for phase in ('Al_pheno', 'Cu_pheno', 'Al_iso', 'Al_elastic', 'TWIP'):
+    for phase in ('Al_pheno', 'Cu_pheno', 'Al_iso', 'Al_elastic', 'TWIP', 'W_tungsten', 'Steel_kine'):
         material, _, _ = W.polycrystal((4, 4, 4), 5, phase, 1)
         p = tmp_path / ('material_%s.yaml' % phase)
         p.write_text(yaml.safe_dump(material))
@@ -116,7 +116,7 @@ def test_cpp_material_setup_equals_python_host(tmp_path, golden_dir):
         f = os.path.join(golden_dir, name)
         if os.path.exists(f):
             decks.append((f, yaml.safe_load(open(f))))
-    assert len(decks) >= 7
+    assert len(decks) >= 9
     for path, material in decks:
         n_mat = len(material['material'])
         phases = (L.Phase * L.MAX_PHASES)()
@@ -169,3 +169,57 @@ def test_cpp_numerics_equals_python_host(tmp_path):
     assert lib.dmk_grid_numerics_from_yaml(str(p).encode(), C.byref(gn)) == 0
     assert (gn.N_staggered_iter_max, gn.N_cutback_max, gn.alpha, gn.beta, gn.eps_abs_curl, gn.eps_rel_curl) == (7, 3, 1.5, 0.5, 1e-8, 1e-3)
     assert job.read_numerics(str(p))[4] == dict(alpha=1.5, beta=0.5, eps_abs_curl=1e-8, eps_rel_curl=1e-3)
+
+
+def test_example_phase_configs_of_the_reference_through_both_readers(tmp_path):
+    """every plastic parameter set the reference ships (examples/config/phase/mechanical/plastic/*.yaml, 18 files) combined with a
+    Hooke set of its material: the Python host and the library's C++ reader must either both build the phase -- byte-identical
+    tables -- or both refuse it, for the same reason (lattices hP / tI, the nonlocal law, transformation systems, shear banding
+    without slip, cI slip families whose interaction types are not offered).  Reads the reference tree: build container only."""
+    import glob
+    from solver_cpp_b200 import lib as L, material as M
+    base = '/root/reference/examples/config/phase/mechanical/'
+    files = sorted(glob.glob(base + 'plastic/*.yaml'))
+    if not files:
+        pytest.skip('needs the reference tree')
+    assert len(files) == 18
+    elastic = {'AA6022': 'Al', 'phenopowerlaw_Al': 'Al', 'nonlocal_Al': 'Al', 'Au': 'Au', 'phenopowerlaw_Cu': 'Cu', 'Pt': 'Pt', 'DP-steel': 'Fe',
+               'martensite': 'SAE1050-martensite', 'Mg': 'Mg', 'Ti': 'Ti', 'Sn': 'Sn-beta', 'dislotungsten_W': 'W', '317L': 'AISI304',
+               'IF-steel': 'Fe', 'TWIP': 'TWIP-steel', 'Brass': 'Cu', 'Ni': 'Ni', 'free-surface': 'Al'}
+    lattice = {'DP-steel': 'cI', 'martensite': 'cI', 'Mg': 'hP', 'Ti': 'hP', 'Sn': 'tI', 'dislotungsten_W': 'cI', 'IF-steel': 'cI'}
+    lib = L.load()
+    built, refused = [], {}
+    for f in files:
+        name = os.path.basename(f)
+        key = [k for k in elastic if k in name]
+        assert len(key) == 1, name
+        lat = ([v for k, v in lattice.items() if k in name] or ['cF'])[0]
+        phase = {'lattice': lat, 'mechanical': {'elastic': yaml.safe_load(open(base + 'elastic/Hooke_%s.yaml' % elastic[key[0]])),
+                                                'plastic': yaml.safe_load(open(f))}}
+        if lat in ('hP', 'tI'):
+            phase['c/a'] = 1.6
+        material = {'homogenization': {'SX': {'N_constituents': 1, 'mechanical': {'type': 'pass'}}}, 'phase': {'X': phase},
+                    'material': [{'homogenization': 'SX', 'constituents': [{'phase': 'X', 'v': 1.0, 'O': [1.0, 0.0, 0.0, 0.0]}]}]}
+        path = tmp_path / 'material.yaml'
+        path.write_text(yaml.safe_dump(material))
+        try:
+            ref, why = M.Material(material, np.arange(1)), None
+        except L.DmkError as e:
+            ref, why = None, str(e)
+        phases = (L.Phase * L.MAX_PHASES)()
+        nph, nm = C.c_int(), C.c_int()
+        ph_of, O = np.zeros(1, dtype=np.int32), np.zeros((1, 9))
+        rc = lib.dmk_material_from_yaml(str(path).encode(), C.c_double(M.T_ROOM), phases, C.c_int(L.MAX_PHASES), C.byref(nph),
+                                        ph_of.ctypes.data_as(C.c_void_p), O.ctypes.data_as(C.c_void_p), C.c_int(1), C.byref(nm))
+        if ref is None:
+            assert rc != 0, name
+            cpp = lib.dmk_last_error().decode()
+            assert why.split(' (')[0][-40:] in cpp, (name, why, cpp)            # the same reason
+            refused[name] = why
+        else:
+            assert rc == 0, (name, lib.dmk_last_error())
+            assert bytes(phases[0]) == bytes(ref.phases[0]), name
+            built.append(name)
+    assert built == ['dislotungsten_W.yaml', 'isotropic_free-surface.yaml', 'kinehardening_317L.yaml', 'phenopowerlaw_AA6022-T4.yaml',
+                     'phenopowerlaw_Al.yaml', 'phenopowerlaw_Au.yaml', 'phenopowerlaw_Cu.yaml', 'phenopowerlaw_Pt-5%Cu.yaml']
+    assert 'N_tr' in refused['dislotwin_TWIP-TRIP.yaml'] and 'nonlocal' in refused['nonlocal_Ni.yaml'] and 'hP' in refused['phenopowerlaw_Mg.yaml']
