@@ -223,3 +223,34 @@ def test_example_phase_configs_of_the_reference_through_both_readers(tmp_path):
     assert built == ['dislotungsten_W.yaml', 'isotropic_free-surface.yaml', 'kinehardening_317L.yaml', 'phenopowerlaw_AA6022-T4.yaml',
                      'phenopowerlaw_Al.yaml', 'phenopowerlaw_Au.yaml', 'phenopowerlaw_Cu.yaml', 'phenopowerlaw_Pt-5%Cu.yaml']
     assert 'N_tr' in refused['dislotwin_TWIP-TRIP.yaml'] and 'nonlocal' in refused['nonlocal_Ni.yaml'] and 'hP' in refused['phenopowerlaw_Mg.yaml']
+
+
+def test_example_elastic_configs_of_the_reference_through_both_readers(tmp_path):
+    """every Hooke parameter set the reference ships (examples/config/phase/mechanical/elastic/*.yaml, 19 files, most with
+    temperature polynomials C_ij,T / C_ij,T^2) evaluated at room temperature and at 500 K: the stiffness the C++ reader builds
+    equals the Python host's bit for bit (phase_mechanical_elastic.f90:74-104, polynomials.f90:65-110).  Build container only."""
+    import glob
+    from solver_cpp_b200 import lib as L, material as M
+    files = sorted(glob.glob('/root/reference/examples/config/phase/mechanical/elastic/*.yaml'))
+    if not files:
+        pytest.skip('needs the reference tree')
+    assert len(files) == 19
+    lib = L.load()
+    differs = 0
+    for f in files:
+        for T in (M.T_ROOM, 500.0):
+            material = {'homogenization': {'SX': {'N_constituents': 1, 'mechanical': {'type': 'pass'}}},
+                        'phase': {'X': {'lattice': 'cF', 'mechanical': {'elastic': yaml.safe_load(open(f))}}},
+                        'material': [{'homogenization': 'SX', 'constituents': [{'phase': 'X', 'v': 1.0, 'O': [1.0, 0.0, 0.0, 0.0]}]}]}
+            path = tmp_path / 'material.yaml'
+            path.write_text(yaml.safe_dump(material))
+            ref = M.Material(material, np.arange(1), T=T)
+            phases = (L.Phase * L.MAX_PHASES)()
+            nph, nm = C.c_int(), C.c_int()
+            ph_of, O = np.zeros(1, dtype=np.int32), np.zeros((1, 9))
+            rc = lib.dmk_material_from_yaml(str(path).encode(), C.c_double(T), phases, C.c_int(L.MAX_PHASES), C.byref(nph),
+                                            ph_of.ctypes.data_as(C.c_void_p), O.ctypes.data_as(C.c_void_p), C.c_int(1), C.byref(nm))
+            assert rc == 0, (f, lib.dmk_last_error())
+            assert bytes(phases[0]) == bytes(ref.phases[0]), (f, T)
+            differs += int(T != M.T_ROOM and bytes(ref.phases[0]) != bytes(M.Material(material, np.arange(1)).phases[0]))
+    assert differs >= 10                       # the polynomials are exercised: most sets change with temperature
