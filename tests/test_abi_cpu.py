@@ -144,3 +144,46 @@ def test_public_header_is_plain_c(tmp_path):
     r = subprocess.run(['gcc', '-std=c99', '-Wall', '-Wextra', '-pedantic', '-Werror', '-I', os.path.join(ROOT, 'include'), '-fsyntax-only', str(src)],
                        capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
+
+
+def _phase_tables_agree(phase, tol=5e-16):
+    """product tables (solver_cpp_b200.material.make_phase: crystallography from the library's C++) against the oracle's
+    (oracle.constitutive.make_phase: crystallography in Python), field by field over the leading block both layouts hold"""
+    from solver_cpp_b200 import lib as L, material as M
+    from oracle import constitutive as OC
+    a, b = M.make_phase(phase, M.T_ROOM), OC.make_phase('X', phase, OC.T_ROOM)
+    oracle_fields = {f for f, _ in OC.Phase._fields_}
+
+    def arr(v):
+        return np.ctypeslib.as_array(v).astype(float) if hasattr(v, '_length_') else np.asarray(v, float)
+    compared = 0
+    for f, _ in L.Phase._fields_:
+        assert f in oracle_fields, f
+        x, y = arr(getattr(a, f)), arr(getattr(b, f))
+        sl = tuple(slice(0, min(p, q)) for p, q in zip(x.shape, y.shape))
+        x, y = x[sl], y[sl]
+        scale = np.abs(y).max() if y.size else 0.0
+        assert np.abs(x - y).max() <= tol * max(scale, 1e-300) if y.size else True, (f, np.abs(x - y).max(), scale)
+        compared += 1
+    return compared
+
+
+def test_phase_tables_product_vs_oracle():
+    """two independent set-ups of the same phase parameters (Schmid and non-Schmid projections, interaction matrices, forest
+    projections, twin systems, stiffness, law parameters): every workload phase of this repo, and -- in the build container --
+    every parameter set of the reference's examples that the device path offers"""
+    import glob
+    import yaml
+    from solver_cpp_b200 import workloads as W
+    for name, phase in W.PHASES.items():
+        assert _phase_tables_agree(phase) > 80, name
+    base = '/root/reference/examples/config/phase/mechanical/'
+    offered = {'dislotungsten_W': ('W', 'cI'), 'isotropic_free-surface': ('Al', 'cF'), 'kinehardening_317L': ('AISI304', 'cF'),
+               'phenopowerlaw_AA6022-T4': ('Al', 'cF'), 'phenopowerlaw_Al': ('Al', 'cF'), 'phenopowerlaw_Au': ('Au', 'cF'),
+               'phenopowerlaw_Cu': ('Cu', 'cF'), 'phenopowerlaw_Pt-5%Cu': ('Pt', 'cF')}
+    if not glob.glob(base + 'plastic/*.yaml'):
+        return
+    for name, (el, lat) in offered.items():
+        phase = {'lattice': lat, 'mechanical': {'elastic': yaml.safe_load(open(base + 'elastic/Hooke_%s.yaml' % el)),
+                                                'plastic': yaml.safe_load(open(base + 'plastic/%s.yaml' % name))}}
+        assert _phase_tables_agree(phase) > 80, name
