@@ -49,6 +49,11 @@ def parse_load(load_dict):
         for k in ('P', 'dot_P'):
             if k in mech:
                 step['stress'] = BoundaryCondition(*parse_bc(mech[k]), k)
+        if 'stress' not in step:
+            # upstream DAMASK_grid.f90: no stress entry = no component is stress controlled (mask all 'x'); the deformation must
+            # then prescribe all nine.  (Config::parse_load, config.cpp:309-311, throws here -- on the reference's own example
+            # decks examples/grid/shearXY.yaml and shearZX.yaml.)
+            step['stress'] = BoundaryCondition(np.zeros((3, 3)), np.ones((3, 3), bool), 'P')
         if 'R' in mech:
             from .crystal import qu2om
             step['R'] = qu2om(mech['R'])

@@ -102,7 +102,13 @@ extern "C" int dmk_load_from_yaml(const char* load_yaml_path, dmk_load_step* ste
           copy_name(st.stress_type, sizeof st.stress_type, name);
         }
       }
-      if (!st.stress_type[0]) fail("Stress specification required for each loadstep, not specified for loadstep at index " + std::to_string(k));
+      if (!st.stress_type[0]) {
+        // upstream DAMASK_grid.f90: no stress entry = no component is stress controlled (mask all 'x'); the deformation must then
+        // prescribe all nine (next check).  Config::parse_load (config.cpp:309-311) throws here -- on the reference's own example
+        // decks examples/grid/shearXY.yaml and shearZX.yaml
+        copy_name(st.stress_type, sizeof st.stress_type, "P");
+        for (int c = 0; c < 9; c++) { st.stress_mask[c] = 1; st.stress_values[c] = 0.0; }
+      }
       for (int c = 0; c < 9; c++)
         if (st.deformation_mask[c] == st.stress_mask[c]) fail("load step " + std::to_string(k) + ": each component must be controlled by exactly one of deformation and stress");
       st.estimate_rate = item->has("estimate_rate") ? (int)item->get("estimate_rate")->as_bool() : 1;      // config.h:92-95 defaults

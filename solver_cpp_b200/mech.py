@@ -44,8 +44,13 @@ def parse_load(load):
         for k in ('P', 'dot_P'):
             if k in mech:
                 step['stress'] = BoundaryCondition(*_parse_bc(mech[k]), k)
-        if 'deformation' not in step or 'stress' not in step:
-            raise L.DmkError('load step needs one of F/dot_F/L and one of P/dot_P')
+        if 'deformation' not in step:
+            raise L.DmkError('load step needs one of F / dot_F / L')
+        if 'stress' not in step:
+            # upstream DAMASK_grid.f90: no stress entry = no component is stress controlled (mask all 'x'); the deformation must then
+            # prescribe all nine (next check).  Config::parse_load (config.cpp:309-311) throws instead -- on the reference's own
+            # example decks examples/grid/shearXY.yaml and shearZX.yaml
+            step['stress'] = BoundaryCondition(np.zeros((3, 3)), np.ones((3, 3), bool), 'P')
         if np.any(step['deformation'].mask == step['stress'].mask):
             raise L.DmkError('each component must be controlled by exactly one of deformation and stress')
         if 'R' in mech:

@@ -512,3 +512,46 @@ def test_reference_16cubed_deck_solves_like_the_recorded_27_cell_run():
     assert np.abs(P11 / np.array([35.2362, 64.6648, 72.9485]) - 1.0).max() < 0.03
     for r in recs:                                                     # uniaxial stress state of tensionX
         assert abs(r['P_av'][1, 1]) < 1e-3 * r['P_av'][0, 0] and abs(r['P_av'][2, 2]) < 1e-3 * r['P_av'][0, 0]
+
+
+def test_fully_deformation_controlled_load_case_like_the_reference_shear_decks():
+    """examples/grid/shearXY.yaml of the reference: dot_F prescribes all nine components, no stress entry.  The masked compliance
+    of an all-'x' stress mask is zero (oracle and the library's host helper), F_aim follows the prescribed rate exactly, and the
+    solver converges on the equilibrium alone."""
+    import ctypes as C
+    from oracle.solver import MechSolverBasicOracle, run_loadcase, parse_load as oparse
+    from solver_cpp_b200 import workloads as W, lib as L
+    load = {'solver': {'mechanical': 'spectral_basic'},
+            'loadstep': [{'boundary_conditions': {'mechanical': {'dot_F': [[0, 0, 0], [1.0e-3, 0, 0], [0, 0, 0]]}},
+                          'discretization': {'t': 60, 'N': 120}, 'f_out': 20}]}
+    Cs = np.einsum('ik,jl->ijkl', np.eye(3), np.eye(3)) * 1.0e11
+    assert np.abs(sp.masked_compliance(Cs, np.eye(3), np.ones((3, 3), bool))).max() == 0.0
+    lib = L.load()
+    S, mask, R = np.ones(81), np.ones(9, dtype=np.int32), np.eye(3).reshape(9).copy()
+    Cf = np.ascontiguousarray(np.transpose(Cs, (3, 2, 1, 0))).reshape(-1)
+    P = lambda a: a.ctypes.data_as(C.c_void_p)
+    assert lib.dmk_masked_compliance(P(Cf), P(R), P(mask), P(S)) == 0 and np.abs(S).max() == 0.0
+    cells = (6, 6, 6)
+    material, material_at, size = W.polycrystal(cells, 6, 'Al_pheno', 0)
+    o = MechSolverBasicOracle(cells, size, material, material_at, tangent_every_eval=False)
+    o.log_fields = False
+    o.init()
+    recs = []
+
+    class Stop(Exception):
+        pass
+
+    def cb(rec, s):
+        recs.append(rec)
+        if len(recs) == 3:
+            raise Stop
+    try:
+        run_loadcase(o, oparse(load), callback=cb)
+    except Stop:
+        pass
+    assert [r['converged'] for r in recs] == [True] * 3
+    for k, r in enumerate(recs):
+        expect = np.eye(3); expect[1, 0] = 1.0e-3 * 0.5 * (k + 1)
+        assert np.abs(r['F_aim'] - expect).max() < 1e-18 and np.abs(r['F_av'] - expect).max() < 1e-15
+        assert o.err_BC == 0.0                                         # nothing is stress controlled
+    assert recs[2]['P_av'][1, 0] > recs[1]['P_av'][1, 0] > recs[0]['P_av'][1, 0] > 1.0e7
