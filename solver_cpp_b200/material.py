@@ -164,10 +164,17 @@ def _set(field, values):
 def make_phase(cfg, T=T_ROOM):
     """one `phase:` entry of material.yaml -> lib.Phase"""
     ph = L.Phase()
+    if not isinstance(cfg, dict):
+        raise L.DmkError('phase entry is empty')
+    for key in ('lattice', 'mechanical'):                       # the same refusals, in the same words, as csrc/init_dropin.cpp
+        if key not in cfg:
+            raise L.DmkError("missing key '%s'" % key)
     lattice = cfg['lattice']
     if lattice not in ('cF', 'cI'):
         raise L.DmkError('lattice %s is not offered on the device path (cF, cI)' % lattice)
     mech = cfg['mechanical']
+    if not isinstance(mech, dict) or 'elastic' not in mech:
+        raise L.DmkError("missing key 'elastic'")
     el = mech['elastic']
     if el.get('type', 'Hooke') != 'Hooke':
         raise L.DmkError('elastic type %s' % el.get('type'))
@@ -425,7 +432,15 @@ class Material:
     def __init__(self, material, material_at, T=T_ROOM):
         names = list(material['phase'].keys())
         self.phase_names = names
-        self.phases = (L.Phase * len(names))(*[make_phase(material['phase'][k], T) for k in names])
+        built = []
+        for k in names:
+            try:
+                built.append(make_phase(material['phase'][k], T))
+            except KeyError as e:                               # a parameter the law needs is not in the deck
+                raise L.DmkError('phase %s: missing key %s' % (k, e)) from None
+            except L.DmkError as e:
+                raise L.DmkError('phase %s: %s' % (k, e)) from None
+        self.phases = (L.Phase * len(names))(*built)
         mats = material['material']
         material_at = np.asarray(material_at).reshape(-1)
         used = np.unique(material_at)
