@@ -21,6 +21,7 @@
 #include <cstdio>
 #include <cstring>
 #include <fstream>
+#include <initializer_list>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -390,7 +391,8 @@ void read_numerics(const YamlNode& root, dmk_numerics& n, int* derivative, int* 
   if (const YamlNode* solver = root.get("solver")) if (const YamlNode* grid = solver->get("grid")) {
     if (const YamlNode* m = grid->get("mechanical")) {
       // a key the parser does not know must not be dropped silently (the Python host refuses it as well)
-      static const char* known[] = {"N_iter_min", "N_iter_max", "eps_abs_div(P)", "eps_rel_div(P)", "eps_abs_P", "eps_rel_P", "update_gamma"};
+      static const char* known[] = {"N_iter_min", "N_iter_max", "eps_abs_div(P)", "eps_rel_div(P)", "eps_abs_P", "eps_rel_P", "update_gamma",
+                                    "itmin", "itmax", "eps_abs_div", "eps_rel_div"};                 // + the struct's own names, as the Python host
       if (m->is_map()) for (const auto& kv : m->map) {
         bool ok = false;
         for (const char* k : known) ok = ok || kv.first == k;
@@ -403,6 +405,10 @@ void read_numerics(const YamlNode& root, dmk_numerics& n, int* derivative, int* 
       if (m->has("eps_abs_P")) n.eps_abs_P = m->get("eps_abs_P")->as_double();
       if (m->has("eps_rel_P")) n.eps_rel_P = m->get("eps_rel_P")->as_double();
       if (m->has("update_gamma")) n.update_gamma = m->get("update_gamma")->as_bool() ? 1 : 0;
+      if (m->has("itmin")) n.itmin = (int)m->get("itmin")->as_int();
+      if (m->has("itmax")) n.itmax = (int)m->get("itmax")->as_int();
+      if (m->has("eps_abs_div")) n.eps_abs_div = m->get("eps_abs_div")->as_double();
+      if (m->has("eps_rel_div")) n.eps_rel_div = m->get("eps_rel_div")->as_double();
     }
     if (const YamlNode* f = grid->get("FFT")) {
       if (f->has("derivative")) {
@@ -419,6 +425,19 @@ void read_numerics(const YamlNode& root, dmk_numerics& n, int* derivative, int* 
     }
   }
   if (const YamlNode* phase = root.get("phase")) if (const YamlNode* m = phase->get("mechanical")) {
+    // phase_mechanical.f90:277-294; keys the integrator does not know are refused (the Python host does the same); the Li keys of
+    // `eigen` are accepted and unused: no law with Li != 0 is offered on the device path
+    auto refuse_unknown = [](const YamlNode* node, std::initializer_list<const char*> known, const std::string& where) {
+      if (!node || !node->is_map()) return;
+      for (const auto& kv : node->map) {
+        bool ok = false;
+        for (const char* k : known) ok = ok || kv.first == k;
+        if (!ok) bad("numerics: unknown key '" + kv.first + "' under " + where);
+      }
+    };
+    refuse_unknown(m, {"r_cutback_min", "r_cutback", "r_increase", "eps_rel_state", "N_iter_state_max", "plastic", "eigen"}, "phase/mechanical");
+    refuse_unknown(m->get("plastic"), {"N_iter_Lp_max", "r_linesearch_Lp", "eps_rel_Lp", "eps_abs_Lp", "f_update_jacobi_Lp", "integrator_state"}, "phase/mechanical/plastic");
+    refuse_unknown(m->get("eigen"), {"N_iter_Li_max", "r_linesearch_Li", "eps_rel_Li", "eps_abs_Li", "f_update_jacobi_Li"}, "phase/mechanical/eigen");
     if (m->has("r_cutback_min")) n.r_cutback_min = m->get("r_cutback_min")->as_double();
     if (m->has("r_cutback")) n.r_cutback = m->get("r_cutback")->as_double();
     if (m->has("r_increase")) n.r_increase = m->get("r_increase")->as_double();

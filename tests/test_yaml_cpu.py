@@ -165,6 +165,17 @@ def test_cpp_numerics_equals_python_host(tmp_path):
     assert b"unknown key 'eps_div'" in lib.dmk_last_error()
     with pytest.raises(L.DmkError):
         job.read_numerics(str(p))
+    for deck in ({'phase': {'mechanical': {'plastic': {'N_iter_Lp': 3}}}}, {'phase': {'mechanical': {'eps_state': 1e-3}}},
+                 {'phase': {'mechanical': {'eigen': {'N_iter_Li': 3}}}}):
+        p.write_text(yaml.safe_dump(deck))
+        assert lib.dmk_numerics_from_yaml(str(p).encode(), C.byref(num), C.byref(der), C.byref(div)) != 0 and b'unknown key' in lib.dmk_last_error()
+        with pytest.raises(L.DmkError):
+            job.read_numerics(str(p))
+    # the struct's own names and the Li keys are accepted by both
+    p.write_text(yaml.safe_dump({'solver': {'grid': {'mechanical': {'itmin': 2, 'itmax': 50, 'eps_abs_div': 1e-3, 'eps_rel_div': 1e-2}}},
+                                 'phase': {'mechanical': {'eigen': {'N_iter_Li_max': 30}, 'eps_rel_state': 1e-5}}}))
+    assert lib.dmk_numerics_from_yaml(str(p).encode(), C.byref(num), C.byref(der), C.byref(div)) == 0, lib.dmk_last_error()
+    assert bytes(num) == bytes(job.read_numerics(str(p))[0]) and (num.itmin, num.itmax, num.eps_abs_div, num.eps_rel_state) == (2, 50, 1e-3, 1e-5)
     p.write_text(yaml.safe_dump({'solver': {'grid': {'N_staggered_iter_max': 7, 'FFT': {'alpha': 1.5, 'beta': 0.5, 'eps_abs_curl(F)': 1e-8, 'eps_rel_curl(F)': 1e-3}}}}))
     assert lib.dmk_grid_numerics_from_yaml(str(p).encode(), C.byref(gn)) == 0
     assert (gn.N_staggered_iter_max, gn.N_cutback_max, gn.alpha, gn.beta, gn.eps_abs_curl, gn.eps_rel_curl) == (7, 3, 1.5, 0.5, 1e-8, 1e-3)
