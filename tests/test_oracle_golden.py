@@ -555,3 +555,48 @@ def test_fully_deformation_controlled_load_case_like_the_reference_shear_decks()
         assert np.abs(r['F_aim'] - expect).max() < 1e-18 and np.abs(r['F_av'] - expect).max() < 1e-15
         assert o.err_BC == 0.0                                         # nothing is stress controlled
     assert recs[2]['P_av'][1, 0] > recs[1]['P_av'][1, 0] > recs[0]['P_av'][1, 0] > 1.0e7
+
+
+def _g8_job(golden_dir):
+    import yaml
+    g8 = np.load(os.path.join(golden_dir, 'g8_reference_run_2x2x2.npz'))
+    material = yaml.safe_load(str(g8['material_yaml']))
+    numerics = yaml.safe_load(str(g8['numerics_yaml']))['solver']['grid']['mechanical']
+    load = {'solver': {'mechanical': 'spectral_basic'},
+            'loadstep': [{'boundary_conditions': {'mechanical': {'dot_F': [[1.0e-3, 0, 0], [0, 'x', 0], [0, 0, 'x']],
+                                                                  'P': [['x', 'x', 'x'], ['x', 0, 'x'], ['x', 'x', 0]]}},
+                          'discretization': {'t': 10, 'N': 10}, 'f_out': 1}]}                # dt = t of the stored increment = 1 s
+    return g8, material, dict(itmin=int(numerics['N_iter_min']), itmax=int(numerics['N_iter_max'])), load
+
+
+def test_g8_result_file_of_the_reference_fork_itself(golden_dir):
+    """Golden set G8: increment 1 of a result file the reference's author wrote with the C++ fork (2 x 2 x 2 cells of one
+    cube-oriented Al crystal, tensionX, N_iter_min 4): a complete converged increment -- forward, four NGMRES iterations, stress BC --
+    in the reference's own output.  The oracle's free-running solve must land on it: F, F_e, F_p, xi_sl to rounding (3e-16),
+    P and L_p to 1e-11 (the zero-stress components are converged to 6e-5 Pa of 6e7 in both)."""
+    from oracle.solver import MechSolverBasicOracle, run_loadcase, parse_load as oparse
+    g8, material, num, load = _g8_job(golden_dir)
+    assert float(g8['t']) == 1.0 and 'alpha8' in str(g8['creator'])
+    for k in ('F', 'F_e', 'F_p', 'L_p', 'P', 'xi_sl'):
+        assert np.abs(g8[k] - g8[k][0]).max() == 0.0                    # homogeneous: all 8 cells alike
+    o = MechSolverBasicOracle((2, 2, 2), (1.0, 1.0, 1.0), material, np.zeros(8, dtype=int), grid_mech=num, tangent_every_eval=False)
+    o.log_fields = False
+    o.init()
+    recs = []
+
+    class Stop(Exception):
+        pass
+
+    def cb(rec, s):
+        recs.append(rec)
+        raise Stop
+    try:
+        run_loadcase(o, oparse(load), callback=cb)
+    except Stop:
+        pass
+    assert recs[0]['converged'] and recs[0]['iterations'] == 4 and recs[0]['t'] == float(g8['t'])
+    got = {'F': o.con.a['F'], 'F_e': o.con.a['Fe'], 'F_p': o.con.a['Fp'], 'L_p': o.con.a['Lp'], 'P': o.con.a['P'], 'xi_sl': o.con.a['state'][:, :12]}
+    for k, tol in (('F', 3e-16), ('F_e', 3e-16), ('F_p', 3e-16), ('xi_sl', 3e-16), ('P', 1e-11), ('L_p', 1e-11)):
+        ref = g8[k].reshape(8, -1)
+        assert np.abs(got[k].reshape(8, -1) - ref).max() <= tol * np.abs(ref).max(), (k, np.abs(got[k].reshape(8, -1) - ref).max() / np.abs(ref).max())
+    assert abs(o.con.a['F'][0, 4] - 0.9996331955299964) < 2e-16            # the lateral contraction the stress BC found
