@@ -600,3 +600,20 @@ def test_g8_result_file_of_the_reference_fork_itself(golden_dir):
         ref = g8[k].reshape(8, -1)
         assert np.abs(got[k].reshape(8, -1) - ref).max() <= tol * np.abs(ref).max(), (k, np.abs(got[k].reshape(8, -1) - ref).max() / np.abs(ref).max())
     assert abs(o.con.a['F'][0, 4] - 0.9996331955299964) < 2e-16            # the lateral contraction the stress BC found
+
+
+def test_g8_first_evaluation_known_answer_of_the_fortran_log(golden_dir):
+    """The same 2 x 2 x 2 job, first residual evaluation, as the Fortran side printed it (test.patch at the root of the reference
+    tree, the author's diff of the Fortran and the C++ run logs; lines 706-746): F = diag(1.001, 1, 1), dt = 1 s, virgin cube-oriented
+    Al -> per point F_e11 = 1.0009998313594122, S11 = 106795532.01732938, S22 = 60444088.135403559 and the homogenised
+    P11 = 106902291.52922715, P22 = 60444098.318547405.  17 printed digits: the oracle must reproduce every one."""
+    import yaml
+    g8 = np.load(os.path.join(golden_dir, 'g8_reference_run_2x2x2.npz'))
+    o = ConstitutiveOracle(yaml.safe_load(str(g8['material_yaml'])), np.zeros(8, dtype=int))
+    o.mechanical_response(np.tile(np.diag([1.001, 1.0, 1.0]).reshape(9), (8, 1)), 1.0)
+    P, _ = o.mechanical_response2(1.0, tangent=False)
+    assert np.abs(P - P[0]).max() == 0.0                                                   # homogeneous: every cell alike
+    assert P[0, 0, 0] == 106902291.52922715 and P[0, 1, 1] == 60444098.318547405          # the same doubles as the log's P_av2
+    assert o.a['Fe'][0, 0] == 1.0009998313594122 and abs(o.a['Fe'][0, 4] - 1.0000000842360579) <= 2.3e-16
+    S = o.a['S'][0].reshape(3, 3)
+    assert S[0, 0] == 106795532.01732938 and abs(S[1, 1] - 60444088.135403559) <= 1.5e-8
