@@ -596,6 +596,18 @@ extern "C" int dmk_numerics_from_yaml(const char* numerics_yaml_path, dmk_numeri
     default_numerics(*num);
     int der = DMK_DERIVATIVE_CONTINUOUS, div = DMK_DIVCORR_SIZE_GRID;
     if (numerics_yaml_path && *numerics_yaml_path) read_numerics(*yaml_parse_file(numerics_yaml_path), *num, &der, &div);
+    // the range checks of upstream DAMASK (grid_mechanical_spectral_basic_init, IO_error 301; phase_mechanical.f90:296-309), in the
+    // Python host's order; Config::parse_numerics does not check
+    std::string wrong;
+    auto flag = [&](bool is_wrong, const char* name) { if (is_wrong) wrong += std::string(wrong.empty() ? "" : ", ") + name; };
+    const dmk_numerics& n = *num;
+    flag(!(n.eps_abs_div > 0.0), "eps_abs_div"); flag(!(n.eps_rel_div > 0.0), "eps_rel_div"); flag(!(n.eps_abs_P > 0.0), "eps_abs_P");
+    flag(!(n.eps_rel_P > 0.0), "eps_rel_P"); flag(!(n.r_cutback_min > 0.0), "r_cutback_min"); flag(!(n.r_cutback > 0.0), "r_cutback");
+    flag(!(n.r_increase > 0.0), "r_increase"); flag(!(n.eps_rel_state > 0.0), "eps_rel_state"); flag(!(n.r_linesearch_Lp > 0.0), "r_linesearch_Lp");
+    flag(!(n.eps_rel_Lp > 0.0), "eps_rel_Lp"); flag(!(n.eps_abs_Lp > 0.0), "eps_abs_Lp");
+    flag(n.N_iter_state_max < 1, "N_iter_state_max"); flag(n.N_iter_Lp_max < 1, "N_iter_Lp_max"); flag(n.f_update_jacobi_Lp < 1, "f_update_jacobi_Lp");
+    flag(n.itmax <= 1, "N_iter_max"); flag(n.itmin > n.itmax || n.itmin < 1, "N_iter_min");
+    if (!wrong.empty()) bad("numerics: value out of range: " + wrong);
     if (derivative) *derivative = der;
     if (divergence_correction) *divergence_correction = div;
     return DMK_OK;

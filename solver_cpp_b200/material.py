@@ -416,6 +416,17 @@ def make_numerics(phase_mech=None, grid_mech=None):
             raise L.DmkError('numerics: unknown key %r under solver/grid/mechanical (known: %s)' % (k, ', '.join(sorted(ren))))
         k = ren[k]
         d[k] = int(v) if k in ('itmin', 'itmax', 'update_gamma') else float(v)
+    # the range checks of upstream DAMASK (grid_mechanical_spectral_basic_init, IO_error 301; phase_mechanical.f90:296-309):
+    # Config::parse_numerics does not check, the values would be used as they come
+    wrong = [k for k in ('eps_abs_div', 'eps_rel_div', 'eps_abs_P', 'eps_rel_P', 'r_cutback_min', 'r_cutback', 'r_increase',
+                         'eps_rel_state', 'r_linesearch_Lp', 'eps_rel_Lp', 'eps_abs_Lp') if not float(d[k]) > 0.0]
+    wrong += [k for k in ('N_iter_state_max', 'N_iter_Lp_max', 'f_update_jacobi_Lp') if int(d[k]) < 1]
+    if int(d['itmax']) <= 1:
+        wrong.append('N_iter_max')
+    if int(d['itmin']) > int(d['itmax']) or int(d['itmin']) < 1:
+        wrong.append('N_iter_min')
+    if wrong:
+        raise L.DmkError('numerics: value out of range: ' + ', '.join(wrong))
     n = L.Numerics()
     for k, v in d.items():
         setattr(n, k, v)

@@ -171,6 +171,14 @@ def test_cpp_numerics_equals_python_host(tmp_path):
         assert lib.dmk_numerics_from_yaml(str(p).encode(), C.byref(num), C.byref(der), C.byref(div)) != 0 and b'unknown key' in lib.dmk_last_error()
         with pytest.raises(L.DmkError):
             job.read_numerics(str(p))
+    # values out of range are refused by both, with the same list (upstream's IO_error 301; Config::parse_numerics does not check)
+    p.write_text(yaml.safe_dump({'solver': {'grid': {'mechanical': {'N_iter_min': 5, 'N_iter_max': 3, 'eps_rel_P': 0.0}}},
+                                 'phase': {'mechanical': {'r_cutback': -0.5, 'plastic': {'N_iter_Lp_max': 0}}}}))
+    assert lib.dmk_numerics_from_yaml(str(p).encode(), C.byref(num), C.byref(der), C.byref(div)) != 0
+    cpp = lib.dmk_last_error().decode()
+    with pytest.raises(L.DmkError) as err:
+        job.read_numerics(str(p))
+    assert cpp == 'numerics: value out of range: eps_rel_P, r_cutback, N_iter_Lp_max, N_iter_min' and cpp in str(err.value)
     # the struct's own names and the Li keys are accepted by both
     p.write_text(yaml.safe_dump({'solver': {'grid': {'mechanical': {'itmin': 2, 'itmax': 50, 'eps_abs_div': 1e-3, 'eps_rel_div': 1e-2}}},
                                  'phase': {'mechanical': {'eigen': {'N_iter_Li_max': 30}, 'eps_rel_state': 1e-5}}}))
