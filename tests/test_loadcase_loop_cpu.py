@@ -279,3 +279,21 @@ def test_example_load_decks_of_the_reference_through_all_parsers():
             assert (c.t, c.N, c.f_out) == (side['t'], side['N'], side['f_out'])
         if 'shear' in f:
             assert p['stress'].mask.all() and (c.t, c.N, c.f_out) == (60.0, 120, 20)
+
+
+def test_cpp_loop_geometric_time_steps_equal_python_loop(tmp_path):
+    """discretization with r != 1 (config.h:80: geometric series of time steps, damask_grid.cpp:95-101) incl. a cut-back"""
+    load = {'loadstep': [{'boundary_conditions': LOAD['loadstep'][0]['boundary_conditions'], 'discretization': {'t': 7.0, 'N': 5, 'r': 1.7}, 'f_out': 2},
+                         {'boundary_conditions': LOAD['loadstep'][1]['boundary_conditions'], 'discretization': {'t': 2.0, 'N': 3, 'r': 0.5}}]}
+    steps, n_steps, _ = _c_steps(load, tmp_path)
+    outcomes = [True, True, False, True, True]
+    s = _Scripted(outcomes)
+    recs = mech.loop_over_loadcase(s, mech.parse_load(load))
+    rc, crecs, calls, forwards, _ = _run_cpp_loop(outcomes, steps, n_steps)
+    assert rc == 0 and len(crecs) == len(recs) == 8
+    assert [r.t for r in crecs] == [r['t'] for r in recs] and abs(recs[4]['t'] - 7.0) < 1e-14 and abs(recs[-1]['t'] - 9.0) < 1e-14
+    assert [(c['dt'], c['dt_prev'], c['t_remaining'], c['cut_back'], c['guess']) for c in calls] == \
+           [(c['dt'], c['dt_prev'], c['t_remaining'], c['cut_back'], c['guess']) for c in s.calls]
+    dts = [c['dt'] for c in s.calls[:2]]
+    assert abs(dts[1] / dts[0] - 1.0 / 1.7) < 1e-15 or abs(dts[1] / dts[0] - 1.7) < 1e-15      # a geometric series
+    assert forwards == s.g.forwards
