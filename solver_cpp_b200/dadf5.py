@@ -269,7 +269,9 @@ class ResultReader:
         n_cells = m.shape[0]
         m = m.reshape(-1)
         # flat (cell, constituent) order; with one constituent per cell simply the cells
-        self.phase_label = np.array([l.split(b'\0')[0].decode() for l in m['label']], dtype=object)
+        # labels are fixed-length strings: padded with NULs (libhdf5's C default, this repo's writer) or with spaces (Fortran's
+        # character arrays, DAMASK 3.0.0-alpha7-880 and later); libhdf5 strips either on conversion to a memory type
+        self.phase_label = np.array([l.split(b'\0')[0].decode().rstrip(' ') for l in m['label']], dtype=object)
         self.phase_entry = m['entry'].astype(np.int64)
         self.n_cells = n_cells
         self.phases = sorted(set(self.phase_label))

@@ -385,3 +385,25 @@ def test_reader_places_constituents_like_damask_own_python_library():
     for inc in r.increments:
         for name in ('u_p', 'u_n'):
             assert np.abs(r.geometry(name, inc) - ref['increment_%d' % inc]['geometry'][name]).max() <= 1e-10
+
+
+def test_reader_strips_space_padded_labels_of_newer_damask_files(tmp_path):
+    """DAMASK 3.0.0-alpha7-880 and later write the (label, entry) mappings from Fortran character arrays: labels of unequal length
+    are padded with SPACES (the older files, and this repo's writer, pad with NULs).  libhdf5 strips either; so must the reader --
+    found on the reference's 2phase_irregularGrid result file ('Matrix     ' next to 'Precipitate'), here on a file with hand-padded
+    labels."""
+    from solver_cpp_b200.hdf5_min import H5Writer
+    w = H5Writer()
+    w.group('/', DADF5_version_major=np.int32(1), DADF5_version_minor=np.int32(0))
+    w.group('/geometry', cells=np.array([2, 1, 1], np.int32), size=np.ones(3), origin=np.zeros(3))
+    m = np.zeros((2, 1), dtype=[('label', 'S11'), ('entry', '<i8')])
+    m['label'][0, 0] = b'Matrix     '; m['label'][1, 0] = b'Precipitate'
+    w.dataset('/cell_to/phase', m)
+    w.group('/increment_3', **{'t/s': 1.5})
+    w.dataset('/increment_3/phase/Matrix/mechanical/F', np.full((1, 3, 3), 1.0))
+    w.dataset('/increment_3/phase/Precipitate/mechanical/F', np.full((1, 3, 3), 2.0))
+    path = str(tmp_path / 'padded.hdf5')
+    w.save(path)
+    r = dadf5.ResultReader(path)
+    assert r.phases == ['Matrix', 'Precipitate']
+    assert np.array_equal(r.place('F', 3)[:, 0, 0], [1.0, 2.0])

@@ -617,3 +617,37 @@ def test_g8_first_evaluation_known_answer_of_the_fortran_log(golden_dir):
     assert o.a['Fe'][0, 0] == 1.0009998313594122 and abs(o.a['Fe'][0, 4] - 1.0000000842360579) <= 2.3e-16
     S = o.a['S'][0].reshape(3, 3)
     assert S[0, 0] == 106795532.01732938 and abs(S[1, 1] - 60444088.135403559) <= 1.5e-8
+
+
+def test_g9_third_real_damask_run_on_an_odd_two_phase_grid(golden_dir):
+    """Golden set G9: python/tests/resources/Result/2phase_irregularGrid_tensionX_*.hdf5 of the reference (DAMASK_grid
+    3.0.0-alpha7-880; 13 x 8 x 10 cells: an odd, non-power-of-two grid; 18 grains of an fcc phenopowerlaw matrix and an ELASTIC bcc
+    precipitate; tensionX, 40 increments of 0.25 s; inputs from the result file's own /setup group, tests/golden/make_golden_g9.py).
+    Two converged solves agree to the solver's tolerances (eps_rel_div 5e-4, eps_rel_P 1e-3): per-cell F to 1e-4, P to 3e-4 of
+    max|P|, homogenised P to 1e-4, the matrix's final slip resistances to 2e-4 (observed 4.6e-5, 1e-4, 1.8e-5, 6.5e-5)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location('dmk_vti', os.path.join(golden_dir, '..', '..', 'solver_cpp_b200', 'vti.py'))
+    vti = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(vti)
+    g9 = np.load(os.path.join(golden_dir, 'g9_damask_run_irregular.npz'))
+    geo = vti.read_vti(os.path.join(golden_dir, 'g9_irregular.vti'))
+    assert tuple(int(c) for c in geo['cells']) == (13, 8, 10) and 'DAMASK_grid' in str(g9['creator'])
+    mat = yaml.safe_load(open(os.path.join(golden_dir, 'g9_irregular.material.yaml')))
+    load = yaml.safe_load(open(os.path.join(golden_dir, 'g9_irregular.load.yaml')))
+    assert mat['phase']['Precipitate']['lattice'] == 'cI' and 'plastic' not in mat['phase']['Precipitate']['mechanical']
+    o = MechSolverBasicOracle(tuple(int(c) for c in geo['cells']), tuple(geo['size']), mat, geo['material'].reshape(-1), tangent_every_eval=False)
+    o.log_fields = False
+    o.init()
+    recs = run_loadcase(o, parse_load(load))
+    assert len(recs) == 40 and all(r['converged'] for r in recs) and abs(recs[-1]['t'] - float(g9['t'])) < 1e-12
+    F, P = o.F.reshape(-1, 3, 3), o.con.a['P'].reshape(-1, 3, 3)
+    assert np.abs(F - g9['F']).max() < 1e-4
+    assert np.abs(P - g9['P']).max() < 3e-4 * np.abs(g9['P']).max()
+    assert np.abs(P.mean(0) - g9['P'].mean(0)).max() < 1e-4 * np.abs(g9['P'].mean(0)).max()
+    matrix = g9['phase_of_cell'] == 'Matrix'
+    assert 0 < matrix.sum() < matrix.size and np.isnan(g9['xi_sl'][~matrix]).all()          # the precipitate carries no slip resistance
+    assert np.abs(o.con.a['state'][matrix, :12] - g9['xi_sl'][matrix]).max() < 2e-4 * g9['xi_sl'][matrix].max()
+    dFav = np.abs(F.mean(0) - g9['F'].mean(0))
+    free = np.zeros((3, 3), bool)
+    free[1, 1] = free[2, 2] = True                                         # stress-controlled components of the average
+    assert dFav[~free].max() < 1e-12 and dFav[free].max() < 1e-6
