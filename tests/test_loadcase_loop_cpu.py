@@ -297,3 +297,25 @@ def test_cpp_loop_geometric_time_steps_equal_python_loop(tmp_path):
     dts = [c['dt'] for c in s.calls[:2]]
     assert abs(dts[1] / dts[0] - 1.0 / 1.7) < 1e-15 or abs(dts[1] / dts[0] - 1.7) < 1e-15      # a geometric series
     assert forwards == s.g.forwards
+
+
+@pytest.mark.parametrize('deck', ['load_tensionX.yaml', '6grains6x7x8_tensionY.load.yaml', 'g9_irregular.load.yaml'])
+def test_cpp_load_reader_on_the_golden_decks(deck, golden_dir):
+    """the load files of the golden runs (G1's tensionX, G4's tensionY, G9's tensionX) through the C++ reader and the Python host"""
+    import ctypes as C
+    import os
+    import yaml
+    path = os.path.join(golden_dir, deck)
+    ref = mech.parse_load(yaml.safe_load(open(path)))
+    lib = L.load()
+    steps = (L.LoadStep * 4)()
+    n = C.c_int()
+    assert lib.dmk_load_from_yaml(path.encode(), steps, C.c_int(4), C.byref(n), None, C.c_int(0)) == 0, lib.dmk_last_error()
+    assert n.value == len(ref)
+    for c, p in zip(steps, ref):
+        assert np.array_equal(np.array(c.deformation_values).reshape(3, 3), p['deformation'].values)
+        assert np.array_equal(np.array(c.deformation_mask).reshape(3, 3).astype(bool), p['deformation'].mask.astype(bool))
+        assert np.array_equal(np.array(c.stress_values).reshape(3, 3), p['stress'].values)
+        assert np.array_equal(np.array(c.stress_mask).reshape(3, 3).astype(bool), p['stress'].mask.astype(bool))
+        assert (c.deformation_type.decode(), c.stress_type.decode(), c.t, c.N, c.r, c.f_out) == \
+               (p['deformation'].type, p['stress'].type, p['t'], p['N'], p['r'], p['f_out'])
