@@ -112,11 +112,11 @@ def test_cpp_material_setup_equals_python_host(tmp_path, golden_dir):
         p = tmp_path / ('material_%s.yaml' % phase)
         p.write_text(yaml.safe_dump(material))
         decks.append((str(p), material))
-    for name in ('material_20grains_Al.yaml', '12grains6x7x8.material.yaml', '6grains6x7x8_single_phase_tensionY.material.yaml'):
+    for name in ('material_20grains_Al.yaml', '12grains6x7x8.material.yaml', '6grains6x7x8_single_phase.material.yaml', 'g9_irregular.material.yaml'):
         f = os.path.join(golden_dir, name)
         if os.path.exists(f):
             decks.append((f, yaml.safe_load(open(f))))
-    assert len(decks) >= 9
+    assert len(decks) >= 11
     for path, material in decks:
         n_mat = len(material['material'])
         phases = (L.Phase * L.MAX_PHASES)()
