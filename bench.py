@@ -157,8 +157,23 @@ def cpu_solve(config, cells, K, threads):
     evals = len(o.log)
     o.log = []
     n = float(np.prod(cells))
+    # the per-point update alone, on the last iterate of the solve, with all threads and with one: the reference's own cell loop is
+    # serial per MPI rank (homogenization.f90:233; upstream's OpenMP directive was dropped in the fork), SURVEY 8(d)
+    per_point = {}
+    try:
+        snap = o.con.snapshot()
+        for label, th in (('all_threads', 0), ('one_thread', 1)):
+            o.con.set_threads(th)
+            tc = time.perf_counter()
+            o.con.mechanical_response(o.F.reshape(-1, 9), o.params['dt'])
+            per_point[label] = n / (time.perf_counter() - tc)
+            o.con.restore(snap)
+        o.con.set_threads(0)
+    except Exception as e:                                  # a reported extra, never a reason to lose the line
+        per_point = {'error': str(e)[:100]}
     return dict(value=n * evals / wall, wall_s=wall, evaluations=evals, iterations=[r['iterations'] for r in recs],
-                evaluations_cumulative=[r['evaluations'] for r in recs], P11=[r['P11'] for r in recs])
+                evaluations_cumulative=[r['evaluations'] for r in recs], P11=[r['P11'] for r in recs],
+                per_point_update_cells_per_s=per_point)
 
 
 def cpu_evaluations(cells, steps, warmup, threads):
@@ -238,7 +253,8 @@ def run_reference(args):
                            'warmup_note': 'none: a solve from the virgin state is not repeatable without re-initialisation; the CPU arm has no clocks or caches to warm'},
                 'ngmres_iterations': r['iterations'], 'evaluations': r['evaluations'],
                 'newton_iters_per_s': sum(r['iterations']) / r['wall_s'],
-                'cpu_baseline': {'value': r['value'], 'unit': 'cells*evaluations/s', 'cores': threads, 'kind': 'port', 'sample': desc},
+                'cpu_baseline': {'value': r['value'], 'unit': 'cells*evaluations/s', 'cores': threads, 'kind': 'port', 'sample': desc,
+                                 'per_point_update_cells_per_s': r['per_point_update_cells_per_s']},
                 'e2e': {'value': r['value'], 'unit': 'cells*evaluations/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
                 'note': note}
     else:
@@ -528,7 +544,8 @@ def run_solve(args):
         r = cpu_solve(args.config, sample, min(K, 3), threads)
         line['cpu_baseline'] = {'value': r['value'], 'unit': 'cells*evaluations/s', 'cores': threads, 'kind': 'port',
                                 'sample': '%dx%dx%d sub-problem of the same workload, same protocol (first %d increments solved): %d evaluations, '
-                                          'NGMRES iterations %s, %.1f s' % (sample + (min(K, 3), r['evaluations'], r['iterations'], r['wall_s']))}
+                                          'NGMRES iterations %s, %.1f s' % (sample + (min(K, 3), r['evaluations'], r['iterations'], r['wall_s'])),
+                                'per_point_update_cells_per_s': r['per_point_update_cells_per_s']}
     emit(line)
     if world > 1:
         dist.destroy_process_group()

@@ -987,6 +987,18 @@ void orc_set_point_log(int *buf) { g_point_cutbacks = buf; }
 static int *g_point_lp_iter = NULL;
 void orc_set_point_lp_log(int *buf) { g_point_lp_iter = buf; }
 
+/* threads of the cell loops below (the reference's own loop is serial per MPI rank, homogenization.f90:233; upstream DAMASK's is
+ * an OpenMP loop): 0 or less = the OpenMP default.  Used by bench.py's CPU arm to report a 1-thread figure next to the all-core one */
+#ifdef _OPENMP
+#include <omp.h>
+static int g_omp_default = 0;
+void orc_set_threads(int n) { if (!g_omp_default) g_omp_default = omp_get_max_threads(); omp_set_num_threads(n > 0 ? n : g_omp_default); }
+int orc_get_threads(void) { return omp_get_max_threads(); }
+#else
+void orc_set_threads(int n) { (void)n; }
+int orc_get_threads(void) { return 1; }
+#endif
+
 int orc_mechanical_response(const orc_phase_t *phases, const orc_num_t *num, orc_points_t *st, const double *F_in,
                             double Dt, int cell_start, int cell_end, long *counters) {
   int ill = 0;

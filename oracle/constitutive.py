@@ -400,6 +400,11 @@ class ConstitutiveOracle:
         m = self.n_cells
         return P.reshape(m, 3, 3), (dPdF.reshape(m, 3, 3, 3, 3) if tangent else None)
 
+    def set_threads(self, n):
+        """OpenMP threads of the cell loops (0: the default); -> the number now in effect"""
+        self.lib.orc_set_threads(C.c_int(int(n)))
+        return int(self.lib.orc_get_threads())
+
     # f_materialpoint_forward
     def forward(self):
         self.lib.orc_forward(self.phases, C.byref(self.st))
